@@ -1,0 +1,144 @@
+/*
+ * clusten_b200.h -- C ABI of libclusten_b200.so: the B200 (sm_100a) implementation of
+ * AutoFocusFormer's CLUSTEN neighbourhood-attention hot path.
+ *
+ * Every entry point replaces one piece of the reference's native / library interface
+ * (Eiphodos/autofocusformerMod; paths relative to mask2former/modeling/):
+ *
+ *   clusten_qk_fwd / clusten_qk_bwd   <- clusten/src/clustenqk_cuda.cpp:25-45  (pybind forward/backward, :48-51)
+ *   clusten_av_fwd / clusten_av_bwd   <- clusten/src/clustenav_cuda.cpp:25-45
+ *   clusten_wf_fwd / clusten_wf_bwd   <- clusten/src/clustenwf_cuda.cpp:25-45
+ *   clusten_wg_fwd / clusten_wg_bwd   <- clusten/src/weighted_gather_cuda.cpp:25-45
+ *   clusten_csr_*                     <- replaces the fastAtomicAdd scatter of the reference backward kernels
+ *                                        (clustenqk_cuda_kernel.cu:125, clustenav_cuda_kernel.cu:121,
+ *                                         clustenwf_cuda_kernel.cu:129, weighted_gather_cuda_kernel.cu:115)
+ *   clusten_knn                       <- backbone/point_utils.py:28-60 (knn_keops; pykeops argKmin / Kmin_argKmin)
+ *   clusten_sfc_cluster               <- backbone/point_utils.py:135-287 (space_filling_cluster, default branch)
+ *   clusten_topk_select, clusten_mask_select <- backbone/aff.py:320,323 (topk(sorted=False), nonzero)
+ *
+ * Conventions
+ *   - Plain C: raw DEVICE pointers, sizes, element strides, a CUDA stream handle (cudaStream_t passed as void*).
+ *     No torch types.  All calls are asynchronous on `stream`; none synchronises the host.
+ *   - Return value: 0 = ok; > 0 = cudaError_t of the failing launch; < 0 = CLUSTEN_E* argument error.
+ *     clusten_last_error() returns a thread-local message for the last non-zero return.
+ *   - dtype: CLUSTEN_F32 / CLUSTEN_F16 / CLUSTEN_BF16 for all floating tensors of a call; accumulation is fp32.
+ *   - "rows" tensors (q, k, v, feat, and their gradients) are addressed as
+ *         base + b*sb + h*sh + n*sn + c      (strides in ELEMENTS, innermost stride must be 1)
+ *     so the non-contiguous [B,N,H,C] -> [B,H,N,C] views the reference model produces (aff.py:111-113) are
+ *     consumed and produced without the .contiguous() copies of clusten.py:25-33.
+ *   - neighbour index tensors are int64 [B, Nq, M] contiguous, exactly what the reference passes
+ *     (clusten.py:29); values must lie in [0, Nk) (unchecked, as in the reference).
+ *   - Outputs are fully overwritten (callers may allocate them uninitialised).
+ */
+#ifndef CLUSTEN_B200_H
+#define CLUSTEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLUSTEN_ABI_VERSION 1
+
+enum { CLUSTEN_F32 = 0, CLUSTEN_F16 = 1, CLUSTEN_BF16 = 2 };
+
+enum {
+    CLUSTEN_EINVAL = -1,      /* bad size / null pointer */
+    CLUSTEN_EDTYPE = -2,      /* unknown dtype */
+    CLUSTEN_EUNSUPPORTED = -3,/* shape outside the supported range (message says which) */
+    CLUSTEN_EWORKSPACE = -4   /* workspace too small */
+};
+
+int clusten_abi_version(void);
+const char *clusten_last_error(void);
+
+/* ---- inverse neighbour list (CSR over key rows), built once per index tensor and reused by every backward ----
+ * offsets: int32 [B, Nk+1]; entries: uint32 [B, Nq*M], entry = (i << 8) | j  (query i, slot j), ascending per row.
+ * Requires M <= 256 and Nq < 2^24.  Deterministic (stable radix sort, no atomics on the data path). */
+size_t clusten_csr_workspace_bytes(int B, int Nq, int M, int Nk);
+int clusten_csr_build(const int64_t *nbhd_idx, int B, int Nq, int M, int Nk,
+                      int32_t *offsets, uint32_t *entries, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- QK: attn[b,h,i,j] = sum_c q[b,h,i,c] * k[b,h,idx[b,i,j],c]            (clustenqk_cuda_kernel.cu:38-45) */
+int clusten_qk_fwd(const void *q, const void *k, const int64_t *nbhd_idx, void *attn /* [B,H,Nq,M] contiguous */,
+                   int B, int H, int Nq, int Nk, int C, int M,
+                   int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t k_sb, int64_t k_sh, int64_t k_sn,
+                   int dtype, void *stream);
+/* d_q[b,h,i,:] = sum_j d_attn[b,h,i,j] k[b,h,idx,:];  d_k[b,h,r,:] = sum_{(i,j): idx[b,i,j]=r} d_attn[b,h,i,j] q[b,h,i,:]
+ *                                                                        (clustenqk_cuda_kernel.cu:118-128) */
+int clusten_qk_bwd(const void *d_attn /* [B,H,Nq,M] contiguous */, const void *q, const void *k,
+                   const int64_t *nbhd_idx, const int32_t *csr_offsets, const uint32_t *csr_entries,
+                   void *d_q, void *d_k,
+                   int B, int H, int Nq, int Nk, int C, int M,
+                   int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t k_sb, int64_t k_sh, int64_t k_sn,
+                   int64_t dq_sb, int64_t dq_sh, int64_t dq_sn, int64_t dk_sb, int64_t dk_sh, int64_t dk_sn,
+                   int dtype, void *stream);
+
+/* ---- AV: feat[b,h,i,c] = sum_j attn[b,h,i,j] * v[b,h,idx[b,i,j],c]          (clustenav_cuda_kernel.cu:40-46)
+ * attn is addressed base + b*a_sb + h*a_sh + i*a_sn + j (so the attn[..., :-1] slice of aff.py:146 needs no copy). */
+int clusten_av_fwd(const void *attn, const void *v, const int64_t *nbhd_idx, void *feat,
+                   int B, int H, int Nq, int Nk, int C, int M,
+                   int64_t a_sb, int64_t a_sh, int64_t a_sn, int64_t v_sb, int64_t v_sh, int64_t v_sn,
+                   int64_t f_sb, int64_t f_sh, int64_t f_sn, int dtype, void *stream);
+/* d_attn[b,h,i,j] = sum_c v[b,h,idx,c] d_feat[b,h,i,c];  d_v[b,h,r,:] = sum_{(i,j)->r} attn[b,h,i,j] d_feat[b,h,i,:]
+ *                                                                 (clustenav_cuda_kernel.cu:117-123,152-156) */
+int clusten_av_bwd(const void *d_feat, const void *attn, const void *v,
+                   const int64_t *nbhd_idx, const int32_t *csr_offsets, const uint32_t *csr_entries,
+                   void *d_attn /* [B,H,Nq,M] contiguous */, void *d_v,
+                   int B, int H, int Nq, int Nk, int C, int M,
+                   int64_t df_sb, int64_t df_sh, int64_t df_sn, int64_t a_sb, int64_t a_sh, int64_t a_sn,
+                   int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t dv_sb, int64_t dv_sh, int64_t dv_sn,
+                   int dtype, void *stream);
+
+/* ---- WF: out[b,i,ic,c] = sum_j w[b,i,j,ic] * f[b,idx[b,i,j],c]             (clustenwf_cuda_kernel.cu:41-49)
+ * w [B,Nq,M,IC] contiguous, f rows base + b*f_sb + n*f_sn + c, out [B,Nq,IC,C] contiguous.  IC in {1,2,4,8}. */
+int clusten_wf_fwd(const void *w, const void *f, const int64_t *nbhd_idx, void *out,
+                   int B, int Nq, int Nk, int C, int M, int IC, int64_t f_sb, int64_t f_sn, int dtype, void *stream);
+/* d_w[b,i,j,ic] = sum_c f[b,idx,c] d_out[b,i,ic,c];  d_f[b,r,:] = sum_{(i,j)->r} sum_ic w[b,i,j,ic] d_out[b,i,ic,:]
+ *                                                                 (clustenwf_cuda_kernel.cu:120-131,161-165) */
+int clusten_wf_bwd(const void *d_out, const void *w, const void *f,
+                   const int64_t *nbhd_idx, const int32_t *csr_offsets, const uint32_t *csr_entries,
+                   void *d_w, void *d_f,
+                   int B, int Nq, int Nk, int C, int M, int IC, int64_t f_sb, int64_t f_sn,
+                   int64_t df_sb, int64_t df_sn, int dtype, void *stream);
+
+/* ---- WEIGHTEDGATHER: out[b,i,c] = sum_k w[b,i,k] * f[b,idx[b,i,k],c]   (weighted_gather_cuda_kernel.cu:38-45);
+ * argument order follows the reference (idx, weights, feat).  Same kernels as WF with IC = 1. */
+int clusten_wg_fwd(const int64_t *nbhd_idx, const void *w, const void *f, void *out,
+                   int B, int Nq, int Nk, int C, int K, int64_t f_sb, int64_t f_sn, int dtype, void *stream);
+int clusten_wg_bwd(const void *d_out, const int64_t *nbhd_idx, const void *w, const void *f,
+                   const int32_t *csr_offsets, const uint32_t *csr_entries, void *d_w, void *d_f,
+                   int B, int Nq, int Nk, int C, int K, int64_t f_sb, int64_t f_sn,
+                   int64_t df_sb, int64_t df_sn, int dtype, void *stream);
+
+/* ---- kNN (2-D, fp32): the k nearest database points of each query, ascending distance, ties -> lowest index;
+ * dist = sqrt_rn(fl(dx*dx) + fl(dy*dy)) without FMA contraction.  idx_out int64 [B,Nq,k]; dist_out fp32 [B,Nq,k] or NULL.
+ * 1 <= k <= 16, k <= Ndb.                                                    (point_utils.py:41-60) */
+int clusten_knn(const float *query /* [B,Nq,2] */, const float *database /* [B,Ndb,2] */,
+                int B, int Nq, int Ndb, int k, int64_t *idx_out, float *dist_out, void *stream);
+
+/* ---- balanced space-filling-curve clustering (point_utils.py:135-287, sf_type='', use_anchor=True, no_reorder=False)
+ * pos fp32 [B,n,2]; outputs: pos_sorted fp32 [B,n,2], mean_pos fp32 [B,k,2], member_idx int64 [B,k,m],
+ * cluster_mask int64 [B,k,m] (written only when k*m != n; may be NULL otherwise), pos_ranking int64 [B,n],
+ * with k = ceil(n/m).  The sort is stable (ties -> lower original index). */
+size_t clusten_sfc_workspace_bytes(int B, int n);
+int clusten_sfc_cluster(const float *pos, int B, int n, int m, int h, int w,
+                        float *pos_sorted, float *mean_pos, int64_t *member_idx, int64_t *cluster_mask,
+                        int64_t *pos_ranking, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- selection primitives of the adaptive downsampling (aff.py:320-324)
+ * topk_select: idx_out[b, 0:k] = first k of a stable DESCENDING sort of score[b,:] (fp32 [B,n]);
+ *              written at idx_out + b*out_stride.
+ * mask_select: idx_out[b, 0:count] = ascending indices i with mask[b,i] != 0 (fp32 [B,n]); exactly `count` slots are
+ *              written per row (surplus indices dropped, missing slots filled with 0). */
+size_t clusten_topk_workspace_bytes(int B, int n);
+int clusten_topk_select(const float *score, int B, int n, int k, int64_t *idx_out, int64_t out_stride,
+                        void *workspace, size_t workspace_bytes, void *stream);
+int clusten_mask_select(const float *mask, int B, int n, int count, int64_t *idx_out, int64_t out_stride, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLUSTEN_B200_H */

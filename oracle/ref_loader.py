@@ -1,0 +1,124 @@
+"""Import the reference's OWN Python (point_utils.py, aff.py) on CPU -- authoring container only.
+
+TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box, so nothing at test / smoke /
+bench run time imports this module; it is used by oracle/make_golden.py to generate the committed
+fixtures in tests/golden and by the (skipped-when-absent) oracle-vs-reference tests.
+
+Recipe: the reference files are loaded by path under a fake package
+``_affref`` so their relative imports resolve; ``detectron2``, ``timm`` and ``pykeops`` (not
+installed, no network) are replaced by minimal stubs; ``..clusten`` is bound to the CPU
+restatements of oracle/clusten_ops.py; ``knn_keops`` is replaced (pykeops cannot be imported)
+by oracle.point_ops.knn; torch.sort / topk inside the reference are forced to the canonical
+stable forms while ``canonical_ties()`` is active.
+"""
+import contextlib
+import importlib.util
+import os
+import sys
+import types
+
+import torch
+
+REF_ROOT = "/root/reference/mask2former/modeling"
+
+
+def available():
+    return os.path.isfile(os.path.join(REF_ROOT, "backbone", "aff.py"))
+
+
+def _mod(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def _install_stubs():
+    class _Registry:
+        def register(self, obj=None):
+            return obj if obj is not None else (lambda o: o)
+
+    class DropPath(torch.nn.Module):            # timm 0.6.12 DropPath: identity in eval / p=0
+        def __init__(self, p=0.0):
+            super().__init__()
+            self.p = p
+
+        def forward(self, x):
+            return x
+
+    class ShapeSpec:
+        def __init__(self, channels=None, stride=None, **kw):
+            self.channels, self.stride = channels, stride
+
+    if "timm" not in sys.modules:
+        _mod("timm"), _mod("timm.models")
+        _mod("timm.models.layers", DropPath=DropPath, trunc_normal_=torch.nn.init.trunc_normal_)
+    if "detectron2" not in sys.modules:
+        _mod("detectron2")
+        _mod("detectron2.modeling", BACKBONE_REGISTRY=_Registry(), SEM_SEG_HEADS_REGISTRY=_Registry(),
+             Backbone=torch.nn.Module, ShapeSpec=ShapeSpec)
+
+
+_cache = {}
+
+
+def load():
+    """Returns (point_utils, aff) reference modules wired to the CPU oracle ops."""
+    if "mods" in _cache:
+        return _cache["mods"]
+    if not available():
+        raise RuntimeError("reference tree not present (GPU box) -- use tests/golden fixtures")
+    _install_stubs()
+    from . import clusten_ops, point_ops
+
+    pkg = _mod("_affref")
+    pkg.__path__ = []
+    cl = _mod("_affref.clusten",
+              CLUSTENQKFunction=clusten_ops.CLUSTENQKFunction,
+              CLUSTENAVFunction=clusten_ops.CLUSTENAVFunction,
+              CLUSTENWFFunction=clusten_ops.CLUSTENWFFunction,
+              WEIGHTEDGATHERFunction=clusten_ops.WEIGHTEDGATHERFunction,
+              MSDETRPCFunction=clusten_ops.MSDETRPCFunction)
+    pkg.clusten = cl
+    bb = _mod("_affref.backbone")
+    bb.__path__ = []
+
+    def _load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF_ROOT, rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    pu = _load("_affref.backbone.point_utils", "backbone/point_utils.py")
+    aff = _load("_affref.backbone.aff", "backbone/aff.py")
+    # pykeops is not importable: replace knn_keops in every module that imported it by name
+    pu.knn_keops = point_ops.knn
+    aff.knn_keops = point_ops.knn
+    _cache["mods"] = (pu, aff)
+    return pu, aff
+
+
+@contextlib.contextmanager
+def canonical_ties():
+    """Force the canonical tie rules inside reference code: Tensor.sort -> stable,
+    Tensor.topk(sorted=False) -> first k of a stable descending sort."""
+    orig_sort, orig_topk = torch.Tensor.sort, torch.Tensor.topk
+
+    def sort(self, *a, **kw):
+        kw["stable"] = True
+        if a:
+            kw["dim"] = a[0]
+            if len(a) > 1:
+                kw["descending"] = a[1]
+        return orig_sort(self, **kw)
+
+    def topk(self, k, dim=-1, largest=True, sorted=True):
+        v, i = orig_sort(self, dim=dim, descending=largest, stable=True)
+        return v.narrow(dim, 0, k), i.narrow(dim, 0, k)
+
+    torch.Tensor.sort, torch.Tensor.topk = sort, topk
+    try:
+        yield
+    finally:
+        torch.Tensor.sort, torch.Tensor.topk = orig_sort, orig_topk
