@@ -1,0 +1,298 @@
+"""The CLUSTEN autograd boundary: drop-in replacements of the reference's ``torch.autograd.Function``s
+(mask2former/modeling/clusten/clusten.py:19-120) on top of libclusten_b200.so.
+
+Same class names, same ``.apply`` argument order, shapes, dtype-cast rules and ``None``-gradient positions:
+
+    CLUSTENQKFunction.apply(query[B,H,N,C], key[B,H,N,C], nbhd_idx[B,N,M])        -> attn[B,H,N,M]      (clusten.py:24)
+    CLUSTENAVFunction.apply(attn[B,H,N,M], v[B,H,N,C], nbhd_idx[B,N,M])           -> feat[B,H,N,C]      (clusten.py:50)
+    CLUSTENWFFunction.apply(weights[B,N',M,IC], feat[B,N,C], nbhd_idx[B,N',M])    -> feat_new[B,N',IC,C](clusten.py:76)
+    WEIGHTEDGATHERFunction.apply(nbhd_idx[B,N,K], weights[B,N,K], feat[B,N_,C])   -> feat_new[B,N,C]    (clusten.py:102)
+
+Differences from the reference that a caller can observe, all deliberate:
+  * row operands (query/key/v/feat) may be arbitrary strided views with unit innermost stride -- the permuted
+    ``b h n c`` views of aff.py:111-113 are consumed in place instead of being copied three times (clusten.py:25-33);
+  * bfloat16 is supported (the reference dispatches fp64/fp32/fp16 only); accumulation is always fp32; float64 is not;
+  * backward is deterministic: the ``fastAtomicAdd`` scatter is replaced by a gather over an inverse neighbour list
+    that is built once per index tensor and cached ON that tensor (``nbhd_idx`` is the same object for every block of
+    an AFF stage, aff.py:487-493);
+  * ``feat`` of AV is returned as a [B,H,N,C] VIEW of token-major [B,N,H,C] memory so that the caller's
+    ``permute(0,2,1,3).reshape(b,n,c)`` (aff.py:154) is free.  Set ``TOKEN_MAJOR_AV_OUTPUT = False`` for a
+    contiguous [B,H,N,C] result.
+There is no CPU path: non-CUDA operands raise RuntimeError, like CHECK_CUDA in clustenqk_cuda.cpp:21.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+TOKEN_MAJOR_AV_OUTPUT = True
+
+# ---- optional per-kernel device timing (bench.py uses it for the roofline line) --------------------------------------
+_timer = None     # dict(name=<entry point>, events=[(start, end), ...]) or None
+
+
+def start_kernel_timer(name):
+    """Record a (start, end) CUDA-event pair around every call of C-ABI entry point ``name`` on its launch stream."""
+    global _timer
+    _timer = {"name": name, "events": []}
+
+
+def stop_kernel_timer():
+    """Returns the list of per-call durations in milliseconds (synchronises)."""
+    global _timer
+    t, _timer = _timer, None
+    if t is None:
+        return []
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in t["events"]]
+
+
+_launch_count = 0
+
+
+def launch_count():
+    """Number of C-ABI compute entry points called so far in this process (each launches >= 1 kernel of ours)."""
+    return _launch_count
+
+
+def _call(name, dev, *args):
+    global _launch_count
+    _launch_count += 1
+    fn = getattr(_lib.lib(), name)
+    timed = _timer is not None and _timer["name"] == name
+    if timed:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(torch.cuda.current_stream(dev))
+    rc = fn(*args, _lib.stream_ptr(dev))
+    if timed:
+        b.record(torch.cuda.current_stream(dev))
+        _timer["events"].append((a, b))
+    _lib.check(rc, name)
+
+
+# ---- helpers ---------------------------------------------------------------------------------------------------------
+def _rows(t):
+    """Tensor addressed as base + sum(idx*stride) with unit innermost stride (copied only if it is not)."""
+    if t.shape[-1] > 1 and t.stride(-1) != 1:
+        t = t.contiguous()
+    elif t.shape[-1] == 1 and t.stride(-1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def _idx(nbhd_idx):
+    if nbhd_idx.dtype != torch.int64:
+        raise RuntimeError(f"nbhd_idx must be int64 (got {nbhd_idx.dtype})")
+    return nbhd_idx if nbhd_idx.is_contiguous() else nbhd_idx.contiguous()
+
+
+def _check_shapes(cond, msg):
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def inverse_neighbour_list(nbhd_idx, Nk):
+    """(offsets int32 [B,Nk+1], entries uint32-as-int32 [B,Nq*M]) of clusten_csr_build, cached on the index tensor."""
+    cache = getattr(nbhd_idx, "_clusten_csr", None)
+    ver = nbhd_idx._version
+    if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr():
+        return cache[3], cache[4]
+    B, Nq, M = nbhd_idx.shape
+    dev = nbhd_idx.device
+    L = _lib.lib()
+    offsets = torch.empty((B, Nk + 1), dtype=torch.int32, device=dev)
+    entries = torch.empty((B, max(Nq * M, 1)), dtype=torch.int32, device=dev)
+    ws_bytes = L.clusten_csr_workspace_bytes(B, Nq, M, Nk)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _call("clusten_csr_build", dev, nbhd_idx.data_ptr(), B, Nq, M, Nk, offsets.data_ptr(), entries.data_ptr(),
+              ws.data_ptr(), ws_bytes)
+    try:
+        nbhd_idx._clusten_csr = (ver, Nk, nbhd_idx.data_ptr(), offsets, entries)
+    except Exception:  # pragma: no cover  (tensor subclass without __dict__)
+        pass
+    return offsets, entries
+
+
+def _s3(t):
+    return t.stride(0), t.stride(1), t.stride(2)
+
+
+# ---- QK --------------------------------------------------------------------------------------------------------------
+class CLUSTENQKFunction(Function):
+    """query times key: attn[b,h,i,j] = sum_c query[b,h,i,c] * key[b,h,nbhd_idx[b,i,j],c]   (clusten.py:19-42)"""
+
+    @staticmethod
+    def forward(ctx, query, key, nbhd_idx):
+        dev = _lib.require_cuda(query, key, nbhd_idx)
+        if key.dtype != query.dtype:
+            key = key.to(query.dtype)                                   # clusten.py:27-28
+        _check_shapes(query.dim() == 4 and key.dim() == 4 and nbhd_idx.dim() == 3, "QK: query/key 4-D, nbhd_idx 3-D")
+        B, H, Nq, C = query.shape
+        Nk = key.shape[2]
+        M = nbhd_idx.shape[2]
+        _check_shapes(key.shape[0] == B and key.shape[1] == H and key.shape[3] == C and
+                      nbhd_idx.shape[0] == B and nbhd_idx.shape[1] == Nq, "QK: shape mismatch")
+        query, key, nbhd_idx = _rows(query), _rows(key), _idx(nbhd_idx)
+        attn = torch.empty((B, H, Nq, M), dtype=query.dtype, device=dev)
+        if attn.numel():
+            with torch.cuda.device(dev):
+                _call("clusten_qk_fwd", dev, query.data_ptr(), key.data_ptr(), nbhd_idx.data_ptr(), attn.data_ptr(),
+                      B, H, Nq, Nk, C, M, *_s3(query), *_s3(key), _lib.dtype_code(query))
+        ctx.save_for_backward(query, key, nbhd_idx)
+        return attn
+
+    @staticmethod
+    def backward(ctx, grad_attn):
+        query, key, nbhd_idx = ctx.saved_tensors
+        dev = query.device
+        B, H, Nq, C = query.shape
+        Nk, M = key.shape[2], nbhd_idx.shape[2]
+        grad_attn = grad_attn.contiguous()
+        if grad_attn.dtype != query.dtype:
+            grad_attn = grad_attn.to(query.dtype)
+        d_query = torch.empty_like(query)
+        d_key = torch.empty_like(key)
+        d_query, d_key = _rows(d_query), _rows(d_key)
+        if Nq * M == 0 or B == 0:
+            return d_query.zero_(), d_key.zero_(), None
+        off, ent = inverse_neighbour_list(nbhd_idx, Nk)
+        with torch.cuda.device(dev):
+            _call("clusten_qk_bwd", dev, grad_attn.data_ptr(), query.data_ptr(), key.data_ptr(), nbhd_idx.data_ptr(),
+                  off.data_ptr(), ent.data_ptr(), d_query.data_ptr(), d_key.data_ptr(), B, H, Nq, Nk, C, M,
+                  *_s3(query), *_s3(key), *_s3(d_query), *_s3(d_key), _lib.dtype_code(query))
+        return d_query, d_key, None
+
+
+# ---- AV --------------------------------------------------------------------------------------------------------------
+class CLUSTENAVFunction(Function):
+    """attention times value: feat[b,h,i,c] = sum_j attn[b,h,i,j] * v[b,h,nbhd_idx[b,i,j],c]   (clusten.py:45-68)"""
+
+    @staticmethod
+    def forward(ctx, attn, v, nbhd_idx):
+        dev = _lib.require_cuda(attn, v, nbhd_idx)
+        if attn.dtype != v.dtype:
+            v = v.to(attn.dtype)                                        # clusten.py:54-55
+        _check_shapes(attn.dim() == 4 and v.dim() == 4 and nbhd_idx.dim() == 3, "AV: attn/v 4-D, nbhd_idx 3-D")
+        B, H, Nq, M = attn.shape
+        Nk, C = v.shape[2], v.shape[3]
+        _check_shapes(v.shape[0] == B and v.shape[1] == H and tuple(nbhd_idx.shape) == (B, Nq, M), "AV: shape mismatch")
+        attn, v, nbhd_idx = _rows(attn), _rows(v), _idx(nbhd_idx)
+        if TOKEN_MAJOR_AV_OUTPUT:
+            feat = torch.empty((B, Nq, H, C), dtype=attn.dtype, device=dev).permute(0, 2, 1, 3)
+        else:
+            feat = torch.empty((B, H, Nq, C), dtype=attn.dtype, device=dev)
+        if feat.numel():
+            with torch.cuda.device(dev):
+                _call("clusten_av_fwd", dev, attn.data_ptr(), v.data_ptr(), nbhd_idx.data_ptr(), feat.data_ptr(),
+                      B, H, Nq, Nk, C, M, *_s3(attn), *_s3(v), *_s3(feat), _lib.dtype_code(attn))
+        ctx.save_for_backward(attn, v, nbhd_idx)
+        return feat
+
+    @staticmethod
+    def backward(ctx, grad_feat):
+        attn, v, nbhd_idx = ctx.saved_tensors
+        dev = attn.device
+        B, H, Nq, M = attn.shape
+        Nk, C = v.shape[2], v.shape[3]
+        grad_feat = _rows(grad_feat)
+        if grad_feat.dtype != attn.dtype:
+            grad_feat = grad_feat.to(attn.dtype)
+        d_attn = torch.empty((B, H, Nq, M), dtype=attn.dtype, device=dev)
+        d_v = _rows(torch.empty_like(v))
+        if Nq * M == 0 or B == 0:
+            return d_attn, d_v.zero_(), None
+        off, ent = inverse_neighbour_list(nbhd_idx, Nk)
+        with torch.cuda.device(dev):
+            _call("clusten_av_bwd", dev, grad_feat.data_ptr(), attn.data_ptr(), v.data_ptr(), nbhd_idx.data_ptr(),
+                  off.data_ptr(), ent.data_ptr(), d_attn.data_ptr(), d_v.data_ptr(), B, H, Nq, Nk, C, M,
+                  *_s3(grad_feat), *_s3(attn), *_s3(v), *_s3(d_v), _lib.dtype_code(attn))
+        return d_attn, d_v, None
+
+
+# ---- WF --------------------------------------------------------------------------------------------------------------
+class CLUSTENWFFunction(Function):
+    """weights times feature: feat_new[b,i,ic,c] = sum_j weights[b,i,j,ic] * feat[b,nbhd_idx[b,i,j],c]  (clusten.py:71-94)"""
+
+    @staticmethod
+    def forward(ctx, weights, feat, nbhd_idx):
+        dev = _lib.require_cuda(weights, feat, nbhd_idx)
+        if feat.dtype != weights.dtype:
+            feat = feat.to(weights.dtype)                               # clusten.py:80-81
+        _check_shapes(weights.dim() == 4 and feat.dim() == 3 and nbhd_idx.dim() == 3, "WF: weights 4-D, feat/nbhd_idx 3-D")
+        B, Nq, M, IC = weights.shape
+        Nk, C = feat.shape[1], feat.shape[2]
+        _check_shapes(feat.shape[0] == B and tuple(nbhd_idx.shape) == (B, Nq, M), "WF: shape mismatch")
+        weights, feat, nbhd_idx = weights.contiguous(), _rows(feat), _idx(nbhd_idx)
+        out = torch.empty((B, Nq, IC, C), dtype=weights.dtype, device=dev)
+        if out.numel():
+            with torch.cuda.device(dev):
+                _call("clusten_wf_fwd", dev, weights.data_ptr(), feat.data_ptr(), nbhd_idx.data_ptr(), out.data_ptr(),
+                      B, Nq, Nk, C, M, IC, feat.stride(0), feat.stride(1), _lib.dtype_code(weights))
+        ctx.save_for_backward(weights, feat, nbhd_idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_feat_new):
+        weights, feat, nbhd_idx = ctx.saved_tensors
+        dev = weights.device
+        B, Nq, M, IC = weights.shape
+        Nk, C = feat.shape[1], feat.shape[2]
+        grad_feat_new = grad_feat_new.contiguous()
+        if grad_feat_new.dtype != weights.dtype:
+            grad_feat_new = grad_feat_new.to(weights.dtype)
+        d_weights = torch.empty_like(weights)
+        d_feat = torch.empty((B, Nk, C), dtype=weights.dtype, device=dev)
+        if Nq * M == 0 or B == 0:
+            return d_weights, d_feat.zero_(), None
+        off, ent = inverse_neighbour_list(nbhd_idx, Nk)
+        with torch.cuda.device(dev):
+            _call("clusten_wf_bwd", dev, grad_feat_new.data_ptr(), weights.data_ptr(), feat.data_ptr(),
+                  nbhd_idx.data_ptr(), off.data_ptr(), ent.data_ptr(), d_weights.data_ptr(), d_feat.data_ptr(),
+                  B, Nq, Nk, C, M, IC, feat.stride(0), feat.stride(1), d_feat.stride(0), d_feat.stride(1),
+                  _lib.dtype_code(weights))
+        return d_weights, d_feat, None
+
+
+# ---- WEIGHTEDGATHER --------------------------------------------------------------------------------------------------
+class WEIGHTEDGATHERFunction(Function):
+    """weighted gather: feat_new[b,i,c] = sum_k weights[b,i,k] * feat[b,nbhd_idx[b,i,k],c]   (clusten.py:97-120)"""
+
+    @staticmethod
+    def forward(ctx, nbhd_idx, weights, feat):
+        dev = _lib.require_cuda(nbhd_idx, weights, feat)
+        if feat.dtype != weights.dtype:
+            weights = weights.to(feat.dtype)                            # clusten.py:106-107
+        _check_shapes(weights.dim() == 3 and feat.dim() == 3 and nbhd_idx.dim() == 3, "WG: all operands 3-D")
+        B, Nq, K = weights.shape
+        Nk, C = feat.shape[1], feat.shape[2]
+        _check_shapes(feat.shape[0] == B and tuple(nbhd_idx.shape) == (B, Nq, K), "WG: shape mismatch")
+        weights, feat, nbhd_idx = weights.contiguous(), _rows(feat), _idx(nbhd_idx)
+        out = torch.empty((B, Nq, C), dtype=feat.dtype, device=dev)
+        if out.numel():
+            with torch.cuda.device(dev):
+                _call("clusten_wg_fwd", dev, nbhd_idx.data_ptr(), weights.data_ptr(), feat.data_ptr(), out.data_ptr(),
+                      B, Nq, Nk, C, K, feat.stride(0), feat.stride(1), _lib.dtype_code(feat))
+        ctx.save_for_backward(nbhd_idx, weights, feat)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_feat_new):
+        nbhd_idx, weights, feat = ctx.saved_tensors
+        dev = feat.device
+        B, Nq, K = weights.shape
+        Nk, C = feat.shape[1], feat.shape[2]
+        grad_feat_new = grad_feat_new.contiguous()
+        if grad_feat_new.dtype != feat.dtype:
+            grad_feat_new = grad_feat_new.to(feat.dtype)
+        d_weights = torch.empty_like(weights)
+        d_feat = torch.empty((B, Nk, C), dtype=feat.dtype, device=dev)
+        if Nq * K == 0 or B == 0:
+            return None, d_weights, d_feat.zero_()
+        off, ent = inverse_neighbour_list(nbhd_idx, Nk)
+        with torch.cuda.device(dev):
+            _call("clusten_wg_bwd", dev, grad_feat_new.data_ptr(), nbhd_idx.data_ptr(), weights.data_ptr(),
+                  feat.data_ptr(), off.data_ptr(), ent.data_ptr(), d_weights.data_ptr(), d_feat.data_ptr(),
+                  B, Nq, Nk, C, K, feat.stride(0), feat.stride(1), d_feat.stride(0), d_feat.stride(1),
+                  _lib.dtype_code(feat))
+        return None, d_weights, d_feat

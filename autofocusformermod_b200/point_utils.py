@@ -1,0 +1,149 @@
+"""Point utilities of the CLUSTEN path on libclusten_b200.so: host-side mirror of the functions of the reference's
+``mask2former/modeling/backbone/point_utils.py`` that the AFF backbone and the point-cloud pixel decoder call
+(same names, argument meaning and return conventions):
+
+    knn_keops(query, database, k, return_dist=False)                     point_utils.py:28-60   -> clusten_knn
+    space_filling_cluster(pos, m, h, w, no_reorder=False, sf_type='', use_anchor=True)
+                                                                         point_utils.py:135-287 -> clusten_sfc_cluster
+    shepard_decay_weights(dist, power=3)                                 point_utils.py:63-75   (elementwise torch)
+    upsample_feature_shepard(query, database, feature, ...)              point_utils.py:78-121  -> clusten_knn + clusten_wg_*
+    topk_select / mask_select / merge_select                             aff.py:292-329         -> clusten_topk_select, clusten_mask_select
+
+Tie rules are canonical (stable; ties -> lowest index), see DESIGN.md.  CUDA tensors only: no CPU path.
+"""
+import math
+
+import torch
+
+from . import _lib
+from .ops import WEIGHTEDGATHERFunction, _call
+
+
+def _f32c(t):
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)                       # point_utils.py:45-49 (positions are always searched in fp32)
+    return t.contiguous()
+
+
+def knn_keops(query, database, k, return_dist=False):
+    """k nearest database points of each query: idx int64 [B, n_q, k] ascending by distance (ties -> lowest index),
+    plus the fp32 distances when ``return_dist`` (returned as ``(nn_idx, nn_dist)``, point_utils.py:55-57)."""
+    dev = _lib.require_cuda(query, database)
+    q, d = _f32c(query), _f32c(database)
+    if q.dim() != 3 or d.dim() != 3 or q.shape[2] != 2 or d.shape[2] != 2 or q.shape[0] != d.shape[0]:
+        raise RuntimeError(f"knn: expected [B,n,2] positions, got {tuple(q.shape)} / {tuple(d.shape)}")
+    B, Nq, _ = q.shape
+    Ndb = d.shape[1]
+    idx = torch.empty((B, Nq, k), dtype=torch.int64, device=dev)
+    dist = torch.empty((B, Nq, k), dtype=torch.float32, device=dev) if return_dist else None
+    with torch.cuda.device(dev):
+        _call("clusten_knn", dev, q.data_ptr(), d.data_ptr(), B, Nq, Ndb, k, idx.data_ptr(), _lib.ptr(dist))
+    if return_dist:
+        return idx, dist
+    return idx
+
+
+knn = knn_keops
+
+
+def space_filling_cluster(pos, m, h, w, no_reorder=False, sf_type='', use_anchor=True):
+    """Balanced clustering along the boustrophedon anchor curve (default branch of point_utils.py:135-287).
+    Returns (pos [B,n,2] reordered, cluster_mean_pos [B,k,2], member_idx [B,k,m] int64,
+    cluster_mask [B,k,m] int64 or None when k*m == n, pos_ranking [B,n,1] int64)."""
+    if no_reorder or sf_type != '' or not use_anchor:
+        raise NotImplementedError("only the default branch (no_reorder=False, sf_type='', use_anchor=True) is on the "
+                                  "accelerated path; Peano/Hilbert orders are out of scope (DESIGN.md)")
+    dev = _lib.require_cuda(pos)
+    dtype_in = pos.dtype
+    p = _f32c(pos)
+    B, n, d = p.shape
+    if d != 2:
+        raise RuntimeError("space_filling_cluster: positions must be 2-D")
+    k = int(math.ceil(n / float(m)))
+    L = _lib.lib()
+    pos_sorted = torch.empty_like(p)
+    mean_pos = torch.empty((B, k, 2), dtype=torch.float32, device=dev)
+    member_idx = torch.empty((B, k, m), dtype=torch.int64, device=dev)
+    cluster_mask = torch.empty((B, k, m), dtype=torch.int64, device=dev) if k * m != n else None
+    ranking = torch.empty((B, n, 1), dtype=torch.int64, device=dev)
+    ws_bytes = L.clusten_sfc_workspace_bytes(B, n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _call("clusten_sfc_cluster", dev, p.data_ptr(), B, n, m, h, w, pos_sorted.data_ptr(), mean_pos.data_ptr(),
+              member_idx.data_ptr(), _lib.ptr(cluster_mask), ranking.data_ptr(), ws.data_ptr(), ws_bytes)
+    if dtype_in != torch.float32:
+        pos_sorted = pos_sorted.to(dtype_in)
+    return pos_sorted, mean_pos, member_idx, cluster_mask, ranking
+
+
+def topk_select(score, k, out=None):
+    """Canonical ``score.topk(k, sorted=False)[1]`` (aff.py:320): first k of a stable descending sort, int64 [B,k]."""
+    dev = _lib.require_cuda(score)
+    s = _f32c(score)
+    B, n = s.shape
+    if out is None:
+        out = torch.empty((B, k), dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    ws_bytes = L.clusten_topk_workspace_bytes(B, n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _call("clusten_topk_select", dev, s.data_ptr(), B, n, k, out.data_ptr(), out.stride(0), ws.data_ptr(), ws_bytes)
+    return out
+
+
+def mask_select(mask, count, out=None):
+    """``mask.nonzero(as_tuple=True)[1].reshape(B, count)`` (aff.py:323) without the dynamic shape / host sync."""
+    dev = _lib.require_cuda(mask)
+    mk = _f32c(mask)
+    B, n = mk.shape
+    if out is None:
+        out = torch.empty((B, count), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _call("clusten_mask_select", dev, mk.data_ptr(), B, n, count, out.data_ptr(), out.stride(0))
+    return out
+
+
+def merge_select(final_prob, reserve_mask, keep_num, reserve_num):
+    """idx [B, keep_num, 1] = cat(canonical top-(keep-reserve) of final_prob, reserve tokens ascending) (aff.py:320-324)."""
+    B = final_prob.shape[0]
+    idx = torch.empty((B, keep_num), dtype=torch.int64, device=final_prob.device)
+    k = keep_num - reserve_num
+    if k > 0:
+        topk_select(final_prob, k, out=idx)
+    if reserve_num > 0:
+        mask_select(reserve_mask, reserve_num, out=idx[:, k:])
+    return idx.unsqueeze(2)
+
+
+def shepard_decay_weights(dist, power=3):
+    """Inverse-distance weights (point_utils.py:63-75)."""
+    dist = dist.clamp(min=1e-2)
+    ipd = 1.0 / (dist.pow(power) + 1e-6)
+    return ipd / (ipd.sum(dim=2, keepdim=True) + 1e-6)
+
+
+def upsample_feature_shepard(query, database, feature, database_idx=None, k=4, power=3, custom_kernel=True,
+                             nn_idx=None, return_weight_only=False):
+    """kNN inverse-distance interpolation of ``feature`` (at ``database``) to ``query`` (point_utils.py:78-121).
+    ``custom_kernel`` is accepted for signature parity; the CUDA weighted gather is always used."""
+    b, n_, d = database.shape
+    n = query.shape[1]
+    if (n == n_) and bool((query == database).all()):                    # point_utils.py:97
+        return feature
+    if nn_idx is not None:
+        k = nn_idx.shape[-1]
+    else:
+        k = min(k, n_)
+        nn_idx = knn_keops(query, database, k=k, return_dist=False)
+    nn_pos = database.gather(index=nn_idx.view(b, -1, 1).expand(-1, -1, 2), dim=1).reshape(b, n, k, d)
+    nn_dist = (query.unsqueeze(2) - nn_pos).pow(2).sum(-1)               # squared distance, point_utils.py:105
+    nn_weights = shepard_decay_weights(nn_dist, power=power)
+    if return_weight_only:
+        return nn_weights
+    c = feature.shape[-1]
+    assert feature.shape[1] == n_
+    up_features = WEIGHTEDGATHERFunction.apply(nn_idx, nn_weights, feature)
+    if database_idx is not None:
+        up_features.scatter_(dim=1, index=database_idx.long().expand(-1, -1, c), src=feature)
+    return up_features

@@ -1,0 +1,150 @@
+"""Per-kernel roofline micro-benchmark of the CLUSTEN ops at backbone-scale shapes.
+
+For every op: CUDA-event time of our C-ABI call (L2 flushed between iterations), ALGORITHMIC bytes (each operand read
+once, each result written once, idx counted as the int64 the interface delivers), achieved GB/s and the fraction of
+MEASURED_PEAKS.json's hbm_gbs.  With --ref also times the reference's own CUDA kernels (oracle/_ref) on the same inputs.
+
+    python benchmarks/op_bench.py [--shape small_s0|mini_s0|tiny_s0|base_s0|cfg1] [--dtype bf16|f32] [--ref] [--iters 10]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+SHAPES = {  # B, H, N, C(per head), M, m ; merge: N' ; WF channel dim = H*C
+    "cfg1":     dict(B=2, H=2, N=4096, C=32, M=48, m=8, Nq_wf=1024),
+    "mini_s0":  dict(B=16, H=2, N=16384, C=16, M=48, m=8, Nq_wf=4096),
+    "tiny_s0":  dict(B=32, H=2, N=16384, C=32, M=48, m=8, Nq_wf=3276),
+    "small_s0": dict(B=32, H=3, N=16384, C=32, M=48, m=8, Nq_wf=4096),
+    "small_s1": dict(B=32, H=6, N=4096, C=32, M=48, m=8, Nq_wf=1024),
+    "base_s0":  dict(B=4, H=4, N=32768, C=32, M=144, m=24, Nq_wf=8192),
+}
+
+
+def peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def structured_idx(B, N, M, m, gen):
+    """Curve-ordered, run-structured neighbourhoods like aff.py:475-478 produces: M/m runs of m consecutive rows drawn
+    from clusters near the token's own cluster."""
+    nnc = M // m
+    k = N // m
+    own = (torch.arange(N, device="cuda") // m).view(1, N, 1)
+    off = torch.randint(-8, 9, (B, N, nnc), device="cuda", generator=gen)
+    off[..., 0] = 0
+    cl = (own + off).clamp_(0, k - 1)
+    return (cl.unsqueeze(-1) * m + torch.arange(m, device="cuda")).reshape(B, N, M).contiguous()
+
+
+def time_fn(fn, iters, flush):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.add_(1)                       # > L2 (126 MB): evicts the operands
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="small_s0")
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--ref", action="store_true")
+    ap.add_argument("--random-idx", action="store_true")
+    args = ap.parse_args()
+    from autofocusformermod_b200 import _lib, ops
+    S = SHAPES[args.shape]
+    B, H, N, C, M, m = S["B"], S["H"], S["N"], S["C"], S["M"], S["m"]
+    dt = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}[args.dtype]
+    s = torch.finfo(dt).bits // 8
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    peak, psrc = peak_gbs()
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")
+    idx = torch.randint(0, N, (B, N, M), device="cuda", generator=gen) if args.random_idx else structured_idx(B, N, M, m, gen)
+    # token-major memory, head-major views: exactly what aff.py:111-113 hands to the ops
+    q = torch.randn(B, N, H, C, device="cuda", generator=gen).to(dt).permute(0, 2, 1, 3)
+    kv = torch.randn(B, N, H, 2, C, device="cuda", generator=gen).to(dt).permute(3, 0, 2, 1, 4)
+    k, v = kv[0], kv[1]
+    attn = torch.randn(B, H, N, M, device="cuda", generator=gen).softmax(-1).to(dt)
+    d_attn = torch.randn(B, H, N, M, device="cuda", generator=gen).to(dt)
+    d_feat = torch.randn(B, N, H, C, device="cuda", generator=gen).to(dt).permute(0, 2, 1, 3)
+    L = _lib.lib()
+    st = lambda: torch.cuda.current_stream().cuda_stream
+    code = _lib.dtype_code(q)
+    off, ent = ops.inverse_neighbour_list(idx, N)
+    out_attn = torch.empty(B, H, N, M, device="cuda", dtype=dt)
+    feat = torch.empty(B, N, H, C, device="cuda", dtype=dt).permute(0, 2, 1, 3)
+    d_q, d_k, d_v = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    s3 = lambda t: (t.stride(0), t.stride(1), t.stride(2))
+    BHNC, BHNM, BNM8 = B * H * N * C * s, B * H * N * M * s, B * N * M * 8
+    rows = []
+
+    def run(name, fn, nbytes):
+        ms = time_fn(fn, args.iters, flush)
+        gbs = nbytes / ms / 1e6
+        rows.append(dict(op=name, ms=round(ms, 4), algo_MB=round(nbytes / 1e6, 1), GBs=round(gbs, 1), frac=round(gbs / peak, 3)))
+        print(json.dumps(rows[-1]), flush=True)
+
+    ck = lambda rc: _lib.check(rc, "bench")
+    run("qk_fwd", lambda: ck(L.clusten_qk_fwd(q.data_ptr(), k.data_ptr(), idx.data_ptr(), out_attn.data_ptr(), B, H, N, N, C, M,
+                                              *s3(q), *s3(k), code, st())), 2 * BHNC + BNM8 + BHNM)
+    run("av_fwd", lambda: ck(L.clusten_av_fwd(attn.data_ptr(), v.data_ptr(), idx.data_ptr(), feat.data_ptr(), B, H, N, N, C, M,
+                                              *s3(attn), *s3(v), *s3(feat), code, st())), BHNM + 2 * BHNC + BNM8)
+    run("qk_bwd", lambda: ck(L.clusten_qk_bwd(d_attn.data_ptr(), q.data_ptr(), k.data_ptr(), idx.data_ptr(), off.data_ptr(),
+                                              ent.data_ptr(), d_q.data_ptr(), d_k.data_ptr(), B, H, N, N, C, M,
+                                              *s3(q), *s3(k), *s3(d_q), *s3(d_k), code, st())), BHNM + 4 * BHNC + BNM8)
+    run("av_bwd", lambda: ck(L.clusten_av_bwd(d_feat.data_ptr(), attn.data_ptr(), v.data_ptr(), idx.data_ptr(), off.data_ptr(),
+                                              ent.data_ptr(), out_attn.data_ptr(), d_v.data_ptr(), B, H, N, N, C, M,
+                                              *s3(d_feat), *s3(attn), *s3(v), *s3(d_v), code, st())), 3 * BHNC + 2 * BHNM + BNM8)
+    ws_b = L.clusten_csr_workspace_bytes(B, N, M, N)
+    ws = torch.empty(ws_b, dtype=torch.uint8, device="cuda")
+    run("csr_build", lambda: ck(L.clusten_csr_build(idx.data_ptr(), B, N, M, N, off.data_ptr(), ent.data_ptr(), ws.data_ptr(), ws_b, st())),
+        BNM8 + B * N * M * 4 + B * (N + 1) * 4)
+    # WF merge: N' tokens in top-k (not curve) order gather M rows of the [B,N,H*C] feature map
+    Nq, Cw, IC = S["Nq_wf"], H * C, 4
+    sel = torch.stack([torch.randperm(N, device="cuda", generator=gen)[:Nq] for _ in range(B)])
+    idx_w = idx.gather(1, sel.unsqueeze(-1).expand(-1, -1, M)).contiguous()
+    w = torch.randn(B, Nq, M, IC, device="cuda", generator=gen).to(dt)
+    f = torch.randn(B, N, Cw, device="cuda", generator=gen).to(dt)
+    out_w = torch.empty(B, Nq, IC, Cw, device="cuda", dtype=dt)
+    d_out = torch.randn(B, Nq, IC, Cw, device="cuda", generator=gen).to(dt)
+    d_w, d_f = torch.empty_like(w), torch.empty_like(f)
+    offw, entw = ops.inverse_neighbour_list(idx_w, N)
+    wb, fb, ib, ob = B * Nq * M * IC * s, B * N * Cw * s, B * Nq * M * 8, B * Nq * IC * Cw * s
+    run("wf_fwd", lambda: ck(L.clusten_wf_fwd(w.data_ptr(), f.data_ptr(), idx_w.data_ptr(), out_w.data_ptr(), B, Nq, N, Cw, M, IC,
+                                              f.stride(0), f.stride(1), code, st())), wb + fb + ib + ob)
+    run("wf_bwd", lambda: ck(L.clusten_wf_bwd(d_out.data_ptr(), w.data_ptr(), f.data_ptr(), idx_w.data_ptr(), offw.data_ptr(),
+                                              entw.data_ptr(), d_w.data_ptr(), d_f.data_ptr(), B, Nq, N, Cw, M, IC,
+                                              f.stride(0), f.stride(1), d_f.stride(0), d_f.stride(1), code, st())),
+        ob + wb + fb + ib + wb + fb)
+    if args.ref and dt != torch.bfloat16:
+        from oracle import ref_cuda
+        qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
+        run("REF qk_fwd (incl. its K transpose)", lambda: ref_cuda.qk_forward(qc, kc, idx), 2 * BHNC + BNM8 + BHNM)
+        run("REF av_fwd", lambda: ref_cuda.av_forward(attn, vc, idx), BHNM + 2 * BHNC + BNM8)
+        run("REF qk_bwd", lambda: ref_cuda.qk_backward(d_attn, qc, kc, idx), BHNM + 4 * BHNC + BNM8)
+        run("REF av_bwd", lambda: ref_cuda.av_backward(d_feat.contiguous(), attn, vc, idx), 3 * BHNC + 2 * BHNM + BNM8)
+        run("REF wf_fwd", lambda: ref_cuda.wf_forward(w, f, idx_w), wb + fb + ib + ob)
+        run("REF wf_bwd", lambda: ref_cuda.wf_backward(d_out, w, f, idx_w), ob + wb + fb + ib + wb + fb)
+    print(json.dumps(dict(shape=args.shape, dtype=args.dtype, peak_gbs=peak, peak_source=psrc, idx="random" if args.random_idx else "structured")))
+
+
+if __name__ == "__main__":
+    main()

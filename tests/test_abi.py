@@ -1,0 +1,82 @@
+"""CPU: the C-ABI library loads, exports every symbol include/clusten_b200.h declares, the ctypes table mirrors the
+header, and argument errors are reported without touching a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from autofocusformermod_b200 import _build, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "clusten_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(int|size_t|const char \*)\s*(clusten_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = [a.strip() for a in m.group(3).split(",")]
+        out[m.group(2)] = 0 if args == ["void"] else len(args)
+    return out
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _build.build()
+    return _lib.lib()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    decl = _declared()
+    assert len(decl) >= 18
+    for name in decl:
+        assert hasattr(lib, name), f"{name} declared in include/clusten_b200.h but not exported"
+
+
+def test_ctypes_table_mirrors_header(lib):
+    decl = _declared()
+    assert set(decl) == set(_lib.SIGNATURES)
+    for name, nargs in decl.items():
+        assert len(_lib.SIGNATURES[name][1]) == nargs, name
+
+
+def test_abi_version(lib):
+    assert lib.clusten_abi_version() == 1
+
+
+def test_argument_errors_without_gpu(lib):
+    # H = 0 -> CLUSTEN_EINVAL before any CUDA call
+    rc = lib.clusten_qk_fwd(1, 1, 1, 1, 1, 0, 4, 4, 8, 4, 0, 0, 0, 0, 0, 0, 0, None)
+    assert rc == -1 and b"bad sizes" in lib.clusten_last_error()
+    rc = lib.clusten_qk_fwd(1, 1, 1, 1, 1, 1, 4, 4, 8, 4, 0, 0, 0, 0, 0, 0, 7, None)
+    assert rc == -2                                  # unknown dtype
+    rc = lib.clusten_knn(1, 1, 1, 4, 4, 17, 1, None, None)
+    assert rc == -3                                  # k > 16
+    rc = lib.clusten_csr_build(1, 1, 4, 300, 4, 1, 1, 1, 1 << 30, None)
+    assert rc == -3                                  # M > 256
+    rc = lib.clusten_sfc_cluster(1, 1, 16, 8, 4, 4, 1, 1, 1, None, 1, 1, 0, None)
+    assert rc == -4                                  # workspace too small
+    assert lib.clusten_csr_workspace_bytes(2, 64, 48, 64) >= 4 * 2 * 64 * 48 * 4
+
+
+def test_ops_refuse_cpu_tensors():
+    """No CPU fallback: CHECK_CUDA of clustenqk_cuda.cpp:21."""
+    from autofocusformermod_b200 import CLUSTENQKFunction, WEIGHTEDGATHERFunction, knn_keops
+    q = torch.randn(1, 1, 4, 4)
+    idx = torch.zeros(1, 4, 2, dtype=torch.int64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        CLUSTENQKFunction.apply(q, q, idx)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        WEIGHTEDGATHERFunction.apply(idx, torch.randn(1, 4, 2), torch.randn(1, 4, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        knn_keops(torch.zeros(1, 4, 2), torch.zeros(1, 4, 2), 2)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.lib()

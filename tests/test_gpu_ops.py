@@ -1,0 +1,266 @@
+"""GPU parity: the four CLUSTEN autograd Functions (ctypes -> C ABI -> sm_100a kernels) against the CPU oracle on the
+same seeded inputs.  Tolerances (BASELINE north_star): max|a-b|/max|b| <= 1e-5 fp32, <= 1e-2 bf16/fp16 (vs the fp32
+oracle on inputs rounded to the low-precision type)."""
+import pytest
+import torch
+
+from oracle import clusten_ops as co
+from oracle import inputs
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.bfloat16: 1e-2, torch.float16: 1e-2}
+
+
+def _ops():
+    import autofocusformermod_b200 as pkg
+    return pkg
+
+
+def _run(fn, tensors, grad_out, dtype):
+    """our Function on cuda in `dtype`; returns fp32 cpu (out, grads of float inputs)."""
+    args, leaves = [], []
+    for t in tensors:
+        if t.is_floating_point():
+            t = t.to("cuda", dtype).requires_grad_(True)
+            leaves.append(t)
+        else:
+            t = t.cuda()
+        args.append(t)
+    out = fn(*args)
+    out.backward(grad_out.to("cuda", dtype))
+    torch.cuda.synchronize()
+    return out.detach().float().cpu(), [l.grad.float().cpu() for l in leaves]
+
+
+def _check(got, ref, dtype, what):
+    out, grads = got
+    rout, rgrads = ref
+    assert out.shape == rout.shape, what
+    e = rel_err(out, rout)
+    assert e <= TOL[dtype], f"{what} forward rel err {e:.3e}"
+    for n, (g, r) in enumerate(zip(grads, rgrads)):
+        assert g.shape == r.shape
+        e = rel_err(g, r)
+        assert e <= TOL[dtype], f"{what} grad[{n}] rel err {e:.3e}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
+@pytest.mark.parametrize("structured", [True, False], ids=["clustered-idx", "random-idx"])
+def test_qk_av_config1(dtype, structured):
+    """BASELINE configs[0]: B=2, N=4096, heads=2, C=32, 48 neighbours."""
+    P = _ops()
+    c = inputs.qkv_case(B=2, H=2, N=4096, C=32, M=48, seed=0, structured=structured, dtype=dtype)
+    ref = co.fwd_bwd(co.qk_forward, [c["q"], c["k"], c["idx"]], c["d_attn"])
+    _check(_run(P.CLUSTENQKFunction.apply, [c["q"], c["k"], c["idx"]], c["d_attn"], dtype), ref, dtype, "QK")
+    ref = co.fwd_bwd(co.av_forward, [c["attn"], c["v"], c["idx"]], c["d_feat"])
+    _check(_run(P.CLUSTENAVFunction.apply, [c["attn"], c["v"], c["idx"]], c["d_feat"], dtype), ref, dtype, "AV")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_wf_config1(dtype):
+    P = _ops()
+    c = inputs.wf_case(B=2, Nq=1024, N=4096, C=64, M=48, IC=4, seed=0, dtype=dtype)
+    ref = co.fwd_bwd(co.wf_forward, [c["w"], c["f"], c["idx"]], c["d_out"])
+    _check(_run(P.CLUSTENWFFunction.apply, [c["w"], c["f"], c["idx"]], c["d_out"], dtype), ref, dtype, "WF")
+
+
+SHAPES_QK = [
+    # B, H, N, C, M      what it covers
+    (1, 1, 1, 4, 1),     # smallest
+    (2, 3, 37, 24, 48),  # C=24 (AFF-Mini stage 3), ragged N
+    (1, 4, 300, 16, 48), # C=16 (AFF-Mini stage 0)
+    (2, 2, 257, 32, 144),# M=144 (AFF-Base)
+    (1, 2, 50, 20, 7),   # C not a multiple of 8 -> bf16 scalar path, fp32 vector path
+    (1, 2, 33, 5, 9),    # odd C -> scalar path
+    (1, 1, 64, 128, 48), # C=128: full-warp rows
+    (1, 1, 40, 256, 12), # C=256 > 32 chunks in fp32 -> scalar path
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("B,H,N,C,M", SHAPES_QK)
+def test_qk_av_shapes(B, H, N, C, M, dtype):
+    P = _ops()
+    g = torch.Generator().manual_seed(B * 1000 + N + C + M)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dtype).float()
+    q, k, v = rnd(B, H, N, C), rnd(B, H, N, C), rnd(B, H, N, C)
+    idx = torch.randint(0, N, (B, N, M), generator=g)
+    attn, d_attn, d_feat = rnd(B, H, N, M).softmax(-1).to(dtype).float(), rnd(B, H, N, M), rnd(B, H, N, C)
+    _check(_run(P.CLUSTENQKFunction.apply, [q, k, idx], d_attn, dtype), co.fwd_bwd(co.qk_forward, [q, k, idx], d_attn), dtype, "QK")
+    _check(_run(P.CLUSTENAVFunction.apply, [attn, v, idx], d_feat, dtype), co.fwd_bwd(co.av_forward, [attn, v, idx], d_feat), dtype, "AV")
+
+
+def test_qk_av_cross_sizes_and_unreferenced_rows():
+    """Nk != Nq; key rows nobody points at must get exactly zero gradient (the reference zero-fills d_key)."""
+    P = _ops()
+    g = torch.Generator().manual_seed(4)
+    B, H, Nq, Nk, C, M = 2, 2, 100, 260, 32, 16
+    q, k = torch.randn(B, H, Nq, C, generator=g), torch.randn(B, H, Nk, C, generator=g)
+    idx = torch.randint(0, 200, (B, Nq, M), generator=g)          # rows 200..259 unreferenced
+    d_attn = torch.randn(B, H, Nq, M, generator=g)
+    got = _run(P.CLUSTENQKFunction.apply, [q, k, idx], d_attn, torch.float32)
+    _check(got, co.fwd_bwd(co.qk_forward, [q, k, idx], d_attn), torch.float32, "QK cross")
+    assert float(got[1][1][:, :, 200:].abs().max()) == 0.0
+
+
+def test_reference_model_views_are_consumed_without_copies():
+    """q / key / v exactly as aff.py:103-113 builds them (permuted, non-contiguous views) and attn[..., :-1] slice
+    (aff.py:146) -- results must equal the contiguous call bit for bit, and grads flow back to the packed kv."""
+    P = _ops()
+    torch.manual_seed(0)
+    b, n, h, c_ = 2, 512, 4, 32
+    c = inputs.qkv_case(B=b, H=h, N=n, C=c_, M=48, seed=2, structured=False)
+    idx = c["idx"].cuda()
+    qf = torch.randn(b, n, h * c_, device="cuda", requires_grad=True)
+    kvf = torch.randn(b, n, 2 * h * c_, device="cuda", requires_grad=True)
+    q = qf.reshape(b, n, h, c_).permute(0, 2, 1, 3)
+    kv = kvf.view(b, n, h, 2, c_).permute(3, 0, 2, 1, 4)
+    key, v = kv[0], kv[1]
+    assert not q.is_contiguous() and not key.is_contiguous()
+    attn = P.CLUSTENQKFunction.apply(q, key, idx)
+    attn_c = P.CLUSTENQKFunction.apply(q.contiguous(), key.contiguous(), idx)
+    assert torch.equal(attn, attn_c)
+    sm = torch.cat([attn, torch.zeros_like(attn[..., :1])], -1).softmax(-1)
+    feat = P.CLUSTENAVFunction.apply(sm[..., :-1], v, idx)
+    feat_c = P.CLUSTENAVFunction.apply(sm[..., :-1].contiguous(), v.contiguous(), idx)
+    assert torch.equal(feat, feat_c)
+    out = feat.permute(0, 2, 1, 3).reshape(b, n, h * c_)
+    out.square().sum().backward()
+    # oracle on CPU, same graph
+    qf2, kvf2 = qf.detach().cpu().requires_grad_(True), kvf.detach().cpu().requires_grad_(True)
+    q2 = qf2.reshape(b, n, h, c_).permute(0, 2, 1, 3)
+    kv2 = kvf2.view(b, n, h, 2, c_).permute(3, 0, 2, 1, 4)
+    a2 = co.qk_forward(q2, kv2[0], c["idx"])
+    sm2 = torch.cat([a2, torch.zeros_like(a2[..., :1])], -1).softmax(-1)
+    f2 = co.av_forward(sm2[..., :-1], kv2[1], c["idx"])
+    f2.permute(0, 2, 1, 3).reshape(b, n, h * c_).square().sum().backward()
+    assert rel_err(qf.grad, qf2.grad) <= 2e-5
+    assert rel_err(kvf.grad, kvf2.grad) <= 2e-5
+
+
+def test_backward_is_deterministic():
+    P = _ops()
+    c = inputs.qkv_case(B=2, H=2, N=2048, C=32, M=48, seed=5, structured=False)
+    a = _run(P.CLUSTENQKFunction.apply, [c["q"], c["k"], c["idx"]], c["d_attn"], torch.float32)
+    b = _run(P.CLUSTENQKFunction.apply, [c["q"], c["k"], c["idx"]], c["d_attn"], torch.float32)
+    assert all(torch.equal(x, y) for x, y in zip(a[1], b[1]))
+
+
+SHAPES_WF = [
+    # B, Nq, N, C, M, IC
+    (1, 1, 1, 4, 1, 1),
+    (2, 100, 400, 32, 48, 4),    # merge 0 of AFF-Mini
+    (2, 77, 300, 128, 48, 4),
+    (1, 64, 64, 256, 9, 4),      # PointConv (msdeformattn_pc.py:309)
+    (1, 50, 200, 384, 48, 4),    # C=384 (Mini stage 3 width)
+    (2, 31, 90, 20, 5, 3),       # IC=3 -> scalar path
+    (1, 40, 80, 7, 4, 2),        # odd C -> scalar path
+    (1, 40, 300, 96, 144, 4),    # Base M=144
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("B,Nq,N,C,M,IC", SHAPES_WF)
+def test_wf_shapes(B, Nq, N, C, M, IC, dtype):
+    P = _ops()
+    c = inputs.wf_case(B=B, Nq=Nq, N=N, C=C, M=M, IC=IC, seed=Nq + C, dtype=dtype)
+    ref = co.fwd_bwd(co.wf_forward, [c["w"], c["f"], c["idx"]], c["d_out"])
+    _check(_run(P.CLUSTENWFFunction.apply, [c["w"], c["f"], c["idx"]], c["d_out"], dtype), ref, dtype, "WF")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("B,Nq,N,C,K", [(3, 50, 100, 32, 4), (2, 1024, 256, 256, 4), (1, 300, 70, 100, 4), (1, 9, 5, 3, 2)])
+def test_weighted_gather_shapes(B, Nq, N, C, K, dtype):
+    """includes the reference's own test shape family (clusten/test_wg_kernel.py: n=50, n_=100, k=4, c=32)."""
+    P = _ops()
+    g = torch.Generator().manual_seed(Nq)
+    idx = torch.randint(0, N, (B, Nq, K), generator=g)
+    w = torch.rand(B, Nq, K, generator=g).to(dtype).float()
+    f = torch.rand(B, N, C, generator=g).to(dtype).float()
+    d_out = torch.randn(B, Nq, C, generator=g).to(dtype).float()
+    ref = co.fwd_bwd(co.wg_forward, [idx, w, f], d_out)
+    _check(_run(P.WEIGHTEDGATHERFunction.apply, [idx, w, f], d_out, dtype), ref, dtype, "WG")
+
+
+def test_weighted_gather_golden(golden_dir):
+    """The reference's seeded WEIGHTEDGATHER check (tests/golden/wg_refcheck.npz)."""
+    import os
+    import numpy as np
+    P = _ops()
+    g = np.load(os.path.join(golden_dir, "wg_refcheck.npz"))
+    idx = torch.from_numpy(g["idx"].astype(np.int64))
+    w, f, up = torch.from_numpy(g["w"]), torch.from_numpy(g["f"]), torch.from_numpy(g["up"])
+    out, (d_w, d_f) = _run(P.WEIGHTEDGATHERFunction.apply, [idx, w, f], torch.full_like(up, 1.0 / up.numel()), torch.float32)
+    assert rel_err(out, up) <= 1e-5
+    assert rel_err(d_w, torch.from_numpy(g["d_w"])) <= 1e-5
+    assert rel_err(d_f, torch.from_numpy(g["d_f"])) <= 1e-5
+
+
+def test_dtype_cast_rules_and_none_grads():
+    """clusten.py:27-28,54-55,80-81,106-107: second operand follows the first; idx gets no gradient."""
+    P = _ops()
+    q = torch.randn(1, 2, 16, 32, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(1, 2, 16, 32, device="cuda", dtype=torch.float32)
+    idx = torch.randint(0, 16, (1, 16, 8), device="cuda")
+    assert P.CLUSTENQKFunction.apply(q, k, idx).dtype == torch.bfloat16
+    a = torch.rand(1, 2, 16, 8, device="cuda")
+    assert P.CLUSTENAVFunction.apply(a, k.bfloat16(), idx).dtype == torch.float32
+    w = torch.rand(1, 16, 8, device="cuda", dtype=torch.float32)
+    f = torch.rand(1, 16, 24, device="cuda", dtype=torch.bfloat16)
+    assert P.WEIGHTEDGATHERFunction.apply(idx, w, f).dtype == torch.bfloat16
+    w4 = torch.rand(1, 16, 8, 4, device="cuda", dtype=torch.bfloat16)
+    assert P.CLUSTENWFFunction.apply(w4, f.float(), idx).dtype == torch.bfloat16
+    with pytest.raises(RuntimeError):
+        P.CLUSTENQKFunction.apply(q.double(), k.double(), idx)            # fp64 is not supported (documented)
+
+
+def test_empty_inputs():
+    P = _ops()
+    q = torch.randn(0, 2, 16, 32, device="cuda")
+    idx = torch.zeros(0, 16, 8, dtype=torch.int64, device="cuda")
+    assert P.CLUSTENQKFunction.apply(q, q, idx).shape == (0, 2, 16, 8)
+
+
+@pytest.mark.parametrize("shape", ["small_stage0", "base_stage0"])
+def test_backbone_scale_properties(shape):
+    """Full BASELINE-size shapes, checked through size-independent properties (the CPU oracle would take minutes):
+    linearity in each operand, and the adjoint identity <QK(q,k), g> == <q, d_q> == <k, d_k> evaluated in fp64."""
+    P = _ops()
+    if shape == "small_stage0":
+        B, H, N, C, M, m = 8, 3, 16384, 32, 48, 8
+    else:
+        B, H, N, C, M, m = 2, 4, 32768, 32, 144, 24
+    g = torch.Generator(device="cuda").manual_seed(0)
+    q = torch.randn(B, H, N, C, device="cuda", generator=g, requires_grad=True)
+    k = torch.randn(B, H, N, C, device="cuda", generator=g, requires_grad=True)
+    # run-structured neighbourhoods: M/m runs of m consecutive rows
+    runs = torch.randint(0, N // m, (B, N, M // m), device="cuda", generator=g)
+    idx = (runs.unsqueeze(-1) * m + torch.arange(m, device="cuda")).reshape(B, N, M)
+    go = torch.randn(B, H, N, M, device="cuda", generator=g)
+    attn = P.CLUSTENQKFunction.apply(q, k, idx)
+    attn2 = P.CLUSTENQKFunction.apply(2.0 * q.detach(), k.detach(), idx)
+    assert rel_err(attn2, 2.0 * attn) <= 1e-6
+    attn.backward(go)
+    lhs = float((attn.detach().double() * go.double()).sum())
+    for t in (q, k):
+        rhs = float((t.detach().double() * t.grad.double()).sum())
+        assert abs(lhs - rhs) <= 1e-5 * abs(lhs) + 1e-3
+    # spot-check 64 random tokens against direct dot products
+    bi = torch.randint(0, B, (64,), device="cuda", generator=g)
+    ti = torch.randint(0, N, (64,), device="cuda", generator=g)
+    rows = k.detach()[bi[:, None, None], torch.arange(H, device="cuda")[None, :, None], idx[bi, ti][:, None, :]]   # 64 H M C
+    ref = (q.detach()[bi, :, ti].unsqueeze(2) * rows).sum(-1)
+    assert rel_err(attn.detach()[bi, :, ti], ref) <= 1e-5
+    # AV adjoint identity
+    a = torch.rand(B, H, N, M, device="cuda", generator=g, requires_grad=True)
+    v = torch.randn(B, H, N, C, device="cuda", generator=g, requires_grad=True)
+    gf = torch.randn(B, H, N, C, device="cuda", generator=g)
+    feat = P.CLUSTENAVFunction.apply(a, v, idx)
+    feat.backward(gf)
+    lhs = float((feat.detach().double() * gf.double()).sum())
+    for t in (a, v):
+        rhs = float((t.detach().double() * t.grad.double()).sum())
+        assert abs(lhs - rhs) <= 1e-5 * abs(lhs) + 1e-3

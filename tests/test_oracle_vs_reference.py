@@ -1,0 +1,54 @@
+"""CPU, authoring container only (needs /root/reference; skipped on the GPU box): the oracle restatements against the
+reference's own Python imported with stubs (oracle/ref_loader.py) on fresh seeded inputs -- the live version of what
+tests/golden freezes."""
+import pytest
+import torch
+
+from oracle import inputs, ref_loader
+from oracle import point_ops as pt
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+
+
+@pytest.mark.parametrize("n,h,w,m", [(1024, 32, 32, 8), (3276, 128, 128, 8), (131, 32, 32, 8), (2048, 32, 64, 24)])
+def test_space_filling_cluster(n, h, w, m):
+    pu, _ = ref_loader.load()
+    pos = inputs.grid_positions(2, h, w) if n == h * w else inputs.random_positions(2, n, h, w, seed=n)
+    with ref_loader.canonical_ties():
+        ref = pu.space_filling_cluster(pos, m, h, w)
+    got = pt.space_filling_cluster(pos, m, h, w)
+    for a, b in zip(got, ref):
+        if b is None:
+            assert a is None
+        elif a.is_floating_point():
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+        else:
+            assert torch.equal(a, b.expand_as(a))
+
+
+def test_merge_selection_matches_reference_cluster_merging():
+    """ClusterMerging.forward selection (aff.py:292-329) vs oracle merge_select."""
+    _, aff = ref_loader.load()
+    torch.manual_seed(0)
+    B, h, w, m = 2, 32, 32, 8
+    n = 256
+    # tokens of a stage >= 1 always contain every reserve position (multiples of 2*stride), like in the backbone
+    g = torch.Generator().manual_seed(3)
+    cells = torch.arange(h * w)
+    is_res = ((cells % w) % 8 == 0) & ((cells // w) % 8 == 0)
+    rows = []
+    for _ in range(B):
+        others = cells[~is_res][torch.randperm(int((~is_res).sum()), generator=g)[:n - int(is_res.sum())]]
+        sel = torch.cat([cells[is_res], others])[torch.randperm(n, generator=g)]
+        rows.append(torch.stack([sel % w, sel // w], dim=1))
+    pos = torch.stack(rows).float()
+    pos, mean, member, cmask, _ = pt.space_filling_cluster(pos, m, h, w)
+    nb, mask, pe_idx = pt.assemble_neighbourhood(pos, mean, member, cmask, 6)
+    feat = torch.randn(B, n, 16)
+    lp = torch.rand(B, n, 1)
+    mod = aff.ClusterMerging(dim=16, out_dim=32, norm_layer=torch.nn.LayerNorm, alpha=4.0, ds_rate=0.25, reserve_on=True)
+    reserve_num = 4 * 4
+    with torch.no_grad(), ref_loader.canonical_ties():
+        pos2, feat2 = mod(pos, feat, nb, mask, lp, 4, pe_idx, reserve_num)
+    idx = pt.merge_select(pos, lp, 4, 4.0, 0.25, reserve_num)
+    assert torch.equal(pos2, pos.gather(1, idx.expand(-1, -1, 2)))
