@@ -19,6 +19,7 @@ _P, _I, _L, _Z = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_size_t
 SIGNATURES = {
     "clusten_abi_version": (_I, []),
     "clusten_last_error": (_c.c_char_p, []),
+    "clusten_kernel_launches": (_c.c_longlong, []),
     "clusten_csr_workspace_bytes": (_Z, [_I] * 4),
     "clusten_csr_build": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "clusten_qk_fwd": (_I, [_P] * 4 + [_I] * 6 + [_L] * 6 + [_I, _P]),

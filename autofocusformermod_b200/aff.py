@@ -1,0 +1,397 @@
+"""AFF backbone as the CALLER of the CLUSTEN path (host-side mirror of mask2former/modeling/backbone/aff.py).
+
+Same module tree and parameter names as the reference (``patch_embed.{proj1,bn,proj2,norm}``,
+``layers.{i}.blocks.{j}.{norm1,attn.{q,kv,blank_k,blank_v,pos_embed,proj},norm2,mlp.{fc1,fc2},gamma1,gamma2}``,
+``layers.{i}.downsample.{weight_net,norm,linear}``, ``layers.{i}.prob_net``, ``norm{i}``) so reference checkpoints load
+with ``load_state_dict``; same constructor arguments as ``AFF.__init__`` (aff.py:592-602); same outputs
+(``res2..res5``, ``res*_pos``, ``res*_spatial_shape``, aff.py:679-685).
+
+What runs where:
+  * clustering, kNN, top-k selection, QK / AV / WF          -> libclusten_b200.so (this package's C ABI)
+  * Linear / LayerNorm / GELU / softmax / conv stem         -> torch (cuBLAS / cuDNN / ATen), as in the reference
+Differences from the reference, none of which changes results beyond fp rounding:
+  * the reserve-token ``nonzero`` (aff.py:323, a device->host sync per merge) is a fixed-size ordered compaction;
+  * ties in the clustering sort and in top-k follow the canonical stable rule;
+  * the [1023^2, heads] bias table (aff.py:129) and the PointConv weight table (aff.py:346) are evaluated only at the
+    table rows a stage actually references (``_TableLookup``): same per-row arithmetic, ~100x less work.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .ops import CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction
+from .point_utils import knn_keops, merge_select, space_filling_cluster
+
+# aff.py:17-19: the relative-position table covers inputs up to 2048 px (stem grid 512)
+REL_POS_WIDTH = 2048 // 4 - 1
+TABLE_WIDTH = 2 * REL_POS_WIDTH + 1
+
+_pre_tables = {}
+
+
+def rel_pos_features(pe_idx):
+    """Rows of the reference's ``pre_table`` (aff.py:21-31) for the given table indices, computed on the fly:
+    (dx, dy, dist, dy/dist, dx/dist) with the 0/0 centre zeroed.  pe_idx int64 [...] -> fp32 [..., 5]."""
+    ys = (pe_idx // TABLE_WIDTH - REL_POS_WIDTH).to(torch.float32)
+    xs = (pe_idx % TABLE_WIDTH - REL_POS_WIDTH).to(torch.float32)
+    dis = (ys ** 2 + xs ** 2) ** 0.5
+    t = torch.stack([xs, ys, dis, ys / dis, xs / dis], dim=-1)
+    return torch.where(torch.isfinite(t), t, torch.zeros_like(t))
+
+
+def pre_table(device):
+    """The full 1023^2 x 5 table (only needed by the global-attention branch of tiny inputs)."""
+    key = str(device)
+    if key not in _pre_tables:
+        _pre_tables[key] = rel_pos_features(torch.arange(TABLE_WIDTH * TABLE_WIDTH, device=device))
+    return _pre_tables[key]
+
+
+class _TableLookup:
+    """``net(pre_table)[pe_idx]`` evaluated as ``net(pre_table[unique rows])[inverse]``.
+
+    The reference pushes all 1 046 529 table rows through ``pos_embed`` in every block and through ``weight_net`` in
+    every merge.  The rows a stage references are a few thousand (neighbours are a few stem-grid cells away), and they
+    are the same for every block of the stage, so the unique rows and the inverse map are computed once per stage."""
+
+    def __init__(self, pe_idx):
+        self.shape = pe_idx.shape
+        uniq, inv = torch.unique(pe_idx.reshape(-1), return_inverse=True)
+        self.features = rel_pos_features(uniq)            # [U, 5]
+        self.inverse = inv                                # [prod(shape)]
+
+    def select(self, rows):
+        """Keep only the given token rows (dim 1) of the lookup: used by ClusterMerging after top-k."""
+        out = _TableLookup.__new__(_TableLookup)
+        inv = self.inverse.view(self.shape)
+        inv = inv.gather(1, rows.expand(-1, -1, self.shape[2]))
+        out.shape, out.features, out.inverse = inv.shape, self.features, inv.reshape(-1)
+        return out
+
+    def __call__(self, net):
+        t = net(self.features)                            # [U, ch]
+        return t[self.inverse].reshape(*self.shape, t.shape[-1])
+
+
+class DropPath(nn.Module):
+    """Stochastic depth per sample (timm 0.6.12 DropPath semantics, aff.py:10,193); identity in eval / p == 0."""
+
+    def __init__(self, drop_prob=0.0):
+        super().__init__()
+        self.drop_prob = float(drop_prob)
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1.0 - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
+        return x * mask.div_(keep)
+
+
+class Mlp(nn.Module):
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features or in_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features or in_features, out_features or in_features)
+        self.drop = nn.Dropout(drop)
+
+    def forward(self, x):
+        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+
+
+class ClusterAttention(nn.Module):
+    """Local attention over each token's neighbourhood of clusters (aff.py:53-160)."""
+
+    def __init__(self, dim, num_heads, attn_drop=0.0, proj_drop=0.0):
+        super().__init__()
+        assert dim % num_heads == 0
+        self.dim, self.num_heads, self.pos_dim = dim, num_heads, 2
+        self.scale = (dim // num_heads) ** -0.5
+        self.q = nn.Linear(dim, dim)
+        self.kv = nn.Linear(dim, 2 * dim)
+        self.softmax = nn.Softmax(dim=-1)
+        self.blank_k = nn.Parameter(torch.randn(dim))
+        self.blank_v = nn.Parameter(torch.randn(dim))
+        self.pos_embed = nn.Linear(self.pos_dim + 3, num_heads)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+
+    def forward(self, feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup=None):
+        b, n, c = feat.shape
+        h = self.num_heads
+        c_ = c // h
+        q = (self.q(feat) * self.scale).reshape(b, n, h, c_).permute(0, 2, 1, 3)          # b h n c_ (view)
+        kv = self.kv(feat).view(b, n, h, 2, c_).permute(3, 0, 2, 1, 4)                   # 2 b h n c_ (view)
+        key, v = kv[0], kv[1]
+        if global_attn:
+            attn = q @ key.transpose(-1, -2)                                             # aff.py:121
+            mask = None
+        else:
+            attn = CLUSTENQKFunction.apply(q, key, member_idx)                           # aff.py:114
+            mask = None if cluster_mask is None else cluster_mask.reshape(b, 1, n, -1)
+        if pe_lookup is None:
+            pe_lookup = _TableLookup(pe_idx)
+        pos_embed = pe_lookup(self.pos_embed).permute(0, 3, 1, 2)                        # aff.py:129-132
+        attn = attn + pos_embed.to(attn.dtype)
+        if mask is not None:
+            attn = attn + (1 - mask) * (-100)                                            # aff.py:137
+        blank_attn = (q * self.blank_k.reshape(1, h, 1, c_)).sum(-1, keepdim=True)       # aff.py:140
+        attn = self.attn_drop(self.softmax(torch.cat([attn, blank_attn], dim=-1)))
+        blank_attn, attn = attn[..., -1:], attn[..., :-1]
+        blank_v = blank_attn * self.blank_v.reshape(1, h, 1, c_)
+        if global_attn:
+            out = attn @ v
+        else:
+            out = CLUSTENAVFunction.apply(attn, v, member_idx)                           # aff.py:154
+        out = (out + blank_v).permute(0, 2, 1, 3).reshape(b, n, c)
+        return self.proj_drop(self.proj(out))
+
+
+class ClusterTransformerBlock(nn.Module):
+    """LN -> ClusterAttention -> residual -> LN -> MLP -> residual, optional layer scale (aff.py:166-238)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=2.0, drop=0.0, attn_drop=0.0, drop_path=0.0, layer_scale=0.0,
+                 act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim, self.num_heads, self.mlp_ratio = dim, num_heads, mlp_ratio
+        self.norm1 = norm_layer(dim)
+        self.attn = ClusterAttention(dim, num_heads=num_heads, attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        self.layer_scale = False
+        if layer_scale is not None and type(layer_scale) in [int, float] and layer_scale > 0:
+            self.layer_scale = True
+            self.gamma1 = nn.Parameter(layer_scale * torch.ones(dim), requires_grad=True)
+            self.gamma2 = nn.Parameter(layer_scale * torch.ones(dim), requires_grad=True)
+
+    def forward(self, feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup=None):
+        a = self.attn(self.norm1(feat), member_idx, cluster_mask, pe_idx, global_attn, pe_lookup)
+        feat = feat + self.drop_path(self.gamma1 * a if self.layer_scale else a)
+        m = self.mlp(self.norm2(feat))
+        return feat + self.drop_path(self.gamma2 * m if self.layer_scale else m)
+
+
+class ClusterMerging(nn.Module):
+    """Adaptive downsampling: importance top-k + reserve grid, then a PointConv merge of each kept token's
+    neighbourhood (aff.py:245-365)."""
+
+    def __init__(self, dim, out_dim, norm_layer=nn.LayerNorm, alpha=4.0, ds_rate=0.25, reserve_on=True):
+        super().__init__()
+        self.dim, self.pos_dim, self.alpha, self.ds_rate, self.reserve_on = dim, 2, alpha, ds_rate, reserve_on
+        inner_ch = 4
+        self.weight_net = nn.Sequential(nn.Linear(self.pos_dim + 3, inner_ch, bias=True), nn.LayerNorm(inner_ch), nn.GELU())
+        self.norm = norm_layer(inner_ch * dim)
+        self.linear = nn.Linear(dim * inner_ch, out_dim)
+
+    def select(self, pos, learned_prob, stride, reserve_num):
+        """Indices [b, keep, 1] of the tokens that survive (aff.py:292-329)."""
+        b, n, _ = pos.shape
+        keep_num = int(n * self.ds_rate)
+        pos_long = pos.long()
+        if stride == 2:
+            grid_prob = ((pos_long % stride) == 0).all(-1).float()                                   # aff.py:297
+        else:
+            _, min_dist = knn_keops(pos, pos, 2, return_dist=True)                                   # aff.py:299
+            ada_stride = 2 ** (min_dist[:, :, 1].log2().ceil() + 1)
+            grid_prob = ((pos_long % ada_stride.unsqueeze(2).long()) == 0).all(-1).float()           # aff.py:302
+        final_prob = grid_prob
+        if learned_prob is not None:
+            final_prob = final_prob + learned_prob.detach().view(b, n).float() * self.alpha          # aff.py:307-310
+        if self.reserve_on:
+            reserve_mask = ((pos_long % (stride * 2)) == 0).all(dim=-1).float()
+            final_prob = final_prob + reserve_mask * (-100)                                          # aff.py:313-315
+            return merge_select(final_prob, reserve_mask, keep_num, reserve_num)
+        return merge_select(final_prob, final_prob, keep_num, 0)
+
+    def forward(self, pos, feat, member_idx, cluster_mask, learned_prob, stride, pe_idx, reserve_num, pe_lookup=None):
+        b, n, c = feat.shape
+        d = pos.shape[2]
+        M = member_idx.shape[-1]
+        idx = self.select(pos, learned_prob, stride, reserve_num)
+        n2 = idx.shape[1]
+        pos = pos.gather(index=idx.expand(-1, -1, d), dim=1)                                         # aff.py:332
+        member_idx = member_idx.gather(index=idx.expand(-1, -1, M), dim=1)                           # aff.py:335
+        if pe_lookup is None:
+            pe_lookup = _TableLookup(pe_idx)
+        weights = pe_lookup.select(idx)(self.weight_net)                                             # aff.py:346-349
+        if cluster_mask is not None:
+            cluster_mask = cluster_mask.gather(index=idx.expand(-1, -1, M), dim=1)
+        if learned_prob is not None:
+            lp = learned_prob.gather(index=member_idx.reshape(b, -1, 1), dim=1).reshape(b, n2, M, 1)  # aff.py:340
+            if cluster_mask is not None:
+                lp = lp * cluster_mask.unsqueeze(3)
+            weights = weights * lp
+        elif cluster_mask is not None:
+            weights = weights * cluster_mask.unsqueeze(3)
+        feat = CLUSTENWFFunction.apply(weights, feat, member_idx).reshape(b, n2, -1)                 # aff.py:361
+        return pos, self.linear(self.norm(feat))
+
+
+class BasicLayer(nn.Module):
+    """One AFF stage: cluster -> neighbourhoods -> transformer blocks -> (optional) merge (aff.py:368-510)."""
+
+    def __init__(self, dim, out_dim, cluster_size, nbhd_size, depth, num_heads, mlp_ratio, alpha=4.0, ds_rate=0.25,
+                 reserve_on=True, drop=0.0, attn_drop=0.0, drop_path=0.0, norm_layer=nn.LayerNorm, layer_scale=0.0,
+                 downsample=None):
+        super().__init__()
+        self.dim, self.nbhd_size, self.cluster_size, self.depth = dim, nbhd_size, cluster_size, depth
+        self.blocks = nn.ModuleList([
+            ClusterTransformerBlock(dim=dim, num_heads=num_heads, mlp_ratio=mlp_ratio, drop=drop, attn_drop=attn_drop,
+                                    drop_path=drop_path[i] if isinstance(drop_path, (list, tuple)) else drop_path,
+                                    layer_scale=layer_scale, norm_layer=norm_layer)
+            for i in range(depth)])
+        if downsample is not None:
+            self.downsample = downsample(dim=dim, out_dim=out_dim, norm_layer=norm_layer, alpha=alpha, ds_rate=ds_rate,
+                                         reserve_on=reserve_on)
+            self.prob_net = nn.Linear(dim, 1)
+        else:
+            self.downsample = None
+        self._grid_cache = None          # stage-0 clustering of an on-grid batch in training (aff.py:461-467)
+
+    def _cluster(self, pos, feat, h, w, on_grid):
+        b, n, c = feat.shape
+        if on_grid and self.training:
+            if self._grid_cache is None or self._grid_cache[0].shape[0] < b or self._grid_cache[0].shape[1] != n:
+                self._grid_cache = space_filling_cluster(pos, self.cluster_size, h, w)
+            pos, mean_pos, member, cmask, reorder = (None if t is None else t[:b] for t in self._grid_cache)
+        else:
+            pos, mean_pos, member, cmask, reorder = space_filling_cluster(pos, self.cluster_size, h, w)
+        feat = feat.gather(1, reorder.expand(-1, -1, c))                                             # aff.py:471
+        return pos, feat, mean_pos, member, cmask
+
+    def forward(self, pos, feat, h, w, on_grid, stride):
+        b, n, d = pos.shape
+        m = self.cluster_size
+        assert m > 0, "cluster_size must be positive"
+        if self.nbhd_size >= n:                                                                      # aff.py:442
+            global_attn, member_idx, cluster_mask = True, None, None
+            rel_pos = (pos[:, None, :, :] + REL_POS_WIDTH) - pos[:, :, None, :]
+        else:
+            global_attn = False
+            k = int(math.ceil(n / float(m)))
+            nnc = min(int(round(self.nbhd_size / float(m))), k)
+            if k == n:                                                                               # aff.py:456-459
+                mean_pos, cluster_mask = pos, None
+                member = torch.arange(n, device=feat.device).reshape(1, n, 1).expand(b, -1, -1)
+            else:
+                pos, feat, mean_pos, member, cluster_mask = self._cluster(pos, feat, h, w, on_grid)
+            nearest = knn_keops(pos, mean_pos, nnc)                                                  # aff.py:475
+            gi = nearest.view(b, -1, 1).expand(-1, -1, m)
+            member_idx = member.gather(index=gi, dim=1).reshape(b, n, nnc * m)                       # aff.py:478
+            if cluster_mask is not None:
+                cluster_mask = cluster_mask.gather(index=gi, dim=1).reshape(b, n, nnc * m)
+            pos_nb = pos.gather(index=member_idx.view(b, -1, 1).expand(-1, -1, d), dim=1).reshape(b, n, nnc * m, d)
+            rel_pos = pos_nb - (pos.unsqueeze(2) - REL_POS_WIDTH)                                    # aff.py:481-482
+        rel_pos = rel_pos.clamp(0, TABLE_WIDTH - 1)
+        pe_idx = (rel_pos[..., 1] * TABLE_WIDTH + rel_pos[..., 0]).long()                            # aff.py:484-485
+        pe_lookup = _TableLookup(pe_idx)
+        for blk in self.blocks:
+            feat = blk(feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup)
+        if self.downsample is None:
+            return pos, feat, pos, feat
+        learned_prob = self.prob_net(feat).sigmoid()                                                 # aff.py:496
+        reserve_num = math.ceil(h / (stride * 2)) * math.ceil(w / (stride * 2))
+        if global_attn:
+            raise NotImplementedError("merging after a global-attention stage (inputs with <= nbhd_size tokens) is "
+                                      "not supported by the reference either (member_idx is None, aff.py:335)")
+        pos_down, feat_down = self.downsample(pos, feat, member_idx, cluster_mask, learned_prob, stride, pe_idx,
+                                              reserve_num, pe_lookup)
+        return pos, feat, pos_down, feat_down
+
+    def extra_repr(self):
+        return f"dim={self.dim}, depth={self.depth}"
+
+
+class PatchEmbed(nn.Module):
+    """Two stride-2 3x3 convs -> tokens on the H/4 x W/4 stem grid with integer (x, y) positions (aff.py:513-565)."""
+
+    def __init__(self, patch_size=4, in_chans=3, embed_dim=32, norm_layer=None):
+        super().__init__()
+        self.patch_size, self.in_chans, self.embed_dim = 4, in_chans, embed_dim
+        self.proj1 = nn.Conv2d(in_chans, embed_dim // 2, kernel_size=3, stride=2, padding=1)
+        self.bn = nn.BatchNorm2d(embed_dim // 2)
+        self.act1 = nn.GELU()
+        self.proj2 = nn.Conv2d(embed_dim // 2, embed_dim, kernel_size=3, stride=2, padding=1)
+        self.norm = norm_layer(embed_dim) if norm_layer is not None else None
+
+    def forward(self, x):
+        _, _, H, W = x.shape
+        if W % self.patch_size != 0:
+            x = F.pad(x, (0, self.patch_size - W % self.patch_size))
+        if H % self.patch_size != 0:
+            x = F.pad(x, (0, 0, 0, self.patch_size - H % self.patch_size))
+        x = self.proj2(self.act1(self.bn(self.proj1(x))))
+        b, c, h, w = x.shape
+        x = x.flatten(2).transpose(1, 2)
+        if self.norm is not None:
+            x = self.norm(x)
+        ys, xs = torch.meshgrid(torch.arange(h, device=x.device), torch.arange(w, device=x.device), indexing="ij")
+        # positions stay fp32 even under autocast: bf16 cannot hold integers > 256 (the reference casts to x.dtype, aff.py:563)
+        pos = torch.stack([xs, ys], dim=2).reshape(1, h * w, 2).expand(b, -1, -1).to(torch.float32)
+        return pos, x, h, w
+
+
+class AFF(nn.Module):
+    """AutoFocusFormer backbone (aff.py:568-686)."""
+
+    def __init__(self, in_chans=3, embed_dim=[32, 128, 256, 512], cluster_size=8, nbhd_size=[48, 48, 48, 48],
+                 alpha=4.0, ds_rate=0.25, reserve_on=True, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], mlp_ratio=2.0,
+                 drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.1, norm_layer=nn.LayerNorm, patch_norm=True,
+                 layer_scale=0.0, downsample=ClusterMerging, out_indices=(0, 1, 2, 3)):
+        super().__init__()
+        self.num_layers = len(depths)
+        self.embed_dim, self.patch_norm, self.mlp_ratio, self.out_indices = embed_dim, patch_norm, mlp_ratio, out_indices
+        self.num_features = embed_dim
+        self.patch_embed = PatchEmbed(in_chans=in_chans, embed_dim=embed_dim[0],
+                                      norm_layer=norm_layer if patch_norm else None)
+        self.pos_drop = nn.Dropout(p=drop_rate)
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths))]
+        self.layers = nn.ModuleList()
+        for i in range(self.num_layers):
+            last = i == self.num_layers - 1
+            self.layers.append(BasicLayer(
+                dim=int(embed_dim[i]), out_dim=None if last else int(embed_dim[i + 1]), cluster_size=cluster_size,
+                nbhd_size=nbhd_size[i], depth=depths[i], num_heads=num_heads[i], mlp_ratio=mlp_ratio, alpha=alpha,
+                ds_rate=ds_rate, reserve_on=reserve_on, drop=drop_rate, attn_drop=attn_drop_rate,
+                drop_path=dpr[sum(depths[:i]):sum(depths[:i + 1])], norm_layer=norm_layer, layer_scale=layer_scale,
+                downsample=None if last else downsample))
+        for i in out_indices:
+            self.add_module(f"norm{i}", norm_layer(embed_dim[i]))
+
+    def forward(self, x):
+        pos, x, h, w = self.patch_embed(x)
+        x = self.pos_drop(x)
+        outs = {}
+        for i, layer in enumerate(self.layers):
+            pos_out, x_out, pos, x = layer(pos, x, h=h, w=w, on_grid=(i == 0), stride=2 ** (i + 1))
+            if i in self.out_indices:
+                outs[f"res{i + 2}"] = getattr(self, f"norm{i}")(x_out)
+                outs[f"res{i + 2}_pos"] = pos_out
+                outs[f"res{i + 2}_spatial_shape"] = (h, w)
+        return outs
+
+
+# cfg.MODEL.AFF.* of the reference yaml files (configs/**/aff/*.yaml; defaults mask2former/config.py:87-104)
+PRESETS = {
+    "mini":     dict(embed_dim=[32, 128, 256, 384], depths=[2, 2, 6, 2], num_heads=[2, 4, 8, 16], mlp_ratio=2.0,
+                     cluster_size=8, nbhd_size=[48, 48, 48, 48], layer_scale=0.0, alpha=4.0, ds_rate=0.25, drop_path_rate=0.0),
+    "tiny_1_5": dict(embed_dim=[64, 128, 256, 512], depths=[3, 4, 18, 5], num_heads=[2, 4, 8, 16], mlp_ratio=3.0,
+                     cluster_size=8, nbhd_size=[48, 48, 48, 48], layer_scale=0.0, alpha=4.0, ds_rate=0.2, drop_path_rate=0.3),
+    "small":    dict(embed_dim=[96, 192, 384, 768], depths=[3, 4, 18, 2], num_heads=[3, 6, 12, 24], mlp_ratio=3.0,
+                     cluster_size=8, nbhd_size=[48, 48, 48, 48], layer_scale=1e-5, alpha=8.0, ds_rate=0.25, drop_path_rate=0.3),
+    "base":     dict(embed_dim=[128, 256, 512, 1024], depths=[3, 4, 18, 2], num_heads=[4, 8, 16, 32], mlp_ratio=3.0,
+                     cluster_size=24, nbhd_size=[144, 144, 144, 144], layer_scale=1e-5, alpha=8.0, ds_rate=0.25, drop_path_rate=0.3),
+    "test":     dict(embed_dim=[32, 128, 256, 384], depths=[1, 1, 2, 1], num_heads=[2, 4, 8, 16], mlp_ratio=2.0,
+                     cluster_size=8, nbhd_size=[48, 48, 48, 48], layer_scale=1e-5, alpha=4.0, ds_rate=0.25, drop_path_rate=0.0),
+}
+
+
+def build_aff(preset, **overrides):
+    cfg = dict(PRESETS[preset])
+    cfg.update(overrides)
+    return AFF(**cfg)

@@ -261,6 +261,7 @@ static int launch_dot(const T *X, const T *Y, const int64_t *idx, T *out, int B,
         dot_rows_scalar<T><<<ceil_div(total, 256), 256, 0, st>>>(X, Y, idx, out, B, H, Nq, C, M,
                                                                  x.sb, x.sh, x.sn, y.sb, y.sh, y.sn);
     }
+    note_launches(1);
     return check_launch("dot_rows");
 }
 
@@ -281,6 +282,7 @@ static int launch_axpy(const T *W, const T *Y, const int64_t *idx, T *out, int B
         axpy_rows_scalar<T><<<ceil_div(total, 256), 256, 0, st>>>(W, Y, idx, out, B, H, Nq, C, M, w.sb, w.sh, w.sn,
                                                                   y.sb, y.sh, y.sn, o.sb, o.sh, o.sn);
     }
+    note_launches(1);
     return check_launch("axpy_rows");
 }
 
@@ -300,6 +302,7 @@ static int launch_csr(const T *W, const T *X, const int32_t *off, const uint32_t
         csr_rows_scalar<T><<<ceil_div(total, 256), 256, 0, st>>>(W, X, off, ent, out, B, H, Nq, Nk, C, M, w.sb, w.sh,
                                                                  w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn);
     }
+    note_launches(1);
     return check_launch("csr_rows");
 }
 

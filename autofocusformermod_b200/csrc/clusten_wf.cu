@@ -267,6 +267,7 @@ static int wf_fwd_impl(const T *w, const T *f, const int64_t *idx, T *out, int B
         const int64_t total = (int64_t)B * Nq * IC_ * C;
         wf_fwd_scalar<T><<<ceil_div(total, 256), 256, 0, st>>>(w, f, idx, out, B, Nq, C, M, IC_, f_sb, f_sn);
     }
+    note_launches(1);
     return check_launch("wf_fwd");
 }
 
@@ -285,6 +286,7 @@ static int wf_bwd_impl(const T *d_out, const T *w, const T *f, const int64_t *id
             const int64_t total = (int64_t)B * Nq * M * IC_;
             wf_dw_scalar<T><<<ceil_div(total, 256), 256, 0, st>>>(d_out, f, idx, d_w, B, Nq, C, M, IC_, f_sb, f_sn);
         }
+        note_launches(1);
         if (int e = check_launch("wf_dw")) return e;
     }
     if ((int64_t)B * Nk > 0) {
@@ -298,6 +300,7 @@ static int wf_bwd_impl(const T *d_out, const T *w, const T *f, const int64_t *id
             const int64_t total = (int64_t)B * Nk * C;
             wf_df_scalar<T><<<ceil_div(total, 256), 256, 0, st>>>(d_out, w, off, ent, d_f, B, Nq, Nk, C, M, IC_, df_sb, df_sn);
         }
+        note_launches(1);
         if (int e = check_launch("wf_df")) return e;
     }
     return 0;

@@ -11,6 +11,7 @@ namespace clusten {
 
 int set_error(int code, const char *fmt, ...);
 int check_launch(const char *what);
+void note_launches(int n);   // bumps the counter behind clusten_kernel_launches()
 
 constexpr int WARPS_PER_CTA = 8;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;

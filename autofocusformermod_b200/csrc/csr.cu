@@ -6,6 +6,7 @@
 // list of every row is in ascending (i, j) order -> the summation order is fixed -> gradients are deterministic.
 // The list depends only on idx, which is constant across all blocks of an AFF stage (aff.py:487-493), so one build is
 // amortised over 2*depth backward kernels.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -14,6 +15,9 @@
 namespace clusten {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int set_error(int code, const char *fmt, ...) {
     va_list ap;
@@ -64,6 +68,7 @@ using namespace clusten;
 
 extern "C" int clusten_abi_version(void) { return CLUSTEN_ABI_VERSION; }
 extern "C" const char *clusten_last_error(void) { return g_err; }
+extern "C" long long clusten_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" size_t clusten_csr_workspace_bytes(int B, int Nq, int M, int Nk) {
     (void)Nk;
@@ -103,5 +108,6 @@ extern "C" int clusten_csr_build(const int64_t *nbhd_idx, int B, int Nq, int M, 
     if (int e = radix_sort_pairs(kA, nullptr, kB, vB, kA, vA, B, nseg, passes * 8, hist, st)) return e;
     const dim3 grid(ceil_div(nseg, 256), B);
     csr_finalize_kernel<<<grid, 256, 0, st>>>(kA, vA, offsets, entries, nseg, Nk, M);
+    note_launches(2);
     return check_launch("csr_build");
 }

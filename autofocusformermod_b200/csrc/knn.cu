@@ -84,5 +84,6 @@ extern "C" int clusten_knn(const float *query, const float *database, int B, int
         KNN_CASE(9) KNN_CASE(10) KNN_CASE(11) KNN_CASE(12) KNN_CASE(13) KNN_CASE(14) KNN_CASE(15) KNN_CASE(16)
     }
 #undef KNN_CASE
+    note_launches(1);
     return check_launch("knn");
 }

@@ -93,6 +93,7 @@ extern "C" int clusten_topk_select(const float *score, int B, int n, int k, int6
     topk_keys_kernel<<<ceil_div((int64_t)tot, 256), 256, 0, st>>>(score, k0, (int64_t)tot);
     if (int e = radix_sort_pairs(k0, nullptr, k1, v1, k2, v2, B, n, 32, hist, st)) return e;
     topk_emit_kernel<<<dim3(ceil_div(k, 256), B), 256, 0, st>>>(v2, n, k, idx_out, out_stride);
+    note_launches(2);
     return check_launch("topk_select");
 }
 
@@ -101,5 +102,6 @@ extern "C" int clusten_mask_select(const float *mask, int B, int n, int count, i
     if (!mask || !idx_out) return set_error(CLUSTEN_EINVAL, "null pointer");
     if (B == 0 || count == 0) return 0;
     mask_select_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(mask, n, count, idx_out, out_stride);
+    note_launches(1);
     return check_launch("mask_select");
 }

@@ -163,5 +163,6 @@ extern "C" int clusten_sfc_cluster(const float *pos, int B, int n, int m, int h,
     sfc_gather_kernel<<<dim3(ceil_div(n, 256), B), 256, 0, st>>>(pos2, v2, n, reinterpret_cast<float2 *>(pos_sorted), pos_ranking);
     sfc_cluster_kernel<<<dim3(ceil_div(k, 128), B), 128, 0, st>>>(pos2, v2, n, m, k, reinterpret_cast<float2 *>(mean_pos),
                                                                    member_idx, ((int64_t)k * m != n) ? cluster_mask : nullptr);
+    note_launches(4);
     return check_launch("sfc_cluster");
 }

@@ -150,6 +150,7 @@ int radix_sort_pairs(uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_
         rs_hist_kernel<<<grid, RS_THREADS, 0, st>>>(kin, n, 8 * p, hist, T);
         rs_scan_kernel<<<B, 1024, 0, st>>>(hist, RS_RADIX * T);
         rs_scatter_kernel<<<grid, RS_THREADS, 0, st>>>(kin, vin, ko, vo, n, 8 * p, hist, T);
+        note_launches(3);
         kin = ko;
         vin = vo;
     }

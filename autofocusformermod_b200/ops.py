@@ -32,19 +32,20 @@ _timer = None     # dict(name=<entry point>, events=[(start, end), ...]) or None
 
 
 def start_kernel_timer(name):
-    """Record a (start, end) CUDA-event pair around every call of C-ABI entry point ``name`` on its launch stream."""
+    """Record a (start, end) CUDA-event pair around every call of C-ABI entry point ``name`` ("*" = all of them) on
+    its launch stream."""
     global _timer
     _timer = {"name": name, "events": []}
 
 
 def stop_kernel_timer():
-    """Returns the list of per-call durations in milliseconds (synchronises)."""
+    """Returns [(entry point, milliseconds, algorithmic bytes)] per recorded call (synchronises)."""
     global _timer
     t, _timer = _timer, None
     if t is None:
         return []
     torch.cuda.synchronize()
-    return [a.elapsed_time(b) for a, b in t["events"]]
+    return [(n, a.elapsed_time(b), nb) for n, a, b, nb in t["events"]]
 
 
 _launch_count = 0
@@ -55,18 +56,25 @@ def launch_count():
     return _launch_count
 
 
-def _call(name, dev, *args):
+def kernel_launches():
+    """Number of CUDA kernels libclusten_b200.so has launched in this process (clusten_kernel_launches)."""
+    return int(_lib.lib().clusten_kernel_launches())
+
+
+def _call(name, dev, *args, nbytes=0):
+    """Invoke C-ABI entry point ``name`` on the current stream of ``dev``.  ``nbytes`` = ALGORITHMIC bytes of the call
+    (each operand read once, each result written once, idx as the int64 delivered) for roofline reports."""
     global _launch_count
     _launch_count += 1
     fn = getattr(_lib.lib(), name)
-    timed = _timer is not None and _timer["name"] == name
+    timed = _timer is not None and _timer["name"] in (name, "*")
     if timed:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(torch.cuda.current_stream(dev))
     rc = fn(*args, _lib.stream_ptr(dev))
     if timed:
         b.record(torch.cuda.current_stream(dev))
-        _timer["events"].append((a, b))
+        _timer["events"].append((name, a, b, nbytes))
     _lib.check(rc, name)
 
 
@@ -135,10 +143,12 @@ class CLUSTENQKFunction(Function):
                       nbhd_idx.shape[0] == B and nbhd_idx.shape[1] == Nq, "QK: shape mismatch")
         query, key, nbhd_idx = _rows(query), _rows(key), _idx(nbhd_idx)
         attn = torch.empty((B, H, Nq, M), dtype=query.dtype, device=dev)
+        es = query.element_size()
         if attn.numel():
             with torch.cuda.device(dev):
                 _call("clusten_qk_fwd", dev, query.data_ptr(), key.data_ptr(), nbhd_idx.data_ptr(), attn.data_ptr(),
-                      B, H, Nq, Nk, C, M, *_s3(query), *_s3(key), _lib.dtype_code(query))
+                      B, H, Nq, Nk, C, M, *_s3(query), *_s3(key), _lib.dtype_code(query),
+                      nbytes=es * (B * H * (Nq + Nk) * C + B * H * Nq * M) + 8 * B * Nq * M)
         ctx.save_for_backward(query, key, nbhd_idx)
         return attn
 
@@ -160,7 +170,8 @@ class CLUSTENQKFunction(Function):
         with torch.cuda.device(dev):
             _call("clusten_qk_bwd", dev, grad_attn.data_ptr(), query.data_ptr(), key.data_ptr(), nbhd_idx.data_ptr(),
                   off.data_ptr(), ent.data_ptr(), d_query.data_ptr(), d_key.data_ptr(), B, H, Nq, Nk, C, M,
-                  *_s3(query), *_s3(key), *_s3(d_query), *_s3(d_key), _lib.dtype_code(query))
+                  *_s3(query), *_s3(key), *_s3(d_query), *_s3(d_key), _lib.dtype_code(query),
+                  nbytes=query.element_size() * (B * H * Nq * M + 2 * B * H * (Nq + Nk) * C) + 8 * B * Nq * M)
         return d_query, d_key, None
 
 
@@ -185,7 +196,8 @@ class CLUSTENAVFunction(Function):
         if feat.numel():
             with torch.cuda.device(dev):
                 _call("clusten_av_fwd", dev, attn.data_ptr(), v.data_ptr(), nbhd_idx.data_ptr(), feat.data_ptr(),
-                      B, H, Nq, Nk, C, M, *_s3(attn), *_s3(v), *_s3(feat), _lib.dtype_code(attn))
+                      B, H, Nq, Nk, C, M, *_s3(attn), *_s3(v), *_s3(feat), _lib.dtype_code(attn),
+                      nbytes=attn.element_size() * (B * H * Nq * M + B * H * (Nq + Nk) * C) + 8 * B * Nq * M)
         ctx.save_for_backward(attn, v, nbhd_idx)
         return feat
 
@@ -206,7 +218,8 @@ class CLUSTENAVFunction(Function):
         with torch.cuda.device(dev):
             _call("clusten_av_bwd", dev, grad_feat.data_ptr(), attn.data_ptr(), v.data_ptr(), nbhd_idx.data_ptr(),
                   off.data_ptr(), ent.data_ptr(), d_attn.data_ptr(), d_v.data_ptr(), B, H, Nq, Nk, C, M,
-                  *_s3(grad_feat), *_s3(attn), *_s3(v), *_s3(d_v), _lib.dtype_code(attn))
+                  *_s3(grad_feat), *_s3(attn), *_s3(v), *_s3(d_v), _lib.dtype_code(attn),
+                  nbytes=attn.element_size() * (2 * B * H * Nq * M + B * H * (Nq + 2 * Nk) * C) + 8 * B * Nq * M)
         return d_attn, d_v, None
 
 
@@ -228,7 +241,8 @@ class CLUSTENWFFunction(Function):
         if out.numel():
             with torch.cuda.device(dev):
                 _call("clusten_wf_fwd", dev, weights.data_ptr(), feat.data_ptr(), nbhd_idx.data_ptr(), out.data_ptr(),
-                      B, Nq, Nk, C, M, IC, feat.stride(0), feat.stride(1), _lib.dtype_code(weights))
+                      B, Nq, Nk, C, M, IC, feat.stride(0), feat.stride(1), _lib.dtype_code(weights),
+                      nbytes=weights.element_size() * (B * Nq * M * IC + B * Nk * C + B * Nq * IC * C) + 8 * B * Nq * M)
         ctx.save_for_backward(weights, feat, nbhd_idx)
         return out
 
@@ -250,7 +264,8 @@ class CLUSTENWFFunction(Function):
             _call("clusten_wf_bwd", dev, grad_feat_new.data_ptr(), weights.data_ptr(), feat.data_ptr(),
                   nbhd_idx.data_ptr(), off.data_ptr(), ent.data_ptr(), d_weights.data_ptr(), d_feat.data_ptr(),
                   B, Nq, Nk, C, M, IC, feat.stride(0), feat.stride(1), d_feat.stride(0), d_feat.stride(1),
-                  _lib.dtype_code(weights))
+                  _lib.dtype_code(weights),
+                  nbytes=weights.element_size() * (B * Nq * IC * C + 2 * B * Nq * M * IC + 2 * B * Nk * C) + 8 * B * Nq * M)
         return d_weights, d_feat, None
 
 
@@ -272,7 +287,8 @@ class WEIGHTEDGATHERFunction(Function):
         if out.numel():
             with torch.cuda.device(dev):
                 _call("clusten_wg_fwd", dev, nbhd_idx.data_ptr(), weights.data_ptr(), feat.data_ptr(), out.data_ptr(),
-                      B, Nq, Nk, C, K, feat.stride(0), feat.stride(1), _lib.dtype_code(feat))
+                      B, Nq, Nk, C, K, feat.stride(0), feat.stride(1), _lib.dtype_code(feat),
+                      nbytes=feat.element_size() * (B * Nq * K + B * Nk * C + B * Nq * C) + 8 * B * Nq * K)
         ctx.save_for_backward(nbhd_idx, weights, feat)
         return out
 
@@ -294,5 +310,6 @@ class WEIGHTEDGATHERFunction(Function):
             _call("clusten_wg_bwd", dev, grad_feat_new.data_ptr(), nbhd_idx.data_ptr(), weights.data_ptr(),
                   feat.data_ptr(), off.data_ptr(), ent.data_ptr(), d_weights.data_ptr(), d_feat.data_ptr(),
                   B, Nq, Nk, C, K, feat.stride(0), feat.stride(1), d_feat.stride(0), d_feat.stride(1),
-                  _lib.dtype_code(feat))
+                  _lib.dtype_code(feat),
+                  nbytes=feat.element_size() * (B * Nq * C + 2 * B * Nq * K + 2 * B * Nk * C) + 8 * B * Nq * K)
         return None, d_weights, d_feat

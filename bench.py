@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- AFF backbone images/s on the CLUSTEN B200 path (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A step = one pass of the hot path (AFF backbone: clustering -> kNN -> QK/AV blocks -> top-k merge/WF, x4 stages) over
+one batch of synthetic images.  Default workload = BASELINE configs[1]'s backbone: AFF-Mini, 512x512, batch 16 per
+GPU, fp32 forward, random-init weights (the Mask2Former head is out of scope).
+
+  value         images/s, inputs resident in HBM, CUDA events, max over ranks (one process per GPU, batch-sharded:
+                no collective on the forward path; training workloads add DDP's NCCL gradient all-reduce)
+  e2e           same metric through the public API with HOST buffers: pinned-host images -> H2D -> AFF.forward ->
+                all outputs D2H, every step, inside the timed region
+  roofline      the dominant libclusten_b200 entry point of the step, timed live with CUDA events around each of its
+                launches inside the timed region; achieved = its ALGORITHMIC bytes / its device time
+  cpu_baseline  the CPU oracle port of the same backbone (oracle/aff_oracle.py) on the host cores, bounded sample
+  --impl reference   times that CPU port alone (the reference's Python cannot travel to the GPU box: it needs
+                detectron2 / pykeops / the reference tree), rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: preset, per-GPU batch, H, W, mode, dtype
+    "aff_mini_fwd_b16_512": dict(preset="mini", batch=16, H=512, W=512, mode="fwd", dtype="f32",
+                                 note="BASELINE configs[1] backbone (AFF-Mini ADE20K, 512x512, batch 16), eval forward"),
+    "aff_tiny15_train_b32_512_bf16": dict(preset="tiny_1_5", batch=32, H=512, W=512, mode="train", dtype="bf16",
+                                          note="BASELINE configs[2]: AFF-Tiny-1/5 fwd+bwd+AdamW, 512x512, batch 32, bf16 autocast"),
+    "aff_small_fwd_b16_512": dict(preset="small", batch=16, H=512, W=512, mode="fwd", dtype="f32",
+                                  note="AFF-Small backbone forward, 512x512, batch 16 (north_star scaling target)"),
+    "aff_small_fwd_b1_1024x2048": dict(preset="small", batch=1, H=1024, W=2048, mode="fwd", dtype="f32",
+                                       note="BASELINE configs[3] backbone: AFF-Small Cityscapes 1024x2048, 1 image per GPU"),
+    "aff_base_train_b2_512x1024_bf16": dict(preset="base", batch=2, H=512, W=1024, mode="train", dtype="bf16",
+                                            note="BASELINE configs[4] backbone: AFF-Base 512x1024 crop, 2 per GPU, bf16, DDP"),
+}
+DEFAULT_WORKLOAD = "aff_mini_fwd_b16_512"
+CPU_SAMPLE_IMAGES = 2
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        busy = [x for x in sm if x > 0.5 * (mx[0] if mx else 1e9)] or sm
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_images(batch, H, W, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, 3, H, W, generator=g)
+
+
+def run_reference(args, wl, rank, world):
+    """CPU arm: the oracle port of the backbone on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import aff_oracle as ao
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = ao.PRESETS[wl["preset"]]
+    W = ao.synthetic_state(cfg)
+    train = wl["mode"] == "train"
+    if train:
+        W = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in W.items()}
+    x = make_images(CPU_SAMPLE_IMAGES, wl["H"], wl["W"], seed=0)
+
+    def step():
+        if train:
+            out = ao.aff_forward(x, W, cfg, training=False)
+            sum(out[f"res{i}"].float().mean() for i in range(2, 6)).backward()
+        else:
+            with torch.no_grad():
+                ao.aff_forward(x, W, cfg)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = CPU_SAMPLE_IMAGES * args.steps / dt
+    sample = f"{CPU_SAMPLE_IMAGES} images of {wl['H']}x{wl['W']} per step, fp32, {wl['mode']}"
+    print(json.dumps({
+        "impl": "reference", "metric": "aff_backbone_images_per_sec", "value": round(val, 4), "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "note": wl["note"], "batch_per_step": CPU_SAMPLE_IMAGES},
+        "cpu_baseline": {"value": round(val, 4), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from autofocusformermod_b200 import ops
+    from autofocusformermod_b200.aff import build_aff
+
+    torch.manual_seed(0)
+    train = wl["mode"] == "train"
+    model = build_aff(wl["preset"]).to(dev)
+    model.train(train)
+    amp = wl["dtype"] == "bf16"
+    opt = None
+    net = model
+    if train:
+        if world > 1:
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+
+    B = wl["batch"]
+    x_host = make_images(B, wl["H"], wl["W"], seed=rank).pin_memory()
+    x_dev = x_host.to(dev)
+
+    def step(x):
+        if train:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                out = net(x)
+                loss = sum(out[f"res{i}"].float().mean() for i in range(2, 6))
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return {"loss": loss.detach()}
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            return net(x)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step(x_dev)
+    barrier()
+    # untimed pre-pass: which of our entry points dominates a step?
+    ops.start_kernel_timer("*")
+    step(x_dev)
+    per = {}
+    for name, ms, nb in ops.stop_kernel_timer():
+        e = per.setdefault(name, [0.0, 0, 0])
+        e[0] += ms
+        e[1] += nb
+        e[2] += 1
+    dominant = max((n for n in per if per[n][1] > 0), key=lambda n: per[n][0])
+    torch.cuda.reset_peak_memory_stats()
+
+    # ---- timed region 1: inputs resident in HBM --------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    k0 = ops.kernel_launches()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ops.start_kernel_timer(dominant)
+    ev0.record()
+    for _ in range(args.steps):
+        step(x_dev)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    dom = ops.stop_kernel_timer()
+    launches = ops.kernel_launches() - k0
+    clocks = sampler.stop()
+    peak_mem = torch.cuda.max_memory_allocated()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---- timed region 2: end to end with host buffers --------------------------------------------------------------
+    out = step(x_dev)
+    host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items() if torch.is_tensor(v)}
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+    h2d = x_host.numel() * x_host.element_size()
+    x_stage = torch.empty_like(x_dev)
+
+    def e2e_step():
+        x_stage.copy_(x_host, non_blocking=True)
+        o = step(x_stage)
+        for k, buf in host_out.items():
+            buf.copy_(o[k], non_blocking=True)
+        torch.cuda.synchronize()          # the step's result is on the host
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_max = float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (sustained copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
+    dom_ms = sum(m for _, m, _ in dom)
+    dom_bytes = sum(nb for _, _, nb in dom)
+    achieved = dom_bytes / dom_ms / 1e6 if dom_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")          # filled from an `ncu --set full` capture (per launch)
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get(dominant)
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "launches_timed": len(dom), "algorithmic_bytes_per_launch_avg": int(dom_bytes / max(len(dom), 1)),
+                "avg_launch_ms": round(dom_ms / max(len(dom), 1), 4),
+                "share_of_step": round(dom_ms / ms, 4),
+                "per_entry_ms_per_step": {n: round(v[0], 4) for n, v in sorted(per.items())}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import aff_oracle as ao
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cfg = ao.PRESETS[wl["preset"]]
+        Wc = ao.synthetic_state(cfg)
+        xs = make_images(CPU_SAMPLE_IMAGES, wl["H"], wl["W"], seed=0)
+        if train:
+            Wc = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in Wc.items()}
+        reps, t0 = 0, time.perf_counter()
+        while reps < 2 or (time.perf_counter() - t0 < 10.0 and reps < 8):
+            if train:
+                o = ao.aff_forward(xs, Wc, cfg)
+                sum(o[f"res{i}"].float().mean() for i in range(2, 6)).backward()
+            else:
+                with torch.no_grad():
+                    ao.aff_forward(xs, Wc, cfg)
+            reps += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": round(CPU_SAMPLE_IMAGES * reps / dt, 4), "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"{reps} passes of {CPU_SAMPLE_IMAGES} images {wl['H']}x{wl['W']}, fp32, {wl['mode']} (oracle/aff_oracle.py)"}
+
+    total_images = B * world * args.steps
+    line = {
+        "metric": "aff_backbone_images_per_sec", "value": round(total_images / (ms_max / 1e3), 2), "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+        "config": {"workload": args.workload, "note": wl["note"], "batch_per_gpu": B, "global_batch": B * world,
+                   "image": [wl["H"], wl["W"]], "parallelism": f"dp{world} (batch-sharded, no data-path collective"
+                   + (", NCCL gradient all-reduce)" if train and world > 1 else ")"),
+                   "l2": f"no explicit flush: one step streams {peak_mem / 2**20:.0f} MiB of live activations (>> 126 MB L2)"},
+        "e2e": {"value": round(total_images / e2e_max, 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

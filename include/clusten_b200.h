@@ -53,6 +53,8 @@ enum {
 
 int clusten_abi_version(void);
 const char *clusten_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+long long clusten_kernel_launches(void);
 
 /* ---- inverse neighbour list (CSR over key rows), built once per index tensor and reused by every backward ----
  * offsets: int32 [B, Nk+1]; entries: uint32 [B, Nq*M], entry = (i << 8) | j  (query i, slot j), ascending per row.

@@ -6,7 +6,17 @@ torch.topk(sorted=False), KeOps argKmin) the oracle fixes the canonical rule doc
 oracle/__init__.py: stable sorts, ties -> lowest index.
 """
 import math
+
+import numpy as np
 import torch
+
+
+def sqrt_rn(x):
+    """Correctly rounded fp32 square root.  torch.sqrt on CPU is NOT correctly rounded on every build (measured in the
+    authoring container: 6 of 640 multiples of 1/64 near 144 are off by one ulp), numpy's is (it matches the
+    round-to-nearest result obtained through float64).  The CUDA path uses __fsqrt_rn."""
+    return torch.from_numpy(np.sqrt(x.contiguous().numpy()))
+
 
 
 # --------------------------------------------------------------------------------------- kNN
@@ -24,6 +34,7 @@ def knn(query, database, k, return_dist=False, chunk=2048):
     B, Nq, _ = q.shape
     idx_out = torch.empty(B, Nq, k, dtype=torch.int64)
     dist_out = torch.empty(B, Nq, k, dtype=torch.float32)
+    ar = torch.arange(d.shape[1], dtype=torch.int64)
     for b in range(B):
         for s in range(0, Nq, chunk):
             diff = q[b, s:s + chunk, None, :] - d[b, None, :, :]          # nq x ndb x D
@@ -31,10 +42,13 @@ def knn(query, database, k, return_dist=False, chunk=2048):
             acc = sq[..., 0]
             for t in range(1, sq.shape[-1]):
                 acc = acc + sq[..., t]                                    # left-to-right, rounded adds
-            dist = torch.sqrt(acc)
-            sv, si = torch.sort(dist, dim=1, stable=True)
-            idx_out[b, s:s + chunk] = si[:, :k]
-            dist_out[b, s:s + chunk] = sv[:, :k]
+            dist = sqrt_rn(acc)
+            # canonical order = ascending (distance, index): dist >= 0 so its bit pattern is order-preserving and
+            # (bits << 32 | index) is a total order; the k smallest keys ARE the first k of a stable ascending sort.
+            key = (dist.view(torch.int32).to(torch.int64) << 32) | ar
+            top = torch.topk(key, k, dim=1, largest=False, sorted=True)[0]
+            idx_out[b, s:s + chunk] = top & 0xFFFFFFFF
+            dist_out[b, s:s + chunk] = (top >> 32).to(torch.int32).view(torch.float32)
     if return_dist:
         return idx_out, dist_out
     return idx_out

@@ -17,7 +17,7 @@ def _declared():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"\b(int|size_t|const char \*)\s*(clusten_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\b(int|size_t|long long|const char \*)\s*(clusten_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = [a.strip() for a in m.group(3).split(",")]
         out[m.group(2)] = 0 if args == ["void"] else len(args)
     return out

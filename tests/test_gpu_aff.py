@@ -1,0 +1,93 @@
+"""GPU parity of the AFF backbone running on the CLUSTEN C-ABI path against (1) the golden vectors produced by the
+reference's own ``AFF`` class (tests/golden/aff_test_256.npz) and (2) the CPU oracle on other shapes, forward and
+backward.  Token selections / positions must be bit-exact; features within 1e-4 (fp32 through ~10 layers)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import aff_oracle as ao
+
+from conftest import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(preset, W):
+    from autofocusformermod_b200.aff import build_aff
+    m = build_aff(preset)
+    missing, unexpected = m.load_state_dict(W, strict=False)
+    assert not unexpected and set(missing) <= {"patch_embed.bn.num_batches_tracked"}, (missing, unexpected)
+    return m.cuda()
+
+
+def test_parameter_names_match_reference():
+    from autofocusformermod_b200.aff import build_aff
+    for preset in ("mini", "small", "base"):
+        cfg = ao.PRESETS[preset]
+        names = set(build_aff(preset).state_dict()) - {"patch_embed.bn.num_batches_tracked"}
+        assert names == set(ao.param_shapes(cfg)), preset
+
+
+def test_forward_matches_reference_class_golden():
+    g = np.load(os.path.join(GOLDEN, "aff_test_256.npz"))
+    cfg = ao.PRESETS["test"]
+    m = _model("test", ao.synthetic_state(cfg)).eval()
+    x = ao.synthetic_images(2, 256, 256).cuda()
+    with torch.no_grad():
+        out = m(x)
+    for i in range(2, 6):
+        assert torch.equal(out[f"res{i}_pos"].cpu().to(torch.int16), torch.from_numpy(g[f"res{i}_pos"])), f"res{i}_pos"
+        s = int(g[f"res{i}_stride"])
+        assert rel_err(out[f"res{i}"][:, ::s], torch.from_numpy(g[f"res{i}_sub"])) <= 1e-4, f"res{i}"
+        assert abs(float(out[f"res{i}"].double().sum()) - float(g[f"res{i}_sum"])) <= 1e-4 * float(g[f"res{i}_abs"])
+        assert out[f"res{i}_spatial_shape"] == (64, 64)
+
+
+@pytest.mark.parametrize("H,W", [(128, 192), (96, 100)])
+def test_forward_backward_matches_oracle(H, W):
+    """Non-square / non-multiple-of-4 inputs (padding branch aff.py:541-546, padded clusters -> cluster_mask)."""
+    cfg = ao.PRESETS["test"]
+    Wt = ao.synthetic_state(cfg, seed=1)
+    m = _model("test", Wt).eval()
+    x = ao.synthetic_images(2, H, W, seed=1)
+    Wr = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in Wt.items()}
+    ref = ao.aff_forward(x, Wr, cfg)
+    out = m(x.cuda())
+    loss_r = sum(ref[f"res{i}"].square().mean() for i in range(2, 6))
+    loss_g = sum(out[f"res{i}"].square().mean() for i in range(2, 6))
+    for i in range(2, 6):
+        assert torch.equal(out[f"res{i}_pos"].cpu(), ref[f"res{i}_pos"]), f"res{i}_pos"
+        assert rel_err(out[f"res{i}"], ref[f"res{i}"]) <= 1e-4, f"res{i}"
+    loss_r.backward()
+    loss_g.backward()
+    worst = 0.0
+    for name, p in m.named_parameters():
+        gr = Wr[name].grad
+        if gr is None:
+            continue
+        worst = max(worst, rel_err(p.grad, gr))
+    assert worst <= 2e-3, worst          # fp32 through ~10 layers with different summation orders
+
+
+def test_bf16_autocast_runs_and_tracks_fp32():
+    cfg = ao.PRESETS["test"]
+    m = _model("test", ao.synthetic_state(cfg)).eval()
+    x = ao.synthetic_images(2, 128, 128).cuda()
+    with torch.no_grad():
+        ref = m(x)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = m(x)
+    assert out["res2"].dtype == torch.float32 or out["res2"].dtype == torch.bfloat16
+    assert torch.equal(out["res2_pos"], ref["res2_pos"])
+    assert rel_err(out["res2"].float(), ref["res2"]) <= 5e-2
+
+
+def test_training_mode_caches_stage0_clustering():
+    m = _model("test", ao.synthetic_state(ao.PRESETS["test"])).train()
+    x = ao.synthetic_images(2, 64, 64).cuda()
+    m(x)
+    cache = m.layers[0]._grid_cache
+    m(x)
+    assert m.layers[0]._grid_cache is cache
