@@ -46,6 +46,14 @@ def structured_idx(B, N, M, m, gen):
 
 
 def time_fn(fn, iters, flush):
+    if iters <= 0:                          # --once: a single cold launch
+        flush.add_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b)
     for _ in range(3):
         fn()
     ts = []
@@ -68,6 +76,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--ref", action="store_true")
     ap.add_argument("--random-idx", action="store_true")
+    ap.add_argument("--once", action="store_true", help="run every op exactly once (for ncu captures)")
     args = ap.parse_args()
     from autofocusformermod_b200 import _lib, ops
     S = SHAPES[args.shape]
@@ -97,7 +106,7 @@ def main():
     rows = []
 
     def run(name, fn, nbytes):
-        ms = time_fn(fn, args.iters, flush)
+        ms = time_fn(fn, 0 if args.once else args.iters, flush)
         gbs = nbytes / ms / 1e6
         rows.append(dict(op=name, ms=round(ms, 4), algo_MB=round(nbytes / 1e6, 1), GBs=round(gbs, 1), frac=round(gbs / peak, 3)))
         print(json.dumps(rows[-1]), flush=True)
