@@ -11,7 +11,7 @@
 // over the inverse neighbour list built by clusten_csr_build.
 #include <initializer_list>
 
-#include "common.cuh"
+#include "tile.cuh"
 
 namespace clusten {
 
@@ -21,7 +21,9 @@ template <typename T, int G>
 __global__ void __launch_bounds__(CTA_THREADS)
 dot_rows_kernel(const T *__restrict__ X, const T *__restrict__ Y, const int64_t *__restrict__ idx, T *__restrict__ out,
                 int B, int H, int Nq, int nchunk, int M,
-                int64_t x_sb, int64_t x_sh, int64_t x_sn, int64_t y_sb, int64_t y_sh, int64_t y_sn) {
+                int64_t x_sb, int64_t x_sh, int64_t x_sn, int64_t y_sb, int64_t y_sh, int64_t y_sn,
+                const int *__restrict__ tile_flag) {
+    if (tile_flag && tile_flag[0] == 0) return;        // the tile-union kernel (clusten_tile.cu) takes this call
     constexpr int VPT = Vec<T>::VPT;
     constexpr int RPI = 32 / G;
     extern __shared__ int smem_i[];
@@ -73,7 +75,8 @@ __global__ void __launch_bounds__(CTA_THREADS)
 axpy_rows_kernel(const T *__restrict__ W, const T *__restrict__ Y, const int64_t *__restrict__ idx, T *__restrict__ out,
                  int B, int H, int Nq, int nchunk, int M,
                  int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t y_sb, int64_t y_sh, int64_t y_sn,
-                 int64_t o_sb, int64_t o_sh, int64_t o_sn) {
+                 int64_t o_sb, int64_t o_sh, int64_t o_sn, const int *__restrict__ tile_flag) {
+    if (tile_flag && tile_flag[0] == 0) return;
     constexpr int VPT = Vec<T>::VPT;
     constexpr int RPI = 32 / G;
     extern __shared__ int smem_i[];
@@ -127,7 +130,8 @@ csr_rows_kernel(const T *__restrict__ W, const T *__restrict__ X, const int32_t 
                 const uint32_t *__restrict__ entries, T *__restrict__ out,
                 int B, int H, int Nq, int Nk, int nchunk, int M,
                 int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t x_sb, int64_t x_sh, int64_t x_sn,
-                int64_t o_sb, int64_t o_sh, int64_t o_sn) {
+                int64_t o_sb, int64_t o_sh, int64_t o_sn, const int *__restrict__ tile_flag) {
+    if (tile_flag && tile_flag[0] == 0) return;
     constexpr int VPT = Vec<T>::VPT;
     constexpr int RPI = 32 / G;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,7 +178,9 @@ csr_rows_kernel(const T *__restrict__ W, const T *__restrict__ X, const int32_t 
 // ---- scalar fallbacks: any C / stride / alignment; one thread per output element -------------------------------
 template <typename T>
 __global__ void dot_rows_scalar(const T *X, const T *Y, const int64_t *idx, T *out, int B, int H, int Nq, int C, int M,
-                                int64_t x_sb, int64_t x_sh, int64_t x_sn, int64_t y_sb, int64_t y_sh, int64_t y_sn) {
+                                int64_t x_sb, int64_t x_sh, int64_t x_sn, int64_t y_sb, int64_t y_sh, int64_t y_sn,
+                                const int *tile_flag) {
+    if (tile_flag && tile_flag[0] == 0) return;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)B * H * Nq * M) return;
     const int j = (int)(t % M);
@@ -190,7 +196,8 @@ __global__ void dot_rows_scalar(const T *X, const T *Y, const int64_t *idx, T *o
 template <typename T>
 __global__ void axpy_rows_scalar(const T *W, const T *Y, const int64_t *idx, T *out, int B, int H, int Nq, int C, int M,
                                  int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t y_sb, int64_t y_sh, int64_t y_sn,
-                                 int64_t o_sb, int64_t o_sh, int64_t o_sn) {
+                                 int64_t o_sb, int64_t o_sh, int64_t o_sn, const int *tile_flag) {
+    if (tile_flag && tile_flag[0] == 0) return;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)B * H * Nq * C) return;
     const int c = (int)(t % C);
@@ -208,7 +215,8 @@ template <typename T>
 __global__ void csr_rows_scalar(const T *W, const T *X, const int32_t *offsets, const uint32_t *entries, T *out,
                                 int B, int H, int Nq, int Nk, int C, int M,
                                 int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t x_sb, int64_t x_sh, int64_t x_sn,
-                                int64_t o_sb, int64_t o_sh, int64_t o_sn) {
+                                int64_t o_sb, int64_t o_sh, int64_t o_sn, const int *tile_flag) {
+    if (tile_flag && tile_flag[0] == 0) return;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)B * H * Nk * C) return;
     const int c = (int)(t % C);
@@ -229,6 +237,19 @@ __global__ void csr_rows_scalar(const T *W, const T *X, const int32_t *offsets, 
 // ---- host-side launchers --------------------------------------------------------------------------------------
 struct Rows { const void *p; int64_t sb, sh, sn; };
 
+template <typename T> bool tile_dot_eligible(int C, int M, Rows4 x, Rows4 y);
+template <typename T> bool tile_axpy_eligible(int C, int M, Rows4 w, Rows4 y, Rows4 o);
+template <typename T> bool tile_scat_eligible(int C, int M, Rows4 w, Rows4 x, Rows4 o);
+template <typename T> int launch_dot_tile(const T *X, const T *Y, const void *pack, T *out, int B, int H, int Nq, int Nk, int C,
+                                          int M, Rows4 x, Rows4 y, cudaStream_t st);
+template <typename T> int launch_axpy_tile(const T *W, const T *Y, const void *pack, T *out, int B, int H, int Nq, int Nk, int C,
+                                           int M, Rows4 w, Rows4 y, Rows4 o, cudaStream_t st);
+template <typename T> int launch_scat_tile(const T *W, const T *X, const void *pack, T *out, int B, int H, int Nq, int Nk, int C,
+                                           int M, Rows4 w, Rows4 x, Rows4 o, cudaStream_t st);
+
+static inline Rows4 r4(const Rows &r) { return Rows4{r.p, r.sb, r.sh, r.sn}; }
+static inline const int *tile_flag_of(const void *pack) { return reinterpret_cast<const int *>(pack); }   // PackView.flags is at offset 0
+
 template <typename T> static bool vec_ok(int C, std::initializer_list<Rows> rows) {
     constexpr int VPT = Vec<T>::VPT;
     if (C % VPT != 0 || C / VPT > 32) return false;
@@ -245,30 +266,42 @@ static int check_common(int B, int H, int Nq, int Nk, int C, int M) {
     return 0;
 }
 
+// Every launcher enqueues the tile-union kernel (when a pack is given and the shape qualifies) AND the generic kernel;
+// the pack's device-side flag lets exactly one of them do the work, so no host synchronisation is needed.
 template <typename T>
-static int launch_dot(const T *X, const T *Y, const int64_t *idx, T *out, int B, int H, int Nq, int C, int M,
-                      Rows x, Rows y, cudaStream_t st) {
+static int launch_dot(const T *X, const T *Y, const int64_t *idx, const void *pack, T *out, int B, int H, int Nq, int Nk,
+                      int C, int M, Rows x, Rows y, cudaStream_t st) {
     if ((int64_t)B * Nq == 0) return 0;
+    const int *flag = nullptr;
+    if (pack && tile_dot_eligible<T>(C, M, r4(x), r4(y))) {
+        if (int e = launch_dot_tile<T>(X, Y, pack, out, B, H, Nq, Nk, C, M, r4(x), r4(y), st)) return e;
+        flag = tile_flag_of(pack);
+    }
     if (vec_ok<T>(C, {x, y})) {
         const int nchunk = C / Vec<T>::VPT;
         const int grid = ceil_div((int64_t)B * Nq, WARPS_PER_CTA);
         const size_t smem = (size_t)WARPS_PER_CTA * 2 * M * sizeof(int);
         CLUSTEN_DISPATCH_GROUP(pick_group(nchunk),
             (dot_rows_kernel<T, G><<<grid, CTA_THREADS, smem, st>>>(X, Y, idx, out, B, H, Nq, nchunk, M,
-                                                                     x.sb, x.sh, x.sn, y.sb, y.sh, y.sn)));
+                                                                     x.sb, x.sh, x.sn, y.sb, y.sh, y.sn, flag)));
     } else {
         const int64_t total = (int64_t)B * H * Nq * M;
         dot_rows_scalar<T><<<ceil_div(total, 256), 256, 0, st>>>(X, Y, idx, out, B, H, Nq, C, M,
-                                                                 x.sb, x.sh, x.sn, y.sb, y.sh, y.sn);
+                                                                 x.sb, x.sh, x.sn, y.sb, y.sh, y.sn, flag);
     }
     note_launches(1);
     return check_launch("dot_rows");
 }
 
 template <typename T>
-static int launch_axpy(const T *W, const T *Y, const int64_t *idx, T *out, int B, int H, int Nq, int C, int M,
-                       Rows w, Rows y, Rows o, cudaStream_t st) {
+static int launch_axpy(const T *W, const T *Y, const int64_t *idx, const void *pack, T *out, int B, int H, int Nq, int Nk,
+                       int C, int M, Rows w, Rows y, Rows o, cudaStream_t st) {
     if ((int64_t)B * Nq == 0) return 0;
+    const int *flag = nullptr;
+    if (pack && tile_axpy_eligible<T>(C, M, r4(w), r4(y), r4(o))) {
+        if (int e = launch_axpy_tile<T>(W, Y, pack, out, B, H, Nq, Nk, C, M, r4(w), r4(y), r4(o), st)) return e;
+        flag = tile_flag_of(pack);
+    }
     if (vec_ok<T>(C, {y, o})) {
         const int nchunk = C / Vec<T>::VPT;
         const int grid = ceil_div((int64_t)B * Nq, WARPS_PER_CTA);
@@ -276,31 +309,36 @@ static int launch_axpy(const T *W, const T *Y, const int64_t *idx, T *out, int B
         CLUSTEN_DISPATCH_GROUP(pick_group(nchunk),
             (axpy_rows_kernel<T, G><<<grid, CTA_THREADS, smem, st>>>(W, Y, idx, out, B, H, Nq, nchunk, M,
                                                                       w.sb, w.sh, w.sn, y.sb, y.sh, y.sn,
-                                                                      o.sb, o.sh, o.sn)));
+                                                                      o.sb, o.sh, o.sn, flag)));
     } else {
         const int64_t total = (int64_t)B * H * Nq * C;
         axpy_rows_scalar<T><<<ceil_div(total, 256), 256, 0, st>>>(W, Y, idx, out, B, H, Nq, C, M, w.sb, w.sh, w.sn,
-                                                                  y.sb, y.sh, y.sn, o.sb, o.sh, o.sn);
+                                                                  y.sb, y.sh, y.sn, o.sb, o.sh, o.sn, flag);
     }
     note_launches(1);
     return check_launch("axpy_rows");
 }
 
 template <typename T>
-static int launch_csr(const T *W, const T *X, const int32_t *off, const uint32_t *ent, T *out,
+static int launch_csr(const T *W, const T *X, const int32_t *off, const uint32_t *ent, const void *pack, T *out,
                       int B, int H, int Nq, int Nk, int C, int M, Rows w, Rows x, Rows o, cudaStream_t st) {
     if ((int64_t)B * Nk == 0) return 0;
+    const int *flag = nullptr;
+    if (pack && tile_scat_eligible<T>(C, M, r4(w), r4(x), r4(o))) {
+        if (int e = launch_scat_tile<T>(W, X, pack, out, B, H, Nq, Nk, C, M, r4(w), r4(x), r4(o), st)) return e;
+        flag = tile_flag_of(pack);
+    }
     if (vec_ok<T>(C, {x, o})) {
         const int nchunk = C / Vec<T>::VPT;
         const int grid = ceil_div((int64_t)B * Nk, WARPS_PER_CTA);
         CLUSTEN_DISPATCH_GROUP(pick_group(nchunk),
             (csr_rows_kernel<T, G><<<grid, CTA_THREADS, 0, st>>>(W, X, off, ent, out, B, H, Nq, Nk, nchunk, M,
                                                                   w.sb, w.sh, w.sn, x.sb, x.sh, x.sn,
-                                                                  o.sb, o.sh, o.sn)));
+                                                                  o.sb, o.sh, o.sn, flag)));
     } else {
         const int64_t total = (int64_t)B * H * Nk * C;
         csr_rows_scalar<T><<<ceil_div(total, 256), 256, 0, st>>>(W, X, off, ent, out, B, H, Nq, Nk, C, M, w.sb, w.sh,
-                                                                 w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn);
+                                                                 w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn, flag);
     }
     note_launches(1);
     return check_launch("csr_rows");
@@ -310,20 +348,20 @@ static int launch_csr(const T *W, const T *X, const int32_t *off, const uint32_t
 
 using namespace clusten;
 
-extern "C" int clusten_qk_fwd(const void *q, const void *k, const int64_t *nbhd_idx, void *attn,
+extern "C" int clusten_qk_fwd(const void *q, const void *k, const int64_t *nbhd_idx, const void *pack, void *attn,
                               int B, int H, int Nq, int Nk, int C, int M,
                               int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t k_sb, int64_t k_sh, int64_t k_sn,
                               int dtype, void *stream) {
     if (int e = check_common(B, H, Nq, Nk, C, M)) return e;
     if (!q || !k || !nbhd_idx || !attn) return set_error(CLUSTEN_EINVAL, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    CLUSTEN_DISPATCH_DTYPE(dtype, return launch_dot<T>((const T *)q, (const T *)k, nbhd_idx, (T *)attn, B, H, Nq, C, M,
+    CLUSTEN_DISPATCH_DTYPE(dtype, return launch_dot<T>((const T *)q, (const T *)k, nbhd_idx, pack, (T *)attn, B, H, Nq, Nk, C, M,
                                                        Rows{q, q_sb, q_sh, q_sn}, Rows{k, k_sb, k_sh, k_sn}, st));
     return 0;
 }
 
 extern "C" int clusten_qk_bwd(const void *d_attn, const void *q, const void *k, const int64_t *nbhd_idx,
-                              const int32_t *csr_offsets, const uint32_t *csr_entries, void *d_q, void *d_k,
+                              const int32_t *csr_offsets, const uint32_t *csr_entries, const void *pack, void *d_q, void *d_k,
                               int B, int H, int Nq, int Nk, int C, int M,
                               int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t k_sb, int64_t k_sh, int64_t k_sn,
                               int64_t dq_sb, int64_t dq_sh, int64_t dq_sn, int64_t dk_sb, int64_t dk_sh, int64_t dk_sn,
@@ -335,29 +373,29 @@ extern "C" int clusten_qk_bwd(const void *d_attn, const void *q, const void *k, 
     cudaStream_t st = (cudaStream_t)stream;
     const Rows da{d_attn, (int64_t)H * Nq * M, (int64_t)Nq * M, (int64_t)M};
     CLUSTEN_DISPATCH_DTYPE(dtype, {
-        if (int e = launch_axpy<T>((const T *)d_attn, (const T *)k, nbhd_idx, (T *)d_q, B, H, Nq, C, M, da,
+        if (int e = launch_axpy<T>((const T *)d_attn, (const T *)k, nbhd_idx, pack, (T *)d_q, B, H, Nq, Nk, C, M, da,
                                    Rows{k, k_sb, k_sh, k_sn}, Rows{d_q, dq_sb, dq_sh, dq_sn}, st)) return e;
-        return launch_csr<T>((const T *)d_attn, (const T *)q, csr_offsets, csr_entries, (T *)d_k, B, H, Nq, Nk, C, M, da,
+        return launch_csr<T>((const T *)d_attn, (const T *)q, csr_offsets, csr_entries, pack, (T *)d_k, B, H, Nq, Nk, C, M, da,
                              Rows{q, q_sb, q_sh, q_sn}, Rows{d_k, dk_sb, dk_sh, dk_sn}, st);
     });
     return 0;
 }
 
-extern "C" int clusten_av_fwd(const void *attn, const void *v, const int64_t *nbhd_idx, void *feat,
+extern "C" int clusten_av_fwd(const void *attn, const void *v, const int64_t *nbhd_idx, const void *pack, void *feat,
                               int B, int H, int Nq, int Nk, int C, int M,
                               int64_t a_sb, int64_t a_sh, int64_t a_sn, int64_t v_sb, int64_t v_sh, int64_t v_sn,
                               int64_t f_sb, int64_t f_sh, int64_t f_sn, int dtype, void *stream) {
     if (int e = check_common(B, H, Nq, Nk, C, M)) return e;
     if (!attn || !v || !nbhd_idx || !feat) return set_error(CLUSTEN_EINVAL, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    CLUSTEN_DISPATCH_DTYPE(dtype, return launch_axpy<T>((const T *)attn, (const T *)v, nbhd_idx, (T *)feat, B, H, Nq, C, M,
+    CLUSTEN_DISPATCH_DTYPE(dtype, return launch_axpy<T>((const T *)attn, (const T *)v, nbhd_idx, pack, (T *)feat, B, H, Nq, Nk, C, M,
                                                         Rows{attn, a_sb, a_sh, a_sn}, Rows{v, v_sb, v_sh, v_sn},
                                                         Rows{feat, f_sb, f_sh, f_sn}, st));
     return 0;
 }
 
 extern "C" int clusten_av_bwd(const void *d_feat, const void *attn, const void *v, const int64_t *nbhd_idx,
-                              const int32_t *csr_offsets, const uint32_t *csr_entries, void *d_attn, void *d_v,
+                              const int32_t *csr_offsets, const uint32_t *csr_entries, const void *pack, void *d_attn, void *d_v,
                               int B, int H, int Nq, int Nk, int C, int M,
                               int64_t df_sb, int64_t df_sh, int64_t df_sn, int64_t a_sb, int64_t a_sh, int64_t a_sn,
                               int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t dv_sb, int64_t dv_sh, int64_t dv_sn,
@@ -368,9 +406,9 @@ extern "C" int clusten_av_bwd(const void *d_feat, const void *attn, const void *
     if (M > 256) return set_error(CLUSTEN_EUNSUPPORTED, "backward needs M <= 256 (got %d)", M);
     cudaStream_t st = (cudaStream_t)stream;
     CLUSTEN_DISPATCH_DTYPE(dtype, {
-        if (int e = launch_dot<T>((const T *)d_feat, (const T *)v, nbhd_idx, (T *)d_attn, B, H, Nq, C, M,
+        if (int e = launch_dot<T>((const T *)d_feat, (const T *)v, nbhd_idx, pack, (T *)d_attn, B, H, Nq, Nk, C, M,
                                   Rows{d_feat, df_sb, df_sh, df_sn}, Rows{v, v_sb, v_sh, v_sn}, st)) return e;
-        return launch_csr<T>((const T *)attn, (const T *)d_feat, csr_offsets, csr_entries, (T *)d_v, B, H, Nq, Nk, C, M,
+        return launch_csr<T>((const T *)attn, (const T *)d_feat, csr_offsets, csr_entries, pack, (T *)d_v, B, H, Nq, Nk, C, M,
                              Rows{attn, a_sb, a_sh, a_sn}, Rows{d_feat, df_sb, df_sh, df_sn},
                              Rows{d_v, dv_sb, dv_sh, dv_sn}, st);
     });

@@ -1,0 +1,148 @@
+// clusten_pack_build: analyse an index tensor once (per AFF stage) and emit the tile pack of tile.cuh.
+#include "tile.cuh"
+
+namespace clusten {
+
+constexpr int PACK_WARPS = 4;
+
+__global__ void __launch_bounds__(PACK_WARPS * 32)
+pack_tile_kernel(const int64_t *__restrict__ idx, int B, int Nq, int M, int Nk, PackView pk) {
+    __shared__ int oct_rs[PACK_WARPS][TILE_TOK][S_MAX];
+    __shared__ __align__(16) int8_t slot_s[PACK_WARPS][TILE_TOK][U_MAX];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bt = blockIdx.x * PACK_WARPS + warp;
+    if (bt >= B * pk.T) return;
+    const int b = bt / pk.T, tile = bt - b * pk.T;
+    const int i0 = tile * TILE_TOK;
+    const int S = M >> 3;
+    // step 1: every (row, slot) -> octet id, -1 (impure) or -2 (row beyond Nq)
+    for (int item = lane; item < TILE_TOK * S; item += 32) {
+        const int r = item / S, s = item - r * S;
+        const int i = i0 + r;
+        int o = -2;
+        if (i < Nq) {
+            const int64_t *p = idx + ((int64_t)b * Nq + i) * M + 8 * s;
+            const int64_t base = p[0];
+            bool pure = base >= 0 && (base & 7) == 0 && base + 7 < (int64_t)Nk;
+#pragma unroll
+            for (int k = 1; k < 8; ++k) pure = pure && (p[k] == base + k);
+            o = pure ? (int)(base >> 3) : -1;
+        }
+        oct_rs[warp][r][s] = o;
+    }
+    for (int x = lane; x < TILE_TOK * U_MAX / 4; x += 32) reinterpret_cast<int *>(&slot_s[warp][0][0])[x] = -1;
+    __syncwarp();
+    // step 2: union in first-seen order (lane u holds union position u / u + 32)
+    int my0 = -1, my1 = -1, U = 0, bad = 0;
+    for (int r = 0; r < TILE_TOK; ++r) {
+        for (int s = 0; s < S; ++s) {
+            const int o = oct_rs[warp][r][s];
+            if (o == -2) continue;
+            if (o == -1) { ++bad; continue; }
+            const unsigned m0 = __ballot_sync(FULL, my0 == o), m1 = __ballot_sync(FULL, my1 == o);
+            int pos;
+            if (m0) pos = __ffs(m0) - 1;
+            else if (m1) pos = 32 + __ffs(m1) - 1;
+            else {
+                pos = U;
+                if (U < 32) { if (lane == U) my0 = o; }
+                else if (U < 64) { if (lane == U - 32) my1 = o; }
+                ++U;
+            }
+            if (pos < U_MAX) {
+                const int prev = slot_s[warp][r][pos];
+                __syncwarp();
+                if (prev != -1) ++bad;                       // the token references one octet twice: generic path
+                else if (lane == 0) slot_s[warp][r][pos] = (int8_t)s;
+                __syncwarp();
+            }
+        }
+    }
+    const int Uc = min(U, U_MAX);
+    pk.tile_oct[(int64_t)bt * U_MAX + lane] = lane < Uc ? my0 : 0;
+    if (lane + 32 < U_MAX) pk.tile_oct[(int64_t)bt * U_MAX + 32 + lane] = (lane + 32 < Uc) ? my1 : 0;
+    const int4 *src = reinterpret_cast<const int4 *>(&slot_s[warp][0][0]);
+    int4 *dst = reinterpret_cast<int4 *>(pk.slot_of + (int64_t)bt * TILE_TOK * U_MAX);
+    for (int x = lane; x < TILE_TOK * U_MAX / 16; x += 32) dst[x] = src[x];
+    if (lane == 0) {
+        pk.tile_u[bt] = Uc;
+        atomicMax(pk.flags + 1, U);
+        if (bad) atomicAdd(pk.flags + 2, bad);
+        if (U > U_MAX) atomicAdd(pk.flags + 3, 1);
+        if (bad || U > U_MAX) atomicExch(pk.flags + 0, 1);
+    }
+}
+
+// inverse lists: one (key = octet, implicit value = tile*U_MAX + u) pair per union entry, NO = sentinel for padding
+__global__ void pack_inv_keys_kernel(PackView pk, int B, uint32_t *__restrict__ keys) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per_b = (int64_t)pk.T * U_MAX;
+    if (p >= (int64_t)B * per_b) return;
+    const int64_t bt = p / U_MAX;
+    const int u = (int)(p - bt * U_MAX);
+    keys[p] = u < pk.tile_u[bt] ? (uint32_t)pk.tile_oct[p] : (uint32_t)pk.NO;
+}
+
+__global__ void pack_inv_finalize_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
+                                         PackView pk, int nseg) {
+    const int b = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nseg) return;
+    const uint32_t *k = skeys + (int64_t)b * nseg;
+    int *off = pk.oct_off + (int64_t)b * (pk.NO + 1);
+    const int key = (int)min(k[p], (uint32_t)pk.NO);
+    const int prev = p ? (int)min(k[p - 1], (uint32_t)pk.NO) : -1;
+    for (int r = prev + 1; r <= key; ++r) off[r] = p;
+    if (p == nseg - 1)
+        for (int r = key + 1; r <= pk.NO; ++r) off[r] = nseg;
+    pk.oct_ent[(int64_t)b * nseg + p] = svals[(int64_t)b * nseg + p];
+}
+
+__global__ void pack_disable_kernel(int *flags) { flags[0] = 1; }
+
+}  // namespace clusten
+
+using namespace clusten;
+
+extern "C" size_t clusten_pack_bytes(int B, int Nq, int M, int Nk) {
+    (void)M;
+    if (B <= 0 || Nq <= 0 || Nk <= 0) return 256;
+    return pack_layout(B, Nq, Nk).total;
+}
+
+extern "C" int clusten_pack_build(const int64_t *nbhd_idx, int B, int Nq, int M, int Nk, void *pack, size_t pack_bytes,
+                                  void *stream) {
+    if (B < 0 || Nq < 0 || M <= 0 || Nk <= 0) return set_error(CLUSTEN_EINVAL, "bad sizes B=%d Nq=%d M=%d Nk=%d", B, Nq, M, Nk);
+    if (!nbhd_idx || !pack) return set_error(CLUSTEN_EINVAL, "null pointer");
+    if (pack_bytes < clusten_pack_bytes(B, Nq, M, Nk))
+        return set_error(CLUSTEN_EWORKSPACE, "pack buffer too small: %zu < %zu", pack_bytes, clusten_pack_bytes(B, Nq, M, Nk));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(pack, 0, 256, st);
+    if (B == 0 || Nq == 0) return check_launch("pack memset");
+    PackView pk = pack_view(pack, B, Nq, Nk);
+    if ((M & 7) || (M >> 3) > S_MAX || (int64_t)pk.T * U_MAX >= (1LL << 31) / 2) {
+        pack_disable_kernel<<<1, 1, 0, st>>>(pk.flags);       // no octet structure: generic kernels only
+        note_launches(1);
+        return check_launch("pack_disable");
+    }
+    const int bt = B * pk.T;
+    pack_tile_kernel<<<ceil_div(bt, PACK_WARPS), PACK_WARPS * 32, 0, st>>>(nbhd_idx, B, Nq, M, Nk, pk);
+    // inverse lists (key octet -> referencing (tile, u)), stable sort keeps ascending tile order -> deterministic sums
+    const PackLayout L = pack_layout(B, Nq, Nk);
+    const int nseg = pk.T * U_MAX;
+    const size_t stride = pack_align((size_t)nseg * B * 4);
+    char *ws = reinterpret_cast<char *>(pack) + L.sort_ws;
+    uint32_t *kA = reinterpret_cast<uint32_t *>(ws);
+    uint32_t *kB = reinterpret_cast<uint32_t *>(ws + stride);
+    uint32_t *vA = reinterpret_cast<uint32_t *>(ws + 2 * stride);
+    uint32_t *vB = reinterpret_cast<uint32_t *>(ws + 3 * stride);
+    uint32_t *kC = reinterpret_cast<uint32_t *>(ws + 4 * stride);
+    void *hist = ws + 5 * stride;
+    pack_inv_keys_kernel<<<ceil_div((int64_t)B * nseg, 256), 256, 0, st>>>(pk, B, kA);
+    int bits = 1;
+    while ((1LL << bits) <= pk.NO) ++bits;
+    if (int e = radix_sort_pairs(kA, nullptr, kB, vB, kC, vA, B, nseg, bits, hist, st)) return e;
+    pack_inv_finalize_kernel<<<dim3(ceil_div(nseg, 256), B), 256, 0, st>>>(kC, vA, pk, nseg);
+    note_launches(3);
+    return check_launch("pack_build");
+}

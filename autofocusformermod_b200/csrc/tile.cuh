@@ -1,0 +1,70 @@
+// Tile pack: the per-index-tensor structure behind the tensor-core ("tile-union") kernels of clusten_tile.cu.
+//
+// Tokens are taken 16 at a time (one mma M-tile).  Key rows are taken 8 at a time ("octets": rows 8o..8o+7 -- a
+// balanced cluster of the reference is m = 8 or 24 consecutive rows, point_utils.py:282-285, so a neighbourhood is
+// M/8 octets).  For every tile the pack holds the UNION of octets its 16 tokens reference and, per (token, union
+// position), the neighbour slot (j / 8) at which the token references that octet, or -1.  A slot is "pure" when
+// idx[i, 8s + r] == 8o + r for r = 0..7; impure slots (padded tails, arbitrary index tensors) are left to the generic
+// kernels: one impure slot, or a tile whose union exceeds U_MAX, switches the WHOLE tensor to the generic path through
+// the device-side flag (no host synchronisation: both kernels are enqueued, one of them exits at once).
+#pragma once
+#include "common.cuh"
+
+namespace clusten {
+
+constexpr int TILE_TOK = 16;     // tokens per tile (mma M)
+constexpr int U_MAX = 48;        // max union octets per tile (measured: <= 18 for m = 8, <= 39 for m = 24 / M = 144)
+constexpr int S_MAX = 32;        // max slots per token (M <= 256)
+
+struct PackView {
+    int *flags;          // [0] != 0 -> generic path; [1] max U seen; [2] impure slots; [3] tiles over U_MAX
+    int *tile_u;         // [B*T]
+    int *tile_oct;       // [B*T*U_MAX]
+    int8_t *slot_of;     // [B*T*16*U_MAX]  slot of (token row, union position) or -1
+    int *oct_off;        // [B*(NO+1)]      inverse lists: for key octet o the (tile, u) pairs referencing it ...
+    uint32_t *oct_ent;   // [B*T*U_MAX]     ... entry = tile*64 + u, ascending tile order
+    int T, NO;
+};
+
+struct Rows4 { const void *p; int64_t sb, sh, sn; };   // strided [B,H,N,C] operand: element strides, unit inner stride
+
+struct PackLayout {
+    size_t flags, tile_u, tile_oct, slot_of, oct_off, oct_ent, sort_ws, total;
+    int T, NO;
+};
+
+inline size_t pack_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+inline PackLayout pack_layout(int B, int Nq, int Nk) {
+    PackLayout L;
+    L.T = (Nq + TILE_TOK - 1) / TILE_TOK;
+    L.NO = (Nk + 7) / 8;
+    const size_t bt = (size_t)B * L.T;
+    size_t o = 0;
+    L.flags = o;    o += 256;
+    L.tile_u = o;   o += pack_align(bt * 4);
+    L.tile_oct = o; o += pack_align(bt * U_MAX * 4);
+    L.slot_of = o;  o += pack_align(bt * TILE_TOK * U_MAX);
+    L.oct_off = o;  o += pack_align((size_t)B * (L.NO + 1) * 4);
+    L.oct_ent = o;  o += pack_align(bt * U_MAX * 4);
+    L.sort_ws = o;  o += 5 * pack_align((size_t)L.T * U_MAX * B * 4) + radix_sort_workspace_bytes(B, L.T * U_MAX) + 256;
+    L.total = o;
+    return L;
+}
+
+inline PackView pack_view(void *buf, int B, int Nq, int Nk) {
+    const PackLayout L = pack_layout(B, Nq, Nk);
+    char *p = reinterpret_cast<char *>(buf);
+    PackView v;
+    v.flags = reinterpret_cast<int *>(p + L.flags);
+    v.tile_u = reinterpret_cast<int *>(p + L.tile_u);
+    v.tile_oct = reinterpret_cast<int *>(p + L.tile_oct);
+    v.slot_of = reinterpret_cast<int8_t *>(p + L.slot_of);
+    v.oct_off = reinterpret_cast<int *>(p + L.oct_off);
+    v.oct_ent = reinterpret_cast<uint32_t *>(p + L.oct_ent);
+    v.T = L.T;
+    v.NO = L.NO;
+    return v;
+}
+
+}  // namespace clusten

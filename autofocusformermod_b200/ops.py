@@ -122,6 +122,40 @@ def inverse_neighbour_list(nbhd_idx, Nk):
     return offsets, entries
 
 
+USE_TILE_KERNELS = True      # False: always the generic row-gather kernels (pack == NULL)
+
+
+def neighbourhood_pack(nbhd_idx, Nk):
+    """Opaque tile pack of clusten_pack_build for this index tensor (uint8 device buffer), cached on the tensor; None
+    when the tile-union kernels are switched off.  The pack decides ON THE DEVICE whether the tensor-core kernels or the
+    generic ones run (no host sync); see ``pack_flags``."""
+    if not USE_TILE_KERNELS:
+        return None
+    cache = getattr(nbhd_idx, "_clusten_pack", None)
+    ver = nbhd_idx._version
+    if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr():
+        return cache[3]
+    B, Nq, M = nbhd_idx.shape
+    dev = nbhd_idx.device
+    nbytes = _lib.lib().clusten_pack_bytes(B, Nq, M, Nk)
+    pack = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _call("clusten_pack_build", dev, nbhd_idx.data_ptr(), B, Nq, M, Nk, pack.data_ptr(), nbytes)
+    try:
+        nbhd_idx._clusten_pack = (ver, Nk, nbhd_idx.data_ptr(), pack)
+    except Exception:  # pragma: no cover
+        pass
+    return pack
+
+
+def pack_flags(nbhd_idx, Nk):
+    """(generic_path, max_union, impure_slots, tiles_over_limit) of the pack -- synchronises; for tests / diagnostics."""
+    pack = neighbourhood_pack(nbhd_idx, Nk)
+    if pack is None:
+        return (1, 0, 0, 0)
+    return tuple(int(x) for x in pack[:16].view(torch.int32).tolist())
+
+
 def _s3(t):
     return t.stride(0), t.stride(1), t.stride(2)
 
@@ -146,7 +180,8 @@ class CLUSTENQKFunction(Function):
         es = query.element_size()
         if attn.numel():
             with torch.cuda.device(dev):
-                _call("clusten_qk_fwd", dev, query.data_ptr(), key.data_ptr(), nbhd_idx.data_ptr(), attn.data_ptr(),
+                _call("clusten_qk_fwd", dev, query.data_ptr(), key.data_ptr(), nbhd_idx.data_ptr(),
+                      _lib.ptr(neighbourhood_pack(nbhd_idx, Nk)), attn.data_ptr(),
                       B, H, Nq, Nk, C, M, *_s3(query), *_s3(key), _lib.dtype_code(query),
                       nbytes=es * (B * H * (Nq + Nk) * C + B * H * Nq * M) + 8 * B * Nq * M)
         ctx.save_for_backward(query, key, nbhd_idx)
@@ -169,7 +204,8 @@ class CLUSTENQKFunction(Function):
         off, ent = inverse_neighbour_list(nbhd_idx, Nk)
         with torch.cuda.device(dev):
             _call("clusten_qk_bwd", dev, grad_attn.data_ptr(), query.data_ptr(), key.data_ptr(), nbhd_idx.data_ptr(),
-                  off.data_ptr(), ent.data_ptr(), d_query.data_ptr(), d_key.data_ptr(), B, H, Nq, Nk, C, M,
+                  off.data_ptr(), ent.data_ptr(), _lib.ptr(neighbourhood_pack(nbhd_idx, Nk)), d_query.data_ptr(),
+                  d_key.data_ptr(), B, H, Nq, Nk, C, M,
                   *_s3(query), *_s3(key), *_s3(d_query), *_s3(d_key), _lib.dtype_code(query),
                   nbytes=query.element_size() * (B * H * Nq * M + 2 * B * H * (Nq + Nk) * C) + 8 * B * Nq * M)
         return d_query, d_key, None
@@ -195,7 +231,8 @@ class CLUSTENAVFunction(Function):
             feat = torch.empty((B, H, Nq, C), dtype=attn.dtype, device=dev)
         if feat.numel():
             with torch.cuda.device(dev):
-                _call("clusten_av_fwd", dev, attn.data_ptr(), v.data_ptr(), nbhd_idx.data_ptr(), feat.data_ptr(),
+                _call("clusten_av_fwd", dev, attn.data_ptr(), v.data_ptr(), nbhd_idx.data_ptr(),
+                      _lib.ptr(neighbourhood_pack(nbhd_idx, Nk)), feat.data_ptr(),
                       B, H, Nq, Nk, C, M, *_s3(attn), *_s3(v), *_s3(feat), _lib.dtype_code(attn),
                       nbytes=attn.element_size() * (B * H * Nq * M + B * H * (Nq + Nk) * C) + 8 * B * Nq * M)
         ctx.save_for_backward(attn, v, nbhd_idx)
@@ -217,7 +254,8 @@ class CLUSTENAVFunction(Function):
         off, ent = inverse_neighbour_list(nbhd_idx, Nk)
         with torch.cuda.device(dev):
             _call("clusten_av_bwd", dev, grad_feat.data_ptr(), attn.data_ptr(), v.data_ptr(), nbhd_idx.data_ptr(),
-                  off.data_ptr(), ent.data_ptr(), d_attn.data_ptr(), d_v.data_ptr(), B, H, Nq, Nk, C, M,
+                  off.data_ptr(), ent.data_ptr(), _lib.ptr(neighbourhood_pack(nbhd_idx, Nk)), d_attn.data_ptr(),
+                  d_v.data_ptr(), B, H, Nq, Nk, C, M,
                   *_s3(grad_feat), *_s3(attn), *_s3(v), *_s3(d_v), _lib.dtype_code(attn),
                   nbytes=attn.element_size() * (2 * B * H * Nq * M + B * H * (Nq + 2 * Nk) * C) + 8 * B * Nq * M)
         return d_attn, d_v, None

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define CLUSTEN_ABI_VERSION 1
+#define CLUSTEN_ABI_VERSION 2
 
 enum { CLUSTEN_F32 = 0, CLUSTEN_F16 = 1, CLUSTEN_BF16 = 2 };
 
@@ -63,8 +63,16 @@ size_t clusten_csr_workspace_bytes(int B, int Nq, int M, int Nk);
 int clusten_csr_build(const int64_t *nbhd_idx, int B, int Nq, int M, int Nk,
                       int32_t *offsets, uint32_t *entries, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- tile pack: per-index-tensor structure behind the tensor-core ("tile-union") kernels.  Built once per index tensor
+ * (it is constant across the blocks of an AFF stage, aff.py:487-493) and passed as `pack` to the QK / AV entry points;
+ * pack == NULL selects the generic row-gather kernels.  The pack carries a device-side flag: index tensors without
+ * octet structure (M % 8 != 0, impure runs, too little locality) fall back to the generic kernels with no host sync. */
+size_t clusten_pack_bytes(int B, int Nq, int M, int Nk);
+int clusten_pack_build(const int64_t *nbhd_idx, int B, int Nq, int M, int Nk, void *pack, size_t pack_bytes, void *stream);
+
 /* ---- QK: attn[b,h,i,j] = sum_c q[b,h,i,c] * k[b,h,idx[b,i,j],c]            (clustenqk_cuda_kernel.cu:38-45) */
-int clusten_qk_fwd(const void *q, const void *k, const int64_t *nbhd_idx, void *attn /* [B,H,Nq,M] contiguous */,
+int clusten_qk_fwd(const void *q, const void *k, const int64_t *nbhd_idx, const void *pack /* or NULL */,
+                   void *attn /* [B,H,Nq,M] contiguous */,
                    int B, int H, int Nq, int Nk, int C, int M,
                    int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t k_sb, int64_t k_sh, int64_t k_sn,
                    int dtype, void *stream);
@@ -72,7 +80,7 @@ int clusten_qk_fwd(const void *q, const void *k, const int64_t *nbhd_idx, void *
  *                                                                        (clustenqk_cuda_kernel.cu:118-128) */
 int clusten_qk_bwd(const void *d_attn /* [B,H,Nq,M] contiguous */, const void *q, const void *k,
                    const int64_t *nbhd_idx, const int32_t *csr_offsets, const uint32_t *csr_entries,
-                   void *d_q, void *d_k,
+                   const void *pack /* or NULL */, void *d_q, void *d_k,
                    int B, int H, int Nq, int Nk, int C, int M,
                    int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t k_sb, int64_t k_sh, int64_t k_sn,
                    int64_t dq_sb, int64_t dq_sh, int64_t dq_sn, int64_t dk_sb, int64_t dk_sh, int64_t dk_sn,
@@ -80,7 +88,7 @@ int clusten_qk_bwd(const void *d_attn /* [B,H,Nq,M] contiguous */, const void *q
 
 /* ---- AV: feat[b,h,i,c] = sum_j attn[b,h,i,j] * v[b,h,idx[b,i,j],c]          (clustenav_cuda_kernel.cu:40-46)
  * attn is addressed base + b*a_sb + h*a_sh + i*a_sn + j (so the attn[..., :-1] slice of aff.py:146 needs no copy). */
-int clusten_av_fwd(const void *attn, const void *v, const int64_t *nbhd_idx, void *feat,
+int clusten_av_fwd(const void *attn, const void *v, const int64_t *nbhd_idx, const void *pack /* or NULL */, void *feat,
                    int B, int H, int Nq, int Nk, int C, int M,
                    int64_t a_sb, int64_t a_sh, int64_t a_sn, int64_t v_sb, int64_t v_sh, int64_t v_sn,
                    int64_t f_sb, int64_t f_sh, int64_t f_sn, int dtype, void *stream);
@@ -88,7 +96,7 @@ int clusten_av_fwd(const void *attn, const void *v, const int64_t *nbhd_idx, voi
  *                                                                 (clustenav_cuda_kernel.cu:117-123,152-156) */
 int clusten_av_bwd(const void *d_feat, const void *attn, const void *v,
                    const int64_t *nbhd_idx, const int32_t *csr_offsets, const uint32_t *csr_entries,
-                   void *d_attn /* [B,H,Nq,M] contiguous */, void *d_v,
+                   const void *pack /* or NULL */, void *d_attn /* [B,H,Nq,M] contiguous */, void *d_v,
                    int B, int H, int Nq, int Nk, int C, int M,
                    int64_t df_sb, int64_t df_sh, int64_t df_sn, int64_t a_sb, int64_t a_sh, int64_t a_sn,
                    int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t dv_sb, int64_t dv_sh, int64_t dv_sn,

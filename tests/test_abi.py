@@ -44,14 +44,14 @@ def test_ctypes_table_mirrors_header(lib):
 
 
 def test_abi_version(lib):
-    assert lib.clusten_abi_version() == 1
+    assert lib.clusten_abi_version() == 2
 
 
 def test_argument_errors_without_gpu(lib):
     # H = 0 -> CLUSTEN_EINVAL before any CUDA call
-    rc = lib.clusten_qk_fwd(1, 1, 1, 1, 1, 0, 4, 4, 8, 4, 0, 0, 0, 0, 0, 0, 0, None)
+    rc = lib.clusten_qk_fwd(1, 1, 1, None, 1, 1, 0, 4, 4, 8, 4, 0, 0, 0, 0, 0, 0, 0, None)
     assert rc == -1 and b"bad sizes" in lib.clusten_last_error()
-    rc = lib.clusten_qk_fwd(1, 1, 1, 1, 1, 1, 4, 4, 8, 4, 0, 0, 0, 0, 0, 0, 7, None)
+    rc = lib.clusten_qk_fwd(1, 1, 1, None, 1, 1, 1, 4, 4, 8, 4, 0, 0, 0, 0, 0, 0, 7, None)
     assert rc == -2                                  # unknown dtype
     rc = lib.clusten_knn(1, 1, 1, 4, 4, 17, 1, None, None)
     assert rc == -3                                  # k > 16

@@ -264,3 +264,47 @@ def test_backbone_scale_properties(shape):
     for t in (a, v):
         rhs = float((t.detach().double() * t.grad.double()).sum())
         assert abs(lhs - rhs) <= 1e-5 * abs(lhs) + 1e-3
+
+
+def test_tile_path_is_taken_for_clustered_idx_and_refused_for_random_idx():
+    """The device-side dispatch flag of the tile pack: curve-ordered octet neighbourhoods run on the tensor-core
+    kernels (flag 0, union <= U_MAX, no impure slot); a random index tensor falls back to the generic kernels."""
+    from autofocusformermod_b200 import ops
+    c = inputs.qkv_case(B=2, H=2, N=4096, C=32, M=48, seed=0, structured=True)
+    generic, max_u, impure, over = ops.pack_flags(c["idx"].cuda(), 4096)
+    assert generic == 0 and impure == 0 and over == 0 and 6 <= max_u <= 48
+    r = inputs.random_neighbourhood(2, 512, 512, 48, seed=1).cuda()
+    assert ops.pack_flags(r, 512)[0] == 1
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
+@pytest.mark.parametrize("H,C", [(2, 16), (3, 32), (16, 24), (4, 8)])
+@pytest.mark.parametrize("n,m,nbhd", [(1024, 8, 48), (2000, 8, 48), (1536, 24, 144)])
+def test_tile_kernels_match_generic_and_oracle(n, m, nbhd, H, C, dtype):
+    """Tensor-core tile path vs the generic row-gather path vs the oracle on the model's own neighbourhood structure
+    (m = 8 / M = 48 and AFF-Base's m = 24 / M = 144), per-head dims 8/16/24/32, ragged last tile (n = 2000)."""
+    from autofocusformermod_b200 import ops
+    P = _ops()
+    B = 2
+    _, idx, _, _ = inputs.structured_neighbourhood(B, n, 64, 64, m, nbhd, seed=n)
+    M = idx.shape[-1]
+    g = torch.Generator().manual_seed(n + C)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dtype).float()
+    q, k, v = rnd(B, H, n, C), rnd(B, H, n, C), rnd(B, H, n, C)
+    attn, d_attn, d_feat = rnd(B, H, n, M).softmax(-1).to(dtype).float(), rnd(B, H, n, M), rnd(B, H, n, C)
+    if n % m == 0:
+        assert ops.pack_flags(idx.cuda(), n)[0] == 0, ops.pack_flags(idx.cuda(), n)
+    tile_qk = _run(P.CLUSTENQKFunction.apply, [q, k, idx], d_attn, dtype)
+    tile_av = _run(P.CLUSTENAVFunction.apply, [attn, v, idx], d_feat, dtype)
+    ops.USE_TILE_KERNELS = False
+    try:
+        gen_qk = _run(P.CLUSTENQKFunction.apply, [q, k, idx], d_attn, dtype)
+        gen_av = _run(P.CLUSTENAVFunction.apply, [attn, v, idx], d_feat, dtype)
+    finally:
+        ops.USE_TILE_KERNELS = True
+    ref_qk = co.fwd_bwd(co.qk_forward, [q, k, idx], d_attn)
+    ref_av = co.fwd_bwd(co.av_forward, [attn, v, idx], d_feat)
+    _check(tile_qk, ref_qk, dtype, "QK tile")
+    _check(tile_av, ref_av, dtype, "AV tile")
+    _check(gen_qk, ref_qk, dtype, "QK generic")
+    _check(gen_av, ref_av, dtype, "AV generic")
