@@ -444,9 +444,269 @@ int launch_axpy_tile(const T *W, const T *Y, const void *pack, T *out, int B, in
     return check_launch("axpy_tile");
 }
 
-// ---- stub until the scatter tile kernel lands ---------------------------------------------------------------------
-template <typename T> bool tile_scat_eligible(int, int, Rows4, Rows4, Rows4) { return false; }
-template <typename T> int launch_scat_tile(const T *, const T *, const void *, T *, int, int, int, int, int, int, Rows4, Rows4, Rows4, cudaStream_t) { return 0; }
+// ---------------------------------------------------------------------------------------------------------------------
+// scatter: out[key rows of octets (o, o+1)][C] = sum over the tiles that reference them of  W-block^T[16 keys x 16 tok] *
+// X-tile[16 tok x C].  One warp owns a PAIR of adjacent key octets (= one mma M-tile of 16 output rows; adjacent octets
+// are referenced by nearly the same tiles) and one head, and walks the merged inverse lists of the pack (ascending tile
+// order -> fixed summation order -> deterministic gradients, no atomics).  Both operands are needed token-major along
+// k, so the X tile (cp.async, double buffered) and the W block are staged in shared memory and read with
+// ldmatrix.trans (16-bit) / conflict-free scalar LDS (fp32, 3xTF32).
+constexpr int TWS = 4;                   // warps per CTA for the scatter kernels (more shared memory per warp)
+
+struct PairCtx {
+    int b, h, o, lane, g, t;
+    int pa, ea, pb, eb;                   // inverse-list cursors of octet o and o + 1
+    const uint32_t *ent;
+};
+
+__device__ __forceinline__ bool pair_ctx(PairCtx &c, const PackView &pk, int B, int H) {
+    const int NP = (pk.NO + 1) >> 1;
+    const int64_t item = (int64_t)blockIdx.x * TWS + (threadIdx.x >> 5);
+    if (item >= (int64_t)B * NP * H) return false;
+    c.lane = threadIdx.x & 31;
+    c.g = c.lane >> 2;
+    c.t = c.lane & 3;
+    c.h = (int)(item % H);
+    const int bp = (int)(item / H);
+    c.b = bp / NP;
+    c.o = (bp - c.b * NP) * 2;
+    const int *off = pk.oct_off + (int64_t)c.b * (pk.NO + 1);
+    c.pa = off[c.o];
+    c.ea = off[c.o + 1];
+    c.pb = c.ea;
+    c.eb = c.o + 1 < pk.NO ? off[c.o + 2] : c.ea;
+    c.ent = pk.oct_ent + (int64_t)c.b * pk.T * U_MAX;
+    return true;
+}
+// next tile of the merged lists; ua / ub = union position of octet o / o+1 in that tile or -1.  Warp-uniform.
+__device__ __forceinline__ bool pair_next(PairCtx &c, int &tile, int &ua, int &ub) {
+    if (c.pa >= c.ea && c.pb >= c.eb) return false;
+    const unsigned ea = c.pa < c.ea ? __ldg(c.ent + c.pa) : 0xffffffffu;
+    const unsigned eb = c.pb < c.eb ? __ldg(c.ent + c.pb) : 0xffffffffu;
+    const unsigned ta = ea == 0xffffffffu ? 0xffffffffu : ea / U_MAX, tb = eb == 0xffffffffu ? 0xffffffffu : eb / U_MAX;
+    const unsigned tm = min(ta, tb);
+    tile = (int)tm;
+    ua = ub = -1;
+    if (ta == tm) { ua = (int)(ea - ta * U_MAX); ++c.pa; }
+    if (tb == tm) { ub = (int)(eb - tb * U_MAX); ++c.pb; }
+    return true;
+}
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(TWS * 32)
+scat_tile16_kernel(const T *__restrict__ W, const T *__restrict__ X, const PackView pk, T *__restrict__ out,
+                   int B, int H, int Nq, int Nk, int C, int M,
+                   int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t x_sb, int64_t x_sh, int64_t x_sn,
+                   int64_t o_sb, int64_t o_sh, int64_t o_sn, int w_al16) {
+    constexpr int ROWB = NT * 16 + 16;                 // X tile row (bytes), padded
+    constexpr int WROWB = 48;                          // W block row: 16 keys x 2 bytes + 16 pad
+    constexpr int CPL = NT / 2;
+    __shared__ __align__(16) unsigned char xs_all[TWS][2][16 * ROWB];
+    __shared__ __align__(16) unsigned char ws_all[TWS][16 * WROWB];
+    if (pk.flags[0]) return;
+    PairCtx c;
+    if (!pair_ctx(c, pk, B, H)) return;
+    unsigned char(*xs)[16 * ROWB] = xs_all[threadIdx.x >> 5];
+    unsigned char *ws = ws_all[threadIdx.x >> 5];
+    const T *xbase = X + c.b * x_sb + c.h * x_sh;
+    const T *wbase = W + c.b * w_sb + c.h * w_sh;
+    float acc[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+
+    auto stage_x = [&](int tile, int which) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            const int ch = c.lane + 32 * j;
+            const int row = ch / NT, blk = ch % NT;
+            const int i = tile * TILE_TOK + row;
+            const bool ok = i < Nq && 8 * blk < C;
+            cp_async16(xs[which] + row * ROWB + blk * 16, ok ? (const void *)(xbase + (int64_t)i * x_sn + 8 * blk) : (const void *)X, ok);
+        }
+        cp_async_commit();
+    };
+
+    int tile, ua, ub, ntile = -1, nua = -1, nub = -1;
+    bool have = pair_next(c, tile, ua, ub);
+    if (have) stage_x(tile, 0);
+    int it = 0;
+    while (have) {
+        const bool more = pair_next(c, ntile, nua, nub);
+        if (more) stage_x(ntile, (it + 1) & 1);
+        // W block: lane -> (token = lane & 15, octet half = lane >> 4): 8 weights of that token for that octet or zeros
+        {
+            const int tok = c.lane & 15, half = c.lane >> 4;
+            const int u = half ? ub : ua;
+            const int i = tile * TILE_TOK + tok;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (u >= 0) {
+                const int s = pk.slot_of[((int64_t)(c.b * pk.T + tile) * TILE_TOK + tok) * U_MAX + u];
+                if (s >= 0) {
+                    const T *wp = wbase + (int64_t)i * w_sn + 8 * s;
+                    if (w_al16) v = __ldg(reinterpret_cast<const uint4 *>(wp));
+                    else {
+                        const unsigned short *hp = reinterpret_cast<const unsigned short *>(wp);
+                        v.x = __ldg(hp) | ((uint32_t)__ldg(hp + 1) << 16);
+                        v.y = __ldg(hp + 2) | ((uint32_t)__ldg(hp + 3) << 16);
+                        v.z = __ldg(hp + 4) | ((uint32_t)__ldg(hp + 5) << 16);
+                        v.w = __ldg(hp + 6) | ((uint32_t)__ldg(hp + 7) << 16);
+                    }
+                }
+            }
+            *reinterpret_cast<uint4 *>(ws + tok * WROWB + half * 16) = v;
+        }
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncwarp();
+        const int mi = c.lane >> 3;
+        uint32_t a[4];
+        // A = W-block^T: matrices (tok 0-7 | keys o), (tok 0-7 | keys o+1), (tok 8-15 | keys o), (tok 8-15 | keys o+1)
+        ldmatrix_x4_trans(a, ws + (((mi >> 1) << 3) + (c.lane & 7)) * WROWB + (mi & 1) * 16);
+        const unsigned char *lrow = xs[it & 1] + (((mi & 1) << 3) + (c.lane & 7)) * ROWB + (mi >> 1) * 16;
+#pragma unroll
+        for (int n = 0; n < NT; n += 2) {
+            uint32_t bfr[4];
+            ldmatrix_x4_trans(bfr, lrow + n * 16);
+            mma16816(acc[n], a[0], a[1], a[2], a[3], bfr[0], bfr[1], T());
+            mma16816(acc[n + 1], a[0], a[1], a[2], a[3], bfr[2], bfr[3], T());
+        }
+        __syncwarp();
+        have = more; tile = ntile; ua = nua; ub = nub; ++it;
+    }
+    const int ka = c.o * 8 + c.g, kb = ka + 8;
+    T *oa = out + c.b * o_sb + c.h * o_sh + (int64_t)ka * o_sn + 2 * c.t;
+    T *ob = oa + 8 * o_sn;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        if (8 * n + 2 * c.t < C) {
+            if (ka < Nk) store_pair<T>(oa + 8 * n, acc[n][0], acc[n][1]);
+            if (kb < Nk) store_pair<T>(ob + 8 * n, acc[n][2], acc[n][3]);
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(TWS * 32)
+scat_tile32_kernel(const float *__restrict__ W, const float *__restrict__ X, const PackView pk, float *__restrict__ out,
+                   int B, int H, int Nq, int Nk, int C, int M,
+                   int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t x_sb, int64_t x_sh, int64_t x_sn,
+                   int64_t o_sb, int64_t o_sh, int64_t o_sn, int w_al16) {
+    constexpr int RS = NT * 8 + 8;                     // X tile row stride (floats)
+    constexpr int WRS = 24;                            // W block row stride: 16 keys + 8 pad
+    constexpr int CPL = NT;                            // 16 rows x 2 NT chunks of 4 floats / 32 lanes
+    __shared__ __align__(16) float xs_all[TWS][2][16 * RS];
+    __shared__ __align__(16) float ws_all[TWS][16 * WRS];
+    if (pk.flags[0]) return;
+    PairCtx c;
+    if (!pair_ctx(c, pk, B, H)) return;
+    float(*xs)[16 * RS] = xs_all[threadIdx.x >> 5];
+    float *ws = ws_all[threadIdx.x >> 5];
+    const float *xbase = X + c.b * x_sb + c.h * x_sh;
+    const float *wbase = W + c.b * w_sb + c.h * w_sh;
+    float acc[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+
+    auto stage_x = [&](int tile, int which) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            const int ch = c.lane + 32 * j;
+            const int row = ch / (2 * NT), blk = ch % (2 * NT);
+            const int i = tile * TILE_TOK + row;
+            const bool ok = i < Nq && 4 * blk < C;
+            cp_async16(xs[which] + row * RS + blk * 4, ok ? (const void *)(xbase + (int64_t)i * x_sn + 4 * blk) : (const void *)X, ok);
+        }
+        cp_async_commit();
+    };
+
+    int tile, ua, ub, ntile = -1, nua = -1, nub = -1;
+    bool have = pair_next(c, tile, ua, ub);
+    if (have) stage_x(tile, 0);
+    int it = 0;
+    while (have) {
+        const bool more = pair_next(c, ntile, nua, nub);
+        if (more) stage_x(ntile, (it + 1) & 1);
+        {
+            const int tok = c.lane & 15, half = c.lane >> 4;
+            const int u = half ? ub : ua;
+            const int i = tile * TILE_TOK + tok;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (u >= 0) {
+                const int s = pk.slot_of[((int64_t)(c.b * pk.T + tile) * TILE_TOK + tok) * U_MAX + u];
+                if (s >= 0) {
+                    const float *wp = wbase + (int64_t)i * w_sn + 8 * s;
+                    if (w_al16) {
+                        v0 = __ldg(reinterpret_cast<const float4 *>(wp));
+                        v1 = __ldg(reinterpret_cast<const float4 *>(wp) + 1);
+                    } else {
+                        v0 = make_float4(__ldg(wp), __ldg(wp + 1), __ldg(wp + 2), __ldg(wp + 3));
+                        v1 = make_float4(__ldg(wp + 4), __ldg(wp + 5), __ldg(wp + 6), __ldg(wp + 7));
+                    }
+                }
+            }
+            float4 *dst = reinterpret_cast<float4 *>(ws + tok * WRS + half * 8);
+            dst[0] = v0;
+            dst[1] = v1;
+        }
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncwarp();
+        const float *xb = xs[it & 1];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {               // k-step = 8 tokens
+            uint32_t ah[4], al[4];
+            const float *wr = ws + (8 * ks + c.t) * WRS + c.g;
+            tf32_split(wr[0], ah[0], al[0]);                     // (row = key g of o,     k = tok t)
+            tf32_split(wr[8], ah[1], al[1]);                     // (row = key g of o + 1, k = tok t)
+            tf32_split(wr[4 * WRS], ah[2], al[2]);               // k = tok t + 4
+            tf32_split(wr[4 * WRS + 8], ah[3], al[3]);
+            const float *bp = xb + (8 * ks + c.t) * RS + c.g;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                uint32_t b0h, b0l, b1h, b1l;
+                tf32_split(bp[8 * n], b0h, b0l);
+                tf32_split(bp[4 * RS + 8 * n], b1h, b1l);
+                mma_3xtf32(acc[n], ah, al, b0h, b1h, b0l, b1l);
+            }
+        }
+        __syncwarp();
+        have = more; tile = ntile; ua = nua; ub = nub; ++it;
+    }
+    const int ka = c.o * 8 + c.g, kb = ka + 8;
+    float *oa = out + c.b * o_sb + c.h * o_sh + (int64_t)ka * o_sn + 2 * c.t;
+    float *ob = oa + 8 * o_sn;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        if (8 * n + 2 * c.t < C) {
+            if (ka < Nk) store_pair<float>(oa + 8 * n, acc[n][0], acc[n][1]);
+            if (kb < Nk) store_pair<float>(ob + 8 * n, acc[n][2], acc[n][3]);
+        }
+    }
+}
+
+template <typename T> bool tile_scat_eligible(int C, int M, Rows4 w, Rows4 x, Rows4 o) {
+    (void)w;
+    return tile_shape_ok<T>(C, M) && rows_ok<T>(x) && rows_ok<T>(o);
+}
+
+template <typename T>
+int launch_scat_tile(const T *W, const T *X, const void *pack, T *out, int B, int H, int Nq, int Nk, int C, int M,
+                     Rows4 w, Rows4 x, Rows4 o, cudaStream_t st) {
+    const PackView pk = pack_view(const_cast<void *>(pack), B, Nq, Nk);
+    const int64_t items = (int64_t)B * ((pk.NO + 1) / 2) * H;
+    if (items == 0) return 0;
+    const int grid = ceil_div(items, TWS);
+    constexpr int VPT = 16 / sizeof(T);
+    const int al16 = (aligned16(w.p) && w.sb % VPT == 0 && w.sh % VPT == 0 && w.sn % VPT == 0) ? 1 : 0;
+    if constexpr (sizeof(T) == 2) {
+        if (C <= 16) scat_tile16_kernel<T, 2><<<grid, TWS * 32, 0, st>>>(W, X, pk, out, B, H, Nq, Nk, C, M, w.sb, w.sh, w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn, al16);
+        else scat_tile16_kernel<T, 4><<<grid, TWS * 32, 0, st>>>(W, X, pk, out, B, H, Nq, Nk, C, M, w.sb, w.sh, w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn, al16);
+    } else {
+        if (C <= 16) scat_tile32_kernel<2><<<grid, TWS * 32, 0, st>>>(W, X, pk, out, B, H, Nq, Nk, C, M, w.sb, w.sh, w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn, al16);
+        else scat_tile32_kernel<4><<<grid, TWS * 32, 0, st>>>(W, X, pk, out, B, H, Nq, Nk, C, M, w.sb, w.sh, w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn, al16);
+    }
+    note_launches(1);
+    return check_launch("scat_tile");
+}
+
 #define INST(T) \
     template bool tile_axpy_eligible<T>(int, int, Rows4, Rows4, Rows4); \
     template bool tile_scat_eligible<T>(int, int, Rows4, Rows4, Rows4); \
