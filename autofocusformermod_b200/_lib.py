@@ -21,9 +21,10 @@ SIGNATURES = {
     "clusten_last_error": (_c.c_char_p, []),
     "clusten_kernel_launches": (_c.c_longlong, []),
     "clusten_csr_workspace_bytes": (_Z, [_I] * 4),
-    "clusten_csr_build": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    "clusten_csr_build": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _P, _P]),
     "clusten_pack_bytes": (_Z, [_I] * 4),
     "clusten_pack_build": (_I, [_P, _I, _I, _I, _I, _P, _Z, _P]),
+    "clusten_pack_inverse": (_I, [_P, _Z, _I, _I, _I, _I, _P]),
     "clusten_qk_fwd": (_I, [_P] * 5 + [_I] * 6 + [_L] * 6 + [_I, _P]),
     "clusten_qk_bwd": (_I, [_P] * 9 + [_I] * 6 + [_L] * 12 + [_I, _P]),
     "clusten_av_fwd": (_I, [_P] * 5 + [_I] * 6 + [_L] * 9 + [_I, _P]),

@@ -30,14 +30,16 @@ dot_rows_kernel(const T *__restrict__ X, const T *__restrict__ Y, const int64_t 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int *idx_s = smem_i + warp * 2 * M;
     float *out_s = reinterpret_cast<float *>(idx_s + M);
-    const int64_t tok = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;   // b * Nq + i
-    if (tok >= (int64_t)B * Nq) return;
-    const int b = (int)(tok / Nq), i = (int)(tok - (int64_t)b * Nq);
-    const int64_t *irow = idx + tok * M;
-    for (int j = lane; j < M; j += 32) idx_s[j] = (int)irow[j];
-    __syncwarp();
     const int grp = lane / G, lg = lane % G;
     const bool act = lg < nchunk;
+    // grid-stride over tokens (b * Nq + i): one pass when the grid covers them all, a short grid when this launch is
+    // only the fallback of the tile-union kernel
+    for (int64_t tok = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; tok < (int64_t)B * Nq; tok += (int64_t)gridDim.x * WARPS_PER_CTA) {
+    const int b = (int)(tok / Nq), i = (int)(tok - (int64_t)b * Nq);
+    const int64_t *irow = idx + tok * M;
+    __syncwarp();
+    for (int j = lane; j < M; j += 32) idx_s[j] = (int)irow[j];
+    __syncwarp();
     for (int h = 0; h < H; ++h) {
         float xf[VPT];
 #pragma unroll
@@ -68,6 +70,7 @@ dot_rows_kernel(const T *__restrict__ X, const T *__restrict__ Y, const int64_t 
         for (int j = lane; j < M; j += 32) orow[j] = from_f<T>(out_s[j]);
         __syncwarp();
     }
+    }
 }
 
 template <typename T, int G>
@@ -83,13 +86,13 @@ axpy_rows_kernel(const T *__restrict__ W, const T *__restrict__ Y, const int64_t
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int *idx_s = smem_i + warp * 2 * M;
     float *w_s = reinterpret_cast<float *>(idx_s + M);
-    const int64_t tok = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
-    if (tok >= (int64_t)B * Nq) return;
-    const int b = (int)(tok / Nq), i = (int)(tok - (int64_t)b * Nq);
-    const int64_t *irow = idx + tok * M;
-    for (int j = lane; j < M; j += 32) idx_s[j] = (int)irow[j];
     const int grp = lane / G, lg = lane % G;
     const bool act = lg < nchunk;
+    for (int64_t tok = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; tok < (int64_t)B * Nq; tok += (int64_t)gridDim.x * WARPS_PER_CTA) {
+    const int b = (int)(tok / Nq), i = (int)(tok - (int64_t)b * Nq);
+    const int64_t *irow = idx + tok * M;
+    __syncwarp();
+    for (int j = lane; j < M; j += 32) idx_s[j] = (int)irow[j];
     for (int h = 0; h < H; ++h) {
         __syncwarp();
         const T *wrow = W + b * w_sb + h * w_sh + (int64_t)i * w_sn;
@@ -122,6 +125,7 @@ axpy_rows_kernel(const T *__restrict__ W, const T *__restrict__ Y, const int64_t
         for (int v = 0; v < VPT; ++v) acc[v] = cross_group_sum<G>(acc[v]);
         if (grp == 0 && act) store16(out + b * o_sb + h * o_sh + (int64_t)i * o_sn + lg * VPT, acc);
     }
+    }
 }
 
 template <typename T, int G>
@@ -135,13 +139,12 @@ csr_rows_kernel(const T *__restrict__ W, const T *__restrict__ X, const int32_t 
     constexpr int VPT = Vec<T>::VPT;
     constexpr int RPI = 32 / G;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;   // b * Nk + r
-    if (row >= (int64_t)B * Nk) return;
+    const int grp = lane / G, lg = lane % G;
+    const bool act = lg < nchunk;
+    for (int64_t row = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; row < (int64_t)B * Nk; row += (int64_t)gridDim.x * WARPS_PER_CTA) {   // b * Nk + r
     const int b = (int)(row / Nk), r = (int)(row - (int64_t)b * Nk);
     const int lo = offsets[(int64_t)b * (Nk + 1) + r], hi = offsets[(int64_t)b * (Nk + 1) + r + 1];
     const uint32_t *ent = entries + (int64_t)b * Nq * M;
-    const int grp = lane / G, lg = lane % G;
-    const bool act = lg < nchunk;
     for (int h = 0; h < H; ++h) {
         float acc[VPT];
 #pragma unroll
@@ -173,6 +176,7 @@ csr_rows_kernel(const T *__restrict__ W, const T *__restrict__ X, const int32_t 
         for (int v = 0; v < VPT; ++v) acc[v] = cross_group_sum<G>(acc[v]);
         if (grp == 0 && act) store16(out + b * o_sb + h * o_sh + (int64_t)r * o_sn + lg * VPT, acc);
     }
+    }
 }
 
 // ---- scalar fallbacks: any C / stride / alignment; one thread per output element -------------------------------
@@ -181,8 +185,7 @@ __global__ void dot_rows_scalar(const T *X, const T *Y, const int64_t *idx, T *o
                                 int64_t x_sb, int64_t x_sh, int64_t x_sn, int64_t y_sb, int64_t y_sh, int64_t y_sn,
                                 const int *tile_flag) {
     if (tile_flag && tile_flag[0] == 0) return;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)B * H * Nq * M) return;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)B * H * Nq * M; t += (int64_t)gridDim.x * blockDim.x) {
     const int j = (int)(t % M);
     const int64_t u = t / M;
     const int i = (int)(u % Nq);
@@ -192,14 +195,14 @@ __global__ void dot_rows_scalar(const T *X, const T *Y, const int64_t *idx, T *o
     float s = 0.f;
     for (int c = 0; c < C; ++c) s = fmaf(to_f(x[c]), to_f(y[c]), s);
     out[t] = from_f<T>(s);
+    }
 }
 template <typename T>
 __global__ void axpy_rows_scalar(const T *W, const T *Y, const int64_t *idx, T *out, int B, int H, int Nq, int C, int M,
                                  int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t y_sb, int64_t y_sh, int64_t y_sn,
                                  int64_t o_sb, int64_t o_sh, int64_t o_sn, const int *tile_flag) {
     if (tile_flag && tile_flag[0] == 0) return;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)B * H * Nq * C) return;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)B * H * Nq * C; t += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(t % C);
     const int64_t u = t / C;
     const int i = (int)(u % Nq);
@@ -210,6 +213,7 @@ __global__ void axpy_rows_scalar(const T *W, const T *Y, const int64_t *idx, T *
     float s = 0.f;
     for (int j = 0; j < M; ++j) s = fmaf(to_f(w[j]), to_f(y[ir[j] * y_sn]), s);
     out[b * o_sb + h * o_sh + (int64_t)i * o_sn + c] = from_f<T>(s);
+    }
 }
 template <typename T>
 __global__ void csr_rows_scalar(const T *W, const T *X, const int32_t *offsets, const uint32_t *entries, T *out,
@@ -217,8 +221,7 @@ __global__ void csr_rows_scalar(const T *W, const T *X, const int32_t *offsets, 
                                 int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t x_sb, int64_t x_sh, int64_t x_sn,
                                 int64_t o_sb, int64_t o_sh, int64_t o_sn, const int *tile_flag) {
     if (tile_flag && tile_flag[0] == 0) return;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)B * H * Nk * C) return;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)B * H * Nk * C; t += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(t % C);
     const int64_t u = t / C;
     const int r = (int)(u % Nk);
@@ -232,6 +235,7 @@ __global__ void csr_rows_scalar(const T *W, const T *X, const int32_t *offsets, 
         s = fmaf(to_f(W[b * w_sb + h * w_sh + qi * w_sn + (pk & 255u)]), to_f(X[b * x_sb + h * x_sh + qi * x_sn + c]), s);
     }
     out[b * o_sb + h * o_sh + (int64_t)r * o_sn + c] = from_f<T>(s);
+    }
 }
 
 // ---- host-side launchers --------------------------------------------------------------------------------------
@@ -249,6 +253,9 @@ template <typename T> int launch_scat_tile(const T *W, const T *X, const void *p
 
 static inline Rows4 r4(const Rows &r) { return Rows4{r.p, r.sb, r.sh, r.sn}; }
 static inline const int *tile_flag_of(const void *pack) { return reinterpret_cast<const int *>(pack); }   // PackView.flags is at offset 0
+// grid of a generic kernel: everything when it is the only kernel, a short grid-stride grid when it is the (usually
+// idle) fallback of a tile-union launch, so that skipping it costs microseconds
+static inline int fallback_grid(int full, const int *flag) { return flag ? (full < 148 * 8 ? full : 148 * 8) : full; }
 
 template <typename T> static bool vec_ok(int C, std::initializer_list<Rows> rows) {
     constexpr int VPT = Vec<T>::VPT;
@@ -279,14 +286,14 @@ static int launch_dot(const T *X, const T *Y, const int64_t *idx, const void *pa
     }
     if (vec_ok<T>(C, {x, y})) {
         const int nchunk = C / Vec<T>::VPT;
-        const int grid = ceil_div((int64_t)B * Nq, WARPS_PER_CTA);
+        const int grid = fallback_grid(ceil_div((int64_t)B * Nq, WARPS_PER_CTA), flag);
         const size_t smem = (size_t)WARPS_PER_CTA * 2 * M * sizeof(int);
         CLUSTEN_DISPATCH_GROUP(pick_group(nchunk),
             (dot_rows_kernel<T, G><<<grid, CTA_THREADS, smem, st>>>(X, Y, idx, out, B, H, Nq, nchunk, M,
                                                                      x.sb, x.sh, x.sn, y.sb, y.sh, y.sn, flag)));
     } else {
         const int64_t total = (int64_t)B * H * Nq * M;
-        dot_rows_scalar<T><<<ceil_div(total, 256), 256, 0, st>>>(X, Y, idx, out, B, H, Nq, C, M,
+        dot_rows_scalar<T><<<fallback_grid(ceil_div(total, 256), flag), 256, 0, st>>>(X, Y, idx, out, B, H, Nq, C, M,
                                                                  x.sb, x.sh, x.sn, y.sb, y.sh, y.sn, flag);
     }
     note_launches(1);
@@ -304,7 +311,7 @@ static int launch_axpy(const T *W, const T *Y, const int64_t *idx, const void *p
     }
     if (vec_ok<T>(C, {y, o})) {
         const int nchunk = C / Vec<T>::VPT;
-        const int grid = ceil_div((int64_t)B * Nq, WARPS_PER_CTA);
+        const int grid = fallback_grid(ceil_div((int64_t)B * Nq, WARPS_PER_CTA), flag);
         const size_t smem = (size_t)WARPS_PER_CTA * 2 * M * sizeof(int);
         CLUSTEN_DISPATCH_GROUP(pick_group(nchunk),
             (axpy_rows_kernel<T, G><<<grid, CTA_THREADS, smem, st>>>(W, Y, idx, out, B, H, Nq, nchunk, M,
@@ -312,7 +319,7 @@ static int launch_axpy(const T *W, const T *Y, const int64_t *idx, const void *p
                                                                       o.sb, o.sh, o.sn, flag)));
     } else {
         const int64_t total = (int64_t)B * H * Nq * C;
-        axpy_rows_scalar<T><<<ceil_div(total, 256), 256, 0, st>>>(W, Y, idx, out, B, H, Nq, C, M, w.sb, w.sh, w.sn,
+        axpy_rows_scalar<T><<<fallback_grid(ceil_div(total, 256), flag), 256, 0, st>>>(W, Y, idx, out, B, H, Nq, C, M, w.sb, w.sh, w.sn,
                                                                   y.sb, y.sh, y.sn, o.sb, o.sh, o.sn, flag);
     }
     note_launches(1);
@@ -330,14 +337,14 @@ static int launch_csr(const T *W, const T *X, const int32_t *off, const uint32_t
     }
     if (vec_ok<T>(C, {x, o})) {
         const int nchunk = C / Vec<T>::VPT;
-        const int grid = ceil_div((int64_t)B * Nk, WARPS_PER_CTA);
+        const int grid = fallback_grid(ceil_div((int64_t)B * Nk, WARPS_PER_CTA), flag);
         CLUSTEN_DISPATCH_GROUP(pick_group(nchunk),
             (csr_rows_kernel<T, G><<<grid, CTA_THREADS, 0, st>>>(W, X, off, ent, out, B, H, Nq, Nk, nchunk, M,
                                                                   w.sb, w.sh, w.sn, x.sb, x.sh, x.sn,
                                                                   o.sb, o.sh, o.sn, flag)));
     } else {
         const int64_t total = (int64_t)B * H * Nk * C;
-        csr_rows_scalar<T><<<ceil_div(total, 256), 256, 0, st>>>(W, X, off, ent, out, B, H, Nq, Nk, C, M, w.sb, w.sh,
+        csr_rows_scalar<T><<<fallback_grid(ceil_div(total, 256), flag), 256, 0, st>>>(W, X, off, ent, out, B, H, Nq, Nk, C, M, w.sb, w.sh,
                                                                  w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn, flag);
     }
     note_launches(1);

@@ -87,9 +87,10 @@ size_t radix_sort_workspace_bytes(int B, int n);          // histogram scratch o
 // Stable LSD radix sort of B segments of n (key,val) pairs over key bits [0, key_bits).
 // vals_in == nullptr -> implicit iota (val = position within segment).  Result lands in (keys_out, vals_out);
 // (keys_tmp, vals_tmp) and (keys_in) are scratch / clobbered.  All buffers B*n uint32.
+// skip_if_zero != nullptr: every kernel of the sort exits at once when skip_if_zero[0] == 0 (device-side dispatch).
 int radix_sort_pairs(uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_tmp, uint32_t *vals_tmp,
                      uint32_t *keys_out, uint32_t *vals_out, int B, int n, int key_bits,
-                     void *hist_ws, cudaStream_t stream);
+                     void *hist_ws, cudaStream_t stream, const int *skip_if_zero = nullptr);
 
 }  // namespace clusten
 

@@ -36,7 +36,8 @@ int check_launch(const char *what) {
     return 0;
 }
 
-__global__ void csr_keys_kernel(const int64_t *__restrict__ idx, uint32_t *__restrict__ keys, int64_t total) {
+__global__ void csr_keys_kernel(const int64_t *__restrict__ idx, uint32_t *__restrict__ keys, int64_t total, const int *skip) {
+    if (skip && skip[0] == 0) return;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < total) keys[p] = (uint32_t)idx[p];
 }
@@ -44,7 +45,8 @@ __global__ void csr_keys_kernel(const int64_t *__restrict__ idx, uint32_t *__res
 // sorted keys/vals of one segment -> row offsets + packed entries
 __global__ void csr_finalize_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
                                     int32_t *__restrict__ offsets, uint32_t *__restrict__ entries,
-                                    int nseg, int Nk, int M) {
+                                    int nseg, int Nk, int M, const int *skip) {
+    if (skip && skip[0] == 0) return;
     const int b = blockIdx.y;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= nseg) return;
@@ -77,7 +79,7 @@ extern "C" size_t clusten_csr_workspace_bytes(int B, int Nq, int M, int Nk) {
 }
 
 extern "C" int clusten_csr_build(const int64_t *nbhd_idx, int B, int Nq, int M, int Nk, int32_t *offsets,
-                                 uint32_t *entries, void *workspace, size_t workspace_bytes, void *stream) {
+                                 uint32_t *entries, void *workspace, size_t workspace_bytes, const void *pack, void *stream) {
     if (B < 0 || Nq < 0 || M <= 0 || Nk <= 0) return set_error(CLUSTEN_EINVAL, "bad sizes B=%d Nq=%d M=%d Nk=%d", B, Nq, M, Nk);
     if (M > 256 || Nq >= (1 << 24) || (int64_t)Nq * M >= (1LL << 31))
         return set_error(CLUSTEN_EUNSUPPORTED, "csr needs M <= 256, Nq < 2^24, Nq*M < 2^31 (M=%d Nq=%d)", M, Nq);
@@ -87,6 +89,9 @@ extern "C" int clusten_csr_build(const int64_t *nbhd_idx, int B, int Nq, int M, 
                          clusten_csr_workspace_bytes(B, Nq, M, Nk));
     cudaStream_t st = (cudaStream_t)stream;
     if (B == 0) return 0;
+    // with a tile pack the list is only needed when the pack routes to the generic kernels (flag != 0): every kernel
+    // below exits at once otherwise -- decided on the device, no host synchronisation
+    const int *skip = reinterpret_cast<const int *>(pack);
     const int nseg = Nq * M;
     if (nseg == 0) {
         cudaMemsetAsync(offsets, 0, (size_t)B * (Nk + 1) * sizeof(int32_t), st);
@@ -100,14 +105,14 @@ extern "C" int clusten_csr_build(const int64_t *nbhd_idx, int B, int Nq, int M, 
     uint32_t *vA = reinterpret_cast<uint32_t *>(ws + 2 * stride);
     uint32_t *vB = reinterpret_cast<uint32_t *>(ws + 3 * stride);
     void *hist = ws + 4 * stride;
-    csr_keys_kernel<<<ceil_div((int64_t)tot, 256), 256, 0, st>>>(nbhd_idx, kA, (int64_t)tot);
+    csr_keys_kernel<<<ceil_div((int64_t)tot, 256), 256, 0, st>>>(nbhd_idx, kA, (int64_t)tot, skip);
     // an EVEN number of passes lets the sorted keys land back in kA (see radix_sort_pairs ping-pong)
     int bits = 1;
     while ((1LL << bits) < Nk) ++bits;
     const int passes = bits <= 16 ? 2 : 4;
-    if (int e = radix_sort_pairs(kA, nullptr, kB, vB, kA, vA, B, nseg, passes * 8, hist, st)) return e;
+    if (int e = radix_sort_pairs(kA, nullptr, kB, vB, kA, vA, B, nseg, passes * 8, hist, st, skip)) return e;
     const dim3 grid(ceil_div(nseg, 256), B);
-    csr_finalize_kernel<<<grid, 256, 0, st>>>(kA, vA, offsets, entries, nseg, Nk, M);
+    csr_finalize_kernel<<<grid, 256, 0, st>>>(kA, vA, offsets, entries, nseg, Nk, M, skip);
     note_launches(2);
     return check_launch("csr_build");
 }

@@ -127,6 +127,18 @@ extern "C" int clusten_pack_build(const int64_t *nbhd_idx, int B, int Nq, int M,
     }
     const int bt = B * pk.T;
     pack_tile_kernel<<<ceil_div(bt, PACK_WARPS), PACK_WARPS * 32, 0, st>>>(nbhd_idx, B, Nq, M, Nk, pk);
+    note_launches(1);
+    return check_launch("pack_build");
+}
+
+extern "C" int clusten_pack_inverse(void *pack, size_t pack_bytes, int B, int Nq, int M, int Nk, void *stream) {
+    if (B < 0 || Nq < 0 || M <= 0 || Nk <= 0) return set_error(CLUSTEN_EINVAL, "bad sizes B=%d Nq=%d M=%d Nk=%d", B, Nq, M, Nk);
+    if (!pack) return set_error(CLUSTEN_EINVAL, "null pointer");
+    if (pack_bytes < clusten_pack_bytes(B, Nq, M, Nk)) return set_error(CLUSTEN_EWORKSPACE, "pack buffer too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0 || Nq == 0) return 0;
+    PackView pk = pack_view(pack, B, Nq, Nk);
+    if ((M & 7) || (M >> 3) > S_MAX || (int64_t)pk.T * U_MAX >= (1LL << 31) / 2) return 0;   // generic-only pack
     // inverse lists (key octet -> referencing (tile, u)), stable sort keeps ascending tile order -> deterministic sums
     const PackLayout L = pack_layout(B, Nq, Nk);
     const int nseg = pk.T * U_MAX;
@@ -143,6 +155,6 @@ extern "C" int clusten_pack_build(const int64_t *nbhd_idx, int B, int Nq, int M,
     while ((1LL << bits) <= pk.NO) ++bits;
     if (int e = radix_sort_pairs(kA, nullptr, kB, vB, kC, vA, B, nseg, bits, hist, st)) return e;
     pack_inv_finalize_kernel<<<dim3(ceil_div(nseg, 256), B), 256, 0, st>>>(kC, vA, pk, nseg);
-    note_launches(3);
-    return check_launch("pack_build");
+    note_launches(2);
+    return check_launch("pack_inverse");
 }

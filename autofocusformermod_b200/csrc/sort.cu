@@ -23,7 +23,8 @@ size_t radix_sort_workspace_bytes(int B, int n) {
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
-rs_hist_kernel(const uint32_t *__restrict__ keys, int n, int shift, int *__restrict__ hist, int T) {
+rs_hist_kernel(const uint32_t *__restrict__ keys, int n, int shift, int *__restrict__ hist, int T, const int *skip) {
+    if (skip && skip[0] == 0) return;
     __shared__ int h[RS_RADIX];
     const int t = blockIdx.x, b = blockIdx.y;
     h[threadIdx.x] = 0;
@@ -40,7 +41,8 @@ rs_hist_kernel(const uint32_t *__restrict__ keys, int n, int shift, int *__restr
 }
 
 // exclusive scan of L = 256*T ints per segment, in place; one CTA of 1024 threads per segment
-__global__ void __launch_bounds__(1024) rs_scan_kernel(int *__restrict__ hist, int L) {
+__global__ void __launch_bounds__(1024) rs_scan_kernel(int *__restrict__ hist, int L, const int *skip) {
+    if (skip && skip[0] == 0) return;
     __shared__ int warp_tot[32];
     __shared__ int carry_s;
     int *a = hist + (int64_t)blockIdx.x * L;
@@ -80,7 +82,8 @@ __global__ void __launch_bounds__(1024) rs_scan_kernel(int *__restrict__ hist, i
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                   uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
-                  int n, int shift, const int *__restrict__ hist, int T) {
+                  int n, int shift, const int *__restrict__ hist, int T, const int *skip) {
+    if (skip && skip[0] == 0) return;
     __shared__ int cnt[RS_WARPS][RS_RADIX + 1];
     __shared__ int base_s[RS_WARPS][RS_RADIX];
     const int t = blockIdx.x, b = blockIdx.y;
@@ -134,7 +137,7 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
 
 int radix_sort_pairs(uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_tmp, uint32_t *vals_tmp,
                      uint32_t *keys_out, uint32_t *vals_out, int B, int n, int key_bits,
-                     void *hist_ws, cudaStream_t st) {
+                     void *hist_ws, cudaStream_t st, const int *skip) {
     if (B <= 0 || n <= 0) return 0;
     const int passes = key_bits <= 0 ? 1 : (key_bits + 7) / 8;
     const int T = rs_tiles(n);
@@ -147,9 +150,9 @@ int radix_sort_pairs(uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_
         const bool to_out = ((passes - 1 - p) % 2) == 0;
         uint32_t *ko = to_out ? keys_out : keys_tmp;
         uint32_t *vo = to_out ? vals_out : vals_tmp;
-        rs_hist_kernel<<<grid, RS_THREADS, 0, st>>>(kin, n, 8 * p, hist, T);
-        rs_scan_kernel<<<B, 1024, 0, st>>>(hist, RS_RADIX * T);
-        rs_scatter_kernel<<<grid, RS_THREADS, 0, st>>>(kin, vin, ko, vo, n, 8 * p, hist, T);
+        rs_hist_kernel<<<grid, RS_THREADS, 0, st>>>(kin, n, 8 * p, hist, T, skip);
+        rs_scan_kernel<<<B, 1024, 0, st>>>(hist, RS_RADIX * T, skip);
+        rs_scatter_kernel<<<grid, RS_THREADS, 0, st>>>(kin, vin, ko, vo, n, 8 * p, hist, T, skip);
         note_launches(3);
         kin = ko;
         vin = vo;

@@ -103,20 +103,22 @@ def inverse_neighbour_list(nbhd_idx, Nk):
     """(offsets int32 [B,Nk+1], entries uint32-as-int32 [B,Nq*M]) of clusten_csr_build, cached on the index tensor."""
     cache = getattr(nbhd_idx, "_clusten_csr", None)
     ver = nbhd_idx._version
-    if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr():
+    pack = neighbourhood_pack(nbhd_idx, Nk)
+    # (a list built beside a pack may have been skipped on the device: never reuse it for a pack-less call)
+    if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr() and cache[5] == (pack is not None):
         return cache[3], cache[4]
     B, Nq, M = nbhd_idx.shape
     dev = nbhd_idx.device
     L = _lib.lib()
-    offsets = torch.empty((B, Nk + 1), dtype=torch.int32, device=dev)
-    entries = torch.empty((B, max(Nq * M, 1)), dtype=torch.int32, device=dev)
+    offsets = torch.zeros((B, Nk + 1), dtype=torch.int32, device=dev)     # zeros: stays a valid (empty) list when the
+    entries = torch.empty((B, max(Nq * M, 1)), dtype=torch.int32, device=dev)   # build is skipped on the device
     ws_bytes = L.clusten_csr_workspace_bytes(B, Nq, M, Nk)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _call("clusten_csr_build", dev, nbhd_idx.data_ptr(), B, Nq, M, Nk, offsets.data_ptr(), entries.data_ptr(),
-              ws.data_ptr(), ws_bytes)
+              ws.data_ptr(), ws_bytes, _lib.ptr(pack))
     try:
-        nbhd_idx._clusten_csr = (ver, Nk, nbhd_idx.data_ptr(), offsets, entries)
+        nbhd_idx._clusten_csr = (ver, Nk, nbhd_idx.data_ptr(), offsets, entries, pack is not None)
     except Exception:  # pragma: no cover  (tensor subclass without __dict__)
         pass
     return offsets, entries
@@ -125,7 +127,7 @@ def inverse_neighbour_list(nbhd_idx, Nk):
 USE_TILE_KERNELS = True      # False: always the generic row-gather kernels (pack == NULL)
 
 
-def neighbourhood_pack(nbhd_idx, Nk):
+def neighbourhood_pack(nbhd_idx, Nk, inverse=False):
     """Opaque tile pack of clusten_pack_build for this index tensor (uint8 device buffer), cached on the tensor; None
     when the tile-union kernels are switched off.  The pack decides ON THE DEVICE whether the tensor-core kernels or the
     generic ones run (no host sync); see ``pack_flags``."""
@@ -133,16 +135,21 @@ def neighbourhood_pack(nbhd_idx, Nk):
         return None
     cache = getattr(nbhd_idx, "_clusten_pack", None)
     ver = nbhd_idx._version
-    if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr():
-        return cache[3]
     B, Nq, M = nbhd_idx.shape
     dev = nbhd_idx.device
-    nbytes = _lib.lib().clusten_pack_bytes(B, Nq, M, Nk)
-    pack = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
-        _call("clusten_pack_build", dev, nbhd_idx.data_ptr(), B, Nq, M, Nk, pack.data_ptr(), nbytes)
+    if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr():
+        pack, has_inv = cache[3], cache[4]
+    else:
+        nbytes = _lib.lib().clusten_pack_bytes(B, Nq, M, Nk)
+        pack, has_inv = torch.empty(nbytes, dtype=torch.uint8, device=dev), False
+        with torch.cuda.device(dev):
+            _call("clusten_pack_build", dev, nbhd_idx.data_ptr(), B, Nq, M, Nk, pack.data_ptr(), nbytes)
+    if inverse and not has_inv:                  # the inverse lists are only needed by backward: built on first use
+        with torch.cuda.device(dev):
+            _call("clusten_pack_inverse", dev, pack.data_ptr(), pack.numel(), B, Nq, M, Nk)
+        has_inv = True
     try:
-        nbhd_idx._clusten_pack = (ver, Nk, nbhd_idx.data_ptr(), pack)
+        nbhd_idx._clusten_pack = (ver, Nk, nbhd_idx.data_ptr(), pack, has_inv)
     except Exception:  # pragma: no cover
         pass
     return pack
@@ -204,7 +211,7 @@ class CLUSTENQKFunction(Function):
         off, ent = inverse_neighbour_list(nbhd_idx, Nk)
         with torch.cuda.device(dev):
             _call("clusten_qk_bwd", dev, grad_attn.data_ptr(), query.data_ptr(), key.data_ptr(), nbhd_idx.data_ptr(),
-                  off.data_ptr(), ent.data_ptr(), _lib.ptr(neighbourhood_pack(nbhd_idx, Nk)), d_query.data_ptr(),
+                  off.data_ptr(), ent.data_ptr(), _lib.ptr(neighbourhood_pack(nbhd_idx, Nk, inverse=True)), d_query.data_ptr(),
                   d_key.data_ptr(), B, H, Nq, Nk, C, M,
                   *_s3(query), *_s3(key), *_s3(d_query), *_s3(d_key), _lib.dtype_code(query),
                   nbytes=query.element_size() * (B * H * Nq * M + 2 * B * H * (Nq + Nk) * C) + 8 * B * Nq * M)
@@ -254,7 +261,7 @@ class CLUSTENAVFunction(Function):
         off, ent = inverse_neighbour_list(nbhd_idx, Nk)
         with torch.cuda.device(dev):
             _call("clusten_av_bwd", dev, grad_feat.data_ptr(), attn.data_ptr(), v.data_ptr(), nbhd_idx.data_ptr(),
-                  off.data_ptr(), ent.data_ptr(), _lib.ptr(neighbourhood_pack(nbhd_idx, Nk)), d_attn.data_ptr(),
+                  off.data_ptr(), ent.data_ptr(), _lib.ptr(neighbourhood_pack(nbhd_idx, Nk, inverse=True)), d_attn.data_ptr(),
                   d_v.data_ptr(), B, H, Nq, Nk, C, M,
                   *_s3(grad_feat), *_s3(attn), *_s3(v), *_s3(d_v), _lib.dtype_code(attn),
                   nbytes=attn.element_size() * (2 * B * H * Nq * M + B * H * (Nq + 2 * Nk) * C) + 8 * B * Nq * M)

@@ -41,6 +41,8 @@ WORKLOADS = {
                                        note="BASELINE configs[3] backbone: AFF-Small Cityscapes 1024x2048, 1 image per GPU"),
     "aff_base_train_b2_512x1024_bf16": dict(preset="base", batch=2, H=512, W=1024, mode="train", dtype="bf16",
                                             note="BASELINE configs[4] backbone: AFF-Base 512x1024 crop, 2 per GPU, bf16, DDP"),
+    # tiny case for the CPU tests of the host logic (never a bench line)
+    "aff_test_fwd_b2_128": dict(preset="test", batch=2, H=128, W=128, mode="fwd", dtype="f32", note="unit-test workload"),
 }
 DEFAULT_WORKLOAD = "aff_mini_fwd_b16_512"
 CPU_SAMPLE_IMAGES = 2
@@ -88,6 +90,19 @@ def make_images(batch, H, W, seed):
     import torch
     g = torch.Generator().manual_seed(seed)
     return torch.randn(batch, 3, H, W, generator=g)
+
+
+def max_over_ranks(t, world):
+    """Step time of the job = the slowest rank's (t: 1-element tensor on the rank's device)."""
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_images(batch_per_gpu, world, steps):
+    """Weak scaling: every rank processes its own batch_per_gpu images per step; value = this / max-over-ranks time."""
+    return batch_per_gpu * world * steps
 
 
 def run_reference(args, wl, rank, world):
@@ -227,10 +242,7 @@ def main():
     launches = ops.kernel_launches() - k0
     clocks = sampler.stop()
     peak_mem = torch.cuda.max_memory_allocated()
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = max_over_ranks(torch.tensor([ms], device=dev, dtype=torch.float64), world)
 
     # ---- timed region 2: end to end with host buffers --------------------------------------------------------------
     out = step(x_dev)
@@ -254,10 +266,7 @@ def main():
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_max = float(t.item())
+    e2e_max = max_over_ranks(torch.tensor([e2e_s], device=dev, dtype=torch.float64), world)
 
     if rank != 0:
         if world > 1:
@@ -306,7 +315,7 @@ def main():
         cpu = {"value": round(CPU_SAMPLE_IMAGES * reps / dt, 4), "unit": "images/s", "cores": cores, "kind": "port",
                "sample": f"{reps} passes of {CPU_SAMPLE_IMAGES} images {wl['H']}x{wl['W']}, fp32, {wl['mode']} (oracle/aff_oracle.py)"}
 
-    total_images = B * world * args.steps
+    total_images = whole_job_images(B, world, args.steps)
     line = {
         "metric": "aff_backbone_images_per_sec", "value": round(total_images / (ms_max / 1e3), 2), "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 3),

@@ -110,7 +110,7 @@ def main():
     code = _lib.dtype_code(q)
     off, ent = ops.inverse_neighbour_list(idx, N)
     ops.USE_TILE_KERNELS = not args.generic
-    pack = ops.neighbourhood_pack(idx, N)
+    pack = ops.neighbourhood_pack(idx, N, inverse=True)
     pk = 0 if pack is None else pack.data_ptr()
     print(json.dumps({"pack_flags(generic,maxU,impure,overlimit)": ops.pack_flags(idx, N)}), flush=True)
     out_attn = torch.empty(B, H, N, M, device="cuda", dtype=dt)
@@ -140,9 +140,10 @@ def main():
     pb = L.clusten_pack_bytes(B, N, M, N)
     pbuf = torch.empty(pb, dtype=torch.uint8, device="cuda")
     run("pack_build", lambda: ck(L.clusten_pack_build(idx.data_ptr(), B, N, M, N, pbuf.data_ptr(), pb, st())), BNM8)
+    run("pack_inverse", lambda: ck(L.clusten_pack_inverse(pbuf.data_ptr(), pb, B, N, M, N, st())), BNM8)
     ws_b = L.clusten_csr_workspace_bytes(B, N, M, N)
     ws = torch.empty(ws_b, dtype=torch.uint8, device="cuda")
-    run("csr_build", lambda: ck(L.clusten_csr_build(idx.data_ptr(), B, N, M, N, off.data_ptr(), ent.data_ptr(), ws.data_ptr(), ws_b, st())),
+    run("csr_build", lambda: ck(L.clusten_csr_build(idx.data_ptr(), B, N, M, N, off.data_ptr(), ent.data_ptr(), ws.data_ptr(), ws_b, None, st())),
         BNM8 + B * N * M * 4 + B * (N + 1) * 4)
     # WF merge: N' tokens in top-k (not curve) order gather M rows of the [B,N,H*C] feature map
     Nq, Cw, IC = S["Nq_wf"], H * C, 4

@@ -61,7 +61,9 @@ long long clusten_kernel_launches(void);
  * Requires M <= 256 and Nq < 2^24.  Deterministic (stable radix sort, no atomics on the data path). */
 size_t clusten_csr_workspace_bytes(int B, int Nq, int M, int Nk);
 int clusten_csr_build(const int64_t *nbhd_idx, int B, int Nq, int M, int Nk,
-                      int32_t *offsets, uint32_t *entries, void *workspace, size_t workspace_bytes, void *stream);
+                      int32_t *offsets, uint32_t *entries, void *workspace, size_t workspace_bytes,
+                      const void *pack /* or NULL: when given, the build is skipped on the device unless the pack routes to the generic kernels */,
+                      void *stream);
 
 /* ---- tile pack: per-index-tensor structure behind the tensor-core ("tile-union") kernels.  Built once per index tensor
  * (it is constant across the blocks of an AFF stage, aff.py:487-493) and passed as `pack` to the QK / AV entry points;
@@ -69,6 +71,8 @@ int clusten_csr_build(const int64_t *nbhd_idx, int B, int Nq, int M, int Nk,
  * octet structure (M % 8 != 0, impure runs, too little locality) fall back to the generic kernels with no host sync. */
 size_t clusten_pack_bytes(int B, int Nq, int M, int Nk);
 int clusten_pack_build(const int64_t *nbhd_idx, int B, int Nq, int M, int Nk, void *pack, size_t pack_bytes, void *stream);
+/* inverse lists (key octet -> referencing tiles) of an already built pack: needed by the backward entry points only */
+int clusten_pack_inverse(void *pack, size_t pack_bytes, int B, int Nq, int M, int Nk, void *stream);
 
 /* ---- QK: attn[b,h,i,j] = sum_c q[b,h,i,c] * k[b,h,idx[b,i,j],c]            (clustenqk_cuda_kernel.cu:38-45) */
 int clusten_qk_fwd(const void *q, const void *k, const int64_t *nbhd_idx, const void *pack /* or NULL */,

@@ -55,7 +55,7 @@ def test_argument_errors_without_gpu(lib):
     assert rc == -2                                  # unknown dtype
     rc = lib.clusten_knn(1, 1, 1, 4, 4, 17, 1, None, None)
     assert rc == -3                                  # k > 16
-    rc = lib.clusten_csr_build(1, 1, 4, 300, 4, 1, 1, 1, 1 << 30, None)
+    rc = lib.clusten_csr_build(1, 1, 4, 300, 4, 1, 1, 1, 1 << 30, None, None)
     assert rc == -3                                  # M > 256
     rc = lib.clusten_sfc_cluster(1, 1, 16, 8, 4, 4, 1, 1, 1, None, 1, 1, 0, None)
     assert rc == -4                                  # workspace too small
