@@ -244,12 +244,12 @@ struct Rows { const void *p; int64_t sb, sh, sn; };
 template <typename T> bool tile_dot_eligible(int C, int M, Rows4 x, Rows4 y);
 template <typename T> bool tile_axpy_eligible(int C, int M, Rows4 w, Rows4 y, Rows4 o);
 template <typename T> bool tile_scat_eligible(int C, int M, Rows4 w, Rows4 x, Rows4 o);
-template <typename T> int launch_dot_tile(const T *X, const T *Y, const void *pack, T *out, int B, int H, int Nq, int Nk, int C,
-                                          int M, Rows4 x, Rows4 y, cudaStream_t st);
-template <typename T> int launch_axpy_tile(const T *W, const T *Y, const void *pack, T *out, int B, int H, int Nq, int Nk, int C,
-                                           int M, Rows4 w, Rows4 y, Rows4 o, cudaStream_t st);
-template <typename T> int launch_scat_tile(const T *W, const T *X, const void *pack, T *out, int B, int H, int Nq, int Nk, int C,
-                                           int M, Rows4 w, Rows4 x, Rows4 o, cudaStream_t st);
+template <typename T> int launch_dot_tile(const T *X, const T *Y, const int64_t *idx, const void *pack, T *out, int B, int H, int Nq,
+                                          int Nk, int C, int M, Rows4 x, Rows4 y, cudaStream_t st);
+template <typename T> int launch_axpy_tile(const T *W, const T *Y, const int64_t *idx, const void *pack, T *out, int B, int H, int Nq,
+                                           int Nk, int C, int M, Rows4 w, Rows4 y, Rows4 o, cudaStream_t st);
+template <typename T> int launch_scat_tile(const T *W, const T *X, const int32_t *csr_off, const uint32_t *csr_ent, const void *pack,
+                                           T *out, int B, int H, int Nq, int Nk, int C, int M, Rows4 w, Rows4 x, Rows4 o, cudaStream_t st);
 
 static inline Rows4 r4(const Rows &r) { return Rows4{r.p, r.sb, r.sh, r.sn}; }
 static inline const int *tile_flag_of(const void *pack) { return reinterpret_cast<const int *>(pack); }   // PackView.flags is at offset 0
@@ -281,7 +281,7 @@ static int launch_dot(const T *X, const T *Y, const int64_t *idx, const void *pa
     if ((int64_t)B * Nq == 0) return 0;
     const int *flag = nullptr;
     if (pack && tile_dot_eligible<T>(C, M, r4(x), r4(y))) {
-        if (int e = launch_dot_tile<T>(X, Y, pack, out, B, H, Nq, Nk, C, M, r4(x), r4(y), st)) return e;
+        if (int e = launch_dot_tile<T>(X, Y, idx, pack, out, B, H, Nq, Nk, C, M, r4(x), r4(y), st)) return e;
         flag = tile_flag_of(pack);
     }
     if (vec_ok<T>(C, {x, y})) {
@@ -306,7 +306,7 @@ static int launch_axpy(const T *W, const T *Y, const int64_t *idx, const void *p
     if ((int64_t)B * Nq == 0) return 0;
     const int *flag = nullptr;
     if (pack && tile_axpy_eligible<T>(C, M, r4(w), r4(y), r4(o))) {
-        if (int e = launch_axpy_tile<T>(W, Y, pack, out, B, H, Nq, Nk, C, M, r4(w), r4(y), r4(o), st)) return e;
+        if (int e = launch_axpy_tile<T>(W, Y, idx, pack, out, B, H, Nq, Nk, C, M, r4(w), r4(y), r4(o), st)) return e;
         flag = tile_flag_of(pack);
     }
     if (vec_ok<T>(C, {y, o})) {
@@ -332,7 +332,7 @@ static int launch_csr(const T *W, const T *X, const int32_t *off, const uint32_t
     if ((int64_t)B * Nk == 0) return 0;
     const int *flag = nullptr;
     if (pack && tile_scat_eligible<T>(C, M, r4(w), r4(x), r4(o))) {
-        if (int e = launch_scat_tile<T>(W, X, pack, out, B, H, Nq, Nk, C, M, r4(w), r4(x), r4(o), st)) return e;
+        if (int e = launch_scat_tile<T>(W, X, off, ent, pack, out, B, H, Nq, Nk, C, M, r4(w), r4(x), r4(o), st)) return e;
         flag = tile_flag_of(pack);
     }
     if (vec_ok<T>(C, {x, o})) {

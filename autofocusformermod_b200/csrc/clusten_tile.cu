@@ -109,12 +109,44 @@ __device__ __forceinline__ int tile_octet(const TileCtx &c, int u) {        // u
     return __shfl_sync(FULL, u < 32 ? c.o0 : c.o1, u & 31);
 }
 
+// ---- slow in-kernel paths for impure tokens (rare: the padded last cluster of a stage, point_utils.py:282-283) -------------
+// All warp-cooperative and warp-uniform; they read the int64 index tensor the interface delivered.
+__device__ __forceinline__ uint32_t tile_imp_mask(const PackView &pk, int bt) {          // bit r = token row r is impure
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(pk.tok_imp + (int64_t)bt * TILE_TOK));
+    uint32_t m = 0;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m |= ((w[q] >> (8 * k)) & 1u) << (4 * q + k);
+    return m;
+}
+template <typename T>
+__device__ __forceinline__ void slow_dot_row(const T *xrow, const T *ybase, int64_t y_sn, const int64_t *irow, T *orow,
+                                             int C, int M, int lane) {
+    for (int j = lane; j < M; j += 32) {
+        const T *y = ybase + irow[j] * y_sn;
+        float s = 0.f;
+        for (int ch = 0; ch < C; ++ch) s = fmaf(to_f(xrow[ch]), to_f(y[ch]), s);
+        orow[j] = from_f<T>(s);
+    }
+}
+template <typename T>
+__device__ __forceinline__ void slow_axpy_row(const T *wrow, const T *ybase, int64_t y_sn, const int64_t *irow, T *orow,
+                                              int C, int M, int lane) {
+    for (int ch = lane; ch < C; ch += 32) {
+        float s = 0.f;
+        for (int j = 0; j < M; ++j) s = fmaf(to_f(wrow[j]), to_f(ybase[irow[j] * y_sn + ch]), s);
+        orow[ch] = from_f<T>(s);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // dot: 16-bit types
 template <typename T, int CH>
 __global__ void __launch_bounds__(TW * 32)
-dot_tile16_kernel(const T *__restrict__ X, const T *__restrict__ Y, const PackView pk, T *__restrict__ out,
-                  int B, int H, int Nq, int C, int M,
+dot_tile16_kernel(const T *__restrict__ X, const T *__restrict__ Y, const int64_t *__restrict__ idx, const PackView pk,
+                  T *__restrict__ out, int B, int H, int Nq, int C, int M,
                   int64_t x_sb, int64_t x_sh, int64_t x_sn, int64_t y_sb, int64_t y_sh, int64_t y_sn) {
     if (pk.flags[0]) return;
     TileCtx c;
@@ -153,13 +185,18 @@ dot_tile16_kernel(const T *__restrict__ X, const T *__restrict__ Y, const PackVi
             if (sgb[j] >= 0) store_pair<T>(ob + 8 * sgb[j], acc[2], acc[3]);
         }
     }
+    for (uint32_t imp = tile_imp_mask(pk, c.bt); imp; imp &= imp - 1) {          // impure tokens of this tile
+        const int i = c.i0 + __ffs(imp) - 1;
+        slow_dot_row<T>(X + c.b * x_sb + c.h * x_sh + (int64_t)i * x_sn, Y + c.b * y_sb + c.h * y_sh, y_sn,
+                        idx + ((int64_t)c.b * Nq + i) * M, out + (((int64_t)c.b * H + c.h) * Nq + i) * M, C, M, c.lane);
+    }
 }
 
 // dot: fp32 through 3xTF32
 template <int CH>
 __global__ void __launch_bounds__(TW * 32)
-dot_tile32_kernel(const float *__restrict__ X, const float *__restrict__ Y, const PackView pk, float *__restrict__ out,
-                  int B, int H, int Nq, int C, int M,
+dot_tile32_kernel(const float *__restrict__ X, const float *__restrict__ Y, const int64_t *__restrict__ idx, const PackView pk,
+                  float *__restrict__ out, int B, int H, int Nq, int C, int M,
                   int64_t x_sb, int64_t x_sh, int64_t x_sn, int64_t y_sb, int64_t y_sh, int64_t y_sn) {
     if (pk.flags[0]) return;
     TileCtx c;
@@ -213,6 +250,11 @@ dot_tile32_kernel(const float *__restrict__ X, const float *__restrict__ Y, cons
             if (sgb[j] >= 0) store_pair<float>(ob + 8 * sgb[j], acc[2], acc[3]);
         }
     }
+    for (uint32_t imp = tile_imp_mask(pk, c.bt); imp; imp &= imp - 1) {
+        const int i = c.i0 + __ffs(imp) - 1;
+        slow_dot_row<float>(X + c.b * x_sb + c.h * x_sh + (int64_t)i * x_sn, Y + c.b * y_sb + c.h * y_sh, y_sn,
+                            idx + ((int64_t)c.b * Nq + i) * M, out + (((int64_t)c.b * H + c.h) * Nq + i) * M, C, M, c.lane);
+    }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
@@ -225,26 +267,26 @@ template <typename T> static bool rows_ok(const Rows4 &r) {
 template <typename T> static bool tile_shape_ok(int C, int M) { return C % 8 == 0 && C >= 8 && C <= 32 && M % 8 == 0 && M <= 256; }
 
 template <typename T>
-int launch_dot_tile(const T *X, const T *Y, const void *pack, T *out, int B, int H, int Nq, int Nk, int C, int M,
-                    Rows4 x, Rows4 y, cudaStream_t st) {
+int launch_dot_tile(const T *X, const T *Y, const int64_t *idx, const void *pack, T *out, int B, int H, int Nq, int Nk, int C,
+                    int M, Rows4 x, Rows4 y, cudaStream_t st) {
     const PackView pk = pack_view(const_cast<void *>(pack), B, Nq, Nk);
     const int64_t items = (int64_t)B * pk.T * H;
     if (items == 0) return 0;
     const int grid = ceil_div(items, TW);
     if constexpr (sizeof(T) == 2) {
-        if (C <= 16) dot_tile16_kernel<T, 4><<<grid, TW * 32, 0, st>>>(X, Y, pk, out, B, H, Nq, C, M, x.sb, x.sh, x.sn, y.sb, y.sh, y.sn);
-        else dot_tile16_kernel<T, 8><<<grid, TW * 32, 0, st>>>(X, Y, pk, out, B, H, Nq, C, M, x.sb, x.sh, x.sn, y.sb, y.sh, y.sn);
+        if (C <= 16) dot_tile16_kernel<T, 4><<<grid, TW * 32, 0, st>>>(X, Y, idx, pk, out, B, H, Nq, C, M, x.sb, x.sh, x.sn, y.sb, y.sh, y.sn);
+        else dot_tile16_kernel<T, 8><<<grid, TW * 32, 0, st>>>(X, Y, idx, pk, out, B, H, Nq, C, M, x.sb, x.sh, x.sn, y.sb, y.sh, y.sn);
     } else {
-        if (C <= 16) dot_tile32_kernel<4><<<grid, TW * 32, 0, st>>>(X, Y, pk, out, B, H, Nq, C, M, x.sb, x.sh, x.sn, y.sb, y.sh, y.sn);
-        else dot_tile32_kernel<8><<<grid, TW * 32, 0, st>>>(X, Y, pk, out, B, H, Nq, C, M, x.sb, x.sh, x.sn, y.sb, y.sh, y.sn);
+        if (C <= 16) dot_tile32_kernel<4><<<grid, TW * 32, 0, st>>>(X, Y, idx, pk, out, B, H, Nq, C, M, x.sb, x.sh, x.sn, y.sb, y.sh, y.sn);
+        else dot_tile32_kernel<8><<<grid, TW * 32, 0, st>>>(X, Y, idx, pk, out, B, H, Nq, C, M, x.sb, x.sh, x.sn, y.sb, y.sh, y.sn);
     }
     note_launches(1);
     return check_launch("dot_tile");
 }
 
-template int launch_dot_tile<float>(const float *, const float *, const void *, float *, int, int, int, int, int, int, Rows4, Rows4, cudaStream_t);
-template int launch_dot_tile<__half>(const __half *, const __half *, const void *, __half *, int, int, int, int, int, int, Rows4, Rows4, cudaStream_t);
-template int launch_dot_tile<__nv_bfloat16>(const __nv_bfloat16 *, const __nv_bfloat16 *, const void *, __nv_bfloat16 *, int, int, int, int, int, int, Rows4, Rows4, cudaStream_t);
+template int launch_dot_tile<float>(const float *, const float *, const int64_t *, const void *, float *, int, int, int, int, int, int, Rows4, Rows4, cudaStream_t);
+template int launch_dot_tile<__half>(const __half *, const __half *, const int64_t *, const void *, __half *, int, int, int, int, int, int, Rows4, Rows4, cudaStream_t);
+template int launch_dot_tile<__nv_bfloat16>(const __nv_bfloat16 *, const __nv_bfloat16 *, const int64_t *, const void *, __nv_bfloat16 *, int, int, int, int, int, int, Rows4, Rows4, cudaStream_t);
 
 template <typename T> bool tile_dot_eligible(int C, int M, Rows4 x, Rows4 y) { return tile_shape_ok<T>(C, M) && rows_ok<T>(x) && rows_ok<T>(y); }
 template bool tile_dot_eligible<float>(int, int, Rows4, Rows4);
@@ -279,8 +321,8 @@ template <typename T> __device__ __forceinline__ uint32_t load_w_pair(const T *p
 
 template <typename T, int NT>
 __global__ void __launch_bounds__(TW * 32)
-axpy_tile16_kernel(const T *__restrict__ W, const T *__restrict__ Y, const PackView pk, T *__restrict__ out,
-                   int B, int H, int Nq, int C, int M,
+axpy_tile16_kernel(const T *__restrict__ W, const T *__restrict__ Y, const int64_t *__restrict__ idx, const PackView pk,
+                   T *__restrict__ out, int B, int H, int Nq, int C, int M,
                    int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t y_sb, int64_t y_sh, int64_t y_sn,
                    int64_t o_sb, int64_t o_sh, int64_t o_sn, int w_al4) {
     constexpr int ROWB = NT * 16 + 16;                 // padded row: ldmatrix phases hit 8 distinct 16-byte bank groups
@@ -340,21 +382,27 @@ axpy_tile16_kernel(const T *__restrict__ W, const T *__restrict__ Y, const PackV
         }
         __syncwarp();
     }
+    const uint32_t impm = tile_imp_mask(pk, c.bt);
     T *oa = out + c.b * o_sb + c.h * o_sh + (int64_t)ra * o_sn + 2 * c.t;
     T *ob = oa + 8 * o_sn;
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
         if (8 * n + 2 * c.t < C) {
-            if (ra < Nq) store_pair<T>(oa + 8 * n, acc[n][0], acc[n][1]);
-            if (rb < Nq) store_pair<T>(ob + 8 * n, acc[n][2], acc[n][3]);
+            if (ra < Nq && !((impm >> c.g) & 1u)) store_pair<T>(oa + 8 * n, acc[n][0], acc[n][1]);
+            if (rb < Nq && !((impm >> (c.g + 8)) & 1u)) store_pair<T>(ob + 8 * n, acc[n][2], acc[n][3]);
         }
+    }
+    for (uint32_t imp = impm; imp; imp &= imp - 1) {
+        const int i = c.i0 + __ffs(imp) - 1;
+        slow_axpy_row<T>(W + c.b * w_sb + c.h * w_sh + (int64_t)i * w_sn, ybase, y_sn, idx + ((int64_t)c.b * Nq + i) * M,
+                         out + c.b * o_sb + c.h * o_sh + (int64_t)i * o_sn, C, M, c.lane);
     }
 }
 
 template <int NT>
 __global__ void __launch_bounds__(TW * 32)
-axpy_tile32_kernel(const float *__restrict__ W, const float *__restrict__ Y, const PackView pk, float *__restrict__ out,
-                   int B, int H, int Nq, int C, int M,
+axpy_tile32_kernel(const float *__restrict__ W, const float *__restrict__ Y, const int64_t *__restrict__ idx, const PackView pk,
+                   float *__restrict__ out, int B, int H, int Nq, int C, int M,
                    int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t y_sb, int64_t y_sh, int64_t y_sn,
                    int64_t o_sb, int64_t o_sh, int64_t o_sn) {
     constexpr int RS = NT * 8 + 8;                     // padded row stride in floats: lanes (t, g) hit 32 distinct banks
@@ -408,14 +456,20 @@ axpy_tile32_kernel(const float *__restrict__ W, const float *__restrict__ Y, con
         }
         __syncwarp();
     }
+    const uint32_t impm = tile_imp_mask(pk, c.bt);
     float *oa = out + c.b * o_sb + c.h * o_sh + (int64_t)ra * o_sn + 2 * c.t;
     float *ob = oa + 8 * o_sn;
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
         if (8 * n + 2 * c.t < C) {
-            if (ra < Nq) store_pair<float>(oa + 8 * n, acc[n][0], acc[n][1]);
-            if (rb < Nq) store_pair<float>(ob + 8 * n, acc[n][2], acc[n][3]);
+            if (ra < Nq && !((impm >> c.g) & 1u)) store_pair<float>(oa + 8 * n, acc[n][0], acc[n][1]);
+            if (rb < Nq && !((impm >> (c.g + 8)) & 1u)) store_pair<float>(ob + 8 * n, acc[n][2], acc[n][3]);
         }
+    }
+    for (uint32_t imp = impm; imp; imp &= imp - 1) {
+        const int i = c.i0 + __ffs(imp) - 1;
+        slow_axpy_row<float>(W + c.b * w_sb + c.h * w_sh + (int64_t)i * w_sn, ybase, y_sn, idx + ((int64_t)c.b * Nq + i) * M,
+                             out + c.b * o_sb + c.h * o_sh + (int64_t)i * o_sn, C, M, c.lane);
     }
 }
 
@@ -426,19 +480,19 @@ template <typename T> bool tile_axpy_eligible(int C, int M, Rows4 w, Rows4 y, Ro
 }
 
 template <typename T>
-int launch_axpy_tile(const T *W, const T *Y, const void *pack, T *out, int B, int H, int Nq, int Nk, int C, int M,
-                     Rows4 w, Rows4 y, Rows4 o, cudaStream_t st) {
+int launch_axpy_tile(const T *W, const T *Y, const int64_t *idx, const void *pack, T *out, int B, int H, int Nq, int Nk, int C,
+                     int M, Rows4 w, Rows4 y, Rows4 o, cudaStream_t st) {
     const PackView pk = pack_view(const_cast<void *>(pack), B, Nq, Nk);
     const int64_t items = (int64_t)B * pk.T * H;
     if (items == 0) return 0;
     const int grid = ceil_div(items, TW);
     if constexpr (sizeof(T) == 2) {
         const int al4 = ((reinterpret_cast<uintptr_t>(w.p) & 3u) == 0 && w.sb % 2 == 0 && w.sh % 2 == 0 && w.sn % 2 == 0) ? 1 : 0;
-        if (C <= 16) axpy_tile16_kernel<T, 2><<<grid, TW * 32, 0, st>>>(W, Y, pk, out, B, H, Nq, C, M, w.sb, w.sh, w.sn, y.sb, y.sh, y.sn, o.sb, o.sh, o.sn, al4);
-        else axpy_tile16_kernel<T, 4><<<grid, TW * 32, 0, st>>>(W, Y, pk, out, B, H, Nq, C, M, w.sb, w.sh, w.sn, y.sb, y.sh, y.sn, o.sb, o.sh, o.sn, al4);
+        if (C <= 16) axpy_tile16_kernel<T, 2><<<grid, TW * 32, 0, st>>>(W, Y, idx, pk, out, B, H, Nq, C, M, w.sb, w.sh, w.sn, y.sb, y.sh, y.sn, o.sb, o.sh, o.sn, al4);
+        else axpy_tile16_kernel<T, 4><<<grid, TW * 32, 0, st>>>(W, Y, idx, pk, out, B, H, Nq, C, M, w.sb, w.sh, w.sn, y.sb, y.sh, y.sn, o.sb, o.sh, o.sn, al4);
     } else {
-        if (C <= 16) axpy_tile32_kernel<2><<<grid, TW * 32, 0, st>>>(W, Y, pk, out, B, H, Nq, C, M, w.sb, w.sh, w.sn, y.sb, y.sh, y.sn, o.sb, o.sh, o.sn);
-        else axpy_tile32_kernel<4><<<grid, TW * 32, 0, st>>>(W, Y, pk, out, B, H, Nq, C, M, w.sb, w.sh, w.sn, y.sb, y.sh, y.sn, o.sb, o.sh, o.sn);
+        if (C <= 16) axpy_tile32_kernel<2><<<grid, TW * 32, 0, st>>>(W, Y, idx, pk, out, B, H, Nq, C, M, w.sb, w.sh, w.sn, y.sb, y.sh, y.sn, o.sb, o.sh, o.sn);
+        else axpy_tile32_kernel<4><<<grid, TW * 32, 0, st>>>(W, Y, idx, pk, out, B, H, Nq, C, M, w.sb, w.sh, w.sn, y.sb, y.sh, y.sn, o.sb, o.sh, o.sn);
     }
     note_launches(1);
     return check_launch("axpy_tile");
@@ -492,9 +546,39 @@ __device__ __forceinline__ bool pair_next(PairCtx &c, int &tile, int &ua, int &u
     return true;
 }
 
+// Contributions of impure tokens (left out of the tile structure) to the 16 key rows of this octet pair: walk the full
+// inverse neighbour list of each flagged row (csr.cu; built because the pack has impure tokens), keep the entries of
+// impure tokens, add them to the row just written.  Ascending (i, j) order -> deterministic.
+template <typename T>
+__device__ __forceinline__ void scat_fixup(const T *W, const T *X, const int32_t *csr_off, const uint32_t *csr_ent,
+                                           const PackView &pk, T *out, const PairCtx &c, int Nq, int Nk, int C, int M,
+                                           int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t x_sb, int64_t x_sh, int64_t x_sn,
+                                           int64_t o_sb, int64_t o_sh, int64_t o_sn) {
+    if (pk.flags[2] == 0) return;
+    __syncwarp();
+    for (int rr = 0; rr < 16; ++rr) {
+        const int row = c.o * 8 + rr;
+        if (row >= Nk || !pk.row_imp[(int64_t)c.b * Nk + row]) continue;
+        const int lo = csr_off[(int64_t)c.b * (Nk + 1) + row], hi = csr_off[(int64_t)c.b * (Nk + 1) + row + 1];
+        const uint32_t *ent = csr_ent + (int64_t)c.b * Nq * M;
+        for (int ch = c.lane; ch < C; ch += 32) {
+            float s = 0.f;
+            for (int e = lo; e < hi; ++e) {
+                const uint32_t pkd = ent[e];
+                const int i = (int)(pkd >> 8), j = (int)(pkd & 255u);
+                if (!pk.tok_imp[(int64_t)c.b * pk.T * TILE_TOK + i]) continue;
+                s = fmaf(to_f(W[c.b * w_sb + c.h * w_sh + (int64_t)i * w_sn + j]), to_f(X[c.b * x_sb + c.h * x_sh + (int64_t)i * x_sn + ch]), s);
+            }
+            T *op = out + c.b * o_sb + c.h * o_sh + (int64_t)row * o_sn + ch;
+            *op = from_f<T>(to_f(*op) + s);
+        }
+    }
+}
+
 template <typename T, int NT>
 __global__ void __launch_bounds__(TWS * 32)
-scat_tile16_kernel(const T *__restrict__ W, const T *__restrict__ X, const PackView pk, T *__restrict__ out,
+scat_tile16_kernel(const T *__restrict__ W, const T *__restrict__ X, const int32_t *__restrict__ csr_off,
+                   const uint32_t *__restrict__ csr_ent, const PackView pk, T *__restrict__ out,
                    int B, int H, int Nq, int Nk, int C, int M,
                    int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t x_sb, int64_t x_sh, int64_t x_sn,
                    int64_t o_sb, int64_t o_sh, int64_t o_sn, int w_al16) {
@@ -582,11 +666,13 @@ scat_tile16_kernel(const T *__restrict__ W, const T *__restrict__ X, const PackV
             if (kb < Nk) store_pair<T>(ob + 8 * n, acc[n][2], acc[n][3]);
         }
     }
+    scat_fixup<T>(W, X, csr_off, csr_ent, pk, out, c, Nq, Nk, C, M, w_sb, w_sh, w_sn, x_sb, x_sh, x_sn, o_sb, o_sh, o_sn);
 }
 
 template <int NT>
 __global__ void __launch_bounds__(TWS * 32)
-scat_tile32_kernel(const float *__restrict__ W, const float *__restrict__ X, const PackView pk, float *__restrict__ out,
+scat_tile32_kernel(const float *__restrict__ W, const float *__restrict__ X, const int32_t *__restrict__ csr_off,
+                   const uint32_t *__restrict__ csr_ent, const PackView pk, float *__restrict__ out,
                    int B, int H, int Nq, int Nk, int C, int M,
                    int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t x_sb, int64_t x_sh, int64_t x_sn,
                    int64_t o_sb, int64_t o_sh, int64_t o_sn, int w_al16) {
@@ -680,6 +766,7 @@ scat_tile32_kernel(const float *__restrict__ W, const float *__restrict__ X, con
             if (kb < Nk) store_pair<float>(ob + 8 * n, acc[n][2], acc[n][3]);
         }
     }
+    scat_fixup<float>(W, X, csr_off, csr_ent, pk, out, c, Nq, Nk, C, M, w_sb, w_sh, w_sn, x_sb, x_sh, x_sn, o_sb, o_sh, o_sn);
 }
 
 template <typename T> bool tile_scat_eligible(int C, int M, Rows4 w, Rows4 x, Rows4 o) {
@@ -688,8 +775,8 @@ template <typename T> bool tile_scat_eligible(int C, int M, Rows4 w, Rows4 x, Ro
 }
 
 template <typename T>
-int launch_scat_tile(const T *W, const T *X, const void *pack, T *out, int B, int H, int Nq, int Nk, int C, int M,
-                     Rows4 w, Rows4 x, Rows4 o, cudaStream_t st) {
+int launch_scat_tile(const T *W, const T *X, const int32_t *csr_off, const uint32_t *csr_ent, const void *pack, T *out,
+                     int B, int H, int Nq, int Nk, int C, int M, Rows4 w, Rows4 x, Rows4 o, cudaStream_t st) {
     const PackView pk = pack_view(const_cast<void *>(pack), B, Nq, Nk);
     const int64_t items = (int64_t)B * ((pk.NO + 1) / 2) * H;
     if (items == 0) return 0;
@@ -697,11 +784,11 @@ int launch_scat_tile(const T *W, const T *X, const void *pack, T *out, int B, in
     constexpr int VPT = 16 / sizeof(T);
     const int al16 = (aligned16(w.p) && w.sb % VPT == 0 && w.sh % VPT == 0 && w.sn % VPT == 0) ? 1 : 0;
     if constexpr (sizeof(T) == 2) {
-        if (C <= 16) scat_tile16_kernel<T, 2><<<grid, TWS * 32, 0, st>>>(W, X, pk, out, B, H, Nq, Nk, C, M, w.sb, w.sh, w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn, al16);
-        else scat_tile16_kernel<T, 4><<<grid, TWS * 32, 0, st>>>(W, X, pk, out, B, H, Nq, Nk, C, M, w.sb, w.sh, w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn, al16);
+        if (C <= 16) scat_tile16_kernel<T, 2><<<grid, TWS * 32, 0, st>>>(W, X, csr_off, csr_ent, pk, out, B, H, Nq, Nk, C, M, w.sb, w.sh, w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn, al16);
+        else scat_tile16_kernel<T, 4><<<grid, TWS * 32, 0, st>>>(W, X, csr_off, csr_ent, pk, out, B, H, Nq, Nk, C, M, w.sb, w.sh, w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn, al16);
     } else {
-        if (C <= 16) scat_tile32_kernel<2><<<grid, TWS * 32, 0, st>>>(W, X, pk, out, B, H, Nq, Nk, C, M, w.sb, w.sh, w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn, al16);
-        else scat_tile32_kernel<4><<<grid, TWS * 32, 0, st>>>(W, X, pk, out, B, H, Nq, Nk, C, M, w.sb, w.sh, w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn, al16);
+        if (C <= 16) scat_tile32_kernel<2><<<grid, TWS * 32, 0, st>>>(W, X, csr_off, csr_ent, pk, out, B, H, Nq, Nk, C, M, w.sb, w.sh, w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn, al16);
+        else scat_tile32_kernel<4><<<grid, TWS * 32, 0, st>>>(W, X, csr_off, csr_ent, pk, out, B, H, Nq, Nk, C, M, w.sb, w.sh, w.sn, x.sb, x.sh, x.sn, o.sb, o.sh, o.sn, al16);
     }
     note_launches(1);
     return check_launch("scat_tile");
@@ -710,8 +797,8 @@ int launch_scat_tile(const T *W, const T *X, const void *pack, T *out, int B, in
 #define INST(T) \
     template bool tile_axpy_eligible<T>(int, int, Rows4, Rows4, Rows4); \
     template bool tile_scat_eligible<T>(int, int, Rows4, Rows4, Rows4); \
-    template int launch_axpy_tile<T>(const T *, const T *, const void *, T *, int, int, int, int, int, int, Rows4, Rows4, Rows4, cudaStream_t); \
-    template int launch_scat_tile<T>(const T *, const T *, const void *, T *, int, int, int, int, int, int, Rows4, Rows4, Rows4, cudaStream_t);
+    template int launch_axpy_tile<T>(const T *, const T *, const int64_t *, const void *, T *, int, int, int, int, int, int, Rows4, Rows4, Rows4, cudaStream_t); \
+    template int launch_scat_tile<T>(const T *, const T *, const int32_t *, const uint32_t *, const void *, T *, int, int, int, int, int, int, Rows4, Rows4, Rows4, cudaStream_t);
 INST(float) INST(__half) INST(__nv_bfloat16)
 #undef INST
 

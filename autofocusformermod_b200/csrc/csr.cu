@@ -89,9 +89,9 @@ extern "C" int clusten_csr_build(const int64_t *nbhd_idx, int B, int Nq, int M, 
                          clusten_csr_workspace_bytes(B, Nq, M, Nk));
     cudaStream_t st = (cudaStream_t)stream;
     if (B == 0) return 0;
-    // with a tile pack the list is only needed when the pack routes to the generic kernels (flag != 0): every kernel
+    // with a tile pack the list is only needed when the pack routes to the generic kernels or has impure tokens: every kernel
     // below exits at once otherwise -- decided on the device, no host synchronisation
-    const int *skip = reinterpret_cast<const int *>(pack);
+    const int *skip = pack ? reinterpret_cast<const int *>(pack) + 4 : nullptr;     // PackView.flags[4]: list needed
     const int nseg = Nq * M;
     if (nseg == 0) {
         cudaMemsetAsync(offsets, 0, (size_t)B * (Nk + 1) * sizeof(int32_t), st);

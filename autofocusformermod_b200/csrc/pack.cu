@@ -9,6 +9,7 @@ __global__ void __launch_bounds__(PACK_WARPS * 32)
 pack_tile_kernel(const int64_t *__restrict__ idx, int B, int Nq, int M, int Nk, PackView pk) {
     __shared__ int oct_rs[PACK_WARPS][TILE_TOK][S_MAX];
     __shared__ __align__(16) int8_t slot_s[PACK_WARPS][TILE_TOK][U_MAX];
+    __shared__ int row_bad[PACK_WARPS][TILE_TOK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bt = blockIdx.x * PACK_WARPS + warp;
     if (bt >= B * pk.T) return;
@@ -31,14 +32,18 @@ pack_tile_kernel(const int64_t *__restrict__ idx, int B, int Nq, int M, int Nk, 
         oct_rs[warp][r][s] = o;
     }
     for (int x = lane; x < TILE_TOK * U_MAX / 4; x += 32) reinterpret_cast<int *>(&slot_s[warp][0][0])[x] = -1;
+    if (lane < TILE_TOK) row_bad[warp][lane] = 0;
+    __syncwarp();
+    for (int item = lane; item < TILE_TOK * S; item += 32)
+        if (oct_rs[warp][item / S][item % S] == -1) row_bad[warp][item / S] = 1;      // benign race: all writers store 1
     __syncwarp();
     // step 2: union in first-seen order (lane u holds union position u / u + 32)
-    int my0 = -1, my1 = -1, U = 0, bad = 0;
+    int my0 = -1, my1 = -1, U = 0;
     for (int r = 0; r < TILE_TOK; ++r) {
+        if (row_bad[warp][r]) continue;                      // impure token: contributes nothing to the union
         for (int s = 0; s < S; ++s) {
             const int o = oct_rs[warp][r][s];
-            if (o == -2) continue;
-            if (o == -1) { ++bad; continue; }
+            if (o < 0) continue;
             const unsigned m0 = __ballot_sync(FULL, my0 == o), m1 = __ballot_sync(FULL, my1 == o);
             int pos;
             if (m0) pos = __ffs(m0) - 1;
@@ -52,12 +57,28 @@ pack_tile_kernel(const int64_t *__restrict__ idx, int B, int Nq, int M, int Nk, 
             if (pos < U_MAX) {
                 const int prev = slot_s[warp][r][pos];
                 __syncwarp();
-                if (prev != -1) ++bad;                       // the token references one octet twice: generic path
+                if (prev != -1) { if (lane == 0) row_bad[warp][r] = 1; }   // one octet twice: impure token
                 else if (lane == 0) slot_s[warp][r][pos] = (int8_t)s;
                 __syncwarp();
             }
         }
     }
+    __syncwarp();
+    // impure tokens: no slots in the tile structure, flagged for the slow paths, their key rows flagged for the scatter
+    int bad = 0;
+    for (int r = 0; r < TILE_TOK; ++r) {
+        const int rb_ = row_bad[warp][r];
+        if (lane == 0) pk.tok_imp[(int64_t)bt * TILE_TOK + r] = (uint8_t)rb_;
+        if (!rb_) continue;
+        ++bad;
+        for (int u = lane; u < U_MAX; u += 32) slot_s[warp][r][u] = -1;
+        const int64_t *p = idx + ((int64_t)b * Nq + i0 + r) * M;
+        for (int j = lane; j < M; j += 32) {
+            const int64_t v = p[j];
+            if (v >= 0 && v < (int64_t)Nk) pk.row_imp[(int64_t)b * Nk + v] = 1;
+        }
+    }
+    __syncwarp();
     const int Uc = min(U, U_MAX);
     pk.tile_oct[(int64_t)bt * U_MAX + lane] = lane < Uc ? my0 : 0;
     if (lane + 32 < U_MAX) pk.tile_oct[(int64_t)bt * U_MAX + 32 + lane] = (lane + 32 < Uc) ? my1 : 0;
@@ -69,8 +90,14 @@ pack_tile_kernel(const int64_t *__restrict__ idx, int B, int Nq, int M, int Nk, 
         atomicMax(pk.flags + 1, U);
         if (bad) atomicAdd(pk.flags + 2, bad);
         if (U > U_MAX) atomicAdd(pk.flags + 3, 1);
-        if (bad || U > U_MAX) atomicExch(pk.flags + 0, 1);
     }
+}
+
+// generic path when a union overflowed or more than 1/16 of the tokens (and more than 64) are impure
+__global__ void pack_decide_kernel(int *flags, int tokens) {
+    const bool generic = flags[3] > 0 || (flags[2] > 64 && flags[2] > tokens / 16);
+    flags[0] = generic ? 1 : 0;
+    flags[4] = (generic || flags[2] > 0) ? 1 : 0;
 }
 
 // inverse lists: one (key = octet, implicit value = tile*U_MAX + u) pair per union entry, NO = sentinel for padding
@@ -98,7 +125,7 @@ __global__ void pack_inv_finalize_kernel(const uint32_t *__restrict__ skeys, con
     pk.oct_ent[(int64_t)b * nseg + p] = svals[(int64_t)b * nseg + p];
 }
 
-__global__ void pack_disable_kernel(int *flags) { flags[0] = 1; }
+__global__ void pack_disable_kernel(int *flags) { flags[0] = 1; flags[4] = 1; }
 
 }  // namespace clusten
 
@@ -126,8 +153,10 @@ extern "C" int clusten_pack_build(const int64_t *nbhd_idx, int B, int Nq, int M,
         return check_launch("pack_disable");
     }
     const int bt = B * pk.T;
+    cudaMemsetAsync(pk.row_imp, 0, (size_t)B * Nk, st);
     pack_tile_kernel<<<ceil_div(bt, PACK_WARPS), PACK_WARPS * 32, 0, st>>>(nbhd_idx, B, Nq, M, Nk, pk);
-    note_launches(1);
+    pack_decide_kernel<<<1, 1, 0, st>>>(pk.flags, B * Nq);
+    note_launches(2);
     return check_launch("pack_build");
 }
 

@@ -4,9 +4,11 @@
 // balanced cluster of the reference is m = 8 or 24 consecutive rows, point_utils.py:282-285, so a neighbourhood is
 // M/8 octets).  For every tile the pack holds the UNION of octets its 16 tokens reference and, per (token, union
 // position), the neighbour slot (j / 8) at which the token references that octet, or -1.  A slot is "pure" when
-// idx[i, 8s + r] == 8o + r for r = 0..7; impure slots (padded tails, arbitrary index tensors) are left to the generic
-// kernels: one impure slot, or a tile whose union exceeds U_MAX, switches the WHOLE tensor to the generic path through
-// the device-side flag (no host synchronisation: both kernels are enqueued, one of them exits at once).
+// idx[i, 8s + r] == 8o + r for r = 0..7.  A token with an impure slot (padded tail of the last cluster,
+// point_utils.py:282-283, or an arbitrary index tensor) is an "impure token": the tile kernels leave it out of the
+// tensor-core work and handle it whole in a slow in-kernel path (tok_imp / row_imp below).  Too many impure tokens,
+// or a tile whose union exceeds U_MAX, switch the WHOLE tensor to the generic kernels through the device-side flag (no
+// host synchronisation: both kernels are enqueued, one of them exits at once).
 #pragma once
 #include "common.cuh"
 
@@ -17,19 +19,22 @@ constexpr int U_MAX = 48;        // max union octets per tile (measured: <= 18 f
 constexpr int S_MAX = 32;        // max slots per token (M <= 256)
 
 struct PackView {
-    int *flags;          // [0] != 0 -> generic path; [1] max U seen; [2] impure slots; [3] tiles over U_MAX
+    int *flags;          // [0] != 0 -> generic path; [1] max U seen; [2] impure tokens; [3] tiles over U_MAX;
+                         // [4] != 0 -> the full inverse neighbour list (csr.cu) is needed (generic path or impure tokens)
     int *tile_u;         // [B*T]
     int *tile_oct;       // [B*T*U_MAX]
     int8_t *slot_of;     // [B*T*16*U_MAX]  slot of (token row, union position) or -1
     int *oct_off;        // [B*(NO+1)]      inverse lists: for key octet o the (tile, u) pairs referencing it ...
-    uint32_t *oct_ent;   // [B*T*U_MAX]     ... entry = tile*64 + u, ascending tile order
+    uint32_t *oct_ent;   // [B*T*U_MAX]     ... entry = tile*U_MAX + u, ascending tile order
+    uint8_t *tok_imp;    // [B*T*16]        1 = impure token (handled by the slow in-kernel path)
+    uint8_t *row_imp;    // [B*Nk]          1 = key row referenced by an impure token (scatter kernels fix it up)
     int T, NO;
 };
 
 struct Rows4 { const void *p; int64_t sb, sh, sn; };   // strided [B,H,N,C] operand: element strides, unit inner stride
 
 struct PackLayout {
-    size_t flags, tile_u, tile_oct, slot_of, oct_off, oct_ent, sort_ws, total;
+    size_t flags, tile_u, tile_oct, slot_of, oct_off, oct_ent, tok_imp, row_imp, sort_ws, total;
     int T, NO;
 };
 
@@ -47,6 +52,8 @@ inline PackLayout pack_layout(int B, int Nq, int Nk) {
     L.slot_of = o;  o += pack_align(bt * TILE_TOK * U_MAX);
     L.oct_off = o;  o += pack_align((size_t)B * (L.NO + 1) * 4);
     L.oct_ent = o;  o += pack_align(bt * U_MAX * 4);
+    L.tok_imp = o;  o += pack_align(bt * TILE_TOK);
+    L.row_imp = o;  o += pack_align((size_t)B * Nk);
     L.sort_ws = o;  o += 5 * pack_align((size_t)L.T * U_MAX * B * 4) + radix_sort_workspace_bytes(B, L.T * U_MAX) + 256;
     L.total = o;
     return L;
@@ -62,6 +69,8 @@ inline PackView pack_view(void *buf, int B, int Nq, int Nk) {
     v.slot_of = reinterpret_cast<int8_t *>(p + L.slot_of);
     v.oct_off = reinterpret_cast<int *>(p + L.oct_off);
     v.oct_ent = reinterpret_cast<uint32_t *>(p + L.oct_ent);
+    v.tok_imp = reinterpret_cast<uint8_t *>(p + L.tok_imp);
+    v.row_imp = reinterpret_cast<uint8_t *>(p + L.row_imp);
     v.T = L.T;
     v.NO = L.NO;
     return v;

@@ -99,11 +99,13 @@ def _check_shapes(cond, msg):
         raise RuntimeError(msg)
 
 
-def inverse_neighbour_list(nbhd_idx, Nk):
-    """(offsets int32 [B,Nk+1], entries uint32-as-int32 [B,Nq*M]) of clusten_csr_build, cached on the index tensor."""
+def inverse_neighbour_list(nbhd_idx, Nk, with_pack=False):
+    """(offsets int32 [B,Nk+1], entries uint32-as-int32 [B,Nq*M]) of clusten_csr_build, cached on the index tensor.
+    ``with_pack`` (QK / AV backward only): the list is built beside the tile pack and SKIPPED on the device when the
+    pack routes the call to the tile-union kernels, which do not need it."""
     cache = getattr(nbhd_idx, "_clusten_csr", None)
     ver = nbhd_idx._version
-    pack = neighbourhood_pack(nbhd_idx, Nk)
+    pack = neighbourhood_pack(nbhd_idx, Nk) if with_pack else None
     # (a list built beside a pack may have been skipped on the device: never reuse it for a pack-less call)
     if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr() and cache[5] == (pack is not None):
         return cache[3], cache[4]
@@ -208,7 +210,7 @@ class CLUSTENQKFunction(Function):
         d_query, d_key = _rows(d_query), _rows(d_key)
         if Nq * M == 0 or B == 0:
             return d_query.zero_(), d_key.zero_(), None
-        off, ent = inverse_neighbour_list(nbhd_idx, Nk)
+        off, ent = inverse_neighbour_list(nbhd_idx, Nk, with_pack=True)
         with torch.cuda.device(dev):
             _call("clusten_qk_bwd", dev, grad_attn.data_ptr(), query.data_ptr(), key.data_ptr(), nbhd_idx.data_ptr(),
                   off.data_ptr(), ent.data_ptr(), _lib.ptr(neighbourhood_pack(nbhd_idx, Nk, inverse=True)), d_query.data_ptr(),
@@ -258,7 +260,7 @@ class CLUSTENAVFunction(Function):
         d_v = _rows(torch.empty_like(v))
         if Nq * M == 0 or B == 0:
             return d_attn, d_v.zero_(), None
-        off, ent = inverse_neighbour_list(nbhd_idx, Nk)
+        off, ent = inverse_neighbour_list(nbhd_idx, Nk, with_pack=True)
         with torch.cuda.device(dev):
             _call("clusten_av_bwd", dev, grad_feat.data_ptr(), attn.data_ptr(), v.data_ptr(), nbhd_idx.data_ptr(),
                   off.data_ptr(), ent.data_ptr(), _lib.ptr(neighbourhood_pack(nbhd_idx, Nk, inverse=True)), d_attn.data_ptr(),

@@ -279,7 +279,7 @@ def test_tile_path_is_taken_for_clustered_idx_and_refused_for_random_idx():
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
 @pytest.mark.parametrize("H,C", [(2, 16), (3, 32), (16, 24), (4, 8)])
-@pytest.mark.parametrize("n,m,nbhd", [(1024, 8, 48), (2000, 8, 48), (1536, 24, 144)])
+@pytest.mark.parametrize("n,m,nbhd", [(1024, 8, 48), (2000, 8, 48), (1536, 24, 144), (2003, 8, 48), (655, 8, 48), (1540, 24, 144)])
 def test_tile_kernels_match_generic_and_oracle(n, m, nbhd, H, C, dtype):
     """Tensor-core tile path vs the generic row-gather path vs the oracle on the model's own neighbourhood structure
     (m = 8 / M = 48 and AFF-Base's m = 24 / M = 144), per-head dims 8/16/24/32, ragged last tile (n = 2000)."""
@@ -292,8 +292,9 @@ def test_tile_kernels_match_generic_and_oracle(n, m, nbhd, H, C, dtype):
     rnd = lambda *s: torch.randn(*s, generator=g).to(dtype).float()
     q, k, v = rnd(B, H, n, C), rnd(B, H, n, C), rnd(B, H, n, C)
     attn, d_attn, d_feat = rnd(B, H, n, M).softmax(-1).to(dtype).float(), rnd(B, H, n, M), rnd(B, H, n, C)
-    if n % m == 0:
-        assert ops.pack_flags(idx.cuda(), n)[0] == 0, ops.pack_flags(idx.cuda(), n)
+    flags = ops.pack_flags(idx.cuda(), n)
+    assert flags[0] == 0, flags                                   # tensor-core path, also with a padded last cluster ...
+    assert (flags[2] > 0) == (n % m != 0), flags                  # ... whose tokens take the slow in-kernel path
     tile_qk = _run(P.CLUSTENQKFunction.apply, [q, k, idx], d_attn, dtype)
     tile_av = _run(P.CLUSTENAVFunction.apply, [attn, v, idx], d_feat, dtype)
     ops.USE_TILE_KERNELS = False
