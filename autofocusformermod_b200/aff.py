@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction
+from .ops import CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction, cluster_attention_fused
 from .point_utils import knn_keops, merge_select, space_filling_cluster
 
 # aff.py:17-19: the relative-position table covers inputs up to 2048 px (stem grid 512)
@@ -29,6 +29,10 @@ REL_POS_WIDTH = 2048 // 4 - 1
 TABLE_WIDTH = 2 * REL_POS_WIDTH + 1
 
 _pre_tables = {}
+
+# Inference fast path: QK + bias + mask + blank token + softmax + AV in one kernel (clusten_attn_fwd) whenever autograd
+# is off.  Training keeps the signature-preserving ops (their backward is the accelerated one).
+USE_FUSED_ATTENTION = True
 
 
 def rel_pos_features(pe_idx):
@@ -120,13 +124,19 @@ class ClusterAttention(nn.Module):
         self.proj = nn.Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
 
-    def forward(self, feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup=None):
+    def forward(self, feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup=None, fused_ctx=None):
         b, n, c = feat.shape
         h = self.num_heads
         c_ = c // h
         q = (self.q(feat) * self.scale).reshape(b, n, h, c_).permute(0, 2, 1, 3)          # b h n c_ (view)
         kv = self.kv(feat).view(b, n, h, 2, c_).permute(3, 0, 2, 1, 4)                   # 2 b h n c_ (view)
         key, v = kv[0], kv[1]
+        if (fused_ctx is not None and not global_attn and USE_FUSED_ATTENTION and not torch.is_grad_enabled()
+                and (self.attn_drop.p == 0.0 or not self.training)):
+            bias_idx, mask_u8 = fused_ctx
+            out = cluster_attention_fused(q, key, v, member_idx, self.pos_embed(pe_lookup.features), bias_idx, mask_u8,
+                                          self.blank_k, self.blank_v)                    # aff.py:114-155 in one kernel
+            return self.proj_drop(self.proj(out))
         if global_attn:
             attn = q @ key.transpose(-1, -2)                                             # aff.py:121
             mask = None
@@ -169,8 +179,8 @@ class ClusterTransformerBlock(nn.Module):
             self.gamma1 = nn.Parameter(layer_scale * torch.ones(dim), requires_grad=True)
             self.gamma2 = nn.Parameter(layer_scale * torch.ones(dim), requires_grad=True)
 
-    def forward(self, feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup=None):
-        a = self.attn(self.norm1(feat), member_idx, cluster_mask, pe_idx, global_attn, pe_lookup)
+    def forward(self, feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup=None, fused_ctx=None):
+        a = self.attn(self.norm1(feat), member_idx, cluster_mask, pe_idx, global_attn, pe_lookup, fused_ctx)
         feat = feat + self.drop_path(self.gamma1 * a if self.layer_scale else a)
         m = self.mlp(self.norm2(feat))
         return feat + self.drop_path(self.gamma2 * m if self.layer_scale else m)
@@ -290,8 +300,12 @@ class BasicLayer(nn.Module):
         rel_pos = rel_pos.clamp(0, TABLE_WIDTH - 1)
         pe_idx = (rel_pos[..., 1] * TABLE_WIDTH + rel_pos[..., 0]).long()                            # aff.py:484-485
         pe_lookup = _TableLookup(pe_idx)
+        fused_ctx = None
+        if not global_attn and USE_FUSED_ATTENTION and not torch.is_grad_enabled():
+            fused_ctx = (pe_lookup.inverse.view(b, n, -1).to(torch.int32),
+                         None if cluster_mask is None else cluster_mask.to(torch.uint8).contiguous())
         for blk in self.blocks:
-            feat = blk(feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup)
+            feat = blk(feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup, fused_ctx)
         if self.downsample is None:
             return pos, feat, pos, feat
         learned_prob = self.prob_net(feat).sigmoid()                                                 # aff.py:496

@@ -270,6 +270,39 @@ class CLUSTENAVFunction(Function):
         return d_attn, d_v, None
 
 
+# ---- fused attention core (module-level fast path) -------------------------------------------------
+def cluster_attention_fused(q, key, v, nbhd_idx, bias_tab, bias_idx, mask, blank_k, blank_v, need_probs=False):
+    """Forward of the ClusterAttention core (aff.py:114-155) in one kernel: softmax over the M neighbour logits
+    (q.k + bias_tab[bias_idx, h] + mask) and the blank-token logit, times v (+ blank_v).  No autograd: inference path.
+
+    q, key, v: [B,H,N,C] (any strides, unit inner stride; q already scaled); nbhd_idx int64 [B,N,M]; bias_tab fp32
+    [R,H]; bias_idx int32 [B,N,M]; mask uint8 [B,N,M] or None; blank_k / blank_v [H*C].  Returns out as a [B,N,H*C]
+    tensor (token-major, what ``proj`` consumes) and, when ``need_probs``, the fp32 softmax output [B,H,N,M+1]."""
+    dev = _lib.require_cuda(q, key, v, nbhd_idx, bias_tab, bias_idx, mask, blank_k, blank_v)
+    B, H, Nq, C = q.shape
+    Nk, M = key.shape[2], nbhd_idx.shape[2]
+    dt = q.dtype
+    q, key, v, nbhd_idx = _rows(q), _rows(key.to(dt)), _rows(v.to(dt)), _idx(nbhd_idx)
+    bias_tab = bias_tab.to(torch.float32).contiguous()
+    _check_shapes(bias_tab.dim() == 2 and bias_tab.shape[1] == H and tuple(bias_idx.shape) == (B, Nq, M) and
+                  bias_idx.dtype == torch.int32 and bias_idx.is_contiguous(), "fused attention: bias table / index mismatch")
+    if mask is not None:
+        _check_shapes(mask.dtype == torch.uint8 and tuple(mask.shape) == (B, Nq, M) and mask.is_contiguous(), "fused attention: mask must be uint8 [B,N,M]")
+    blank_k, blank_v = blank_k.to(dt).contiguous(), blank_v.to(dt).contiguous()
+    out = torch.empty((B, Nq, H, C), dtype=dt, device=dev)
+    ov = out.permute(0, 2, 1, 3)
+    probs = torch.empty((B, H, Nq, M + 1), dtype=torch.float32, device=dev) if need_probs else None
+    if out.numel():
+        with torch.cuda.device(dev):
+            _call("clusten_attn_fwd", dev, q.data_ptr(), key.data_ptr(), v.data_ptr(), nbhd_idx.data_ptr(),
+                  _lib.ptr(neighbourhood_pack(nbhd_idx, Nk)), bias_tab.data_ptr(), bias_idx.data_ptr(), _lib.ptr(mask),
+                  blank_k.data_ptr(), blank_v.data_ptr(), out.data_ptr(), _lib.ptr(probs), B, H, Nq, Nk, C, M,
+                  *_s3(q), *_s3(key), *_s3(v), *_s3(ov), _lib.dtype_code(q),
+                  nbytes=q.element_size() * (B * H * (2 * Nq + 2 * Nk) * C) + 4 * B * Nq * M + 8 * B * Nq * M)
+    out = out.reshape(B, Nq, H * C)
+    return (out, probs) if need_probs else out
+
+
 # ---- WF --------------------------------------------------------------------------------------------------------------
 class CLUSTENWFFunction(Function):
     """weights times feature: feat_new[b,i,ic,c] = sum_j weights[b,i,j,ic] * feat[b,nbhd_idx[b,i,j],c]  (clusten.py:71-94)"""

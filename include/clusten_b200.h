@@ -106,6 +106,22 @@ int clusten_av_bwd(const void *d_feat, const void *attn, const void *v,
                    int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t dv_sb, int64_t dv_sh, int64_t dv_sn,
                    int dtype, void *stream);
 
+/* ---- fused ClusterAttention core, forward (aff.py:114-155): QK + position bias + cluster mask + blank
+ * token + softmax + AV in one kernel.
+ *   logit[b,h,i,j] = q[b,h,i,:].k[b,h,idx[b,i,j],:] + bias_tab[bias_idx[b,i,j]*H + h] + (mask && !mask[b,i,j] ? -100 : 0), j < M
+ *   logit[b,h,i,M] = q[b,h,i,:].blank_k[h*C:(h+1)*C];   p = softmax(logit[b,h,i,0..M])
+ *   out[b,h,i,:]   = sum_j p[j] v[b,h,idx[b,i,j],:] + p[M] blank_v[h*C:(h+1)*C]
+ * q is expected pre-scaled (aff.py:104).  q/k/v/out: strided rows like clusten_qk_fwd; bias_tab fp32 [R,H]; bias_idx int32
+ * [B,Nq,M]; mask uint8 [B,Nq,M] or NULL; blank_k/blank_v: [H*C] of the call's dtype; probs: fp32 [B,H,Nq,M+1] or NULL
+ * (the softmax output, written once for a backward pass).  pack may be NULL (generic kernel only). */
+int clusten_attn_fwd(const void *q, const void *k, const void *v, const int64_t *nbhd_idx, const void *pack,
+                     const float *bias_tab, const int32_t *bias_idx, const uint8_t *mask,
+                     const void *blank_k, const void *blank_v, void *out, float *probs,
+                     int B, int H, int Nq, int Nk, int C, int M,
+                     int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t k_sb, int64_t k_sh, int64_t k_sn,
+                     int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t o_sb, int64_t o_sh, int64_t o_sn,
+                     int dtype, void *stream);
+
 /* ---- WF: out[b,i,ic,c] = sum_j w[b,i,j,ic] * f[b,idx[b,i,j],c]             (clustenwf_cuda_kernel.cu:41-49)
  * w [B,Nq,M,IC] contiguous, f rows base + b*f_sb + n*f_sn + c, out [B,Nq,IC,C] contiguous.  IC in {1,2,4,8}. */
 int clusten_wf_fwd(const void *w, const void *f, const int64_t *nbhd_idx, void *out,

@@ -91,3 +91,21 @@ def test_training_mode_caches_stage0_clustering():
     cache = m.layers[0]._grid_cache
     m(x)
     assert m.layers[0]._grid_cache is cache
+
+
+def test_fused_inference_path_matches_unfused_ops():
+    """AFF forward under no_grad takes the fused attention kernel; it must agree with the op-by-op path."""
+    from autofocusformermod_b200 import aff
+    cfg = ao.PRESETS["test"]
+    m = _model("test", ao.synthetic_state(cfg, seed=2)).eval()
+    x = ao.synthetic_images(2, 100, 134, seed=2).cuda()        # padded clusters -> mask + impure tokens
+    with torch.no_grad():
+        fused = m(x)
+        aff.USE_FUSED_ATTENTION = False
+        try:
+            plain = m(x)
+        finally:
+            aff.USE_FUSED_ATTENTION = True
+    for i in range(2, 6):
+        assert torch.equal(fused[f"res{i}_pos"], plain[f"res{i}_pos"])
+        assert rel_err(fused[f"res{i}"], plain[f"res{i}"]) <= 2e-5, f"res{i}"

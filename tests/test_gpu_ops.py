@@ -309,3 +309,51 @@ def test_tile_kernels_match_generic_and_oracle(n, m, nbhd, H, C, dtype):
     _check(tile_av, ref_av, dtype, "AV tile")
     _check(gen_qk, ref_qk, dtype, "QK generic")
     _check(gen_av, ref_av, dtype, "AV generic")
+
+
+def _fused_reference(q, k, v, idx, bias_tab, bias_idx, mask, blank_k, blank_v):
+    """aff.py:114-155 with the oracle ops (CPU, fp32): returns (out [B,N,H*C], probs [B,H,N,M+1])."""
+    B, H, N, C = q.shape
+    attn = co.qk_forward(q, k, idx)
+    attn = attn + bias_tab[bias_idx.long()].permute(0, 3, 1, 2)
+    if mask is not None:
+        attn = attn + (1 - mask.long().reshape(B, 1, N, -1)) * (-100)
+    blank = (q * blank_k.reshape(1, H, 1, C)).sum(-1, keepdim=True)
+    p = torch.cat([attn, blank], dim=-1).softmax(-1)
+    out = co.av_forward(p[..., :-1], v, idx) + p[..., -1:] * blank_v.reshape(1, H, 1, C)
+    return out.permute(0, 2, 1, 3).reshape(B, N, H * C), p
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("H,C", [(2, 16), (3, 32), (16, 24)])
+@pytest.mark.parametrize("n,m,nbhd,kind", [(1024, 8, 48, "clustered"), (2003, 8, 48, "clustered"), (1540, 24, 144, "clustered"),
+                                            (300, 8, 48, "random")])
+def test_fused_attention_core(n, m, nbhd, kind, H, C, dtype):
+    """clusten_attn_fwd (QK + bias + mask + blank + softmax + AV fused) against the op-by-op oracle composition, on the
+    tensor-core tile path (clustered idx, incl. padded last clusters -> cluster mask + impure tokens, and AFF-Base's
+    M = 144) and on the generic kernel (random idx)."""
+    from autofocusformermod_b200 import ops
+    B = 2
+    if kind == "clustered":
+        _, idx, mask, _ = inputs.structured_neighbourhood(B, n, 64, 64, m, nbhd, seed=n)
+    else:
+        idx, mask = inputs.random_neighbourhood(B, n, n, nbhd, seed=n), None
+    M = idx.shape[-1]
+    g = torch.Generator().manual_seed(n + H)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dtype).float()
+    q, k, v = rnd(B, H, n, C) * C ** -0.5, rnd(B, H, n, C), rnd(B, H, n, C)
+    q = q.to(dtype).float()
+    R = 37
+    bias_tab = torch.randn(R, H, generator=g)
+    bias_idx = torch.randint(0, R, (B, n, M), generator=g, dtype=torch.int32)
+    blank_k, blank_v = rnd(H * C), rnd(H * C)
+    ref_out, ref_p = _fused_reference(q, k, v, idx, bias_tab, bias_idx, mask, blank_k, blank_v)
+    cu = lambda t: None if t is None else t.cuda()
+    out, probs = ops.cluster_attention_fused(q.cuda().to(dtype), k.cuda().to(dtype), v.cuda().to(dtype), idx.cuda(), bias_tab.cuda(),
+                                             bias_idx.cuda(), None if mask is None else mask.to(torch.uint8).cuda(),
+                                             blank_k.cuda().to(dtype), blank_v.cuda().to(dtype), need_probs=True)
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    assert rel_err(out.float(), ref_out) <= tol
+    assert rel_err(probs, ref_p) <= tol
+    if kind == "clustered":
+        assert ops.pack_flags(idx.cuda(), n)[0] == 0
