@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libclusten_b200.so")
-SOURCES = ["clusten_attn.cu", "clusten_tile.cu", "clusten_fused.cu", "pack.cu", "clusten_wf.cu", "csr.cu", "sort.cu", "knn.cu", "sfc.cu", "select.cu"]
+SOURCES = ["clusten_attn.cu", "clusten_tile.cu", "clusten_tile2.cu", "clusten_fused.cu", "pack.cu", "clusten_wf.cu", "csr.cu", "sort.cu", "knn.cu", "sfc.cu", "select.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -30,6 +30,8 @@ SIGNATURES = {
     "clusten_av_fwd": (_I, [_P] * 5 + [_I] * 6 + [_L] * 9 + [_I, _P]),
     "clusten_av_bwd": (_I, [_P] * 9 + [_I] * 6 + [_L] * 12 + [_I, _P]),
     "clusten_attn_fwd": (_I, [_P] * 12 + [_I] * 6 + [_L] * 12 + [_I, _P]),
+    "clusten_table_gather": (_I, [_P, _P, _I, _P, _L, _I, _I, _I, _P]),
+    "clusten_table_grad": (_I, [_P, _P, _I, _P, _L, _I, _I, _L, _L, _L, _L, _I, _P]),
     "clusten_wf_fwd": (_I, [_P] * 4 + [_I] * 6 + [_L] * 2 + [_I, _P]),
     "clusten_wf_bwd": (_I, [_P] * 8 + [_I] * 6 + [_L] * 4 + [_I, _P]),
     "clusten_wg_fwd": (_I, [_P] * 4 + [_I] * 5 + [_L] * 2 + [_I, _P]),

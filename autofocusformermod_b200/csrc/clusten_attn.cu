@@ -251,6 +251,14 @@ template <typename T> int launch_axpy_tile(const T *W, const T *Y, const int64_t
 template <typename T> int launch_scat_tile(const T *W, const T *X, const int32_t *csr_off, const uint32_t *csr_ent, const void *pack,
                                            T *out, int B, int H, int Nq, int Nk, int C, int M, Rows4 w, Rows4 x, Rows4 o, cudaStream_t st);
 
+template <typename T> int launch_dot_tile2(const T *X, const T *Y, const int64_t *idx, const void *pack, T *out, int B, int H, int Nq,
+                                           int Nk, int C, int M, Rows4 x, Rows4 y, cudaStream_t st);
+template <typename T> int launch_axpy_tile2(const T *W, const T *Y, const int64_t *idx, const void *pack, T *out, int B, int H, int Nq,
+                                            int Nk, int C, int M, Rows4 w, Rows4 y, Rows4 o, cudaStream_t st);
+
+template <typename T> int launch_scat_tile2(const T *W, const T *X, const int32_t *csr_off, const uint32_t *csr_ent, const void *pack,
+                                            T *out, int B, int H, int Nq, int Nk, int C, int M, Rows4 w, Rows4 x, Rows4 o, cudaStream_t st);
+
 static inline Rows4 r4(const Rows &r) { return Rows4{r.p, r.sb, r.sh, r.sn}; }
 static inline const int *tile_flag_of(const void *pack) { return reinterpret_cast<const int *>(pack); }   // PackView.flags is at offset 0
 // grid of a generic kernel: everything when it is the only kernel, a short grid-stride grid when it is the (usually
@@ -281,7 +289,9 @@ static int launch_dot(const T *X, const T *Y, const int64_t *idx, const void *pa
     if ((int64_t)B * Nq == 0) return 0;
     const int *flag = nullptr;
     if (pack && tile_dot_eligible<T>(C, M, r4(x), r4(y))) {
-        if (int e = launch_dot_tile<T>(X, Y, idx, pack, out, B, H, Nq, Nk, C, M, r4(x), r4(y), st)) return e;
+        int e = launch_dot_tile2<T>(X, Y, idx, pack, out, B, H, Nq, Nk, C, M, r4(x), r4(y), st);      // second generation first
+        if (e < 0) e = launch_dot_tile<T>(X, Y, idx, pack, out, B, H, Nq, Nk, C, M, r4(x), r4(y), st);
+        if (e) return e;
         flag = tile_flag_of(pack);
     }
     if (vec_ok<T>(C, {x, y})) {
@@ -306,7 +316,9 @@ static int launch_axpy(const T *W, const T *Y, const int64_t *idx, const void *p
     if ((int64_t)B * Nq == 0) return 0;
     const int *flag = nullptr;
     if (pack && tile_axpy_eligible<T>(C, M, r4(w), r4(y), r4(o))) {
-        if (int e = launch_axpy_tile<T>(W, Y, idx, pack, out, B, H, Nq, Nk, C, M, r4(w), r4(y), r4(o), st)) return e;
+        int e = launch_axpy_tile2<T>(W, Y, idx, pack, out, B, H, Nq, Nk, C, M, r4(w), r4(y), r4(o), st);
+        if (e < 0) e = launch_axpy_tile<T>(W, Y, idx, pack, out, B, H, Nq, Nk, C, M, r4(w), r4(y), r4(o), st);
+        if (e) return e;
         flag = tile_flag_of(pack);
     }
     if (vec_ok<T>(C, {y, o})) {
@@ -332,7 +344,9 @@ static int launch_csr(const T *W, const T *X, const int32_t *off, const uint32_t
     if ((int64_t)B * Nk == 0) return 0;
     const int *flag = nullptr;
     if (pack && tile_scat_eligible<T>(C, M, r4(w), r4(x), r4(o))) {
-        if (int e = launch_scat_tile<T>(W, X, off, ent, pack, out, B, H, Nq, Nk, C, M, r4(w), r4(x), r4(o), st)) return e;
+        int e = launch_scat_tile2<T>(W, X, off, ent, pack, out, B, H, Nq, Nk, C, M, r4(w), r4(x), r4(o), st);
+        if (e < 0) e = launch_scat_tile<T>(W, X, off, ent, pack, out, B, H, Nq, Nk, C, M, r4(w), r4(x), r4(o), st);
+        if (e) return e;
         flag = tile_flag_of(pack);
     }
     if (vec_ok<T>(C, {x, o})) {

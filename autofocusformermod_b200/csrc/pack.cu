@@ -66,16 +66,27 @@ pack_tile_kernel(const int64_t *__restrict__ idx, int B, int Nq, int M, int Nk, 
     __syncwarp();
     // impure tokens: no slots in the tile structure, flagged for the slow paths, their key rows flagged for the scatter
     int bad = 0;
+    unsigned bad_rows = 0;
     for (int r = 0; r < TILE_TOK; ++r) {
         const int rb_ = row_bad[warp][r];
         if (lane == 0) pk.tok_imp[(int64_t)bt * TILE_TOK + r] = (uint8_t)rb_;
         if (!rb_) continue;
+        if (lane == 0) bad_rows |= 1u << r;
         ++bad;
         for (int u = lane; u < U_MAX; u += 32) slot_s[warp][r][u] = -1;
         const int64_t *p = idx + ((int64_t)b * Nq + i0 + r) * M;
         for (int j = lane; j < M; j += 32) {
             const int64_t v = p[j];
-            if (v >= 0 && v < (int64_t)Nk) pk.row_imp[(int64_t)b * Nk + v] = 1;
+            if (v >= 0 && v < (int64_t)Nk) {
+                // first marker of a key row also appends it to the flagged-row list (byte-wide exchange through the aligned word)
+                unsigned *wp = reinterpret_cast<unsigned *>(pk.row_imp + (((int64_t)b * Nk + v) & ~(int64_t)3));
+                const unsigned bit = 1u << (8 * (((int64_t)b * Nk + v) & 3));
+                const unsigned old = atomicOr(wp, bit);
+                if (!(old & bit)) {
+                    const int pos = atomicAdd(pk.flags + 5, 1);
+                    if (pos < pk.rimp_cap) pk.rimp_list[pos] = (int)((int64_t)b * Nk + v);
+                }
+            }
         }
     }
     __syncwarp();
@@ -88,7 +99,11 @@ pack_tile_kernel(const int64_t *__restrict__ idx, int B, int Nq, int M, int Nk, 
     if (lane == 0) {
         pk.tile_u[bt] = Uc;
         atomicMax(pk.flags + 1, U);
-        if (bad) atomicAdd(pk.flags + 2, bad);
+        if (bad) {
+            int pos = atomicAdd(pk.flags + 2, bad);
+            for (; bad_rows; bad_rows &= bad_rows - 1, ++pos)
+                if (pos < pk.imp_cap) pk.imp_list[pos] = b * Nq + i0 + __ffs(bad_rows) - 1;
+        }
         if (U > U_MAX) atomicAdd(pk.flags + 3, 1);
     }
 }

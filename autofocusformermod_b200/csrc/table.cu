@@ -1,0 +1,111 @@
+// Relative-position table lookup and its gradient (sm_100a).
+//
+// The reference evaluates pos_embed / weight_net on the whole 1023^2-row pre_table and gathers it with pe_idx
+// (mask2former/modeling/backbone/aff.py:129-132, 346-349).  The caller here evaluates the network on the U table rows
+// a stage actually references and gathers with the inverse map:
+//   fwd : out[e, c]  = tab[inv[e], c]                     e < n, c < CH        (a plain gather; output dtype = table dtype)
+//   bwd : d_tab[r,c] = sum_{e : inv[e] = r} d_out[e, c]   r < U                (fp32 accumulation; d_out addressed as
+//         base + (e / n_per)*d_sb + (e % n_per)*d_se + c*d_sc, so the permuted [B,H,N,M] gradient of aff.py:132 needs no copy)
+// ATen's backward of `tab[inv]` (index_put_ with accumulate) sorts the n indices and then walks each unique row's
+// duplicates serially -- with n = B*N*M ~ 25 M lookups into U ~ 10^3 rows that is hundreds of milliseconds per block.
+// Here every CTA accumulates its slice of e into a shared-memory copy of the table (fp32 shared atomics; lanes of a warp
+// hold consecutive neighbours of one token = distinct rows, so intra-warp conflicts are rare) and flushes the non-zero
+// entries with one global fp32 atomic each.  Large tables (U*CH floats > 48 KB) use global atomics directly.
+#include "common.cuh"
+
+namespace clusten {
+
+constexpr int TG_SMEM_FLOATS = 12 * 1024;
+
+template <typename T, typename I>
+__global__ void __launch_bounds__(256)
+table_grad_smem_kernel(const T *__restrict__ dout, const I *__restrict__ inv, float *__restrict__ dtab,
+                       int64_t n, int U, int CH, int64_t n_per, int64_t d_sb, int64_t d_se, int64_t d_sc, int64_t per_cta) {
+    extern __shared__ float tab_s[];
+    const int tot = U * CH;
+    for (int x = threadIdx.x; x < tot; x += blockDim.x) tab_s[x] = 0.f;
+    __syncthreads();
+    const int64_t e0 = (int64_t)blockIdx.x * per_cta, e1 = min(n, e0 + per_cta);
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const int r = (int)inv[e];
+        const int64_t b = e / n_per;
+        const T *dp = dout + b * d_sb + (e - b * n_per) * d_se;
+        for (int c = 0; c < CH; ++c) atomicAdd(tab_s + r * CH + c, to_f(dp[c * d_sc]));
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < tot; x += blockDim.x) {
+        const float v = tab_s[x];
+        if (v != 0.f) atomicAdd(dtab + x, v);
+    }
+}
+
+template <typename T, typename I>
+__global__ void __launch_bounds__(256)
+table_grad_global_kernel(const T *__restrict__ dout, const I *__restrict__ inv, float *__restrict__ dtab,
+                         int64_t n, int CH, int64_t n_per, int64_t d_sb, int64_t d_se, int64_t d_sc) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = (int64_t)inv[e];
+        const int64_t b = e / n_per;
+        const T *dp = dout + b * d_sb + (e - b * n_per) * d_se;
+        for (int c = 0; c < CH; ++c) atomicAdd(dtab + r * CH + c, to_f(dp[c * d_sc]));
+    }
+}
+
+template <typename T, typename I>
+__global__ void __launch_bounds__(256)
+table_gather_kernel(const T *__restrict__ tab, const I *__restrict__ inv, T *__restrict__ out, int64_t n, int CH) {
+    // one thread per (e, c); consecutive threads -> consecutive c of one e: coalesced writes, table reads hit L1/L2
+    const int64_t tot = n * CH;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < tot; x += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = x / CH;
+        const int c = (int)(x - e * CH);
+        out[x] = tab[(int64_t)inv[e] * CH + c];
+    }
+}
+
+template <typename T, typename I>
+static int launch_table_grad(const T *dout, const I *inv, float *dtab, int64_t n, int U, int CH, int64_t n_per, int64_t d_sb,
+                             int64_t d_se, int64_t d_sc, cudaStream_t st) {
+    if (n == 0) return 0;
+    if ((int64_t)U * CH <= TG_SMEM_FLOATS) {
+        const int grid = (int)std::min<int64_t>(148 * 4, (n + 2047) / 2048);
+        const int64_t per_cta = (n + grid - 1) / grid;
+        table_grad_smem_kernel<T, I><<<grid, 256, (size_t)U * CH * sizeof(float), st>>>(dout, inv, dtab, n, U, CH, n_per, d_sb, d_se, d_sc, per_cta);
+    } else {
+        const int grid = (int)std::min<int64_t>(148 * 8, (n + 255) / 256);
+        table_grad_global_kernel<T, I><<<grid, 256, 0, st>>>(dout, inv, dtab, n, CH, n_per, d_sb, d_se, d_sc);
+    }
+    note_launches(1);
+    return check_launch("table_grad");
+}
+
+}  // namespace clusten
+
+using namespace clusten;
+
+extern "C" int clusten_table_gather(const void *tab, const void *inv, int inv_is_i64, void *out, int64_t n, int U, int CH,
+                                    int dtype, void *stream) {
+    if (n < 0 || U <= 0 || CH <= 0) return set_error(CLUSTEN_EINVAL, "bad sizes n=%lld U=%d CH=%d", (long long)n, U, CH);
+    if (!tab || !inv || !out) return set_error(CLUSTEN_EINVAL, "null pointer");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)std::min<int64_t>(148 * 16, (n * CH + 255) / 256);
+    CLUSTEN_DISPATCH_DTYPE(dtype, {
+        if (inv_is_i64) table_gather_kernel<T, int64_t><<<grid, 256, 0, st>>>((const T *)tab, (const int64_t *)inv, (T *)out, n, CH);
+        else table_gather_kernel<T, int32_t><<<grid, 256, 0, st>>>((const T *)tab, (const int32_t *)inv, (T *)out, n, CH);
+    });
+    note_launches(1);
+    return check_launch("table_gather");
+}
+
+extern "C" int clusten_table_grad(const void *d_out, const void *inv, int inv_is_i64, float *d_tab, int64_t n, int U, int CH,
+                                  int64_t n_per, int64_t d_sb, int64_t d_se, int64_t d_sc, int dtype, void *stream) {
+    if (n < 0 || U <= 0 || CH <= 0 || n_per <= 0) return set_error(CLUSTEN_EINVAL, "bad sizes n=%lld U=%d CH=%d", (long long)n, U, CH);
+    if (!d_out || !inv || !d_tab) return set_error(CLUSTEN_EINVAL, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    CLUSTEN_DISPATCH_DTYPE(dtype, {
+        if (inv_is_i64) return launch_table_grad<T, int64_t>((const T *)d_out, (const int64_t *)inv, d_tab, n, U, CH, n_per, d_sb, d_se, d_sc, st);
+        return launch_table_grad<T, int32_t>((const T *)d_out, (const int32_t *)inv, d_tab, n, U, CH, n_per, d_sb, d_se, d_sc, st);
+    });
+    return 0;
+}

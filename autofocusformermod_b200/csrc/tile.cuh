@@ -10,6 +10,8 @@
 // or a tile whose union exceeds U_MAX, switch the WHOLE tensor to the generic kernels through the device-side flag (no
 // host synchronisation: both kernels are enqueued, one of them exits at once).
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace clusten {
@@ -28,14 +30,16 @@ struct PackView {
     uint32_t *oct_ent;   // [B*T*U_MAX]     ... entry = tile*U_MAX + u, ascending tile order
     uint8_t *tok_imp;    // [B*T*16]        1 = impure token (handled by the slow in-kernel path)
     uint8_t *row_imp;    // [B*Nk]          1 = key row referenced by an impure token (scatter kernels fix it up)
-    int T, NO;
+    int *imp_list;       // [imp_cap]       global ids (b*Nq + i) of the impure tokens, any order; count = min(flags[2], imp_cap)
+    int *rimp_list;      // [rimp_cap]      global ids (b*Nk + r) of the key rows with row_imp set (each once); count = min(flags[5], rimp_cap)
+    int T, NO, imp_cap, rimp_cap;
 };
 
 struct Rows4 { const void *p; int64_t sb, sh, sn; };   // strided [B,H,N,C] operand: element strides, unit inner stride
 
 struct PackLayout {
-    size_t flags, tile_u, tile_oct, slot_of, oct_off, oct_ent, tok_imp, row_imp, sort_ws, total;
-    int T, NO;
+    size_t flags, tile_u, tile_oct, slot_of, oct_off, oct_ent, tok_imp, row_imp, imp_list, rimp_list, sort_ws, total;
+    int T, NO, imp_cap, rimp_cap;
 };
 
 inline size_t pack_align(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -54,6 +58,11 @@ inline PackLayout pack_layout(int B, int Nq, int Nk) {
     L.oct_ent = o;  o += pack_align(bt * U_MAX * 4);
     L.tok_imp = o;  o += pack_align(bt * TILE_TOK);
     L.row_imp = o;  o += pack_align((size_t)B * Nk);
+    // the tile path is only taken while impure tokens <= max(64, tokens / 16) (pack_decide_kernel): the lists never need more
+    L.imp_cap = (int)std::min<int64_t>((int64_t)B * Nq, (int64_t)B * Nq / 16 + 64);
+    L.rimp_cap = (int)std::min<int64_t>((int64_t)B * Nk, (int64_t)1 << 30);
+    L.imp_list = o; o += pack_align((size_t)L.imp_cap * 4);
+    L.rimp_list = o; o += pack_align((size_t)L.rimp_cap * 4);
     L.sort_ws = o;  o += 5 * pack_align((size_t)L.T * U_MAX * B * 4) + radix_sort_workspace_bytes(B, L.T * U_MAX) + 256;
     L.total = o;
     return L;
@@ -71,6 +80,10 @@ inline PackView pack_view(void *buf, int B, int Nq, int Nk) {
     v.oct_ent = reinterpret_cast<uint32_t *>(p + L.oct_ent);
     v.tok_imp = reinterpret_cast<uint8_t *>(p + L.tok_imp);
     v.row_imp = reinterpret_cast<uint8_t *>(p + L.row_imp);
+    v.imp_list = reinterpret_cast<int *>(p + L.imp_list);
+    v.rimp_list = reinterpret_cast<int *>(p + L.rimp_list);
+    v.imp_cap = L.imp_cap;
+    v.rimp_cap = L.rimp_cap;
     v.T = L.T;
     v.NO = L.NO;
     return v;

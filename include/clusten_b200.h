@@ -122,6 +122,16 @@ int clusten_attn_fwd(const void *q, const void *k, const void *v, const int64_t 
                      int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t o_sb, int64_t o_sh, int64_t o_sn,
                      int dtype, void *stream);
 
+/* ---- relative-position table lookup (aff.py:129-132, 346-349) restricted to the table rows a stage references:
+ *   gather: out[e,c] = tab[inv[e],c]  (e < n, c < CH; tab/out of the call's dtype; inv int32 or int64)
+ *   grad  : d_tab[r,c] += sum_{e: inv[e]=r} d_out[e,c], fp32, d_tab [U,CH] must be zeroed by the caller; d_out addressed
+ *           as base + (e / n_per)*d_sb + (e % n_per)*d_se + c*d_sc (element strides) so permuted gradients need no copy.
+ *   Replaces ATen index / index_put_(accumulate) on this path; the gradient uses fp32 atomics (summation order is not fixed). */
+int clusten_table_gather(const void *tab, const void *inv, int inv_is_i64, void *out, int64_t n, int U, int CH,
+                         int dtype, void *stream);
+int clusten_table_grad(const void *d_out, const void *inv, int inv_is_i64, float *d_tab, int64_t n, int U, int CH,
+                       int64_t n_per, int64_t d_sb, int64_t d_se, int64_t d_sc, int dtype, void *stream);
+
 /* ---- WF: out[b,i,ic,c] = sum_j w[b,i,j,ic] * f[b,idx[b,i,j],c]             (clustenwf_cuda_kernel.cu:41-49)
  * w [B,Nq,M,IC] contiguous, f rows base + b*f_sb + n*f_sn + c, out [B,Nq,IC,C] contiguous.  IC in {1,2,4,8}. */
 int clusten_wf_fwd(const void *w, const void *f, const int64_t *nbhd_idx, void *out,
