@@ -29,7 +29,13 @@ SIGNATURES = {
     "clusten_qk_bwd": (_I, [_P] * 9 + [_I] * 6 + [_L] * 12 + [_I, _P]),
     "clusten_av_fwd": (_I, [_P] * 5 + [_I] * 6 + [_L] * 9 + [_I, _P]),
     "clusten_av_bwd": (_I, [_P] * 9 + [_I] * 6 + [_L] * 12 + [_I, _P]),
-    "clusten_attn_fwd": (_I, [_P] * 12 + [_I] * 6 + [_L] * 12 + [_I, _P]),
+    "clusten_attn_fwd": (_I, [_P] * 13 + [_I] * 6 + [_L] * 12 + [_I, _P]),
+    "clusten_attn_bwd": (_I, [_P] * 18 + [_I] * 6 + [_L] * 18 + [_I, _P]),
+    "clusten_scatter_rows": (_I, [_P] * 6 + [_I] * 6 + [_L] * 9 + [_I, _P]),
+    "clusten_layer_norm_fwd": (_I, [_P] * 6 + [_L, _I, _c.c_float, _I, _I, _P]),
+    "clusten_layer_norm_bwd": (_I, [_P] * 8 + [_L, _I, _I, _I, _P]),
+    "clusten_prepare_workspace_bytes": (_Z, []),
+    "clusten_stage_prepare": (_I, [_P] * 4 + [_I] * 5 + [_P] * 6 + [_I, _P, _P, _Z, _P]),
     "clusten_table_gather": (_I, [_P, _P, _I, _P, _L, _I, _I, _I, _P]),
     "clusten_table_grad": (_I, [_P, _P, _I, _P, _L, _I, _I, _L, _L, _L, _L, _I, _P]),
     "clusten_wf_fwd": (_I, [_P] * 4 + [_I] * 6 + [_L] * 2 + [_I, _P]),

@@ -21,8 +21,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction, cluster_attention_fused
-from .point_utils import knn_keops, merge_select, space_filling_cluster
+from .ops import (CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction, cluster_attention_core, cluster_attention_fused,
+                  layer_norm, table_lookup)
+from .point_utils import knn_keops, merge_select, space_filling_cluster, stage_prepare
 
 # aff.py:17-19: the relative-position table covers inputs up to 2048 px (stem grid 512)
 REL_POS_WIDTH = 2048 // 4 - 1
@@ -60,11 +61,15 @@ class _TableLookup:
     every merge.  The rows a stage references are a few thousand (neighbours are a few stem-grid cells away), and they
     are the same for every block of the stage, so the unique rows and the inverse map are computed once per stage."""
 
-    def __init__(self, pe_idx):
-        self.shape = pe_idx.shape
-        uniq, inv = torch.unique(pe_idx.reshape(-1), return_inverse=True)
+    def __init__(self, pe_idx=None, uniq=None, inverse=None):
+        if pe_idx is not None:
+            self.shape = pe_idx.shape
+            uniq, inverse = torch.unique(pe_idx.reshape(-1), return_inverse=True)
+        else:                                             # prepared by clusten_stage_prepare (no sort)
+            self.shape = inverse.shape
+            inverse = inverse.reshape(-1)
         self.features = rel_pos_features(uniq)            # [U, 5]
-        self.inverse = inv                                # [prod(shape)]
+        self.inverse = inverse                            # [prod(shape)], int64 or int32
 
     def select(self, rows):
         """Keep only the given token rows (dim 1) of the lookup: used by ClusterMerging after top-k."""
@@ -76,7 +81,34 @@ class _TableLookup:
 
     def __call__(self, net):
         t = net(self.features)                            # [U, ch]
-        return t[self.inverse].reshape(*self.shape, t.shape[-1])
+        return table_lookup(t, self.inverse.view(self.shape))
+
+
+class LayerNorm(nn.LayerNorm):
+    """``nn.LayerNorm`` (same parameters / state_dict) computed by clusten_layer_norm_* for CUDA inputs with C <= 1024: one
+    warp per token row instead of ATen's CTA per row (16.7 % of the AFF-Mini forward, 15 % of the Tiny training step).
+    Under autocast ATen returns fp32; ``to_autocast_dtype`` returns the autocast dtype instead for norms whose only consumers
+    are Linear layers (they would cast to it anyway -- same values, half the bytes)."""
+
+    to_autocast_dtype = False
+
+    def forward(self, x):
+        C = x.shape[-1]
+        if (not x.is_cuda or len(self.normalized_shape) != 1 or C > 1024 or self.weight is None or self.bias is None
+                or x.dtype not in (torch.float32, torch.float16, torch.bfloat16)):
+            return super().forward(x)
+        out_dtype = x.dtype
+        if torch.is_autocast_enabled():
+            out_dtype = torch.get_autocast_gpu_dtype() if self.to_autocast_dtype else torch.float32
+        return layer_norm(x, self.weight, self.bias, self.eps, out_dtype)
+
+
+def _inner_norm(norm_layer, dim):
+    """A norm whose output only feeds Linear layers."""
+    n = norm_layer(dim)
+    if isinstance(n, LayerNorm):
+        n.to_autocast_dtype = True
+    return n
 
 
 class DropPath(nn.Module):
@@ -128,8 +160,18 @@ class ClusterAttention(nn.Module):
         b, n, c = feat.shape
         h = self.num_heads
         c_ = c // h
-        q = (self.q(feat) * self.scale).reshape(b, n, h, c_).permute(0, 2, 1, 3)          # b h n c_ (view)
-        kv = self.kv(feat).view(b, n, h, 2, c_).permute(3, 0, 2, 1, 4)                   # 2 b h n c_ (view)
+        q_tok = (self.q(feat) * self.scale).reshape(b, n, h, c_)                         # token-major b n h c_
+        kv_tok = self.kv(feat).view(b, n, h, 2, c_)
+        fusable = (fused_ctx is not None and not global_attn and USE_FUSED_ATTENTION
+                   and (self.attn_drop.p == 0.0 or not self.training))
+        if fusable and torch.is_grad_enabled() and q_tok.dtype in (torch.float16, torch.bfloat16):
+            # training fast path: one differentiable op, fp16 / bf16 (autocast); fp32 training keeps the separate ops below
+            bias_idx, mask_u8 = fused_ctx
+            out = cluster_attention_core(q_tok, kv_tok, self.pos_embed(pe_lookup.features), self.blank_k, self.blank_v,
+                                         member_idx, bias_idx, mask_u8)
+            return self.proj_drop(self.proj(out))
+        q = q_tok.permute(0, 2, 1, 3)                                                    # b h n c_ (view)
+        kv = kv_tok.permute(3, 0, 2, 1, 4)                                               # 2 b h n c_ (view)
         key, v = kv[0], kv[1]
         if (fused_ctx is not None and not global_attn and USE_FUSED_ATTENTION and not torch.is_grad_enabled()
                 and (self.attn_drop.p == 0.0 or not self.training)):
@@ -165,13 +207,13 @@ class ClusterTransformerBlock(nn.Module):
     """LN -> ClusterAttention -> residual -> LN -> MLP -> residual, optional layer scale (aff.py:166-238)."""
 
     def __init__(self, dim, num_heads, mlp_ratio=2.0, drop=0.0, attn_drop=0.0, drop_path=0.0, layer_scale=0.0,
-                 act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+                 act_layer=nn.GELU, norm_layer=LayerNorm):
         super().__init__()
         self.dim, self.num_heads, self.mlp_ratio = dim, num_heads, mlp_ratio
-        self.norm1 = norm_layer(dim)
+        self.norm1 = _inner_norm(norm_layer, dim)
         self.attn = ClusterAttention(dim, num_heads=num_heads, attn_drop=attn_drop, proj_drop=drop)
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
-        self.norm2 = norm_layer(dim)
+        self.norm2 = _inner_norm(norm_layer, dim)
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
         self.layer_scale = False
         if layer_scale is not None and type(layer_scale) in [int, float] and layer_scale > 0:
@@ -190,12 +232,12 @@ class ClusterMerging(nn.Module):
     """Adaptive downsampling: importance top-k + reserve grid, then a PointConv merge of each kept token's
     neighbourhood (aff.py:245-365)."""
 
-    def __init__(self, dim, out_dim, norm_layer=nn.LayerNorm, alpha=4.0, ds_rate=0.25, reserve_on=True):
+    def __init__(self, dim, out_dim, norm_layer=LayerNorm, alpha=4.0, ds_rate=0.25, reserve_on=True):
         super().__init__()
         self.dim, self.pos_dim, self.alpha, self.ds_rate, self.reserve_on = dim, 2, alpha, ds_rate, reserve_on
         inner_ch = 4
         self.weight_net = nn.Sequential(nn.Linear(self.pos_dim + 3, inner_ch, bias=True), nn.LayerNorm(inner_ch), nn.GELU())
-        self.norm = norm_layer(inner_ch * dim)
+        self.norm = _inner_norm(norm_layer, inner_ch * dim)
         self.linear = nn.Linear(dim * inner_ch, out_dim)
 
     def select(self, pos, learned_prob, stride, reserve_num):
@@ -246,7 +288,7 @@ class BasicLayer(nn.Module):
     """One AFF stage: cluster -> neighbourhoods -> transformer blocks -> (optional) merge (aff.py:368-510)."""
 
     def __init__(self, dim, out_dim, cluster_size, nbhd_size, depth, num_heads, mlp_ratio, alpha=4.0, ds_rate=0.25,
-                 reserve_on=True, drop=0.0, attn_drop=0.0, drop_path=0.0, norm_layer=nn.LayerNorm, layer_scale=0.0,
+                 reserve_on=True, drop=0.0, attn_drop=0.0, drop_path=0.0, norm_layer=LayerNorm, layer_scale=0.0,
                  downsample=None):
         super().__init__()
         self.dim, self.nbhd_size, self.cluster_size, self.depth = dim, nbhd_size, cluster_size, depth
@@ -291,19 +333,16 @@ class BasicLayer(nn.Module):
             else:
                 pos, feat, mean_pos, member, cluster_mask = self._cluster(pos, feat, h, w, on_grid)
             nearest = knn_keops(pos, mean_pos, nnc)                                                  # aff.py:475
-            gi = nearest.view(b, -1, 1).expand(-1, -1, m)
-            member_idx = member.gather(index=gi, dim=1).reshape(b, n, nnc * m)                       # aff.py:478
-            if cluster_mask is not None:
-                cluster_mask = cluster_mask.gather(index=gi, dim=1).reshape(b, n, nnc * m)
-            pos_nb = pos.gather(index=member_idx.view(b, -1, 1).expand(-1, -1, d), dim=1).reshape(b, n, nnc * m, d)
-            rel_pos = pos_nb - (pos.unsqueeze(2) - REL_POS_WIDTH)                                    # aff.py:481-482
-        rel_pos = rel_pos.clamp(0, TABLE_WIDTH - 1)
-        pe_idx = (rel_pos[..., 1] * TABLE_WIDTH + rel_pos[..., 0]).long()                            # aff.py:484-485
-        pe_lookup = _TableLookup(pe_idx)
-        fused_ctx = None
-        if not global_attn and USE_FUSED_ATTENTION and not torch.is_grad_enabled():
-            fused_ctx = (pe_lookup.inverse.view(b, n, -1).to(torch.int32),
-                         None if cluster_mask is None else cluster_mask.to(torch.uint8).contiguous())
+            # aff.py:478-485 (member / mask gathers, relative positions, table index) + the table-row restriction: one pass
+            member_idx, cluster_mask, mask_u8, uniq, bias_idx = stage_prepare(pos, nearest, member, cluster_mask)
+            pe_idx = None
+            pe_lookup = _TableLookup(uniq=uniq, inverse=bias_idx)
+            fused_ctx = (bias_idx, mask_u8) if USE_FUSED_ATTENTION else None
+        if global_attn:
+            rel_pos = rel_pos.clamp(0, TABLE_WIDTH - 1)
+            pe_idx = (rel_pos[..., 1] * TABLE_WIDTH + rel_pos[..., 0]).long()                        # aff.py:484-485
+            pe_lookup = _TableLookup(pe_idx)
+            fused_ctx = None
         for blk in self.blocks:
             feat = blk(feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup, fused_ctx)
         if self.downsample is None:
@@ -355,7 +394,7 @@ class AFF(nn.Module):
 
     def __init__(self, in_chans=3, embed_dim=[32, 128, 256, 512], cluster_size=8, nbhd_size=[48, 48, 48, 48],
                  alpha=4.0, ds_rate=0.25, reserve_on=True, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], mlp_ratio=2.0,
-                 drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.1, norm_layer=nn.LayerNorm, patch_norm=True,
+                 drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.1, norm_layer=LayerNorm, patch_norm=True,
                  layer_scale=0.0, downsample=ClusterMerging, out_indices=(0, 1, 2, 3)):
         super().__init__()
         self.num_layers = len(depths)

@@ -435,3 +435,18 @@ extern "C" int clusten_av_bwd(const void *d_feat, const void *attn, const void *
     });
     return 0;
 }
+
+// out[b,h,r,:] = sum_{(i,j): idx[b,i,j] = r} w[b,h,i,j] * x[b,h,i,:] -- the scatter shape on its own (d_k / d_v of the fused
+// attention backward, which produces its own w tensors).
+extern "C" int clusten_scatter_rows(const void *w, const void *x, const int32_t *csr_offsets, const uint32_t *csr_entries,
+                                    const void *pack, void *out, int B, int H, int Nq, int Nk, int C, int M,
+                                    int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t x_sb, int64_t x_sh, int64_t x_sn,
+                                    int64_t o_sb, int64_t o_sh, int64_t o_sn, int dtype, void *stream) {
+    if (int e = check_common(B, H, Nq, Nk, C, M)) return e;
+    if (!w || !x || !csr_offsets || !csr_entries || !out) return set_error(CLUSTEN_EINVAL, "null pointer");
+    if (M > 256) return set_error(CLUSTEN_EUNSUPPORTED, "scatter needs M <= 256 (got %d)", M);
+    cudaStream_t st = (cudaStream_t)stream;
+    CLUSTEN_DISPATCH_DTYPE(dtype, return launch_csr<T>((const T *)w, (const T *)x, csr_offsets, csr_entries, pack, (T *)out, B, H, Nq, Nk, C, M,
+                                                       Rows{w, w_sb, w_sh, w_sn}, Rows{x, x_sb, x_sh, x_sn}, Rows{out, o_sb, o_sh, o_sn}, st));
+    return 0;
+}

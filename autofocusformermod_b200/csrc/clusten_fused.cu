@@ -14,7 +14,7 @@
 // probabilities as the A operand.  The [B,H,N,M] tensor never touches HBM (optionally the probabilities are written
 // once, coalesced, for a backward pass).  Impure tokens and index tensors without octet structure take a
 // one-warp-per-(token, head) generic kernel with the same arithmetic; the pack's device-side flag picks (no host sync).
-#include "tile.cuh"
+#include "t2.cuh"
 
 namespace clusten {
 
@@ -80,7 +80,7 @@ struct FusedArgs {
     const uint8_t *mask;
     const void *blank_k, *blank_v;
     void *out;
-    float *probs;
+    float *probs, *lse;
     int B, H, Nq, Nk, C, M;
     int64_t q_sb, q_sh, q_sn, k_sb, k_sh, k_sn, v_sb, v_sh, v_sn, o_sb, o_sh, o_sn;
 };
@@ -122,6 +122,7 @@ __device__ __forceinline__ void fused_row_generic(const FusedArgs &a, int b, int
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
     const float inv = 1.f / sum;
+    if (a.lse && lane == 0) a.lse[((int64_t)b * a.H + h) * a.Nq + i] = mx + logf(sum);
     __syncwarp();
     T *orow = reinterpret_cast<T *>(a.out) + b * a.o_sb + h * a.o_sh + (int64_t)i * a.o_sn;
     for (int ch = lane; ch < C; ch += 32) {
@@ -187,41 +188,50 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
     constexpr bool F32 = sizeof(T) == 4;
     constexpr int KS = F32 ? CH / 2 : CH / 4;                       // mma k-steps of the dot phase
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
-    const int64_t item = (int64_t)blockIdx.x * W + warp;
-    if (item >= (int64_t)a.B * pk.T * a.H) return;
-    const int h = (int)(item % a.H);
-    const int bt = (int)(item / a.H);
-    const int b = bt / pk.T, i0 = (bt - b * pk.T) * TILE_TOK;
-    const int g = lane >> 2, t = lane & 3;
-    const int U = pk.tile_u[bt];
     const int M = a.M, C = a.C, H = a.H, Nq = a.Nq, MP = M + 4;
     float *S = reinterpret_cast<float *>(dyn + (size_t)warp * smem_per_warp);        // [16][MP]: logits / e, [M] blank, [M+1] 1/sum
     unsigned char *stg = reinterpret_cast<unsigned char *>(S + 16 * MP);              // V staging, 2 buffers
-    const int *octp = pk.tile_oct + (int64_t)bt * U_MAX;
-    const int o0 = octp[lane], o1 = lane + 32 < U_MAX ? octp[lane + 32] : 0;
-    auto octet = [&](int u) { return __shfl_sync(FULL, u < 32 ? o0 : o1, u & 31); };
-    const int8_t *sa = pk.slot_of + ((int64_t)bt * TILE_TOK + g) * U_MAX;
+    const int tile = blockIdx.x * W + warp;                                           // grid: (tiles / W, B * H)
+    if (tile < pk.T) {
+    const int b = blockIdx.y / H, h = blockIdx.y - b * H;
+    const int bt = b * pk.T + tile, i0 = tile * TILE_TOK;
+    const int g = lane >> 2, t = lane & 3;
+    const int U = pk.tile_u[bt];
+    const int *octp = pk.tile_oct + bt * U_MAX;
+    const int o0 = octp[lane], o1 = octp[32 + (lane & 15)];
+    auto octet = [&](int u) { u = min(u, U - 1); return __shfl_sync(FULL, u < 32 ? o0 : o1, u & 31); };
+    const int8_t *sa = pk.slot_of + (bt * TILE_TOK + g) * U_MAX;
     const int8_t *sb = sa + 8 * U_MAX;
     const int ra = i0 + g, rb = ra + 8;
-    uint32_t impm;
+    uint32_t impm = 0;
     {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(pk.tok_imp + (int64_t)bt * TILE_TOK));
-        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-        impm = 0;
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(pk.tok_imp + bt * TILE_TOK));
+        if (v.x | v.y | v.z | v.w) {
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd)
+            for (int qd = 0; qd < 4; ++qd)
 #pragma unroll
-            for (int kq = 0; kq < 4; ++kq) impm |= ((w4[qd] >> (8 * kq)) & 1u) << (4 * qd + kq);
+                for (int kq = 0; kq < 4; ++kq) impm |= ((w4[qd] >> (8 * kq)) & 1u) << (4 * qd + kq);
+        }
     }
-    const T *Q = reinterpret_cast<const T *>(a.q), *K = reinterpret_cast<const T *>(a.k), *V = reinterpret_cast<const T *>(a.v);
+    // per-warp 64-bit bases hidden from the optimiser + 32-bit element offsets (host-checked extents): one IMAD.WIDE per address
+    const T *Q = t2::opaque(reinterpret_cast<const T *>(a.q) + b * a.q_sb + h * a.q_sh);
+    const T *K = t2::opaque(reinterpret_cast<const T *>(a.k) + b * a.k_sb + h * a.k_sh);
+    const T *V = t2::opaque(reinterpret_cast<const T *>(a.v) + b * a.v_sb + h * a.v_sh);
+    const int q_sn = (int)a.q_sn, k_sn = (int)a.k_sn, v_sn = (int)a.v_sn;
 
     // ---- phase 1: logits of the 16 tokens against every union octet (tensor cores), selected blocks -> S ------------------
     {
         const bool cact = CH * t < C;
+        const int cofs = cact ? CH * t : 0;
         FFrag<T, CH> xa, xb;
-        const T *xbase = Q + b * a.q_sb + h * a.q_sh + CH * t;
-        f_load<T, CH>(xa, xbase + (int64_t)ra * a.q_sn, cact && ra < Nq);
-        f_load<T, CH>(xb, xbase + (int64_t)rb * a.q_sn, cact && rb < Nq);
+        // rows beyond Nq re-read the last row (their slots are all -1 and phase 2 zeroes them); inactive channel lanes zero q
+        t2::ld_chunk<CH * (int)sizeof(T)>(xa.r, t2::at(Q, min(ra, Nq - 1) * q_sn + cofs));
+        t2::ld_chunk<CH * (int)sizeof(T)>(xb.r, t2::at(Q, min(rb, Nq - 1) * q_sn + cofs));
+        if (!cact) {
+#pragma unroll
+            for (int x = 0; x < CH * (int)sizeof(T) / 4; ++x) xa.r[x] = xb.r[x] = 0u;
+        }
         {   // blank logit q . blank_k[h] (aff.py:140): partial over this lane's channels, reduced over the 4 lanes of the row
             const T *bk = reinterpret_cast<const T *>(a.blank_k) + h * C + CH * t;
             float pa = 0.f, pb = 0.f;
@@ -248,21 +258,26 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
             }
         }
         constexpr int UB = F32 ? 2 : 4;
-        const T *ybase = K + b * a.k_sb + h * a.k_sh + CH * t + (int64_t)g * a.k_sn;
+        const int ylane = g * k_sn + cofs, k8 = 8 * k_sn;
         for (int u0 = 0; u0 < U; u0 += UB) {
             FFrag<T, CH> y[UB];
             int sga[UB], sgb[UB];
-#pragma unroll
-            for (int j = 0; j < UB; ++j) {
-                const int u = u0 + j;
-                const int o = octet(u < U ? u : 0);
-                f_load<T, CH>(y[j], ybase + (int64_t)o * 8 * a.k_sn, cact && u < U);
-                sga[j] = u < U ? (int)sa[u] : -1;
-                sgb[j] = u < U ? (int)sb[u] : -1;
+            uint32_t sa4, sb4;                           // slots of rows g / g+8 for the UB octets (positions >= U hold -1)
+            if constexpr (UB == 4) {
+                sa4 = __ldg(reinterpret_cast<const uint32_t *>(sa + u0));
+                sb4 = __ldg(reinterpret_cast<const uint32_t *>(sb + u0));
+            } else {
+                sa4 = __ldg(reinterpret_cast<const unsigned short *>(sa + u0));
+                sb4 = __ldg(reinterpret_cast<const unsigned short *>(sb + u0));
             }
 #pragma unroll
             for (int j = 0; j < UB; ++j) {
-                if (u0 + j >= U) break;
+                t2::ld_chunk<CH * (int)sizeof(T)>(y[j].r, t2::at(K, octet(u0 + j) * k8 + ylane));
+                sga[j] = t2::sbyte(sa4, j);
+                sgb[j] = t2::sbyte(sb4, j);
+            }
+#pragma unroll
+            for (int j = 0; j < UB; ++j) {
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int s = 0; s < KS; ++s) {
@@ -295,10 +310,10 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
             for (int j = j0; j < j1; j += 4) {                       // M % 8 == 0 -> Mh % 4 == 0, 16-byte aligned rows
                 const int4 bv = __ldg(reinterpret_cast<const int4 *>(bi + j));
                 float4 x = *reinterpret_cast<float4 *>(Sr + j);
-                x.x += __ldg(a.bias_tab + (int64_t)bv.x * H + h);
-                x.y += __ldg(a.bias_tab + (int64_t)bv.y * H + h);
-                x.z += __ldg(a.bias_tab + (int64_t)bv.z * H + h);
-                x.w += __ldg(a.bias_tab + (int64_t)bv.w * H + h);
+                x.x += __ldg(a.bias_tab + bv.x * H + h);
+                x.y += __ldg(a.bias_tab + bv.y * H + h);
+                x.z += __ldg(a.bias_tab + bv.z * H + h);
+                x.w += __ldg(a.bias_tab + bv.w * H + h);
                 if (mk) {
                     const uchar4 m4 = *reinterpret_cast<const uchar4 *>(mk + j);
                     if (!m4.x) x.x += -100.f;
@@ -327,13 +342,14 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
         }
         sum += __shfl_xor_sync(FULL, sum, 1);
         if (half == 0) Sr[M + 1] = rvalid ? 1.f / sum : 0.f;
+        if (a.lse && half == 0 && rvalid) a.lse[((int64_t)b * H + h) * Nq + i] = mx + logf(sum);
     }
     __syncwarp();
     // ---- phase 3: out = sum_j e_j v_j over the union octets (tensor cores, V staged key-major in shared memory) -------------
     float acc[NT][4];
 #pragma unroll
     for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-    const T *vbase = V + b * a.v_sb + h * a.v_sh;
+    const T *vbase = V;
     const float *Sa = S + g * MP, *Sb = S + (g + 8) * MP;
     if constexpr (!F32) {
         constexpr int ROWB = NT * 16 + 16, CPL = NT / 2;
@@ -344,9 +360,8 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
                 const int row = ch / NT, blk = ch % NT;
                 const int u = 2 * p + (row >> 3);
                 const bool ok = u < U && 8 * blk < C;
-                const int o = octet(u < U ? u : 0);
-                const T *src = vbase + ((int64_t)o * 8 + (row & 7)) * a.v_sn + 8 * blk;
-                f_cp16(stg + which * 16 * ROWB + row * ROWB + blk * 16, ok ? (const void *)src : (const void *)V, ok);
+                const T *src = t2::at(vbase, (octet(u) * 8 + (row & 7)) * v_sn + (ok ? 8 * blk : 0));
+                f_cp16(stg + which * 16 * ROWB + row * ROWB + blk * 16, src, ok);
             }
             f_commit();
         };
@@ -385,8 +400,8 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
                 const int ch = lane + 32 * j;
                 const int row = ch / (2 * NT), blk = ch % (2 * NT);
                 const bool ok = 4 * blk < C;
-                const T *src = vbase + ((int64_t)o * 8 + row) * a.v_sn + 4 * blk;
-                f_cp16(stf + which * 8 * RS + row * RS + blk * 4, ok ? (const void *)src : (const void *)V, ok);
+                const T *src = t2::at(vbase, (o * 8 + row) * v_sn + (ok ? 4 * blk : 0));
+                f_cp16(stf + which * 8 * RS + row * RS + blk * 4, src, ok);
             }
             f_commit();
         };
@@ -416,8 +431,9 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
     {
         const float inva = Sa[M + 1], invb = Sb[M + 1], eba = Sa[M], ebb = Sb[M];
         const T *bv = reinterpret_cast<const T *>(a.blank_v) + h * C;
-        T *oa = reinterpret_cast<T *>(a.out) + b * a.o_sb + h * a.o_sh + (int64_t)ra * a.o_sn + 2 * t;
-        T *ob = oa + 8 * a.o_sn;
+        T *Ob = t2::opaque(reinterpret_cast<T *>(a.out) + b * a.o_sb + h * a.o_sh);
+        T *oa = t2::at(Ob, ra * (int)a.o_sn + 2 * t);
+        T *ob = t2::at(Ob, rb * (int)a.o_sn + 2 * t);
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
             const int ch = 8 * n + 2 * t;
@@ -436,10 +452,14 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
             if (!((impm >> row) & 1u)) pr[x] = S[row * MP + col] * S[row * MP + M + 1];
         }
     }
+    }
     __syncwarp();
-    for (uint32_t imp = impm; imp; imp &= imp - 1) {          // impure tokens: the generic per-row routine, S row as scratch
-        const int r = __ffs(imp) - 1;
-        fused_row_generic<T>(a, b, h, i0 + r, S + r * MP, lane);
+    // impure tokens of the whole call, one (token, head) per warp, spread over the grid (t2::slow_items); S row 0 as scratch
+    const t2::SlowIter si = t2::slow_items(pk, a.H);
+    for (int it = si.first; it < si.n; it += si.stride) {
+        const int gi = pk.imp_list[it / a.H], hh = it % a.H;
+        const int bb = gi / a.Nq;
+        fused_row_generic<T>(a, bb, hh, gi - bb * a.Nq, S, lane);
     }
 }
 
@@ -458,10 +478,12 @@ static int launch_fused(const FusedArgs &a, const void *pack, cudaStream_t st) {
     const bool align_ok = f_rows_ok<T>(a.q, a.q_sb, a.q_sh, a.q_sn) && f_rows_ok<T>(a.k, a.k_sb, a.k_sh, a.k_sn) &&
                           f_rows_ok<T>(a.v, a.v_sb, a.v_sh, a.v_sn) && f_rows_ok<T>(a.out, a.o_sb, a.o_sh, a.o_sn) &&
                           aligned16(a.bias_idx) && (!a.mask || (reinterpret_cast<uintptr_t>(a.mask) & 3u) == 0);
-    if (pack && shape_ok && align_ok) {
+    auto fits = [](int64_t v) { return v >= 0 && v < (1LL << 31); };
+    const bool range_ok = fits(a.Nq * a.q_sn) && fits((int64_t)a.Nk * a.k_sn) && fits((int64_t)a.Nk * a.v_sn) && fits(a.Nq * a.o_sn) &&
+                          (int64_t)a.B * a.H <= 65535 && fits((int64_t)a.B * ((a.Nq + 15) / 16) * 16 * U_MAX);
+    if (pack && shape_ok && align_ok && range_ok) {
         const PackView pk = pack_view(const_cast<void *>(pack), a.B, a.Nq, a.Nk);
-        const int64_t items = (int64_t)a.B * pk.T * a.H;
-        const int grid = ceil_div(items, W);
+        const dim3 grid(ceil_div(pk.T, W), a.B * a.H);
         const size_t smem = per_warp * W;
         if (C <= 16) attn_fused_tile_kernel<T, 4, 2><<<grid, W * 32, smem, st>>>(a, pk, (int)per_warp);
         else attn_fused_tile_kernel<T, 8, 4><<<grid, W * 32, smem, st>>>(a, pk, (int)per_warp);
@@ -485,7 +507,7 @@ using namespace clusten;
 
 extern "C" int clusten_attn_fwd(const void *q, const void *k, const void *v, const int64_t *nbhd_idx, const void *pack,
                                 const float *bias_tab, const int32_t *bias_idx, const uint8_t *mask,
-                                const void *blank_k, const void *blank_v, void *out, float *probs,
+                                const void *blank_k, const void *blank_v, void *out, float *probs, float *lse,
                                 int B, int H, int Nq, int Nk, int C, int M,
                                 int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t k_sb, int64_t k_sh, int64_t k_sn,
                                 int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t o_sb, int64_t o_sh, int64_t o_sn,
@@ -495,7 +517,7 @@ extern "C" int clusten_attn_fwd(const void *q, const void *k, const void *v, con
     if (!q || !k || !v || !nbhd_idx || !bias_tab || !bias_idx || !blank_k || !blank_v || !out)
         return set_error(CLUSTEN_EINVAL, "null pointer");
     if ((int64_t)B * Nq == 0) return 0;
-    FusedArgs a{q, k, v, nbhd_idx, bias_tab, bias_idx, mask, blank_k, blank_v, out, probs, B, H, Nq, Nk, C, M,
+    FusedArgs a{q, k, v, nbhd_idx, bias_tab, bias_idx, mask, blank_k, blank_v, out, probs, lse, B, H, Nq, Nk, C, M,
                 q_sb, q_sh, q_sn, k_sb, k_sh, k_sn, v_sb, v_sh, v_sn, o_sb, o_sh, o_sn};
     cudaStream_t st = (cudaStream_t)stream;
     CLUSTEN_DISPATCH_DTYPE(dtype, return launch_fused<T>(a, pack, st));

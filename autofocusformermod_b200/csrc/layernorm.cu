@@ -1,0 +1,182 @@
+// LayerNorm over the channel dimension of token rows, forward + backward (sm_100a).
+//
+// The AFF backbone normalises [B*n, C] token matrices with C = 32 ... 1024 before every attention / MLP / merge
+// (mask2former/modeling/backbone/aff.py:196-199, 258, 617-620).  ATen's vectorised kernel spends one CTA per row, which at
+// C = 32 and B*n = 262 144 rows is launch- and latency-bound (16.7 % of the AFF-Mini forward in
+// profiles/r1_launches_aff_mini_fwd_b16_v3.md).  Here one WARP owns a row (C <= 1024): the row lives in registers, mean and
+// variance are two shuffle reductions, HBM traffic is one read and one write.  Input / output may be fp32, fp16 or bf16
+// independently; statistics and arithmetic are fp32.
+//   fwd: y = (x - mean) * rstd * gamma + beta;   saves mean, rstd (fp32 [R]) when asked
+//   bwd: dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)), g = dy * gamma;  dgamma += sum_r dy * xhat;  dbeta += sum_r dy
+//        (dgamma / dbeta: per-CTA shared-memory partials, then one fp32 atomic per channel and CTA)
+#include "common.cuh"
+
+namespace clusten {
+
+constexpr int LN_MAX_PER_LANE = 32;      // C <= 1024
+
+template <typename T> __device__ __forceinline__ float ln_ld(const T *p) { return to_f(*p); }
+
+__device__ __forceinline__ float ln_warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+
+// PER = elements per lane (C = 32 * PER exactly when FULLROW, else C <= 32 * PER with a tail predicate)
+template <typename TI, typename TO, int PER>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const TI *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta, TO *__restrict__ y,
+              float *__restrict__ mean_out, float *__restrict__ rstd_out, int64_t R, int C, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= R) return;
+    const TI *xr = x + row * C;
+    float v[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int c = lane + 32 * k;
+        v[k] = c < C ? ln_ld(xr + c) : 0.f;
+        s += v[k];
+    }
+    const float mean = ln_warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int c = lane + 32 * k;
+        const float d = c < C ? v[k] - mean : 0.f;
+        q = fmaf(d, d, q);
+    }
+    const float rstd = rsqrtf(ln_warp_sum(q) / (float)C + eps);
+    TO *yr = y + row * C;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int c = lane + 32 * k;
+        if (c < C) yr[c] = from_f<TO>(fmaf((v[k] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c)));
+    }
+    if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+template <typename TI, typename TG, typename TO, int PER>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const TG *__restrict__ dy, const TI *__restrict__ x, const float *__restrict__ gamma,
+              const float *__restrict__ mean_in, const float *__restrict__ rstd_in, TO *__restrict__ dx,
+              float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t R, int C) {
+    extern __shared__ float ln_s[];                      // [2][C] partial dgamma / dbeta of this CTA
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) ln_s[c] = 0.f;
+    __syncthreads();
+    float ag[PER], ab[PER], gm[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int c = lane + 32 * k;
+        ag[k] = ab[k] = 0.f;
+        gm[k] = c < C ? __ldg(gamma + c) : 0.f;
+    }
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < R; row += (int64_t)gridDim.x * 8) {
+        const TI *xr = x + row * C;
+        const TG *gr = dy + row * C;
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        float xh[PER], g[PER];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int c = lane + 32 * k;
+            const bool in = c < C;
+            const float d = in ? to_f(gr[c]) : 0.f;
+            xh[k] = in ? (ln_ld(xr + c) - mean) * rstd : 0.f;
+            g[k] = d * gm[k];
+            s1 += g[k];
+            s2 = fmaf(g[k], xh[k], s2);
+            ag[k] = fmaf(d, xh[k], ag[k]);
+            ab[k] += d;
+        }
+        s1 = ln_warp_sum(s1) / (float)C;
+        s2 = ln_warp_sum(s2) / (float)C;
+        TO *dr = dx + row * C;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int c = lane + 32 * k;
+            if (c < C) dr[c] = from_f<TO>(rstd * (g[k] - s1 - xh[k] * s2));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int c = lane + 32 * k;
+        if (c < C) { atomicAdd(ln_s + c, ag[k]); atomicAdd(ln_s + C + c, ab[k]); }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(dgamma + c, ln_s[c]);
+        atomicAdd(dbeta + c, ln_s[C + c]);
+    }
+}
+
+template <typename TI, typename TO>
+static int ln_fwd_launch(const TI *x, const float *g, const float *b, TO *y, float *mean, float *rstd, int64_t R, int C, float eps,
+                         cudaStream_t st) {
+    const int grid = (int)((R + 7) / 8);
+    const int per = (C + 31) / 32;
+#define LN_F(P_) ln_fwd_kernel<TI, TO, P_><<<grid, 256, 0, st>>>(x, g, b, y, mean, rstd, R, C, eps)
+    if (per <= 1) LN_F(1); else if (per <= 2) LN_F(2); else if (per <= 4) LN_F(4); else if (per <= 8) LN_F(8);
+    else if (per <= 12) LN_F(12); else if (per <= 16) LN_F(16); else if (per <= 24) LN_F(24); else LN_F(32);
+#undef LN_F
+    note_launches(1);
+    return check_launch("layer_norm_fwd");
+}
+
+template <typename TI, typename TG, typename TO>
+static int ln_bwd_launch(const TG *dy, const TI *x, const float *g, const float *mean, const float *rstd, TO *dx, float *dg, float *db,
+                         int64_t R, int C, cudaStream_t st) {
+    const int grid = (int)std::min<int64_t>((R + 7) / 8, 148 * 8);
+    const int per = (C + 31) / 32;
+    const size_t smem = (size_t)2 * C * sizeof(float);
+#define LN_B(P_) ln_bwd_kernel<TI, TG, TO, P_><<<grid, 256, smem, st>>>(dy, x, g, mean, rstd, dx, dg, db, R, C)
+    if (per <= 1) LN_B(1); else if (per <= 2) LN_B(2); else if (per <= 4) LN_B(4); else if (per <= 8) LN_B(8);
+    else if (per <= 16) LN_B(16); else LN_B(32);
+#undef LN_B
+    note_launches(1);
+    return check_launch("layer_norm_bwd");
+}
+
+}  // namespace clusten
+
+using namespace clusten;
+
+#define LN_DISPATCH2(d0, d1, ...)                                                                         \
+    switch (d0) {                                                                                         \
+        case CLUSTEN_F32: { using TA = float; LN_DISPATCH1(d1, __VA_ARGS__); break; }                     \
+        case CLUSTEN_F16: { using TA = __half; LN_DISPATCH1(d1, __VA_ARGS__); break; }                    \
+        case CLUSTEN_BF16: { using TA = __nv_bfloat16; LN_DISPATCH1(d1, __VA_ARGS__); break; }            \
+        default: return set_error(CLUSTEN_EDTYPE, "unknown dtype %d", d0);                                \
+    }
+#define LN_DISPATCH1(d1, ...)                                                                             \
+    switch (d1) {                                                                                         \
+        case CLUSTEN_F32: { using TB = float; __VA_ARGS__; break; }                                       \
+        case CLUSTEN_F16: { using TB = __half; __VA_ARGS__; break; }                                      \
+        case CLUSTEN_BF16: { using TB = __nv_bfloat16; __VA_ARGS__; break; }                              \
+        default: return set_error(CLUSTEN_EDTYPE, "unknown dtype %d", d1);                                \
+    }
+
+extern "C" int clusten_layer_norm_fwd(const void *x, const float *gamma, const float *beta, void *y, float *mean, float *rstd,
+                                      int64_t R, int C, float eps, int x_dtype, int y_dtype, void *stream) {
+    if (R < 0 || C <= 0 || C > 32 * LN_MAX_PER_LANE) return set_error(CLUSTEN_EUNSUPPORTED, "layer norm: C=%d outside 1..1024", C);
+    if (!x || !gamma || !beta || !y || (mean == nullptr) != (rstd == nullptr)) return set_error(CLUSTEN_EINVAL, "null pointer");
+    if (R == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    LN_DISPATCH2(x_dtype, y_dtype, return ln_fwd_launch<TA, TB>((const TA *)x, gamma, beta, (TB *)y, mean, rstd, R, C, eps, st));
+    return 0;
+}
+
+// d_x has x's dtype, d_y its own (g_dtype); d_gamma / d_beta fp32 [C], accumulated INTO (caller zeroes them)
+extern "C" int clusten_layer_norm_bwd(const void *d_y, const void *x, const float *gamma, const float *mean, const float *rstd,
+                                      void *d_x, float *d_gamma, float *d_beta, int64_t R, int C, int x_dtype, int g_dtype,
+                                      void *stream) {
+    if (R < 0 || C <= 0 || C > 32 * LN_MAX_PER_LANE) return set_error(CLUSTEN_EUNSUPPORTED, "layer norm: C=%d outside 1..1024", C);
+    if (!d_y || !x || !gamma || !mean || !rstd || !d_x || !d_gamma || !d_beta) return set_error(CLUSTEN_EINVAL, "null pointer");
+    if (R == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    LN_DISPATCH2(x_dtype, g_dtype, return ln_bwd_launch<TA, TB, TA>((const TB *)d_y, (const TA *)x, gamma, mean, rstd, (TA *)d_x, d_gamma, d_beta, R, C, st));
+    return 0;
+}

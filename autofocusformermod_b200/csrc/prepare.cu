@@ -1,0 +1,152 @@
+// Stage preparation: neighbourhood assembly + relative-position index of BasicLayer.forward
+// (mask2former/modeling/backbone/aff.py:475-485) in one kernel, and the restriction of the 1023^2-row position table to the
+// rows the stage references without sorting.
+//
+//   nearest [B,n,nnc] (kNN of the tokens among the cluster centres) , member [B,k,m] , cluster_mask [B,k,m] or NULL , pos [B,n,2]
+//   member_idx[b,i,c*m+r] = member[b, nearest[b,i,c], r]                                                   aff.py:478
+//   mask[b,i,c*m+r]       = cluster_mask[b, nearest[b,i,c], r]                                             aff.py:480
+//   rel = pos[b, member_idx] - (pos[b,i] - 511), clamped to [0, 1022];  pe = rel.y * 1023 + rel.x          aff.py:481-485
+//
+// The reference then evaluates pos_embed / weight_net on ALL 1023^2 table rows per block; the torch-level restriction used
+// before (torch.unique over the B*n*M int64 indices) is a 25 M-key radix sort per stage.  Here the prepare kernel marks the
+// referenced table rows in a 1023^2-byte presence map, a single-CTA-per-chunk scan ranks them (ascending row id = the order
+// torch.unique returns), and a second pass rewrites pe -> rank.  Three launches, no sort, one host read (the row count U).
+#include "common.cuh"
+
+namespace clusten {
+
+constexpr int PE_W = 1023;
+constexpr int PE_ROWS = PE_W * PE_W;
+constexpr float PE_HALF = 511.f;
+
+__global__ void __launch_bounds__(256)
+prepare_kernel(const int64_t *__restrict__ nearest, const int64_t *__restrict__ member, const int64_t *__restrict__ cmask,
+               const float *__restrict__ pos, int B, int n, int k, int m, int nnc,
+               int64_t *__restrict__ member_idx, int64_t *__restrict__ mask64, uint8_t *__restrict__ mask8,
+               int32_t *__restrict__ pe, uint8_t *__restrict__ present) {
+    const int M = nnc * m;
+    const int64_t total = (int64_t)B * n * M;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(e % M);
+        const int64_t bi = e / M;                        // b * n + i
+        const int b = (int)(bi / n);
+        const int c = j / m, r = j - c * m;
+        const int64_t cl = nearest[bi * nnc + c];
+        const int64_t src = ((int64_t)b * k + cl) * m + r;
+        const int64_t mi = member[src];
+        member_idx[e] = mi;
+        if (cmask) {
+            const int64_t mk = cmask[src];
+            if (mask64) mask64[e] = mk;
+            if (mask8) mask8[e] = mk != 0;
+        }
+        const float2 pi = *reinterpret_cast<const float2 *>(pos + bi * 2);
+        const float2 pn = *reinterpret_cast<const float2 *>(pos + ((int64_t)b * n + mi) * 2);
+        float rx = __fsub_rn(pn.x, __fsub_rn(pi.x, PE_HALF)), ry = __fsub_rn(pn.y, __fsub_rn(pi.y, PE_HALF));
+        rx = fminf(fmaxf(rx, 0.f), (float)(PE_W - 1));
+        ry = fminf(fmaxf(ry, 0.f), (float)(PE_W - 1));
+        const int p = (int)__fadd_rn(__fmul_rn(ry, (float)PE_W), rx);     // (rel.y * 1023 + rel.x).long(), fp32 arithmetic
+        pe[e] = p;
+        present[p] = 1;                                  // benign race: every writer stores 1
+    }
+}
+
+// rank of every present table row (exclusive prefix count), U = number of present rows, uniq[rank] = row id.
+// One CTA of 1024 threads walks the 1023^2 flags in chunks: 1 M flags, ~1 MB -> a few microseconds; no second kernel, no sync.
+__global__ void __launch_bounds__(1024)
+rank_kernel(const uint8_t *__restrict__ present, int32_t *__restrict__ rank, int32_t *__restrict__ uniq, int32_t *__restrict__ count,
+            int cap) {
+    __shared__ int wsum[32];
+    __shared__ int base_s, chunk_tot;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    constexpr int PER = 16;                              // flags per thread per chunk (one 16-byte load)
+    for (int c0 = 0; c0 < PE_ROWS; c0 += 1024 * PER) {
+        const int p0 = c0 + tid * PER;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (p0 + PER <= PE_ROWS) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(present + p0);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else {
+            for (int x = 0; x < PER; ++x)
+                if (p0 + x < PE_ROWS && present[p0 + x]) w[x >> 2] |= 1u << (8 * (x & 3));
+        }
+        int cnt = 0;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) cnt += __popc(w[x] & 0x01010101u);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = wsum[lane];
+            int iv = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(FULL, iv, o);
+                if (lane >= o) iv += y;
+            }
+            wsum[lane] = iv - v;                         // exclusive over the warps
+            if (lane == 31) chunk_tot = iv;
+        }
+        __syncthreads();
+        int r = base_s + wsum[warp] + incl - cnt;
+#pragma unroll
+        for (int x = 0; x < PER; ++x) {
+            if ((w[x >> 2] >> (8 * (x & 3))) & 1u) {
+                rank[p0 + x] = r;
+                if (r < cap) uniq[r] = p0 + x;
+                ++r;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) base_s += chunk_tot;
+        __syncthreads();
+    }
+    if (tid == 0) *count = base_s;
+}
+
+__global__ void __launch_bounds__(256)
+rerank_kernel(const int32_t *__restrict__ pe, const int32_t *__restrict__ rank, int32_t *__restrict__ inv, int64_t total) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+        inv[e] = __ldg(rank + pe[e]);
+}
+
+}  // namespace clusten
+
+using namespace clusten;
+
+extern "C" size_t clusten_prepare_workspace_bytes(void) {
+    // presence map (padded) + rank table
+    return (size_t)((PE_ROWS + 255) & ~255) + (size_t)PE_ROWS * 4 + 256;
+}
+
+extern "C" int clusten_stage_prepare(const int64_t *nearest, const int64_t *member, const int64_t *cluster_mask, const float *pos,
+                                     int B, int n, int k, int m, int nnc,
+                                     int64_t *member_idx, int64_t *mask64, uint8_t *mask8, int32_t *pe_idx, int32_t *bias_idx,
+                                     int32_t *uniq, int uniq_cap, int32_t *count, void *workspace, size_t workspace_bytes,
+                                     void *stream) {
+    if (B < 0 || n < 0 || k <= 0 || m <= 0 || nnc <= 0 || uniq_cap <= 0)
+        return set_error(CLUSTEN_EINVAL, "bad sizes B=%d n=%d k=%d m=%d nnc=%d", B, n, k, m, nnc);
+    if (!nearest || !member || !pos || !member_idx || !pe_idx || !bias_idx || !uniq || !count || !workspace)
+        return set_error(CLUSTEN_EINVAL, "null pointer");
+    if (workspace_bytes < clusten_prepare_workspace_bytes()) return set_error(CLUSTEN_EWORKSPACE, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *present = reinterpret_cast<uint8_t *>(workspace);
+    const size_t pm = (size_t)((PE_ROWS + 255) & ~255);
+    int32_t *rank = reinterpret_cast<int32_t *>(present + pm);
+    cudaMemsetAsync(present, 0, pm, st);
+    const int64_t total = (int64_t)B * n * nnc * m;
+    if (total == 0) { cudaMemsetAsync(count, 0, 4, st); return check_launch("prepare memset"); }
+    const int grid = (int)std::min<int64_t>(148 * 16, (total + 255) / 256);
+    prepare_kernel<<<grid, 256, 0, st>>>(nearest, member, cluster_mask, pos, B, n, k, m, nnc, member_idx, mask64, mask8, pe_idx, present);
+    rank_kernel<<<1, 1024, 0, st>>>(present, rank, uniq, count, uniq_cap);
+    rerank_kernel<<<grid, 256, 0, st>>>(pe_idx, rank, bias_idx, total);
+    note_launches(3);
+    return check_launch("stage_prepare");
+}

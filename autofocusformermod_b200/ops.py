@@ -296,11 +296,197 @@ def cluster_attention_fused(q, key, v, nbhd_idx, bias_tab, bias_idx, mask, blank
         with torch.cuda.device(dev):
             _call("clusten_attn_fwd", dev, q.data_ptr(), key.data_ptr(), v.data_ptr(), nbhd_idx.data_ptr(),
                   _lib.ptr(neighbourhood_pack(nbhd_idx, Nk)), bias_tab.data_ptr(), bias_idx.data_ptr(), _lib.ptr(mask),
-                  blank_k.data_ptr(), blank_v.data_ptr(), out.data_ptr(), _lib.ptr(probs), B, H, Nq, Nk, C, M,
+                  blank_k.data_ptr(), blank_v.data_ptr(), out.data_ptr(), _lib.ptr(probs), 0, B, H, Nq, Nk, C, M,
                   *_s3(q), *_s3(key), *_s3(v), *_s3(ov), _lib.dtype_code(q),
                   nbytes=q.element_size() * (B * H * (2 * Nq + 2 * Nk) * C) + 4 * B * Nq * M + 8 * B * Nq * M)
     out = out.reshape(B, Nq, H * C)
     return (out, probs) if need_probs else out
+
+
+class ClusterAttentionCoreFunction(Function):
+    """The ClusterAttention core (aff.py:114-155) as ONE differentiable op for fp16 / bf16 training:
+
+        out = softmax([q.k_nbhd + bias_tab[bias_idx] + mask, q.blank_k]) @ [v_nbhd; blank_v]
+
+    q [B,N,H,C] and kv [B,N,H,2,C] are the token-major outputs of the ``q`` / ``kv`` Linear layers (q already scaled),
+    bias_tab [R,H] = ``pos_embed`` evaluated on the R referenced table rows, bias_idx int32 [B,N,M] the matching inverse
+    map, mask uint8 [B,N,M] or None, blank_k / blank_v [H*C].  Returns out [B,N,H*C].  Forward = clusten_attn_fwd (saves
+    only out and the log-sum-exp); backward = clusten_attn_bwd + two clusten_scatter_rows + clusten_table_grad: the
+    [B,H,N,M+1] fp32 tensors autograd keeps for the reference's glue passes never exist."""
+
+    @staticmethod
+    def forward(ctx, q, kv, bias_tab, blank_k, blank_v, nbhd_idx, bias_idx, mask):
+        dev = _lib.require_cuda(q, kv, bias_tab, blank_k, blank_v, nbhd_idx, bias_idx, mask)
+        _check_shapes(q.dim() == 4 and kv.dim() == 5 and kv.shape[3] == 2 and q.dtype == kv.dtype and
+                      q.dtype in (torch.float16, torch.bfloat16), "fused attention: q [B,N,H,C], kv [B,N,H,2,C], fp16/bf16")
+        B, N, H, C = q.shape
+        M = nbhd_idx.shape[2]
+        dt = q.dtype
+        q, kv, nbhd_idx = q.contiguous(), kv.contiguous(), _idx(nbhd_idx)
+        tab = bias_tab.detach().to(torch.float32).contiguous()
+        bk, bv = blank_k.detach().to(dt).contiguous(), blank_v.detach().to(dt).contiguous()
+        _check_shapes(tab.dim() == 2 and tab.shape[1] == H and tuple(bias_idx.shape) == (B, N, M) and
+                      bias_idx.dtype == torch.int32 and bias_idx.is_contiguous(), "fused attention: bias table / index mismatch")
+        if mask is not None:
+            _check_shapes(mask.dtype == torch.uint8 and tuple(mask.shape) == (B, N, M) and mask.is_contiguous(), "fused attention: mask must be uint8 [B,N,M]")
+        out = torch.empty((B, N, H, C), dtype=dt, device=dev)
+        lse = torch.empty((B, H, N), dtype=torch.float32, device=dev)
+        qv, kk, vv, ov = q.permute(0, 2, 1, 3), kv[:, :, :, 0].permute(0, 2, 1, 3), kv[:, :, :, 1].permute(0, 2, 1, 3), out.permute(0, 2, 1, 3)
+        if out.numel():
+            with torch.cuda.device(dev):
+                _call("clusten_attn_fwd", dev, qv.data_ptr(), kk.data_ptr(), vv.data_ptr(), nbhd_idx.data_ptr(),
+                      _lib.ptr(neighbourhood_pack(nbhd_idx, N)), tab.data_ptr(), bias_idx.data_ptr(), _lib.ptr(mask),
+                      bk.data_ptr(), bv.data_ptr(), out.data_ptr(), 0, lse.data_ptr(), B, H, N, N, C, M,
+                      *_s3(qv), *_s3(kk), *_s3(vv), *_s3(ov), _lib.dtype_code(q),
+                      nbytes=q.element_size() * (B * H * 4 * N * C) + 4 * B * N * M + 8 * B * N * M)
+        ctx.save_for_backward(q, kv, tab, bk, bv, out, lse, nbhd_idx, bias_idx, mask)
+        ctx.meta = (bias_tab.dtype, blank_k.dtype, blank_v.dtype)
+        return out.view(B, N, H * C)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, kv, tab, bk, bv, out, lse, nbhd_idx, bias_idx, mask = ctx.saved_tensors
+        dev = q.device
+        B, N, H, C = q.shape
+        M = nbhd_idx.shape[2]
+        dt = q.dtype
+        d_out = d_out.to(dt).contiguous().view(B, N, H, C)
+        d_q = torch.empty_like(q)
+        d_kv = torch.empty_like(kv)
+        P = torch.empty((B, H, N, M), dtype=dt, device=dev)
+        dS = torch.empty((B, H, N, M), dtype=dt, device=dev)
+        Pb = torch.empty((B, H, N), dtype=torch.float32, device=dev)
+        dSb = torch.empty((B, H, N), dtype=torch.float32, device=dev)
+        d_tab = torch.zeros(tab.shape, dtype=torch.float32, device=dev)
+        if q.numel():
+            hv = lambda t: t.permute(0, 2, 1, 3)
+            qv, kk, vv, ov, gv, dqv = hv(q), hv(kv[:, :, :, 0]), hv(kv[:, :, :, 1]), hv(out), hv(d_out), hv(d_q)
+            dkv, dvv = hv(d_kv[:, :, :, 0]), hv(d_kv[:, :, :, 1])
+            off, ent = inverse_neighbour_list(nbhd_idx, N, with_pack=True)
+            pack = neighbourhood_pack(nbhd_idx, N, inverse=True)
+            code = _lib.dtype_code(q)
+            es = q.element_size()
+            with torch.cuda.device(dev):
+                _call("clusten_attn_bwd", dev, gv.data_ptr(), ov.data_ptr(), lse.data_ptr(), qv.data_ptr(), kk.data_ptr(), vv.data_ptr(),
+                      nbhd_idx.data_ptr(), _lib.ptr(pack), tab.data_ptr(), bias_idx.data_ptr(), _lib.ptr(mask), bk.data_ptr(),
+                      bv.data_ptr(), d_q.data_ptr(), P.data_ptr(), dS.data_ptr(), Pb.data_ptr(), dSb.data_ptr(),
+                      B, H, N, N, C, M, *_s3(qv), *_s3(kk), *_s3(vv), *_s3(gv), *_s3(ov), *_s3(dqv), code,
+                      nbytes=es * (6 * B * H * N * C + 2 * B * H * N * M) + 12 * B * N * M)
+                _call("clusten_scatter_rows", dev, dS.data_ptr(), qv.data_ptr(), off.data_ptr(), ent.data_ptr(), _lib.ptr(pack),
+                      dkv.data_ptr(), B, H, N, N, C, M, *_s3(dS), *_s3(qv), *_s3(dkv), code,
+                      nbytes=es * (B * H * N * M + 2 * B * H * N * C) + 8 * B * N * M)
+                _call("clusten_scatter_rows", dev, P.data_ptr(), gv.data_ptr(), off.data_ptr(), ent.data_ptr(), _lib.ptr(pack),
+                      dvv.data_ptr(), B, H, N, N, C, M, *_s3(P), *_s3(gv), *_s3(dvv), code,
+                      nbytes=es * (B * H * N * M + 2 * B * H * N * C) + 8 * B * N * M)
+                _call("clusten_table_grad", dev, dS.data_ptr(), bias_idx.data_ptr(), 0, d_tab.data_ptr(), B * N * M, tab.shape[0], H,
+                      N * M, H * N * M, 1, N * M, code, nbytes=es * B * H * N * M + 4 * B * N * M)
+        # blank-token parameters: tiny [H,C] reductions over all tokens (cuBLAS batched GEMV-like, fp32 accumulation)
+        d_bk = torch.einsum("bhn,bnhc->hc", dSb.to(dt), q).reshape(-1)
+        d_bv = torch.einsum("bhn,bnhc->hc", Pb.to(dt), d_out).reshape(-1)
+        tdt, kdt, vdt = ctx.meta
+        return d_q, d_kv, d_tab.to(tdt), d_bk.to(kdt), d_bv.to(vdt), None, None, None
+
+
+def cluster_attention_core(q, kv, bias_tab, blank_k, blank_v, nbhd_idx, bias_idx, mask):
+    return ClusterAttentionCoreFunction.apply(q, kv, bias_tab, blank_k, blank_v, nbhd_idx, bias_idx, mask)
+
+
+# ---- LayerNorm -------------------------------------------------------------------------------------------------------
+class LayerNormFunction(Function):
+    """LayerNorm over the last dimension (C <= 1024), one warp per row (clusten_layer_norm_fwd / _bwd).  ``out_dtype`` lets
+    the caller take the result in the dtype the consumer will cast it to anyway (the Linear layers under autocast)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        dev = _lib.require_cuda(x, weight, bias)
+        C = x.shape[-1]
+        xc = x.contiguous()
+        w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        R = xc.numel() // C
+        y = torch.empty(xc.shape, dtype=out_dtype, device=dev)
+        need = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or bias.requires_grad)
+        mean = torch.empty(R, dtype=torch.float32, device=dev) if need else None
+        rstd = torch.empty(R, dtype=torch.float32, device=dev) if need else None
+        if R:
+            with torch.cuda.device(dev):
+                _call("clusten_layer_norm_fwd", dev, xc.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), _lib.ptr(mean),
+                      _lib.ptr(rstd), R, C, float(eps), _lib.dtype_code(xc), _lib.DTYPES[out_dtype],
+                      nbytes=R * C * (xc.element_size() + y.element_size()))
+        ctx.save_for_backward(xc, w, mean, rstd)
+        ctx.wdt = (weight.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, w, mean, rstd = ctx.saved_tensors
+        dev = xc.device
+        C = xc.shape[-1]
+        R = xc.numel() // C
+        dy = dy.contiguous()
+        if dy.dtype not in _lib.DTYPES:
+            dy = dy.float()
+        dx = torch.empty_like(xc)
+        dg = torch.zeros(C, dtype=torch.float32, device=dev)
+        db = torch.zeros(C, dtype=torch.float32, device=dev)
+        if R:
+            with torch.cuda.device(dev):
+                _call("clusten_layer_norm_bwd", dev, dy.data_ptr(), xc.data_ptr(), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                      dx.data_ptr(), dg.data_ptr(), db.data_ptr(), R, C, _lib.dtype_code(xc), _lib.dtype_code(dy),
+                      nbytes=R * C * (2 * xc.element_size() + dy.element_size()))
+        return dx, dg.to(ctx.wdt[0]), db.to(ctx.wdt[1]), None, None
+
+
+def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None):
+    return LayerNormFunction.apply(x, weight, bias, eps, out_dtype or x.dtype)
+
+
+# ---- relative-position table lookup ----------------------------------------------------------------------------------
+class TableLookupFunction(Function):
+    """``tab[inverse]`` with a backward that does not go through ATen's sort-based ``index_put_(accumulate=True)``
+    (hundreds of ms for the ~25 M duplicated indices of an AFF stage): out[..., c] = tab[inverse[...], c].
+
+    tab [U, CH] (fp32 / fp16 / bf16), inverse int64 or int32 of any shape -> out [*inverse.shape, CH].  The gradient is a
+    shared-memory-privatised fp32 segment sum (clusten_table_grad); its summation order is not fixed (fp32 atomics)."""
+
+    @staticmethod
+    def forward(ctx, tab, inverse):
+        dev = _lib.require_cuda(tab, inverse)
+        _check_shapes(tab.dim() == 2 and inverse.dtype in (torch.int64, torch.int32), "table lookup: tab [U,CH], inverse int32/int64")
+        tab = tab.contiguous()
+        inverse = inverse.contiguous()
+        U, CH = tab.shape
+        out = torch.empty((*inverse.shape, CH), dtype=tab.dtype, device=dev)
+        n = inverse.numel()
+        if n:
+            with torch.cuda.device(dev):
+                _call("clusten_table_gather", dev, tab.data_ptr(), inverse.data_ptr(), int(inverse.dtype == torch.int64),
+                      out.data_ptr(), n, U, CH, _lib.dtype_code(tab))
+        ctx.save_for_backward(inverse)
+        ctx.tab_shape, ctx.tab_dtype = (U, CH), tab.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (inverse,) = ctx.saved_tensors
+        U, CH = ctx.tab_shape
+        dev = grad.device
+        d_tab = torch.zeros((U, CH), dtype=torch.float32, device=dev)
+        n = inverse.numel()
+        if n:
+            if grad.dtype not in _lib.DTYPES:
+                grad = grad.float()
+            # address grad as base + b*sb + e*se + c*sc with e running over all but the first index dimension
+            g = grad.reshape(inverse.shape[0], -1, CH) if inverse.dim() > 1 else grad.reshape(1, -1, CH)
+            if g.data_ptr() != grad.data_ptr():              # reshape had to copy: now contiguous
+                g = g.contiguous()
+            with torch.cuda.device(dev):
+                _call("clusten_table_grad", dev, g.data_ptr(), inverse.data_ptr(), int(inverse.dtype == torch.int64),
+                      d_tab.data_ptr(), n, U, CH, g.shape[1], g.stride(0), g.stride(1), g.stride(2), _lib.dtype_code(g))
+        return d_tab.to(ctx.tab_dtype), None
+
+
+def table_lookup(tab, inverse):
+    return TableLookupFunction.apply(tab, inverse)
 
 
 # ---- WF --------------------------------------------------------------------------------------------------------------

@@ -77,6 +77,40 @@ def space_filling_cluster(pos, m, h, w, no_reorder=False, sf_type='', use_anchor
     return pos_sorted, mean_pos, member_idx, cluster_mask, ranking
 
 
+PE_TABLE_WIDTH = 1023                                  # aff.py:17-19 (2 * (2048 // 4 - 1) + 1)
+
+
+def stage_prepare(pos, nearest, member, cluster_mask, want_mask64=True):
+    """Neighbourhood assembly of one AFF stage (aff.py:475-485) in one pass: returns
+    (member_idx int64 [B,n,M], mask int64 [B,n,M] or None, mask_u8 uint8 [B,n,M] or None, uniq int64 [U], bias_idx int32
+    [B,n,M]) with uniq = the ascending distinct relative-position table rows ``pe_idx`` takes and bias_idx its inverse map
+    (``torch.unique(pe_idx, return_inverse=True)`` without the sort).  One host read (U)."""
+    dev = _lib.require_cuda(pos, nearest, member, cluster_mask)
+    p = _f32c(pos)
+    nearest, member = nearest.contiguous(), member.contiguous()
+    B, n, nnc = nearest.shape
+    k, m = member.shape[1], member.shape[2]
+    M = nnc * m
+    cm = None if cluster_mask is None else cluster_mask.contiguous()
+    member_idx = torch.empty((B, n, M), dtype=torch.int64, device=dev)
+    mask64 = torch.empty((B, n, M), dtype=torch.int64, device=dev) if (cm is not None and want_mask64) else None
+    mask8 = torch.empty((B, n, M), dtype=torch.uint8, device=dev) if cm is not None else None
+    pe = torch.empty((B, n, M), dtype=torch.int32, device=dev)
+    bias_idx = torch.empty((B, n, M), dtype=torch.int32, device=dev)
+    cap = max(1, min(PE_TABLE_WIDTH * PE_TABLE_WIDTH, B * n * M))
+    uniq = torch.empty(cap, dtype=torch.int32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    ws_bytes = L.clusten_prepare_workspace_bytes()
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _call("clusten_stage_prepare", dev, nearest.data_ptr(), member.data_ptr(), _lib.ptr(cm), p.data_ptr(), B, n, k, m, nnc,
+              member_idx.data_ptr(), _lib.ptr(mask64), _lib.ptr(mask8), pe.data_ptr(), bias_idx.data_ptr(), uniq.data_ptr(), cap,
+              count.data_ptr(), ws.data_ptr(), ws_bytes)
+    U = int(count.item())
+    return member_idx, mask64, mask8, uniq[:U].long(), bias_idx
+
+
 def topk_select(score, k, out=None):
     """Canonical ``score.topk(k, sorted=False)[1]`` (aff.py:320): first k of a stable descending sort, int64 [B,k]."""
     dev = _lib.require_cuda(score)

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define CLUSTEN_ABI_VERSION 2
+#define CLUSTEN_ABI_VERSION 3
 
 enum { CLUSTEN_F32 = 0, CLUSTEN_F16 = 1, CLUSTEN_BF16 = 2 };
 
@@ -113,14 +113,36 @@ int clusten_av_bwd(const void *d_feat, const void *attn, const void *v,
  *   out[b,h,i,:]   = sum_j p[j] v[b,h,idx[b,i,j],:] + p[M] blank_v[h*C:(h+1)*C]
  * q is expected pre-scaled (aff.py:104).  q/k/v/out: strided rows like clusten_qk_fwd; bias_tab fp32 [R,H]; bias_idx int32
  * [B,Nq,M]; mask uint8 [B,Nq,M] or NULL; blank_k/blank_v: [H*C] of the call's dtype; probs: fp32 [B,H,Nq,M+1] or NULL
- * (the softmax output, written once for a backward pass).  pack may be NULL (generic kernel only). */
+ * (the softmax output); lse: fp32 [B,H,Nq] or NULL (log-sum-exp of the M+1 logits, what clusten_attn_bwd recomputes the
+ * probabilities from).  pack may be NULL (generic kernel only). */
 int clusten_attn_fwd(const void *q, const void *k, const void *v, const int64_t *nbhd_idx, const void *pack,
                      const float *bias_tab, const int32_t *bias_idx, const uint8_t *mask,
-                     const void *blank_k, const void *blank_v, void *out, float *probs,
+                     const void *blank_k, const void *blank_v, void *out, float *probs, float *lse,
                      int B, int H, int Nq, int Nk, int C, int M,
                      int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t k_sb, int64_t k_sh, int64_t k_sn,
                      int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t o_sb, int64_t o_sh, int64_t o_sn,
                      int dtype, void *stream);
+
+/* ---- fused ClusterAttention core, backward (fp16 / bf16): token-tile part.  Recomputes p = exp(logit - lse) and writes
+ *   d_q (strided rows), probs = p[:, :, :, 0:M] and d_logits = p (dp - D) as [B,H,Nq,M] tensors of the call's dtype, and the
+ *   blank-token column p_blank / ds_blank as fp32 [B,H,Nq].  The caller finishes with
+ *   d_k = clusten_scatter_rows(d_logits, q), d_v = clusten_scatter_rows(probs, d_out), d_bias_tab = clusten_table_grad(d_logits,
+ *   bias_idx), d_blank_k[h] = sum_i ds_blank q_i, d_blank_v[h] = sum_i p_blank d_out_i.   (aff.py:114-155 backwards) */
+int clusten_attn_bwd(const void *d_out, const void *out, const float *lse, const void *q, const void *k, const void *v,
+                     const int64_t *nbhd_idx, const void *pack, const float *bias_tab, const int32_t *bias_idx,
+                     const uint8_t *mask, const void *blank_k, const void *blank_v,
+                     void *d_q, void *probs, void *d_logits, float *p_blank, float *ds_blank,
+                     int B, int H, int Nq, int Nk, int C, int M,
+                     int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t k_sb, int64_t k_sh, int64_t k_sn,
+                     int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t do_sb, int64_t do_sh, int64_t do_sn,
+                     int64_t o_sb, int64_t o_sh, int64_t o_sn, int64_t dq_sb, int64_t dq_sh, int64_t dq_sn,
+                     int dtype, void *stream);
+/* out[b,h,r,:] = sum_{(i,j): idx[b,i,j]=r} w[b,h,i,j] x[b,h,i,:]: the scatter half of clusten_qk_bwd / clusten_av_bwd on its own
+ * (deterministic: inverse lists, no atomics).  w addressed base + b*w_sb + h*w_sh + i*w_sn + j. */
+int clusten_scatter_rows(const void *w, const void *x, const int32_t *csr_offsets, const uint32_t *csr_entries,
+                         const void *pack /* or NULL */, void *out, int B, int H, int Nq, int Nk, int C, int M,
+                         int64_t w_sb, int64_t w_sh, int64_t w_sn, int64_t x_sb, int64_t x_sh, int64_t x_sn,
+                         int64_t o_sb, int64_t o_sh, int64_t o_sn, int dtype, void *stream);
 
 /* ---- relative-position table lookup (aff.py:129-132, 346-349) restricted to the table rows a stage references:
  *   gather: out[e,c] = tab[inv[e],c]  (e < n, c < CH; tab/out of the call's dtype; inv int32 or int64)
@@ -131,6 +153,28 @@ int clusten_table_gather(const void *tab, const void *inv, int inv_is_i64, void 
                          int dtype, void *stream);
 int clusten_table_grad(const void *d_out, const void *inv, int inv_is_i64, float *d_tab, int64_t n, int U, int CH,
                        int64_t n_per, int64_t d_sb, int64_t d_se, int64_t d_sc, int dtype, void *stream);
+
+/* ---- LayerNorm over the channel dimension of [R, C] token rows, C <= 1024 (aff.py:196-199,258,617-620): one warp per row.
+ * x / y (and d_y) may be fp32 / fp16 / bf16 independently; gamma, beta, mean, rstd, d_gamma, d_beta are fp32.  mean / rstd may
+ * both be NULL in inference.  d_gamma / d_beta are accumulated into (caller zeroes them; fp32 atomics across CTAs). */
+int clusten_layer_norm_fwd(const void *x, const float *gamma, const float *beta, void *y, float *mean, float *rstd,
+                           int64_t R, int C, float eps, int x_dtype, int y_dtype, void *stream);
+int clusten_layer_norm_bwd(const void *d_y, const void *x, const float *gamma, const float *mean, const float *rstd,
+                           void *d_x /* x's dtype */, float *d_gamma, float *d_beta, int64_t R, int C, int x_dtype, int g_dtype,
+                           void *stream);
+
+/* ---- stage preparation (aff.py:475-485 in one pass + the restriction of the 1023^2-row position table to the referenced rows):
+ *   member_idx[b,i,c*m+r] = member[b, nearest[b,i,c], r]   (int64 [B,n,nnc*m]);   mask64 / mask8 = the same gather of
+ *   cluster_mask (either may be NULL; both ignored when cluster_mask is NULL);
+ *   pe_idx[b,i,j] = rel.y*1023 + rel.x with rel = clamp(pos[member_idx] - (pos[i] - 511), 0, 1022)          (int32)
+ *   uniq[0:U] = ascending distinct pe_idx values (what torch.unique returns), bias_idx = rank of pe_idx in uniq (int32),
+ *   *count = U (device scalar; uniq is written up to uniq_cap entries).  No sort: presence map + scan. */
+size_t clusten_prepare_workspace_bytes(void);
+int clusten_stage_prepare(const int64_t *nearest /* [B,n,nnc] */, const int64_t *member /* [B,k,m] */,
+                          const int64_t *cluster_mask /* [B,k,m] or NULL */, const float *pos /* [B,n,2] */,
+                          int B, int n, int k, int m, int nnc,
+                          int64_t *member_idx, int64_t *mask64, uint8_t *mask8, int32_t *pe_idx, int32_t *bias_idx,
+                          int32_t *uniq, int uniq_cap, int32_t *count, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- WF: out[b,i,ic,c] = sum_j w[b,i,j,ic] * f[b,idx[b,i,j],c]             (clustenwf_cuda_kernel.cu:41-49)
  * w [B,Nq,M,IC] contiguous, f rows base + b*f_sb + n*f_sn + c, out [B,Nq,IC,C] contiguous.  IC in {1,2,4,8}. */

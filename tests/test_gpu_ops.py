@@ -357,3 +357,128 @@ def test_fused_attention_core(n, m, nbhd, kind, H, C, dtype):
     assert rel_err(probs, ref_p) <= tol
     if kind == "clustered":
         assert ops.pack_flags(idx.cuda(), n)[0] == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("U,CH,shape,permuted", [(700, 3, (2, 500, 48), True), (700, 3, (2, 500, 48), False), (5000, 16, (1, 300, 48), True),
+                                                 (37, 4, (3, 200, 48), False), (1, 2, (1, 5, 8), False)])
+def test_table_lookup(U, CH, shape, permuted, dtype):
+    """tab[inverse] (aff.py:129-132 restricted to the referenced table rows) and its segment-sum gradient against torch
+    indexing in fp32; the permuted case is the [B,H,N,M] gradient layout of the attention bias."""
+    from autofocusformermod_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    tab = torch.randn(U, CH, generator=g).to(dtype)
+    inv = torch.randint(0, U, shape, generator=g)
+    d_out = torch.randn(*shape, CH, generator=g).to(dtype)
+    t_ref = tab.float().requires_grad_(True)
+    ref = t_ref[inv]
+    ref.backward(d_out.float())
+    for idt in (torch.int64, torch.int32):
+        t = tab.cuda().detach().requires_grad_(True)
+        out = ops.table_lookup(t, inv.cuda().to(idt))
+        assert out.dtype == dtype and tuple(out.shape) == (*shape, CH)
+        assert torch.equal(out.detach().float().cpu(), ref.detach())
+        go = d_out.cuda()
+        if permuted:                                   # gradient arrives as a permuted view of [B,CH,N,M] memory
+            go = go.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+        out.backward(go)
+        torch.cuda.synchronize()
+        assert rel_err(t.grad.float().cpu(), t_ref.grad) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("H,C", [(2, 16), (3, 32), (16, 24)])
+@pytest.mark.parametrize("n,m,nbhd,kind", [(1024, 8, 48, "clustered"), (2003, 8, 48, "clustered"), (1540, 24, 144, "clustered"),
+                                            (300, 8, 48, "random")])
+def test_fused_attention_core_backward(n, m, nbhd, kind, H, C, dtype):
+    """ClusterAttentionCoreFunction (clusten_attn_fwd + clusten_attn_bwd + scatter + table grad) against autograd of the
+    op-by-op oracle composition (aff.py:114-155) in fp32 on the same 16-bit-rounded inputs: out and the gradients of q,
+    kv, the bias table, blank_k and blank_v."""
+    from autofocusformermod_b200 import ops
+    B = 2
+    if kind == "clustered":
+        _, idx, mask, _ = inputs.structured_neighbourhood(B, n, 64, 64, m, nbhd, seed=n)
+    else:
+        idx, mask = inputs.random_neighbourhood(B, n, n, nbhd, seed=n), None
+    M = idx.shape[-1]
+    g = torch.Generator().manual_seed(n + H)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dtype).float()
+    q = (rnd(B, n, H, C) * C ** -0.5).to(dtype).float()
+    kv = rnd(B, n, H, 2, C)
+    R = 37
+    bias_tab = torch.randn(R, H, generator=g)
+    bias_idx = torch.randint(0, R, (B, n, M), generator=g, dtype=torch.int32)
+    blank_k, blank_v = rnd(H * C), rnd(H * C)
+    d_out = rnd(B, n, H * C)
+    leaves = [t.clone().requires_grad_(True) for t in (q, kv, bias_tab, blank_k, blank_v)]
+    rq, rkv, rtab, rbk, rbv = leaves
+    ref_out, _ = _fused_reference(rq.permute(0, 2, 1, 3), rkv[:, :, :, 0].permute(0, 2, 1, 3), rkv[:, :, :, 1].permute(0, 2, 1, 3), idx,
+                                  rtab, bias_idx, mask, rbk, rbv)
+    ref_out.backward(d_out)
+    cq, ckv = q.cuda().to(dtype).requires_grad_(True), kv.cuda().to(dtype).requires_grad_(True)
+    ctab = bias_tab.cuda().requires_grad_(True)
+    cbk, cbv = blank_k.cuda().requires_grad_(True), blank_v.cuda().requires_grad_(True)
+    out = ops.cluster_attention_core(cq, ckv, ctab, cbk, cbv, idx.cuda(), bias_idx.cuda(),
+                                     None if mask is None else mask.to(torch.uint8).cuda())
+    out.backward(d_out.cuda().to(dtype))
+    torch.cuda.synchronize()
+    tol = 1e-2
+    assert rel_err(out.float().cpu(), ref_out.detach()) <= tol
+    for name, got, ref in (("d_q", cq, rq), ("d_kv", ckv, rkv), ("d_bias_tab", ctab, rtab), ("d_blank_k", cbk, rbk), ("d_blank_v", cbv, rbv)):
+        e = rel_err(got.grad.float().cpu(), ref.grad)
+        assert e <= 2 * tol, f"{name} rel err {e:.3e}"
+
+
+@pytest.mark.parametrize("xdt,ydt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16)],
+                         ids=["f32", "bf16-f32", "bf16-bf16"])
+@pytest.mark.parametrize("R,C", [(1000, 32), (513, 96), (64, 384), (7, 1024), (300, 100), (5, 8)])
+def test_layer_norm(R, C, xdt, ydt):
+    """clusten_layer_norm_fwd / _bwd (one warp per token row) against torch.nn.functional.layer_norm in fp32."""
+    from autofocusformermod_b200 import ops
+    g = torch.Generator().manual_seed(R + C)
+    x = (torch.randn(R, C, generator=g) * 2 + 0.5).to(xdt)
+    w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    dy = torch.randn(R, C, generator=g).to(ydt)
+    xr, wr, br = x.float().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (C,), wr, br, 1e-5)
+    ref.backward(dy.float())
+    xc, wc, bc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y = ops.layer_norm(xc, wc, bc, 1e-5, ydt)
+    assert y.dtype == ydt
+    y.backward(dy.cuda())
+    torch.cuda.synchronize()
+    tol = 1e-5 if (xdt, ydt) == (torch.float32, torch.float32) else 1e-2
+    assert rel_err(y.float().cpu(), ref.detach()) <= tol
+    assert rel_err(xc.grad.float().cpu(), xr.grad) <= tol
+    assert rel_err(wc.grad.cpu(), wr.grad) <= max(tol, 2e-5)
+    assert rel_err(bc.grad.cpu(), br.grad) <= max(tol, 2e-5)
+
+
+@pytest.mark.parametrize("n,m,nbhd,hw", [(4096, 8, 48, 64), (2003, 8, 48, 64), (1540, 24, 144, 64), (655, 8, 48, 128)])
+def test_stage_prepare_matches_torch_formulation(n, m, nbhd, hw):
+    """clusten_stage_prepare against the op-by-op torch formulation of aff.py:475-485 + torch.unique (bit-exact integers)."""
+    import math
+    from autofocusformermod_b200 import point_utils as pu
+    B = 2
+    g = torch.Generator().manual_seed(n)
+    pos = torch.stack([torch.randperm(hw * hw, generator=g)[:n] for _ in range(B)])
+    pos = torch.stack([pos % hw, pos // hw], dim=-1).float().cuda()
+    pos, mean_pos, member, cmask, _ = pu.space_filling_cluster(pos, m, hw, hw)
+    k = member.shape[1]
+    nnc = min(int(round(nbhd / float(m))), k)
+    nearest = pu.knn_keops(pos, mean_pos, nnc)
+    gi = nearest.view(B, -1, 1).expand(-1, -1, m)
+    ref_member = member.gather(index=gi, dim=1).reshape(B, n, nnc * m)
+    ref_mask = None if cmask is None else cmask.gather(index=gi, dim=1).reshape(B, n, nnc * m)
+    pos_nb = pos.gather(index=ref_member.view(B, -1, 1).expand(-1, -1, 2), dim=1).reshape(B, n, nnc * m, 2)
+    rel = (pos_nb - (pos.unsqueeze(2) - 511)).clamp(0, 1022)
+    pe = (rel[..., 1] * 1023 + rel[..., 0]).long()
+    ref_uniq, ref_inv = torch.unique(pe.reshape(-1), return_inverse=True)
+    member_idx, mask64, mask8, uniq, bias_idx = pu.stage_prepare(pos, nearest, member, cmask)
+    assert torch.equal(member_idx, ref_member)
+    if cmask is None:
+        assert mask64 is None and mask8 is None
+    else:
+        assert torch.equal(mask64, ref_mask) and torch.equal(mask8.long(), ref_mask)
+    assert torch.equal(uniq, ref_uniq)
+    assert torch.equal(bias_idx.reshape(-1).long(), ref_inv)
