@@ -38,8 +38,10 @@ SIGNATURES = {
     "clusten_stage_prepare": (_I, [_P] * 4 + [_I] * 5 + [_P] * 6 + [_I, _P, _P, _Z, _P]),
     "clusten_table_gather": (_I, [_P, _P, _I, _P, _L, _I, _I, _I, _P]),
     "clusten_table_grad": (_I, [_P, _P, _I, _P, _L, _I, _I, _L, _L, _L, _L, _I, _P]),
-    "clusten_wf_fwd": (_I, [_P] * 4 + [_I] * 6 + [_L] * 2 + [_I, _P]),
-    "clusten_wf_bwd": (_I, [_P] * 8 + [_I] * 6 + [_L] * 4 + [_I, _P]),
+    "clusten_wf_plan_bytes": (_Z, [_I] * 4),
+    "clusten_wf_plan_build": (_I, [_P, _I, _I, _I, _I, _P, _Z, _P]),
+    "clusten_wf_fwd": (_I, [_P] * 5 + [_I] * 6 + [_L] * 2 + [_I, _P]),
+    "clusten_wf_bwd": (_I, [_P] * 9 + [_I] * 6 + [_L] * 4 + [_I, _P]),
     "clusten_wg_fwd": (_I, [_P] * 4 + [_I] * 5 + [_L] * 2 + [_I, _P]),
     "clusten_wg_bwd": (_I, [_P] * 8 + [_I] * 5 + [_L] * 4 + [_I, _P]),
     "clusten_knn": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),

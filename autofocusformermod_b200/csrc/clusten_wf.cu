@@ -8,9 +8,11 @@
 //                                                                    the atomics of clustenwf_cuda_kernel.cu:129
 // One warp owns one output token (fwd, d_w) or one feature row (d_f) and walks the channel dimension in blocks of
 // 32 x 16 bytes; rows with fewer than 32 chunks are shared by lane groups exactly as in clusten_attn.cu.
+#include <algorithm>
 #include <initializer_list>
 
 #include "common.cuh"
+#include "wf2.cuh"
 
 namespace clusten {
 
@@ -140,17 +142,17 @@ template <typename T, int G, int IC>
 __global__ void __launch_bounds__(CTA_THREADS)
 wf_df_kernel(const T *__restrict__ dO, const T *__restrict__ Wt, const int32_t *__restrict__ offsets,
              const uint32_t *__restrict__ entries, T *__restrict__ dF,
-             int B, int Nq, int Nk, int nchunk, int M, int64_t df_sb, int64_t df_sn) {
+             int B, int Nq, int Nk, int nchunk, int M, int64_t df_sb, int64_t df_sn, const int *__restrict__ run_if) {
     constexpr int VPT = Vec<T>::VPT;
+    if (run_if && run_if[0] == 0) return;            // the octet kernels of clusten_wf2.cu own this call (wf2.cuh flags[0])
     constexpr int RPI = 32 / G;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
-    if (row >= (int64_t)B * Nk) return;
+    const int grp = lane / G, lg = lane % G;
+    const int C = nchunk * VPT;
+    for (int64_t row = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; row < (int64_t)B * Nk; row += (int64_t)gridDim.x * WARPS_PER_CTA) {
     const int b = (int)(row / Nk), r = (int)(row - (int64_t)b * Nk);
     const int lo = offsets[(int64_t)b * (Nk + 1) + r], hi = offsets[(int64_t)b * (Nk + 1) + r + 1];
     const uint32_t *ent = entries + (int64_t)b * Nq * M;
-    const int grp = lane / G, lg = lane % G;
-    const int C = nchunk * VPT;
     const T *wb = Wt + (int64_t)b * Nq * M * IC;
     const T *dob = dO + (int64_t)b * Nq * IC * C;
     for (int c0 = 0; c0 < nchunk; c0 += G) {
@@ -180,6 +182,7 @@ wf_df_kernel(const T *__restrict__ dO, const T *__restrict__ Wt, const int32_t *
 #pragma unroll
         for (int v = 0; v < VPT; ++v) acc[v] = cross_group_sum<G>(acc[v]);
         if (grp == 0 && act) store16(dF + b * df_sb + (int64_t)r * df_sn + ch * VPT, acc);
+    }
     }
 }
 
@@ -215,7 +218,8 @@ __global__ void wf_dw_scalar(const T *dO, const T *F, const int64_t *idx, T *dW,
 }
 template <typename T>
 __global__ void wf_df_scalar(const T *dO, const T *Wt, const int32_t *offsets, const uint32_t *entries, T *dF,
-                             int B, int Nq, int Nk, int C, int M, int IC, int64_t df_sb, int64_t df_sn) {
+                             int B, int Nq, int Nk, int C, int M, int IC, int64_t df_sb, int64_t df_sn, const int *run_if) {
+    if (run_if && run_if[0] == 0) return;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)B * Nk * C) return;
     const int c = (int)(t % C);
@@ -254,9 +258,11 @@ template <typename T> static bool wf_vec_ok(int C, int IC, const void *f, int64_
     }
 
 template <typename T>
-static int wf_fwd_impl(const T *w, const T *f, const int64_t *idx, T *out, int B, int Nq, int C, int M, int IC_,
-                       int64_t f_sb, int64_t f_sn, cudaStream_t st) {
+static int wf_fwd_impl(const T *w, const T *f, const int64_t *idx, T *out, const void *plan, int B, int Nq, int Nk, int C, int M, int IC_,
+                       int64_t f_sb, int64_t f_sn, int dtype, cudaStream_t st) {
     if ((int64_t)B * Nq == 0) return 0;
+    if (plan && wf3_fwd(w, f, idx, out, plan, B, Nq, Nk, C, M, IC_, f_sb, f_sn, dtype, st) > 0) return check_launch("wf3_fwd");
+    if (wf2_fwd(w, f, idx, out, plan, B, Nq, Nk, C, M, IC_, f_sb, f_sn, dtype, st)) return check_launch("wf2_fwd");
     if (wf_vec_ok<T>(C, IC_, f, f_sb, f_sn, {out})) {
         const int nchunk = C / Vec<T>::VPT;
         const int grid = ceil_div((int64_t)B * Nq, WARPS_PER_CTA);
@@ -273,9 +279,13 @@ static int wf_fwd_impl(const T *w, const T *f, const int64_t *idx, T *out, int B
 
 template <typename T>
 static int wf_bwd_impl(const T *d_out, const T *w, const T *f, const int64_t *idx, const int32_t *off,
-                       const uint32_t *ent, T *d_w, T *d_f, int B, int Nq, int Nk, int C, int M, int IC_,
-                       int64_t f_sb, int64_t f_sn, int64_t df_sb, int64_t df_sn, cudaStream_t st) {
+                       const uint32_t *ent, const void *plan, T *d_w, T *d_f, int B, int Nq, int Nk, int C, int M, int IC_,
+                       int64_t f_sb, int64_t f_sn, int64_t df_sb, int64_t df_sn, int dtype, cudaStream_t st) {
+    const int *run_if = nullptr;
     if ((int64_t)B * Nq > 0) {
+        if (wf2_dw(d_out, f, idx, d_w, plan, B, Nq, Nk, C, M, IC_, f_sb, f_sn, dtype, st)) {
+            if (int e = check_launch("wf2_dw")) return e;
+        } else {
         if (wf_vec_ok<T>(C, IC_, f, f_sb, f_sn, {d_out})) {
             const int nchunk = C / Vec<T>::VPT;
             const int grid = ceil_div((int64_t)B * Nq, WARPS_PER_CTA);
@@ -288,17 +298,24 @@ static int wf_bwd_impl(const T *d_out, const T *w, const T *f, const int64_t *id
         }
         note_launches(1);
         if (int e = check_launch("wf_dw")) return e;
+        }
+        // octet form of d_f; the generic kernels below then only run when the plan says so (device-side flag)
+        if (wf2_df(d_out, w, idx, d_f, plan, B, Nq, Nk, C, M, IC_, df_sb, df_sn, dtype, st)) {
+            if (int e = check_launch("wf2_df")) return e;
+            run_if = reinterpret_cast<const int *>(plan);
+        }
     }
     if ((int64_t)B * Nk > 0) {
         if (wf_vec_ok<T>(C, IC_, d_f, df_sb, df_sn, {d_out})) {
             const int nchunk = C / Vec<T>::VPT;
-            const int grid = ceil_div((int64_t)B * Nk, WARPS_PER_CTA);
+            // behind a device-side flag the kernel usually exits at once: a short grid (it strides over the rows) keeps that cheap
+            const int grid = run_if ? std::min(ceil_div((int64_t)B * Nk, WARPS_PER_CTA), 148 * 8) : ceil_div((int64_t)B * Nk, WARPS_PER_CTA);
             CLUSTEN_DISPATCH_IC(IC_, CLUSTEN_DISPATCH_GROUP(pick_group(nchunk),
                 (wf_df_kernel<T, G, IC><<<grid, CTA_THREADS, 0, st>>>(d_out, w, off, ent, d_f, B, Nq, Nk, nchunk, M,
-                                                                      df_sb, df_sn))));
+                                                                      df_sb, df_sn, run_if))));
         } else {
             const int64_t total = (int64_t)B * Nk * C;
-            wf_df_scalar<T><<<ceil_div(total, 256), 256, 0, st>>>(d_out, w, off, ent, d_f, B, Nq, Nk, C, M, IC_, df_sb, df_sn);
+            wf_df_scalar<T><<<ceil_div(total, 256), 256, 0, st>>>(d_out, w, off, ent, d_f, B, Nq, Nk, C, M, IC_, df_sb, df_sn, run_if);
         }
         note_launches(1);
         if (int e = check_launch("wf_df")) return e;
@@ -317,18 +334,18 @@ static int wf_check(int B, int Nq, int Nk, int C, int M, int IC) {
 
 using namespace clusten;
 
-extern "C" int clusten_wf_fwd(const void *w, const void *f, const int64_t *nbhd_idx, void *out,
+extern "C" int clusten_wf_fwd(const void *w, const void *f, const int64_t *nbhd_idx, const void *plan, void *out,
                               int B, int Nq, int Nk, int C, int M, int IC, int64_t f_sb, int64_t f_sn,
                               int dtype, void *stream) {
     if (int e = wf_check(B, Nq, Nk, C, M, IC)) return e;
     if (!w || !f || !nbhd_idx || !out) return set_error(CLUSTEN_EINVAL, "null pointer");
-    CLUSTEN_DISPATCH_DTYPE(dtype, return wf_fwd_impl<T>((const T *)w, (const T *)f, nbhd_idx, (T *)out, B, Nq, C, M, IC,
-                                                        f_sb, f_sn, (cudaStream_t)stream));
+    CLUSTEN_DISPATCH_DTYPE(dtype, return wf_fwd_impl<T>((const T *)w, (const T *)f, nbhd_idx, (T *)out, plan, B, Nq, Nk, C, M, IC,
+                                                        f_sb, f_sn, dtype, (cudaStream_t)stream));
     return 0;
 }
 
 extern "C" int clusten_wf_bwd(const void *d_out, const void *w, const void *f, const int64_t *nbhd_idx,
-                              const int32_t *csr_offsets, const uint32_t *csr_entries, void *d_w, void *d_f,
+                              const int32_t *csr_offsets, const uint32_t *csr_entries, const void *plan, void *d_w, void *d_f,
                               int B, int Nq, int Nk, int C, int M, int IC, int64_t f_sb, int64_t f_sn,
                               int64_t df_sb, int64_t df_sn, int dtype, void *stream) {
     if (int e = wf_check(B, Nq, Nk, C, M, IC)) return e;
@@ -336,20 +353,20 @@ extern "C" int clusten_wf_bwd(const void *d_out, const void *w, const void *f, c
         return set_error(CLUSTEN_EINVAL, "null pointer");
     if (M > 256) return set_error(CLUSTEN_EUNSUPPORTED, "backward needs M <= 256 (got %d)", M);
     CLUSTEN_DISPATCH_DTYPE(dtype, return wf_bwd_impl<T>((const T *)d_out, (const T *)w, (const T *)f, nbhd_idx, csr_offsets,
-                                                        csr_entries, (T *)d_w, (T *)d_f, B, Nq, Nk, C, M, IC, f_sb, f_sn,
-                                                        df_sb, df_sn, (cudaStream_t)stream));
+                                                        csr_entries, plan, (T *)d_w, (T *)d_f, B, Nq, Nk, C, M, IC, f_sb, f_sn,
+                                                        df_sb, df_sn, dtype, (cudaStream_t)stream));
     return 0;
 }
 
 extern "C" int clusten_wg_fwd(const int64_t *nbhd_idx, const void *w, const void *f, void *out,
                               int B, int Nq, int Nk, int C, int K, int64_t f_sb, int64_t f_sn, int dtype, void *stream) {
-    return clusten_wf_fwd(w, f, nbhd_idx, out, B, Nq, Nk, C, K, 1, f_sb, f_sn, dtype, stream);
+    return clusten_wf_fwd(w, f, nbhd_idx, nullptr, out, B, Nq, Nk, C, K, 1, f_sb, f_sn, dtype, stream);
 }
 
 extern "C" int clusten_wg_bwd(const void *d_out, const int64_t *nbhd_idx, const void *w, const void *f,
                               const int32_t *csr_offsets, const uint32_t *csr_entries, void *d_w, void *d_f,
                               int B, int Nq, int Nk, int C, int K, int64_t f_sb, int64_t f_sn,
                               int64_t df_sb, int64_t df_sn, int dtype, void *stream) {
-    return clusten_wf_bwd(d_out, w, f, nbhd_idx, csr_offsets, csr_entries, d_w, d_f, B, Nq, Nk, C, K, 1, f_sb, f_sn,
+    return clusten_wf_bwd(d_out, w, f, nbhd_idx, csr_offsets, csr_entries, nullptr, d_w, d_f, B, Nq, Nk, C, K, 1, f_sb, f_sn,
                           df_sb, df_sn, dtype, stream);
 }

@@ -99,15 +99,18 @@ def _check_shapes(cond, msg):
         raise RuntimeError(msg)
 
 
-def inverse_neighbour_list(nbhd_idx, Nk, with_pack=False):
+def inverse_neighbour_list(nbhd_idx, Nk, with_pack=False, wf_plan_buf=None):
     """(offsets int32 [B,Nk+1], entries uint32-as-int32 [B,Nq*M]) of clusten_csr_build, cached on the index tensor.
     ``with_pack`` (QK / AV backward only): the list is built beside the tile pack and SKIPPED on the device when the
-    pack routes the call to the tile-union kernels, which do not need it."""
+    pack routes the call to the tile-union kernels, which do not need it.  ``wf_plan_buf`` (WF backward): same, keyed
+    on the WF plan's device-side flag."""
     cache = getattr(nbhd_idx, "_clusten_csr", None)
     ver = nbhd_idx._version
-    pack = neighbourhood_pack(nbhd_idx, Nk) if with_pack else None
-    # (a list built beside a pack may have been skipped on the device: never reuse it for a pack-less call)
-    if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr() and cache[5] == (pack is not None):
+    pack = neighbourhood_pack(nbhd_idx, Nk) if with_pack else wf_plan_buf
+    kind = "pack" if with_pack and pack is not None else "wf" if pack is not None else None
+    # (a list built beside a pack / plan may have been skipped on the device: only reuse it for the same kind of call;
+    # an unconditional list serves everyone)
+    if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr() and cache[5] in (None, kind):
         return cache[3], cache[4]
     B, Nq, M = nbhd_idx.shape
     dev = nbhd_idx.device
@@ -120,7 +123,7 @@ def inverse_neighbour_list(nbhd_idx, Nk, with_pack=False):
         _call("clusten_csr_build", dev, nbhd_idx.data_ptr(), B, Nq, M, Nk, offsets.data_ptr(), entries.data_ptr(),
               ws.data_ptr(), ws_bytes, _lib.ptr(pack))
     try:
-        nbhd_idx._clusten_csr = (ver, Nk, nbhd_idx.data_ptr(), offsets, entries, pack is not None)
+        nbhd_idx._clusten_csr = (ver, Nk, nbhd_idx.data_ptr(), offsets, entries, kind)
     except Exception:  # pragma: no cover  (tensor subclass without __dict__)
         pass
     return offsets, entries
@@ -155,6 +158,39 @@ def neighbourhood_pack(nbhd_idx, Nk, inverse=False):
     except Exception:  # pragma: no cover
         pass
     return pack
+
+
+USE_WF_PLAN = True          # False: WF runs without a plan (natural token order, generic d_f)
+
+
+def wf_plan(nbhd_idx, Nk):
+    """Opaque WF plan of clusten_wf_plan_build for this index tensor (uint8 device buffer), cached on the tensor; None
+    when M is not a multiple of 8 (no octet structure to exploit: PointConv's kNN-9, the 4-neighbour upsampling)."""
+    B, Nq, M = nbhd_idx.shape
+    if not USE_WF_PLAN or M % 8 != 0 or B * Nq == 0:
+        return None
+    cache = getattr(nbhd_idx, "_clusten_wf_plan", None)
+    ver = nbhd_idx._version
+    if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr():
+        return cache[3]
+    dev = nbhd_idx.device
+    nbytes = _lib.lib().clusten_wf_plan_bytes(B, Nq, M, Nk)
+    plan = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _call("clusten_wf_plan_build", dev, nbhd_idx.data_ptr(), B, Nq, M, Nk, plan.data_ptr(), nbytes)
+    try:
+        nbhd_idx._clusten_wf_plan = (ver, Nk, nbhd_idx.data_ptr(), plan)
+    except Exception:  # pragma: no cover
+        pass
+    return plan
+
+
+def wf_plan_flags(nbhd_idx, Nk):
+    """(generic_d_f, impure_slots, longest_octet_list) of the WF plan -- synchronises; for tests / diagnostics."""
+    plan = wf_plan(nbhd_idx, Nk)
+    if plan is None:
+        return (1, 0, 0)
+    return tuple(int(x) for x in plan[:12].view(torch.int32).tolist())
 
 
 def pack_flags(nbhd_idx, Nk):
@@ -404,7 +440,7 @@ class LayerNormFunction(Function):
         w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
         R = xc.numel() // C
         y = torch.empty(xc.shape, dtype=out_dtype, device=dev)
-        need = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or bias.requires_grad)
+        need = any(ctx.needs_input_grad[:3])          # (grad mode is off inside Function.forward: ask autograd instead)
         mean = torch.empty(R, dtype=torch.float32, device=dev) if need else None
         rstd = torch.empty(R, dtype=torch.float32, device=dev) if need else None
         if R:
@@ -505,8 +541,9 @@ class CLUSTENWFFunction(Function):
         weights, feat, nbhd_idx = weights.contiguous(), _rows(feat), _idx(nbhd_idx)
         out = torch.empty((B, Nq, IC, C), dtype=weights.dtype, device=dev)
         if out.numel():
+            plan = wf_plan(nbhd_idx, Nk) if weights.element_size() == 2 else None
             with torch.cuda.device(dev):
-                _call("clusten_wf_fwd", dev, weights.data_ptr(), feat.data_ptr(), nbhd_idx.data_ptr(), out.data_ptr(),
+                _call("clusten_wf_fwd", dev, weights.data_ptr(), feat.data_ptr(), nbhd_idx.data_ptr(), _lib.ptr(plan), out.data_ptr(),
                       B, Nq, Nk, C, M, IC, feat.stride(0), feat.stride(1), _lib.dtype_code(weights),
                       nbytes=weights.element_size() * (B * Nq * M * IC + B * Nk * C + B * Nq * IC * C) + 8 * B * Nq * M)
         ctx.save_for_backward(weights, feat, nbhd_idx)
@@ -525,10 +562,11 @@ class CLUSTENWFFunction(Function):
         d_feat = torch.empty((B, Nk, C), dtype=weights.dtype, device=dev)
         if Nq * M == 0 or B == 0:
             return d_weights, d_feat.zero_(), None
-        off, ent = inverse_neighbour_list(nbhd_idx, Nk)
+        plan = wf_plan(nbhd_idx, Nk) if weights.element_size() == 2 and IC == 4 and C % 16 == 0 else None
+        off, ent = inverse_neighbour_list(nbhd_idx, Nk, wf_plan_buf=plan)
         with torch.cuda.device(dev):
             _call("clusten_wf_bwd", dev, grad_feat_new.data_ptr(), weights.data_ptr(), feat.data_ptr(),
-                  nbhd_idx.data_ptr(), off.data_ptr(), ent.data_ptr(), d_weights.data_ptr(), d_feat.data_ptr(),
+                  nbhd_idx.data_ptr(), off.data_ptr(), ent.data_ptr(), _lib.ptr(plan), d_weights.data_ptr(), d_feat.data_ptr(),
                   B, Nq, Nk, C, M, IC, feat.stride(0), feat.stride(1), d_feat.stride(0), d_feat.stride(1),
                   _lib.dtype_code(weights),
                   nbytes=weights.element_size() * (B * Nq * IC * C + 2 * B * Nq * M * IC + 2 * B * Nk * C) + 8 * B * Nq * M)

@@ -154,12 +154,22 @@ def main():
     out_w = torch.empty(B, Nq, IC, Cw, device="cuda", dtype=dt)
     d_out = torch.randn(B, Nq, IC, Cw, device="cuda", generator=gen).to(dt)
     d_w, d_f = torch.empty_like(w), torch.empty_like(f)
-    offw, entw = ops.inverse_neighbour_list(idx_w, N)
+    plan = ops.wf_plan(idx_w, N) if (s == 2 and not args.generic) else None
+    pl = 0 if plan is None else plan.data_ptr()
+    offw, entw = ops.inverse_neighbour_list(idx_w, N, wf_plan_buf=plan)
+    if plan is not None:
+        print(json.dumps({"wf_plan_flags(generic,impure,maxlist)": ops.wf_plan_flags(idx_w, N)}), flush=True)
+        plb = L.clusten_wf_plan_bytes(B, Nq, M, N)
+        pbuf2 = torch.empty(plb, dtype=torch.uint8, device="cuda")
+        run("wf_plan_build", lambda: ck(L.clusten_wf_plan_build(idx_w.data_ptr(), B, Nq, M, N, pbuf2.data_ptr(), plb, st())), B * Nq * M * 8)
     wb, fb, ib, ob = B * Nq * M * IC * s, B * N * Cw * s, B * Nq * M * 8, B * Nq * IC * Cw * s
-    run("wf_fwd", lambda: ck(L.clusten_wf_fwd(w.data_ptr(), f.data_ptr(), idx_w.data_ptr(), out_w.data_ptr(), B, Nq, N, Cw, M, IC,
+    run("wf_fwd", lambda: ck(L.clusten_wf_fwd(w.data_ptr(), f.data_ptr(), idx_w.data_ptr(), pl, out_w.data_ptr(), B, Nq, N, Cw, M, IC,
                                               f.stride(0), f.stride(1), code, st())), wb + fb + ib + ob)
+    if plan is not None:
+        run("wf_fwd (no plan: top-k token order)", lambda: ck(L.clusten_wf_fwd(w.data_ptr(), f.data_ptr(), idx_w.data_ptr(), 0, out_w.data_ptr(), B, Nq, N, Cw, M, IC,
+                                                                       f.stride(0), f.stride(1), code, st())), wb + fb + ib + ob)
     run("wf_bwd", lambda: ck(L.clusten_wf_bwd(d_out.data_ptr(), w.data_ptr(), f.data_ptr(), idx_w.data_ptr(), offw.data_ptr(),
-                                              entw.data_ptr(), d_w.data_ptr(), d_f.data_ptr(), B, Nq, N, Cw, M, IC,
+                                              entw.data_ptr(), pl, d_w.data_ptr(), d_f.data_ptr(), B, Nq, N, Cw, M, IC,
                                               f.stride(0), f.stride(1), d_f.stride(0), d_f.stride(1), code, st())),
         ob + wb + fb + ib + wb + fb)
     if args.ref and dt != torch.bfloat16:

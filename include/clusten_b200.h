@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define CLUSTEN_ABI_VERSION 3
+#define CLUSTEN_ABI_VERSION 4
 
 enum { CLUSTEN_F32 = 0, CLUSTEN_F16 = 1, CLUSTEN_BF16 = 2 };
 
@@ -176,15 +176,24 @@ int clusten_stage_prepare(const int64_t *nearest /* [B,n,nnc] */, const int64_t 
                           int64_t *member_idx, int64_t *mask64, uint8_t *mask8, int32_t *pe_idx, int32_t *bias_idx,
                           int32_t *uniq, int uniq_cap, int32_t *count, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- WF plan (optional, 16-bit tensor-core kernels): per index tensor, built once and passed to clusten_wf_fwd / _bwd.
+ * Holds the token processing order (kept tokens arrive in top-k order, aff.py:320-324; neighbouring tokens re-use rows
+ * out of L1 when processed together) and, when M % 8 == 0, the per-octet reference lists that turn the d_f scatter of
+ * clustenwf_cuda_kernel.cu:120-131 into dense per-octet products.  Opaque device buffer of clusten_wf_plan_bytes bytes.
+ * When the plan's device-side flag routes d_f to the generic kernels, clusten_csr_build(..., pack = plan) builds the
+ * inverse list, and skips it otherwise (same flag position as the tile pack). */
+size_t clusten_wf_plan_bytes(int B, int Nq, int M, int Nk);
+int clusten_wf_plan_build(const int64_t *nbhd_idx, int B, int Nq, int M, int Nk, void *plan, size_t plan_bytes, void *stream);
+
 /* ---- WF: out[b,i,ic,c] = sum_j w[b,i,j,ic] * f[b,idx[b,i,j],c]             (clustenwf_cuda_kernel.cu:41-49)
  * w [B,Nq,M,IC] contiguous, f rows base + b*f_sb + n*f_sn + c, out [B,Nq,IC,C] contiguous.  IC in {1,2,4,8}. */
-int clusten_wf_fwd(const void *w, const void *f, const int64_t *nbhd_idx, void *out,
+int clusten_wf_fwd(const void *w, const void *f, const int64_t *nbhd_idx, const void *plan /* or NULL */, void *out,
                    int B, int Nq, int Nk, int C, int M, int IC, int64_t f_sb, int64_t f_sn, int dtype, void *stream);
 /* d_w[b,i,j,ic] = sum_c f[b,idx,c] d_out[b,i,ic,c];  d_f[b,r,:] = sum_{(i,j)->r} sum_ic w[b,i,j,ic] d_out[b,i,ic,:]
  *                                                                 (clustenwf_cuda_kernel.cu:120-131,161-165) */
 int clusten_wf_bwd(const void *d_out, const void *w, const void *f,
                    const int64_t *nbhd_idx, const int32_t *csr_offsets, const uint32_t *csr_entries,
-                   void *d_w, void *d_f,
+                   const void *plan /* or NULL */, void *d_w, void *d_f,
                    int B, int Nq, int Nk, int C, int M, int IC, int64_t f_sb, int64_t f_sn,
                    int64_t df_sb, int64_t df_sn, int dtype, void *stream);
 

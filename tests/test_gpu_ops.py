@@ -171,6 +171,60 @@ def test_wf_shapes(B, Nq, N, C, M, IC, dtype):
     _check(_run(P.CLUSTENWFFunction.apply, [c["w"], c["f"], c["idx"]], c["d_out"], dtype), ref, dtype, "WF")
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32], ids=["bf16", "f16", "f32"])
+@pytest.mark.parametrize("C", [32, 96, 128, 192, 48, 512])
+@pytest.mark.parametrize("n,m,nbhd,hw", [(4096, 8, 48, 64), (2003, 8, 48, 64), (655, 8, 48, 128), (1540, 24, 144, 64)])
+def test_wf_merge_structured(n, m, nbhd, hw, C, dtype):
+    """The PointConv merge as the backbone runs it (aff.py:332-361): neighbourhoods of the reference clustering,
+    gathered for a shuffled quarter of the tokens (top-k order).  16-bit types take the tensor-core kernels and the
+    WF plan (perm + per-octet lists); padded last clusters (n % m != 0) exercise the impure-slot fix-up."""
+    P = _ops()
+    from autofocusformermod_b200 import ops
+    B = 2
+    _, nb, _, _ = inputs.structured_neighbourhood(B, n, hw, hw, m, nbhd, seed=n)
+    g = torch.Generator().manual_seed(n + C)
+    Nq = n // 4
+    sel = torch.stack([torch.randperm(n, generator=g)[:Nq] for _ in range(B)])
+    if n % m:                                       # make sure tokens next to the padded cluster are kept
+        sel[:, :8] = torch.arange(n - 8, n)
+    idx = nb.gather(1, sel.unsqueeze(-1).expand(-1, -1, nb.shape[-1])).contiguous()
+    M = idx.shape[-1]
+    cast = lambda t: t.to(dtype).float()
+    w, f = cast(torch.randn(B, Nq, M, 4, generator=g)), cast(torch.randn(B, n, C, generator=g))
+    d_out = cast(torch.randn(B, Nq, 4, C, generator=g))
+    ref = co.fwd_bwd(co.wf_forward, [w, f, idx], d_out)
+    _check(_run(P.CLUSTENWFFunction.apply, [w, f, idx], d_out, dtype), ref, dtype, "WF merge")
+    flags = ops.wf_plan_flags(idx.cuda(), n)
+    assert flags[0] == 0, flags                      # octet path, not the generic one
+    assert (flags[1] > 0) == (n % m != 0), flags     # impure slots exactly when the last cluster is padded
+
+
+def test_wf_plan_routes_unstructured_idx_to_generic_path():
+    from autofocusformermod_b200 import ops
+    idx = inputs.random_neighbourhood(2, 300, 1000, 48, seed=1).cuda()
+    assert ops.wf_plan_flags(idx, 1000)[0] == 1
+    assert ops.wf_plan(torch.zeros(1, 4, 9, dtype=torch.int64, device="cuda"), 10) is None      # M % 8 != 0: no plan
+
+
+def test_wf_backward_is_deterministic():
+    P = _ops()
+    _, nb, _, _ = inputs.structured_neighbourhood(2, 2003, 64, 64, 8, 48, seed=5)
+    g = torch.Generator().manual_seed(0)
+    sel = torch.stack([torch.randperm(2003, generator=g)[:500] for _ in range(2)])
+    idx = nb.gather(1, sel.unsqueeze(-1).expand(-1, -1, 48)).contiguous().cuda()
+    w = torch.randn(2, 500, 48, 4, generator=g).cuda().bfloat16()
+    f = torch.randn(2, 2003, 96, generator=g).cuda().bfloat16()
+    go = torch.randn(2, 500, 4, 96, generator=g).cuda().bfloat16()
+    res = []
+    for _ in range(3):
+        idx_i = idx.clone()                          # fresh plan every time (the list order must not depend on atomics)
+        wi, fi = w.clone().requires_grad_(True), f.clone().requires_grad_(True)
+        P.CLUSTENWFFunction.apply(wi, fi, idx_i).backward(go)
+        res.append((wi.grad.clone(), fi.grad.clone()))
+    for a, b in res[1:]:
+        assert torch.equal(a, res[0][0]) and torch.equal(b, res[0][1])
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("B,Nq,N,C,K", [(3, 50, 100, 32, 4), (2, 1024, 256, 256, 4), (1, 300, 70, 100, 4), (1, 9, 5, 3, 2)])
 def test_weighted_gather_shapes(B, Nq, N, C, K, dtype):
@@ -442,7 +496,7 @@ def test_layer_norm(R, C, xdt, ydt):
     xr, wr, br = x.float().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
     ref = torch.nn.functional.layer_norm(xr, (C,), wr, br, 1e-5)
     ref.backward(dy.float())
-    xc, wc, bc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    xc, wc, bc = (t.detach().cuda().requires_grad_(True) for t in (x, w, b))
     y = ops.layer_norm(xc, wc, bc, 1e-5, ydt)
     assert y.dtype == ydt
     y.backward(dy.cuda())

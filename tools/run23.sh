@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_ops.py -m gpu -q -x -k "wf or weighted" > gpurun_out/pytest_wf.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_wf.log; tail -5 gpurun_out/pytest_wf.log
+for sh in small_s0 mini_s0 base_s0 small_s1; do timeout 300 python benchmarks/op_bench.py --shape $sh --dtype bf16 > gpurun_out/op_${sh}_bf16_v11.log 2>&1; tail -7 gpurun_out/op_${sh}_bf16_v11.log | grep wf; done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^fwd_tile_kernel" -o gpurun_out/r1_wf3_small_s0_bf16_v11 -f python benchmarks/op_bench.py --shape small_s0 --dtype bf16 --once > gpurun_out/ncu_wf3.log 2>&1
+echo "ncu wf3 exit $?"
