@@ -23,7 +23,7 @@ SIGNATURES = {
     "clusten_csr_workspace_bytes": (_Z, [_I] * 4),
     "clusten_csr_build": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _P, _P]),
     "clusten_pack_bytes": (_Z, [_I] * 4),
-    "clusten_pack_build": (_I, [_P, _I, _I, _I, _I, _P, _Z, _P]),
+    "clusten_pack_build": (_I, [_P, _P, _I, _I, _I, _I, _P, _Z, _P]),
     "clusten_pack_inverse": (_I, [_P, _Z, _I, _I, _I, _I, _P]),
     "clusten_qk_fwd": (_I, [_P] * 5 + [_I] * 6 + [_L] * 6 + [_I, _P]),
     "clusten_qk_bwd": (_I, [_P] * 9 + [_I] * 6 + [_L] * 12 + [_I, _P]),
@@ -37,7 +37,7 @@ SIGNATURES = {
     "clusten_prepare_workspace_bytes": (_Z, []),
     "clusten_stage_prepare": (_I, [_P] * 4 + [_I] * 5 + [_P] * 6 + [_I, _P, _P, _Z, _P]),
     "clusten_table_gather": (_I, [_P, _P, _I, _P, _L, _I, _I, _I, _P]),
-    "clusten_table_grad": (_I, [_P, _P, _I, _P, _L, _I, _I, _L, _L, _L, _L, _I, _P]),
+    "clusten_table_grad": (_I, [_P, _P, _I, _P, _L, _I, _P, _I, _L, _L, _L, _L, _I, _P]),
     "clusten_wf_plan_bytes": (_Z, [_I] * 4),
     "clusten_wf_plan_build": (_I, [_P, _I, _I, _I, _I, _P, _Z, _P]),
     "clusten_wf_fwd": (_I, [_P] * 5 + [_I] * 6 + [_L] * 2 + [_I, _P]),

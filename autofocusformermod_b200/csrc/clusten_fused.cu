@@ -258,7 +258,7 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
             }
         }
         constexpr int UB = F32 ? 2 : 4;
-        const int ylane = g * k_sn + cofs, k8 = 8 * k_sn;
+        const int klast = a.Nk - 1;                      // (mask-aware packs may hold the partial last octet: rows are clamped)
         for (int u0 = 0; u0 < U; u0 += UB) {
             FFrag<T, CH> y[UB];
             int sga[UB], sgb[UB];
@@ -272,7 +272,7 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
             }
 #pragma unroll
             for (int j = 0; j < UB; ++j) {
-                t2::ld_chunk<CH * (int)sizeof(T)>(y[j].r, t2::at(K, octet(u0 + j) * k8 + ylane));
+                t2::ld_chunk<CH * (int)sizeof(T)>(y[j].r, t2::at(K, min(octet(u0 + j) * 8 + g, klast) * k_sn + cofs));
                 sga[j] = t2::sbyte(sa4, j);
                 sgb[j] = t2::sbyte(sb4, j);
             }
@@ -360,7 +360,7 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
                 const int row = ch / NT, blk = ch % NT;
                 const int u = 2 * p + (row >> 3);
                 const bool ok = u < U && 8 * blk < C;
-                const T *src = t2::at(vbase, (octet(u) * 8 + (row & 7)) * v_sn + (ok ? 8 * blk : 0));
+                const T *src = t2::at(vbase, min(octet(u) * 8 + (row & 7), a.Nk - 1) * v_sn + (ok ? 8 * blk : 0));
                 f_cp16(stg + which * 16 * ROWB + row * ROWB + blk * 16, src, ok);
             }
             f_commit();
@@ -400,7 +400,7 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
                 const int ch = lane + 32 * j;
                 const int row = ch / (2 * NT), blk = ch % (2 * NT);
                 const bool ok = 4 * blk < C;
-                const T *src = t2::at(vbase, (o * 8 + row) * v_sn + (ok ? 4 * blk : 0));
+                const T *src = t2::at(vbase, min(o * 8 + row, a.Nk - 1) * v_sn + (ok ? 4 * blk : 0));
                 f_cp16(stf + which * 8 * RS + row * RS + blk * 4, src, ok);
             }
             f_commit();

@@ -203,8 +203,7 @@ attn_bwd_tile_kernel(const BwdArgs a, const PackView pk) {
     const int8_t *sb = sa + 8 * U_MAX;
     // ---- pass 1: S = q.K^T and DP = dO.V^T against every union octet, selected blocks -> shared memory ------------------------
     {
-        const int klane = g * a.k_sn + cofs, vlane = g * a.v_sn + cofs;
-        const int k8 = 8 * a.k_sn, v8 = 8 * a.v_sn;
+        const int klast = a.Nk - 1;                      // (mask-aware packs may hold the partial last octet: rows are clamped)
         float *Sa = S + g * MP + 2 * t, *Sb = S + (g + 8) * MP + 2 * t;
         float *Da_ = DP + g * MP + 2 * t, *Db_ = DP + (g + 8) * MP + 2 * t;
         for (int u0 = 0; u0 < U; u0 += 2) {
@@ -214,8 +213,9 @@ attn_bwd_tile_kernel(const BwdArgs a, const PackView pk) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int o = octet(u0 + j);
-                ld_chunk<CH * 2>(yk[j], at(Kb, o * k8 + klane));
-                ld_chunk<CH * 2>(yv[j], at(Vb, o * v8 + vlane));
+                const int kr = min(o * 8 + g, klast);
+                ld_chunk<CH * 2>(yk[j], at(Kb, kr * a.k_sn + cofs));
+                ld_chunk<CH * 2>(yv[j], at(Vb, kr * a.v_sn + cofs));
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -303,11 +303,10 @@ attn_bwd_tile_kernel(const BwdArgs a, const PackView pk) {
     {
         const int blk = lane % NT, prow = lane / NT;
         const bool act = 8 * blk < C;
-        const int src_lane = (prow & 7) * a.k_sn + 8 * blk;
         const uint32_t dst_lane = sK + prow * ROWB + blk * 16;
-        const int k8 = 8 * a.k_sn;
         auto stage = [&](int p, int which) {
-            const int o0 = octet(2 * p) * k8 + src_lane, o1 = octet(2 * p + 1) * k8 + src_lane;
+            const int o0 = min(octet(2 * p) * 8 + (prow & 7), a.Nk - 1) * a.k_sn + 8 * blk;
+            const int o1 = min(octet(2 * p + 1) * 8 + (prow & 7), a.Nk - 1) * a.k_sn + 8 * blk;
             if (act) {
                 if constexpr (RPP == 8) {
                     cp16(dst_lane + which * KSTG, at(Kb, o0));

@@ -67,13 +67,11 @@ fwd_kernel(const T *__restrict__ W, const T *__restrict__ F, const int64_t *__re
                 const int j0 = k0 + 2 * t, j1 = j0 + 1, j2 = j0 + 8, j3 = j0 + 9;
                 const int r0 = (int)__ldg(irow + min(j0, M - 1)) * f_sn + c0, r1 = (int)__ldg(irow + min(j1, M - 1)) * f_sn + c0;
                 const int r2 = (int)__ldg(irow + min(j2, M - 1)) * f_sn + c0, r3 = (int)__ldg(irow + min(j3, M - 1)) * f_sn + c0;
-                uint32_t b0 = 0u, b1 = 0u;
-                if (g < IC) {
-                    const uint32_t w0 = j0 < M ? ldu16(wrow + j0 * IC + g) : 0u, w1 = j1 < M ? ldu16(wrow + j1 * IC + g) : 0u;
-                    const uint32_t w2 = j2 < M ? ldu16(wrow + j2 * IC + g) : 0u, w3 = j3 < M ? ldu16(wrow + j3 * IC + g) : 0u;
-                    b0 = w0 | (w1 << 16);
-                    b1 = w2 | (w3 << 16);
-                }
+                // weights of ic = g; lanes g >= IC re-read the last ic: their accumulator columns are never stored
+                const int gi = min(g, IC - 1);
+                const uint32_t w0 = j0 < M ? ldu16(wrow + j0 * IC + gi) : 0u, w1 = j1 < M ? ldu16(wrow + j1 * IC + gi) : 0u;
+                const uint32_t w2 = j2 < M ? ldu16(wrow + j2 * IC + gi) : 0u, w3 = j3 < M ? ldu16(wrow + j3 * IC + gi) : 0u;
+                const uint32_t b0 = w0 | (w1 << 16), b1 = w2 | (w3 << 16);
                 Chunk<LW> x0[NB], x1[NB], x2[NB], x3[NB];
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) {
@@ -111,15 +109,13 @@ fwd_kernel(const T *__restrict__ W, const T *__restrict__ F, const int64_t *__re
 // d_w : D[j][ic] = sum_c F[idx_j][c] dO[ic][c]; lane loads LW = 16 (8) bytes = 8 (4) channels of rows g / g+8: one (half a)
 // 32-channel block = 2 (1) k-steps, the k index permuted identically for both operands.
 // ---------------------------------------------------------------------------------------------------------------------
-template <typename T, int LW>
+template <typename T, int LW, int MT>
 __global__ void __launch_bounds__(WPC * 32)
 dw_kernel(const T *__restrict__ dO, const T *__restrict__ F, const int64_t *__restrict__ idx, T *__restrict__ dW,
           const int *__restrict__ perm, int B, int Nq, int C, int M, int IC, int64_t f_sb, int f_sn, int tpw) {
     constexpr int KS = LW / 8, CB = 2 * LW, EPL = LW / 2;       // k-steps / channels per block / channels per lane
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int64_t total = (int64_t)B * Nq;
-    // the warps of a CTA take NEIGHBOURING tokens of the plan's order at the same time: rows they share are fetched from
-    // L2 once (L1 hit, or merged with the miss still in flight)
     const int64_t cta_first = (int64_t)blockIdx.x * WPC * tpw + warp;
     for (int it = 0; it < tpw; ++it) {
         const int64_t r = cta_first + (int64_t)it * WPC;
@@ -128,32 +124,45 @@ dw_kernel(const T *__restrict__ dO, const T *__restrict__ F, const int64_t *__re
         const int64_t tok = perm ? (int64_t)b * Nq + perm[r] : r;
         const int64_t *irow = idx + tok * M;
         const T *Fb = t2::opaque(F + b * f_sb + t * EPL);
-        const T *drow = dO + (tok * IC + min(g, IC - 1)) * C + t * EPL;
+        // B operand: d_out row of ic = g; lanes g >= IC re-read the last ic -- their accumulator columns are never stored
+        const T *drow = t2::opaque(dO + (tok * IC + min(g, IC - 1)) * C + t * EPL);
         T *wrow = dW + tok * M * IC;
-        for (int m0 = 0; m0 < M; m0 += 16) {
-            const int ja = m0 + g, jb = ja + 8;
-            const int ra = (int)__ldg(irow + min(ja, M - 1)) * f_sn, rb = (int)__ldg(irow + min(jb, M - 1)) * f_sn;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-            for (int c0 = 0; c0 < C; c0 += CB) {
-                Chunk<LW> xa, xb, d;
-                ld_bytes<LW>(xa, t2::at(Fb, ra + c0));
-                ld_bytes<LW>(xb, t2::at(Fb, rb + c0));
-                ld_bytes<LW>(d, drow + c0);
-                if (g >= IC) {
+        for (int m0 = 0; m0 < M; m0 += 16 * MT) {               // MT m-tiles of 16 neighbours at a time: 2*MT independent row loads
+            int ra[MT], rb[MT];
 #pragma unroll
-                    for (int w = 0; w < LW / 4; ++w) d.r[w] = 0u;
+            for (int x = 0; x < MT; ++x) {
+                ra[x] = (int)__ldg(irow + min(m0 + 16 * x + g, M - 1)) * f_sn;
+                rb[x] = (int)__ldg(irow + min(m0 + 16 * x + g + 8, M - 1)) * f_sn;
+            }
+            float acc[MT][4];
+#pragma unroll
+            for (int x = 0; x < MT; ++x) acc[x][0] = acc[x][1] = acc[x][2] = acc[x][3] = 0.f;
+#pragma unroll 2
+            for (int c0 = 0; c0 < C; c0 += CB) {
+                Chunk<LW> d, xa[MT], xb[MT];
+                ld_bytes<LW>(d, t2::at(drow, c0));
+#pragma unroll
+                for (int x = 0; x < MT; ++x) {
+                    ld_bytes<LW>(xa[x], t2::at(Fb, ra[x] + c0));
+                    ld_bytes<LW>(xb[x], t2::at(Fb, rb[x] + c0));
                 }
 #pragma unroll
-                for (int s = 0; s < KS; ++s) t2::mma16<T>(acc, xa.r[2 * s], xb.r[2 * s], xa.r[2 * s + 1], xb.r[2 * s + 1], d.r[2 * s], d.r[2 * s + 1]);
+                for (int x = 0; x < MT; ++x)
+#pragma unroll
+                    for (int s = 0; s < KS; ++s)
+                        t2::mma16<T>(acc[x], xa[x].r[2 * s], xb[x].r[2 * s], xa[x].r[2 * s + 1], xb[x].r[2 * s + 1], d.r[2 * s], d.r[2 * s + 1]);
             }
             if (2 * t < IC) {
-                if (IC >= 2) {
-                    if (ja < M) *reinterpret_cast<uint32_t *>(wrow + ja * IC + 2 * t) = t2::pack_pair<T>(acc[0], acc[1]);
-                    if (jb < M) *reinterpret_cast<uint32_t *>(wrow + jb * IC + 2 * t) = t2::pack_pair<T>(acc[2], acc[3]);
-                } else {
-                    if (ja < M) wrow[ja] = from_f<T>(acc[0]);
-                    if (jb < M) wrow[jb] = from_f<T>(acc[2]);
+#pragma unroll
+                for (int x = 0; x < MT; ++x) {
+                    const int ja = m0 + 16 * x + g, jb = ja + 8;
+                    if (IC >= 2) {
+                        if (ja < M) *reinterpret_cast<uint32_t *>(wrow + ja * IC + 2 * t) = t2::pack_pair<T>(acc[x][0], acc[x][1]);
+                        if (jb < M) *reinterpret_cast<uint32_t *>(wrow + jb * IC + 2 * t) = t2::pack_pair<T>(acc[x][2], acc[x][3]);
+                    } else {
+                        if (ja < M) wrow[ja] = from_f<T>(acc[x][0]);
+                        if (jb < M) wrow[jb] = from_f<T>(acc[x][2]);
+                    }
                 }
             }
         }
@@ -572,8 +581,13 @@ static int dw_t(const T *d_out, const T *f, const int64_t *idx, T *d_w, const vo
     const int64_t tokens = (int64_t)B * Nq;
     const int tpw = tokens_per_warp(tokens);
     const int grid = ceil_div(tokens, (int64_t)tpw * WPC);
-    if (LW_ == 16) dw_kernel<T, 16><<<grid, WPC * 32, 0, st>>>(d_out, f, idx, d_w, perm, B, Nq, C, M, IC, f_sb, (int)f_sn, tpw);
-    else dw_kernel<T, 8><<<grid, WPC * 32, 0, st>>>(d_out, f, idx, d_w, perm, B, Nq, C, M, IC, f_sb, (int)f_sn, tpw);
+    if (M <= 16) {
+        if (LW_ == 16) dw_kernel<T, 16, 1><<<grid, WPC * 32, 0, st>>>(d_out, f, idx, d_w, perm, B, Nq, C, M, IC, f_sb, (int)f_sn, tpw);
+        else dw_kernel<T, 8, 1><<<grid, WPC * 32, 0, st>>>(d_out, f, idx, d_w, perm, B, Nq, C, M, IC, f_sb, (int)f_sn, tpw);
+    } else {
+        if (LW_ == 16) dw_kernel<T, 16, 3><<<grid, WPC * 32, 0, st>>>(d_out, f, idx, d_w, perm, B, Nq, C, M, IC, f_sb, (int)f_sn, tpw);
+        else dw_kernel<T, 8, 3><<<grid, WPC * 32, 0, st>>>(d_out, f, idx, d_w, perm, B, Nq, C, M, IC, f_sb, (int)f_sn, tpw);
+    }
     note_launches(1);
     return 1;
 }

@@ -6,7 +6,7 @@ namespace clusten {
 constexpr int PACK_WARPS = 4;
 
 __global__ void __launch_bounds__(PACK_WARPS * 32)
-pack_tile_kernel(const int64_t *__restrict__ idx, int B, int Nq, int M, int Nk, PackView pk) {
+pack_tile_kernel(const int64_t *__restrict__ idx, const uint8_t *__restrict__ mask, int B, int Nq, int M, int Nk, PackView pk) {
     __shared__ int oct_rs[PACK_WARPS][TILE_TOK][S_MAX];
     __shared__ __align__(16) int8_t slot_s[PACK_WARPS][TILE_TOK][U_MAX];
     __shared__ int row_bad[PACK_WARPS][TILE_TOK];
@@ -23,16 +23,42 @@ pack_tile_kernel(const int64_t *__restrict__ idx, int B, int Nq, int M, int Nk, 
         int o = -2;
         if (i < Nq) {
             const int64_t *p = idx + ((int64_t)b * Nq + i) * M + 8 * s;
-            const int64_t base = p[0];
-            bool pure = base >= 0 && (base & 7) == 0 && base + 7 < (int64_t)Nk;
+            if (!mask) {
+                const int64_t base = p[0];
+                bool pure = base >= 0 && (base & 7) == 0 && base + 7 < (int64_t)Nk;
 #pragma unroll
-            for (int k = 1; k < 8; ++k) pure = pure && (p[k] == base + k);
-            o = pure ? (int)(base >> 3) : -1;
+                for (int k = 1; k < 8; ++k) pure = pure && (p[k] == base + k);
+                o = pure ? (int)(base >> 3) : -1;
+            } else {
+                // mask-aware (fused attention only): masked entries are wildcards -- their probability is exp(-100 - ...) = 0
+                // whatever key row they read -- so a padded cluster (point_utils.py:282-283) is a pure, possibly partial, octet
+                const uint8_t *mk = mask + ((int64_t)b * Nq + i) * M + 8 * s;
+                int64_t base = -1;
+                bool pure = true;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (!mk[k]) continue;
+                    if (base < 0) base = p[k] - k;
+                    pure = pure && p[k] == base + k && p[k] < (int64_t)Nk;
+                }
+                if (base < 0) o = -3;                        // fully masked slot: resolved below (continues the previous slot's run)
+                else {
+                    pure = pure && (base & 7) == 0 && base < (int64_t)Nk;
+                    o = pure ? (int)(base >> 3) : -1;
+                }
+            }
         }
         oct_rs[warp][r][s] = o;
     }
     for (int x = lane; x < TILE_TOK * U_MAX / 4; x += 32) reinterpret_cast<int *>(&slot_s[warp][0][0])[x] = -1;
     if (lane < TILE_TOK) row_bad[warp][lane] = 0;
+    __syncwarp();
+    if (mask && lane < TILE_TOK) {
+        // a fully masked slot (the all-padding octets of a padded cluster of m = 24) takes the octet after its predecessor's:
+        // a distinct id, possibly beyond the last real octet -- its rows are clamped by the kernels, its weights are ~ 0
+        for (int s2 = 0; s2 < S; ++s2)
+            if (oct_rs[warp][lane][s2] == -3) oct_rs[warp][lane][s2] = (s2 > 0 && oct_rs[warp][lane][s2 - 1] >= 0) ? oct_rs[warp][lane][s2 - 1] + 1 : -1;
+    }
     __syncwarp();
     for (int item = lane; item < TILE_TOK * S; item += 32)
         if (oct_rs[warp][item / S][item % S] == -1) row_bad[warp][item / S] = 1;      // benign race: all writers store 1
@@ -122,7 +148,7 @@ __global__ void pack_inv_keys_kernel(PackView pk, int B, uint32_t *__restrict__ 
     if (p >= (int64_t)B * per_b) return;
     const int64_t bt = p / U_MAX;
     const int u = (int)(p - bt * U_MAX);
-    keys[p] = u < pk.tile_u[bt] ? (uint32_t)pk.tile_oct[p] : (uint32_t)pk.NO;
+    keys[p] = u < pk.tile_u[bt] ? (uint32_t)min(pk.tile_oct[p], pk.NO) : (uint32_t)pk.NO;     // (octets past the last real one: no key rows)
 }
 
 __global__ void pack_inv_finalize_kernel(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
@@ -152,8 +178,8 @@ extern "C" size_t clusten_pack_bytes(int B, int Nq, int M, int Nk) {
     return pack_layout(B, Nq, Nk).total;
 }
 
-extern "C" int clusten_pack_build(const int64_t *nbhd_idx, int B, int Nq, int M, int Nk, void *pack, size_t pack_bytes,
-                                  void *stream) {
+extern "C" int clusten_pack_build(const int64_t *nbhd_idx, const uint8_t *mask, int B, int Nq, int M, int Nk, void *pack,
+                                  size_t pack_bytes, void *stream) {
     if (B < 0 || Nq < 0 || M <= 0 || Nk <= 0) return set_error(CLUSTEN_EINVAL, "bad sizes B=%d Nq=%d M=%d Nk=%d", B, Nq, M, Nk);
     if (!nbhd_idx || !pack) return set_error(CLUSTEN_EINVAL, "null pointer");
     if (pack_bytes < clusten_pack_bytes(B, Nq, M, Nk))
@@ -169,7 +195,7 @@ extern "C" int clusten_pack_build(const int64_t *nbhd_idx, int B, int Nq, int M,
     }
     const int bt = B * pk.T;
     cudaMemsetAsync(pk.row_imp, 0, (size_t)B * Nk, st);
-    pack_tile_kernel<<<ceil_div(bt, PACK_WARPS), PACK_WARPS * 32, 0, st>>>(nbhd_idx, B, Nq, M, Nk, pk);
+    pack_tile_kernel<<<ceil_div(bt, PACK_WARPS), PACK_WARPS * 32, 0, st>>>(nbhd_idx, mask, B, Nq, M, Nk, pk);
     pack_decide_kernel<<<1, 1, 0, st>>>(pk.flags, B * Nq);
     note_launches(2);
     return check_launch("pack_build");

@@ -11,31 +11,49 @@
 // Here every CTA accumulates its slice of e into a shared-memory copy of the table (fp32 shared atomics; lanes of a warp
 // hold consecutive neighbours of one token = distinct rows, so intra-warp conflicts are rare) and flushes the non-zero
 // entries with one global fp32 atomic each.  Large tables (U*CH floats > 48 KB) use global atomics directly.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace clusten {
 
-constexpr int TG_SMEM_FLOATS = 12 * 1024;
+constexpr int TG_SMEM_FLOATS = 50 * 1024;        // 200 KB of the 227 KB a CTA may use
 
+// blockIdx.y = channel split (channels [c_lo, c_lo + chs) of the table live in this CTA's shared memory).  U_dev (optional,
+// device scalar): the number of table rows actually referenced (<= U, the row count the host knows): only that many rows
+// are cleared and flushed, so callers may size the table by an upper bound without reading U back to the host.  A slice
+// that does not fit the shared-memory budget after all is accumulated with global atomics by the same CTA.
 template <typename T, typename I>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 table_grad_smem_kernel(const T *__restrict__ dout, const I *__restrict__ inv, float *__restrict__ dtab,
-                       int64_t n, int U, int CH, int64_t n_per, int64_t d_sb, int64_t d_se, int64_t d_sc, int64_t per_cta) {
+                       int64_t n, int U_host, const int *__restrict__ U_dev, int smem_floats, int CH, int chs, int64_t n_per,
+                       int64_t d_sb, int64_t d_se, int64_t d_sc, int64_t per_cta) {
     extern __shared__ float tab_s[];
-    const int tot = U * CH;
+    const int U = U_dev ? min(U_dev[0], U_host) : U_host;
+    const int c_lo = blockIdx.y * chs, cw = min(chs, CH - c_lo);
+    const int64_t e0 = (int64_t)blockIdx.x * per_cta, e1 = min(n, e0 + per_cta);
+    if ((int64_t)U * cw > smem_floats) {
+        for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            const int64_t r = (int64_t)inv[e];
+            const int64_t b = e / n_per;
+            const T *dp = dout + b * d_sb + (e - b * n_per) * d_se + c_lo * d_sc;
+            for (int c = 0; c < cw; ++c) atomicAdd(dtab + r * CH + c_lo + c, to_f(dp[c * d_sc]));
+        }
+        return;
+    }
+    const int tot = U * cw;
     for (int x = threadIdx.x; x < tot; x += blockDim.x) tab_s[x] = 0.f;
     __syncthreads();
-    const int64_t e0 = (int64_t)blockIdx.x * per_cta, e1 = min(n, e0 + per_cta);
     for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
         const int r = (int)inv[e];
         const int64_t b = e / n_per;
-        const T *dp = dout + b * d_sb + (e - b * n_per) * d_se;
-        for (int c = 0; c < CH; ++c) atomicAdd(tab_s + r * CH + c, to_f(dp[c * d_sc]));
+        const T *dp = dout + b * d_sb + (e - b * n_per) * d_se + c_lo * d_sc;
+        for (int c = 0; c < cw; ++c) atomicAdd(tab_s + r * cw + c, to_f(dp[c * d_sc]));
     }
     __syncthreads();
     for (int x = threadIdx.x; x < tot; x += blockDim.x) {
         const float v = tab_s[x];
-        if (v != 0.f) atomicAdd(dtab + x, v);
+        if (v != 0.f) { const int r = x / cw; atomicAdd(dtab + r * CH + c_lo + (x - r * cw), v); }
     }
 }
 
@@ -64,13 +82,32 @@ table_gather_kernel(const T *__restrict__ tab, const I *__restrict__ inv, T *__r
 }
 
 template <typename T, typename I>
-static int launch_table_grad(const T *dout, const I *inv, float *dtab, int64_t n, int U, int CH, int64_t n_per, int64_t d_sb,
-                             int64_t d_se, int64_t d_sc, cudaStream_t st) {
+static int launch_table_grad(const T *dout, const I *inv, float *dtab, int64_t n, int U, const int *U_dev, int CH, int64_t n_per,
+                             int64_t d_sb, int64_t d_se, int64_t d_sc, cudaStream_t st) {
     if (n == 0) return 0;
-    if ((int64_t)U * CH <= TG_SMEM_FLOATS) {
-        const int grid = (int)std::min<int64_t>(148 * 4, (n + 2047) / 2048);
+    // shared-memory accumulation of a channel slice of the table per CTA.  With a device-side row count the host only knows
+    // an upper bound of U: slices are sized for the tables AFF stages really produce (a few thousand rows) within a 48 KB
+    // budget (4 CTAs per SM); an oversized table falls back to global atomics inside the kernel.
+    const int64_t Ug = U_dev ? std::min<int64_t>(U, 6000) : U;
+    const int budget = U_dev ? 12 * 1024 : TG_SMEM_FLOATS;
+    int splits = 1;
+    while (splits < CH && Ug * ((CH + splits - 1) / splits) > budget) ++splits;
+    const int chs = (CH + splits - 1) / splits;
+    const int smem_floats = (int)std::min<int64_t>((int64_t)U * chs, budget);
+    if (Ug * chs <= budget) {
+        const size_t smem = (size_t)smem_floats * sizeof(float);
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / (smem + 1024)));
+        int64_t grid = std::min<int64_t>((int64_t)148 * per_sm, std::max<int64_t>(1, n / ((int64_t)4 * std::max<int64_t>(Ug, 64))));
+        grid = std::min<int64_t>(grid, (n + 2047) / 2048);
+        grid = std::max<int64_t>(grid, 1);
         const int64_t per_cta = (n + grid - 1) / grid;
-        table_grad_smem_kernel<T, I><<<grid, 256, (size_t)U * CH * sizeof(float), st>>>(dout, inv, dtab, n, U, CH, n_per, d_sb, d_se, d_sc, per_cta);
+        static bool attr = false;                        // (one flag per (T, I): this function is a template)
+        if (!attr) {
+            cudaFuncSetAttribute(table_grad_smem_kernel<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_FLOATS * 4);
+            attr = true;
+        }
+        table_grad_smem_kernel<T, I><<<dim3((unsigned)grid, splits), 512, smem, st>>>(dout, inv, dtab, n, U, U_dev, smem_floats, CH, chs, n_per,
+                                                                                     d_sb, d_se, d_sc, per_cta);
     } else {
         const int grid = (int)std::min<int64_t>(148 * 8, (n + 255) / 256);
         table_grad_global_kernel<T, I><<<grid, 256, 0, st>>>(dout, inv, dtab, n, CH, n_per, d_sb, d_se, d_sc);
@@ -98,14 +135,15 @@ extern "C" int clusten_table_gather(const void *tab, const void *inv, int inv_is
     return check_launch("table_gather");
 }
 
-extern "C" int clusten_table_grad(const void *d_out, const void *inv, int inv_is_i64, float *d_tab, int64_t n, int U, int CH,
-                                  int64_t n_per, int64_t d_sb, int64_t d_se, int64_t d_sc, int dtype, void *stream) {
+extern "C" int clusten_table_grad(const void *d_out, const void *inv, int inv_is_i64, float *d_tab, int64_t n, int U,
+                                  const int32_t *U_dev, int CH, int64_t n_per, int64_t d_sb, int64_t d_se, int64_t d_sc, int dtype,
+                                  void *stream) {
     if (n < 0 || U <= 0 || CH <= 0 || n_per <= 0) return set_error(CLUSTEN_EINVAL, "bad sizes n=%lld U=%d CH=%d", (long long)n, U, CH);
     if (!d_out || !inv || !d_tab) return set_error(CLUSTEN_EINVAL, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     CLUSTEN_DISPATCH_DTYPE(dtype, {
-        if (inv_is_i64) return launch_table_grad<T, int64_t>((const T *)d_out, (const int64_t *)inv, d_tab, n, U, CH, n_per, d_sb, d_se, d_sc, st);
-        return launch_table_grad<T, int32_t>((const T *)d_out, (const int32_t *)inv, d_tab, n, U, CH, n_per, d_sb, d_se, d_sc, st);
+        if (inv_is_i64) return launch_table_grad<T, int64_t>((const T *)d_out, (const int64_t *)inv, d_tab, n, U, U_dev, CH, n_per, d_sb, d_se, d_sc, st);
+        return launch_table_grad<T, int32_t>((const T *)d_out, (const int32_t *)inv, d_tab, n, U, U_dev, CH, n_per, d_sb, d_se, d_sc, st);
     });
     return 0;
 }

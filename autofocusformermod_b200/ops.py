@@ -99,15 +99,15 @@ def _check_shapes(cond, msg):
         raise RuntimeError(msg)
 
 
-def inverse_neighbour_list(nbhd_idx, Nk, with_pack=False, wf_plan_buf=None):
+def inverse_neighbour_list(nbhd_idx, Nk, with_pack=False, wf_plan_buf=None, pack_buf=None):
     """(offsets int32 [B,Nk+1], entries uint32-as-int32 [B,Nq*M]) of clusten_csr_build, cached on the index tensor.
     ``with_pack`` (QK / AV backward only): the list is built beside the tile pack and SKIPPED on the device when the
     pack routes the call to the tile-union kernels, which do not need it.  ``wf_plan_buf`` (WF backward): same, keyed
     on the WF plan's device-side flag."""
     cache = getattr(nbhd_idx, "_clusten_csr", None)
     ver = nbhd_idx._version
-    pack = neighbourhood_pack(nbhd_idx, Nk) if with_pack else wf_plan_buf
-    kind = "pack" if with_pack and pack is not None else "wf" if pack is not None else None
+    pack = pack_buf if pack_buf is not None else neighbourhood_pack(nbhd_idx, Nk) if with_pack else wf_plan_buf
+    kind = ("mpack" if pack_buf is not None else "pack" if with_pack and pack is not None else "wf" if pack is not None else None)
     # (a list built beside a pack / plan may have been skipped on the device: only reuse it for the same kind of call;
     # an unconditional list serves everyone)
     if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr() and cache[5] in (None, kind):
@@ -132,29 +132,32 @@ def inverse_neighbour_list(nbhd_idx, Nk, with_pack=False, wf_plan_buf=None):
 USE_TILE_KERNELS = True      # False: always the generic row-gather kernels (pack == NULL)
 
 
-def neighbourhood_pack(nbhd_idx, Nk, inverse=False):
+def neighbourhood_pack(nbhd_idx, Nk, inverse=False, mask=None):
     """Opaque tile pack of clusten_pack_build for this index tensor (uint8 device buffer), cached on the tensor; None
     when the tile-union kernels are switched off.  The pack decides ON THE DEVICE whether the tensor-core kernels or the
-    generic ones run (no host sync); see ``pack_flags``."""
+    generic ones run (no host sync); see ``pack_flags``.  ``mask`` (uint8 [B,Nq,M]; fused attention only): a mask-aware
+    pack, cached separately -- masked neighbour slots are wildcards, so padded clusters stay on the tensor-core path."""
     if not USE_TILE_KERNELS:
         return None
-    cache = getattr(nbhd_idx, "_clusten_pack", None)
+    attr = "_clusten_pack" if mask is None else "_clusten_pack_masked"
+    cache = getattr(nbhd_idx, attr, None)
     ver = nbhd_idx._version
     B, Nq, M = nbhd_idx.shape
     dev = nbhd_idx.device
-    if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr():
+    mkey = None if mask is None else (mask.data_ptr(), mask._version)
+    if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr() and cache[5] == mkey:
         pack, has_inv = cache[3], cache[4]
     else:
         nbytes = _lib.lib().clusten_pack_bytes(B, Nq, M, Nk)
         pack, has_inv = torch.empty(nbytes, dtype=torch.uint8, device=dev), False
         with torch.cuda.device(dev):
-            _call("clusten_pack_build", dev, nbhd_idx.data_ptr(), B, Nq, M, Nk, pack.data_ptr(), nbytes)
+            _call("clusten_pack_build", dev, nbhd_idx.data_ptr(), _lib.ptr(mask), B, Nq, M, Nk, pack.data_ptr(), nbytes)
     if inverse and not has_inv:                  # the inverse lists are only needed by backward: built on first use
         with torch.cuda.device(dev):
             _call("clusten_pack_inverse", dev, pack.data_ptr(), pack.numel(), B, Nq, M, Nk)
         has_inv = True
     try:
-        nbhd_idx._clusten_pack = (ver, Nk, nbhd_idx.data_ptr(), pack, has_inv)
+        setattr(nbhd_idx, attr, (ver, Nk, nbhd_idx.data_ptr(), pack, has_inv, mkey))
     except Exception:  # pragma: no cover
         pass
     return pack
@@ -193,9 +196,9 @@ def wf_plan_flags(nbhd_idx, Nk):
     return tuple(int(x) for x in plan[:12].view(torch.int32).tolist())
 
 
-def pack_flags(nbhd_idx, Nk):
+def pack_flags(nbhd_idx, Nk, mask=None):
     """(generic_path, max_union, impure_slots, tiles_over_limit) of the pack -- synchronises; for tests / diagnostics."""
-    pack = neighbourhood_pack(nbhd_idx, Nk)
+    pack = neighbourhood_pack(nbhd_idx, Nk, mask=mask)
     if pack is None:
         return (1, 0, 0, 0)
     return tuple(int(x) for x in pack[:16].view(torch.int32).tolist())
@@ -331,7 +334,7 @@ def cluster_attention_fused(q, key, v, nbhd_idx, bias_tab, bias_idx, mask, blank
     if out.numel():
         with torch.cuda.device(dev):
             _call("clusten_attn_fwd", dev, q.data_ptr(), key.data_ptr(), v.data_ptr(), nbhd_idx.data_ptr(),
-                  _lib.ptr(neighbourhood_pack(nbhd_idx, Nk)), bias_tab.data_ptr(), bias_idx.data_ptr(), _lib.ptr(mask),
+                  _lib.ptr(neighbourhood_pack(nbhd_idx, Nk, mask=mask)), bias_tab.data_ptr(), bias_idx.data_ptr(), _lib.ptr(mask),
                   blank_k.data_ptr(), blank_v.data_ptr(), out.data_ptr(), _lib.ptr(probs), 0, B, H, Nq, Nk, C, M,
                   *_s3(q), *_s3(key), *_s3(v), *_s3(ov), _lib.dtype_code(q),
                   nbytes=q.element_size() * (B * H * (2 * Nq + 2 * Nk) * C) + 4 * B * Nq * M + 8 * B * Nq * M)
@@ -351,8 +354,9 @@ class ClusterAttentionCoreFunction(Function):
     [B,H,N,M+1] fp32 tensors autograd keeps for the reference's glue passes never exist."""
 
     @staticmethod
-    def forward(ctx, q, kv, bias_tab, blank_k, blank_v, nbhd_idx, bias_idx, mask):
+    def forward(ctx, q, kv, bias_tab, blank_k, blank_v, nbhd_idx, bias_idx, mask, count=None):
         dev = _lib.require_cuda(q, kv, bias_tab, blank_k, blank_v, nbhd_idx, bias_idx, mask)
+        ctx.count = count                  # device int32 scalar: bias-table rows actually referenced (see table_lookup)
         _check_shapes(q.dim() == 4 and kv.dim() == 5 and kv.shape[3] == 2 and q.dtype == kv.dtype and
                       q.dtype in (torch.float16, torch.bfloat16), "fused attention: q [B,N,H,C], kv [B,N,H,2,C], fp16/bf16")
         B, N, H, C = q.shape
@@ -371,7 +375,7 @@ class ClusterAttentionCoreFunction(Function):
         if out.numel():
             with torch.cuda.device(dev):
                 _call("clusten_attn_fwd", dev, qv.data_ptr(), kk.data_ptr(), vv.data_ptr(), nbhd_idx.data_ptr(),
-                      _lib.ptr(neighbourhood_pack(nbhd_idx, N)), tab.data_ptr(), bias_idx.data_ptr(), _lib.ptr(mask),
+                      _lib.ptr(neighbourhood_pack(nbhd_idx, N, mask=mask)), tab.data_ptr(), bias_idx.data_ptr(), _lib.ptr(mask),
                       bk.data_ptr(), bv.data_ptr(), out.data_ptr(), 0, lse.data_ptr(), B, H, N, N, C, M,
                       *_s3(qv), *_s3(kk), *_s3(vv), *_s3(ov), _lib.dtype_code(q),
                       nbytes=q.element_size() * (B * H * 4 * N * C) + 4 * B * N * M + 8 * B * N * M)
@@ -398,8 +402,8 @@ class ClusterAttentionCoreFunction(Function):
             hv = lambda t: t.permute(0, 2, 1, 3)
             qv, kk, vv, ov, gv, dqv = hv(q), hv(kv[:, :, :, 0]), hv(kv[:, :, :, 1]), hv(out), hv(d_out), hv(d_q)
             dkv, dvv = hv(d_kv[:, :, :, 0]), hv(d_kv[:, :, :, 1])
-            off, ent = inverse_neighbour_list(nbhd_idx, N, with_pack=True)
-            pack = neighbourhood_pack(nbhd_idx, N, inverse=True)
+            pack = neighbourhood_pack(nbhd_idx, N, inverse=True, mask=mask)
+            off, ent = inverse_neighbour_list(nbhd_idx, N, with_pack=True, pack_buf=pack if mask is not None else None)
             code = _lib.dtype_code(q)
             es = q.element_size()
             with torch.cuda.device(dev):
@@ -414,17 +418,18 @@ class ClusterAttentionCoreFunction(Function):
                 _call("clusten_scatter_rows", dev, P.data_ptr(), gv.data_ptr(), off.data_ptr(), ent.data_ptr(), _lib.ptr(pack),
                       dvv.data_ptr(), B, H, N, N, C, M, *_s3(P), *_s3(gv), *_s3(dvv), code,
                       nbytes=es * (B * H * N * M + 2 * B * H * N * C) + 8 * B * N * M)
-                _call("clusten_table_grad", dev, dS.data_ptr(), bias_idx.data_ptr(), 0, d_tab.data_ptr(), B * N * M, tab.shape[0], H,
+                _call("clusten_table_grad", dev, dS.data_ptr(), bias_idx.data_ptr(), 0, d_tab.data_ptr(), B * N * M, tab.shape[0],
+                      _lib.ptr(ctx.count), H,
                       N * M, H * N * M, 1, N * M, code, nbytes=es * B * H * N * M + 4 * B * N * M)
         # blank-token parameters: tiny [H,C] reductions over all tokens (cuBLAS batched GEMV-like, fp32 accumulation)
         d_bk = torch.einsum("bhn,bnhc->hc", dSb.to(dt), q).reshape(-1)
         d_bv = torch.einsum("bhn,bnhc->hc", Pb.to(dt), d_out).reshape(-1)
         tdt, kdt, vdt = ctx.meta
-        return d_q, d_kv, d_tab.to(tdt), d_bk.to(kdt), d_bv.to(vdt), None, None, None
+        return d_q, d_kv, d_tab.to(tdt), d_bk.to(kdt), d_bv.to(vdt), None, None, None, None
 
 
-def cluster_attention_core(q, kv, bias_tab, blank_k, blank_v, nbhd_idx, bias_idx, mask):
-    return ClusterAttentionCoreFunction.apply(q, kv, bias_tab, blank_k, blank_v, nbhd_idx, bias_idx, mask)
+def cluster_attention_core(q, kv, bias_tab, blank_k, blank_v, nbhd_idx, bias_idx, mask, count=None):
+    return ClusterAttentionCoreFunction.apply(q, kv, bias_tab, blank_k, blank_v, nbhd_idx, bias_idx, mask, count)
 
 
 # ---- LayerNorm -------------------------------------------------------------------------------------------------------
@@ -485,7 +490,7 @@ class TableLookupFunction(Function):
     shared-memory-privatised fp32 segment sum (clusten_table_grad); its summation order is not fixed (fp32 atomics)."""
 
     @staticmethod
-    def forward(ctx, tab, inverse):
+    def forward(ctx, tab, inverse, count=None):
         dev = _lib.require_cuda(tab, inverse)
         _check_shapes(tab.dim() == 2 and inverse.dtype in (torch.int64, torch.int32), "table lookup: tab [U,CH], inverse int32/int64")
         tab = tab.contiguous()
@@ -498,6 +503,7 @@ class TableLookupFunction(Function):
                 _call("clusten_table_gather", dev, tab.data_ptr(), inverse.data_ptr(), int(inverse.dtype == torch.int64),
                       out.data_ptr(), n, U, CH, _lib.dtype_code(tab))
         ctx.save_for_backward(inverse)
+        ctx.count = count                  # device int32 scalar: rows actually referenced (tab may be sized by an upper bound)
         ctx.tab_shape, ctx.tab_dtype = (U, CH), tab.dtype
         return out
 
@@ -517,12 +523,12 @@ class TableLookupFunction(Function):
                 g = g.contiguous()
             with torch.cuda.device(dev):
                 _call("clusten_table_grad", dev, g.data_ptr(), inverse.data_ptr(), int(inverse.dtype == torch.int64),
-                      d_tab.data_ptr(), n, U, CH, g.shape[1], g.stride(0), g.stride(1), g.stride(2), _lib.dtype_code(g))
-        return d_tab.to(ctx.tab_dtype), None
+                      d_tab.data_ptr(), n, U, _lib.ptr(ctx.count), CH, g.shape[1], g.stride(0), g.stride(1), g.stride(2), _lib.dtype_code(g))
+        return d_tab.to(ctx.tab_dtype), None, None
 
 
-def table_lookup(tab, inverse):
-    return TableLookupFunction.apply(tab, inverse)
+def table_lookup(tab, inverse, count=None):
+    return TableLookupFunction.apply(tab, inverse, count)
 
 
 # ---- WF --------------------------------------------------------------------------------------------------------------

@@ -80,11 +80,13 @@ def space_filling_cluster(pos, m, h, w, no_reorder=False, sf_type='', use_anchor
 PE_TABLE_WIDTH = 1023                                  # aff.py:17-19 (2 * (2048 // 4 - 1) + 1)
 
 
-def stage_prepare(pos, nearest, member, cluster_mask, want_mask64=True):
+def stage_prepare(pos, nearest, member, cluster_mask, want_mask64=True, extent=None):
     """Neighbourhood assembly of one AFF stage (aff.py:475-485) in one pass: returns
     (member_idx int64 [B,n,M], mask int64 [B,n,M] or None, mask_u8 uint8 [B,n,M] or None, uniq int64 [U], bias_idx int32
     [B,n,M]) with uniq = the ascending distinct relative-position table rows ``pe_idx`` takes and bias_idx its inverse map
-    (``torch.unique(pe_idx, return_inverse=True)`` without the sort).  One host read (U)."""
+    (``torch.unique(pe_idx, return_inverse=True)`` without the sort).  One host read (U) -- unless ``extent = (h, w)`` of
+    the stem grid the positions live on is given: then uniq is returned at its upper bound (2h-1)(2w-1) rows (the tail
+    repeats table row 0) together with the device-side count as a sixth result, and nothing is read back."""
     dev = _lib.require_cuda(pos, nearest, member, cluster_mask)
     p = _f32c(pos)
     nearest, member = nearest.contiguous(), member.contiguous()
@@ -98,7 +100,9 @@ def stage_prepare(pos, nearest, member, cluster_mask, want_mask64=True):
     pe = torch.empty((B, n, M), dtype=torch.int32, device=dev)
     bias_idx = torch.empty((B, n, M), dtype=torch.int32, device=dev)
     cap = max(1, min(PE_TABLE_WIDTH * PE_TABLE_WIDTH, B * n * M))
-    uniq = torch.empty(cap, dtype=torch.int32, device=dev)
+    if extent is not None:                         # |dx| <= w-1, |dy| <= h-1 (clamped to the table): at most that many distinct rows
+        cap = min(cap, min(2 * int(extent[1]) - 1, PE_TABLE_WIDTH) * min(2 * int(extent[0]) - 1, PE_TABLE_WIDTH))
+    uniq = (torch.zeros if extent is not None else torch.empty)(cap, dtype=torch.int32, device=dev)
     count = torch.empty(1, dtype=torch.int32, device=dev)
     L = _lib.lib()
     ws_bytes = L.clusten_prepare_workspace_bytes()
@@ -107,6 +111,8 @@ def stage_prepare(pos, nearest, member, cluster_mask, want_mask64=True):
         _call("clusten_stage_prepare", dev, nearest.data_ptr(), member.data_ptr(), _lib.ptr(cm), p.data_ptr(), B, n, k, m, nnc,
               member_idx.data_ptr(), _lib.ptr(mask64), _lib.ptr(mask8), pe.data_ptr(), bias_idx.data_ptr(), uniq.data_ptr(), cap,
               count.data_ptr(), ws.data_ptr(), ws_bytes)
+    if extent is not None:
+        return member_idx, mask64, mask8, uniq.long(), bias_idx, count
     U = int(count.item())
     return member_idx, mask64, mask8, uniq[:U].long(), bias_idx
 

@@ -139,7 +139,7 @@ def main():
                                               *s3(d_feat), *s3(attn), *s3(v), *s3(d_v), code, st())), 3 * BHNC + 2 * BHNM + BNM8)
     pb = L.clusten_pack_bytes(B, N, M, N)
     pbuf = torch.empty(pb, dtype=torch.uint8, device="cuda")
-    run("pack_build", lambda: ck(L.clusten_pack_build(idx.data_ptr(), B, N, M, N, pbuf.data_ptr(), pb, st())), BNM8)
+    run("pack_build", lambda: ck(L.clusten_pack_build(idx.data_ptr(), 0, B, N, M, N, pbuf.data_ptr(), pb, st())), BNM8)
     run("pack_inverse", lambda: ck(L.clusten_pack_inverse(pbuf.data_ptr(), pb, B, N, M, N, st())), BNM8)
     ws_b = L.clusten_csr_workspace_bytes(B, N, M, N)
     ws = torch.empty(ws_b, dtype=torch.uint8, device="cuda")

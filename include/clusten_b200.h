@@ -70,7 +70,12 @@ int clusten_csr_build(const int64_t *nbhd_idx, int B, int Nq, int M, int Nk,
  * pack == NULL selects the generic row-gather kernels.  The pack carries a device-side flag: index tensors without
  * octet structure (M % 8 != 0, impure runs, too little locality) fall back to the generic kernels with no host sync. */
 size_t clusten_pack_bytes(int B, int Nq, int M, int Nk);
-int clusten_pack_build(const int64_t *nbhd_idx, int B, int Nq, int M, int Nk, void *pack, size_t pack_bytes, void *stream);
+/* mask (uint8 [B,Nq,M], 0 = padded neighbour slot, aff.py:480; or NULL): ONLY for packs handed to the fused attention entry
+ * points (clusten_attn_fwd / _bwd and the clusten_scatter_rows calls behind them), which apply the same mask: masked entries
+ * become wildcards, so the padded last cluster of point_utils.py:282-283 stays on the tensor-core path.  Packs for
+ * clusten_qk_* / clusten_av_* must be built with mask == NULL (those ops honour every index literally). */
+int clusten_pack_build(const int64_t *nbhd_idx, const uint8_t *mask, int B, int Nq, int M, int Nk, void *pack, size_t pack_bytes,
+                       void *stream);
 /* inverse lists (key octet -> referencing tiles) of an already built pack: needed by the backward entry points only */
 int clusten_pack_inverse(void *pack, size_t pack_bytes, int B, int Nq, int M, int Nk, void *stream);
 
@@ -151,8 +156,10 @@ int clusten_scatter_rows(const void *w, const void *x, const int32_t *csr_offset
  *   Replaces ATen index / index_put_(accumulate) on this path; the gradient uses fp32 atomics (summation order is not fixed). */
 int clusten_table_gather(const void *tab, const void *inv, int inv_is_i64, void *out, int64_t n, int U, int CH,
                          int dtype, void *stream);
-int clusten_table_grad(const void *d_out, const void *inv, int inv_is_i64, float *d_tab, int64_t n, int U, int CH,
-                       int64_t n_per, int64_t d_sb, int64_t d_se, int64_t d_sc, int dtype, void *stream);
+/* U_dev (device int32 scalar or NULL): number of table rows actually referenced when U is only an upper bound (the count
+ * clusten_stage_prepare leaves on the device) -- lets the caller skip the device->host read of U. */
+int clusten_table_grad(const void *d_out, const void *inv, int inv_is_i64, float *d_tab, int64_t n, int U, const int32_t *U_dev,
+                       int CH, int64_t n_per, int64_t d_sb, int64_t d_se, int64_t d_sc, int dtype, void *stream);
 
 /* ---- LayerNorm over the channel dimension of [R, C] token rows, C <= 1024 (aff.py:196-199,258,617-620): one warp per row.
  * x / y (and d_y) may be fp32 / fp16 / bf16 independently; gamma, beta, mean, rstd, d_gamma, d_beta are fp32.  mean / rstd may

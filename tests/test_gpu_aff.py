@@ -109,3 +109,25 @@ def test_fused_inference_path_matches_unfused_ops():
     for i in range(2, 6):
         assert torch.equal(fused[f"res{i}_pos"], plain[f"res{i}_pos"])
         assert rel_err(fused[f"res{i}"], plain[f"res{i}"]) <= 2e-5, f"res{i}"
+
+
+def test_graphed_forward_equals_eager():
+    """AFF.graphed: the CUDA-graph replay of the inference forward returns exactly what the eager forward returns, for
+    several different batches through the same graph (no host synchronisation inside the forward)."""
+    import torch
+    from autofocusformermod_b200.aff import build_aff
+    torch.manual_seed(0)
+    model = build_aff("test").cuda().eval()
+    g = torch.Generator().manual_seed(1)
+    # 256x256: 64 tokens in the last stage (> nbhd_size): no global-attention stage, whose torch.unique cannot be captured
+    xs = [torch.randn(2, 3, 256, 256, generator=g).cuda() for _ in range(3)]
+    graphed = model.graphed(xs[0])
+    assert graphed.launches_per_replay > 0
+    for x in xs:
+        with torch.no_grad():
+            ref = model(x)
+        out = graphed(x)
+        torch.cuda.synchronize()
+        for k, v in ref.items():
+            if torch.is_tensor(v):
+                assert torch.equal(out[k], v), k

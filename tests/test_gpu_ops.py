@@ -413,6 +413,17 @@ def test_fused_attention_core(n, m, nbhd, kind, H, C, dtype):
         assert ops.pack_flags(idx.cuda(), n)[0] == 0
 
 
+@pytest.mark.parametrize("n,m,nbhd", [(2003, 8, 48), (655, 8, 48), (131, 8, 48), (1540, 24, 144)])
+def test_mask_aware_pack_keeps_padded_clusters_on_the_tile_path(n, m, nbhd):
+    """Padded last cluster (point_utils.py:282-283): impure tokens for the literal pack (QK / AV ops), none for the mask-aware
+    pack of the fused attention path, which treats masked slots as wildcards."""
+    from autofocusformermod_b200 import ops
+    _, idx, mask, _ = inputs.structured_neighbourhood(2, n, 64, 64, m, nbhd, seed=n)
+    idx, mask8 = idx.cuda(), mask.to(torch.uint8).cuda()
+    plain, masked = ops.pack_flags(idx, n), ops.pack_flags(idx, n, mask=mask8)
+    assert plain[2] > 0 and masked[2] == 0 and masked[0] == 0, (plain, masked)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("U,CH,shape,permuted", [(700, 3, (2, 500, 48), True), (700, 3, (2, 500, 48), False), (5000, 16, (1, 300, 48), True),
                                                  (37, 4, (3, 200, 48), False), (1, 2, (1, 5, 8), False)])
@@ -438,6 +449,13 @@ def test_table_lookup(U, CH, shape, permuted, dtype):
         out.backward(go)
         torch.cuda.synchronize()
         assert rel_err(t.grad.float().cpu(), t_ref.grad) <= TOL[dtype]
+        # table sized by an upper bound, the referenced row count known only on the device
+        t2 = torch.cat([tab, torch.zeros(3 * U + 5, CH, dtype=dtype)]).cuda().detach().requires_grad_(True)
+        cnt = torch.tensor([U], dtype=torch.int32, device="cuda")
+        out2 = ops.table_lookup(t2, inv.cuda().to(idt), cnt)
+        assert torch.equal(out2.detach(), out.detach())
+        out2.backward(go)
+        assert rel_err(t2.grad[:U].float().cpu(), t_ref.grad) <= TOL[dtype] and float(t2.grad[U:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
@@ -536,3 +554,8 @@ def test_stage_prepare_matches_torch_formulation(n, m, nbhd, hw):
         assert torch.equal(mask64, ref_mask) and torch.equal(mask8.long(), ref_mask)
     assert torch.equal(uniq, ref_uniq)
     assert torch.equal(bias_idx.reshape(-1).long(), ref_inv)
+    # no-host-read variant: uniq at its upper bound (2h-1)(2w-1), the count stays on the device
+    r2 = pu.stage_prepare(pos, nearest, member, cmask, extent=(hw, hw))
+    U = int(r2[5].item())
+    assert U == ref_uniq.numel() and r2[3].numel() == min((2 * hw - 1) ** 2, B * n * nnc * m) >= U
+    assert torch.equal(r2[3][:U], ref_uniq) and bool((r2[3][U:] == 0).all()) and torch.equal(r2[4], bias_idx)
