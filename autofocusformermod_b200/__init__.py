@@ -4,10 +4,10 @@ Drop-in for ``mask2former.modeling.clusten`` (the four autograd Functions) and f
 calls.  All compute goes through libclusten_b200.so (C ABI, include/clusten_b200.h); there is no CPU fallback.
 """
 from .ops import (CLUSTENQKFunction, CLUSTENAVFunction, CLUSTENWFFunction, WEIGHTEDGATHERFunction,  # noqa: F401
-                  inverse_neighbour_list)
+                  MSDETRPCFunction, inverse_neighbour_list)
 from .point_utils import (knn_keops, space_filling_cluster, shepard_decay_weights, upsample_feature_shepard,  # noqa: F401
                           topk_select, mask_select, merge_select)
 
-__all__ = ["CLUSTENQKFunction", "CLUSTENAVFunction", "CLUSTENWFFunction", "WEIGHTEDGATHERFunction",
+__all__ = ["CLUSTENQKFunction", "CLUSTENAVFunction", "CLUSTENWFFunction", "WEIGHTEDGATHERFunction", "MSDETRPCFunction",
            "knn_keops", "space_filling_cluster", "shepard_decay_weights", "upsample_feature_shepard",
            "topk_select", "mask_select", "merge_select", "inverse_neighbour_list"]

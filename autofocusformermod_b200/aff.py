@@ -465,6 +465,50 @@ class GraphedAFF:
         with torch.no_grad(), torch.autocast("cuda", dtype=self.autocast_dtype or torch.bfloat16, enabled=self.autocast_dtype is not None):
             return self.model(self.static_in)
 
+    def stream(self, batches, sinks):
+        """Serving loop with the copies taken off the critical path: ``batches`` = iterable of pinned host inputs,
+        ``sinks`` = two dicts of pinned host buffers (one per output tensor) filled alternately.  The host->device copy of
+        batch i+1 and the device->host copy of result i-1 run on their own streams while the graph replays batch i
+        (double-buffered staging on the device; PCIe is full duplex).  Yields (i, sink) once result i is on the host."""
+        dev = self.static_in.device
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_pipe"):
+            keys = [k for k, v in self.static_out.items() if torch.is_tensor(v)]
+            self._pipe = dict(h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev), keys=keys,
+                              xin=[torch.empty_like(self.static_in) for _ in range(2)],
+                              out=[{k: torch.empty_like(self.static_out[k]) for k in keys} for _ in range(2)],
+                              ev=[[torch.cuda.Event() for _ in range(4)] for _ in range(2)])
+        P = self._pipe
+        last = -1
+        for i, x in enumerate(batches):
+            j = i & 1
+            e_h2d, e_used, e_comp, e_d2h = P["ev"][j]
+            if i >= 2:
+                P["h2d"].wait_event(e_used)                  # staging input j has been consumed by replay i-2
+            with torch.cuda.stream(P["h2d"]):
+                P["xin"][j].copy_(x, non_blocking=True)
+                e_h2d.record(P["h2d"])
+            cur.wait_event(e_h2d)
+            if i >= 2:
+                cur.wait_event(e_d2h)                        # staging output j has been drained by copy i-2
+            o = self(P["xin"][j])
+            e_used.record(cur)
+            for k in P["keys"]:
+                P["out"][j][k].copy_(o[k], non_blocking=True)
+            e_comp.record(cur)
+            with torch.cuda.stream(P["d2h"]):
+                P["d2h"].wait_event(e_comp)
+                for k in P["keys"]:
+                    sinks[j][k].copy_(P["out"][j][k], non_blocking=True)
+                e_d2h.record(P["d2h"])
+            if i >= 1:
+                P["ev"][1 - j][3].synchronize()              # result i-1 is on the host
+                yield i - 1, sinks[1 - j]
+            last = i
+        if last >= 0:
+            P["ev"][last & 1][3].synchronize()
+            yield last, sinks[last & 1]
+
     def __call__(self, x):
         if x.shape != self.static_in.shape or x.dtype != self.static_in.dtype:
             raise RuntimeError(f"graph captured for {tuple(self.static_in.shape)} {self.static_in.dtype}, got {tuple(x.shape)} {x.dtype}")

@@ -6,7 +6,9 @@
 //     dx = qx - px; dy = qy - py; s = fl(fl(dx*dx) + fl(dy*dy)); r = sqrt_rn(s)          (no FMA contraction)
 // and candidates are compared on r (NOT on s: sqrt merges distinct s into equal r, which changes tie groups).
 // The database is scanned in ascending index and insertion uses strict '<', so equal distances keep the lower index
-// first: the canonical tie rule.
+// first: the canonical tie rule.  The square root is only taken for the few candidates that can still enter the list:
+// sqrt_rn is monotone, so s > T^2 (1 + 2^-20) (T = current k-th distance; the factor covers the roundings of T = sqrt_rn(s_k)
+// and of T*T) implies r >= T, which the strict '<' rejects anyway.
 #include "common.cuh"
 
 namespace clusten {
@@ -27,6 +29,7 @@ knn_kernel(const float2 *__restrict__ query, const float2 *__restrict__ db, int 
     int bi[K];
 #pragma unroll
     for (int t = 0; t < K; ++t) { bd[t] = __int_as_float(0x7f800000); bi[t] = 0; }
+    float thr = __int_as_float(0x7f800000);             // candidates with s > thr cannot enter the list
     const float2 *dbb = db + (int64_t)b * Ndb;
     for (int t0 = 0; t0 < Ndb; t0 += KNN_TILE) {
         const int cnt = min(KNN_TILE, Ndb - t0);
@@ -36,7 +39,9 @@ knn_kernel(const float2 *__restrict__ query, const float2 *__restrict__ db, int 
         for (int x = 0; x < cnt; ++x) {
             const float2 p = tile[x];
             const float dx = __fsub_rn(q.x, p.x), dy = __fsub_rn(q.y, p.y);
-            const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+            const float s = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            if (s > thr) continue;
+            const float r = __fsqrt_rn(s);
             if (r < bd[K - 1]) {
                 const int pi = t0 + x;
 #pragma unroll
@@ -49,6 +54,7 @@ knn_kernel(const float2 *__restrict__ query, const float2 *__restrict__ db, int 
                     bi[t] = in ? ni : bi[t];
                 }
                 if (r < bd[0]) { bd[0] = r; bi[0] = pi; }
+                thr = __fmul_rn(__fmul_rn(bd[K - 1], bd[K - 1]), 1.00000095367431640625f);      // T^2 (1 + 2^-20); inf stays inf
             }
         }
     }

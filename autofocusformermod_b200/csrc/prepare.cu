@@ -23,9 +23,10 @@ __global__ void __launch_bounds__(256)
 prepare_kernel(const int64_t *__restrict__ nearest, const int64_t *__restrict__ member, const int64_t *__restrict__ cmask,
                const float *__restrict__ pos, int B, int n, int k, int m, int nnc,
                int64_t *__restrict__ member_idx, int64_t *__restrict__ mask64, uint8_t *__restrict__ mask8,
-               int32_t *__restrict__ pe, uint8_t *__restrict__ present) {
+               int32_t *__restrict__ pe, uint8_t *__restrict__ present, int *__restrict__ range) {
     const int M = nnc * m;
     const int64_t total = (int64_t)B * n * M;
+    int pmin = 0x7fffffff, pmax = -1;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int j = (int)(e % M);
         const int64_t bi = e / M;                        // b * n + i
@@ -48,21 +49,28 @@ prepare_kernel(const int64_t *__restrict__ nearest, const int64_t *__restrict__ 
         const int p = (int)__fadd_rn(__fmul_rn(ry, (float)PE_W), rx);     // (rel.y * 1023 + rel.x).long(), fp32 arithmetic
         pe[e] = p;
         present[p] = 1;                                  // benign race: every writer stores 1
+        pmin = min(pmin, p);
+        pmax = max(pmax, p);
     }
+    // span of the referenced table rows (neighbours are a few grid cells away: a small band of the 1023^2 rows)
+    pmin = __reduce_min_sync(FULL, pmin);
+    pmax = __reduce_max_sync(FULL, pmax);
+    if ((threadIdx.x & 31) == 0 && pmax >= 0) { atomicMin(range, pmin); atomicMax(range + 1, pmax); }
 }
 
 // rank of every present table row (exclusive prefix count), U = number of present rows, uniq[rank] = row id.
 // One CTA of 1024 threads walks the 1023^2 flags in chunks: 1 M flags, ~1 MB -> a few microseconds; no second kernel, no sync.
 __global__ void __launch_bounds__(1024)
 rank_kernel(const uint8_t *__restrict__ present, int32_t *__restrict__ rank, int32_t *__restrict__ uniq, int32_t *__restrict__ count,
-            int cap) {
+            int cap, const int *__restrict__ range) {
     __shared__ int wsum[32];
     __shared__ int base_s, chunk_tot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) base_s = 0;
     __syncthreads();
     constexpr int PER = 16;                              // flags per thread per chunk (one 16-byte load)
-    for (int c0 = 0; c0 < PE_ROWS; c0 += 1024 * PER) {
+    const int lo = range[0], hi = range[1];              // only the chunks that hold referenced rows are walked
+    for (int c0 = lo / (1024 * PER) * (1024 * PER); c0 < PE_ROWS && c0 <= hi; c0 += 1024 * PER) {
         const int p0 = c0 + tid * PER;
         uint32_t w[4] = {0u, 0u, 0u, 0u};
         if (p0 + PER <= PE_ROWS) {
@@ -141,11 +149,14 @@ extern "C" int clusten_stage_prepare(const int64_t *nearest, const int64_t *memb
     const size_t pm = (size_t)((PE_ROWS + 255) & ~255);
     int32_t *rank = reinterpret_cast<int32_t *>(present + pm);
     cudaMemsetAsync(present, 0, pm, st);
+    int *range = reinterpret_cast<int *>(reinterpret_cast<char *>(workspace) + pm + (size_t)PE_ROWS * 4);      // {min, max} referenced row
+    cudaMemsetAsync(range, 0x7f, 4, st);
+    cudaMemsetAsync(range + 1, 0, 4, st);
     const int64_t total = (int64_t)B * n * nnc * m;
     if (total == 0) { cudaMemsetAsync(count, 0, 4, st); return check_launch("prepare memset"); }
     const int grid = (int)std::min<int64_t>(148 * 16, (total + 255) / 256);
-    prepare_kernel<<<grid, 256, 0, st>>>(nearest, member, cluster_mask, pos, B, n, k, m, nnc, member_idx, mask64, mask8, pe_idx, present);
-    rank_kernel<<<1, 1024, 0, st>>>(present, rank, uniq, count, uniq_cap);
+    prepare_kernel<<<grid, 256, 0, st>>>(nearest, member, cluster_mask, pos, B, n, k, m, nnc, member_idx, mask64, mask8, pe_idx, present, range);
+    rank_kernel<<<1, 1024, 0, st>>>(present, rank, uniq, count, uniq_cap, range);
     rerank_kernel<<<grid, 256, 0, st>>>(pe_idx, rank, bias_idx, total);
     note_launches(3);
     return check_launch("stage_prepare");

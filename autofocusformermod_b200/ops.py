@@ -623,3 +623,66 @@ class WEIGHTEDGATHERFunction(Function):
                   _lib.dtype_code(feat),
                   nbytes=feat.element_size() * (B * Nq * C + 2 * B * Nq * K + 2 * B * Nk * C) + 8 * B * Nq * K)
         return None, d_weights, d_feat
+
+
+# ---- MSDETRPC --------------------------------------------------------------------------------------------------------
+class MSDETRPCFunction(Function):
+    """deformable multi-scale DETR attention on point clouds (clusten.py:123-146, msdetrpc_cuda_kernel.cu:18-55):
+
+        feat[b,i,c] = sum_m attn[b,i,m] * sum_k nn_weight[b,i,m,k] * val[b, nn_idx[b,i,m,k], c]
+
+    i.e. a weighted gather over the m*k interpolation points with the product weights attn[m] * nn_weight[m,k]: it runs
+    on the WEIGHTEDGATHER kernels (clusten_wg_fwd / clusten_wg_bwd, deterministic inverse-list backward instead of the
+    reference's atomics, msdetrpc_cuda_kernel.cu:113-131); the product and its two-term gradient are small elementwise
+    passes over [B,N,M,K].  ``.apply(nn_idx, nn_weight, attn, val)`` -> [B,N,C]; backward returns (None, d_weight, d_attn, d_val)."""
+
+    @staticmethod
+    def forward(ctx, nn_idx, nn_weight, attn, val):
+        dev = _lib.require_cuda(nn_idx, nn_weight, attn, val)
+        _check_shapes(nn_idx.dim() == 4 and nn_weight.shape == nn_idx.shape and attn.dim() == 3 and val.dim() == 3 and
+                      tuple(attn.shape) == tuple(nn_idx.shape[:3]) and val.shape[0] == nn_idx.shape[0], "MSDETRPC: shape mismatch")
+        if nn_idx.dtype != torch.int64:
+            raise RuntimeError(f"nn_idx must be int64 (got {nn_idx.dtype})")
+        B, N, M, K = nn_idx.shape
+        Nk, C = val.shape[1], val.shape[2]
+        nn_idx, nn_weight, attn, val = nn_idx.contiguous(), nn_weight.contiguous(), attn.contiguous(), _rows(val)
+        w = (attn.unsqueeze(3) * nn_weight).to(val.dtype).reshape(B, N, M * K)
+        out = torch.empty((B, N, C), dtype=val.dtype, device=dev)
+        if out.numel():
+            with torch.cuda.device(dev):
+                _call("clusten_wg_fwd", dev, nn_idx.data_ptr(), w.data_ptr(), val.data_ptr(), out.data_ptr(),
+                      B, N, Nk, C, M * K, val.stride(0), val.stride(1), _lib.dtype_code(val),
+                      nbytes=val.element_size() * (2 * B * N * M * K + B * Nk * C + B * N * C) + 8 * B * N * M * K)
+        ctx.save_for_backward(nn_idx, nn_weight, attn, val)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_feat):
+        nn_idx, nn_weight, attn, val = ctx.saved_tensors
+        dev = val.device
+        B, N, M, K = nn_idx.shape
+        Nk, C = val.shape[1], val.shape[2]
+        grad_feat = grad_feat.contiguous().to(val.dtype)
+        d_val = torch.empty((B, Nk, C), dtype=val.dtype, device=dev)
+        if B * N * M * K == 0:
+            return None, torch.zeros_like(nn_weight), torch.zeros_like(attn), d_val.zero_()
+        w = (attn.unsqueeze(3) * nn_weight).to(val.dtype).reshape(B, N, M * K)
+        d_w = torch.empty_like(w)
+        idx3 = nn_idx.view(B, N, M * K)
+        cached = getattr(nn_idx, "_clusten_csr", None)           # built by an earlier backward on the same index tensor
+        if cached is not None:
+            idx3._clusten_csr = cached
+        off, ent = inverse_neighbour_list(idx3, Nk)
+        try:                                                     # keep the list cached on the tensor the caller holds
+            nn_idx._clusten_csr = idx3._clusten_csr
+        except Exception:  # pragma: no cover
+            pass
+        with torch.cuda.device(dev):
+            _call("clusten_wg_bwd", dev, grad_feat.data_ptr(), idx3.data_ptr(), w.data_ptr(), val.data_ptr(), off.data_ptr(),
+                  ent.data_ptr(), d_w.data_ptr(), d_val.data_ptr(), B, N, Nk, C, M * K, val.stride(0), val.stride(1),
+                  d_val.stride(0), d_val.stride(1), _lib.dtype_code(val),
+                  nbytes=val.element_size() * (B * N * C + 2 * B * N * M * K + 2 * B * Nk * C) + 8 * B * N * M * K)
+        d_w = d_w.view(B, N, M, K)
+        d_weight = (d_w * attn.unsqueeze(3)).to(nn_weight.dtype)
+        d_attn = (d_w * nn_weight).sum(3).to(attn.dtype)
+        return None, d_weight, d_attn, d_val

@@ -239,3 +239,19 @@ def aff_forward(x, W, cfg, training=False, trace=None):
         outs[f"res{i + 2}_pos"] = pos_out
         outs[f"res{i + 2}_spatial_shape"] = (h, w)
     return outs
+
+
+def point_conv(x, pos, W, p):
+    """PointConv.forward of the point-cloud pixel decoder (pixel_decoder/msdeformattn_pc.py:285-314): kNN-9 among the points
+    themselves, weight_net over the relative-position table rows, CLUSTENWF, LayerNorm, Linear.  ``W`` = reference-named
+    state dict with prefix ``p`` (weight_net.0 / weight_net.1 / norm / linear)."""
+    b, n, c = x.shape
+    nn_idx = pt.knn(pos, pos, 9)
+    nn_pos = pos.gather(index=nn_idx.view(b, -1, 1).expand(-1, -1, 2), dim=1).reshape(b, n, 9, 2)
+    rel_pos = pos.unsqueeze(2) - nn_pos
+    rel = (rel_pos.long() + pt.REL_POS_WIDTH).clamp(0, pt.TABLE_WIDTH - 1)
+    pe_idx = rel[..., 1] * pt.TABLE_WIDTH + rel[..., 0]
+    t = F.gelu(_ln(_lin(pre_table(), W, p + "weight_net.0"), W, p + "weight_net.1"))
+    weights = t[pe_idx.reshape(-1)].reshape(b, n, 9, -1)
+    feat = ops.wf_forward(weights, x, nn_idx).reshape(b, n, -1)
+    return _lin(_ln(feat, W, p + "norm"), W, p + "linear")

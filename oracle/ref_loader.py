@@ -99,6 +99,22 @@ def load():
     return pu, aff
 
 
+def load_point_conv():
+    """The reference's own ``PointConv`` class (pixel_decoder/msdeformattn_pc.py:271-314), executed from the reference file
+    without importing the rest of the module (which needs detectron2 / fvcore): the class source is cut out with ``ast``
+    and run against the reference ``aff`` module's table constants, the oracle kNN and the oracle CLUSTENWF."""
+    import ast
+    pu, aff = load()
+    from . import clusten_ops, point_ops
+    path = os.path.join(REF_ROOT, "pixel_decoder", "msdeformattn_pc.py")
+    src = open(path).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "PointConv")
+    ns = {"nn": torch.nn, "torch": torch, "knn_keops": point_ops.knn, "CLUSTENWFFunction": clusten_ops.CLUSTENWFFunction,
+          "pre_table": aff.pre_table, "rel_pos_width": aff.rel_pos_width, "table_width": aff.table_width}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns["PointConv"]
+
+
 @contextlib.contextmanager
 def canonical_ties():
     """Force the canonical tie rules inside reference code: Tensor.sort -> stable,

@@ -131,3 +131,44 @@ def test_graphed_forward_equals_eager():
         for k, v in ref.items():
             if torch.is_tensor(v):
                 assert torch.equal(out[k], v), k
+    # pipelined serving loop: pinned host batches in, pinned host results out, same numbers
+    hx = [x.cpu().pin_memory() for x in xs]
+    sinks = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in ref.items() if torch.is_tensor(v)} for _ in range(2)]
+    seen = 0
+    for i, sink in graphed.stream(hx, sinks):
+        with torch.no_grad():
+            r = model(xs[i])
+        for k, v in sink.items():
+            assert torch.equal(v, r[k].cpu()), (i, k)
+        seen += 1
+    assert seen == len(xs)
+
+
+@pytest.mark.parametrize("dim,out_dim,n,hw", [(32, 48, 1024, 32), (64, 64, 700, 48)])
+def test_point_conv_matches_oracle(dim, out_dim, n, hw):
+    """PointConv of the point-cloud pixel decoder (msdeformattn_pc.py:271-314) on the CLUSTEN path (kNN-9, table lookup, WF)
+    against the oracle restatement, forward and gradients, fp32 (tolerance 1e-5 of the north star widened to 2e-5 for the
+    two LayerNorms and the Linear in between)."""
+    import torch
+    from autofocusformermod_b200.pixel_decoder import PointConv
+    from oracle import inputs
+    torch.manual_seed(0)
+    mod = PointConv(dim, out_dim, bias=True)
+    W = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    g = torch.Generator().manual_seed(n)
+    pos = inputs.grid_positions(2, hw, hw) if n == hw * hw else inputs.random_positions(2, n, hw, hw, seed=n)
+    x = torch.randn(2, n, dim, generator=g)
+    go = torch.randn(2, n, out_dim, generator=g)
+    Wr = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    xr = x.clone().requires_grad_(True)
+    ref = ao.point_conv(xr, pos, Wr, "")
+    ref.backward(go)
+    mod = mod.cuda()
+    xc = x.cuda().requires_grad_(True)
+    out = mod((xc, pos.cuda()))
+    out.backward(go.cuda())
+    torch.cuda.synchronize()
+    assert rel_err(out.detach().cpu(), ref.detach()) <= 2e-5
+    assert rel_err(xc.grad.cpu(), xr.grad) <= 2e-5
+    for k, prm in mod.named_parameters():
+        assert rel_err(prm.grad.cpu(), Wr[k].grad) <= 5e-5, k

@@ -253,6 +253,21 @@ def test_weighted_gather_golden(golden_dir):
     assert rel_err(d_f, torch.from_numpy(g["d_f"])) <= 1e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("B,N,Nk,M,K,C", [(100, 50, 100, 8, 4, 32), (2, 300, 1200, 12, 4, 256), (1, 7, 5, 3, 2, 20)])
+def test_msdetrpc(B, N, Nk, M, K, C, dtype):
+    """MSDETRPCFunction against the torch formulation of the reference's own check (clusten/test_msdetrpc_kernel.py:14-42,
+    first case = its sizes, seeded): forward and the three gradients."""
+    P = _ops()
+    g = torch.Generator().manual_seed(B + N)
+    cast = lambda t: t.to(dtype).float()
+    idx = torch.randint(Nk, (B, N, M, K), generator=g)
+    w, attn, val = cast(torch.rand(B, N, M, K, generator=g)), cast(torch.rand(B, N, M, generator=g)), cast(torch.rand(B, Nk, C, generator=g))
+    go = cast(torch.randn(B, N, C, generator=g))
+    ref = co.fwd_bwd(co.msdetrpc_forward, [idx, w, attn, val], go)
+    _check(_run(P.MSDETRPCFunction.apply, [idx, w, attn, val], go, dtype), ref, dtype, "MSDETRPC")
+
+
 def test_dtype_cast_rules_and_none_grads():
     """clusten.py:27-28,54-55,80-81,106-107: second operand follows the first; idx gets no gradient."""
     P = _ops()

@@ -52,3 +52,19 @@ def test_merge_selection_matches_reference_cluster_merging():
         pos2, feat2 = mod(pos, feat, nb, mask, lp, 4, pe_idx, reserve_num)
     idx = pt.merge_select(pos, lp, 4, 4.0, 0.25, reserve_num)
     assert torch.equal(pos2, pos.gather(1, idx.expand(-1, -1, 2)))
+
+
+def test_point_conv_oracle_matches_reference_class():
+    """oracle.aff_oracle.point_conv against the reference's own PointConv (msdeformattn_pc.py:271-314) run from the
+    reference file, same weights, same seeded points."""
+    from oracle import aff_oracle as ao
+    PointConv = ref_loader.load_point_conv()
+    torch.manual_seed(0)
+    mod = PointConv(16, 24, True)
+    W = {k: v.detach() for k, v in mod.state_dict().items()}
+    pos = inputs.random_positions(2, 300, 32, 32, seed=5)
+    x = torch.randn(2, 300, 16)
+    with torch.no_grad():
+        ref = mod((x, pos))
+        got = ao.point_conv(x, pos, W, "")
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6)
