@@ -434,6 +434,31 @@ class AFF(nn.Module):
         return GraphedAFF(self, example, autocast_dtype)
 
 
+class _Features(nn.Module):
+    """The backbone's feature tensors as a tuple (res2, res3, ...): what torch.cuda.make_graphed_callables can carry."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+
+    def forward(self, x):
+        out = self.model(x)
+        return tuple(out[f"res{i + 2}"] for i in self.model.out_indices)
+
+
+def graphed_training_forward(model, example, autocast_dtype=None, num_warmup_iters=3):
+    """Training forward AND backward of the backbone as two CUDA graphs (torch.cuda.make_graphed_callables over the
+    module tree; every CLUSTEN op and its backward is capturable: no host reads, device-side dispatch flags).  Returns a
+    callable ``f(x) -> (res2, res3, ...)`` that takes part in autograd like the module: ``loss.backward()`` replays the
+    backward graph and leaves the gradients in ``param.grad``.  One process per GPU, fixed input shape; run the optimizer
+    eagerly (or captured separately).  The ~9 k launches of an AFF-Tiny training step collapse into two replays."""
+    if not model.training:
+        raise RuntimeError("graphed_training_forward captures the training step: call model.train() first")
+    wrapped = _Features(model)
+    with torch.autocast("cuda", dtype=autocast_dtype or torch.bfloat16, enabled=autocast_dtype is not None, cache_enabled=False):
+        return torch.cuda.make_graphed_callables(wrapped, (example.detach().clone(),), num_warmup_iters=num_warmup_iters)
+
+
 class GraphedAFF:
     """Inference through ONE CUDA graph: the whole backbone forward (clustering, kNN, stage preparation, every block and merge
     -- a few hundred to a few thousand kernel launches, no host synchronisation anywhere) captured once for a fixed input

@@ -1,6 +1,6 @@
 // Tile-union WF forward for 16-bit types (sm_100a): out[b,i,ic,c] = sum_j w[b,i,j,ic] f[b,idx[b,i,j],c], IC = 4.
 //
-// ncu on the token-by-token kernel of clusten_wf2.cu (profiles/r1_wf2_small_s0_bf16_v8.csv) showed it bound by L1 data-pipe
+// ncu on the token-by-token kernel of clusten_wf2.cu (profiles/r1_wf2_small_s0_bf16_v8_ncu_keys.txt) showed it bound by L1 data-pipe
 // wavefronts (81 %): every token pulls its own M rows through L1 in 4-rows-per-instruction fragments, hit or miss.  Here a
 // tile = 16 consecutive tokens of the plan's order (spatial neighbours, wf2.cuh) and the rows of the UNION of their
 // octets are staged ONCE per tile: cp.async (coalesced 16-byte chunks) into shared memory, ldmatrix.trans into B

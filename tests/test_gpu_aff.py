@@ -172,3 +172,45 @@ def test_point_conv_matches_oracle(dim, out_dim, n, hw):
     assert rel_err(xc.grad.cpu(), xr.grad) <= 2e-5
     for k, prm in mod.named_parameters():
         assert rel_err(prm.grad.cpu(), Wr[k].grad) <= 5e-5, k
+
+
+@pytest.mark.parametrize("amp", [False, True], ids=["fp32", "bf16-autocast"])
+def test_graphed_training_step_matches_eager(amp):
+    """graphed_training_forward: forward + backward as CUDA graphs give the same features and parameter gradients as the
+    eager module (the CLUSTEN ops, their backwards, the packs / plans / inverse lists built on the fly are all capturable)."""
+    import copy
+    import torch
+    from autofocusformermod_b200.aff import build_aff, graphed_training_forward
+    torch.manual_seed(0)
+    model = build_aff("test").cuda().train()
+    ref_model = copy.deepcopy(model)
+    g = torch.Generator().manual_seed(2)
+    xs = [torch.randn(2, 3, 256, 256, generator=g).cuda() for _ in range(2)]
+    dt = torch.bfloat16 if amp else None
+    f = graphed_training_forward(model, xs[0], autocast_dtype=dt)
+    tol = 2e-2 if amp else 1e-4
+    for x in xs:
+        for m in (model, ref_model):
+            m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp, cache_enabled=False):
+            feats = f(x)
+            loss = sum(t.float().square().mean() for t in feats)
+        loss.backward()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            out = ref_model(x)
+            ref_loss = sum(out[f"res{i}"].float().square().mean() for i in range(2, 6))
+        ref_loss.backward()
+        torch.cuda.synchronize()
+        assert abs(float(loss) - float(ref_loss)) <= tol * abs(float(ref_loss))
+        checked = 0
+        for (k, p), (_, q) in zip(model.named_parameters(), ref_model.named_parameters()):
+            if q.grad is None:
+                continue
+            assert p.grad is not None, k
+            a, r = p.grad.float().cpu(), q.grad.float().cpu()
+            if float(r.abs().max()) < 1e-7:          # analytically zero (a bias in front of BatchNorm): rounding noise only
+                assert float(a.abs().max()) < 1e-6, k
+                continue
+            assert rel_err(a, r) <= tol, k
+            checked += 1
+        assert checked > 50
