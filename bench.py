@@ -178,6 +178,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION: keep stdout to the one JSON line of the contract
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     from autofocusformermod_b200 import ops
     from autofocusformermod_b200.aff import build_aff
