@@ -115,6 +115,16 @@ def load_point_conv():
     return ns["PointConv"]
 
 
+def load_point2img():
+    """The reference's own ``point2img`` (transformer_decoder/mask2former_transformer_decoder.py:20-39), cut out with ``ast``."""
+    import ast
+    path = os.path.join(REF_ROOT, "transformer_decoder", "mask2former_transformer_decoder.py")
+    node = next(n for n in ast.parse(open(path).read()).body if isinstance(n, ast.FunctionDef) and n.name == "point2img")
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns["point2img"]
+
+
 @contextlib.contextmanager
 def canonical_ties():
     """Force the canonical tie rules inside reference code: Tensor.sort -> stable,

@@ -214,3 +214,32 @@ def test_graphed_training_step_matches_eager(amp):
             assert rel_err(a, r) <= tol, k
             checked += 1
         assert checked > 50
+
+
+def test_decoder_helpers_point2img_and_attn_mask():
+    """point2img against its definition (mask2former_transformer_decoder.py:20-39: value of point p lands at pixel pos[p]) and
+    point_attn_mask against the oracle Shepard upsampling (point_utils.py:78-121) thresholded at sigmoid < 0.5."""
+    import torch
+    from autofocusformermod_b200.pixel_decoder import point2img, point_attn_mask
+    from oracle import inputs
+    from oracle import point_ops as pt
+    g = torch.Generator().manual_seed(0)
+    h, w, q = 12, 20, 5
+    perm = torch.stack([torch.randperm(h * w, generator=g) for _ in range(2)])
+    pos = torch.stack([perm % w, perm // w], dim=-1).float()
+    x = torch.randn(2, q, h * w, generator=g)
+    img = point2img(x.cuda(), pos.cuda(), (h, w)).cpu()
+    img2 = point2img(x.cuda(), pos.cuda()).cpu()                    # reference behaviour: size from the positions
+    ref = torch.zeros(2, q, h, w)
+    for b in range(2):
+        ref[b, :, pos[b, :, 1].long(), pos[b, :, 0].long()] = x[b]
+    assert torch.equal(img, ref) and torch.equal(img2, ref)
+    mf_pos = inputs.grid_positions(2, 16, 16)
+    tgt = inputs.random_positions(2, 90, 16, 16, seed=3)
+    logits = torch.randn(2, 7, 256, generator=g)
+    got = point_attn_mask(tgt.cuda(), mf_pos.cuda(), logits.cuda(), 4).cpu()
+    up = pt.upsample_feature_shepard(tgt, mf_pos, logits.permute(0, 2, 1)).permute(0, 2, 1)
+    want = (up.sigmoid().unsqueeze(1).repeat(1, 4, 1, 1).flatten(0, 1) < 0.5)
+    assert got.shape == want.shape and got.dtype == torch.bool
+    near = (up.sigmoid() - 0.5).abs().unsqueeze(1).repeat(1, 4, 1, 1).flatten(0, 1) < 1e-5     # ignore logits on the threshold
+    assert bool(((got == want) | near).all())

@@ -68,3 +68,17 @@ def test_point_conv_oracle_matches_reference_class():
         ref = mod((x, pos))
         got = ao.point_conv(x, pos, W, "")
     assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_point2img_definition_matches_reference_function():
+    """The indexed-assignment definition used by the GPU test equals the reference's scatter (point2img, :20-39)."""
+    p2i = ref_loader.load_point2img()
+    g = torch.Generator().manual_seed(0)
+    h, w, q = 6, 9, 3
+    perm = torch.stack([torch.randperm(h * w, generator=g) for _ in range(2)])
+    pos = torch.stack([perm % w, perm // w], dim=-1).float()
+    x = torch.randn(2, q, h * w, generator=g)
+    ref = torch.zeros(2, q, h, w)
+    for b in range(2):
+        ref[b, :, pos[b, :, 1].long(), pos[b, :, 0].long()] = x[b]
+    assert torch.equal(p2i(x, pos), ref) and torch.equal(p2i(x, pos, (h, w)), ref)
