@@ -34,6 +34,7 @@ _pre_tables = {}
 # Inference fast path: QK + bias + mask + blank token + softmax + AV in one kernel (clusten_attn_fwd) whenever autograd
 # is off.  Training keeps the signature-preserving ops (their backward is the accelerated one).
 USE_FUSED_ATTENTION = True
+GRID_STRUCTURE_CACHE = True        # memoise the position-only structures of the on-grid stage (see BasicLayer._grid_structure)
 
 
 def rel_pos_features(pe_idx):
@@ -304,18 +305,28 @@ class BasicLayer(nn.Module):
             self.prob_net = nn.Linear(dim, 1)
         else:
             self.downsample = None
-        self._grid_cache = None          # stage-0 clustering of an on-grid batch in training (aff.py:461-467)
+        self._grid_cache = None          # position-only structures of an on-grid stage (see _grid_structure; aff.py:461-467)
 
     def _cluster(self, pos, feat, h, w, on_grid):
         b, n, c = feat.shape
-        if on_grid and self.training:
-            if self._grid_cache is None or self._grid_cache[0].shape[0] < b or self._grid_cache[0].shape[1] != n:
-                self._grid_cache = space_filling_cluster(pos, self.cluster_size, h, w)
-            pos, mean_pos, member, cmask, reorder = (None if t is None else t[:b] for t in self._grid_cache)
-        else:
-            pos, mean_pos, member, cmask, reorder = space_filling_cluster(pos, self.cluster_size, h, w)
+        pos, mean_pos, member, cmask, reorder = space_filling_cluster(pos, self.cluster_size, h, w)
         feat = feat.gather(1, reorder.expand(-1, -1, c))                                             # aff.py:471
         return pos, feat, mean_pos, member, cmask
+
+    def _grid_structure(self, pos, b, n, h, w, m, nnc):
+        """Everything a stage derives from the token POSITIONS alone, for an on-grid stage (the stem grid of stage 0): clustering,
+        nearest clusters, neighbourhoods, masks, table rows.  The grid is the same for every batch of a given shape, so this is a
+        constant of (b, h, w): the reference memoises the clustering part in training (aff.py:461-467); here the whole structure
+        is memoised, in training and in inference (it also keeps the tile pack cached on ``member_idx`` alive across calls)."""
+        key = (b, n, h, w, m, nnc, pos.device)
+        if self._grid_cache is None or self._grid_cache[0] != key:
+            with torch.no_grad():
+                spos, mean_pos, member, cmask, reorder = space_filling_cluster(pos, m, h, w)
+                nearest = knn_keops(spos, mean_pos, nnc)
+                prepared = stage_prepare(spos, nearest, member, cmask, extent=(h, w))
+                lookup = _TableLookup(uniq=prepared[3], inverse=prepared[4], count=prepared[5])
+            self._grid_cache = (key, spos, reorder, prepared, lookup)
+        return self._grid_cache[1:]
 
     def forward(self, pos, feat, h, w, on_grid, stride):
         b, n, d = pos.shape
@@ -328,16 +339,23 @@ class BasicLayer(nn.Module):
             global_attn = False
             k = int(math.ceil(n / float(m)))
             nnc = min(int(round(self.nbhd_size / float(m))), k)
-            if k == n:                                                                               # aff.py:456-459
-                mean_pos, cluster_mask = pos, None
-                member = torch.arange(n, device=feat.device).reshape(1, n, 1).expand(b, -1, -1)
+            if on_grid and k != n and GRID_STRUCTURE_CACHE:
+                pos, reorder, prepared, pe_lookup = self._grid_structure(pos, b, n, h, w, m, nnc)
+                feat = feat.gather(1, reorder.expand(-1, -1, feat.shape[2]))                         # aff.py:471
+                member_idx, cluster_mask, mask_u8, uniq, bias_idx, count = prepared
             else:
-                pos, feat, mean_pos, member, cluster_mask = self._cluster(pos, feat, h, w, on_grid)
-            nearest = knn_keops(pos, mean_pos, nnc)                                                  # aff.py:475
-            # aff.py:478-485 (member / mask gathers, relative positions, table index) + the table-row restriction: one pass
-            member_idx, cluster_mask, mask_u8, uniq, bias_idx, count = stage_prepare(pos, nearest, member, cluster_mask, extent=(h, w))
+                pe_lookup = None
+                if k == n:                                                                           # aff.py:456-459
+                    mean_pos, cluster_mask = pos, None
+                    member = torch.arange(n, device=feat.device).reshape(1, n, 1).expand(b, -1, -1)
+                else:
+                    pos, feat, mean_pos, member, cluster_mask = self._cluster(pos, feat, h, w, on_grid)
+                nearest = knn_keops(pos, mean_pos, nnc)                                              # aff.py:475
+                # aff.py:478-485 (member / mask gathers, relative positions, table index) + the table-row restriction: one pass
+                member_idx, cluster_mask, mask_u8, uniq, bias_idx, count = stage_prepare(pos, nearest, member, cluster_mask, extent=(h, w))
             pe_idx = None
-            pe_lookup = _TableLookup(uniq=uniq, inverse=bias_idx, count=count)
+            if pe_lookup is None:
+                pe_lookup = _TableLookup(uniq=uniq, inverse=bias_idx, count=count)
             fused_ctx = (bias_idx, mask_u8) if USE_FUSED_ATTENTION else None
         if global_attn:
             rel_pos = rel_pos.clamp(0, TABLE_WIDTH - 1)
