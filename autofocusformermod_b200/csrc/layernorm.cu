@@ -9,6 +9,8 @@
 //   fwd: y = (x - mean) * rstd * gamma + beta;   saves mean, rstd (fp32 [R]) when asked
 //   bwd: dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)), g = dy * gamma;  dgamma += sum_r dy * xhat;  dbeta += sum_r dy
 //        (dgamma / dbeta: per-CTA shared-memory partials, then one fp32 atomic per channel and CTA)
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace clusten {
@@ -24,40 +26,70 @@ __device__ __forceinline__ float ln_warp_sum(float x) {
 }
 
 // PER = elements per lane (C = 32 * PER exactly when FULLROW, else C <= 32 * PER with a tail predicate)
+// Rows are walked grid-stride, TWO per warp and iteration (their loads are issued together, their shuffle reductions
+// interleave): with one short-lived CTA per 8 rows the kernel sat at 2.0 TB/s at C = 64 (ncu, AFF-Tiny stage 0) -- CTA
+// turnover, not bandwidth.
 template <typename TI, typename TO, int PER>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const TI *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta, TO *__restrict__ y,
               float *__restrict__ mean_out, float *__restrict__ rstd_out, int64_t R, int C, float eps) {
     const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= R) return;
-    const TI *xr = x + row * C;
-    float v[PER];
-    float s = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    constexpr bool KEEP = PER <= 8;                     // gamma / beta live in registers for narrow rows only
+    float gm[KEEP ? PER : 1], bt[KEEP ? PER : 1];
+    if constexpr (KEEP) {
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int c = lane + 32 * k;
-        v[k] = c < C ? ln_ld(xr + c) : 0.f;
-        s += v[k];
+        for (int k = 0; k < PER; ++k) {
+            const int c = lane + 32 * k;
+            gm[k] = c < C ? __ldg(gamma + c) : 0.f;
+            bt[k] = c < C ? __ldg(beta + c) : 0.f;
+        }
     }
-    const float mean = ln_warp_sum(s) / (float)C;
-    float q = 0.f;
+    const float invC = 1.f / (float)C;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < R; row += 2 * stride) {
+        const int64_t row2 = row + stride;
+        const bool two = row2 < R;
+        const TI *xa = x + row * C, *xb = x + (two ? row2 : row) * C;
+        float va[PER], vb[PER];
+        float sa = 0.f, sb = 0.f;
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int c = lane + 32 * k;
-        const float d = c < C ? v[k] - mean : 0.f;
-        q = fmaf(d, d, q);
-    }
-    const float rstd = rsqrtf(ln_warp_sum(q) / (float)C + eps);
-    TO *yr = y + row * C;
+        for (int k = 0; k < PER; ++k) {
+            const int c = lane + 32 * k;
+            va[k] = c < C ? ln_ld(xa + c) : 0.f;
+            vb[k] = c < C ? ln_ld(xb + c) : 0.f;
+            sa += va[k];
+            sb += vb[k];
+        }
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int c = lane + 32 * k;
-        if (c < C) yr[c] = from_f<TO>(fmaf((v[k] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c)));
+        for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(FULL, sa, o); sb += __shfl_xor_sync(FULL, sb, o); }
+        const float ma = sa * invC, mb = sb * invC;
+        float qa = 0.f, qb = 0.f;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int c = lane + 32 * k;
+            const float da = c < C ? va[k] - ma : 0.f, db = c < C ? vb[k] - mb : 0.f;
+            qa = fmaf(da, da, qa);
+            qb = fmaf(db, db, qb);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { qa += __shfl_xor_sync(FULL, qa, o); qb += __shfl_xor_sync(FULL, qb, o); }
+        const float ra = rsqrtf(qa * invC + eps), rb = rsqrtf(qb * invC + eps);
+        TO *ya = y + row * C, *yb = y + row2 * C;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int c = lane + 32 * k;
+            if (c < C) {
+                const float g = KEEP ? gm[KEEP ? k : 0] : __ldg(gamma + c), be = KEEP ? bt[KEEP ? k : 0] : __ldg(beta + c);
+                ya[c] = from_f<TO>(fmaf((va[k] - ma) * ra, g, be));
+                if (two) yb[c] = from_f<TO>(fmaf((vb[k] - mb) * rb, g, be));
+            }
+        }
+        if (lane == 0 && mean_out) {
+            mean_out[row] = ma; rstd_out[row] = ra;
+            if (two) { mean_out[row2] = mb; rstd_out[row2] = rb; }
+        }
     }
-    if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
-
 template <typename TI, typename TG, typename TO, int PER>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const TG *__restrict__ dy, const TI *__restrict__ x, const float *__restrict__ gamma,
@@ -116,7 +148,7 @@ ln_bwd_kernel(const TG *__restrict__ dy, const TI *__restrict__ x, const float *
 template <typename TI, typename TO>
 static int ln_fwd_launch(const TI *x, const float *g, const float *b, TO *y, float *mean, float *rstd, int64_t R, int C, float eps,
                          cudaStream_t st) {
-    const int grid = (int)((R + 7) / 8);
+    const int grid = (int)std::min<int64_t>((R + 7) / 8, 148 * 8);
     const int per = (C + 31) / 32;
 #define LN_F(P_) ln_fwd_kernel<TI, TO, P_><<<grid, 256, 0, st>>>(x, g, b, y, mean, rstd, R, C, eps)
     if (per <= 1) LN_F(1); else if (per <= 2) LN_F(2); else if (per <= 4) LN_F(4); else if (per <= 8) LN_F(8);

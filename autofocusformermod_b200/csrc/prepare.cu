@@ -19,38 +19,59 @@ constexpr int PE_W = 1023;
 constexpr int PE_ROWS = PE_W * PE_W;
 constexpr float PE_HALF = 511.f;
 
+// one thread per (token, neighbour cluster, group of 4 members): the cluster lookup and the token's position are shared by the
+// group, member_idx / mask / pe leave as 32- / 16- / 4-byte vector stores (m % 4 == 0; a scalar tail covers other m)
 __global__ void __launch_bounds__(256)
 prepare_kernel(const int64_t *__restrict__ nearest, const int64_t *__restrict__ member, const int64_t *__restrict__ cmask,
                const float *__restrict__ pos, int B, int n, int k, int m, int nnc,
                int64_t *__restrict__ member_idx, int64_t *__restrict__ mask64, uint8_t *__restrict__ mask8,
                int32_t *__restrict__ pe, uint8_t *__restrict__ present, int *__restrict__ range) {
     const int M = nnc * m;
-    const int64_t total = (int64_t)B * n * M;
+    const int G = (m & 3) == 0 ? 4 : 1;                  // members per thread
+    const int gpc = m / G;                               // groups per cluster
+    const int64_t total = (int64_t)B * n * nnc * gpc;
     int pmin = 0x7fffffff, pmax = -1;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int j = (int)(e % M);
-        const int64_t bi = e / M;                        // b * n + i
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int gq = (int)(t % gpc);
+        const int64_t tc = t / gpc;                      // (b * n + i) * nnc + c
+        const int c = (int)(tc % nnc);
+        const int64_t bi = tc / nnc;                     // b * n + i
         const int b = (int)(bi / n);
-        const int c = j / m, r = j - c * m;
-        const int64_t cl = nearest[bi * nnc + c];
-        const int64_t src = ((int64_t)b * k + cl) * m + r;
-        const int64_t mi = member[src];
-        member_idx[e] = mi;
-        if (cmask) {
-            const int64_t mk = cmask[src];
-            if (mask64) mask64[e] = mk;
-            if (mask8) mask8[e] = mk != 0;
-        }
+        const int64_t cl = nearest[tc];
+        const int64_t src = ((int64_t)b * k + cl) * m + gq * G;
+        const int64_t e = bi * M + c * m + gq * G;
         const float2 pi = *reinterpret_cast<const float2 *>(pos + bi * 2);
-        const float2 pn = *reinterpret_cast<const float2 *>(pos + ((int64_t)b * n + mi) * 2);
-        float rx = __fsub_rn(pn.x, __fsub_rn(pi.x, PE_HALF)), ry = __fsub_rn(pn.y, __fsub_rn(pi.y, PE_HALF));
-        rx = fminf(fmaxf(rx, 0.f), (float)(PE_W - 1));
-        ry = fminf(fmaxf(ry, 0.f), (float)(PE_W - 1));
-        const int p = (int)__fadd_rn(__fmul_rn(ry, (float)PE_W), rx);     // (rel.y * 1023 + rel.x).long(), fp32 arithmetic
-        pe[e] = p;
-        present[p] = 1;                                  // benign race: every writer stores 1
-        pmin = min(pmin, p);
-        pmax = max(pmax, p);
+        const float qx = __fsub_rn(pi.x, PE_HALF), qy = __fsub_rn(pi.y, PE_HALF);
+        int64_t mi[4], mk[4] = {1, 1, 1, 1};
+        int pv[4];
+        for (int x = 0; x < G; ++x) mi[x] = member[src + x];
+        if (cmask)
+            for (int x = 0; x < G; ++x) mk[x] = cmask[src + x];
+        for (int x = 0; x < G; ++x) {
+            const float2 pn = *reinterpret_cast<const float2 *>(pos + ((int64_t)b * n + mi[x]) * 2);
+            float rx = __fsub_rn(pn.x, qx), ry = __fsub_rn(pn.y, qy);
+            rx = fminf(fmaxf(rx, 0.f), (float)(PE_W - 1));
+            ry = fminf(fmaxf(ry, 0.f), (float)(PE_W - 1));
+            pv[x] = (int)__fadd_rn(__fmul_rn(ry, (float)PE_W), rx);       // (rel.y * 1023 + rel.x).long(), fp32 arithmetic
+            present[pv[x]] = 1;                          // benign race: every writer stores 1
+            pmin = min(pmin, pv[x]);
+            pmax = max(pmax, pv[x]);
+        }
+        if (G == 4) {                                    // e % 4 == 0: aligned vector stores
+            *reinterpret_cast<longlong4 *>(member_idx + e) = make_longlong4(mi[0], mi[1], mi[2], mi[3]);
+            *reinterpret_cast<int4 *>(pe + e) = make_int4(pv[0], pv[1], pv[2], pv[3]);
+            if (cmask) {
+                if (mask64) *reinterpret_cast<longlong4 *>(mask64 + e) = make_longlong4(mk[0], mk[1], mk[2], mk[3]);
+                if (mask8) *reinterpret_cast<uchar4 *>(mask8 + e) = make_uchar4(mk[0] != 0, mk[1] != 0, mk[2] != 0, mk[3] != 0);
+            }
+        } else {
+            member_idx[e] = mi[0];
+            pe[e] = pv[0];
+            if (cmask) {
+                if (mask64) mask64[e] = mk[0];
+                if (mask8) mask8[e] = mk[0] != 0;
+            }
+        }
     }
     // span of the referenced table rows (neighbours are a few grid cells away: a small band of the 1023^2 rows)
     pmin = __reduce_min_sync(FULL, pmin);
@@ -154,8 +175,10 @@ extern "C" int clusten_stage_prepare(const int64_t *nearest, const int64_t *memb
     cudaMemsetAsync(range + 1, 0, 4, st);
     const int64_t total = (int64_t)B * n * nnc * m;
     if (total == 0) { cudaMemsetAsync(count, 0, 4, st); return check_launch("prepare memset"); }
+    const int64_t pthreads = (m & 3) == 0 ? total / 4 : total;
+    const int pgrid = (int)std::min<int64_t>(148 * 16, (pthreads + 255) / 256);
     const int grid = (int)std::min<int64_t>(148 * 16, (total + 255) / 256);
-    prepare_kernel<<<grid, 256, 0, st>>>(nearest, member, cluster_mask, pos, B, n, k, m, nnc, member_idx, mask64, mask8, pe_idx, present, range);
+    prepare_kernel<<<pgrid, 256, 0, st>>>(nearest, member, cluster_mask, pos, B, n, k, m, nnc, member_idx, mask64, mask8, pe_idx, present, range);
     rank_kernel<<<1, 1024, 0, st>>>(present, rank, uniq, count, uniq_cap, range);
     rerank_kernel<<<grid, 256, 0, st>>>(pe_idx, rank, bias_idx, total);
     note_launches(3);

@@ -44,11 +44,19 @@ table_grad_smem_kernel(const T *__restrict__ dout, const I *__restrict__ inv, fl
     const int tot = U * cw;
     for (int x = threadIdx.x; x < tot; x += blockDim.x) tab_s[x] = 0.f;
     __syncthreads();
-    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-        const int r = (int)inv[e];
-        const int64_t b = e / n_per;
-        const T *dp = dout + b * d_sb + (e - b * n_per) * d_se + c_lo * d_sc;
-        for (int c = 0; c < cw; ++c) atomicAdd(tab_s + r * cw + c, to_f(dp[c * d_sc]));
+    {
+        // (sample, position in sample) of this thread's entry, advanced incrementally: no 64-bit division per entry
+        int64_t e = e0 + threadIdx.x;
+        int64_t b = e < e1 ? e / n_per : 0;
+        int64_t el = e - b * n_per;
+        const T *base = dout + c_lo * d_sc;
+        for (; e < e1; e += blockDim.x) {
+            const int r = (int)inv[e];
+            const T *dp = base + b * d_sb + el * d_se;
+            for (int c = 0; c < cw; ++c) atomicAdd(tab_s + r * cw + c, to_f(dp[c * d_sc]));
+            el += blockDim.x;
+            while (el >= n_per) { el -= n_per; ++b; }
+        }
     }
     __syncthreads();
     for (int x = threadIdx.x; x < tot; x += blockDim.x) {

@@ -421,9 +421,16 @@ class ClusterAttentionCoreFunction(Function):
                 _call("clusten_table_grad", dev, dS.data_ptr(), bias_idx.data_ptr(), 0, d_tab.data_ptr(), B * N * M, tab.shape[0],
                       _lib.ptr(ctx.count), H,
                       N * M, H * N * M, 1, N * M, code, nbytes=es * B * H * N * M + 4 * B * N * M)
-        # blank-token parameters: tiny [H,C] reductions over all tokens (cuBLAS batched GEMV-like, fp32 accumulation)
-        d_bk = torch.einsum("bhn,bnhc->hc", dSb.to(dt), q).reshape(-1)
-        d_bv = torch.einsum("bhn,bnhc->hc", Pb.to(dt), d_out).reshape(-1)
+        # blank-token parameters: [H,C] column sums over all tokens -- one pass over q and d_out (clusten_blank_grad)
+        if q.numel() and C % 8 == 0 and H * C <= 2048:
+            d_bk = torch.zeros(H * C, dtype=torch.float32, device=dev)
+            d_bv = torch.zeros(H * C, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _call("clusten_blank_grad", dev, qv.data_ptr(), gv.data_ptr(), dSb.data_ptr(), Pb.data_ptr(), d_bk.data_ptr(),
+                      d_bv.data_ptr(), B, H, N, C, *_s3(qv), *_s3(gv), code, nbytes=es * 2 * B * H * N * C + 8 * B * H * N)
+        else:
+            d_bk = torch.einsum("bhn,bnhc->hc", dSb.to(dt), q).reshape(-1)
+            d_bv = torch.einsum("bhn,bnhc->hc", Pb.to(dt), d_out).reshape(-1)
         tdt, kdt, vdt = ctx.meta
         return d_q, d_kv, d_tab.to(tdt), d_bk.to(kdt), d_bv.to(vdt), None, None, None, None
 

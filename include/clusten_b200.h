@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define CLUSTEN_ABI_VERSION 4
+#define CLUSTEN_ABI_VERSION 5
 
 enum { CLUSTEN_F32 = 0, CLUSTEN_F16 = 1, CLUSTEN_BF16 = 2 };
 
@@ -142,6 +142,14 @@ int clusten_attn_bwd(const void *d_out, const void *out, const float *lse, const
                      int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t do_sb, int64_t do_sh, int64_t do_sn,
                      int64_t o_sb, int64_t o_sh, int64_t o_sn, int64_t dq_sb, int64_t dq_sh, int64_t dq_sn,
                      int dtype, void *stream);
+/* blank-token parameter gradients of the fused core (aff.py:138-146 backwards), 16-bit q / d_out as strided [B,H,N,C] views,
+ * dS_blank / P_blank fp32 [B,H,N] as written by clusten_attn_bwd; d_blank_k / d_blank_v fp32 [H*C], accumulated INTO
+ * (caller zeroes them).  One pass over q and d_out instead of two skinny GEMMs. */
+int clusten_blank_grad(const void *q, const void *d_out, const float *dS_blank, const float *P_blank,
+                       float *d_blank_k, float *d_blank_v, int B, int H, int N, int C,
+                       int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t g_sb, int64_t g_sh, int64_t g_sn,
+                       int dtype, void *stream);
+
 /* out[b,h,r,:] = sum_{(i,j): idx[b,i,j]=r} w[b,h,i,j] x[b,h,i,:]: the scatter half of clusten_qk_bwd / clusten_av_bwd on its own
  * (deterministic: inverse lists, no atomics).  w addressed base + b*w_sb + h*w_sh + i*w_sn + j. */
 int clusten_scatter_rows(const void *w, const void *x, const int32_t *csr_offsets, const uint32_t *csr_entries,
