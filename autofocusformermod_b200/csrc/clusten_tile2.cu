@@ -309,18 +309,26 @@ scat2_kernel16(const ScatArgs a, const PackView pk) {
     const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(dyn2) + (threadIdx.x >> 5) * a.smem_per_warp;
     const T *Wb = opaque(reinterpret_cast<const T *>(a.W) + b * a.w_sb + h0 * a.w_sh);
     const T *Xb = opaque(reinterpret_cast<const T *>(a.X) + b * a.x_sb + h0 * a.x_sh);
-    const int8_t *slotb = opaque(pk.slot_of + (int64_t)b * pk.T * (TILE_TOK * U_MAX));
-    // inverse-list cursors of octets o and o + 1
+    const int8_t *slotb = opaque(pk.slot_t + (int64_t)b * pk.T * (TILE_TOK * U_MAX));
+    // inverse-list cursors of octets o and o + 1; the first 32 entries of either list are fetched once (one per lane) and
+    // handed out by shuffle, so the walk does not start every step with a dependent global load
     const int *off = pk.oct_off + b * (pk.NO + 1) + o;
-    int pa = off[0];
+    const int pa0 = off[0];
+    int pa = pa0;
     const int ea = off[1];
+    const int pb0 = ea;
     int pb = ea;
     const int eb = o + 1 < pk.NO ? off[2] : ea;
     const uint32_t *ent = opaque(pk.oct_ent + (int64_t)b * pk.T * U_MAX);
+    const unsigned pre_a = pa0 + lane < ea ? ldg4(ent + pa0 + lane) : 0xffffffffu;
+    const unsigned pre_b = pb0 + lane < eb ? ldg4(ent + pb0 + lane) : 0xffffffffu;
     auto next = [&](int &tile, int &ua, int &ub) -> bool {
         if (pa >= ea && pb >= eb) return false;
-        const unsigned va = pa < ea ? ldg4(ent + pa) : 0xffffffffu;
-        const unsigned vb = pb < eb ? ldg4(ent + pb) : 0xffffffffu;
+        unsigned va = __shfl_sync(FULL, pre_a, (pa - pa0) & 31), vb = __shfl_sync(FULL, pre_b, (pb - pb0) & 31);
+        if (pa - pa0 >= 32) va = ldg4(ent + min(pa, ea - 1));          // (lists longer than a warp: rare)
+        if (pb - pb0 >= 32) vb = ldg4(ent + min(pb, max(eb - 1, pb0)));
+        if (pa >= ea) va = 0xffffffffu;
+        if (pb >= eb) vb = 0xffffffffu;
         const unsigned ta = va == 0xffffffffu ? va : va / U_MAX, tb = vb == 0xffffffffu ? vb : vb / U_MAX;
         const unsigned tm = min(ta, tb);
         tile = (int)tm;
@@ -348,7 +356,7 @@ scat2_kernel16(const ScatArgs a, const PackView pk) {
         }
         const int u = half ? ub : ua;
         int s = -1;
-        if (u >= 0) s = (int)slotb[(tile * TILE_TOK + tok) * U_MAX + u];
+        if (u >= 0) s = (int)slotb[(tile * U_MAX + u) * TILE_TOK + tok];      // 16 contiguous bytes per (tile, u)
         const int wo = (tile * TILE_TOK + tok) * a.w_sn + 8 * max(s, 0);
 #pragma unroll
         for (int hh = 0; hh < HG; ++hh) {

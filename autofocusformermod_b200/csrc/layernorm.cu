@@ -106,31 +106,55 @@ ln_bwd_kernel(const TG *__restrict__ dy, const TI *__restrict__ x, const float *
         ag[k] = ab[k] = 0.f;
         gm[k] = c < C ? __ldg(gamma + c) : 0.f;
     }
-    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < R; row += (int64_t)gridDim.x * 8) {
-        const TI *xr = x + row * C;
-        const TG *gr = dy + row * C;
-        const float mean = mean_in[row], rstd = rstd_in[row];
-        float xh[PER], g[PER];
-        float s1 = 0.f, s2 = 0.f;
+    // narrow rows (C <= 256): two rows per warp and iteration -- their loads are in flight together, their reductions
+    // interleave (see ln_fwd_kernel); wide rows keep one row per iteration (registers)
+    constexpr bool TWO = PER <= 8;
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    const float invC = 1.f / (float)C;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < R; row += (TWO ? 2 : 1) * stride) {
+        const int64_t row2 = row + stride;
+        const bool two = TWO && row2 < R;
+        const int64_t rb = two ? row2 : row;
+        const TI *xa = x + row * C, *xb = x + rb * C;
+        const TG *ga = dy + row * C, *gb = dy + rb * C;
+        const float mean_a = mean_in[row], rstd_a = rstd_in[row], mean_b = mean_in[rb], rstd_b = rstd_in[rb];
+        float xha[PER], gva[PER], xhb[TWO ? PER : 1], gvb[TWO ? PER : 1];
+        float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
             const int c = lane + 32 * k;
             const bool in = c < C;
-            const float d = in ? to_f(gr[c]) : 0.f;
-            xh[k] = in ? (ln_ld(xr + c) - mean) * rstd : 0.f;
-            g[k] = d * gm[k];
-            s1 += g[k];
-            s2 = fmaf(g[k], xh[k], s2);
-            ag[k] = fmaf(d, xh[k], ag[k]);
-            ab[k] += d;
+            const float da = in ? to_f(ga[c]) : 0.f;
+            xha[k] = in ? (ln_ld(xa + c) - mean_a) * rstd_a : 0.f;
+            gva[k] = da * gm[k];
+            s1a += gva[k];
+            s2a = fmaf(gva[k], xha[k], s2a);
+            ag[k] = fmaf(da, xha[k], ag[k]);
+            ab[k] += da;
+            if constexpr (TWO) {
+                const float db = (in && two) ? to_f(gb[c]) : 0.f;
+                xhb[k] = in ? (ln_ld(xb + c) - mean_b) * rstd_b : 0.f;
+                gvb[k] = db * gm[k];
+                s1b += gvb[k];
+                s2b = fmaf(gvb[k], xhb[k], s2b);
+                ag[k] = fmaf(db, xhb[k], ag[k]);
+                ab[k] += db;
+            }
         }
-        s1 = ln_warp_sum(s1) / (float)C;
-        s2 = ln_warp_sum(s2) / (float)C;
-        TO *dr = dx + row * C;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1a += __shfl_xor_sync(FULL, s1a, o); s2a += __shfl_xor_sync(FULL, s2a, o);
+            if constexpr (TWO) { s1b += __shfl_xor_sync(FULL, s1b, o); s2b += __shfl_xor_sync(FULL, s2b, o); }
+        }
+        s1a *= invC; s2a *= invC; s1b *= invC; s2b *= invC;
+        TO *da_ = dx + row * C, *db_ = dx + row2 * C;
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
             const int c = lane + 32 * k;
-            if (c < C) dr[c] = from_f<TO>(rstd * (g[k] - s1 - xh[k] * s2));
+            if (c < C) {
+                da_[c] = from_f<TO>(rstd_a * (gva[k] - s1a - xha[k] * s2a));
+                if constexpr (TWO) { if (two) db_[c] = from_f<TO>(rstd_b * (gvb[k] - s1b - xhb[k] * s2b)); }
+            }
         }
     }
 #pragma unroll

@@ -122,6 +122,13 @@ pack_tile_kernel(const int64_t *__restrict__ idx, const uint8_t *__restrict__ ma
     const int4 *src = reinterpret_cast<const int4 *>(&slot_s[warp][0][0]);
     int4 *dst = reinterpret_cast<int4 *>(pk.slot_of + (int64_t)bt * TILE_TOK * U_MAX);
     for (int x = lane; x < TILE_TOK * U_MAX / 16; x += 32) dst[x] = src[x];
+    // transposed copy [u][token] for the scatter kernels: one 16-byte vector per (tile, union position)
+    for (int u = lane; u < U_MAX; u += 32) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int r = 0; r < TILE_TOK; ++r) w[r >> 2] |= (uint32_t)(uint8_t)slot_s[warp][r][u] << (8 * (r & 3));
+        *reinterpret_cast<uint4 *>(pk.slot_t + ((int64_t)bt * U_MAX + u) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
     if (lane == 0) {
         pk.tile_u[bt] = Uc;
         atomicMax(pk.flags + 1, U);

@@ -53,7 +53,16 @@ table_grad_smem_kernel(const T *__restrict__ dout, const I *__restrict__ inv, fl
         for (; e < e1; e += blockDim.x) {
             const int r = (int)inv[e];
             const T *dp = base + b * d_sb + el * d_se;
-            for (int c = 0; c < cw; ++c) atomicAdd(tab_s + r * cw + c, to_f(dp[c * d_sc]));
+            // all channel loads of the entry first, then the shared-memory atomics: issued one by one behind each atomic they
+            // serialised on global latency (ncu: 24 long-scoreboard stalls per issue, 122 us for 20 MB)
+            for (int cb = 0; cb < cw; cb += 8) {
+                float v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = cb + c < cw ? to_f(dp[(int64_t)(cb + c) * d_sc]) : 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (cb + c < cw) atomicAdd(tab_s + r * cw + cb + c, v[c]);
+            }
             el += blockDim.x;
             while (el >= n_per) { el -= n_per; ++b; }
         }

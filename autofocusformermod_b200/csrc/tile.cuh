@@ -26,6 +26,8 @@ struct PackView {
     int *tile_u;         // [B*T]
     int *tile_oct;       // [B*T*U_MAX]
     int8_t *slot_of;     // [B*T*16*U_MAX]  slot of (token row, union position) or -1
+    int8_t *slot_t;      // [B*T*U_MAX*16]  the same table transposed: the 16 token slots of one (tile, union position) are
+                         //                 16 contiguous bytes at (tile*U_MAX + u)*16 = inverse-list entry * 16 (scatter kernels)
     int *oct_off;        // [B*(NO+1)]      inverse lists: for key octet o the (tile, u) pairs referencing it ...
     uint32_t *oct_ent;   // [B*T*U_MAX]     ... entry = tile*U_MAX + u, ascending tile order
     uint8_t *tok_imp;    // [B*T*16]        1 = impure token (handled by the slow in-kernel path)
@@ -38,7 +40,7 @@ struct PackView {
 struct Rows4 { const void *p; int64_t sb, sh, sn; };   // strided [B,H,N,C] operand: element strides, unit inner stride
 
 struct PackLayout {
-    size_t flags, tile_u, tile_oct, slot_of, oct_off, oct_ent, tok_imp, row_imp, imp_list, rimp_list, sort_ws, total;
+    size_t flags, tile_u, tile_oct, slot_of, slot_t, oct_off, oct_ent, tok_imp, row_imp, imp_list, rimp_list, sort_ws, total;
     int T, NO, imp_cap, rimp_cap;
 };
 
@@ -54,6 +56,7 @@ inline PackLayout pack_layout(int B, int Nq, int Nk) {
     L.tile_u = o;   o += pack_align(bt * 4);
     L.tile_oct = o; o += pack_align(bt * U_MAX * 4);
     L.slot_of = o;  o += pack_align(bt * TILE_TOK * U_MAX);
+    L.slot_t = o;   o += pack_align(bt * TILE_TOK * U_MAX);
     L.oct_off = o;  o += pack_align((size_t)B * (L.NO + 1) * 4);
     L.oct_ent = o;  o += pack_align(bt * U_MAX * 4);
     L.tok_imp = o;  o += pack_align(bt * TILE_TOK);
@@ -76,6 +79,7 @@ inline PackView pack_view(void *buf, int B, int Nq, int Nk) {
     v.tile_u = reinterpret_cast<int *>(p + L.tile_u);
     v.tile_oct = reinterpret_cast<int *>(p + L.tile_oct);
     v.slot_of = reinterpret_cast<int8_t *>(p + L.slot_of);
+    v.slot_t = reinterpret_cast<int8_t *>(p + L.slot_t);
     v.oct_off = reinterpret_cast<int *>(p + L.oct_off);
     v.oct_ent = reinterpret_cast<uint32_t *>(p + L.oct_ent);
     v.tok_imp = reinterpret_cast<uint8_t *>(p + L.tok_imp);

@@ -488,6 +488,61 @@ def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None):
     return LayerNormFunction.apply(x, weight, bias, eps, out_dtype or x.dtype)
 
 
+# ---- Linear with a bandwidth-bound bias gradient -----------------------------------------------------------------------
+def col_sum(x2d):
+    """fp32 [C] column sums of a [R, C] matrix (clusten_col_sum); falls back to torch for shapes the kernel does not take."""
+    R, C = x2d.shape
+    vpt = 4 if x2d.dtype == torch.float32 else 8
+    if (x2d.dtype not in _lib.DTYPES or C % vpt or x2d.stride(1) != 1 or x2d.stride(0) % vpt or x2d.data_ptr() % 16 or R == 0
+            or R >= 2 ** 31):
+        return x2d.float().sum(0)
+    out = torch.zeros(C, dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        _call("clusten_col_sum", x2d.device, x2d.data_ptr(), out.data_ptr(), R, C, x2d.stride(0), _lib.dtype_code(x2d),
+              nbytes=x2d.element_size() * R * C)
+    return out
+
+
+class LinearFunction(Function):
+    """``F.linear`` whose backward takes the bias gradient with clusten_col_sum (one coalesced pass, fp32 accumulation) instead
+    of ATen's generic reduction; the two GEMMs of the backward stay in cuBLAS.  Autocast-aware like the native op: under
+    autocast the operands are cast once, the casts are what is saved, and the gradients come back in the parameters' dtypes."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        if torch.is_autocast_enabled():
+            dt = torch.get_autocast_dtype("cuda")
+            xc, wc = x.to(dt), weight.to(dt)
+            bc = None if bias is None else bias.to(dt)
+        else:
+            xc, wc, bc = x, weight, bias
+        with torch.autocast("cuda", enabled=False):
+            y = torch.nn.functional.linear(xc, wc, bc)
+        ctx.save_for_backward(xc, wc)
+        ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, wc = ctx.saved_tensors
+        xdt, wdt, bdt = ctx.meta
+        g2 = gy.reshape(-1, gy.shape[-1])
+        if g2.dtype != wc.dtype:
+            g2 = g2.to(wc.dtype)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = (g2 @ wc).view(xc.shape).to(xdt)
+        if ctx.needs_input_grad[1]:
+            gw = (g2.t() @ xc.reshape(-1, xc.shape[-1])).to(wdt)
+        if bdt is not None and ctx.needs_input_grad[2]:
+            gb = col_sum(g2 if g2.is_contiguous() else g2.contiguous()).to(bdt)
+        return gx, gw, gb
+
+
+def linear(x, weight, bias=None):
+    return LinearFunction.apply(x, weight, bias)
+
+
 # ---- relative-position table lookup ----------------------------------------------------------------------------------
 class TableLookupFunction(Function):
     """``tab[inverse]`` with a backward that does not go through ATen's sort-based ``index_put_(accumulate=True)``

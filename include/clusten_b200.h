@@ -191,6 +191,10 @@ int clusten_stage_prepare(const int64_t *nearest /* [B,n,nnc] */, const int64_t 
                           int64_t *member_idx, int64_t *mask64, uint8_t *mask8, int32_t *pe_idx, int32_t *bias_idx,
                           int32_t *uniq, int uniq_cap, int32_t *count, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- column sum: out[c] += sum_r x[r*ld + c] (fp32 accumulation INTO out; caller zeroes it).  The bias gradient of the
+ * backbone's Linear layers (grad_bias = grad_output.sum(0)); x fp32 / fp16 / bf16, C and ld multiples of 16 bytes. */
+int clusten_col_sum(const void *x, float *out, int64_t R, int C, int64_t ld, int dtype, void *stream);
+
 /* ---- WF plan (optional, 16-bit tensor-core kernels): per index tensor, built once and passed to clusten_wf_fwd / _bwd.
  * Holds the token processing order (kept tokens arrive in top-k order, aff.py:320-324; neighbouring tokens re-use rows
  * out of L1 when processed together) and, when M % 8 == 0, the per-octet reference lists that turn the d_f scatter of

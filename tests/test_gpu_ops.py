@@ -268,6 +268,30 @@ def test_msdetrpc(B, N, Nk, M, K, C, dtype):
     _check(_run(P.MSDETRPCFunction.apply, [idx, w, attn, val], go, dtype), ref, dtype, "MSDETRPC")
 
 
+@pytest.mark.parametrize("amp", [False, True], ids=["fp32", "bf16-autocast"])
+@pytest.mark.parametrize("shape,cin,cout", [((2, 500, 64), 64, 192), ((3, 77, 96), 96, 96), ((1000, 128), 128, 1536), ((5, 40), 40, 7)])
+def test_linear_function_matches_torch(shape, cin, cout, amp):
+    """ops.linear (F.linear with the column-sum bias gradient) against nn.functional.linear + autograd, eager and under bf16
+    autocast: output, grad_input, grad_weight, grad_bias (dtypes included)."""
+    from autofocusformermod_b200 import ops
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(*shape, generator=g).cuda()
+    w = (torch.randn(cout, cin, generator=g) * cin ** -0.5).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    go = torch.randn(*shape[:-1], cout, generator=g).cuda()
+    res = []
+    for fn in (torch.nn.functional.linear, ops.linear):
+        xi, wi, bi = (t.clone().requires_grad_(True) for t in (x, w, b))
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            y = fn(xi, wi, bi)
+        y.backward(go.to(y.dtype))
+        res.append((y.detach(), xi.grad, wi.grad, bi.grad))
+    tol = 2e-2 if amp else 1e-5
+    for a, r in zip(res[1], res[0]):
+        assert a.dtype == r.dtype and a.shape == r.shape
+        assert rel_err(a.float().cpu(), r.float().cpu()) <= tol
+
+
 def test_dtype_cast_rules_and_none_grads():
     """clusten.py:27-28,54-55,80-81,106-107: second operand follows the first; idx gets no gradient."""
     P = _ops()
