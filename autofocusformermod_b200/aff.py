@@ -16,6 +16,7 @@ Differences from the reference, none of which changes results beyond fp rounding
     table rows a stage actually references (``_TableLookup``): same per-row arithmetic, ~100x less work.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -34,9 +35,9 @@ _pre_tables = {}
 # Inference fast path: QK + bias + mask + blank token + softmax + AV in one kernel (clusten_attn_fwd) whenever autograd
 # is off.  Training keeps the signature-preserving ops (their backward is the accelerated one).
 USE_FUSED_ATTENTION = True
-FAST_LINEAR_BACKWARD = True        # Linear layers of the blocks: bias gradient by clusten_col_sum (see Linear)
-CHANNELS_LAST_STEM = True          # run the two stem convolutions + BatchNorm in NHWC (see PatchEmbed.forward)
-GRID_STRUCTURE_CACHE = True        # memoise the position-only structures of the on-grid stage (see BasicLayer._grid_structure)
+FAST_LINEAR_BACKWARD = os.environ.get("CLUSTEN_FAST_LINEAR", "1") != "0"        # Linear layers of the blocks: bias gradient by clusten_col_sum (see Linear)
+CHANNELS_LAST_STEM = os.environ.get("CLUSTEN_CHANNELS_LAST", "1") != "0"          # run the two stem convolutions + BatchNorm in NHWC (see PatchEmbed.forward)
+GRID_STRUCTURE_CACHE = os.environ.get("CLUSTEN_GRID_CACHE", "1") != "0"        # memoise the position-only structures of the on-grid stage (see BasicLayer._grid_structure)
 
 
 def rel_pos_features(pe_idx):
@@ -490,6 +491,10 @@ def graphed_training_forward(model, example, autocast_dtype=None, num_warmup_ite
     if not model.training:
         raise RuntimeError("graphed_training_forward captures the training step: call model.train() first")
     wrapped = _Features(model)
+    # return the caching allocator's idle blocks first: inside a capture the allocator may only grow its pool (cudaMalloc);
+    # having to release cached blocks mid-capture (cudaFree) would invalidate it
+    torch.cuda.synchronize(example.device)
+    torch.cuda.empty_cache()
     with torch.autocast("cuda", dtype=autocast_dtype or torch.bfloat16, enabled=autocast_dtype is not None, cache_enabled=False):
         return torch.cuda.make_graphed_callables(wrapped, (example.detach().clone(),), num_warmup_iters=num_warmup_iters)
 
@@ -514,6 +519,7 @@ class GraphedAFF:
                 self._run()
         torch.cuda.current_stream(example.device).wait_stream(side)
         torch.cuda.synchronize(example.device)
+        torch.cuda.empty_cache()          # (see graphed_training_forward: no cudaFree may be needed during the capture)
         from .ops import kernel_launches
         self.graph = torch.cuda.CUDAGraph()
         k0 = kernel_launches()

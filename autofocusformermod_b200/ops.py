@@ -48,6 +48,25 @@ def stop_kernel_timer():
     return [(n, a.elapsed_time(b), nb) for n, a, b, nb in t["events"]]
 
 
+_DEBUG_CAPTURE = __import__("os").environ.get("CLUSTEN_DEBUG_CAPTURE", "0") == "1"
+_cudart = None
+
+
+def _capture_status(tag):
+    """Debug aid (CLUSTEN_DEBUG_CAPTURE=1): report the first point at which the current stream's capture turns invalid."""
+    global _cudart
+    if not _DEBUG_CAPTURE:
+        return
+    import ctypes
+    if _cudart is None:
+        _cudart = ctypes.CDLL("libcudart.so.12")
+    st = ctypes.c_int(0)
+    rc = _cudart.cudaStreamIsCapturing(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), ctypes.byref(st))
+    if st.value == 2 or rc != 0:
+        print(f"[capture] INVALID at {tag} (rc={rc}, status={st.value})", flush=True)
+        raise RuntimeError(f"capture invalidated before/at {tag}")
+
+
 _launch_count = 0
 
 
@@ -67,6 +86,7 @@ def _call(name, dev, *args, nbytes=0):
     global _launch_count
     _launch_count += 1
     fn = getattr(_lib.lib(), name)
+    _capture_status("before " + name)
     timed = _timer is not None and _timer["name"] in (name, "*")
     if timed:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -510,14 +530,17 @@ class LinearFunction(Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
+        _capture_status("linear: entry")
         if torch.is_autocast_enabled():
             dt = torch.get_autocast_dtype("cuda")
             xc, wc = x.to(dt), weight.to(dt)
             bc = None if bias is None else bias.to(dt)
         else:
             xc, wc, bc = x, weight, bias
+        _capture_status("linear: after casts")
         with torch.autocast("cuda", enabled=False):
             y = torch.nn.functional.linear(xc, wc, bc)
+        _capture_status(f"linear: after F.linear {tuple(xc.shape)} x {tuple(wc.shape)} {xc.dtype}")
         ctx.save_for_backward(xc, wc)
         ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype)
         return y

@@ -465,7 +465,7 @@ def test_mask_aware_pack_keeps_padded_clusters_on_the_tile_path(n, m, nbhd):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("U,CH,shape,permuted", [(700, 3, (2, 500, 48), True), (700, 3, (2, 500, 48), False), (5000, 16, (1, 300, 48), True),
-                                                 (37, 4, (3, 200, 48), False), (1, 2, (1, 5, 8), False)])
+                                                 (37, 4, (3, 200, 48), False), (1, 2, (1, 5, 8), False), (9000, 2, (1, 400, 48), False)])
 def test_table_lookup(U, CH, shape, permuted, dtype):
     """tab[inverse] (aff.py:129-132 restricted to the referenced table rows) and its segment-sum gradient against torch
     indexing in fp32; the permuted case is the [B,H,N,M] gradient layout of the attention bias."""
