@@ -6,3 +6,8 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 timeout 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench exit $?"; cat gpurun_out/bench_default.json; tail -3 gpurun_out/bench_default.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref exit $?"; cut -c1-300 gpurun_out/bench_reference.json
 timeout 900 python bench.py --no-cpu-baseline --workload aff_tiny15_train_b32_512_bf16 --steps 5 --warmup 3 > gpurun_out/bench_tiny_train.json 2> gpurun_out/bench_tiny_train.err; echo "tiny exit $?"; cut -c1-300 gpurun_out/bench_tiny_train.json
+# launch list of the default bench command (a window of ~2 passes: graph replays + the eager roofline pass)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 5000 -c 2400 --csv --log-file gpurun_out/launches_default.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
+echo "ncu launches exit $?"
+for sh in small_s0 mini_s0; do timeout 300 python benchmarks/op_bench.py --shape $sh --dtype bf16 > gpurun_out/op_${sh}_bf16_final.log 2>&1; done
+tail -14 gpurun_out/op_small_s0_bf16_final.log
