@@ -15,6 +15,8 @@ Differences from the reference, none of which changes results beyond fp rounding
   * the [1023^2, heads] bias table (aff.py:129) and the PointConv weight table (aff.py:346) are evaluated only at the
     table rows a stage actually references (``_TableLookup``): same per-row arithmetic, ~100x less work.
 """
+import contextlib
+import gc
 import math
 import os
 
@@ -470,6 +472,25 @@ class AFF(nn.Module):
         return GraphedAFF(self, example, autocast_dtype)
 
 
+@contextlib.contextmanager
+def _quiet_capture(device):
+    """Conditions for a CUDA-graph capture: no idle allocator blocks (the allocator may only GROW its pool inside a capture)
+    and no Python garbage collection while it runs.  A dead reference cycle from earlier work can own CUDA graphs, events or
+    memory pools; if the cyclic collector happens to run mid-capture, their destructors (cudaGraphExecDestroy, cudaFree) are
+    'unsafe' calls that invalidate a global-mode capture -- seen as an order-dependent failure of the first kernel launch
+    after the collection.  torch.cuda.graph used to collect before capturing; it no longer does by default."""
+    torch.cuda.synchronize(device)
+    gc.collect()
+    torch.cuda.empty_cache()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was_enabled:
+            gc.enable()
+
+
 class _Features(nn.Module):
     """The backbone's feature tensors as a tuple (res2, res3, ...): what torch.cuda.make_graphed_callables can carry."""
 
@@ -491,11 +512,8 @@ def graphed_training_forward(model, example, autocast_dtype=None, num_warmup_ite
     if not model.training:
         raise RuntimeError("graphed_training_forward captures the training step: call model.train() first")
     wrapped = _Features(model)
-    # return the caching allocator's idle blocks first: inside a capture the allocator may only grow its pool (cudaMalloc);
-    # having to release cached blocks mid-capture (cudaFree) would invalidate it
-    torch.cuda.synchronize(example.device)
-    torch.cuda.empty_cache()
-    with torch.autocast("cuda", dtype=autocast_dtype or torch.bfloat16, enabled=autocast_dtype is not None, cache_enabled=False):
+    with _quiet_capture(example.device), torch.autocast("cuda", dtype=autocast_dtype or torch.bfloat16,
+                                                        enabled=autocast_dtype is not None, cache_enabled=False):
         return torch.cuda.make_graphed_callables(wrapped, (example.detach().clone(),), num_warmup_iters=num_warmup_iters)
 
 
@@ -518,13 +536,12 @@ class GraphedAFF:
             for _ in range(2):                               # warm-up: lazy one-time initialisation happens outside the capture
                 self._run()
         torch.cuda.current_stream(example.device).wait_stream(side)
-        torch.cuda.synchronize(example.device)
-        torch.cuda.empty_cache()          # (see graphed_training_forward: no cudaFree may be needed during the capture)
         from .ops import kernel_launches
         self.graph = torch.cuda.CUDAGraph()
-        k0 = kernel_launches()
-        with torch.cuda.graph(self.graph):
-            self.static_out = self._run()
+        with _quiet_capture(example.device):
+            k0 = kernel_launches()
+            with torch.cuda.graph(self.graph):
+                self.static_out = self._run()
         self.launches_per_replay = kernel_launches() - k0   # libclusten kernels inside one replay
 
     def _run(self):

@@ -12,6 +12,7 @@
 // hold consecutive neighbours of one token = distinct rows, so intra-warp conflicts are rare) and flushes the non-zero
 // entries with one global fp32 atomic each.  Large tables (U*CH floats > 48 KB) use global atomics directly.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -198,7 +199,8 @@ template <typename T, typename I>
 static int launch_table_grad(const T *dout, const I *inv, float *dtab, int64_t n, int U, const int *U_dev, int CH, int64_t n_per,
                              int64_t d_sb, int64_t d_se, int64_t d_sc, cudaStream_t st) {
     if (n == 0) return 0;
-    if (U_dev || U <= TGS_HIST_CAP) {
+    static const bool old_path = getenv("CLUSTEN_TG_OLD") != nullptr;        // diagnostics: the shared-memory-atomic variant
+    if (!old_path && (U_dev || U <= TGS_HIST_CAP)) {
         // counting-sort variant (no floating-point shared-memory atomics): histogram of up to TGS_HIST_CAP rows, <= 8 channels
         // of <= 8192 entries in row order; tables that turn out larger on the device fall back to global REDs inside the kernel
         const int hist_cap = std::min(U, TGS_HIST_CAP);
