@@ -106,7 +106,7 @@ class LayerNorm(nn.LayerNorm):
             return super().forward(x)
         out_dtype = x.dtype
         if torch.is_autocast_enabled():
-            out_dtype = torch.get_autocast_gpu_dtype() if self.to_autocast_dtype else torch.float32
+            out_dtype = torch.get_autocast_dtype("cuda") if self.to_autocast_dtype else torch.float32
         return layer_norm(x, self.weight, self.bias, self.eps, out_dtype)
 
 
@@ -540,7 +540,9 @@ class GraphedAFF:
         self.graph = torch.cuda.CUDAGraph()
         with _quiet_capture(example.device):
             k0 = kernel_launches()
-            with torch.cuda.graph(self.graph):
+            # under torch.distributed the NCCL watchdog thread polls CUDA events: its calls must not count against this capture
+            mode = "thread_local" if (torch.distributed.is_available() and torch.distributed.is_initialized()) else "global"
+            with torch.cuda.graph(self.graph, capture_error_mode=mode):
                 self.static_out = self._run()
         self.launches_per_replay = kernel_launches() - k0   # libclusten kernels inside one replay
 
