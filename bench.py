@@ -136,7 +136,7 @@ def run_reference(args, wl, rank, world):
     dt = time.perf_counter() - t0
     val = CPU_SAMPLE_IMAGES * args.steps / dt
     sample = f"{CPU_SAMPLE_IMAGES} images of {wl['H']}x{wl['W']} per step, fp32, {wl['mode']}"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "aff_backbone_images_per_sec", "value": round(val, 4), "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -144,10 +144,33 @@ def run_reference(args, wl, rank, world):
         "cpu_baseline": {"value": round(val, 4), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(val, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries print there too (NCCL's version banner under torchrun), so
+    file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -396,7 +419,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
