@@ -62,6 +62,24 @@ def test_argument_errors_without_gpu(lib):
     assert lib.clusten_csr_workspace_bytes(2, 64, 48, 64) >= 4 * 2 * 64 * 48 * 4
 
 
+def test_argument_errors_of_the_structure_builders(lib):
+    """Plans / packs / helper kernels reject bad arguments before any CUDA call (still no GPU here)."""
+    assert lib.clusten_wf_plan_bytes(2, 100, 48, 400) > lib.clusten_wf_plan_bytes(1, 100, 48, 400) >= 256
+    assert lib.clusten_pack_bytes(2, 100, 48, 400) > lib.clusten_pack_bytes(1, 100, 48, 400) >= 256
+    rc = lib.clusten_wf_plan_build(1, 2, 100, 9, 400, 1, 1 << 30, None)
+    assert rc == -3 and b"M % 8" in lib.clusten_last_error()                 # no octet structure
+    rc = lib.clusten_wf_plan_build(1, 2, 100, 48, 400, 1, 16, None)
+    assert rc == -4                                                         # plan buffer too small
+    rc = lib.clusten_pack_build(1, None, 2, 100, 48, 400, 1, 16, None)
+    assert rc == -4
+    rc = lib.clusten_col_sum(1, 1, 10, 12, 12, 2, None)
+    assert rc == -3                                                         # C not a multiple of 8 for a 16-bit type
+    rc = lib.clusten_blank_grad(1, 1, 1, 1, 1, 1, 2, 2, 16, 12, 0, 0, 0, 0, 0, 0, 2, None)
+    assert rc == -3                                                         # C % 8 != 0
+    rc = lib.clusten_table_grad(1, 1, 0, 1, 10, 0, None, 4, 10, 0, 0, 0, 0, None)
+    assert rc == -1                                                         # U <= 0
+
+
 def test_ops_refuse_cpu_tensors():
     """No CPU fallback: CHECK_CUDA of clustenqk_cuda.cpp:21."""
     from autofocusformermod_b200 import CLUSTENQKFunction, WEIGHTEDGATHERFunction, knn_keops
