@@ -32,6 +32,8 @@ SIGNATURES = {
     "clusten_attn_fwd": (_I, [_P] * 13 + [_I] * 6 + [_L] * 12 + [_I, _P]),
     "clusten_attn_bwd": (_I, [_P] * 18 + [_I] * 6 + [_L] * 18 + [_I, _P]),
     "clusten_col_sum": (_I, [_P, _P, _L, _I, _L, _I, _P]),
+    "clusten_scale_residual_fwd": (_I, [_P] * 5 + [_L, _L, _I, _I, _I, _I, _P]),
+    "clusten_scale_residual_bwd": (_I, [_P] * 6 + [_L, _L, _I, _I, _I, _P]),
     "clusten_blank_grad": (_I, [_P] * 6 + [_I] * 4 + [_L] * 6 + [_I, _P]),
     "clusten_scatter_rows": (_I, [_P] * 6 + [_I] * 6 + [_L] * 9 + [_I, _P]),
     "clusten_layer_norm_fwd": (_I, [_P] * 6 + [_L, _I, _c.c_float, _I, _I, _P]),

@@ -25,7 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .ops import (CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction, cluster_attention_core, cluster_attention_fused,
-                  layer_norm, linear, table_lookup)
+                  layer_norm, linear, scale_residual, table_lookup)
 from .point_utils import knn_keops, merge_select, space_filling_cluster, stage_prepare
 
 # aff.py:17-19: the relative-position table covers inputs up to 2048 px (stem grid 512)
@@ -40,6 +40,8 @@ USE_FUSED_ATTENTION = True
 FAST_LINEAR_BACKWARD = os.environ.get("CLUSTEN_FAST_LINEAR", "1") != "0"        # Linear layers of the blocks: bias gradient by clusten_col_sum (see Linear)
 CHANNELS_LAST_STEM = os.environ.get("CLUSTEN_CHANNELS_LAST", "1") != "0"          # run the two stem convolutions + BatchNorm in NHWC (see PatchEmbed.forward)
 GRID_STRUCTURE_CACHE = os.environ.get("CLUSTEN_GRID_CACHE", "1") != "0"        # memoise the position-only structures of the on-grid stage (see BasicLayer._grid_structure)
+FUSED_RESIDUAL = os.environ.get("CLUSTEN_FUSED_RESIDUAL", "1") != "0"           # residual + layer scale + stochastic depth in one kernel (see ClusterTransformerBlock._residual)
+NATIVE_WEIGHT_NET_NORM = os.environ.get("CLUSTEN_WEIGHT_NET_NORM", "1") != "0"   # LayerNorm(4) of the merge's weight_net through clusten_layer_norm_* (see ClusterMerging)
 
 
 def rel_pos_features(pe_idx):
@@ -142,6 +144,14 @@ class DropPath(nn.Module):
         mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
         return x * mask.div_(keep)
 
+    def sample_scale(self, x):
+        """The per-sample factor bernoulli(keep) / keep as fp32 [B] (None when the layer is the identity) -- what forward
+        multiplies by, for callers that fold it into the residual kernel (ops.scale_residual)."""
+        if self.drop_prob == 0.0 or not self.training:
+            return None
+        keep = 1.0 - self.drop_prob
+        return torch.empty(x.shape[0], dtype=torch.float32, device=x.device).bernoulli_(keep).div_(keep)
+
 
 class Mlp(nn.Module):
     def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
@@ -240,9 +250,16 @@ class ClusterTransformerBlock(nn.Module):
 
     def forward(self, feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup=None, fused_ctx=None):
         a = self.attn(self.norm1(feat), member_idx, cluster_mask, pe_idx, global_attn, pe_lookup, fused_ctx)
-        feat = feat + self.drop_path(self.gamma1 * a if self.layer_scale else a)
+        feat = self._residual(feat, a, self.gamma1 if self.layer_scale else None)                    # aff.py:230
         m = self.mlp(self.norm2(feat))
-        return feat + self.drop_path(self.gamma2 * m if self.layer_scale else m)
+        return self._residual(feat, m, self.gamma2 if self.layer_scale else None)                    # aff.py:236
+
+    def _residual(self, feat, x, gamma):
+        """``feat + drop_path(gamma * x)``: one kernel (ops.scale_residual) instead of up to three broadcasting ATen passes."""
+        if FUSED_RESIDUAL and feat.is_cuda and isinstance(self.drop_path, (DropPath, nn.Identity)):
+            scale = self.drop_path.sample_scale(x) if isinstance(self.drop_path, DropPath) else None
+            return scale_residual(feat, x, gamma, scale)
+        return feat + self.drop_path(gamma * x if gamma is not None else x)
 
 
 class ClusterMerging(nn.Module):
@@ -253,7 +270,9 @@ class ClusterMerging(nn.Module):
         super().__init__()
         self.dim, self.pos_dim, self.alpha, self.ds_rate, self.reserve_on = dim, 2, alpha, ds_rate, reserve_on
         inner_ch = 4
-        self.weight_net = nn.Sequential(nn.Linear(self.pos_dim + 3, inner_ch, bias=True), nn.LayerNorm(inner_ch), nn.GELU())
+        # LayerNorm over 4 channels of ~65 k table rows: ATen's gamma / beta backward spent 0.26 ms per merge on it
+        wn_norm = LayerNorm if NATIVE_WEIGHT_NET_NORM else nn.LayerNorm
+        self.weight_net = nn.Sequential(nn.Linear(self.pos_dim + 3, inner_ch, bias=True), wn_norm(inner_ch), nn.GELU())
         self.norm = _inner_norm(norm_layer, inner_ch * dim)
         self.linear = Linear(dim * inner_ch, out_dim)
 

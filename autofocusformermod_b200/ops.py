@@ -508,6 +508,90 @@ def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None):
     return LayerNormFunction.apply(x, weight, bias, eps, out_dtype or x.dtype)
 
 
+# ---- residual + layer scale + stochastic depth -----------------------------------------------------------------------
+def _residual_out_dtype(res, x, gamma):
+    """Type promotion of ``res + x * gamma * scale`` as ATen does it (gamma is a dimensioned tensor: fp32 gamma lifts 16-bit x)."""
+    dt = torch.promote_types(res.dtype, x.dtype)
+    return dt if gamma is None else torch.promote_types(dt, gamma.dtype)
+
+
+def scale_residual_supported(res, x, gamma, sample_scale):
+    if not (res.is_cuda and res.dim() >= 2 and res.shape == x.shape and res.is_contiguous() and x.is_contiguous()):
+        return False
+    C = res.shape[-1]
+    odt = _residual_out_dtype(res, x, gamma)
+    f32 = torch.float32
+    combo = (res.dtype, x.dtype, odt)
+    ok = combo == (f32, f32, f32) or (x.dtype in (torch.float16, torch.bfloat16) and (
+        combo == (f32, x.dtype, f32) or combo == (x.dtype, x.dtype, x.dtype) or combo == (x.dtype, x.dtype, f32)))
+    if gamma is not None and (gamma.dtype != f32 or gamma.shape != (C,)):
+        return False
+    if sample_scale is not None and (sample_scale.dtype != f32 or sample_scale.shape != (res.shape[0],)):
+        return False
+    return bool(ok and C % 4 == 0 and C <= 1024 and res.shape[0] <= 65535 and res.numel() > 0
+                and res.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0)
+
+
+class ScaleResidualFunction(Function):
+    """``res + x * gamma * sample_scale`` in one pass (clusten_scale_residual_fwd / _bwd): the residual lines of the block,
+    backbone/aff.py:230,236, with the layer scale (gamma [C] or None) and the per-sample stochastic-depth factor
+    (sample_scale [B] = bernoulli(keep) / keep or None) folded in.  d_gamma accumulates with fp32 atomics."""
+
+    @staticmethod
+    def forward(ctx, res, x, gamma, sample_scale):
+        dev = _lib.require_cuda(res, x)
+        B, C = res.shape[0], res.shape[-1]
+        rows = res.numel() // (B * C)
+        odt = _residual_out_dtype(res, x, gamma)
+        out = torch.empty(res.shape, dtype=odt, device=dev)
+        g = None if gamma is None else gamma.detach().contiguous()
+        with torch.cuda.device(dev):
+            _call("clusten_scale_residual_fwd", dev, res.data_ptr(), x.data_ptr(), _lib.ptr(g), _lib.ptr(sample_scale),
+                  out.data_ptr(), B, rows, C, _lib.dtype_code(res), _lib.dtype_code(x), _lib.DTYPES[odt],
+                  nbytes=res.numel() * (res.element_size() + x.element_size() + out.element_size()))
+        need_dgamma = gamma is not None and ctx.needs_input_grad[2]
+        ctx.save_for_backward(x if need_dgamma else None, g, sample_scale)
+        ctx.meta = (res.dtype, x.dtype, B, rows, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, g, s = ctx.saved_tensors
+        rdt, xdt, B, rows, C = ctx.meta
+        dev = d_out.device
+        d_out = d_out.contiguous()
+        d_res = d_x = d_gamma = None
+        if ctx.needs_input_grad[0]:
+            d_res = d_out if d_out.dtype == rdt else d_out.to(rdt)
+        want_x, want_g = ctx.needs_input_grad[1], x is not None
+        if want_x or want_g:
+            if g is None and s is None and want_x:
+                d_x = d_out if d_out.dtype == xdt else d_out.to(xdt)
+            else:
+                if want_x:
+                    d_x = torch.empty(d_out.shape, dtype=xdt, device=dev)
+                if want_g:
+                    d_gamma = torch.zeros(C, dtype=torch.float32, device=dev)
+                with torch.cuda.device(dev):
+                    _call("clusten_scale_residual_bwd", dev, d_out.data_ptr(), _lib.ptr(x), _lib.ptr(g), _lib.ptr(s), _lib.ptr(d_x),
+                          _lib.ptr(d_gamma), B, rows, C, _lib.dtype_code(d_out), _lib.DTYPES[xdt],
+                          nbytes=d_out.numel() * (d_out.element_size() + (2 if want_g else 1) * (4 if xdt == torch.float32 else 2)))
+        return d_res, d_x, d_gamma, None
+
+
+def scale_residual(res, x, gamma=None, sample_scale=None):
+    """``res + x * gamma[c] * sample_scale[b]``; shapes / dtypes the kernel does not take go through the op-by-op formulation."""
+    if gamma is None and sample_scale is None:
+        return res + x
+    if scale_residual_supported(res, x, gamma, sample_scale):
+        return ScaleResidualFunction.apply(res, x, gamma, sample_scale)
+    if gamma is not None:
+        x = gamma * x
+    if sample_scale is not None:
+        x = x * sample_scale.to(x.dtype).view(-1, *([1] * (x.dim() - 1)))
+    return res + x
+
+
 # ---- Linear with a bandwidth-bound bias gradient -----------------------------------------------------------------------
 def col_sum(x2d):
     """fp32 [C] column sums of a [R, C] matrix (clusten_col_sum); falls back to torch for shapes the kernel does not take."""

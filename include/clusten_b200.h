@@ -195,6 +195,19 @@ int clusten_stage_prepare(const int64_t *nearest /* [B,n,nnc] */, const int64_t 
  * backbone's Linear layers (grad_bias = grad_output.sum(0)); x fp32 / fp16 / bf16, C and ld multiples of 16 bytes. */
 int clusten_col_sum(const void *x, float *out, int64_t R, int C, int64_t ld, int dtype, void *stream);
 
+/* ---- residual add with layer scale and stochastic depth: out[b,i,c] = res[b,i,c] + x[b,i,c] * gamma[c] * sample_scale[b]
+ * -- the `x = shortcut + drop_path(gamma * x)` lines of the reference block (backbone/aff.py:230,236; DropPath = timm 0.6.12).
+ * res / x / out contiguous [B, rows, C], C % 4 == 0, C <= 1024; gamma fp32 [C] or NULL (= 1), sample_scale fp32 [B] or
+ * NULL (= 1).  dtype triples (res, x, out): (f32,f32,f32) (f32,h,f32) (h,h,h) (h,h,f32) for h = fp16 / bf16; products and
+ * the sum are rounded one by one in fp32 (the fp32 case equals the op-by-op ATen result bit for bit).
+ * Backward: d_x = d_out * gamma * sample_scale (x's dtype; d_x may be NULL), d_gamma[c] += sum d_out * x * sample_scale
+ * (fp32, accumulated INTO d_gamma with one atomic per CTA and channel; NULL = not wanted, then x may be NULL too);
+ * d_res = d_out needs no kernel.  (d_out, x) dtypes: (f32,f32) (f32,h) (h,h). */
+int clusten_scale_residual_fwd(const void *res, const void *x, const float *gamma, const float *sample_scale, void *out,
+                               int64_t B, int64_t rows, int C, int res_dtype, int x_dtype, int out_dtype, void *stream);
+int clusten_scale_residual_bwd(const void *d_out, const void *x, const float *gamma, const float *sample_scale, void *d_x,
+                               float *d_gamma, int64_t B, int64_t rows, int C, int g_dtype, int x_dtype, void *stream);
+
 /* ---- WF plan (optional, 16-bit tensor-core kernels): per index tensor, built once and passed to clusten_wf_fwd / _bwd.
  * Holds the token processing order (kept tokens arrive in top-k order, aff.py:320-324; neighbouring tokens re-use rows
  * out of L1 when processed together) and, when M % 8 == 0, the per-octet reference lists that turn the d_f scatter of

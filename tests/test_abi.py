@@ -78,6 +78,12 @@ def test_argument_errors_of_the_structure_builders(lib):
     assert rc == -3                                                         # C % 8 != 0
     rc = lib.clusten_table_grad(1, 1, 0, 1, 10, 0, None, 4, 10, 0, 0, 0, 0, None)
     assert rc == -1                                                         # U <= 0
+    rc = lib.clusten_scale_residual_fwd(16, 16, None, None, 16, 2, 10, 6, 0, 0, 0, None)
+    assert rc == -3 and b"C % 4" in lib.clusten_last_error()                 # channel count not a multiple of 4
+    rc = lib.clusten_scale_residual_fwd(16, 16, None, None, 16, 2, 10, 8, 2, 0, 0, None)
+    assert rc == -2                                                         # (bf16 res, fp32 x) is not a supported pair
+    rc = lib.clusten_scale_residual_bwd(16, None, None, None, None, None, 2, 10, 8, 0, 0, None)
+    assert rc == -1                                                         # neither d_x nor d_gamma wanted
 
 
 def test_ops_refuse_cpu_tensors():

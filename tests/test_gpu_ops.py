@@ -542,7 +542,7 @@ def test_fused_attention_core_backward(n, m, nbhd, kind, H, C, dtype):
 
 @pytest.mark.parametrize("xdt,ydt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16)],
                          ids=["f32", "bf16-f32", "bf16-bf16"])
-@pytest.mark.parametrize("R,C", [(1000, 32), (513, 96), (64, 384), (7, 1024), (300, 100), (5, 8)])
+@pytest.mark.parametrize("R,C", [(1000, 32), (513, 96), (64, 384), (7, 1024), (300, 100), (5, 8), (65025, 4)])
 def test_layer_norm(R, C, xdt, ydt):
     """clusten_layer_norm_fwd / _bwd (one warp per token row) against torch.nn.functional.layer_norm in fp32."""
     from autofocusformermod_b200 import ops
@@ -563,6 +563,72 @@ def test_layer_norm(R, C, xdt, ydt):
     assert rel_err(xc.grad.float().cpu(), xr.grad) <= tol
     assert rel_err(wc.grad.cpu(), wr.grad) <= max(tol, 2e-5)
     assert rel_err(bc.grad.cpu(), br.grad) <= max(tol, 2e-5)
+
+
+@pytest.mark.parametrize("use_gamma,use_scale", [(True, True), (True, False), (False, True)], ids=["gamma+drop", "gamma", "drop"])
+@pytest.mark.parametrize("rdt,xdt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16),
+                                     (torch.float16, torch.float16)], ids=["f32", "f32+bf16", "bf16", "f16"])
+@pytest.mark.parametrize("B,rows,C", [(3, 77, 96), (2, 1000, 32), (1, 5, 1024), (5, 333, 64)])
+def test_scale_residual(B, rows, C, rdt, xdt, use_gamma, use_scale):
+    """clusten_scale_residual_fwd / _bwd (res + x * gamma * sample_scale, aff.py:230,236 with timm's DropPath folded in) against
+    the op-by-op torch formulation: bit-exact in fp32, 16-bit within 1e-2; gradients of res, x and gamma."""
+    from autofocusformermod_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + rows + C)
+    res = torch.randn(B, rows, C, generator=g).to(rdt)
+    x = torch.randn(B, rows, C, generator=g).to(xdt)
+    gamma = (torch.randn(C, generator=g) * 0.5) if use_gamma else None
+    scale = (torch.bernoulli(torch.full((B,), 0.6), generator=g) / 0.6) if use_scale else None
+    if scale is not None and B > 1:
+        scale[0], scale[-1] = 0.0, 1 / 0.6                      # both outcomes present
+    up = torch.randn(B, rows, C, generator=g)
+
+    def leaf(t):
+        return None if t is None else t.detach().cuda().requires_grad_(t.is_floating_point())
+
+    rc, xc, gc = leaf(res), leaf(x), leaf(gamma)
+    sc = None if scale is None else scale.cuda()
+    assert ops.scale_residual_supported(rc, xc, gc, sc)
+    out = ops.scale_residual(rc, xc, gc, sc)
+    want_dtype = torch.float32 if (use_gamma or rdt == torch.float32) else rdt
+    assert out.dtype == want_dtype and out.shape == res.shape
+    out.backward(up.cuda().to(out.dtype))
+    # reference: the same formula in fp32 on the (rounded) inputs
+    rr, xr = res.float().requires_grad_(True), x.float().requires_grad_(True)
+    gr = None if gamma is None else gamma.clone().requires_grad_(True)
+    t = xr if gr is None else gr * xr
+    if scale is not None:
+        t = t * scale.view(B, 1, 1)
+    ref = rr + t
+    ref.backward(up.to(out.dtype).float())
+    torch.cuda.synchronize()
+    if (rdt, xdt) == (torch.float32, torch.float32):
+        assert torch.equal(out.cpu(), ref.detach()), "fp32 forward must equal the op-by-op result bit for bit"
+        assert torch.equal(xc.grad.cpu(), xr.grad)
+    tol = 1e-6 if (rdt, xdt) == (torch.float32, torch.float32) else 1e-2
+    assert rel_err(out.float().cpu(), ref.detach()) <= tol
+    assert rel_err(rc.grad.float().cpu(), rr.grad) <= tol
+    assert rel_err(xc.grad.float().cpu(), xr.grad) <= tol
+    if gr is not None:
+        assert gc.grad.dtype == torch.float32
+        assert rel_err(gc.grad.cpu(), gr.grad) <= max(tol, 2e-5)
+
+
+def test_scale_residual_falls_back_for_shapes_the_kernel_does_not_take():
+    """Non-contiguous operands and odd channel counts go through the torch formulation with the same result."""
+    from autofocusformermod_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    res = torch.randn(2, 50, 30, generator=g).cuda()
+    x = torch.randn(2, 50, 30, generator=g).cuda()
+    gamma = torch.randn(30, generator=g).cuda()
+    scale = torch.tensor([0.0, 2.0]).cuda()
+    assert not ops.scale_residual_supported(res, x, gamma, scale)               # C % 4 != 0
+    out = ops.scale_residual(res, x, gamma, scale)
+    assert torch.equal(out, res + (gamma * x) * scale.view(2, 1, 1))
+    res2 = torch.randn(2, 64, 50, generator=g).cuda().transpose(1, 2)           # [2, 50, 64] non-contiguous
+    x2 = torch.randn(2, 50, 64, generator=g).cuda()
+    assert not ops.scale_residual_supported(res2, x2, None, scale)
+    assert torch.equal(ops.scale_residual(res2, x2, None, scale), res2 + x2 * scale.view(2, 1, 1))
+    assert torch.equal(ops.scale_residual(res2, x2), res2 + x2)
 
 
 @pytest.mark.parametrize("n,m,nbhd,hw", [(4096, 8, 48, 64), (2003, 8, 48, 64), (1540, 24, 144, 64), (655, 8, 48, 128)])
