@@ -614,17 +614,14 @@ class LinearFunction(Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        _capture_status("linear: entry")
         if torch.is_autocast_enabled():
             dt = torch.get_autocast_dtype("cuda")
             xc, wc = x.to(dt), weight.to(dt)
             bc = None if bias is None else bias.to(dt)
         else:
             xc, wc, bc = x, weight, bias
-        _capture_status("linear: after casts")
         with torch.autocast("cuda", enabled=False):
             y = torch.nn.functional.linear(xc, wc, bc)
-        _capture_status(f"linear: after F.linear {tuple(xc.shape)} x {tuple(wc.shape)} {xc.dtype}")
         ctx.save_for_backward(xc, wc)
         ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype)
         return y

@@ -2,7 +2,7 @@
 stage shape: per-entry device time, algorithmic bytes, achieved GB/s.  Index tensors come from the reference pipeline
 (oracle clustering + kNN on a random token subset), so padded last clusters (n % m != 0) show their real cost.
 
-    python benchmarks/attn_bench.py --n 655 --heads 8 --batch 32 [--m 8 --nbhd 48 --c 32 --dtype bf16 --iters 10]
+    python benchmarks/attn_bench.py --n 655 --heads 8 --batch 32 [--m 8 --nbhd 48 --c 32 --dtype bf16|f16|f32 --iters 10]   (f32: inference forward only)
 """
 import argparse
 import json
@@ -30,7 +30,9 @@ def main():
     args = ap.parse_args()
     from autofocusformermod_b200 import ops
     from oracle import inputs
-    dt = {"bf16": torch.bfloat16, "f16": torch.float16}[args.dtype]
+    dt = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[args.dtype]
+    if dt == torch.float32:
+        args.fwd_only = True                              # fp32 runs the fused kernel on the inference path only
     B, N, H, C = args.batch, args.n, args.heads, args.c
     _, nb, mask, pe_idx = inputs.structured_neighbourhood(1, N, args.grid, args.grid, args.m, args.nbhd, seed=0)
     M = nb.shape[-1]
@@ -52,9 +54,14 @@ def main():
         flush.add_(1)
         if it >= 3:
             ops.start_kernel_timer("*")
-        out = ops.cluster_attention_core(q, kv, tab, bk, bv, idx, bias_idx, mask8)
-        if not args.fwd_only:
-            out.backward(go)
+        if dt == torch.float32:
+            with torch.no_grad():
+                kvp = kv.permute(3, 0, 2, 1, 4)
+                ops.cluster_attention_fused(q.permute(0, 2, 1, 3), kvp[0], kvp[1], idx, tab, bias_idx, mask8, bk, bv)
+        else:
+            out = ops.cluster_attention_core(q, kv, tab, bk, bv, idx, bias_idx, mask8)
+            if not args.fwd_only:
+                out.backward(go)
         if it >= 3:
             for name, ms, nbytes in ops.stop_kernel_timer():
                 e = per.setdefault(name, [0.0, 0, 0])
