@@ -25,7 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .ops import (CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction, cluster_attention_core, cluster_attention_fused,
-                  layer_norm, linear, scale_residual, table_lookup)
+                  layer_norm, linear, scale_residual, table_linear, table_linear_supported, table_lookup)
 from .point_utils import knn_keops, merge_select, space_filling_cluster, stage_prepare
 
 # aff.py:17-19: the relative-position table covers inputs up to 2048 px (stem grid 512)
@@ -40,6 +40,7 @@ USE_FUSED_ATTENTION = True
 FAST_LINEAR_BACKWARD = os.environ.get("CLUSTEN_FAST_LINEAR", "1") != "0"        # Linear layers of the blocks: bias gradient by clusten_col_sum (see Linear)
 CHANNELS_LAST_STEM = os.environ.get("CLUSTEN_CHANNELS_LAST", "1") != "0"          # run the two stem convolutions + BatchNorm in NHWC (see PatchEmbed.forward)
 GRID_STRUCTURE_CACHE = os.environ.get("CLUSTEN_GRID_CACHE", "1") != "0"        # memoise the position-only structures of the on-grid stage (see BasicLayer._grid_structure)
+NATIVE_TABLE_LINEAR = os.environ.get("CLUSTEN_TABLE_LINEAR", "1") != "0"      # pos_embed = Linear(5, heads) over the referenced table rows by clusten_table_linear_* (see TableLinear)
 FUSED_RESIDUAL = os.environ.get("CLUSTEN_FUSED_RESIDUAL", "1") != "0"           # residual + layer scale + stochastic depth in one kernel (see ClusterTransformerBlock._residual)
 NATIVE_WEIGHT_NET_NORM = os.environ.get("CLUSTEN_WEIGHT_NET_NORM", "1") != "0"   # LayerNorm(4) of the merge's weight_net through clusten_layer_norm_* (see ClusterMerging)
 
@@ -89,7 +90,7 @@ class _TableLookup:
         return out
 
     def __call__(self, net):
-        t = net(self.features)                            # [U, ch]
+        t = net(self.features, self.count) if isinstance(net, TableLinear) else net(self.features)      # [U, ch]
         return table_lookup(t, self.inverse.view(self.shape), self.count)
 
 
@@ -127,6 +128,16 @@ class Linear(nn.Linear):
     def forward(self, x):
         if FAST_LINEAR_BACKWARD and x.is_cuda and torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
             return linear(x, self.weight, self.bias)
+        return F.linear(x, self.weight, self.bias)
+
+
+class TableLinear(nn.Linear):
+    """``pos_embed`` (Linear(5, heads), aff.py:101; same parameters / state_dict keys) evaluated on the feature rows a stage
+    references: fp32, only the first ``count`` rows (device scalar), without the K = 5 GEMM cuBLAS has no good kernel for."""
+
+    def forward(self, x, count=None):
+        if NATIVE_TABLE_LINEAR and table_linear_supported(x, self.weight, self.bias):
+            return table_linear(x, self.weight, self.bias, count)
         return F.linear(x, self.weight, self.bias)
 
 
@@ -178,7 +189,7 @@ class ClusterAttention(nn.Module):
         self.softmax = nn.Softmax(dim=-1)
         self.blank_k = nn.Parameter(torch.randn(dim))
         self.blank_v = nn.Parameter(torch.randn(dim))
-        self.pos_embed = nn.Linear(self.pos_dim + 3, num_heads)
+        self.pos_embed = TableLinear(self.pos_dim + 3, num_heads)
         self.attn_drop = nn.Dropout(attn_drop)
         self.proj = Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
@@ -194,7 +205,7 @@ class ClusterAttention(nn.Module):
         if fusable and torch.is_grad_enabled() and q_tok.dtype in (torch.float16, torch.bfloat16):
             # training fast path: one differentiable op, fp16 / bf16 (autocast); fp32 training keeps the separate ops below
             bias_idx, mask_u8 = fused_ctx
-            out = cluster_attention_core(q_tok, kv_tok, self.pos_embed(pe_lookup.features), self.blank_k, self.blank_v,
+            out = cluster_attention_core(q_tok, kv_tok, self.pos_embed(pe_lookup.features, pe_lookup.count), self.blank_k, self.blank_v,
                                          member_idx, bias_idx, mask_u8, pe_lookup.count)
             return self.proj_drop(self.proj(out))
         q = q_tok.permute(0, 2, 1, 3)                                                    # b h n c_ (view)
@@ -203,7 +214,7 @@ class ClusterAttention(nn.Module):
         if (fused_ctx is not None and not global_attn and USE_FUSED_ATTENTION and not torch.is_grad_enabled()
                 and (self.attn_drop.p == 0.0 or not self.training)):
             bias_idx, mask_u8 = fused_ctx
-            out = cluster_attention_fused(q, key, v, member_idx, self.pos_embed(pe_lookup.features), bias_idx, mask_u8,
+            out = cluster_attention_fused(q, key, v, member_idx, self.pos_embed(pe_lookup.features, pe_lookup.count), bias_idx, mask_u8,
                                           self.blank_k, self.blank_v)                    # aff.py:114-155 in one kernel
             return self.proj_drop(self.proj(out))
         if global_attn:

@@ -592,6 +592,54 @@ def scale_residual(res, x, gamma=None, sample_scale=None):
     return res + x
 
 
+# ---- Linear over the relative-position feature table ------------------------------------------------------------------
+class TableLinearFunction(Function):
+    """``F.linear(features, weight, bias)`` for the [R, F <= 8] relative-position feature table and H <= 32 outputs
+    (pos_embed = Linear(5, heads), aff.py:101,129) in fp32, restricted to the first ``count`` rows (device int32 scalar, or
+    None = all): rows past it come back as zeros and take no part in the weight gradient.  features get no gradient."""
+
+    @staticmethod
+    def forward(ctx, features, weight, bias, count):
+        dev = _lib.require_cuda(features, weight, bias, count)
+        R, F = features.shape
+        H = weight.shape[0]
+        feat = features.detach().contiguous()
+        w = weight.detach().contiguous()
+        b = None if bias is None else bias.detach().contiguous()
+        out = torch.empty((R, H), dtype=torch.float32, device=dev)
+        if R:
+            with torch.cuda.device(dev):
+                _call("clusten_table_linear_fwd", dev, feat.data_ptr(), w.data_ptr(), _lib.ptr(b), out.data_ptr(), R, F, H,
+                      _lib.ptr(count), nbytes=4 * R * (F + H))
+        ctx.save_for_backward(feat, count)
+        ctx.meta = (R, F, H, weight.dtype, None if bias is None else bias.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        feat, count = ctx.saved_tensors
+        R, F, H, wdt, bdt = ctx.meta
+        dev = g.device
+        g = g.to(torch.float32).contiguous()
+        dW = torch.zeros((H, F), dtype=torch.float32, device=dev)
+        db = torch.zeros(H, dtype=torch.float32, device=dev) if bdt is not None else None
+        if R:
+            with torch.cuda.device(dev):
+                _call("clusten_table_linear_bwd", dev, g.data_ptr(), feat.data_ptr(), dW.data_ptr(), _lib.ptr(db), R, F, H,
+                      _lib.ptr(count), nbytes=4 * R * (F + H))
+        return None, dW.to(wdt), None if db is None else db.to(bdt), None
+
+
+def table_linear_supported(features, weight, bias):
+    return bool(features.is_cuda and features.dim() == 2 and features.dtype == torch.float32 and weight.dtype == torch.float32
+                and (bias is None or bias.dtype == torch.float32) and features.shape[1] == weight.shape[1] <= 8
+                and weight.shape[0] <= 32 and features.shape[0] * weight.shape[0] < 2 ** 31)
+
+
+def table_linear(features, weight, bias=None, count=None):
+    return TableLinearFunction.apply(features, weight, bias, count)
+
+
 # ---- Linear with a bandwidth-bound bias gradient -----------------------------------------------------------------------
 def col_sum(x2d):
     """fp32 [C] column sums of a [R, C] matrix (clusten_col_sum); falls back to torch for shapes the kernel does not take."""

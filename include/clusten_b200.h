@@ -191,6 +191,17 @@ int clusten_stage_prepare(const int64_t *nearest /* [B,n,nnc] */, const int64_t 
                           int64_t *member_idx, int64_t *mask64, uint8_t *mask8, int32_t *pe_idx, int32_t *bias_idx,
                           int32_t *uniq, int uniq_cap, int32_t *count, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- Linear(F -> H) over the rows of the relative-position feature table: out[r,h] = bias[h] + sum_j feat[r,j] * weight[h,j]
+ * -- `self.pos_embed(pre_table)` of backbone/aff.py:101,129 on the rows a stage references.  fp32; F <= 8, H <= 32;
+ * count = device int32 scalar (rows actually referenced, see clusten_stage_prepare) or NULL (= R): rows >= *count are written
+ * as zeros forward and ignored backward.  Backward: d_weight[h,j] += sum_r d_out[r,h] * feat[r,j], d_bias[h] += sum_r
+ * d_out[r,h] (accumulated INTO with fp32 atomics, one per CTA and weight; d_bias may be NULL); feat gets no gradient
+ * (the table is a constant, aff.py:17-31). */
+int clusten_table_linear_fwd(const float *feat, const float *weight, const float *bias, float *out, int R, int F, int H,
+                             const int32_t *count, void *stream);
+int clusten_table_linear_bwd(const float *d_out, const float *feat, float *d_weight, float *d_bias, int R, int F, int H,
+                             const int32_t *count, void *stream);
+
 /* ---- column sum: out[c] += sum_r x[r*ld + c] (fp32 accumulation INTO out; caller zeroes it).  The bias gradient of the
  * backbone's Linear layers (grad_bias = grad_output.sum(0)); x fp32 / fp16 / bf16, C and ld multiples of 16 bytes. */
 int clusten_col_sum(const void *x, float *out, int64_t R, int C, int64_t ld, int dtype, void *stream);

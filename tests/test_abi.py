@@ -84,6 +84,10 @@ def test_argument_errors_of_the_structure_builders(lib):
     assert rc == -2                                                         # (bf16 res, fp32 x) is not a supported pair
     rc = lib.clusten_scale_residual_bwd(16, None, None, None, None, None, 2, 10, 8, 0, 0, None)
     assert rc == -1                                                         # neither d_x nor d_gamma wanted
+    rc = lib.clusten_table_linear_fwd(16, 16, None, 16, 100, 9, 4, None, None)
+    assert rc == -3 and b"F <= 8" in lib.clusten_last_error()                # more than 8 input features
+    rc = lib.clusten_table_linear_bwd(16, 16, None, None, 100, 5, 4, None, None)
+    assert rc == -1                                                         # d_weight missing
 
 
 def test_ops_refuse_cpu_tensors():

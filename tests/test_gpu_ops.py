@@ -613,6 +613,36 @@ def test_scale_residual(B, rows, C, rdt, xdt, use_gamma, use_scale):
         assert rel_err(gc.grad.cpu(), gr.grad) <= max(tol, 2e-5)
 
 
+@pytest.mark.parametrize("use_count", [False, True], ids=["all-rows", "device-count"])
+@pytest.mark.parametrize("R,F,H", [(1000, 5, 2), (65025, 5, 16), (333, 5, 32), (77, 8, 3), (1, 5, 4)])
+def test_table_linear(R, F, H, use_count):
+    """clusten_table_linear_fwd / _bwd (pos_embed = Linear(5, heads) on the referenced table rows, aff.py:101,129) against
+    F.linear in fp64 on the first ``count`` rows; rows past the count are zeros and take no part in the gradients."""
+    from autofocusformermod_b200 import ops
+    g = torch.Generator().manual_seed(R + 7 * H)
+    feat = torch.randn(R, F, generator=g) * 3
+    w, b = torch.randn(H, F, generator=g), torch.randn(H, generator=g)
+    up = torch.randn(R, H, generator=g)
+    U = max(1, (R * 2) // 3) if use_count else R
+    count = torch.tensor(U, dtype=torch.int32).cuda() if use_count else None
+    wc, bc = w.clone().cuda().requires_grad_(True), b.clone().cuda().requires_grad_(True)
+    assert ops.table_linear_supported(feat.cuda(), wc, bc)
+    out = ops.table_linear(feat.cuda(), wc, bc, count)
+    out.backward(up.cuda())
+    torch.cuda.synchronize()
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = torch.nn.functional.linear(feat[:U].double(), wr, br)
+    ref.backward(up[:U].double())
+    assert out.dtype == torch.float32 and out.shape == (R, H)
+    assert rel_err(out[:U].cpu().double(), ref.detach()) <= 1e-6
+    assert not out[U:].any()
+    assert rel_err(wc.grad.cpu().double(), wr.grad) <= 2e-5
+    assert rel_err(bc.grad.cpu().double(), br.grad) <= 2e-5
+    # no bias
+    out2 = ops.table_linear(feat.cuda(), wc.detach(), None, count)
+    assert rel_err(out2[:U].cpu().double(), torch.nn.functional.linear(feat[:U].double(), w.double())) <= 1e-6
+
+
 def test_scale_residual_falls_back_for_shapes_the_kernel_does_not_take():
     """Non-contiguous operands and odd channel counts go through the torch formulation with the same result."""
     from autofocusformermod_b200 import ops
