@@ -25,7 +25,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .ops import (CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction, cluster_attention_core, cluster_attention_fused,
-                  layer_norm, linear, scale_residual, table_linear, table_linear_supported, table_lookup)
+                  cluster_attention_core_pos, cluster_attention_fused_pos, layer_norm, linear, scale_residual, table_linear,
+                  table_linear_supported, table_lookup)
 from .point_utils import knn_keops, merge_select, space_filling_cluster, stage_prepare
 
 # aff.py:17-19: the relative-position table covers inputs up to 2048 px (stem grid 512)
@@ -41,6 +42,8 @@ FAST_LINEAR_BACKWARD = os.environ.get("CLUSTEN_FAST_LINEAR", "1") != "0"        
 CHANNELS_LAST_STEM = os.environ.get("CLUSTEN_CHANNELS_LAST", "1") != "0"          # run the two stem convolutions + BatchNorm in NHWC (see PatchEmbed.forward)
 GRID_STRUCTURE_CACHE = os.environ.get("CLUSTEN_GRID_CACHE", "1") != "0"        # memoise the position-only structures of the on-grid stage (see BasicLayer._grid_structure)
 NATIVE_TABLE_LINEAR = os.environ.get("CLUSTEN_TABLE_LINEAR", "1") != "0"      # pos_embed = Linear(5, heads) over the referenced table rows by clusten_table_linear_* (see TableLinear)
+# opt-in (round-2 work): relative-position bias computed from positions inside the fused attention kernels
+INKERNEL_BIAS = os.environ.get("CLUSTEN_INKERNEL_BIAS", "0") == "1"
 FUSED_RESIDUAL = os.environ.get("CLUSTEN_FUSED_RESIDUAL", "1") != "0"           # residual + layer scale + stochastic depth in one kernel (see ClusterTransformerBlock._residual)
 NATIVE_WEIGHT_NET_NORM = os.environ.get("CLUSTEN_WEIGHT_NET_NORM", "1") != "0"   # LayerNorm(4) of the merge's weight_net through clusten_layer_norm_* (see ClusterMerging)
 
@@ -204,18 +207,26 @@ class ClusterAttention(nn.Module):
                    and (self.attn_drop.p == 0.0 or not self.training))
         if fusable and torch.is_grad_enabled() and q_tok.dtype in (torch.float16, torch.bfloat16):
             # training fast path: one differentiable op, fp16 / bf16 (autocast); fp32 training keeps the separate ops below
-            bias_idx, mask_u8 = fused_ctx
-            out = cluster_attention_core(q_tok, kv_tok, self.pos_embed(pe_lookup.features, pe_lookup.count), self.blank_k, self.blank_v,
-                                         member_idx, bias_idx, mask_u8, pe_lookup.count)
+            bias_idx, mask_u8, spos = fused_ctx
+            if INKERNEL_BIAS and self.pos_embed.weight.dtype == torch.float32:
+                out = cluster_attention_core_pos(q_tok, kv_tok, self.pos_embed.weight, self.pos_embed.bias, self.blank_k, self.blank_v,
+                                                 member_idx, spos, mask_u8)
+            else:
+                out = cluster_attention_core(q_tok, kv_tok, self.pos_embed(pe_lookup.features, pe_lookup.count), self.blank_k,
+                                             self.blank_v, member_idx, bias_idx, mask_u8, pe_lookup.count)
             return self.proj_drop(self.proj(out))
         q = q_tok.permute(0, 2, 1, 3)                                                    # b h n c_ (view)
         kv = kv_tok.permute(3, 0, 2, 1, 4)                                               # 2 b h n c_ (view)
         key, v = kv[0], kv[1]
         if (fused_ctx is not None and not global_attn and USE_FUSED_ATTENTION and not torch.is_grad_enabled()
                 and (self.attn_drop.p == 0.0 or not self.training)):
-            bias_idx, mask_u8 = fused_ctx
-            out = cluster_attention_fused(q, key, v, member_idx, self.pos_embed(pe_lookup.features, pe_lookup.count), bias_idx, mask_u8,
-                                          self.blank_k, self.blank_v)                    # aff.py:114-155 in one kernel
+            bias_idx, mask_u8, spos = fused_ctx
+            if INKERNEL_BIAS and self.pos_embed.weight.dtype == torch.float32:
+                out = cluster_attention_fused_pos(q, key, v, member_idx, spos, self.pos_embed.weight, self.pos_embed.bias, mask_u8,
+                                                  self.blank_k, self.blank_v)
+            else:
+                out = cluster_attention_fused(q, key, v, member_idx, self.pos_embed(pe_lookup.features, pe_lookup.count), bias_idx,
+                                              mask_u8, self.blank_k, self.blank_v)       # aff.py:114-155 in one kernel
             return self.proj_drop(self.proj(out))
         if global_attn:
             attn = q @ key.transpose(-1, -2)                                             # aff.py:121
@@ -401,7 +412,7 @@ class BasicLayer(nn.Module):
             pe_idx = None
             if pe_lookup is None:
                 pe_lookup = _TableLookup(uniq=uniq, inverse=bias_idx, count=count)
-            fused_ctx = (bias_idx, mask_u8) if USE_FUSED_ATTENTION else None
+            fused_ctx = (bias_idx, mask_u8, pos) if USE_FUSED_ATTENTION else None
         if global_attn:
             rel_pos = rel_pos.clamp(0, TABLE_WIDTH - 1)
             pe_idx = (rel_pos[..., 1] * TABLE_WIDTH + rel_pos[..., 0]).long()                        # aff.py:484-485

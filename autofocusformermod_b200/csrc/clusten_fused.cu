@@ -14,6 +14,7 @@
 // probabilities as the A operand.  The [B,H,N,M] tensor never touches HBM (optionally the probabilities are written
 // once, coalesced, for a backward pass).  Impure tokens and index tensors without octet structure take a
 // one-warp-per-(token, head) generic kernel with the same arithmetic; the pack's device-side flag picks (no host sync).
+#include "posbias.cuh"
 #include "t2.cuh"
 
 namespace clusten {
@@ -84,26 +85,41 @@ struct FusedArgs {
     int B, H, Nq, Nk, C, M;
     int64_t q_sb, q_sh, q_sn, k_sb, k_sh, k_sn, v_sb, v_sh, v_sn, o_sb, o_sh, o_sn;
 };
+// position-bias variant (PB kernels, clusten_attn_pos_fwd): bias from positions instead of bias_tab / bias_idx (posbias.cuh).
+// A separate type so that the kernels of the table variant keep their parameter block exactly as validated.
+struct FusedArgsPB : FusedArgs {
+    const float *pos_q, *pos_k, *pe_w, *pe_b;            // [B,Nq,2], [B,Nk,2], [H,5], [H] or NULL
+};
+template <bool PB> using FArgsOf = std::conditional_t<PB, FusedArgsPB, FusedArgs>;
 
 // One (token, head) computed the slow way by one warp; `sm` = M + 2 floats of shared scratch.  Also THE generic kernel body.
-template <typename T>
-__device__ __forceinline__ void fused_row_generic(const FusedArgs &a, int b, int h, int i, float *sm, int lane) {
+template <typename T, bool PB = false>
+__device__ __forceinline__ void fused_row_generic(const FArgsOf<PB> &a, int b, int h, int i, float *sm, int lane) {
     const T *q = reinterpret_cast<const T *>(a.q) + b * a.q_sb + h * a.q_sh + (int64_t)i * a.q_sn;
     const T *kb = reinterpret_cast<const T *>(a.k) + b * a.k_sb + h * a.k_sh;
     const T *vb = reinterpret_cast<const T *>(a.v) + b * a.v_sb + h * a.v_sh;
     const T *bk = reinterpret_cast<const T *>(a.blank_k) + h * a.C;
     const T *bv = reinterpret_cast<const T *>(a.blank_v) + h * a.C;
     const int64_t *irow = a.idx + ((int64_t)b * a.Nq + i) * a.M;
-    const int32_t *bi = a.bias_idx + ((int64_t)b * a.Nq + i) * a.M;
+    const int32_t *bi = PB ? nullptr : a.bias_idx + ((int64_t)b * a.Nq + i) * a.M;
     const uint8_t *mk = a.mask ? a.mask + ((int64_t)b * a.Nq + i) * a.M : nullptr;
     const int M = a.M, C = a.C;
+    PosBiasW pw = {};
+    float2 pq = make_float2(0.f, 0.f);
+    const float2 *PK = nullptr;
+    if constexpr (PB) {
+        pw = pos_bias_load(a.pe_w, a.pe_b, h);
+        pq = __ldg(reinterpret_cast<const float2 *>(a.pos_q) + (int64_t)b * a.Nq + i);
+        PK = reinterpret_cast<const float2 *>(a.pos_k) + (int64_t)b * a.Nk;
+    }
     float mx = -INFINITY;
     for (int j = lane; j <= M; j += 32) {
         float s = 0.f;
         if (j < M) {
             const T *kr = kb + irow[j] * a.k_sn;
             for (int ch = 0; ch < C; ++ch) s = fmaf(to_f(q[ch]), to_f(kr[ch]), s);
-            s += a.bias_tab[(int64_t)bi[j] * a.H + h];
+            if constexpr (PB) s += pos_bias(pw, pq, __ldg(PK + irow[j]));
+            else s += a.bias_tab[(int64_t)bi[j] * a.H + h];
             if (mk && !mk[j]) s += -100.f;
         } else {
             for (int ch = 0; ch < C; ++ch) s = fmaf(to_f(q[ch]), to_f(bk[ch]), s);
@@ -137,9 +153,9 @@ __device__ __forceinline__ void fused_row_generic(const FusedArgs &a, int b, int
     __syncwarp();
 }
 
-template <typename T>
+template <typename T, bool PB>
 __global__ void __launch_bounds__(256)
-attn_fused_generic_kernel(const FusedArgs a, const int *__restrict__ tile_flag) {
+attn_fused_generic_kernel(const FArgsOf<PB> a, const int *__restrict__ tile_flag) {
     extern __shared__ __align__(16) float dyn_f[];
     if (tile_flag && tile_flag[0] == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
@@ -148,7 +164,7 @@ attn_fused_generic_kernel(const FusedArgs a, const int *__restrict__ tile_flag) 
     for (int64_t it = (int64_t)blockIdx.x * W + warp; it < total; it += (int64_t)gridDim.x * W) {
         const int h = (int)(it % a.H);
         const int64_t bi = it / a.H;
-        fused_row_generic<T>(a, (int)(bi / a.Nq), h, (int)(bi % a.Nq), sm, lane);
+        fused_row_generic<T, PB>(a, (int)(bi / a.Nq), h, (int)(bi % a.Nq), sm, lane);
     }
 }
 
@@ -180,9 +196,9 @@ template <typename T, int CH> __device__ __forceinline__ float f_elem(const FFra
     }
 }
 
-template <typename T, int CH, int NT>
+template <typename T, int CH, int NT, bool PB>
 __global__ void __launch_bounds__(256)
-attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) {
+attn_fused_tile_kernel(const FArgsOf<PB> a, const PackView pk, int smem_per_warp) {
     extern __shared__ __align__(16) unsigned char dyn[];
     if (pk.flags[0]) return;
     constexpr bool F32 = sizeof(T) == 4;
@@ -259,9 +275,20 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
         }
         constexpr int UB = F32 ? 2 : 4;
         const int klast = a.Nk - 1;                      // (mask-aware packs may hold the partial last octet: rows are clamped)
+        // PB: the lane owns the logits of rows g / g+8 against keys 2t, 2t+1 of each octet -> their bias from the four positions
+        PosBiasW pw = {};
+        float2 pqa = make_float2(0.f, 0.f), pqb = pqa;
+        const float2 *PK = nullptr;
+        if constexpr (PB) {
+            pw = pos_bias_load(a.pe_w, a.pe_b, h);
+            const float2 *PQ = reinterpret_cast<const float2 *>(a.pos_q) + (int64_t)b * Nq;
+            pqa = __ldg(PQ + min(ra, Nq - 1));
+            pqb = __ldg(PQ + min(rb, Nq - 1));
+            PK = reinterpret_cast<const float2 *>(a.pos_k) + (int64_t)b * a.Nk;
+        }
         for (int u0 = 0; u0 < U; u0 += UB) {
             FFrag<T, CH> y[UB];
-            int sga[UB], sgb[UB];
+            int sga[UB], sgb[UB], oct8[UB];
             uint32_t sa4, sb4;                           // slots of rows g / g+8 for the UB octets (positions >= U hold -1)
             if constexpr (UB == 4) {
                 sa4 = __ldg(reinterpret_cast<const uint32_t *>(sa + u0));
@@ -272,7 +299,8 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
             }
 #pragma unroll
             for (int j = 0; j < UB; ++j) {
-                t2::ld_chunk<CH * (int)sizeof(T)>(y[j].r, t2::at(K, min(octet(u0 + j) * 8 + g, klast) * k_sn + cofs));
+                oct8[j] = octet(u0 + j) * 8;
+                t2::ld_chunk<CH * (int)sizeof(T)>(y[j].r, t2::at(K, min(oct8[j] + g, klast) * k_sn + cofs));
                 sga[j] = t2::sbyte(sa4, j);
                 sgb[j] = t2::sbyte(sb4, j);
             }
@@ -290,6 +318,11 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
                         f_mma16816(acc, ah[s], y[j].r[2 * s], y[j].r[2 * s + 1], T());
                     }
                 }
+                if constexpr (PB) {
+                    const float2 k0 = __ldg(PK + min(oct8[j] + 2 * t, klast)), k1 = __ldg(PK + min(oct8[j] + 2 * t + 1, klast));
+                    acc[0] += pos_bias(pw, pqa, k0); acc[1] += pos_bias(pw, pqa, k1);
+                    acc[2] += pos_bias(pw, pqb, k0); acc[3] += pos_bias(pw, pqb, k1);
+                }
                 if (sga[j] >= 0) *reinterpret_cast<float2 *>(S + g * MP + 8 * sga[j] + 2 * t) = make_float2(acc[0], acc[1]);
                 if (sgb[j] >= 0) *reinterpret_cast<float2 *>(S + (g + 8) * MP + 8 * sgb[j] + 2 * t) = make_float2(acc[2], acc[3]);
             }
@@ -305,15 +338,17 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
         const int Mh = M >> 1, j0 = half * Mh, j1 = j0 + Mh;
         float mx = -INFINITY;
         if (rvalid) {
-            const int32_t *bi = a.bias_idx + ((int64_t)b * Nq + i) * M;
+            const int32_t *bi = PB ? nullptr : a.bias_idx + ((int64_t)b * Nq + i) * M;
             const uint8_t *mk = a.mask ? a.mask + ((int64_t)b * Nq + i) * M : nullptr;
             for (int j = j0; j < j1; j += 4) {                       // M % 8 == 0 -> Mh % 4 == 0, 16-byte aligned rows
-                const int4 bv = __ldg(reinterpret_cast<const int4 *>(bi + j));
                 float4 x = *reinterpret_cast<float4 *>(Sr + j);
-                x.x += __ldg(a.bias_tab + bv.x * H + h);
-                x.y += __ldg(a.bias_tab + bv.y * H + h);
-                x.z += __ldg(a.bias_tab + bv.z * H + h);
-                x.w += __ldg(a.bias_tab + bv.w * H + h);
+                if constexpr (!PB) {                                 // (PB: the bias went in with the logits in phase 1)
+                    const int4 bv = __ldg(reinterpret_cast<const int4 *>(bi + j));
+                    x.x += __ldg(a.bias_tab + bv.x * H + h);
+                    x.y += __ldg(a.bias_tab + bv.y * H + h);
+                    x.z += __ldg(a.bias_tab + bv.z * H + h);
+                    x.w += __ldg(a.bias_tab + bv.w * H + h);
+                }
                 if (mk) {
                     const uchar4 m4 = *reinterpret_cast<const uchar4 *>(mk + j);
                     if (!m4.x) x.x += -100.f;
@@ -459,7 +494,7 @@ attn_fused_tile_kernel(const FusedArgs a, const PackView pk, int smem_per_warp) 
     for (int it = si.first; it < si.n; it += si.stride) {
         const int gi = pk.imp_list[it / a.H], hh = it % a.H;
         const int bb = gi / a.Nq;
-        fused_row_generic<T>(a, bb, hh, gi - bb * a.Nq, S, lane);
+        fused_row_generic<T, PB>(a, bb, hh, gi - bb * a.Nq, S, lane);
     }
 }
 
@@ -468,8 +503,8 @@ template <typename T> static bool f_rows_ok(const void *p, int64_t sb, int64_t s
     return aligned16(p) && sb % VPT == 0 && sh % VPT == 0 && sn % VPT == 0;
 }
 
-template <typename T>
-static int launch_fused(const FusedArgs &a, const void *pack, cudaStream_t st) {
+template <typename T, bool PB>
+static int launch_fused(const FArgsOf<PB> &a, const void *pack, cudaStream_t st) {
     const int *flag = nullptr;
     const int M = a.M, C = a.C;
     const size_t per_warp = (size_t)16 * (M + 4) * 4 + 2560;
@@ -477,7 +512,7 @@ static int launch_fused(const FusedArgs &a, const void *pack, cudaStream_t st) {
     const bool shape_ok = C % 8 == 0 && C >= 8 && C <= 32 && M % 8 == 0 && M <= 256 && per_warp * W <= 48 * 1024;
     const bool align_ok = f_rows_ok<T>(a.q, a.q_sb, a.q_sh, a.q_sn) && f_rows_ok<T>(a.k, a.k_sb, a.k_sh, a.k_sn) &&
                           f_rows_ok<T>(a.v, a.v_sb, a.v_sh, a.v_sn) && f_rows_ok<T>(a.out, a.o_sb, a.o_sh, a.o_sn) &&
-                          aligned16(a.bias_idx) && (!a.mask || (reinterpret_cast<uintptr_t>(a.mask) & 3u) == 0);
+                          (PB || aligned16(a.bias_idx)) && (!a.mask || (reinterpret_cast<uintptr_t>(a.mask) & 3u) == 0);
     auto fits = [](int64_t v) { return v >= 0 && v < (1LL << 31); };
     const bool range_ok = fits(a.Nq * a.q_sn) && fits((int64_t)a.Nk * a.k_sn) && fits((int64_t)a.Nk * a.v_sn) && fits(a.Nq * a.o_sn) &&
                           (int64_t)a.B * a.H <= 65535 && fits((int64_t)a.B * ((a.Nq + 15) / 16) * 16 * U_MAX);
@@ -485,8 +520,8 @@ static int launch_fused(const FusedArgs &a, const void *pack, cudaStream_t st) {
         const PackView pk = pack_view(const_cast<void *>(pack), a.B, a.Nq, a.Nk);
         const dim3 grid(ceil_div(pk.T, W), a.B * a.H);
         const size_t smem = per_warp * W;
-        if (C <= 16) attn_fused_tile_kernel<T, 4, 2><<<grid, W * 32, smem, st>>>(a, pk, (int)per_warp);
-        else attn_fused_tile_kernel<T, 8, 4><<<grid, W * 32, smem, st>>>(a, pk, (int)per_warp);
+        if (C <= 16) attn_fused_tile_kernel<T, 4, 2, PB><<<grid, W * 32, smem, st>>>(a, pk, (int)per_warp);
+        else attn_fused_tile_kernel<T, 8, 4, PB><<<grid, W * 32, smem, st>>>(a, pk, (int)per_warp);
         note_launches(1);
         if (int e = check_launch("attn_fused_tile")) return e;
         flag = reinterpret_cast<const int *>(pack);
@@ -496,7 +531,7 @@ static int launch_fused(const FusedArgs &a, const void *pack, cudaStream_t st) {
     if (flag && grid > 148 * 8) grid = 148 * 8;
     const size_t smem = (size_t)8 * (M + 2) * sizeof(float);
     if (smem > 48 * 1024) return set_error(CLUSTEN_EUNSUPPORTED, "fused attention: M=%d too large", M);
-    attn_fused_generic_kernel<T><<<grid, 256, smem, st>>>(a, flag);
+    attn_fused_generic_kernel<T, PB><<<grid, 256, smem, st>>>(a, flag);
     note_launches(1);
     return check_launch("attn_fused_generic");
 }
@@ -520,6 +555,31 @@ extern "C" int clusten_attn_fwd(const void *q, const void *k, const void *v, con
     FusedArgs a{q, k, v, nbhd_idx, bias_tab, bias_idx, mask, blank_k, blank_v, out, probs, lse, B, H, Nq, Nk, C, M,
                 q_sb, q_sh, q_sn, k_sb, k_sh, k_sn, v_sb, v_sh, v_sn, o_sb, o_sh, o_sn};
     cudaStream_t st = (cudaStream_t)stream;
-    CLUSTEN_DISPATCH_DTYPE(dtype, return launch_fused<T>(a, pack, st));
+    CLUSTEN_DISPATCH_DTYPE(dtype, return (launch_fused<T, false>(a, pack, st)));
+    return 0;
+}
+
+// The same core with the relative-position bias computed from the token positions (posbias.cuh) instead of gathered from
+// bias_tab[bias_idx]: pos_q [B,Nq,2] / pos_k [B,Nk,2] fp32 (x, y), pe_weight fp32 [H,5], pe_bias fp32 [H] or NULL.
+extern "C" int clusten_attn_pos_fwd(const void *q, const void *k, const void *v, const int64_t *nbhd_idx, const void *pack,
+                                    const float *pos_q, const float *pos_k, const float *pe_weight, const float *pe_bias,
+                                    const uint8_t *mask, const void *blank_k, const void *blank_v, void *out, float *probs, float *lse,
+                                    int B, int H, int Nq, int Nk, int C, int M,
+                                    int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t k_sb, int64_t k_sh, int64_t k_sn,
+                                    int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t o_sb, int64_t o_sh, int64_t o_sn,
+                                    int dtype, void *stream) {
+    if (B < 0 || H <= 0 || Nq < 0 || Nk <= 0 || C <= 0 || M <= 0)
+        return set_error(CLUSTEN_EINVAL, "bad sizes B=%d H=%d Nq=%d Nk=%d C=%d M=%d", B, H, Nq, Nk, C, M);
+    if (!q || !k || !v || !nbhd_idx || !pos_q || !pos_k || !pe_weight || !blank_k || !blank_v || !out)
+        return set_error(CLUSTEN_EINVAL, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(pos_q) | reinterpret_cast<uintptr_t>(pos_k)) & 7u)
+        return set_error(CLUSTEN_EUNSUPPORTED, "positions must be 8-byte aligned");
+    if ((int64_t)B * Nq == 0) return 0;
+    FusedArgsPB a;
+    static_cast<FusedArgs &>(a) = FusedArgs{q, k, v, nbhd_idx, nullptr, nullptr, mask, blank_k, blank_v, out, probs, lse, B, H, Nq, Nk, C, M,
+                                            q_sb, q_sh, q_sn, k_sb, k_sh, k_sn, v_sb, v_sh, v_sn, o_sb, o_sh, o_sn};
+    a.pos_q = pos_q; a.pos_k = pos_k; a.pe_w = pe_weight; a.pe_b = pe_bias;
+    cudaStream_t st = (cudaStream_t)stream;
+    CLUSTEN_DISPATCH_DTYPE(dtype, return (launch_fused<T, true>(a, pack, st)));
     return 0;
 }

@@ -18,6 +18,7 @@
 // global memory as contiguous tiles for the scatter kernels); pass 2 runs the axpy shape dS.K with K staged key-major by
 // cp.async and read back with ldmatrix.trans.  Impure tokens (tile.cuh) are computed one (token, head) per warp by the warps
 // that finish first, exactly as in clusten_tile2.cu.
+#include "posbias.cuh"
 #include "t2.cuh"
 
 namespace clusten {
@@ -40,6 +41,13 @@ struct BwdArgs {
     int64_t q_sb, k_sb, v_sb, do_sb, o_sb, dq_sb;
     int smem_per_warp;
 };
+// position-bias variant (PB kernels, clusten_attn_pos_bwd; posbias.cuh): bias from positions, pos_embed gradient into pe_parts.
+// A separate type so that the kernels of the table variant keep their parameter block (and code) exactly as validated.
+struct BwdArgsPB : BwdArgs {
+    const float *pos_q, *pos_k, *pe_w, *pe_b;            // [B,Nq,2], [B,Nk,2], [H,5], [H] or NULL
+    float *pe_parts;                                     // [PB_PARTS][H][6] fp32, accumulated into
+};
+template <bool PB> using ArgsOf = std::conditional_t<PB, BwdArgsPB, BwdArgs>;
 
 template <typename T> __device__ __forceinline__ float pair_dot(uint32_t a, uint32_t b) {
     float2 fa, fb_;
@@ -57,6 +65,10 @@ __device__ __forceinline__ float quad_sum(float x) {                 // over the
     x += __shfl_xor_sync(FULL, x, 2);
     return x;
 }
+template <typename T> __device__ __forceinline__ float2 unpack_pair(uint32_t a) {
+    if constexpr (std::is_same<T, __half>::value) return __half22float2(*reinterpret_cast<const __half2 *>(&a));
+    else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a));
+}
 __device__ __forceinline__ float warp_sum(float x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
@@ -65,8 +77,8 @@ __device__ __forceinline__ float warp_sum(float x) {
 
 // One impure (token, head), one warp: everything of the header for this row, rows read as scalars / 16-byte chunks.
 // `sc` = M floats of shared scratch.
-template <typename T>
-__device__ __noinline__ void bwd_row(const BwdArgs &a, int b, int h, int i, float *sc, int lane) {
+template <typename T, bool PB = false>
+__device__ __noinline__ void bwd_row(const ArgsOf<PB> &a, int b, int h, int i, float *sc, int lane) {
     const T *q = reinterpret_cast<const T *>(a.q) + b * a.q_sb + h * a.q_sh + (int64_t)i * a.q_sn;
     const T *dO = reinterpret_cast<const T *>(a.dO) + b * a.do_sb + h * a.do_sh + (int64_t)i * a.do_sn;
     const T *O = reinterpret_cast<const T *>(a.O) + b * a.o_sb + h * a.o_sh + (int64_t)i * a.o_sn;
@@ -76,9 +88,18 @@ __device__ __noinline__ void bwd_row(const BwdArgs &a, int b, int h, int i, floa
     const T *bv = reinterpret_cast<const T *>(a.blank_v) + h * a.C;
     const int64_t row = ((int64_t)b * a.H + h) * a.Nq + i;
     const int64_t *irow = a.idx + ((int64_t)b * a.Nq + i) * a.M;
-    const int32_t *bi = a.bias_idx + ((int64_t)b * a.Nq + i) * a.M;
+    const int32_t *bi = PB ? nullptr : a.bias_idx + ((int64_t)b * a.Nq + i) * a.M;
     const uint8_t *mk = a.mask ? a.mask + ((int64_t)b * a.Nq + i) * a.M : nullptr;
     const int M = a.M, C = a.C;
+    PosBiasW pw = {};
+    float2 pq = make_float2(0.f, 0.f);
+    const float2 *PK = nullptr;
+    float gacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if constexpr (PB) {
+        pw = pos_bias_load(a.pe_w, a.pe_b, h);
+        pq = __ldg(reinterpret_cast<const float2 *>(a.pos_q) + (int64_t)b * a.Nq + i);
+        PK = reinterpret_cast<const float2 *>(a.pos_k) + (int64_t)b * a.Nk;
+    }
     const float lse = a.lse[row];
     float D = 0.f, sb = 0.f, dpb = 0.f;
     if (lane < C) {
@@ -99,14 +120,17 @@ __device__ __noinline__ void bwd_row(const BwdArgs &a, int b, int h, int i, floa
             s = fmaf(to_f(q[c]), to_f(kr[c]), s);
             dp = fmaf(to_f(dO[c]), to_f(vr[c]), dp);
         }
-        s += a.bias_tab[(int64_t)bi[j] * a.H + h];
+        if constexpr (PB) s += pos_bias(pw, pq, __ldg(PK + r));
+        else s += a.bias_tab[(int64_t)bi[j] * a.H + h];
         if (mk && !mk[j]) s += -100.f;
         const float p = __expf(s - lse);
         const T dsr = from_f<T>(p * (dp - D));
         Prow[j] = from_f<T>(p);
         dSrow[j] = dsr;
         sc[j] = to_f(dsr);                               // the rounded value: what the scatter kernels will multiply with
+        if constexpr (PB) pos_bias_grad(gacc, pq, __ldg(PK + r), to_f(dsr));
     }
+    if constexpr (PB) pos_bias_grad_flush(gacc, a.pe_parts, i, a.H, h, lane);
     __syncwarp();
     if (lane < C) {
         float acc = dsb * to_f(bk[lane]);
@@ -116,9 +140,9 @@ __device__ __noinline__ void bwd_row(const BwdArgs &a, int b, int h, int i, floa
     __syncwarp();
 }
 
-template <typename T, int CH, int NT>
+template <typename T, int CH, int NT, bool PB>
 __global__ void __launch_bounds__(128)
-attn_bwd_tile_kernel(const BwdArgs a, const PackView pk) {
+attn_bwd_tile_kernel(const ArgsOf<PB> a, const PackView pk) {
     extern __shared__ __align__(16) unsigned char dyn_fb[];
     if (pk.flags[0]) return;
     constexpr int NR = CH / 2;
@@ -201,6 +225,17 @@ attn_bwd_tile_kernel(const BwdArgs a, const PackView pk) {
     }
     const int8_t *sa = pk.slot_of + (bt * TILE_TOK + g) * U_MAX;
     const int8_t *sb = sa + 8 * U_MAX;
+    // PB: the lane owns rows g / g+8 against keys 2t, 2t+1 of each octet in both passes (posbias.cuh)
+    PosBiasW pw = {};
+    float2 pqa = make_float2(0.f, 0.f), pqb = pqa;
+    const float2 *PK = nullptr;
+    if constexpr (PB) {
+        pw = pos_bias_load(a.pe_w, a.pe_b, h);
+        const float2 *PQ = reinterpret_cast<const float2 *>(a.pos_q) + (int64_t)b * Nq;
+        pqa = __ldg(PQ + rac);
+        pqb = __ldg(PQ + rbc);
+        PK = reinterpret_cast<const float2 *>(a.pos_k) + (int64_t)b * a.Nk;
+    }
     // ---- pass 1: S = q.K^T and DP = dO.V^T against every union octet, selected blocks -> shared memory ------------------------
     {
         const int klast = a.Nk - 1;                      // (mask-aware packs may hold the partial last octet: rows are clamped)
@@ -210,9 +245,11 @@ attn_bwd_tile_kernel(const BwdArgs a, const PackView pk) {
             const uint32_t s2a = __ldg(reinterpret_cast<const unsigned short *>(sa + u0));
             const uint32_t s2b = __ldg(reinterpret_cast<const unsigned short *>(sb + u0));
             uint32_t yk[2][NR], yv[2][NR];
+            int oct8[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int o = octet(u0 + j);
+                oct8[j] = o * 8;
                 const int kr = min(o * 8 + g, klast);
                 ld_chunk<CH * 2>(yk[j], at(Kb, kr * a.k_sn + cofs));
                 ld_chunk<CH * 2>(yv[j], at(Vb, kr * a.v_sn + cofs));
@@ -226,6 +263,11 @@ attn_bwd_tile_kernel(const BwdArgs a, const PackView pk) {
                 for (int s = 0; s < CH / 4; ++s) {
                     mma16<T>(sacc, xa[2 * s], xb[2 * s], xa[2 * s + 1], xb[2 * s + 1], yk[j][2 * s], yk[j][2 * s + 1]);
                     mma16<T>(dacc, da[2 * s], db[2 * s], da[2 * s + 1], db[2 * s + 1], yv[j][2 * s], yv[j][2 * s + 1]);
+                }
+                if constexpr (PB) {
+                    const float2 k0 = __ldg(PK + min(oct8[j] + 2 * t, klast)), k1 = __ldg(PK + min(oct8[j] + 2 * t + 1, klast));
+                    sacc[0] += pos_bias(pw, pqa, k0); sacc[1] += pos_bias(pw, pqa, k1);
+                    sacc[2] += pos_bias(pw, pqb, k0); sacc[3] += pos_bias(pw, pqb, k1);
                 }
                 if (s0 >= 0) {
                     *reinterpret_cast<float2 *>(Sa + 8 * s0) = make_float2(sacc[0], sacc[1]);
@@ -249,16 +291,18 @@ attn_bwd_tile_kernel(const BwdArgs a, const PackView pk) {
         const int Mh = M >> 1, j0 = half * Mh, j1 = j0 + Mh;
         if (rvalid) {
             const float D = Sr[M], lse = Sr[M + 1];
-            const int32_t *bi = a.bias_idx + ((int64_t)b * Nq + i) * M;
+            const int32_t *bi = PB ? nullptr : a.bias_idx + ((int64_t)b * Nq + i) * M;
             const uint8_t *mk = a.mask ? a.mask + ((int64_t)b * Nq + i) * M : nullptr;
             for (int j = j0; j < j1; j += 4) {
-                const int4 bv4 = __ldg(reinterpret_cast<const int4 *>(bi + j));
                 float4 x = *reinterpret_cast<const float4 *>(Sr + j);
                 const float4 d = *reinterpret_cast<const float4 *>(Dr + j);
-                x.x += __ldg(a.bias_tab + bv4.x * H + h);
-                x.y += __ldg(a.bias_tab + bv4.y * H + h);
-                x.z += __ldg(a.bias_tab + bv4.z * H + h);
-                x.w += __ldg(a.bias_tab + bv4.w * H + h);
+                if constexpr (!PB) {                                 // (PB: the bias went in with the logits in pass 1)
+                    const int4 bv4 = __ldg(reinterpret_cast<const int4 *>(bi + j));
+                    x.x += __ldg(a.bias_tab + bv4.x * H + h);
+                    x.y += __ldg(a.bias_tab + bv4.y * H + h);
+                    x.z += __ldg(a.bias_tab + bv4.z * H + h);
+                    x.w += __ldg(a.bias_tab + bv4.w * H + h);
+                }
                 if (mk) {
                     const uchar4 m4 = *reinterpret_cast<const uchar4 *>(mk + j);
                     if (!m4.x) x.x += -100.f;
@@ -300,6 +344,7 @@ attn_bwd_tile_kernel(const BwdArgs a, const PackView pk) {
     float acc[NT][4];
 #pragma unroll
     for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+    float gacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};       // PB: sum of dS * [feat | 1] over this lane's (row, key) pairs
     {
         const int blk = lane % NT, prow = lane / NT;
         const bool act = 8 * blk < C;
@@ -343,6 +388,16 @@ attn_bwd_tile_kernel(const BwdArgs a, const PackView pk) {
             if (s10 < 0) af[1] = 0u;
             if (s01 < 0) af[2] = 0u;
             if (s11 < 0) af[3] = 0u;
+            if constexpr (PB) {                          // af[2jj] / af[2jj+1] = dS of rows g / g+8 at keys 2t, 2t+1 of octet 2p + jj
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int o8 = octet(2 * p + jj) * 8;
+                    const float2 k0 = __ldg(PK + min(o8 + 2 * t, a.Nk - 1)), k1 = __ldg(PK + min(o8 + 2 * t + 1, a.Nk - 1));
+                    const float2 dsa = unpack_pair<T>(af[2 * jj]), dsb2 = unpack_pair<T>(af[2 * jj + 1]);
+                    pos_bias_grad(gacc, pqa, k0, dsa.x); pos_bias_grad(gacc, pqa, k1, dsa.y);
+                    pos_bias_grad(gacc, pqb, k0, dsb2.x); pos_bias_grad(gacc, pqb, k1, dsb2.y);
+                }
+            }
             if (p + 1 < P2) cp_wait<1>(); else cp_wait<0>();
             __syncwarp();
             const uint32_t yst = lrow + (p & 1) * KSTG;
@@ -356,6 +411,7 @@ attn_bwd_tile_kernel(const BwdArgs a, const PackView pk) {
             __syncwarp();
         }
     }
+    if constexpr (PB) pos_bias_grad_flush(gacc, a.pe_parts, tile + 131 * b, H, h, lane);
     // ---- epilogue: d_q = acc + ds_blank * blank_k --------------------------------------------------------------------------------
     {
         T *Dq = opaque(reinterpret_cast<T *>(a.dq) + b * a.dq_sb + h * a.dq_sh);
@@ -376,14 +432,14 @@ attn_bwd_tile_kernel(const BwdArgs a, const PackView pk) {
     for (int it = si.first; it < si.n; it += si.stride) {
         const int gi = pk.imp_list[it / a.H], hh = it % a.H;
         const int bb = gi / a.Nq;
-        bwd_row<T>(a, bb, hh, gi - bb * a.Nq, S, lane);
+        bwd_row<T, PB>(a, bb, hh, gi - bb * a.Nq, S, lane);
     }
 }
 
 // generic path (index tensors without octet structure): one warp per (token, head)
-template <typename T>
+template <typename T, bool PB>
 __global__ void __launch_bounds__(256)
-attn_bwd_generic_kernel(const BwdArgs a, const int *__restrict__ tile_flag) {
+attn_bwd_generic_kernel(const ArgsOf<PB> a, const int *__restrict__ tile_flag) {
     extern __shared__ __align__(16) unsigned char dyn_fb[];
     if (tile_flag && tile_flag[0] == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -392,7 +448,7 @@ attn_bwd_generic_kernel(const BwdArgs a, const int *__restrict__ tile_flag) {
     for (int64_t it = (int64_t)blockIdx.x * 8 + warp; it < total; it += (int64_t)gridDim.x * 8) {
         const int h = (int)(it % a.H);
         const int64_t bi = it / a.H;
-        bwd_row<T>(a, (int)(bi / a.Nq), h, (int)(bi % a.Nq), sc, lane);
+        bwd_row<T, PB>(a, (int)(bi / a.Nq), h, (int)(bi % a.Nq), sc, lane);
     }
 }
 
@@ -403,9 +459,9 @@ template <typename T> int launch_scat_tile2(const T *W, const T *X, const int32_
 
 static inline bool fb_fits31(int64_t v) { return v >= 0 && v < (1LL << 31); }
 
-template <typename T>
-static int launch_attn_bwd(const fb::BwdArgs &a0, const void *pack, cudaStream_t st) {
-    fb::BwdArgs a = a0;
+template <typename T, bool PB>
+static int launch_attn_bwd(const fb::ArgsOf<PB> &a0, const void *pack, cudaStream_t st) {
+    fb::ArgsOf<PB> a = a0;
     const int M = a.M, C = a.C;
     const int *flag = nullptr;
     const int NT = C <= 16 ? 2 : 4;
@@ -415,14 +471,14 @@ static int launch_attn_bwd(const fb::BwdArgs &a0, const void *pack, cudaStream_t
     auto al = [](const void *p, int64_t sb, int sh, int sn) { return aligned16(p) && sb % 8 == 0 && sh % 8 == 0 && sn % 8 == 0; };
     const bool align_ok = al(a.q, a.q_sb, a.q_sh, a.q_sn) && al(a.k, a.k_sb, a.k_sh, a.k_sn) && al(a.v, a.v_sb, a.v_sh, a.v_sn) &&
                           al(a.dO, a.do_sb, a.do_sh, a.do_sn) && al(a.O, a.o_sb, a.o_sh, a.o_sn) && al(a.dq, a.dq_sb, a.dq_sh, a.dq_sn) &&
-                          aligned16(a.P) && aligned16(a.dS) && aligned16(a.bias_idx) && aligned16(a.blank_k) && aligned16(a.blank_v) &&
+                          aligned16(a.P) && aligned16(a.dS) && (PB || aligned16(a.bias_idx)) && aligned16(a.blank_k) && aligned16(a.blank_v) &&
                           (!a.mask || (reinterpret_cast<uintptr_t>(a.mask) & 3u) == 0);
     if (pack && shape_ok && align_ok && (int64_t)a.B * a.H <= 65535 && spw * WPC <= 200 * 1024) {
         const PackView pk = pack_view(const_cast<void *>(pack), a.B, a.Nq, a.Nk);
         a.smem_per_warp = (int)spw;
         const dim3 grid(ceil_div(pk.T, WPC), a.B * a.H);
         const size_t smem = spw * WPC;
-#define FB_LAUNCH(CH_, NT_) do { auto kfn = fb::attn_bwd_tile_kernel<T, CH_, NT_>; \
+#define FB_LAUNCH(CH_, NT_) do { auto kfn = fb::attn_bwd_tile_kernel<T, CH_, NT_, PB>; \
             if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             kfn<<<grid, WPC * 32, smem, st>>>(a, pk); } while (0)
         if (C <= 16) FB_LAUNCH(4, 2); else FB_LAUNCH(8, 4);
@@ -436,7 +492,7 @@ static int launch_attn_bwd(const fb::BwdArgs &a0, const void *pack, cudaStream_t
     if (flag && grid > 148 * 8) grid = 148 * 8;
     const size_t smem = (size_t)8 * M * sizeof(float);
     if (smem > 48 * 1024) return set_error(CLUSTEN_EUNSUPPORTED, "fused attention backward: M=%d too large", M);
-    fb::attn_bwd_generic_kernel<T><<<grid, 256, smem, st>>>(a, flag);
+    fb::attn_bwd_generic_kernel<T, PB><<<grid, 256, smem, st>>>(a, flag);
     note_launches(1);
     return check_launch("attn_bwd_generic");
 }
@@ -470,6 +526,44 @@ extern "C" int clusten_attn_bwd(const void *d_out, const void *out, const float 
                   B, H, Nq, Nk, C, M, (int)q_sh, (int)q_sn, (int)k_sh, (int)k_sn, (int)v_sh, (int)v_sn, (int)do_sh, (int)do_sn,
                   (int)o_sh, (int)o_sn, (int)dq_sh, (int)dq_sn, q_sb, k_sb, v_sb, do_sb, o_sb, dq_sb, 0};
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == CLUSTEN_F16) return launch_attn_bwd<__half>(a, pack, st);
-    return launch_attn_bwd<__nv_bfloat16>(a, pack, st);
+    if (dtype == CLUSTEN_F16) return launch_attn_bwd<__half, false>(a, pack, st);
+    return launch_attn_bwd<__nv_bfloat16, false>(a, pack, st);
+}
+
+// The same backward for the position-bias variant (clusten_attn_pos_fwd): no bias table; the gradient of pos_embed
+// comes out as pe_grad_parts [1024][H][6] fp32 partial sums (accumulated INTO with atomics; caller zeroes the buffer and sums
+// over the first dimension): [.., h, 0:5] = d_pe_weight[h, :], [.., h, 5] = d_pe_bias[h].
+extern "C" int clusten_attn_pos_bwd(const void *d_out, const void *out, const float *lse, const void *q, const void *k, const void *v,
+                                    const int64_t *nbhd_idx, const void *pack, const float *pos_q, const float *pos_k,
+                                    const float *pe_weight, const float *pe_bias,
+                                    const uint8_t *mask, const void *blank_k, const void *blank_v,
+                                    void *d_q, void *probs, void *d_logits, float *p_blank, float *ds_blank, float *pe_grad_parts,
+                                    int B, int H, int Nq, int Nk, int C, int M,
+                                    int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t k_sb, int64_t k_sh, int64_t k_sn,
+                                    int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t do_sb, int64_t do_sh, int64_t do_sn,
+                                    int64_t o_sb, int64_t o_sh, int64_t o_sn, int64_t dq_sb, int64_t dq_sh, int64_t dq_sn,
+                                    int dtype, void *stream) {
+    if (B < 0 || H <= 0 || Nq < 0 || Nk <= 0 || C <= 0 || M <= 0)
+        return set_error(CLUSTEN_EINVAL, "bad sizes B=%d H=%d Nq=%d Nk=%d C=%d M=%d", B, H, Nq, Nk, C, M);
+    if (!d_out || !out || !lse || !q || !k || !v || !nbhd_idx || !pos_q || !pos_k || !pe_weight || !blank_k || !blank_v || !d_q ||
+        !probs || !d_logits || !p_blank || !ds_blank || !pe_grad_parts)
+        return set_error(CLUSTEN_EINVAL, "null pointer");
+    if (dtype != CLUSTEN_F16 && dtype != CLUSTEN_BF16)
+        return set_error(CLUSTEN_EUNSUPPORTED, "fused attention backward supports fp16 / bf16 only (dtype %d)", dtype);
+    if ((reinterpret_cast<uintptr_t>(pos_q) | reinterpret_cast<uintptr_t>(pos_k)) & 7u)
+        return set_error(CLUSTEN_EUNSUPPORTED, "positions must be 8-byte aligned");
+    if ((int64_t)B * Nq == 0) return 0;
+    const int64_t lim[] = {Nq * q_sn + H * q_sh, (int64_t)Nk * k_sn + H * k_sh, (int64_t)Nk * v_sn + H * v_sh, Nq * do_sn + H * do_sh,
+                           Nq * o_sn + H * o_sh, Nq * dq_sn + H * dq_sh, (int64_t)H * Nq * M};
+    for (int64_t x : lim)
+        if (!fb_fits31(x)) return set_error(CLUSTEN_EUNSUPPORTED, "fused attention backward: per-sample extent exceeds 2^31 elements");
+    fb::BwdArgsPB a;
+    static_cast<fb::BwdArgs &>(a) = fb::BwdArgs{q, k, v, d_out, out, nbhd_idx, nullptr, nullptr, mask, blank_k, blank_v, lse, d_q, probs,
+                                                d_logits, p_blank, ds_blank, B, H, Nq, Nk, C, M, (int)q_sh, (int)q_sn, (int)k_sh, (int)k_sn,
+                                                (int)v_sh, (int)v_sn, (int)do_sh, (int)do_sn, (int)o_sh, (int)o_sn, (int)dq_sh, (int)dq_sn,
+                                                q_sb, k_sb, v_sb, do_sb, o_sb, dq_sb, 0};
+    a.pos_q = pos_q; a.pos_k = pos_k; a.pe_w = pe_weight; a.pe_b = pe_bias; a.pe_parts = pe_grad_parts;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CLUSTEN_F16) return launch_attn_bwd<__half, true>(a, pack, st);
+    return launch_attn_bwd<__nv_bfloat16, true>(a, pack, st);
 }

@@ -459,6 +459,135 @@ def cluster_attention_core(q, kv, bias_tab, blank_k, blank_v, nbhd_idx, bias_idx
     return ClusterAttentionCoreFunction.apply(q, kv, bias_tab, blank_k, blank_v, nbhd_idx, bias_idx, mask, count)
 
 
+# ---- the same core with the relative-position bias computed in the kernels (opt-in, round-2 work) -----------------------------
+PE_GRAD_PARTS = 1024                      # partial-sum slots of the pos_embed gradient (posbias.cuh: PB_PARTS)
+
+
+def _check_pos_args(B, N, H, pos, pe_weight, pe_bias):
+    _check_shapes(pos.dtype == torch.float32 and tuple(pos.shape) == (B, N, 2), "fused attention: pos must be fp32 [B,N,2]")
+    _check_shapes(tuple(pe_weight.shape) == (H, 5) and (pe_bias is None or tuple(pe_bias.shape) == (H,)),
+                  "fused attention: pos_embed must be Linear(5, heads)")
+
+
+def cluster_attention_fused_pos(q, key, v, nbhd_idx, pos, pe_weight, pe_bias, mask, blank_k, blank_v):
+    """``cluster_attention_fused`` with the bias ``pos_embed(pre_table)[pe_idx]`` (aff.py:129-132) computed from the token
+    positions inside the kernel (clusten_attn_pos_fwd): pos fp32 [B,N,2] (x, y) of the stage's tokens (queries = keys),
+    pe_weight [H,5] / pe_bias [H] the parameters of ``pos_embed``.  No autograd: inference path."""
+    dev = _lib.require_cuda(q, key, v, nbhd_idx, pos, pe_weight, pe_bias, mask, blank_k, blank_v)
+    B, H, Nq, C = q.shape
+    Nk, M = key.shape[2], nbhd_idx.shape[2]
+    dt = q.dtype
+    q, key, v, nbhd_idx = _rows(q), _rows(key.to(dt)), _rows(v.to(dt)), _idx(nbhd_idx)
+    _check_shapes(Nq == Nk, "fused attention with in-kernel bias: queries and keys are the same token set")
+    pos = pos.contiguous()
+    _check_pos_args(B, Nq, H, pos, pe_weight, pe_bias)
+    w = pe_weight.detach().to(torch.float32).contiguous()
+    b_ = None if pe_bias is None else pe_bias.detach().to(torch.float32).contiguous()
+    if mask is not None:
+        _check_shapes(mask.dtype == torch.uint8 and tuple(mask.shape) == (B, Nq, M) and mask.is_contiguous(), "fused attention: mask must be uint8 [B,N,M]")
+    blank_k, blank_v = blank_k.to(dt).contiguous(), blank_v.to(dt).contiguous()
+    out = torch.empty((B, Nq, H, C), dtype=dt, device=dev)
+    ov = out.permute(0, 2, 1, 3)
+    if out.numel():
+        with torch.cuda.device(dev):
+            _call("clusten_attn_pos_fwd", dev, q.data_ptr(), key.data_ptr(), v.data_ptr(), nbhd_idx.data_ptr(),
+                  _lib.ptr(neighbourhood_pack(nbhd_idx, Nk, mask=mask)), pos.data_ptr(), pos.data_ptr(), w.data_ptr(), _lib.ptr(b_),
+                  _lib.ptr(mask), blank_k.data_ptr(), blank_v.data_ptr(), out.data_ptr(), 0, 0, B, H, Nq, Nk, C, M,
+                  *_s3(q), *_s3(key), *_s3(v), *_s3(ov), _lib.dtype_code(q),
+                  nbytes=q.element_size() * (B * H * (2 * Nq + 2 * Nk) * C) + 8 * B * Nq * M + 8 * B * (Nq + Nk))
+    return out.reshape(B, Nq, H * C)
+
+
+class ClusterAttentionPosFunction(Function):
+    """``ClusterAttentionCoreFunction`` with the relative-position bias computed from positions in the kernels instead of
+    gathered from ``bias_tab[bias_idx]``: no bias-index operand, no table gathers, and the gradient of ``pos_embed`` comes out
+    of the backward kernel as partial sums of dS * [feat | 1] (no clusten_table_grad pass).  fp16 / bf16 training."""
+
+    @staticmethod
+    def forward(ctx, q, kv, pe_weight, pe_bias, blank_k, blank_v, nbhd_idx, pos, mask):
+        dev = _lib.require_cuda(q, kv, pe_weight, pe_bias, blank_k, blank_v, nbhd_idx, pos, mask)
+        _check_shapes(q.dim() == 4 and kv.dim() == 5 and kv.shape[3] == 2 and q.dtype == kv.dtype and
+                      q.dtype in (torch.float16, torch.bfloat16), "fused attention: q [B,N,H,C], kv [B,N,H,2,C], fp16/bf16")
+        B, N, H, C = q.shape
+        M = nbhd_idx.shape[2]
+        dt = q.dtype
+        q, kv, nbhd_idx, pos = q.contiguous(), kv.contiguous(), _idx(nbhd_idx), pos.contiguous()
+        _check_pos_args(B, N, H, pos, pe_weight, pe_bias)
+        w = pe_weight.detach().to(torch.float32).contiguous()
+        b_ = None if pe_bias is None else pe_bias.detach().to(torch.float32).contiguous()
+        bk, bv = blank_k.detach().to(dt).contiguous(), blank_v.detach().to(dt).contiguous()
+        if mask is not None:
+            _check_shapes(mask.dtype == torch.uint8 and tuple(mask.shape) == (B, N, M) and mask.is_contiguous(), "fused attention: mask must be uint8 [B,N,M]")
+        out = torch.empty((B, N, H, C), dtype=dt, device=dev)
+        lse = torch.empty((B, H, N), dtype=torch.float32, device=dev)
+        qv, kk, vv, ov = q.permute(0, 2, 1, 3), kv[:, :, :, 0].permute(0, 2, 1, 3), kv[:, :, :, 1].permute(0, 2, 1, 3), out.permute(0, 2, 1, 3)
+        if out.numel():
+            with torch.cuda.device(dev):
+                _call("clusten_attn_pos_fwd", dev, qv.data_ptr(), kk.data_ptr(), vv.data_ptr(), nbhd_idx.data_ptr(),
+                      _lib.ptr(neighbourhood_pack(nbhd_idx, N, mask=mask)), pos.data_ptr(), pos.data_ptr(), w.data_ptr(), _lib.ptr(b_),
+                      _lib.ptr(mask), bk.data_ptr(), bv.data_ptr(), out.data_ptr(), 0, lse.data_ptr(), B, H, N, N, C, M,
+                      *_s3(qv), *_s3(kk), *_s3(vv), *_s3(ov), _lib.dtype_code(q),
+                      nbytes=q.element_size() * (B * H * 4 * N * C) + 8 * B * N * M + 16 * B * N)
+        ctx.save_for_backward(q, kv, w, b_, bk, bv, out, lse, nbhd_idx, pos, mask)
+        ctx.meta = (pe_weight.dtype, None if pe_bias is None else pe_bias.dtype, blank_k.dtype, blank_v.dtype)
+        return out.view(B, N, H * C)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, kv, w, b_, bk, bv, out, lse, nbhd_idx, pos, mask = ctx.saved_tensors
+        dev = q.device
+        B, N, H, C = q.shape
+        M = nbhd_idx.shape[2]
+        dt = q.dtype
+        d_out = d_out.to(dt).contiguous().view(B, N, H, C)
+        d_q = torch.empty_like(q)
+        d_kv = torch.empty_like(kv)
+        P = torch.empty((B, H, N, M), dtype=dt, device=dev)
+        dS = torch.empty((B, H, N, M), dtype=dt, device=dev)
+        Pb = torch.empty((B, H, N), dtype=torch.float32, device=dev)
+        dSb = torch.empty((B, H, N), dtype=torch.float32, device=dev)
+        parts = torch.zeros((PE_GRAD_PARTS, H, 6), dtype=torch.float32, device=dev)
+        hv = lambda t: t.permute(0, 2, 1, 3)
+        qv, gv = hv(q), hv(d_out)
+        code = _lib.dtype_code(q)
+        es = q.element_size()
+        if q.numel():
+            kk, vv, ov, dqv = hv(kv[:, :, :, 0]), hv(kv[:, :, :, 1]), hv(out), hv(d_q)
+            dkv, dvv = hv(d_kv[:, :, :, 0]), hv(d_kv[:, :, :, 1])
+            pack = neighbourhood_pack(nbhd_idx, N, inverse=True, mask=mask)
+            off, ent = inverse_neighbour_list(nbhd_idx, N, with_pack=True, pack_buf=pack if mask is not None else None)
+            with torch.cuda.device(dev):
+                _call("clusten_attn_pos_bwd", dev, gv.data_ptr(), ov.data_ptr(), lse.data_ptr(), qv.data_ptr(), kk.data_ptr(), vv.data_ptr(),
+                      nbhd_idx.data_ptr(), _lib.ptr(pack), pos.data_ptr(), pos.data_ptr(), w.data_ptr(), _lib.ptr(b_), _lib.ptr(mask),
+                      bk.data_ptr(), bv.data_ptr(), d_q.data_ptr(), P.data_ptr(), dS.data_ptr(), Pb.data_ptr(), dSb.data_ptr(),
+                      parts.data_ptr(), B, H, N, N, C, M, *_s3(qv), *_s3(kk), *_s3(vv), *_s3(gv), *_s3(ov), *_s3(dqv), code,
+                      nbytes=es * (6 * B * H * N * C + 2 * B * H * N * M) + 8 * B * N * M + 16 * B * N)
+                _call("clusten_scatter_rows", dev, dS.data_ptr(), qv.data_ptr(), off.data_ptr(), ent.data_ptr(), _lib.ptr(pack),
+                      dkv.data_ptr(), B, H, N, N, C, M, *_s3(dS), *_s3(qv), *_s3(dkv), code,
+                      nbytes=es * (B * H * N * M + 2 * B * H * N * C) + 8 * B * N * M)
+                _call("clusten_scatter_rows", dev, P.data_ptr(), gv.data_ptr(), off.data_ptr(), ent.data_ptr(), _lib.ptr(pack),
+                      dvv.data_ptr(), B, H, N, N, C, M, *_s3(P), *_s3(gv), *_s3(dvv), code,
+                      nbytes=es * (B * H * N * M + 2 * B * H * N * C) + 8 * B * N * M)
+        if q.numel() and C % 8 == 0 and H * C <= 2048:
+            d_bk = torch.zeros(H * C, dtype=torch.float32, device=dev)
+            d_bv = torch.zeros(H * C, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _call("clusten_blank_grad", dev, qv.data_ptr(), gv.data_ptr(), dSb.data_ptr(), Pb.data_ptr(), d_bk.data_ptr(),
+                      d_bv.data_ptr(), B, H, N, C, *_s3(qv), *_s3(gv), code, nbytes=es * 2 * B * H * N * C + 8 * B * H * N)
+        else:
+            d_bk = torch.einsum("bhn,bnhc->hc", dSb.to(dt), q).reshape(-1)
+            d_bv = torch.einsum("bhn,bnhc->hc", Pb.to(dt), d_out).reshape(-1)
+        g = parts.sum(0)                                                   # [H, 6]
+        wdt, bdt, kdt, vdt = ctx.meta
+        d_w = g[:, :5].to(wdt)
+        d_b = None if bdt is None else g[:, 5].to(bdt)
+        return d_q, d_kv, d_w, d_b, d_bk.to(kdt), d_bv.to(vdt), None, None, None
+
+
+def cluster_attention_core_pos(q, kv, pe_weight, pe_bias, blank_k, blank_v, nbhd_idx, pos, mask):
+    return ClusterAttentionPosFunction.apply(q, kv, pe_weight, pe_bias, blank_k, blank_v, nbhd_idx, pos, mask)
+
+
 # ---- LayerNorm -------------------------------------------------------------------------------------------------------
 class LayerNormFunction(Function):
     """LayerNorm over the last dimension (C <= 1024), one warp per row (clusten_layer_norm_fwd / _bwd).  ``out_dtype`` lets

@@ -142,6 +142,31 @@ int clusten_attn_bwd(const void *d_out, const void *out, const float *lse, const
                      int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t do_sb, int64_t do_sh, int64_t do_sn,
                      int64_t o_sb, int64_t o_sh, int64_t o_sn, int64_t dq_sb, int64_t dq_sh, int64_t dq_sn,
                      int dtype, void *stream);
+/* ---- the fused core with the relative-position bias COMPUTED from token positions instead of gathered from a table
+ * (opt-in, round-2 work: CLUSTEN_INKERNEL_BIAS=1 in the Python layer; see DESIGN.md section 7 for its validation status):
+ *   bias[b,h,i,j] = pe_weight[h,:] . feat(rel) + pe_bias[h],  rel = trunc(clamp(pos_k[idx[b,i,j]] - (pos_q[i] - 511), 0, 1022)) - 511,
+ *   feat = (dx, dy, dist, dy/dist, dx/dist) with the centre zeroed -- exactly pos_embed(pre_table)[pe_idx] of aff.py:17-31,129-132,
+ *   481-485.  pos_q [B,Nq,2] / pos_k [B,Nk,2] fp32 (x, y), pe_weight fp32 [H,5], pe_bias fp32 [H] or NULL; everything else as in
+ *   clusten_attn_fwd / clusten_attn_bwd.  Backward: pe_grad_parts fp32 [1024][H][6], accumulated INTO (caller zeroes it and sums
+ *   over the first dimension): [.., h, 0:5] = d_pe_weight[h,:], [.., h, 5] = d_pe_bias[h]. */
+int clusten_attn_pos_fwd(const void *q, const void *k, const void *v, const int64_t *nbhd_idx, const void *pack,
+                         const float *pos_q, const float *pos_k, const float *pe_weight, const float *pe_bias,
+                         const uint8_t *mask, const void *blank_k, const void *blank_v, void *out, float *probs, float *lse,
+                         int B, int H, int Nq, int Nk, int C, int M,
+                         int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t k_sb, int64_t k_sh, int64_t k_sn,
+                         int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t o_sb, int64_t o_sh, int64_t o_sn,
+                         int dtype, void *stream);
+int clusten_attn_pos_bwd(const void *d_out, const void *out, const float *lse, const void *q, const void *k, const void *v,
+                         const int64_t *nbhd_idx, const void *pack, const float *pos_q, const float *pos_k,
+                         const float *pe_weight, const float *pe_bias,
+                         const uint8_t *mask, const void *blank_k, const void *blank_v,
+                         void *d_q, void *probs, void *d_logits, float *p_blank, float *ds_blank, float *pe_grad_parts,
+                         int B, int H, int Nq, int Nk, int C, int M,
+                         int64_t q_sb, int64_t q_sh, int64_t q_sn, int64_t k_sb, int64_t k_sh, int64_t k_sn,
+                         int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t do_sb, int64_t do_sh, int64_t do_sn,
+                         int64_t o_sb, int64_t o_sh, int64_t o_sn, int64_t dq_sb, int64_t dq_sh, int64_t dq_sn,
+                         int dtype, void *stream);
+
 /* blank-token parameter gradients of the fused core (aff.py:138-146 backwards), 16-bit q / d_out as strided [B,H,N,C] views,
  * dS_blank / P_blank fp32 [B,H,N] as written by clusten_attn_bwd; d_blank_k / d_blank_v fp32 [H*C], accumulated INTO
  * (caller zeroes them).  One pass over q and d_out instead of two skinny GEMMs. */

@@ -1,6 +1,8 @@
 """GPU parity: the four CLUSTEN autograd Functions (ctypes -> C ABI -> sm_100a kernels) against the CPU oracle on the
 same seeded inputs.  Tolerances (BASELINE north_star): max|a-b|/max|b| <= 1e-5 fp32, <= 1e-2 bf16/fp16 (vs the fp32
 oracle on inputs rounded to the low-precision type)."""
+import os
+
 import pytest
 import torch
 
@@ -538,6 +540,76 @@ def test_fused_attention_core_backward(n, m, nbhd, kind, H, C, dtype):
     for name, got, ref in (("d_q", cq, rq), ("d_kv", ckv, rkv), ("d_bias_tab", ctab, rtab), ("d_blank_k", cbk, rbk), ("d_blank_v", cbv, rbv)):
         e = rel_err(got.grad.float().cpu(), ref.grad)
         assert e <= 2 * tol, f"{name} rel err {e:.3e}"
+
+
+INKERNEL_BIAS = os.environ.get("CLUSTEN_INKERNEL_BIAS") == "1"
+
+
+def _pos_bias_case(n, m, nbhd, kind, H, B=2, hw=64):
+    """Positions, neighbourhoods, mask and the table formulation of the bias (aff.py:481-485 + 17-31 + 129) for one stage."""
+    from autofocusformermod_b200.aff import rel_pos_features
+    pos, idx, mask, _ = inputs.structured_neighbourhood(B, n, hw, hw, m, nbhd, seed=n)
+    if kind == "random":
+        idx, mask = inputs.random_neighbourhood(B, n, n, nbhd, seed=n), None
+    M = idx.shape[-1]
+    rel = (pos.gather(1, idx.reshape(B, -1, 1).expand(-1, -1, 2)).reshape(B, n, M, 2) - (pos.unsqueeze(2) - 511)).clamp(0, 1022).long()
+    pe_idx = rel[..., 1] * 1023 + rel[..., 0]
+    uniq, inverse = torch.unique(pe_idx.reshape(-1), return_inverse=True)
+    g = torch.Generator().manual_seed(n + 3 * H)
+    W, bvec = torch.randn(H, 5, generator=g) * 0.2, torch.randn(H, generator=g)
+    return pos.float(), idx, mask, rel_pos_features(uniq), inverse.reshape(B, n, M).to(torch.int32), W, bvec
+
+
+@pytest.mark.skipif(not INKERNEL_BIAS, reason="opt-in round-2 kernels (clusten_attn_pos_*): set CLUSTEN_INKERNEL_BIAS=1")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("H,C", [(2, 16), (3, 32)])
+@pytest.mark.parametrize("n,m,nbhd,kind", [(1024, 8, 48, "clustered"), (2003, 8, 48, "clustered"), (1540, 24, 144, "clustered"),
+                                            (300, 8, 48, "random")])
+def test_inkernel_bias_forward_matches_table_variant(n, m, nbhd, kind, H, C, dtype):
+    """clusten_attn_pos_fwd (bias computed from positions) against clusten_attn_fwd (bias gathered from pos_embed's table)."""
+    from autofocusformermod_b200 import ops
+    B = 2
+    pos, idx, mask, feats, bias_idx, W, bvec = _pos_bias_case(n, m, nbhd, kind, H, B)
+    g = torch.Generator().manual_seed(n + H)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dtype).cuda()
+    q, k, v = rnd(B, H, n, C) * C ** -0.5, rnd(B, H, n, C), rnd(B, H, n, C)
+    bk, bv = rnd(H * C), rnd(H * C)
+    m8 = None if mask is None else mask.to(torch.uint8).cuda()
+    tab = (feats @ W.t() + bvec).cuda()
+    ref = ops.cluster_attention_fused(q, k, v, idx.cuda(), tab, bias_idx.cuda(), m8, bk, bv)
+    out = ops.cluster_attention_fused_pos(q, k, v, idx.cuda(), pos.cuda(), W.cuda(), bvec.cuda(), m8, bk, bv)
+    torch.cuda.synchronize()
+    assert rel_err(out.float(), ref.float()) <= (2e-5 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.skipif(not INKERNEL_BIAS, reason="opt-in round-2 kernels (clusten_attn_pos_*): set CLUSTEN_INKERNEL_BIAS=1")
+@pytest.mark.parametrize("H,C", [(2, 32), (4, 16)])
+@pytest.mark.parametrize("n,m,nbhd,kind", [(1024, 8, 48, "clustered"), (2003, 8, 48, "clustered"), (1540, 24, 144, "clustered"),
+                                            (300, 8, 48, "random")])
+def test_inkernel_bias_training_matches_table_variant(n, m, nbhd, kind, H, C):
+    """ClusterAttentionPosFunction against ClusterAttentionCoreFunction behind table_linear: output and every gradient
+    (q, kv, pos_embed weight / bias, blank tokens)."""
+    from autofocusformermod_b200 import ops
+    B, dt = 2, torch.bfloat16
+    pos, idx, mask, feats, bias_idx, W, bvec = _pos_bias_case(n, m, nbhd, kind, H, B)
+    g = torch.Generator().manual_seed(n + H)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    q0, kv0 = (rnd(B, n, H, C) * C ** -0.5).to(dt), rnd(B, n, H, 2, C).to(dt)
+    bk0, bv0, go = rnd(H * C), rnd(H * C), rnd(B, n, H * C).to(dt).cuda()
+    m8 = None if mask is None else mask.to(torch.uint8).cuda()
+    res = []
+    for variant in ("table", "pos"):
+        leaf = lambda t: t.detach().clone().cuda().requires_grad_(True)
+        q, kv, w, b_, bk, bv = leaf(q0), leaf(kv0), leaf(W), leaf(bvec), leaf(bk0), leaf(bv0)
+        if variant == "table":
+            out = ops.cluster_attention_core(q, kv, ops.table_linear(feats.cuda(), w, b_), bk, bv, idx.cuda(), bias_idx.cuda(), m8)
+        else:
+            out = ops.cluster_attention_core_pos(q, kv, w, b_, bk, bv, idx.cuda(), pos.cuda(), m8)
+        out.backward(go)
+        res.append([out] + [t.grad for t in (q, kv, w, b_, bk, bv)])
+    torch.cuda.synchronize()
+    for name, a, r in zip(("out", "d_q", "d_kv", "d_pe_weight", "d_pe_bias", "d_blank_k", "d_blank_v"), res[1], res[0]):
+        assert rel_err(a.float(), r.float()) <= 2e-2, name
 
 
 @pytest.mark.parametrize("xdt,ydt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16)],
