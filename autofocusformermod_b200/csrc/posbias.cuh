@@ -1,5 +1,5 @@
-// Relative-position bias computed from token positions inside the attention kernels (round-2 work, opt-in: the
-// clusten_attn_pos_* entry points; NOT yet validated on hardware when this header was written -- see DESIGN.md section 7).
+// Relative-position bias computed from token positions inside the attention kernels (opt-in: the clusten_attn_pos_* entry
+// points; first parity cases green on a B200, not yet timed -- see DESIGN.md section 7).
 //
 // The reference gathers it from a table: bias[b,h,i,j] = pos_embed(pre_table)[pe_idx[b,i,j], h] with
 //   rel    = clamp(pos[idx[b,i,j]] - (pos[i] - 511), 0, 1022) truncated to an integer        (backbone/aff.py:481-485)

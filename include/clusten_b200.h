@@ -143,7 +143,7 @@ int clusten_attn_bwd(const void *d_out, const void *out, const float *lse, const
                      int64_t o_sb, int64_t o_sh, int64_t o_sn, int64_t dq_sb, int64_t dq_sh, int64_t dq_sn,
                      int dtype, void *stream);
 /* ---- the fused core with the relative-position bias COMPUTED from token positions instead of gathered from a table
- * (opt-in, round-2 work: CLUSTEN_INKERNEL_BIAS=1 in the Python layer; see DESIGN.md section 7 for its validation status):
+ * (opt-in: CLUSTEN_INKERNEL_BIAS=1 in the Python layer; see DESIGN.md section 7 for its validation status):
  *   bias[b,h,i,j] = pe_weight[h,:] . feat(rel) + pe_bias[h],  rel = trunc(clamp(pos_k[idx[b,i,j]] - (pos_q[i] - 511), 0, 1022)) - 511,
  *   feat = (dx, dy, dist, dy/dist, dx/dist) with the centre zeroed -- exactly pos_embed(pre_table)[pe_idx] of aff.py:17-31,129-132,
  *   481-485.  pos_q [B,Nq,2] / pos_k [B,Nk,2] fp32 (x, y), pe_weight fp32 [H,5], pe_bias fp32 [H] or NULL; everything else as in
