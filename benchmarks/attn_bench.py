@@ -2,7 +2,7 @@
 stage shape: per-entry device time, algorithmic bytes, achieved GB/s.  Index tensors come from the reference pipeline
 (oracle clustering + kNN on a random token subset), so padded last clusters (n % m != 0) show their real cost.
 
-    python benchmarks/attn_bench.py --n 655 --heads 8 --batch 32 [--m 8 --nbhd 48 --c 32 --dtype bf16|f16|f32 --iters 10]   (f32: inference forward only)
+    python benchmarks/attn_bench.py --n 655 --heads 8 --batch 32 [--m 8 --nbhd 48 --c 32 --dtype bf16|f16|f32 --iters 10 --inkernel-bias]   (f32: inference forward only)
 """
 import argparse
 import json
@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--fwd-only", action="store_true")
+    ap.add_argument("--inkernel-bias", action="store_true", help="the clusten_attn_pos_* variant: bias computed from positions in the kernels")
     args = ap.parse_args()
     from autofocusformermod_b200 import ops
     from oracle import inputs
@@ -34,7 +35,8 @@ def main():
     if dt == torch.float32:
         args.fwd_only = True                              # fp32 runs the fused kernel on the inference path only
     B, N, H, C = args.batch, args.n, args.heads, args.c
-    _, nb, mask, pe_idx = inputs.structured_neighbourhood(1, N, args.grid, args.grid, args.m, args.nbhd, seed=0)
+    pos, nb, mask, pe_idx = inputs.structured_neighbourhood(1, N, args.grid, args.grid, args.m, args.nbhd, seed=0)
+    pos = pos.float().expand(B, -1, -1).contiguous().cuda()
     M = nb.shape[-1]
     idx = nb.expand(B, -1, -1).contiguous().cuda()
     mask8 = None if mask is None else mask.expand(B, -1, -1).contiguous().to(torch.uint8).cuda()
@@ -44,6 +46,8 @@ def main():
     q = (torch.randn(B, N, H, C, device="cuda", generator=g) * C ** -0.5).to(dt).requires_grad_(True)
     kv = torch.randn(B, N, H, 2, C, device="cuda", generator=g).to(dt).requires_grad_(True)
     tab = torch.randn(uniq.numel(), H, device="cuda", generator=g).requires_grad_(True)
+    pe_w = (torch.randn(H, 5, device="cuda", generator=g) * 0.2).requires_grad_(True)
+    pe_b = torch.randn(H, device="cuda", generator=g).requires_grad_(True)
     bk = torch.randn(H * C, device="cuda", generator=g).to(dt).requires_grad_(True)
     bv = torch.randn(H * C, device="cuda", generator=g).to(dt).requires_grad_(True)
     go = torch.randn(B, N, H * C, device="cuda", generator=g).to(dt)
@@ -57,9 +61,15 @@ def main():
         if dt == torch.float32:
             with torch.no_grad():
                 kvp = kv.permute(3, 0, 2, 1, 4)
-                ops.cluster_attention_fused(q.permute(0, 2, 1, 3), kvp[0], kvp[1], idx, tab, bias_idx, mask8, bk, bv)
+                if args.inkernel_bias:
+                    ops.cluster_attention_fused_pos(q.permute(0, 2, 1, 3), kvp[0], kvp[1], idx, pos, pe_w, pe_b, mask8, bk, bv)
+                else:
+                    ops.cluster_attention_fused(q.permute(0, 2, 1, 3), kvp[0], kvp[1], idx, tab, bias_idx, mask8, bk, bv)
         else:
-            out = ops.cluster_attention_core(q, kv, tab, bk, bv, idx, bias_idx, mask8)
+            if args.inkernel_bias:
+                out = ops.cluster_attention_core_pos(q, kv, pe_w, pe_b, bk, bv, idx, pos, mask8)
+            else:
+                out = ops.cluster_attention_core(q, kv, tab, bk, bv, idx, bias_idx, mask8)
             if not args.fwd_only:
                 out.backward(go)
         if it >= 3:
