@@ -44,6 +44,9 @@ GRID_STRUCTURE_CACHE = os.environ.get("CLUSTEN_GRID_CACHE", "1") != "0"        #
 NATIVE_TABLE_LINEAR = os.environ.get("CLUSTEN_TABLE_LINEAR", "1") != "0"      # pos_embed = Linear(5, heads) over the referenced table rows by clusten_table_linear_* (see TableLinear)
 # opt-in (round-2 work): relative-position bias computed from positions inside the fused attention kernels
 INKERNEL_BIAS = os.environ.get("CLUSTEN_INKERNEL_BIAS", "0") == "1"
+# opt-in: under autocast run the merge's WF in the autocast dtype (tensor-core kernels) instead of fp32 like the reference under AMP,
+# whose CLUSTENWF casts feat up to the fp32 weights (clusten.py:80-81); not yet timed on hardware
+MERGE_WF_AUTOCAST = os.environ.get("CLUSTEN_MERGE_WF_AUTOCAST", "0") == "1"
 FUSED_RESIDUAL = os.environ.get("CLUSTEN_FUSED_RESIDUAL", "1") != "0"           # residual + layer scale + stochastic depth in one kernel (see ClusterTransformerBlock._residual)
 NATIVE_WEIGHT_NET_NORM = os.environ.get("CLUSTEN_WEIGHT_NET_NORM", "1") != "0"   # LayerNorm(4) of the merge's weight_net through clusten_layer_norm_* (see ClusterMerging)
 
@@ -338,6 +341,8 @@ class ClusterMerging(nn.Module):
             weights = weights * lp
         elif cluster_mask is not None:
             weights = weights * cluster_mask.unsqueeze(3)
+        if MERGE_WF_AUTOCAST and torch.is_autocast_enabled() and weights.dtype == torch.float32:
+            weights = weights.to(torch.get_autocast_dtype("cuda"))
         feat = CLUSTENWFFunction.apply(weights, feat, member_idx).reshape(b, n2, -1)                 # aff.py:361
         return pos, self.linear(self.norm(feat))
 
