@@ -25,7 +25,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .ops import (CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction, cluster_attention_core, cluster_attention_fused,
-                  cluster_attention_core_pos, cluster_attention_fused_pos, layer_norm, linear, scale_residual, table_linear,
+                  cluster_attention_core_pos, cluster_attention_fused_pos, layer_norm, linear, linear_f32, linear_f32_supported,
+                  scale_residual, table_linear,
                   table_linear_supported, table_lookup)
 from .point_utils import knn_keops, merge_select, space_filling_cluster, stage_prepare
 
@@ -44,6 +45,9 @@ GRID_STRUCTURE_CACHE = os.environ.get("CLUSTEN_GRID_CACHE", "1") != "0"        #
 NATIVE_TABLE_LINEAR = os.environ.get("CLUSTEN_TABLE_LINEAR", "1") != "0"      # pos_embed = Linear(5, heads) over the referenced table rows by clusten_table_linear_* (see TableLinear)
 # opt-in (round-2 work): relative-position bias computed from positions inside the fused attention kernels
 INKERNEL_BIAS = os.environ.get("CLUSTEN_INKERNEL_BIAS", "0") == "1"
+# opt-in: fp32 inference Linear layers on the tensor cores with the 3xTF32 split (clusten_linear_f32) instead of cuBLAS SIMT sgemm;
+# not yet run on hardware
+TC_LINEAR = os.environ.get("CLUSTEN_TC_LINEAR", "0") == "1"
 # opt-in: under autocast run the merge's WF in the autocast dtype (tensor-core kernels) instead of fp32 like the reference under AMP,
 # whose CLUSTENWF casts feat up to the fp32 weights (clusten.py:80-81); not yet timed on hardware
 MERGE_WF_AUTOCAST = os.environ.get("CLUSTEN_MERGE_WF_AUTOCAST", "0") == "1"
@@ -134,6 +138,9 @@ class Linear(nn.Linear):
     def forward(self, x):
         if FAST_LINEAR_BACKWARD and x.is_cuda and torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
             return linear(x, self.weight, self.bias)
+        if (TC_LINEAR and not torch.is_grad_enabled() and not torch.is_autocast_enabled()
+                and linear_f32_supported(x, self.weight, self.bias)):
+            return linear_f32(x, self.weight, self.bias)
         return F.linear(x, self.weight, self.bias)
 
 

@@ -784,6 +784,30 @@ def col_sum(x2d):
     return out
 
 
+def linear_f32_supported(x, weight, bias):
+    K = x.shape[-1]
+    return bool(x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.dim() == 2 and weight.shape[1] == K
+                and (bias is None or bias.dtype == torch.float32) and K % 32 == 0 and weight.shape[0] % 2 == 0 and x.numel() > 0
+                and x.numel() // K < 2 ** 31 - 128)
+
+
+def linear_f32(x, weight, bias=None):
+    """fp32 ``F.linear`` on the tensor cores with the 3xTF32 split (clusten_linear_f32; inference, no autograd).  Opt-in: the
+    caller checks ``linear_f32_supported`` first."""
+    dev = _lib.require_cuda(x, weight, bias)
+    K, N = x.shape[-1], weight.shape[0]
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1 or x2.stride(0) % 4 or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    w = weight.detach().contiguous()
+    b = None if bias is None else bias.detach().contiguous()
+    y = torch.empty((x2.shape[0], N), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call("clusten_linear_f32", dev, x2.data_ptr(), w.data_ptr(), _lib.ptr(b), y.data_ptr(), x2.shape[0], K, N, x2.stride(0), N,
+              nbytes=4 * (x2.shape[0] * (K + N) + N * K))
+    return y.view(*x.shape[:-1], N)
+
+
 class LinearFunction(Function):
     """``F.linear`` whose backward takes the bias gradient with clusten_col_sum (one coalesced pass, fp32 accumulation) instead
     of ATen's generic reduction; the two GEMMs of the backward stay in cuBLAS.  Autocast-aware like the native op: under

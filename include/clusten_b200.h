@@ -227,6 +227,13 @@ int clusten_table_linear_fwd(const float *feat, const float *weight, const float
 int clusten_table_linear_bwd(const float *d_out, const float *feat, float *d_weight, float *d_bias, int R, int F, int H,
                              const int32_t *count, void *stream);
 
+/* ---- fp32 Linear layer on the tensor cores (3xTF32 split, fp32-level accuracy): y[r,n] = sum_k x[r,k] * weight[n,k] + bias[n]
+ * -- the q / kv / proj / fc1 / fc2 layers of the block (aff.py:62-70,103-106) in fp32 inference.  x [R,K] with row stride ldx,
+ * weight [N,K] contiguous, bias [N] or NULL, y [R,N] with row stride ldy; K % 32 == 0, N % 2 == 0, 16-byte aligned x / weight rows.
+ * Opt-in in the Python layer (CLUSTEN_TC_LINEAR=1); see DESIGN.md section 7 for its validation status. */
+int clusten_linear_f32(const float *x, const float *weight, const float *bias, float *y, int64_t R, int K, int N,
+                       int64_t ldx, int64_t ldy, void *stream);
+
 /* ---- column sum: out[c] += sum_r x[r*ld + c] (fp32 accumulation INTO out; caller zeroes it).  The bias gradient of the
  * backbone's Linear layers (grad_bias = grad_output.sum(0)); x fp32 / fp16 / bf16, C and ld multiples of 16 bytes. */
 int clusten_col_sum(const void *x, float *out, int64_t R, int C, int64_t ld, int dtype, void *stream);

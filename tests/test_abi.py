@@ -88,6 +88,10 @@ def test_argument_errors_of_the_structure_builders(lib):
     assert rc == -3 and b"F <= 8" in lib.clusten_last_error()                # more than 8 input features
     rc = lib.clusten_table_linear_bwd(16, 16, None, None, 100, 5, 4, None, None)
     assert rc == -1                                                         # d_weight missing
+    rc = lib.clusten_linear_f32(16, 16, None, 16, 100, 48, 32, 48, 32, None)
+    assert rc == -3 and b"K % 32" in lib.clusten_last_error()                # reduction length not a multiple of the k chunk
+    rc = lib.clusten_linear_f32(16, 16, None, 16, 100, 64, 32, 32, 32, None)
+    assert rc == -1                                                         # row stride shorter than the row
 
 
 def test_ops_refuse_cpu_tensors():

@@ -542,6 +542,33 @@ def test_fused_attention_core_backward(n, m, nbhd, kind, H, C, dtype):
         assert e <= 2 * tol, f"{name} rel err {e:.3e}"
 
 
+TC_LINEAR = os.environ.get("CLUSTEN_TC_LINEAR") == "1"
+
+
+@pytest.mark.skipif(not TC_LINEAR, reason="opt-in kernel (clusten_linear_f32): set CLUSTEN_TC_LINEAR=1")
+@pytest.mark.parametrize("R,K,N", [(1000, 32, 32), (4173, 128, 256), (300, 96, 288), (129, 768, 2304), (1, 32, 2), (16384, 64, 32)])
+def test_linear_f32_tensor_core(R, K, N):
+    """clusten_linear_f32 (3xTF32 split on the tensor cores) against a float64 matmul: fp32-level accuracy, ragged R and N,
+    a strided input, no bias."""
+    from autofocusformermod_b200 import ops
+    g = torch.Generator().manual_seed(R + K + N)
+    x = torch.randn(R, K, generator=g)
+    w = torch.randn(N, K, generator=g) * K ** -0.5
+    b = torch.randn(N, generator=g)
+    ref = x.double() @ w.double().t() + b.double()
+    xc, wc, bc = x.cuda(), w.cuda(), b.cuda()
+    assert ops.linear_f32_supported(xc, wc, bc)
+    y = ops.linear_f32(xc, wc, bc)
+    assert y.shape == (R, N) and y.dtype == torch.float32
+    assert rel_err(y.cpu().double(), ref) <= 2e-6
+    y3 = ops.linear_f32(xc.view(1, R, K), wc, None)                      # leading dims, no bias
+    assert y3.shape == (1, R, N)
+    assert rel_err(y3[0].cpu().double(), ref - b.double()) <= 2e-6
+    wide = torch.randn(R, K + 32, generator=g).cuda()                    # row stride K + 32: consumed in place
+    ys = ops.linear_f32(wide[:, :K], wc, bc)
+    assert rel_err(ys.cpu().double(), wide[:, :K].cpu().double() @ w.double().t() + b.double()) <= 2e-6
+
+
 INKERNEL_BIAS = os.environ.get("CLUSTEN_INKERNEL_BIAS") == "1"
 
 
