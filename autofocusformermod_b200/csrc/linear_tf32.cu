@@ -4,11 +4,12 @@
 // (K = 32..768, N = 32..2304, R = 4 096..2 097 152) with SIMT sgemm kernels plus a separate bias kernel: 63 % of the device
 // time of the AFF-Mini forward (profiles/r1_launches_aff_mini_fwd_b16_v12.md).
 //
-// OPT-IN (CLUSTEN_TC_LINEAR=1 in the Python layer) and NOT yet run on hardware when written -- see DESIGN.md section 7.
+// OPT-IN (CLUSTEN_TC_LINEAR=1 in the Python layer); first parity cases green on a B200, not yet timed -- see DESIGN.md section 7.
 //
 // CTA = 128 rows x 64 columns, 8 warps of 16 rows each; K in chunks of 32 through shared memory (cp.async, double buffered,
-// rows padded to 36 floats: the canonical m16n8k8 fragment reads are bank-conflict free); per k8 step and warp: one A fragment
-// (4 values, split once) against 8 B fragments -> 24 mma.  Bias in the epilogue, 8-byte stores.
+// rows padded to 36 floats: the canonical m16n8k8 fragment reads are bank-conflict free); per chunk and warp: four A fragments
+// (split once) against 8 x 4 B fragments -> 96 mma, each chunk summed from zero and added to the running sum outside the
+// tensor cores (their accumulation truncates).  Bias in the epilogue, 8-byte stores.
 #include <algorithm>
 
 #include "common.cuh"
@@ -74,22 +75,30 @@ linear_tf32x3_kernel(const float *__restrict__ X, const float *__restrict__ W, c
         const float *Xs = lt_smem + (kc & 1) * LT_STAGE, *Ws = Xs + LT_BM * LT_LD;
         const float *xa = Xs + (warp * 16 + g) * LT_LD + t, *xb = xa + 8 * LT_LD;
         const float *wr = Ws + g * LT_LD + t;
+        uint32_t ah[LT_BK / 8][4], al[LT_BK / 8][4];
 #pragma unroll
         for (int k8 = 0; k8 < LT_BK / 8; ++k8) {
-            uint32_t ah[4], al[4];
-            lt_split(xa[8 * k8], ah[0], al[0]);          // (row g,   k = t)
-            lt_split(xb[8 * k8], ah[1], al[1]);          // (row g+8, k = t)
-            lt_split(xa[8 * k8 + 4], ah[2], al[2]);      // (row g,   k = t + 4)
-            lt_split(xb[8 * k8 + 4], ah[3], al[3]);      // (row g+8, k = t + 4)
+            lt_split(xa[8 * k8], ah[k8][0], al[k8][0]);          // (row g,   k = t)
+            lt_split(xb[8 * k8], ah[k8][1], al[k8][1]);          // (row g+8, k = t)
+            lt_split(xa[8 * k8 + 4], ah[k8][2], al[k8][2]);      // (row g,   k = t + 4)
+            lt_split(xb[8 * k8 + 4], ah[k8][3], al[k8][3]);      // (row g+8, k = t + 4)
+        }
+        // The tensor cores accumulate with truncation, so a long chain inside the mma accumulator drifts: the first cut, which kept
+        // one chain over all of K, passed K <= 128 and left the 2e-6 band at K = 768 on the B200.  Each K chunk is therefore summed
+        // from zero (12 mma) and added to the running sum with a rounded FADD (not re-run on hardware yet).
 #pragma unroll
-            for (int n = 0; n < LT_BN / 8; ++n) {
+        for (int n = 0; n < LT_BN / 8; ++n) {
+            float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k8 = 0; k8 < LT_BK / 8; ++k8) {
                 uint32_t b0h, b0l, b1h, b1l;
                 lt_split(wr[n * 8 * LT_LD + 8 * k8], b0h, b0l);          // (k = t,     n = g): W[n0 + 8n + g][k]
                 lt_split(wr[n * 8 * LT_LD + 8 * k8 + 4], b1h, b1l);      // (k = t + 4, n = g)
-                lt_mma(acc[n], al, b0h, b1h);
-                lt_mma(acc[n], ah, b0l, b1l);
-                lt_mma(acc[n], ah, b0h, b1h);
+                lt_mma(part, al[k8], b0h, b1h);
+                lt_mma(part, ah[k8], b0l, b1l);
+                lt_mma(part, ah[k8], b0h, b1h);
             }
+            acc[n][0] += part[0]; acc[n][1] += part[1]; acc[n][2] += part[2]; acc[n][3] += part[3];
         }
         __syncthreads();                                 // the buffer is refilled two iterations later
     }
