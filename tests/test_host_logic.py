@@ -1,0 +1,82 @@
+"""CPU: host-side logic of the Python layer that needs no kernel -- the dispatch predicates of the glue ops, the dtype
+promotion and the op-by-op formulation they fall back to (which is also what the GPU parity tests compare the kernels with),
+and the module wrappers that keep the reference's parameter names."""
+import torch
+import torch.nn as nn
+
+from autofocusformermod_b200 import aff, ops
+
+
+def test_scale_residual_formulation_is_the_reference_block_line():
+    """`x = shortcut + drop_path(gamma * x)` (aff.py:230,236 with timm's DropPath): the torch formulation scale_residual uses for
+    operands the kernel does not take (here: CPU tensors) equals the reference line for the same per-sample draw."""
+    g = torch.Generator().manual_seed(0)
+    B, n, C = 4, 7, 12
+    feat, x, gamma = torch.randn(B, n, C, generator=g), torch.randn(B, n, C, generator=g), torch.randn(C, generator=g)
+    keep = 0.7
+    mask = torch.bernoulli(torch.full((B, 1, 1), keep), generator=g)
+    want = feat + (gamma * x) * (mask / keep)                                         # timm 0.6.12 drop_path, scale_by_keep
+    got = ops.scale_residual(feat, x, gamma, (mask / keep).reshape(B))
+    assert torch.equal(got, want)
+    assert torch.equal(ops.scale_residual(feat, x), feat + x)
+    assert torch.equal(ops.scale_residual(feat, x, gamma), feat + gamma * x)
+    assert not ops.scale_residual_supported(feat, x, gamma, None)                     # CPU tensors never reach the kernel
+
+
+def test_scale_residual_dtype_promotion_follows_aten():
+    """The kernel's output dtype rule (_residual_out_dtype) is ATen's promotion of `res + x * gamma`: an fp32 layer scale lifts a
+    16-bit residual stream to fp32 (otherwise a 1e-5 layer scale would vanish in bf16), 16-bit + 16-bit stays 16-bit."""
+    bf, f32 = torch.bfloat16, torch.float32
+    for rdt, xdt, gdt in [(f32, f32, None), (f32, bf, None), (bf, bf, None), (bf, bf, f32), (f32, bf, f32), (bf, bf, bf)]:
+        res, x = torch.zeros(2, 3, 4, dtype=rdt), torch.zeros(2, 3, 4, dtype=xdt)
+        gamma = None if gdt is None else torch.ones(4, dtype=gdt)
+        want = (res + (x if gamma is None else gamma * x)).dtype
+        assert ops._residual_out_dtype(res, x, gamma) == want, (rdt, xdt, gdt)
+
+
+def test_drop_path_sample_scale():
+    dp = aff.DropPath(0.25)
+    x = torch.zeros(4000, 2, 3)
+    dp.train()
+    s = dp.sample_scale(x)
+    assert s.shape == (4000,) and s.dtype == torch.float32
+    vals = torch.unique(s)
+    assert vals.numel() == 2 and vals[0] == 0 and abs(float(vals[1]) - 1 / 0.75) < 1e-6
+    assert abs(float((s > 0).float().mean()) - 0.75) < 0.03
+    dp.eval()
+    assert dp.sample_scale(x) is None and dp(x) is x
+    assert aff.DropPath(0.0).train().sample_scale(x) is None
+
+
+def test_module_wrappers_keep_reference_parameter_names_and_cpu_semantics():
+    """Linear / TableLinear / LayerNorm subclass the torch modules: same state_dict keys (reference checkpoints load) and, for
+    operands the kernels do not take, the torch forward."""
+    torch.manual_seed(0)
+    lin, ref = aff.Linear(8, 6), nn.Linear(8, 6)
+    ref.load_state_dict(lin.state_dict())
+    x = torch.randn(5, 8)
+    assert torch.equal(lin(x), ref(x))
+    tl, tref = aff.TableLinear(5, 3), nn.Linear(5, 3)
+    tref.load_state_dict(tl.state_dict())
+    f = torch.randn(11, 5)
+    assert torch.equal(tl(f, None), tref(f))
+    assert not ops.table_linear_supported(f, tl.weight, tl.bias)                      # CPU
+    ln, lref = aff.LayerNorm(8), nn.LayerNorm(8)
+    lref.load_state_dict(ln.state_dict())
+    assert torch.equal(ln(x), lref(x))
+    blk = aff.ClusterTransformerBlock(32, 2, layer_scale=1e-5, drop_path=0.1)
+    keys = set(blk.state_dict())
+    assert {"gamma1", "gamma2", "attn.pos_embed.weight", "attn.pos_embed.bias", "attn.q.weight", "attn.kv.bias", "attn.blank_k",
+            "mlp.fc1.weight", "norm1.weight"} <= keys
+    merge = aff.ClusterMerging(32, 64)
+    assert {"weight_net.0.weight", "weight_net.1.weight", "weight_net.1.bias", "norm.weight", "linear.weight"} <= set(merge.state_dict())
+
+
+def test_kernel_dispatch_predicates_reject_what_the_kernels_do_not_take():
+    x = torch.zeros(4, 48)
+    w = torch.zeros(6, 48)
+    assert not ops.linear_f32_supported(x, w, None)                                   # CPU tensor
+    assert not ops.linear_f32_supported(x.to(torch.bfloat16), w, None)
+    assert not ops.table_linear_supported(torch.zeros(4, 9), torch.zeros(3, 9), None)
+    res = torch.zeros(2, 5, 30)
+    assert not ops.scale_residual_supported(res, res, None, torch.ones(2))
