@@ -1,6 +1,7 @@
-"""CPU: host-side logic of the Python layer that needs no kernel -- the dispatch predicates of the glue ops, the dtype
-promotion and the op-by-op formulation they fall back to (which is also what the GPU parity tests compare the kernels with),
-and the module wrappers that keep the reference's parameter names."""
+"""Host-side logic of the Python layer that needs no kernel (this suite has no GPU): the dispatch predicates of the glue ops,
+their dtype-promotion rule, the op-by-op torch formulation used for operands outside a kernel's shape / dtype set (it is also
+what the GPU parity tests compare the kernels with), and the module wrappers that keep the reference's parameter names.
+None of this is a CPU path of the product: the CLUSTEN ops refuse non-CUDA tensors (tests/test_abi.py)."""
 import torch
 import torch.nn as nn
 
@@ -9,7 +10,7 @@ from autofocusformermod_b200 import aff, ops
 
 def test_scale_residual_formulation_is_the_reference_block_line():
     """`x = shortcut + drop_path(gamma * x)` (aff.py:230,236 with timm's DropPath): the torch formulation scale_residual uses for
-    operands the kernel does not take (here: CPU tensors) equals the reference line for the same per-sample draw."""
+    operands outside the kernel's set equals the reference line for the same per-sample draw (evaluated on host tensors)."""
     g = torch.Generator().manual_seed(0)
     B, n, C = 4, 7, 12
     feat, x, gamma = torch.randn(B, n, C, generator=g), torch.randn(B, n, C, generator=g), torch.randn(C, generator=g)
@@ -20,7 +21,7 @@ def test_scale_residual_formulation_is_the_reference_block_line():
     assert torch.equal(got, want)
     assert torch.equal(ops.scale_residual(feat, x), feat + x)
     assert torch.equal(ops.scale_residual(feat, x, gamma), feat + gamma * x)
-    assert not ops.scale_residual_supported(feat, x, gamma, None)                     # CPU tensors never reach the kernel
+    assert not ops.scale_residual_supported(feat, x, gamma, None)                     # host tensors are outside the kernel's set
 
 
 def test_scale_residual_dtype_promotion_follows_aten():
@@ -49,8 +50,8 @@ def test_drop_path_sample_scale():
 
 
 def test_module_wrappers_keep_reference_parameter_names_and_cpu_semantics():
-    """Linear / TableLinear / LayerNorm subclass the torch modules: same state_dict keys (reference checkpoints load) and, for
-    operands the kernels do not take, the torch forward."""
+    """Linear / TableLinear / LayerNorm subclass the torch modules: same state_dict keys (reference checkpoints load) and the
+    torch forward for operands outside the kernels' set."""
     torch.manual_seed(0)
     lin, ref = aff.Linear(8, 6), nn.Linear(8, 6)
     ref.load_state_dict(lin.state_dict())
@@ -60,7 +61,7 @@ def test_module_wrappers_keep_reference_parameter_names_and_cpu_semantics():
     tref.load_state_dict(tl.state_dict())
     f = torch.randn(11, 5)
     assert torch.equal(tl(f, None), tref(f))
-    assert not ops.table_linear_supported(f, tl.weight, tl.bias)                      # CPU
+    assert not ops.table_linear_supported(f, tl.weight, tl.bias)
     ln, lref = aff.LayerNorm(8), nn.LayerNorm(8)
     lref.load_state_dict(ln.state_dict())
     assert torch.equal(ln(x), lref(x))
@@ -75,7 +76,7 @@ def test_module_wrappers_keep_reference_parameter_names_and_cpu_semantics():
 def test_kernel_dispatch_predicates_reject_what_the_kernels_do_not_take():
     x = torch.zeros(4, 48)
     w = torch.zeros(6, 48)
-    assert not ops.linear_f32_supported(x, w, None)                                   # CPU tensor
+    assert not ops.linear_f32_supported(x, w, None)                                   # not a CUDA tensor
     assert not ops.linear_f32_supported(x.to(torch.bfloat16), w, None)
     assert not ops.table_linear_supported(torch.zeros(4, 9), torch.zeros(3, 9), None)
     res = torch.zeros(2, 5, 30)
