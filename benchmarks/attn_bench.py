@@ -1,6 +1,6 @@
 """Fused ClusterAttention core (clusten_attn_fwd / clusten_attn_bwd / clusten_scatter_rows / clusten_table_grad) at one AFF
-stage shape: per-entry device time, algorithmic bytes, achieved GB/s.  Index tensors come from the reference pipeline
-(oracle clustering + kNN on a random token subset), so padded last clusters (n % m != 0) show their real cost.
+stage shape: per-entry device time, algorithmic bytes, achieved GB/s.  Index tensors come from the product's own stage pipeline
+(clustering + kNN + stage_prepare on a random token subset), so padded last clusters (n % m != 0) show their real cost.
 
     python benchmarks/attn_bench.py --n 655 --heads 8 --batch 32 [--m 8 --nbhd 48 --c 32 --dtype bf16|f16|f32 --iters 10 --inkernel-bias]   (f32: inference forward only)
 """
@@ -30,18 +30,17 @@ def main():
     ap.add_argument("--inkernel-bias", action="store_true", help="the clusten_attn_pos_* variant: bias computed from positions in the kernels")
     args = ap.parse_args()
     from autofocusformermod_b200 import ops
-    from oracle import inputs
+    from _inputs import stage_structure
     dt = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[args.dtype]
     if dt == torch.float32:
         args.fwd_only = True                              # fp32 runs the fused kernel on the inference path only
     B, N, H, C = args.batch, args.n, args.heads, args.c
-    pos, nb, mask, pe_idx = inputs.structured_neighbourhood(1, N, args.grid, args.grid, args.m, args.nbhd, seed=0)
-    pos = pos.float().expand(B, -1, -1).contiguous().cuda()
+    pos, nb, mask, uniq, inv = stage_structure(1, N, args.grid, args.grid, args.m, args.nbhd, seed=0)
+    pos = pos.expand(B, -1, -1).contiguous()
     M = nb.shape[-1]
-    idx = nb.expand(B, -1, -1).contiguous().cuda()
-    mask8 = None if mask is None else mask.expand(B, -1, -1).contiguous().to(torch.uint8).cuda()
-    uniq, inv = torch.unique(pe_idx.expand(B, -1, -1).contiguous(), return_inverse=True)
-    bias_idx = inv.to(torch.int32).cuda()
+    idx = nb.expand(B, -1, -1).contiguous()
+    mask8 = None if mask is None else mask.expand(B, -1, -1).contiguous()
+    bias_idx = inv.expand(B, -1, -1).contiguous()
     g = torch.Generator(device="cuda").manual_seed(0)
     q = (torch.randn(B, N, H, C, device="cuda", generator=g) * C ** -0.5).to(dt).requires_grad_(True)
     kv = torch.randn(B, N, H, 2, C, device="cuda", generator=g).to(dt).requires_grad_(True)

@@ -34,13 +34,13 @@ def peak_gbs():
 
 
 def real_idx(B, N, M, m, grid):
-    """The reference's own pipeline (oracle restatement on CPU): positions -> space_filling_cluster -> kNN clusters ->
-    member_idx (aff.py:469-478).  Stage-0 tokens sit on the stem grid, so every sample of the batch has the same
-    neighbourhoods -- exactly what the ops see in the backbone; later-stage shapes reuse one sample's structure."""
-    from oracle import inputs
+    """The stage pipeline of the backbone (product kernels): positions -> space_filling_cluster -> kNN clusters -> member_idx
+    (aff.py:469-478).  Stage-0 tokens sit on the stem grid, so every sample of the batch has the same neighbourhoods --
+    exactly what the ops see in the backbone; later-stage shapes reuse one sample's structure."""
+    from _inputs import stage_structure
     h, w = grid
-    _, nb, _, _ = inputs.structured_neighbourhood(1, N, h, w, m, M, seed=0)
-    return nb.expand(B, -1, -1).contiguous().cuda()
+    nb = stage_structure(1, N, h, w, m, M, seed=0)[1]
+    return nb.expand(B, -1, -1).contiguous()
 
 
 def structured_idx(B, N, M, m, gen):
