@@ -1,5 +1,6 @@
 """Index tensors for the benchmarks, produced by the PRODUCT pipeline on the GPU (space_filling_cluster -> knn_keops ->
-stage_prepare, i.e. what BasicLayer.forward runs, backbone/aff.py:469-485): the benchmarks never touch oracle/."""
+stage_prepare, i.e. what BasicLayer.forward runs, backbone/aff.py:469-485): nothing here touches oracle/
+(the one checker-side option of the benchmarks is ``op_bench.py --ref``, which times the reference's own kernels beside ours)."""
 import torch
 
 
