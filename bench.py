@@ -412,7 +412,9 @@ def main():
                    "execution": ("CUDA graph replay (AFF.graphed)" if graphed is not None else
                                  "CUDA graphs for forward and backward (graphed_training_forward), eager AdamW" if graphed_train is not None
                                  else "eager"),
-                   "l2": f"no explicit flush: one step streams {peak_mem / 2**20:.0f} MiB of live activations (>> 126 MB L2)"},
+                   "l2": f"no explicit flush: one step streams {peak_mem / 2**20:.0f} MiB of live activations (>> 126 MB L2)",
+                   # environment switches of the Python layer that differ from their defaults (README.md), so a line says what it ran
+                   "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("CLUSTEN_")}},
         "e2e": {"value": round(total_images / e2e_max, 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clocks,
