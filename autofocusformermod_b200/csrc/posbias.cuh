@@ -27,17 +27,22 @@ __device__ __forceinline__ PosBiasW pos_bias_load(const float *__restrict__ pe_w
 
 struct RelFeat { float dx, dy, d, rd; };            // dist = d, 1/dist = rd (0 at the centre)
 
-__device__ __forceinline__ RelFeat rel_feat(float2 q, float2 k) {
+// (the three functions below also compile for the host: tests/test_posbias_host.py checks their arithmetic against the oracle's table)
+__host__ __device__ __forceinline__ RelFeat rel_feat(float2 q, float2 k) {
     RelFeat f;
     f.dx = truncf(fminf(fmaxf(k.x - (q.x - 511.f), 0.f), 1022.f)) - 511.f;
     f.dy = truncf(fminf(fmaxf(k.y - (q.y - 511.f), 0.f), 1022.f)) - 511.f;
     const float s = fmaf(f.dx, f.dx, f.dy * f.dy);
+#ifdef __CUDA_ARCH__
     f.rd = s > 0.f ? rsqrtf(s) : 0.f;
+#else
+    f.rd = s > 0.f ? 1.f / sqrtf(s) : 0.f;
+#endif
     f.d = s * f.rd;
     return f;
 }
 
-__device__ __forceinline__ float pos_bias(const PosBiasW &w, float2 q, float2 k) {
+__host__ __device__ __forceinline__ float pos_bias(const PosBiasW &w, float2 q, float2 k) {
     const RelFeat f = rel_feat(q, k);
     const float lin = fmaf(w.w0, f.dx, fmaf(w.w1, f.dy, w.b));
     const float ang = fmaf(w.w3, f.dy, w.w4 * f.dx);
@@ -45,7 +50,7 @@ __device__ __forceinline__ float pos_bias(const PosBiasW &w, float2 q, float2 k)
 }
 
 // acc += ds * [dx, dy, dist, dy/dist, dx/dist, 1]
-__device__ __forceinline__ void pos_bias_grad(float (&acc)[6], float2 q, float2 k, float ds) {
+__host__ __device__ __forceinline__ void pos_bias_grad(float (&acc)[6], float2 q, float2 k, float ds) {
     const RelFeat f = rel_feat(q, k);
     acc[0] = fmaf(ds, f.dx, acc[0]);
     acc[1] = fmaf(ds, f.dy, acc[1]);
