@@ -36,23 +36,36 @@ TABLE_WIDTH = 2 * REL_POS_WIDTH + 1
 
 _pre_tables = {}
 
-# Inference fast path: QK + bias + mask + blank token + softmax + AV in one kernel (clusten_attn_fwd) whenever autograd
-# is off.  Training keeps the signature-preserving ops (their backward is the accelerated one).
+def _on(name):          # fast path that is ON unless the environment says NAME=0 (bisecting aid)
+    return os.environ.get(name, "1") != "0"
+
+
+def _opt_in(name):      # path that is OFF unless the environment says NAME=1 (see DESIGN.md section 7 for what each still lacks)
+    return os.environ.get(name, "0") == "1"
+
+
+# Fused ClusterAttention core: inference = clusten_attn_fwd whenever autograd is off; 16-bit training = one differentiable op
+# (ClusterAttentionCoreFunction); fp32 training keeps the signature-preserving ops (their backward is the accelerated one).
 USE_FUSED_ATTENTION = True
-FAST_LINEAR_BACKWARD = os.environ.get("CLUSTEN_FAST_LINEAR", "1") != "0"        # Linear layers of the blocks: bias gradient by clusten_col_sum (see Linear)
-CHANNELS_LAST_STEM = os.environ.get("CLUSTEN_CHANNELS_LAST", "1") != "0"          # run the two stem convolutions + BatchNorm in NHWC (see PatchEmbed.forward)
-GRID_STRUCTURE_CACHE = os.environ.get("CLUSTEN_GRID_CACHE", "1") != "0"        # memoise the position-only structures of the on-grid stage (see BasicLayer._grid_structure)
-NATIVE_TABLE_LINEAR = os.environ.get("CLUSTEN_TABLE_LINEAR", "1") != "0"      # pos_embed = Linear(5, heads) over the referenced table rows by clusten_table_linear_* (see TableLinear)
-# opt-in (round-2 work): relative-position bias computed from positions inside the fused attention kernels
-INKERNEL_BIAS = os.environ.get("CLUSTEN_INKERNEL_BIAS", "0") == "1"
-# opt-in: fp32 inference Linear layers on the tensor cores with the 3xTF32 split (clusten_linear_f32) instead of cuBLAS SIMT sgemm;
-# not yet run on hardware
-TC_LINEAR = os.environ.get("CLUSTEN_TC_LINEAR", "0") == "1"
-# opt-in: under autocast run the merge's WF in the autocast dtype (tensor-core kernels) instead of fp32 like the reference under AMP,
-# whose CLUSTENWF casts feat up to the fp32 weights (clusten.py:80-81); not yet timed on hardware
-MERGE_WF_AUTOCAST = os.environ.get("CLUSTEN_MERGE_WF_AUTOCAST", "0") == "1"
-FUSED_RESIDUAL = os.environ.get("CLUSTEN_FUSED_RESIDUAL", "1") != "0"           # residual + layer scale + stochastic depth in one kernel (see ClusterTransformerBlock._residual)
-NATIVE_WEIGHT_NET_NORM = os.environ.get("CLUSTEN_WEIGHT_NET_NORM", "1") != "0"   # LayerNorm(4) of the merge's weight_net through clusten_layer_norm_* (see ClusterMerging)
+# Linear layers of the blocks: bias gradient by clusten_col_sum (see Linear)
+FAST_LINEAR_BACKWARD = _on("CLUSTEN_FAST_LINEAR")
+# the two stem convolutions + BatchNorm in NHWC under autocast (see PatchEmbed.forward)
+CHANNELS_LAST_STEM = _on("CLUSTEN_CHANNELS_LAST")
+# memoise the position-only structures of the on-grid stage (see BasicLayer._grid_structure)
+GRID_STRUCTURE_CACHE = _on("CLUSTEN_GRID_CACHE")
+# pos_embed = Linear(5, heads) over the referenced table rows by clusten_table_linear_* (see TableLinear)
+NATIVE_TABLE_LINEAR = _on("CLUSTEN_TABLE_LINEAR")
+# residual + layer scale + stochastic depth in one kernel (see ClusterTransformerBlock._residual)
+FUSED_RESIDUAL = _on("CLUSTEN_FUSED_RESIDUAL")
+# LayerNorm(4) of the merge's weight_net through clusten_layer_norm_* (see ClusterMerging)
+NATIVE_WEIGHT_NET_NORM = _on("CLUSTEN_WEIGHT_NET_NORM")
+# opt-in: relative-position bias computed from positions inside the fused attention kernels (clusten_attn_pos_*)
+INKERNEL_BIAS = _opt_in("CLUSTEN_INKERNEL_BIAS")
+# opt-in: fp32 inference Linear layers on the tensor cores with the 3xTF32 split (clusten_linear_f32) instead of cuBLAS SIMT sgemm
+TC_LINEAR = _opt_in("CLUSTEN_TC_LINEAR")
+# opt-in: under autocast the merge's WF runs in the autocast dtype (tensor-core kernels) instead of fp32 like the reference under
+# AMP, whose CLUSTENWF casts feat up to the fp32 weights (clusten.py:80-81)
+MERGE_WF_AUTOCAST = _opt_in("CLUSTEN_MERGE_WF_AUTOCAST")
 
 
 def rel_pos_features(pe_idx):
