@@ -12,6 +12,9 @@ run mini_base X=0 --
 run mini_posbias CLUSTEN_INKERNEL_BIAS=1 --
 run mini_tclinear CLUSTEN_TC_LINEAR=1 --
 run mini_both CLUSTEN_INKERNEL_BIAS=1 CLUSTEN_TC_LINEAR=1 --
+S="--workload aff_small_fwd_b16_512 --steps 10 --warmup 3"     # the north-star scaling model: 80 % of its step is fp32 sgemm
+run small_base X=0 -- $S
+run small_tclinear CLUSTEN_TC_LINEAR=1 -- $S
 T="--workload aff_tiny15_train_b32_512_bf16 --steps 5 --warmup 3"
 run tiny_base X=0 -- $T
 run tiny_posbias CLUSTEN_INKERNEL_BIAS=1 -- $T
