@@ -53,6 +53,7 @@ FAST_LINEAR_BACKWARD = _on("CLUSTEN_FAST_LINEAR")
 CHANNELS_LAST_STEM = _on("CLUSTEN_CHANNELS_LAST")
 # memoise the position-only structures of the on-grid stage (see BasicLayer._grid_structure)
 GRID_STRUCTURE_CACHE = _on("CLUSTEN_GRID_CACHE")
+GRID_CACHE_SHAPES = 4               # input shapes memoised per stage before the oldest is dropped
 # pos_embed = Linear(5, heads) over the referenced table rows by clusten_table_linear_* (see TableLinear)
 NATIVE_TABLE_LINEAR = _on("CLUSTEN_TABLE_LINEAR")
 # residual + layer scale + stochastic depth in one kernel (see ClusterTransformerBlock._residual)
@@ -179,7 +180,9 @@ class DropPath(nn.Module):
             return x
         keep = 1.0 - self.drop_prob
         mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
-        return x * mask.div_(keep)
+        if keep > 0.0:                                    # timm only rescales when something is kept (drop_prob = 1 -> zeros)
+            mask.div_(keep)
+        return x * mask
 
     def sample_scale(self, x):
         """The per-sample factor bernoulli(keep) / keep as fp32 [B] (None when the layer is the identity) -- what forward
@@ -187,7 +190,8 @@ class DropPath(nn.Module):
         if self.drop_prob == 0.0 or not self.training:
             return None
         keep = 1.0 - self.drop_prob
-        return torch.empty(x.shape[0], dtype=torch.float32, device=x.device).bernoulli_(keep).div_(keep)
+        scale = torch.empty(x.shape[0], dtype=torch.float32, device=x.device).bernoulli_(keep)
+        return scale.div_(keep) if keep > 0.0 else scale
 
 
 class Mlp(nn.Module):
@@ -386,7 +390,13 @@ class BasicLayer(nn.Module):
             self.prob_net = nn.Linear(dim, 1)
         else:
             self.downsample = None
-        self._grid_cache = None          # position-only structures of an on-grid stage (see _grid_structure; aff.py:461-467)
+        # position-only structures of an on-grid stage, keyed by shape (see _grid_structure; aff.py:461-467).  CUDA graphs bake
+        # in the addresses of these tensors: GraphedAFF / graphed_training_forward pin the entries they captured (grid_pins).
+        self._grid_cache = {}
+        k_max = 16                                                                                   # clusten_knn keeps k <= 16 in registers
+        if cluster_size > 0 and int(round(nbhd_size / float(cluster_size))) > k_max:
+            raise ValueError(f"nbhd_size / cluster_size = {nbhd_size} / {cluster_size} asks for more than {k_max} nearest clusters "
+                             "per token; clusten_knn supports k <= 16 (INTEGRATION.md)")
 
     def _cluster(self, pos, feat, h, w, on_grid):
         b, n, c = feat.shape
@@ -400,14 +410,18 @@ class BasicLayer(nn.Module):
         constant of (b, h, w): the reference memoises the clustering part in training (aff.py:461-467); here the whole structure
         is memoised, in training and in inference (it also keeps the tile pack cached on ``member_idx`` alive across calls)."""
         key = (b, n, h, w, m, nnc, pos.device)
-        if self._grid_cache is None or self._grid_cache[0] != key:
+        entry = self._grid_cache.get(key)
+        if entry is None:
             with torch.no_grad():
                 spos, mean_pos, member, cmask, reorder = space_filling_cluster(pos, m, h, w)
                 nearest = knn_keops(spos, mean_pos, nnc)
                 prepared = stage_prepare(spos, nearest, member, cmask, extent=(h, w))
                 lookup = _TableLookup(uniq=prepared[3], inverse=prepared[4], count=prepared[5])
-            self._grid_cache = (key, spos, reorder, prepared, lookup)
-        return self._grid_cache[1:]
+            entry = (spos, reorder, prepared, lookup)
+            while len(self._grid_cache) >= GRID_CACHE_SHAPES:            # oldest shape out (entries pinned by a graph stay alive there)
+                self._grid_cache.pop(next(iter(self._grid_cache)))
+            self._grid_cache[key] = entry
+        return entry
 
     def forward(self, pos, feat, h, w, on_grid, stride):
         b, n, d = pos.shape
@@ -557,6 +571,12 @@ def _quiet_capture(device):
             gc.enable()
 
 
+def grid_pins(model):
+    """References to every memoised on-grid structure of the model (BasicLayer._grid_cache), for objects that captured their
+    addresses in a CUDA graph: a later forward at another shape may drop the cache entry, the pinned tensors stay allocated."""
+    return [list(layer._grid_cache.values()) for layer in model.layers]
+
+
 class _Features(nn.Module):
     """The backbone's feature tensors as a tuple (res2, res3, ...): what torch.cuda.make_graphed_callables can carry."""
 
@@ -580,7 +600,9 @@ def graphed_training_forward(model, example, autocast_dtype=None, num_warmup_ite
     wrapped = _Features(model)
     with _quiet_capture(example.device), torch.autocast("cuda", dtype=autocast_dtype or torch.bfloat16,
                                                         enabled=autocast_dtype is not None, cache_enabled=False):
-        return torch.cuda.make_graphed_callables(wrapped, (example.detach().clone(),), num_warmup_iters=num_warmup_iters)
+        f = torch.cuda.make_graphed_callables(wrapped, (example.detach().clone(),), num_warmup_iters=num_warmup_iters)
+    f.grid_pins = grid_pins(model)       # the graphs hold raw addresses of the memoised stage structures: keep them alive
+    return f
 
 
 class GraphedAFF:
@@ -611,6 +633,7 @@ class GraphedAFF:
             with torch.cuda.graph(self.graph, capture_error_mode=mode):
                 self.static_out = self._run()
         self.launches_per_replay = kernel_launches() - k0   # libclusten kernels inside one replay
+        self.grid_pins = grid_pins(model)                   # the graph holds raw addresses of the memoised stage structures
 
     def _run(self):
         with torch.no_grad(), torch.autocast("cuda", dtype=self.autocast_dtype or torch.bfloat16, enabled=self.autocast_dtype is not None):

@@ -130,7 +130,9 @@ def inverse_neighbour_list(nbhd_idx, Nk, with_pack=False, wf_plan_buf=None, pack
     kind = ("mpack" if pack_buf is not None else "pack" if with_pack and pack is not None else "wf" if pack is not None else None)
     # (a list built beside a pack / plan may have been skipped on the device: only reuse it for the same kind of call;
     # an unconditional list serves everyone)
-    if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr() and cache[5] in (None, kind):
+    # (a list built beside a mask-aware pack is only valid for that very pack buffer, which the cache keeps alive)
+    if (cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr() and cache[5] in (None, kind)
+            and (cache[5] != "mpack" or cache[6] is pack_buf)):
         return cache[3], cache[4]
     B, Nq, M = nbhd_idx.shape
     dev = nbhd_idx.device
@@ -143,7 +145,7 @@ def inverse_neighbour_list(nbhd_idx, Nk, with_pack=False, wf_plan_buf=None, pack
         _call("clusten_csr_build", dev, nbhd_idx.data_ptr(), B, Nq, M, Nk, offsets.data_ptr(), entries.data_ptr(),
               ws.data_ptr(), ws_bytes, _lib.ptr(pack))
     try:
-        nbhd_idx._clusten_csr = (ver, Nk, nbhd_idx.data_ptr(), offsets, entries, kind)
+        nbhd_idx._clusten_csr = (ver, Nk, nbhd_idx.data_ptr(), offsets, entries, kind, pack_buf)
     except Exception:  # pragma: no cover  (tensor subclass without __dict__)
         pass
     return offsets, entries
@@ -164,8 +166,10 @@ def neighbourhood_pack(nbhd_idx, Nk, inverse=False, mask=None):
     ver = nbhd_idx._version
     B, Nq, M = nbhd_idx.shape
     dev = nbhd_idx.device
-    mkey = None if mask is None else (mask.data_ptr(), mask._version)
-    if cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr() and cache[5] == mkey:
+    # the mask tensor ITSELF is part of the key (and is kept alive by the cache): an address + version pair can be recycled
+    mver = None if mask is None else mask._version
+    if (cache is not None and cache[0] == ver and cache[1] == Nk and cache[2] == nbhd_idx.data_ptr()
+            and cache[5] is mask and cache[6] == mver):
         pack, has_inv = cache[3], cache[4]
     else:
         nbytes = _lib.lib().clusten_pack_bytes(B, Nq, M, Nk)
@@ -177,7 +181,7 @@ def neighbourhood_pack(nbhd_idx, Nk, inverse=False, mask=None):
             _call("clusten_pack_inverse", dev, pack.data_ptr(), pack.numel(), B, Nq, M, Nk)
         has_inv = True
     try:
-        setattr(nbhd_idx, attr, (ver, Nk, nbhd_idx.data_ptr(), pack, has_inv, mkey))
+        setattr(nbhd_idx, attr, (ver, Nk, nbhd_idx.data_ptr(), pack, has_inv, mask, mver))
     except Exception:  # pragma: no cover
         pass
     return pack

@@ -147,6 +147,8 @@ def mask_select(mask, count, out=None):
 def merge_select(final_prob, reserve_mask, keep_num, reserve_num):
     """idx [B, keep_num, 1] = cat(canonical top-(keep-reserve) of final_prob, reserve tokens ascending) (aff.py:320-324)."""
     B = final_prob.shape[0]
+    if keep_num < reserve_num:                                           # the reference fails in topk(negative k) (aff.py:316-320)
+        raise RuntimeError(f"merge_select: keep_num {keep_num} < reserve_num {reserve_num} (ds_rate too small for this grid)")
     idx = torch.empty((B, keep_num), dtype=torch.int64, device=final_prob.device)
     k = keep_num - reserve_num
     if k > 0:
