@@ -14,8 +14,7 @@
 // probabilities as the A operand.  The [B,H,N,M] tensor never touches HBM (optionally the probabilities are written
 // once, coalesced, for a backward pass).  Impure tokens and index tensors without octet structure take a
 // one-warp-per-(token, head) generic kernel with the same arithmetic; the pack's device-side flag picks (no host sync).
-#include "posbias.cuh"
-#include "t2.cuh"
+#include "fused.cuh"
 
 namespace clusten {
 
@@ -68,90 +67,6 @@ template <typename T> __device__ __forceinline__ void f_store2(T *p, float a, fl
 template <> __device__ __forceinline__ void f_store2<float>(float *p, float a, float b) { *reinterpret_cast<float2 *>(p) = make_float2(a, b); }
 template <> __device__ __forceinline__ void f_store2<__half>(__half *p, float a, float b) { *reinterpret_cast<__half2 *>(p) = __floats2half2_rn(a, b); }
 template <> __device__ __forceinline__ void f_store2<__nv_bfloat16>(__nv_bfloat16 *p, float a, float b) { *reinterpret_cast<__nv_bfloat162 *>(p) = __floats2bfloat162_rn(a, b); }
-
-template <typename T> __device__ __forceinline__ float f_exp(float x) {
-    if constexpr (sizeof(T) == 4) return expf(x); else return __expf(x);
-}
-
-struct FusedArgs {
-    const void *q, *k, *v;
-    const int64_t *idx;
-    const float *bias_tab;
-    const int32_t *bias_idx;
-    const uint8_t *mask;
-    const void *blank_k, *blank_v;
-    void *out;
-    float *probs, *lse;
-    int B, H, Nq, Nk, C, M;
-    int64_t q_sb, q_sh, q_sn, k_sb, k_sh, k_sn, v_sb, v_sh, v_sn, o_sb, o_sh, o_sn;
-};
-// position-bias variant (PB kernels, clusten_attn_pos_fwd): bias from positions instead of bias_tab / bias_idx (posbias.cuh).
-// A separate type so that the kernels of the table variant keep their parameter block exactly as validated.
-struct FusedArgsPB : FusedArgs {
-    const float *pos_q, *pos_k, *pe_w, *pe_b;            // [B,Nq,2], [B,Nk,2], [H,5], [H] or NULL
-};
-template <bool PB> using FArgsOf = std::conditional_t<PB, FusedArgsPB, FusedArgs>;
-
-// One (token, head) computed the slow way by one warp; `sm` = M + 2 floats of shared scratch.  Also THE generic kernel body.
-template <typename T, bool PB = false>
-__device__ __forceinline__ void fused_row_generic(const FArgsOf<PB> &a, int b, int h, int i, float *sm, int lane) {
-    const T *q = reinterpret_cast<const T *>(a.q) + b * a.q_sb + h * a.q_sh + (int64_t)i * a.q_sn;
-    const T *kb = reinterpret_cast<const T *>(a.k) + b * a.k_sb + h * a.k_sh;
-    const T *vb = reinterpret_cast<const T *>(a.v) + b * a.v_sb + h * a.v_sh;
-    const T *bk = reinterpret_cast<const T *>(a.blank_k) + h * a.C;
-    const T *bv = reinterpret_cast<const T *>(a.blank_v) + h * a.C;
-    const int64_t *irow = a.idx + ((int64_t)b * a.Nq + i) * a.M;
-    const int32_t *bi = PB ? nullptr : a.bias_idx + ((int64_t)b * a.Nq + i) * a.M;
-    const uint8_t *mk = a.mask ? a.mask + ((int64_t)b * a.Nq + i) * a.M : nullptr;
-    const int M = a.M, C = a.C;
-    PosBiasW pw = {};
-    float2 pq = make_float2(0.f, 0.f);
-    const float2 *PK = nullptr;
-    if constexpr (PB) {
-        pw = pos_bias_load(a.pe_w, a.pe_b, h);
-        pq = __ldg(reinterpret_cast<const float2 *>(a.pos_q) + (int64_t)b * a.Nq + i);
-        PK = reinterpret_cast<const float2 *>(a.pos_k) + (int64_t)b * a.Nk;
-    }
-    float mx = -INFINITY;
-    for (int j = lane; j <= M; j += 32) {
-        float s = 0.f;
-        if (j < M) {
-            const T *kr = kb + irow[j] * a.k_sn;
-            for (int ch = 0; ch < C; ++ch) s = fmaf(to_f(q[ch]), to_f(kr[ch]), s);
-            if constexpr (PB) s += pos_bias(pw, pq, __ldg(PK + irow[j]));
-            else s += a.bias_tab[(int64_t)bi[j] * a.H + h];
-            if (mk && !mk[j]) s += -100.f;
-        } else {
-            for (int ch = 0; ch < C; ++ch) s = fmaf(to_f(q[ch]), to_f(bk[ch]), s);
-        }
-        sm[j] = s;
-        mx = fmaxf(mx, s);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
-    float sum = 0.f;
-    for (int j = lane; j <= M; j += 32) {
-        const float e = f_exp<T>(sm[j] - mx);
-        sm[j] = e;
-        sum += e;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
-    const float inv = 1.f / sum;
-    if (a.lse && lane == 0) a.lse[((int64_t)b * a.H + h) * a.Nq + i] = mx + logf(sum);
-    __syncwarp();
-    T *orow = reinterpret_cast<T *>(a.out) + b * a.o_sb + h * a.o_sh + (int64_t)i * a.o_sn;
-    for (int ch = lane; ch < C; ch += 32) {
-        float acc = sm[M] * to_f(bv[ch]);
-        for (int j = 0; j < M; ++j) acc = fmaf(sm[j], to_f(vb[irow[j] * a.v_sn + ch]), acc);
-        orow[ch] = from_f<T>(acc * inv);
-    }
-    if (a.probs) {
-        float *pr = a.probs + (((int64_t)b * a.H + h) * a.Nq + i) * (M + 1);
-        for (int j = lane; j <= M; j += 32) pr[j] = sm[j] * inv;
-    }
-    __syncwarp();
-}
 
 template <typename T, bool PB>
 __global__ void __launch_bounds__(256)
@@ -516,7 +431,16 @@ static int launch_fused(const FArgsOf<PB> &a, const void *pack, cudaStream_t st)
     auto fits = [](int64_t v) { return v >= 0 && v < (1LL << 31); };
     const bool range_ok = fits(a.Nq * a.q_sn) && fits((int64_t)a.Nk * a.k_sn) && fits((int64_t)a.Nk * a.v_sn) && fits(a.Nq * a.o_sn) &&
                           (int64_t)a.B * a.H <= 65535 && fits((int64_t)a.B * ((a.Nq + 15) / 16) * 16 * U_MAX);
-    if (pack && shape_ok && align_ok && range_ok) {
+    bool taken = false;
+    if (pack) {
+        // the CTA-cooperative, TMA-staged kernel when the layout allows it (clusten_fused_tma.cu); else one warp per (tile, head)
+        FusedArgsPB ap{};
+        if constexpr (PB) ap = a; else static_cast<FusedArgs &>(ap) = a;
+        constexpr int code = sizeof(T) == 4 ? CLUSTEN_F32 : std::is_same<T, __half>::value ? CLUSTEN_F16 : CLUSTEN_BF16;
+        if (int e = fused_tma_launch(ap, PB, code, pack, st, &taken)) return e;
+        if (taken) flag = reinterpret_cast<const int *>(pack);
+    }
+    if (!taken && pack && shape_ok && align_ok && range_ok) {
         const PackView pk = pack_view(const_cast<void *>(pack), a.B, a.Nq, a.Nk);
         const dim3 grid(ceil_div(pk.T, W), a.B * a.H);
         const size_t smem = per_warp * W;

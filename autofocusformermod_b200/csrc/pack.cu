@@ -141,6 +141,48 @@ pack_tile_kernel(const int64_t *__restrict__ idx, const uint8_t *__restrict__ ma
     }
 }
 
+// union of GROUP_TILES consecutive tiles' unions, first-seen order (one warp per group; lane l holds list entries l, l+32, ...)
+__global__ void __launch_bounds__(PACK_WARPS * 32)
+pack_group_kernel(PackView pk, GroupView gv, int B) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bg = blockIdx.x * PACK_WARPS + warp;
+    if (bg >= B * gv.TG) return;
+    const int b = bg / gv.TG, grp = bg - b * gv.TG;
+    constexpr int PER_LANE = GU_MAX / 32;
+    int mine[PER_LANE];
+#pragma unroll
+    for (int x = 0; x < PER_LANE; ++x) mine[x] = -1;
+    int GU = 0;
+    for (int tl = 0; tl < GROUP_TILES; ++tl) {
+        const int tile = grp * GROUP_TILES + tl;
+        if (tile >= pk.T) break;
+        const int64_t bt = (int64_t)b * pk.T + tile;
+        const int U = pk.tile_u[bt];
+        for (int u = 0; u < U; ++u) {
+            const int o = pk.tile_oct[bt * U_MAX + u];
+            int pos = -1;
+#pragma unroll
+            for (int x = 0; x < PER_LANE; ++x) {
+                const unsigned hit = __ballot_sync(FULL, mine[x] == o);
+                if (hit && pos < 0) pos = 32 * x + __ffs(hit) - 1;
+            }
+            if (pos < 0) {
+                pos = GU++;
+#pragma unroll
+                for (int x = 0; x < PER_LANE; ++x)
+                    if (pos >> 5 == x && lane == (pos & 31)) mine[x] = o;
+            }
+            if (lane == 0) gv.sub_pos[bt * U_MAX + u] = (uint8_t)pos;
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < PER_LANE; ++x) gv.grp_oct[(int64_t)bg * GU_MAX + 32 * x + lane] = (32 * x + lane < GU) ? mine[x] : 0;
+    if (lane == 0) {
+        gv.grp_u[bg] = GU;
+        atomicMax(pk.flags + 6, GU);
+    }
+}
+
 // generic path when a union overflowed or more than 1/16 of the tokens (and more than 64) are impure
 __global__ void pack_decide_kernel(int *flags, int tokens) {
     const bool generic = flags[3] > 0 || (flags[2] > 64 && flags[2] > tokens / 16);
@@ -204,7 +246,9 @@ extern "C" int clusten_pack_build(const int64_t *nbhd_idx, const uint8_t *mask, 
     cudaMemsetAsync(pk.row_imp, 0, (size_t)B * Nk, st);
     pack_tile_kernel<<<ceil_div(bt, PACK_WARPS), PACK_WARPS * 32, 0, st>>>(nbhd_idx, mask, B, Nq, M, Nk, pk);
     pack_decide_kernel<<<1, 1, 0, st>>>(pk.flags, B * Nq);
-    note_launches(2);
+    const GroupView gv = group_view(pack, B, Nq, Nk);
+    pack_group_kernel<<<ceil_div(B * gv.TG, PACK_WARPS), PACK_WARPS * 32, 0, st>>>(pk, gv, B);
+    note_launches(3);
     return check_launch("pack_build");
 }
 

@@ -40,8 +40,22 @@ struct PackView {
 struct Rows4 { const void *p; int64_t sb, sh, sn; };   // strided [B,H,N,C] operand: element strides, unit inner stride
 
 struct PackLayout {
-    size_t flags, tile_u, tile_oct, slot_of, slot_t, oct_off, oct_ent, tok_imp, row_imp, imp_list, rimp_list, sort_ws, total;
-    int T, NO, imp_cap, rimp_cap;
+    size_t flags, tile_u, tile_oct, slot_of, slot_t, oct_off, oct_ent, tok_imp, row_imp, imp_list, rimp_list, sort_ws,
+           grp_u, grp_oct, sub_pos, total;
+    int T, NO, imp_cap, rimp_cap, TG;
+};
+
+// Tile GROUPS (clusten_fused_tma.cu): GROUP_TILES consecutive tiles = the 64 tokens one CTA of the TMA-staged kernels owns.
+// Per group the union of its tiles' unions (first-seen order: a CTA stages these octets in shared memory once, by TMA box
+// loads) and, per (tile, union position), the position of that octet in the group's list.
+constexpr int GROUP_TILES = 4;
+constexpr int GU_MAX = GROUP_TILES * U_MAX;     // a group's union can never exceed the sum of its tiles' unions
+
+struct GroupView {
+    int *grp_u;          // [B*TG]            octets in the group's union
+    int *grp_oct;        // [B*TG*GU_MAX]     their ids, first-seen order over the group's tiles
+    uint8_t *sub_pos;    // [B*T*U_MAX]       position in the group's list of (tile, union position u)
+    int TG;              // groups per batch sample = ceil(T / GROUP_TILES);  flags[6] = largest group union
 };
 
 inline size_t pack_align(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -67,6 +81,10 @@ inline PackLayout pack_layout(int B, int Nq, int Nk) {
     L.imp_list = o; o += pack_align((size_t)L.imp_cap * 4);
     L.rimp_list = o; o += pack_align((size_t)L.rimp_cap * 4);
     L.sort_ws = o;  o += 5 * pack_align((size_t)L.T * U_MAX * B * 4) + radix_sort_workspace_bytes(B, L.T * U_MAX) + 256;
+    L.TG = (L.T + GROUP_TILES - 1) / GROUP_TILES;
+    L.grp_u = o;    o += pack_align((size_t)B * L.TG * 4);
+    L.grp_oct = o;  o += pack_align((size_t)B * L.TG * GU_MAX * 4);
+    L.sub_pos = o;  o += pack_align(bt * U_MAX);
     L.total = o;
     return L;
 }
@@ -91,6 +109,17 @@ inline PackView pack_view(void *buf, int B, int Nq, int Nk) {
     v.T = L.T;
     v.NO = L.NO;
     return v;
+}
+
+inline GroupView group_view(void *buf, int B, int Nq, int Nk) {
+    const PackLayout L = pack_layout(B, Nq, Nk);
+    char *p = reinterpret_cast<char *>(buf);
+    GroupView g;
+    g.grp_u = reinterpret_cast<int *>(p + L.grp_u);
+    g.grp_oct = reinterpret_cast<int *>(p + L.grp_oct);
+    g.sub_pos = reinterpret_cast<uint8_t *>(p + L.sub_pos);
+    g.TG = L.TG;
+    return g;
 }
 
 }  // namespace clusten
