@@ -74,9 +74,19 @@ def make_wg():
     print("wg")
 
 
-def make_aff(aff):
-    """Reference AFF class forward (aff.py:568-686), 'test' preset, closed-form weights and images."""
-    cfg = ao.PRESETS["test"]
+# (preset, B, H, W) of the reference-class goldens: the toy preset plus the BASELINE presets at the shapes the bench runs
+AFF_GOLDENS = {
+    "aff_test_256": ("test", 2, 256, 256),
+    "aff_mini_512": ("mini", 2, 512, 512),                 # configs[1] backbone: 16 384 tokens, ds 0.25
+    "aff_tiny_1_5_512": ("tiny_1_5", 2, 512, 512),         # configs[2]: ds 0.2 -> 3276 / 655 / 131 tokens, padded clusters, masks
+    "aff_base_256x512": ("base", 1, 256, 512),             # configs[4]'s model: m = 24, M = 144 (every stage padded)
+}
+
+
+def make_aff(aff, name):
+    """Reference AFF class forward (aff.py:568-686), closed-form weights and images."""
+    preset, B, H, Wd = AFF_GOLDENS[name]
+    cfg = ao.PRESETS[preset]
     W = ao.synthetic_state(cfg)
     m = aff.AFF(embed_dim=cfg["embed_dim"], cluster_size=cfg["cluster_size"], nbhd_size=list(cfg["nbhd_size"]),
                 alpha=cfg["alpha"], ds_rate=cfg["ds_rate"], depths=cfg["depths"], num_heads=cfg["num_heads"],
@@ -87,7 +97,7 @@ def make_aff(aff):
     W2["patch_embed.bn.num_batches_tracked"] = sd["patch_embed.bn.num_batches_tracked"]
     m.load_state_dict(W2)
     m.eval()
-    x = ao.synthetic_images(2, 256, 256)
+    x = ao.synthetic_images(B, H, Wd)
     with torch.no_grad(), ref_loader.canonical_ties():
         out = m(x)
     save = {}
@@ -100,17 +110,21 @@ def make_aff(aff):
         save[f"res{i}_sub"] = _np(f[:, ::stride])
         save[f"res{i}_sum"] = _np(f.double().sum())
         save[f"res{i}_abs"] = _np(f.double().abs().sum())
-    np.savez_compressed(os.path.join(OUT, "aff_test_256.npz"), **save)
-    print("aff")
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+    print("aff", name, {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v) and not k.endswith("pos")})
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     pu, aff = ref_loader.load()
-    make_sfc(pu)
-    make_shepard(pu)
-    make_wg()
-    make_aff(aff)
+    import sys
+    if len(sys.argv) < 2:
+        make_sfc(pu)
+        make_shepard(pu)
+        make_wg()
+    for name in AFF_GOLDENS:
+        if len(sys.argv) < 2 or name in sys.argv[1:]:
+            make_aff(aff, name)
 
 
 if __name__ == "__main__":
