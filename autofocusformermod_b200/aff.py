@@ -497,7 +497,14 @@ class PatchEmbed(nn.Module):
         # free.  fp32 keeps NCHW: there cuDNN answers NHWC with TF32 tensor-core convolutions (2e-3 off the fp32 oracle).
         if CHANNELS_LAST_STEM and torch.is_autocast_enabled():
             x = x.contiguous(memory_format=torch.channels_last)
-        x = self.proj2(self.act1(self.bn(self.proj1(x))))
+            x = self.proj2(self.act1(self.bn(self.proj1(x))))
+        elif x.dtype == torch.float32 and x.is_cuda and not torch.is_autocast_enabled():
+            # fp32 means fp32: cuDNN is otherwise free to pick TF32 tensor-core convolutions (torch's default), which it does from
+            # ~512x512 inputs on -- 1e-3 off the fp32 reference in res2 and enough to flip top-k selections two stages later
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                x = self.proj2(self.act1(self.bn(self.proj1(x))))
+        else:
+            x = self.proj2(self.act1(self.bn(self.proj1(x))))
         b, c, h, w = x.shape
         x = x.flatten(2).transpose(1, 2)
         if self.norm is not None:

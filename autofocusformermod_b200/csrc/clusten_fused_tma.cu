@@ -73,22 +73,102 @@ __device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], con
     t2::mma_tf32(d, ah[0], ah[1], ah[2], ah[3], b0h, b1h);
 }
 
-// Geometry of one staged octet.  IB = bytes of one operand row (C channels); PACKED: one box whose rows are [k | v] (2*IB bytes),
-// else a K box followed by a V box.  RB = row bytes of a box = its swizzle span (32 / 64 / 128).
+// Geometry of one staged octet = ONE box of 8 rows.  IB = bytes of one operand row (C channels).  PACKED: the box rows are [k | v]
+// (2*IB bytes) and one load serves both contractions; else the staging area holds the K boxes during the dot phase and is refilled
+// with the V boxes (same octets, same positions) while the softmax runs.  RB = row bytes of a box = its swizzle span.
 template <typename T, int C, bool PACKED> struct Geo {
     static constexpr int IB = C * (int)sizeof(T);
     static constexpr int RB = PACKED ? 2 * IB : IB;
     static_assert(RB == 32 || RB == 64 || RB == 128, "box rows are 32, 64 or 128 bytes");
     static constexpr int BOX = 8 * RB;                     // bytes of one box = period of its swizzle pattern
-    static constexpr int BLK = PACKED ? BOX : 2 * BOX;     // bytes of one staged octet (k and v)
-    static constexpr int V_BOX = PACKED ? 0 : BOX;         // byte offset of the box holding v
     static constexpr int V_COL = PACKED ? IB : 0;          // byte offset of v inside a box row
     static constexpr int SH = RB == 128 ? 0 : RB == 64 ? 1 : 2;
     // byte offset inside a box of (row r, byte o of the row): 16-byte chunks XOR-ed with the 128-byte line index (CU_TENSOR_MAP_SWIZZLE_*)
     __device__ static constexpr int at(int r, int o) { return r * RB + ((((o >> 4) ^ ((r >> SH) & (RB / 16 - 1))) << 4) | (o & 15)); }
 };
 
-struct Launch { int cap, warp_bytes; };                    // staging capacity (octets, multiple of OCT_PER_BAR), per-warp scratch bytes
+struct Launch { int cap, warp_bytes, rcp_qm; };            // staging capacity (octets, multiple of OCT_PER_BAR), per-warp scratch bytes,
+                                                           // ceil(2^20 / (M / 4))
+
+constexpr int ZPAD = 8;                                    // floats of zeros in front of every S row: "no slot" (-1) reads them
+
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t s) { return t2::lds32(s); }
+__device__ __forceinline__ uint2 lds64(uint32_t s) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(s));
+    return v;
+}
+__device__ __forceinline__ void sts_f2_if(uint32_t s, float a, float b, int slot) {
+    asm volatile("{ .reg .pred p; setp.ge.s32 p, %3, 0; @p st.shared.v2.f32 [%0], {%1, %2}; }" ::"r"(s), "f"(a), "f"(b), "r"(slot) : "memory");
+}
+__device__ __forceinline__ int s8(uint32_t w, int byte) { return (int)(int8_t)(w >> (8 * byte)); }
+
+// 16 x 8 logits of the warp's tokens against one staged K octet
+template <typename T, int C, bool PACKED>
+__device__ __forceinline__ void qk_octet(float (&acc)[4], const uint32_t (&qa)[sizeof(T) == 4 ? C / 8 : C / 16][4],
+                                         const uint32_t (&ql)[sizeof(T) == 4 ? C / 8 : 1][4], uint32_t blk, const uint32_t *k_off) {
+    constexpr bool F32 = sizeof(T) == 4;
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    if constexpr (F32) {
+#pragma unroll
+        for (int s = 0; s < C / 8; ++s) {
+            uint32_t b0h, b0l, b1h, b1l;
+            t2::split_tf32(lds32(blk + k_off[2 * s]), b0h, b0l);
+            t2::split_tf32(lds32(blk + k_off[2 * s + 1]), b1h, b1l);
+            mma3(acc, qa[s], ql[s], b0h, b1h, b0l, b1l);
+        }
+    } else if constexpr (C == 32) {
+        uint32_t kf[4];
+        ldsm4(kf, blk + k_off[0]);
+        t2::mma16<T>(acc, qa[0][0], qa[0][1], qa[0][2], qa[0][3], kf[0], kf[1]);
+        t2::mma16<T>(acc, qa[1][0], qa[1][1], qa[1][2], qa[1][3], kf[2], kf[3]);
+    } else {
+        uint32_t kf[2];
+        ldsm2(kf, blk + k_off[0]);
+        t2::mma16<T>(acc, qa[0][0], qa[0][1], qa[0][2], qa[0][3], kf[0], kf[1]);
+    }
+}
+
+// out += P[:, octets A|B] . V[octets A|B]  (16-bit: one k16 step = two octets; sA / sB = slot16 entries of the lane's rows, 0xffff = none)
+template <typename T, int C, bool PACKED>
+__device__ __forceinline__ void pv_pair16(float (&acc)[C / 8][4], uint32_t Sa_u, uint32_t Sb_u, uint32_t sA, uint32_t sB, uint32_t blk,
+                                          const uint32_t *v_off) {
+    uint32_t af[4];
+    { const float2 p = lds_f2(Sa_u + s8(sA, 0) * 32); af[0] = t2::pack_pair<T>(p.x, p.y); }
+    { const float2 p = lds_f2(Sb_u + s8(sA, 1) * 32); af[1] = t2::pack_pair<T>(p.x, p.y); }
+    { const float2 p = lds_f2(Sa_u + s8(sB, 0) * 32); af[2] = t2::pack_pair<T>(p.x, p.y); }
+    { const float2 p = lds_f2(Sb_u + s8(sB, 1) * 32); af[3] = t2::pack_pair<T>(p.x, p.y); }
+#pragma unroll
+    for (int n2 = 0; n2 < C / 16; ++n2) {
+        uint32_t bf[4];
+        t2::ldsm4t(bf, blk + v_off[n2]);
+        t2::mma16<T>(acc[2 * n2], af[0], af[1], af[2], af[3], bf[0], bf[1]);
+        t2::mma16<T>(acc[2 * n2 + 1], af[0], af[1], af[2], af[3], bf[2], bf[3]);
+    }
+}
+
+// fp32: one k8 step = one octet (k index t <-> key 2t, t + 4 <-> key 2t + 1: see v_off)
+template <int C>
+__device__ __forceinline__ void pv_octet32(float (&acc)[C / 8][4], uint32_t Sa_u, uint32_t Sb_u, uint32_t s16, uint32_t blk, const uint32_t *v_off) {
+    const float2 p0 = lds_f2(Sa_u + s8(s16, 0) * 32), p1 = lds_f2(Sb_u + s8(s16, 1) * 32);
+    uint32_t ah[4], al[4];
+    t2::split_tf32(__float_as_uint(p0.x), ah[0], al[0]);
+    t2::split_tf32(__float_as_uint(p1.x), ah[1], al[1]);
+    t2::split_tf32(__float_as_uint(p0.y), ah[2], al[2]);
+    t2::split_tf32(__float_as_uint(p1.y), ah[3], al[3]);
+#pragma unroll
+    for (int n = 0; n < C / 8; ++n) {
+        uint32_t b0h, b0l, b1h, b1l;
+        t2::split_tf32(lds32(blk + v_off[2 * n]), b0h, b0l);
+        t2::split_tf32(lds32(blk + v_off[2 * n + 1]), b1h, b1l);
+        mma3(acc[n], ah, al, b0h, b1h, b0l, b1l);
+    }
+}
 
 template <typename T, int C, bool PACKED, bool PB>
 __global__ void __launch_bounds__(GW * 32)
@@ -100,9 +180,10 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
     constexpr bool F32 = sizeof(T) == 4;
     constexpr int KS = F32 ? C / 8 : C / 16;               // mma k-steps of the dot phase
     constexpr int NT = C / 8;                              // 8-channel n-tiles of the output
+    constexpr int UNR = F32 ? 2 : 4;                       // octets in flight per warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int M = a.M, H = a.H, Nq = a.Nq, MP = M + 4;
+    const int M = a.M, H = a.H, Nq = a.Nq, MP = M + ZPAD + 4;
     const int cap = L.cap;
     const int b = blockIdx.y / H, h = blockIdx.y - b * H;
     const int bg = b * gv.TG + blockIdx.x;
@@ -114,11 +195,11 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
     const uint32_t base = (smem_u32(dyn_raw) + 1023u) & ~1023u;
     unsigned char *dyn = dyn_raw + (base - smem_u32(dyn_raw));
     const uint32_t stage = base;
-    const uint32_t bars = base + (uint32_t)cap * G::BLK;
-    unsigned char *wmem = dyn + (size_t)cap * G::BLK + NBAR_MAX * 8 + (size_t)warp * L.warp_bytes;
-    float *S = reinterpret_cast<float *>(wmem);                                  // [16][MP]: logits / e; [M] blank, [M+1] 1/sum
-    unsigned char *slot_s = wmem + (size_t)16 * MP * 4;                          // [U_MAX][16]: slots of rows (g, g+8) adjacent
-    unsigned char *spos_s = slot_s + U_MAX * 16;                                 // [U_MAX (64)]: group position of union entry u
+    const uint32_t bars = base + (uint32_t)cap * G::BOX;
+    unsigned char *wmem = dyn + (size_t)cap * G::BOX + NBAR_MAX * 8 + (size_t)warp * L.warp_bytes;
+    float *S = reinterpret_cast<float *>(wmem) + ZPAD;                           // [16][MP]: row = [ZPAD zeros | M logits / e | blank | 1/sum | pad]
+    unsigned char *slot_s = wmem + (size_t)16 * MP * 4;                          // [8][SLOT_G_ROW]: slot16 of (row g | row g+8, union entry u)
+    unsigned char *spos_s = slot_s + SLOT_G_TILE;                                // [U_MAX]: group position of union entry u
     const int nbar = cap / OCT_PER_BAR;
     if (threadIdx.x == 0) {
         for (int k = 0; k < nbar; ++k) mbar_init(bars + 8 * k, 1);
@@ -130,23 +211,19 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
     const int rounds = (GU + cap - 1) / cap;
     const int *goct = gv.grp_oct + (int64_t)bg * GU_MAX;
     // one load round: octets [r*cap, r*cap + n) of the group's list -> staging positions 0..n-1 (warp 0; every barrier gets exactly
-    // one arrival per round, so its parity is the round counter's)
-    auto issue_round = [&](int r) {
+    // one arrival per round, so its parity is the load counter's)
+    auto issue_round = [&](int r, const CUtensorMap *map) {
         const int p0 = r * cap, n = min(GU - p0, cap);
         if (lane < nbar) {
             const int cnt = min(max(n - lane * OCT_PER_BAR, 0), OCT_PER_BAR);
-            if (cnt > 0) mbar_expect_tx(bars + 8 * lane, (uint32_t)cnt * G::BLK);
+            if (cnt > 0) mbar_expect_tx(bars + 8 * lane, (uint32_t)cnt * G::BOX);
             else mbar_arrive(bars + 8 * lane);
         }
         __syncwarp();
-        for (int x = lane; x < n; x += 32) {
-            const int row0 = __ldg(goct + p0 + x) * 8;
-            const uint32_t bar = bars + 8 * (x / OCT_PER_BAR);
-            tma_box_4d(stage + (uint32_t)x * G::BLK, &mapK, bar, 0, row0, h, b);
-            if constexpr (!PACKED) tma_box_4d(stage + (uint32_t)x * G::BLK + G::V_BOX, &mapV, bar, 0, row0, h, b);
-        }
+        for (int x = lane; x < n; x += 32)
+            tma_box_4d(stage + (uint32_t)x * G::BOX, map, bars + 8 * (x / OCT_PER_BAR), 0, __ldg(goct + p0 + x) * 8, h, b);
     };
-    if (warp == 0) issue_round(0);
+    if (warp == 0) issue_round(0, &mapK);
 
     // ---- per-warp tile context -------------------------------------------------------------------------------------------------
     const int U = active ? pk.tile_u[bt] : 0;
@@ -161,35 +238,32 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
 #pragma unroll
                 for (int kq = 0; kq < 4; ++kq) impm |= ((w4[qd] >> (8 * kq)) & 1u) << (4 * qd + kq);
         }
-        // slot table [u][16 rows] -> shared, rows (g, g+8) side by side; group positions of the union entries
-        for (int u = lane; u < U_MAX; u += 32) {
-            const uint4 s4 = __ldg(reinterpret_cast<const uint4 *>(pk.slot_t + ((int64_t)bt * U_MAX + u) * 16));
-            uint4 o;
-            o.x = __byte_perm(s4.x, s4.z, 0x5140); o.y = __byte_perm(s4.x, s4.z, 0x7362);
-            o.z = __byte_perm(s4.y, s4.w, 0x5140); o.w = __byte_perm(s4.y, s4.w, 0x7362);
-            *reinterpret_cast<uint4 *>(slot_s + u * 16) = o;
-        }
+        const uint4 *sg = reinterpret_cast<const uint4 *>(gv.slot_g + (int64_t)bt * SLOT_G_TILE);
+        for (int x = lane; x < SLOT_G_TILE / 16; x += 32) reinterpret_cast<uint4 *>(slot_s)[x] = __ldg(sg + x);
         if (lane < U_MAX / 4) reinterpret_cast<uint32_t *>(spos_s)[lane] = __ldg(reinterpret_cast<const uint32_t *>(gv.sub_pos + (int64_t)bt * U_MAX) + lane);
+        if (lane < 16) *reinterpret_cast<float4 *>(S + lane * MP - ZPAD) = make_float4(0.f, 0.f, 0.f, 0.f), *reinterpret_cast<float4 *>(S + lane * MP - ZPAD + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const uint32_t S_u = smem_u32(S), slot_u = smem_u32(slot_s) + 2 * g;
-    const T *Q = reinterpret_cast<const T *>(a.q) + b * a.q_sb + h * a.q_sh;
-    uint32_t ready = 0;                                    // barriers seen complete in the current round
-    int round_no = 0;                                      // load rounds issued so far - 1 (CTA-uniform)
+    const uint32_t S_u = smem_u32(S), slot_u = smem_u32(slot_s) + g * SLOT_G_ROW, spos_u = smem_u32(spos_s);
+    const uint32_t Sa_u = S_u + (uint32_t)(g * MP + 2 * t) * 4, Sb_u = Sa_u + (uint32_t)(8 * MP) * 4;
+    uint32_t ready = 0;                                    // general path: barriers seen complete in the current load round
+    int loads = 0;                                         // load rounds issued so far - 1 (CTA-uniform): parity of the barriers
     auto wait_oct = [&](int x) {
         const int k = x / OCT_PER_BAR;
-        if (!((ready >> k) & 1u)) { mbar_wait(bars + 8 * k, round_no & 1); ready |= 1u << k; }
+        if (!((ready >> k) & 1u)) { mbar_wait(bars + 8 * k, loads & 1); ready |= 1u << k; }
     };
 
-    // ---- phase 1: logits of the 16 tokens against every octet of the tile's union (tensor cores), selected blocks -> S ----------
+    // ---- q fragments (straight from global: read once per warp) and the blank logit q . blank_k[h] (aff.py:140) -------------------
     uint32_t qa[KS][4], ql[F32 ? KS : 1][4];
     if (active) {
-        const T *qra = Q + (int64_t)min(ra, Nq - 1) * a.q_sn, *qrb = Q + (int64_t)min(rb, Nq - 1) * a.q_sn;
+        const T *Q = t2::opaque(reinterpret_cast<const T *>(a.q) + b * a.q_sb + h * a.q_sh);
+        const int oa = min(ra, Nq - 1) * (int)a.q_sn, ob = min(rb, Nq - 1) * (int)a.q_sn;
         const T *bk = reinterpret_cast<const T *>(a.blank_k) + h * C;
-        float pa = 0.f, pb = 0.f;                          // blank logit q . blank_k[h] (aff.py:140), this lane's channels
+        float pa = 0.f, pb = 0.f;
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
             if constexpr (F32) {
-                const float x0 = __ldg(qra + 8 * s + t), x1 = __ldg(qrb + 8 * s + t), x2 = __ldg(qra + 8 * s + t + 4), x3 = __ldg(qrb + 8 * s + t + 4);
+                const float x0 = __uint_as_float(t2::ldg4(t2::at(Q, oa + 8 * s + t))), x1 = __uint_as_float(t2::ldg4(t2::at(Q, ob + 8 * s + t)));
+                const float x2 = __uint_as_float(t2::ldg4(t2::at(Q, oa + 8 * s + t + 4))), x3 = __uint_as_float(t2::ldg4(t2::at(Q, ob + 8 * s + t + 4)));
                 const float w0 = __ldg(bk + 8 * s + t), w1 = __ldg(bk + 8 * s + t + 4);
                 pa = fmaf(x0, w0, pa); pa = fmaf(x2, w1, pa);
                 pb = fmaf(x1, w0, pb); pb = fmaf(x3, w1, pb);
@@ -198,8 +272,8 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                 t2::split_tf32(__float_as_uint(x2), qa[s][2], ql[s][2]);
                 t2::split_tf32(__float_as_uint(x3), qa[s][3], ql[s][3]);
             } else {
-                qa[s][0] = t2::ldg4(qra + 16 * s + 2 * t);     qa[s][1] = t2::ldg4(qrb + 16 * s + 2 * t);
-                qa[s][2] = t2::ldg4(qra + 16 * s + 8 + 2 * t); qa[s][3] = t2::ldg4(qrb + 16 * s + 8 + 2 * t);
+                qa[s][0] = t2::ldg4(t2::at(Q, oa + 16 * s + 2 * t));     qa[s][1] = t2::ldg4(t2::at(Q, ob + 16 * s + 2 * t));
+                qa[s][2] = t2::ldg4(t2::at(Q, oa + 16 * s + 8 + 2 * t)); qa[s][3] = t2::ldg4(t2::at(Q, ob + 16 * s + 8 + 2 * t));
                 const uint32_t w0 = t2::ldg4(bk + 16 * s + 2 * t), w1 = t2::ldg4(bk + 16 * s + 8 + 2 * t);
                 auto lo = [](uint32_t w) { return to_f(*reinterpret_cast<const T *>(&w)); };
                 auto hi = [](uint32_t w) { const uint32_t x = w >> 16; return to_f(*reinterpret_cast<const T *>(&x)); };
@@ -214,7 +288,7 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
         if (t == 0) { S[g * MP + M] = pa; S[(g + 8) * MP + M] = pb; }
     }
     __syncwarp();
-    // lane-constant fragment offsets inside a staged octet
+    // lane-constant fragment offsets inside a staged box
     uint32_t k_off[F32 ? 2 * KS : 1];
     if constexpr (F32) {
 #pragma unroll
@@ -222,93 +296,136 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
     } else {
         k_off[0] = G::at(lane & 7, ((lane >> 3) & (C == 32 ? 3 : 1)) * 16);       // ldmatrix: matrix lane>>3 = 16-byte chunk of the k row
     }
-    const uint32_t Sa_u = S_u + (uint32_t)(g * MP + 2 * t) * 4, Sb_u = Sa_u + (uint32_t)(8 * MP) * 4;
-    for (int r = 0; r < rounds; ++r) {
-        if (r > 0) {
-            __syncthreads();                               // every warp is done with the previous round's octets
-            ++round_no; ready = 0;
-            if (warp == 0) issue_round(r);
-        }
-        const int rbase = r * cap;
-        for (int u = 0; u < U; ++u) {
-            const int x = (int)spos_s[u] - rbase;
-            if ((unsigned)x >= (unsigned)cap) continue;    // staged in another round
-            wait_oct(x);
-            const uint32_t blk = stage + (uint32_t)x * G::BLK;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            if constexpr (F32) {
+    uint32_t v_off[F32 ? 2 * NT : NT / 2];
+    if constexpr (F32) {
+        // k index t <-> key 2t, k index t+4 <-> key 2t+1 (any permutation of the summation index is a valid mma): the probabilities
+        // of one lane are then adjacent in S and the V words of a warp fall into 32 different banks of the swizzled box
 #pragma unroll
-                for (int s = 0; s < KS; ++s) {
-                    uint32_t b0h, b0l, b1h, b1l;
-                    t2::split_tf32(t2::lds32(blk + k_off[2 * s]), b0h, b0l);
-                    t2::split_tf32(t2::lds32(blk + k_off[2 * s + 1]), b1h, b1l);
-                    mma3(acc, qa[s], ql[s], b0h, b1h, b0l, b1l);
-                }
-            } else if constexpr (C == 32) {
-                uint32_t kf[4];
-                ldsm4(kf, blk + k_off[0]);
-                t2::mma16<T>(acc, qa[0][0], qa[0][1], qa[0][2], qa[0][3], kf[0], kf[1]);
-                t2::mma16<T>(acc, qa[1][0], qa[1][1], qa[1][2], qa[1][3], kf[2], kf[3]);
-            } else {
-                uint32_t kf[2];
-                ldsm2(kf, blk + k_off[0]);
-                t2::mma16<T>(acc, qa[0][0], qa[0][1], qa[0][2], qa[0][3], kf[0], kf[1]);
-            }
-            const uint32_t s2 = t2::lds16(slot_u + u * 16);
-            const int sga = (int)(int8_t)(s2 & 0xffu), sgb = (int)(int8_t)(s2 >> 8);
-            if (sga >= 0) *reinterpret_cast<float2 *>(S + g * MP + 8 * sga + 2 * t) = make_float2(acc[0], acc[1]);
-            if (sgb >= 0) *reinterpret_cast<float2 *>(S + (g + 8) * MP + 8 * sgb + 2 * t) = make_float2(acc[2], acc[3]);
+        for (int n = 0; n < NT; ++n) {
+            v_off[2 * n] = G::at(2 * t, G::V_COL + (8 * n + g) * 4);
+            v_off[2 * n + 1] = G::at(2 * t + 1, G::V_COL + (8 * n + g) * 4);
         }
+    } else {
+        // ldmatrix.trans: matrices (octet A, n), (octet B, n), (octet A, n+1), (octet B, n+1); lane>>3 picks the matrix
+#pragma unroll
+        for (int n2 = 0; n2 < NT / 2; ++n2) v_off[n2] = G::at(lane & 7, G::V_COL + (2 * n2 + (lane >> 4)) * 16);
+    }
+
+    // ---- phase 1: logits of the 16 tokens against every octet of the tile's union (tensor cores), selected 8-column blocks -> S -----
+    if (rounds == 1) {
+        // fast path (the group's union fits the staging area): UNR octets in flight, barriers taken in list order
+        int wmax = -1;
+        for (int u0 = 0; u0 < U; u0 += UNR) {
+            const uint32_t xw = UNR == 4 ? lds32(spos_u + u0) : (uint32_t)t2::lds16(spos_u + u0);
+            uint32_t sw[2];
+            if constexpr (UNR == 4) { const uint2 v = lds64(slot_u + 2 * u0); sw[0] = v.x; sw[1] = v.y; }
+            else { sw[0] = lds32(slot_u + 2 * u0); sw[1] = 0; }
+            int kneed = 0;
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) kneed = max(kneed, (int)((xw >> (8 * j)) & 0xffu));      // (entries beyond U are 0)
+            kneed /= OCT_PER_BAR;
+            while (wmax < kneed) { ++wmax; mbar_wait(bars + 8 * wmax, 0); }
+            float acc[UNR][4];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) qk_octet<T, C, PACKED>(acc[j], qa, ql, stage + ((xw >> (8 * j)) & 0xffu) * G::BOX, k_off);
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int sga = s8(sw[j >> 1], 2 * (j & 1)), sgb = s8(sw[j >> 1], 2 * (j & 1) + 1);
+                sts_f2_if(Sa_u + sga * 32, acc[j][0], acc[j][1], sga);
+                sts_f2_if(Sb_u + sgb * 32, acc[j][2], acc[j][3], sgb);
+            }
+        }
+    } else {
+        for (int r = 0; r < rounds; ++r) {
+            if (r > 0) {
+                __syncthreads();                           // every warp is done with the previous round's octets
+                ++loads; ready = 0;
+                if (warp == 0) issue_round(r, &mapK);
+            }
+            const int rbase = r * cap;
+            for (int u = 0; u < U; ++u) {
+                const int x = (int)spos_s[u] - rbase;
+                if ((unsigned)x >= (unsigned)cap) continue;    // staged in another round
+                wait_oct(x);
+                float acc[4];
+                qk_octet<T, C, PACKED>(acc, qa, ql, stage + (uint32_t)x * G::BOX, k_off);
+                const uint32_t s2 = t2::lds16(slot_u + 2 * u);
+                const int sga = s8(s2, 0), sgb = s8(s2, 1);
+                sts_f2_if(Sa_u + sga * 32, acc[0], acc[1], sga);
+                sts_f2_if(Sb_u + sgb * 32, acc[2], acc[3], sgb);
+            }
+        }
+    }
+    // unpacked operands: the staging area is refilled with the V boxes of the same octets while the softmax runs
+    if (!PACKED && rounds == 1) {
+        __syncthreads();
+        ++loads; ready = 0;
+        if (warp == 0) issue_round(0, &mapV);
     }
     __syncwarp();
     // ---- phase 2a: + bias + mask, four consecutive neighbours per lane (coalesced reads of the tile's bias-index / mask block) ----
+    // A masked neighbour (aff.py:137: logit - 100, NOT -inf) is a wildcard of the mask-aware pack: the octet column that stands for
+    // it was scored against whatever row the octet holds there (zeros beyond the last key row).  The reference scores it against
+    // row idx[b,i,j] (= 0 for the padded tail of the last cluster, point_utils.py:283), and with large logits exp(. - 100) is not
+    // nothing: such entries (a few tokens per sample) get their exact logit here and their exact value row before phase 3.
+    bool saw_mask = false;
+    auto masked_logit = [&](int row, int64_t kidx) {
+        const T *qr = reinterpret_cast<const T *>(a.q) + b * a.q_sb + h * a.q_sh + (int64_t)(i0 + row) * a.q_sn;
+        const T *kr = reinterpret_cast<const T *>(a.k) + b * a.k_sb + h * a.k_sh + min(max(kidx, (int64_t)0), (int64_t)a.Nk - 1) * a.k_sn;
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s = fmaf(to_f(qr[c]), to_f(kr[c]), s);
+        return s - 100.f;
+    };
     if (active) {
         const int rows = min(TILE_TOK, Nq - i0), QM = M >> 2;
+        const uint8_t *mk = a.mask ? a.mask + ((int64_t)b * Nq + i0) * M : nullptr;
         if constexpr (!PB) {
-            const int32_t *bi = a.bias_idx + ((int64_t)b * Nq + i0) * M;
-            const uint8_t *mk = a.mask ? a.mask + ((int64_t)b * Nq + i0) * M : nullptr;
+            const int4 *bi = reinterpret_cast<const int4 *>(a.bias_idx + ((int64_t)b * Nq + i0) * M);
+            const float *tabh = t2::opaque(a.bias_tab + h);
             for (int e = lane; e < rows * QM; e += 32) {
-                const int row = e / QM, j = (e - row * QM) * 4;
-                const int4 bv = __ldg(reinterpret_cast<const int4 *>(bi) + e);
+                const int row = (e * L.rcp_qm) >> 20, j = (e - row * QM) * 4;
+                const int4 bv = __ldg(bi + e);
+                const float g0 = __ldg(t2::at(tabh, bv.x * H)), g1 = __ldg(t2::at(tabh, bv.y * H));
+                const float g2 = __ldg(t2::at(tabh, bv.z * H)), g3 = __ldg(t2::at(tabh, bv.w * H));
                 float4 x = *reinterpret_cast<float4 *>(S + row * MP + j);
-                x.x += __ldg(a.bias_tab + bv.x * H + h);
-                x.y += __ldg(a.bias_tab + bv.y * H + h);
-                x.z += __ldg(a.bias_tab + bv.z * H + h);
-                x.w += __ldg(a.bias_tab + bv.w * H + h);
+                x.x += g0; x.y += g1; x.z += g2; x.w += g3;
                 if (mk) {
                     const uchar4 m4 = __ldg(reinterpret_cast<const uchar4 *>(mk) + e);
-                    if (!m4.x) x.x += -100.f;
-                    if (!m4.y) x.y += -100.f;
-                    if (!m4.z) x.z += -100.f;
-                    if (!m4.w) x.w += -100.f;
+                    if (!(m4.x && m4.y && m4.z && m4.w)) {
+                        saw_mask = true;
+                        const int64_t *ir = a.idx + ((int64_t)b * Nq + i0 + row) * M + j;
+                        if (!m4.x) x.x = masked_logit(row, ir[0]) + g0;
+                        if (!m4.y) x.y = masked_logit(row, ir[1]) + g1;
+                        if (!m4.z) x.z = masked_logit(row, ir[2]) + g2;
+                        if (!m4.w) x.w = masked_logit(row, ir[3]) + g3;
+                    }
                 }
                 *reinterpret_cast<float4 *>(S + row * MP + j) = x;
             }
         } else {
             const PosBiasW pw = pos_bias_load(a.pe_w, a.pe_b, h);
             const float2 *PQ = reinterpret_cast<const float2 *>(a.pos_q) + (int64_t)b * Nq + i0;
-            const float2 *PK = reinterpret_cast<const float2 *>(a.pos_k) + (int64_t)b * a.Nk;
-            const int64_t *ix = a.idx + ((int64_t)b * Nq + i0) * M;
-            const uint8_t *mk = a.mask ? a.mask + ((int64_t)b * Nq + i0) * M : nullptr;
+            const float2 *PK = t2::opaque(reinterpret_cast<const float2 *>(a.pos_k) + (int64_t)b * a.Nk);
+            const longlong2 *ix = reinterpret_cast<const longlong2 *>(a.idx + ((int64_t)b * Nq + i0) * M);
             const int klast = a.Nk - 1;
             for (int e = lane; e < rows * QM; e += 32) {
-                const int row = e / QM, j = (e - row * QM) * 4;
-                // (a slot is 8 consecutive key rows: the first index of the quad gives the other three; masked entries are wildcards
-                // of the mask-aware pack -- their -100 swamps whatever bias the clamped row yields)
-                const longlong2 i01 = __ldg(reinterpret_cast<const longlong2 *>(ix) + 2 * e);
-                const longlong2 i23 = __ldg(reinterpret_cast<const longlong2 *>(ix) + 2 * e + 1);
+                const int row = (e * L.rcp_qm) >> 20, j = (e - row * QM) * 4;
+                const longlong2 i01 = __ldg(ix + 2 * e), i23 = __ldg(ix + 2 * e + 1);
                 const float2 pq = __ldg(PQ + row);
+                const float2 k0 = __ldg(t2::at(PK, min(max((int)i01.x, 0), klast))), k1 = __ldg(t2::at(PK, min(max((int)i01.y, 0), klast)));
+                const float2 k2 = __ldg(t2::at(PK, min(max((int)i23.x, 0), klast))), k3 = __ldg(t2::at(PK, min(max((int)i23.y, 0), klast)));
                 float4 x = *reinterpret_cast<float4 *>(S + row * MP + j);
-                x.x += pos_bias(pw, pq, __ldg(PK + min(max((int)i01.x, 0), klast)));
-                x.y += pos_bias(pw, pq, __ldg(PK + min(max((int)i01.y, 0), klast)));
-                x.z += pos_bias(pw, pq, __ldg(PK + min(max((int)i23.x, 0), klast)));
-                x.w += pos_bias(pw, pq, __ldg(PK + min(max((int)i23.y, 0), klast)));
+                const float g0 = pos_bias(pw, pq, k0), g1 = pos_bias(pw, pq, k1), g2 = pos_bias(pw, pq, k2), g3 = pos_bias(pw, pq, k3);
+                x.x += g0; x.y += g1; x.z += g2; x.w += g3;
                 if (mk) {
                     const uchar4 m4 = __ldg(reinterpret_cast<const uchar4 *>(mk) + e);
-                    if (!m4.x) x.x += -100.f;
-                    if (!m4.y) x.y += -100.f;
-                    if (!m4.z) x.z += -100.f;
-                    if (!m4.w) x.w += -100.f;
+                    if (!(m4.x && m4.y && m4.z && m4.w)) {
+                        saw_mask = true;
+                        if (!m4.x) x.x = masked_logit(row, i01.x) + g0;
+                        if (!m4.y) x.y = masked_logit(row, i01.y) + g1;
+                        if (!m4.z) x.z = masked_logit(row, i23.x) + g2;
+                        if (!m4.w) x.w = masked_logit(row, i23.y) + g3;
+                    }
                 }
                 *reinterpret_cast<float4 *>(S + row * MP + j) = x;
             }
@@ -317,6 +434,7 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
     __syncwarp();
     // ---- phase 2b: softmax over M + 1 logits, two lanes per token row; e_j stay unnormalised in S ---------------------------------
     if (active) {
+        constexpr float LOG2E = 1.4426950408889634f;
         const int row = lane >> 1, half = lane & 1;
         const int i = i0 + row;
         const bool rvalid = i < Nq && !((impm >> row) & 1u);
@@ -335,11 +453,11 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
         if (rvalid) {
             for (int j = j0; j < j1; j += 4) {
                 float4 x = *reinterpret_cast<float4 *>(Sr + j);
-                x.x = f_exp<T>(x.x - mx); x.y = f_exp<T>(x.y - mx); x.z = f_exp<T>(x.z - mx); x.w = f_exp<T>(x.w - mx);
+                x.x = ex2f((x.x - mx) * LOG2E); x.y = ex2f((x.y - mx) * LOG2E); x.z = ex2f((x.z - mx) * LOG2E); x.w = ex2f((x.w - mx) * LOG2E);
                 sum += (x.x + x.y) + (x.z + x.w);
                 *reinterpret_cast<float4 *>(Sr + j) = x;
             }
-            if (half == 0) { const float e = f_exp<T>(Sr[M] - mx); Sr[M] = e; sum += e; }
+            if (half == 0) { const float e = ex2f((Sr[M] - mx) * LOG2E); Sr[M] = e; sum += e; }
         } else {
             for (int j = j0; j < j1; j += 4) *reinterpret_cast<float4 *>(Sr + j) = make_float4(0.f, 0.f, 0.f, 0.f);
             if (half == 0) Sr[M] = 0.f;
@@ -353,89 +471,82 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
     float acc[NT][4];
 #pragma unroll
     for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-    uint32_t v_off[F32 ? 2 * NT : (NT + 1) / 2];
-    if constexpr (F32) {
-        // k index t <-> key 2t, k index t+4 <-> key 2t+1 (any permutation of the summation index is a valid mma): the probabilities
-        // of one lane are then adjacent in S and the V words of a warp fall into 32 different banks of the swizzled box
+    if (__any_sync(FULL, saw_mask)) {
+        // masked entries: e_j leaves S (its octet column must not pull in the wildcard row) and enters the accumulators with the row
+        // the reference reads, v[idx[b,i,j]]; the lanes that own the token's row in the mma layout take it
+        const int cnt = min(TILE_TOK, Nq - i0) * M;
+        const uint8_t *mk = a.mask + ((int64_t)b * Nq + i0) * M;
+        const T *Vb = reinterpret_cast<const T *>(a.v) + b * a.v_sb + h * a.v_sh;
+        for (int x0 = 0; x0 < cnt; x0 += 32) {
+            unsigned bal = __ballot_sync(FULL, x0 + lane < cnt && !mk[x0 + lane]);
+            while (bal) {
+                const int x = x0 + __ffs(bal) - 1;
+                bal &= bal - 1;
+                const int row = x / M, j = x - row * M;
+                if ((impm >> row) & 1u) continue;
+                const float e = S[row * MP + j];
+                __syncwarp();
+                if (lane == 0) S[row * MP + j] = 0.f;
+                const int64_t kidx = a.idx[((int64_t)b * Nq + i0 + row) * M + j];
+                const T *vr = Vb + min(max(kidx, (int64_t)0), (int64_t)a.Nk - 1) * a.v_sn + 2 * t;
+                if (g == (row & 7)) {
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            v_off[2 * n] = G::V_BOX + G::at(2 * t, G::V_COL + (8 * n + g) * 4);
-            v_off[2 * n + 1] = G::V_BOX + G::at(2 * t + 1, G::V_COL + (8 * n + g) * 4);
+                    for (int n = 0; n < NT; ++n) {
+                        const float v0 = e * to_f(vr[8 * n]), v1 = e * to_f(vr[8 * n + 1]);
+                        if (row < 8) { acc[n][0] += v0; acc[n][1] += v1; }
+                        else { acc[n][2] += v0; acc[n][3] += v1; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (rounds == 1) {
+        int wmax = PACKED ? NBAR_MAX : -1;                 // (packed: every octet of the union was waited for in phase 1)
+        for (int u0 = 0; u0 < U; u0 += 4) {
+            const uint32_t xw = lds32(spos_u + u0);
+            const uint2 sw = lds64(slot_u + 2 * u0);
+            if constexpr (!PACKED) {
+                int kneed = max(max((int)(xw & 0xffu), (int)((xw >> 8) & 0xffu)), max((int)((xw >> 16) & 0xffu), (int)(xw >> 24))) / OCT_PER_BAR;
+                while (wmax < kneed) { ++wmax; mbar_wait(bars + 8 * wmax, loads & 1); }
+            }
+            if constexpr (F32) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)                // (entries beyond U: no slots -> zero probabilities against staged octet 0)
+                    pv_octet32<C>(acc, Sa_u, Sb_u, (j < 2 ? sw.x : sw.y) >> (16 * (j & 1)), stage + ((xw >> (8 * j)) & 0xffu) * G::BOX, v_off);
+            } else {
+                const uint32_t hiB = (lane >> 3) & 1;      // this lane addresses octet B of the pair in the ldmatrix
+                pv_pair16<T, C, PACKED>(acc, Sa_u, Sb_u, sw.x & 0xffffu, sw.x >> 16, stage + ((xw >> (8 * hiB)) & 0xffu) * G::BOX, v_off);
+                pv_pair16<T, C, PACKED>(acc, Sa_u, Sb_u, sw.y & 0xffffu, sw.y >> 16, stage + ((xw >> (16 + 8 * hiB)) & 0xffu) * G::BOX, v_off);
+            }
         }
     } else {
-        // ldmatrix.trans: matrices (octet A, n), (octet B, n), (octet A, n+1), (octet B, n+1); lane>>3 picks the matrix
-#pragma unroll
-        for (int n2 = 0; n2 < (NT + 1) / 2; ++n2) v_off[n2] = G::V_BOX + G::at(lane & 7, G::V_COL + (2 * n2 + (lane >> 4)) * 16);
-    }
-    const int reload = rounds > 1;
-    for (int r = 0; r < rounds; ++r) {
-        if (reload) {
+        for (int r = 0; r < rounds; ++r) {
             __syncthreads();
-            ++round_no; ready = 0;
-            if (warp == 0) issue_round(r);
-        }
-        const int rbase = r * cap;
-        if constexpr (F32) {
-            for (int u = 0; u < U; ++u) {
-                const int x = (int)spos_s[u] - rbase;
-                if ((unsigned)x >= (unsigned)cap) continue;
-                wait_oct(x);
-                const uint32_t blk = stage + (uint32_t)x * G::BLK;
-                const uint32_t s2 = t2::lds16(slot_u + u * 16);
-                const int s0 = (int)(int8_t)(s2 & 0xffu), s1 = (int)(int8_t)(s2 >> 8);
-                float2 p0 = make_float2(0.f, 0.f), p1 = p0;
-                if (s0 >= 0) p0 = lds_f2(Sa_u + (uint32_t)s0 * 32);
-                if (s1 >= 0) p1 = lds_f2(Sb_u + (uint32_t)s1 * 32);
-                uint32_t ah[4], al[4];
-                t2::split_tf32(__float_as_uint(p0.x), ah[0], al[0]);
-                t2::split_tf32(__float_as_uint(p1.x), ah[1], al[1]);
-                t2::split_tf32(__float_as_uint(p0.y), ah[2], al[2]);
-                t2::split_tf32(__float_as_uint(p1.y), ah[3], al[3]);
-#pragma unroll
-                for (int n = 0; n < NT; ++n) {
-                    uint32_t b0h, b0l, b1h, b1l;
-                    t2::split_tf32(t2::lds32(blk + v_off[2 * n]), b0h, b0l);
-                    t2::split_tf32(t2::lds32(blk + v_off[2 * n + 1]), b1h, b1l);
-                    mma3(acc[n], ah, al, b0h, b1h, b0l, b1l);
+            ++loads; ready = 0;
+            if (warp == 0) issue_round(r, PACKED ? &mapK : &mapV);
+            const int rbase = r * cap;
+            if constexpr (F32) {
+                for (int u = 0; u < U; ++u) {
+                    const int x = (int)spos_s[u] - rbase;
+                    if ((unsigned)x >= (unsigned)cap) continue;
+                    wait_oct(x);
+                    pv_octet32<C>(acc, Sa_u, Sb_u, t2::lds16(slot_u + 2 * u), stage + (uint32_t)x * G::BOX, v_off);
                 }
-            }
-        } else {
-            int pend_x = -1, pend_u = 0;
-            auto pair = [&](int uA, int xA, int uB, int xB) {      // octets A (keys 0..7 of the k16 step) and B (8..15; uB < 0: none)
-                const uint32_t sA = t2::lds16(slot_u + uA * 16);
-                const uint32_t sB = uB >= 0 ? t2::lds16(slot_u + uB * 16) : 0xffffu;
-                const int s00 = (int)(int8_t)(sA & 0xffu), s10 = (int)(int8_t)(sA >> 8);
-                const int s01 = (int)(int8_t)(sB & 0xffu), s11 = (int)(int8_t)(sB >> 8);
-                uint32_t af[4] = {0u, 0u, 0u, 0u};
-                if (s00 >= 0) { const float2 p = lds_f2(Sa_u + (uint32_t)s00 * 32); af[0] = t2::pack_pair<T>(p.x, p.y); }
-                if (s10 >= 0) { const float2 p = lds_f2(Sb_u + (uint32_t)s10 * 32); af[1] = t2::pack_pair<T>(p.x, p.y); }
-                if (s01 >= 0) { const float2 p = lds_f2(Sa_u + (uint32_t)s01 * 32); af[2] = t2::pack_pair<T>(p.x, p.y); }
-                if (s11 >= 0) { const float2 p = lds_f2(Sb_u + (uint32_t)s11 * 32); af[3] = t2::pack_pair<T>(p.x, p.y); }
-                const uint32_t blk = stage + (uint32_t)(((lane >> 3) & 1) ? xB : xA) * G::BLK;
-                if constexpr (NT == 4) {
-#pragma unroll
-                    for (int n2 = 0; n2 < 2; ++n2) {
-                        uint32_t bf[4];
-                        t2::ldsm4t(bf, blk + v_off[n2]);
-                        t2::mma16<T>(acc[2 * n2], af[0], af[1], af[2], af[3], bf[0], bf[1]);
-                        t2::mma16<T>(acc[2 * n2 + 1], af[0], af[1], af[2], af[3], bf[2], bf[3]);
-                    }
-                } else {
-                    uint32_t bf[4];
-                    t2::ldsm4t(bf, blk + v_off[0]);
-                    t2::mma16<T>(acc[0], af[0], af[1], af[2], af[3], bf[0], bf[1]);
-                    t2::mma16<T>(acc[1], af[0], af[1], af[2], af[3], bf[2], bf[3]);
+            } else {
+                int pend_x = -1, pend_u = 0;
+                for (int u = 0; u < U; ++u) {
+                    const int x = (int)spos_s[u] - rbase;
+                    if ((unsigned)x >= (unsigned)cap) continue;
+                    wait_oct(x);
+                    if (pend_x < 0) { pend_x = x; pend_u = u; continue; }
+                    pv_pair16<T, C, PACKED>(acc, Sa_u, Sb_u, t2::lds16(slot_u + 2 * pend_u), t2::lds16(slot_u + 2 * u),
+                                            stage + (uint32_t)(((lane >> 3) & 1) ? x : pend_x) * G::BOX, v_off);
+                    pend_x = -1;
                 }
-            };
-            for (int u = 0; u < U; ++u) {
-                const int x = (int)spos_s[u] - rbase;
-                if ((unsigned)x >= (unsigned)cap) continue;
-                wait_oct(x);
-                if (pend_x < 0) { pend_x = x; pend_u = u; continue; }
-                pair(pend_u, pend_x, u, x);
-                pend_x = -1;
+                // odd count: the B half re-reads octet A with zero probabilities
+                if (pend_x >= 0) pv_pair16<T, C, PACKED>(acc, Sa_u, Sb_u, t2::lds16(slot_u + 2 * pend_u), 0xffffu, stage + (uint32_t)pend_x * G::BOX, v_off);
             }
-            if (pend_x >= 0) pair(pend_u, pend_x, -1, pend_x);     // odd count: the B half re-reads octet A with zero probabilities
         }
     }
     // ---- epilogue: + e_blank * blank_v, * 1/sum, token-major store -------------------------------------------------------------------
@@ -443,8 +554,8 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
         const float *Sa = S + g * MP, *Sb = S + (g + 8) * MP;
         const float inva = Sa[M + 1], invb = Sb[M + 1], eba = Sa[M], ebb = Sb[M];
         const T *bv = reinterpret_cast<const T *>(a.blank_v) + h * C;
-        T *Ob = reinterpret_cast<T *>(a.out) + b * a.o_sb + h * a.o_sh;
-        T *oa = Ob + (int64_t)ra * a.o_sn + 2 * t, *ob = Ob + (int64_t)rb * a.o_sn + 2 * t;
+        T *Ob = t2::opaque(reinterpret_cast<T *>(a.out) + b * a.o_sb + h * a.o_sh);
+        T *oa = t2::at(Ob, ra * (int)a.o_sn + 2 * t), *ob = t2::at(Ob, rb * (int)a.o_sn + 2 * t);
         const bool wa = ra < Nq && !((impm >> g) & 1u), wb = rb < Nq && !((impm >> (g + 8)) & 1u);
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
@@ -513,7 +624,7 @@ template <typename T, int C, bool PACKED, bool PB>
 static int launch_cfg(const CUtensorMap &mk, const CUtensorMap &mv, const FusedArgsPB &a, const void *pack, cudaStream_t st, bool *taken) {
     using G = Geo<T, C, PACKED>;
     auto kern = attn_fused_tma_kernel<T, C, PACKED, PB>;
-    const int warp_bytes = ((16 * (a.M + 4) * 4 + U_MAX * 16 + 64) + 15) & ~15;
+    const int warp_bytes = ((16 * (a.M + ZPAD + 4) * 4 + SLOT_G_TILE + 64) + 15) & ~15;
     const size_t fixed = 1024 + NBAR_MAX * 8 + (size_t)GW * warp_bytes;
     // staging capacity: the largest multiple of OCT_PER_BAR that still leaves `want` CTAs per SM, at least the typical union of a
     // 64-token group (~28 octets of 8 rows for M = 48, ~50 for M = 144); larger groups take a second round
@@ -524,12 +635,12 @@ static int launch_cfg(const CUtensorMap &mk, const CUtensorMap &mv, const FusedA
         cap = 0;
         for (int want = 4; want >= 1 && cap < typical; --want) {
             const int64_t room = (int64_t)(227 * 1024) / want - 1024 - (int64_t)fixed;
-            cap = (int)std::min<int64_t>(room / G::BLK, 128);
+            cap = (int)std::min<int64_t>(room / G::BOX, 128);
         }
         cap = std::min(cap, a.M <= 64 ? 40 : 72);
     }
     cap = std::max(OCT_PER_BAR, std::min(cap, OCT_PER_BAR * NBAR_MAX) / OCT_PER_BAR * OCT_PER_BAR);
-    const size_t smem = fixed + (size_t)cap * G::BLK;
+    const size_t smem = fixed + (size_t)cap * G::BOX;
     if (smem > 227 * 1024) return 0;
     static bool attr_done[64] = {};                        // (per instantiation and device)
     int dev = 0;
@@ -541,7 +652,7 @@ static int launch_cfg(const CUtensorMap &mk, const CUtensorMap &mv, const FusedA
     const PackView pk = pack_view(const_cast<void *>(pack), a.B, a.Nq, a.Nk);
     const GroupView gv = group_view(const_cast<void *>(pack), a.B, a.Nq, a.Nk);
     const dim3 grid(gv.TG, a.B * a.H);
-    const Launch L{cap, warp_bytes};
+    const Launch L{cap, warp_bytes, ((1 << 20) + a.M / 4 - 1) / (a.M / 4)};
     if constexpr (PB) kern<<<grid, GW * 32, smem, st>>>(mk, mv, a, pk, gv, L);
     else kern<<<grid, GW * 32, smem, st>>>(mk, mv, static_cast<const FusedArgs &>(a), pk, gv, L);
     note_launches(1);

@@ -6,7 +6,7 @@ namespace clusten {
 constexpr int PACK_WARPS = 4;
 
 __global__ void __launch_bounds__(PACK_WARPS * 32)
-pack_tile_kernel(const int64_t *__restrict__ idx, const uint8_t *__restrict__ mask, int B, int Nq, int M, int Nk, PackView pk) {
+pack_tile_kernel(const int64_t *__restrict__ idx, const uint8_t *__restrict__ mask, int B, int Nq, int M, int Nk, PackView pk, GroupView gv) {
     __shared__ int oct_rs[PACK_WARPS][TILE_TOK][S_MAX];
     __shared__ __align__(16) int8_t slot_s[PACK_WARPS][TILE_TOK][U_MAX];
     __shared__ int row_bad[PACK_WARPS][TILE_TOK];
@@ -129,6 +129,12 @@ pack_tile_kernel(const int64_t *__restrict__ idx, const uint8_t *__restrict__ ma
         for (int r = 0; r < TILE_TOK; ++r) w[r >> 2] |= (uint32_t)(uint8_t)slot_s[warp][r][u] << (8 * (r & 3));
         *reinterpret_cast<uint4 *>(pk.slot_t + ((int64_t)bt * U_MAX + u) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     }
+    // the same table in mma-fragment order (rows g and g + 8 of one union position side by side) for the TMA-staged kernels
+    for (int x = lane; x < 8 * U_MAX; x += 32) {
+        const int gr = x / U_MAX, u = x - gr * U_MAX;
+        const uint16_t v = (uint16_t)(uint8_t)slot_s[warp][gr][u] | (uint16_t)((uint16_t)(uint8_t)slot_s[warp][gr + 8][u] << 8);
+        *reinterpret_cast<uint16_t *>(gv.slot_g + (int64_t)bt * SLOT_G_TILE + gr * SLOT_G_ROW + 2 * u) = v;
+    }
     if (lane == 0) {
         pk.tile_u[bt] = Uc;
         atomicMax(pk.flags + 1, U);
@@ -174,6 +180,7 @@ pack_group_kernel(PackView pk, GroupView gv, int B) {
             }
             if (lane == 0) gv.sub_pos[bt * U_MAX + u] = (uint8_t)pos;
         }
+        for (int u = U + lane; u < U_MAX; u += 32) gv.sub_pos[bt * U_MAX + u] = 0;      // (positions beyond the union: a staged octet)
     }
 #pragma unroll
     for (int x = 0; x < PER_LANE; ++x) gv.grp_oct[(int64_t)bg * GU_MAX + 32 * x + lane] = (32 * x + lane < GU) ? mine[x] : 0;
@@ -244,9 +251,9 @@ extern "C" int clusten_pack_build(const int64_t *nbhd_idx, const uint8_t *mask, 
     }
     const int bt = B * pk.T;
     cudaMemsetAsync(pk.row_imp, 0, (size_t)B * Nk, st);
-    pack_tile_kernel<<<ceil_div(bt, PACK_WARPS), PACK_WARPS * 32, 0, st>>>(nbhd_idx, mask, B, Nq, M, Nk, pk);
-    pack_decide_kernel<<<1, 1, 0, st>>>(pk.flags, B * Nq);
     const GroupView gv = group_view(pack, B, Nq, Nk);
+    pack_tile_kernel<<<ceil_div(bt, PACK_WARPS), PACK_WARPS * 32, 0, st>>>(nbhd_idx, mask, B, Nq, M, Nk, pk, gv);
+    pack_decide_kernel<<<1, 1, 0, st>>>(pk.flags, B * Nq);
     pack_group_kernel<<<ceil_div(B * gv.TG, PACK_WARPS), PACK_WARPS * 32, 0, st>>>(pk, gv, B);
     note_launches(3);
     return check_launch("pack_build");

@@ -41,7 +41,7 @@ struct Rows4 { const void *p; int64_t sb, sh, sn; };   // strided [B,H,N,C] oper
 
 struct PackLayout {
     size_t flags, tile_u, tile_oct, slot_of, slot_t, oct_off, oct_ent, tok_imp, row_imp, imp_list, rimp_list, sort_ws,
-           grp_u, grp_oct, sub_pos, total;
+           grp_u, grp_oct, sub_pos, slot_g, total;
     int T, NO, imp_cap, rimp_cap, TG;
 };
 
@@ -50,11 +50,15 @@ struct PackLayout {
 // loads) and, per (tile, union position), the position of that octet in the group's list.
 constexpr int GROUP_TILES = 4;
 constexpr int GU_MAX = GROUP_TILES * U_MAX;     // a group's union can never exceed the sum of its tiles' unions
+constexpr int SLOT_G_ROW = 2 * U_MAX + 8;       // bytes of one row of slot_g (8 bytes of padding: 64-bit reads of 8 rows hit 16 different banks)
+constexpr int SLOT_G_TILE = 8 * SLOT_G_ROW;     // bytes of one tile's slot_g block (a multiple of 16)
 
 struct GroupView {
     int *grp_u;          // [B*TG]            octets in the group's union
     int *grp_oct;        // [B*TG*GU_MAX]     their ids, first-seen order over the group's tiles
-    uint8_t *sub_pos;    // [B*T*U_MAX]       position in the group's list of (tile, union position u)
+    uint8_t *sub_pos;    // [B*T*U_MAX]       position in the group's list of (tile, union position u); 0 beyond the tile's union
+    uint8_t *slot_g;     // [B*T][8][SLOT_G_ROW]  the slot table in mma-fragment order: row g, entry u (16 bits) = slot of token row g
+                         //                   in the low byte, of token row g + 8 in the high byte (0xff = none)
     int TG;              // groups per batch sample = ceil(T / GROUP_TILES);  flags[6] = largest group union
 };
 
@@ -85,6 +89,7 @@ inline PackLayout pack_layout(int B, int Nq, int Nk) {
     L.grp_u = o;    o += pack_align((size_t)B * L.TG * 4);
     L.grp_oct = o;  o += pack_align((size_t)B * L.TG * GU_MAX * 4);
     L.sub_pos = o;  o += pack_align(bt * U_MAX);
+    L.slot_g = o;   o += pack_align(bt * SLOT_G_TILE);
     L.total = o;
     return L;
 }
@@ -118,6 +123,7 @@ inline GroupView group_view(void *buf, int B, int Nq, int Nk) {
     g.grp_u = reinterpret_cast<int *>(p + L.grp_u);
     g.grp_oct = reinterpret_cast<int *>(p + L.grp_oct);
     g.sub_pos = reinterpret_cast<uint8_t *>(p + L.sub_pos);
+    g.slot_g = reinterpret_cast<uint8_t *>(p + L.slot_g);
     g.TG = L.TG;
     return g;
 }

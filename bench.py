@@ -147,6 +147,60 @@ def run_reference(args, wl, rank, world):
     })
 
 
+def contract_extras(dev, log):
+    """The second half of BASELINE.json's metric and the numbers SURVEY.md 8(d) asks for beside it, measured in the same process on
+    the same GPU after the timed regions (N = 1 only):
+
+      roofline_ops      the CLUSTEN ops (QK / AV / WF forward + backward, weighted gather) at AFF-Small stage 0 (B = 32, N = 16 384,
+                        M = 48; merge N' = 4096), bf16 and fp32, L2 flushed between iterations: ms, achieved GB/s, fraction of the
+                        measured HBM peak on the INTERFACE bytes (``frac``; the int64 index counted as delivered) and on the data
+                        operands + results alone (``frac_data``)
+      ref_cuda_kernels  the reference's OWN kernels (oracle/_ref, built unmodified from /root/reference for sm_100a; checker leg, like
+                        cpu_baseline) on the same fp32 inputs -- the "kernel to beat"
+      integer_path_us   clustering / kNN / stage preparation / merge selection / tile pack at N = 16 384 and 131 072
+      north_star_model  AFF-Small backbone forward, 512x512, batch 16, fp32 (the model north_star's scaling target names)"""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+    import int_bench
+    import op_bench
+    from oracle import ref_cuda
+    quiet = lambda *a, **k: None
+    ours, refk = {}, None
+    for dt in ("bf16", "f32"):
+        want_ref = dt == "f32" and ref_cuda.available()
+        rows = op_bench.bench_ops(op_bench.default_args(shape="small_s0", dtype=dt, iters=5, ref=want_ref), log=quiet)
+        keep = ("qk_fwd", "av_fwd", "qk_bwd", "av_bwd", "wf_fwd", "wf_bwd", "wg_fwd")
+        ours[dt] = {r["op"]: {k: r[k] for k in ("ms", "algo_MB", "GBs", "frac", "frac_data")} for r in rows if r["op"] in keep}
+        if want_ref:
+            refk = {r["op"][4:].split(" ")[0]: {"ms": r["ms"], "GBs": r["GBs"], "frac": r["frac"]} for r in rows if r["op"].startswith("REF ")}
+        torch.cuda.empty_cache()
+    out = {"roofline_ops": {"shape": "AFF-Small stage 0: B=32 H=3 N=16384 C=32 M=48, merge N'=4096 C=96 IC=4, WG K=4 C=256; L2 flushed",
+                            "peak": op_bench.peak_gbs()[0], **ours},
+           "ref_cuda_kernels": ({"kind": "reference (oracle/_ref, unmodified sources, sm_100a)", "dtype": "f32", **refk} if refk else None),
+           "integer_path_us": int_bench.integer_path_us(iters=5)}
+    torch.cuda.empty_cache()
+    # the north-star model on the same device: graph replay, inputs resident, CUDA events
+    from autofocusformermod_b200.aff import build_aff
+    torch.manual_seed(0)
+    wl = WORKLOADS["aff_small_fwd_b16_512"]
+    m = build_aff(wl["preset"]).to(dev).eval()
+    x = make_images(wl["batch"], wl["H"], wl["W"], seed=0).to(dev)
+    g = m.graphed(x)
+    for _ in range(3):
+        g(x)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        g(x)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    out["north_star_model"] = {"workload": "aff_small_fwd_b16_512", "images_per_s": round(wl["batch"] / ms * 1e3, 1), "ms_per_step": round(ms, 3),
+                               "dtype": "f32", "steps": 5, "execution": "CUDA graph replay, inputs resident in HBM"}
+    return out
+
+
 _REAL_STDOUT = None
 
 
@@ -178,6 +232,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip roofline_ops / ref_cuda_kernels / integer_path_us / north_star_model")
     ap.add_argument("--no-graph", action="store_true", help="inference workloads: eager forward instead of the CUDA-graph replay")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of the workload (diagnostics; the line says so)")
     args = ap.parse_args()
@@ -378,6 +433,12 @@ def main():
                 "share_of_step": round(dom_ms / ms, 4), "timing": roof_timing,
                 "per_entry_ms_per_step": {n: round(v[0], 4) for n, v in sorted(per.items())}}
 
+    extras = {}
+    if world == 1 and not args.no_extras and args.workload == DEFAULT_WORKLOAD:
+        del graphed, graphed_train, out
+        torch.cuda.empty_cache()
+        extras = contract_extras(dev, None)
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import aff_oracle as ao
@@ -413,6 +474,9 @@ def main():
                                  "CUDA graphs for forward and backward (graphed_training_forward), eager AdamW" if graphed_train is not None
                                  else "eager"),
                    "l2": f"no explicit flush: one step streams {peak_mem / 2**20:.0f} MiB of live activations (>> 126 MB L2)",
+                   "memoised": ("the position-only structures of the on-grid stage 0 (clustering, kNN, neighbourhoods, tile pack) are constants "
+                                "of the input shape and are built once, outside the timed region (the reference memoises its stage-0 "
+                                "clustering the same way in training, aff.py:461-467); their cost is in integer_path_us"),
                    # environment switches of the Python layer that differ from their defaults (README.md), so a line says what it ran
                    "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("CLUSTEN_")}},
         "e2e": {"value": round(total_images / e2e_max, 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -420,6 +484,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        **extras,
     }
     emit(line)
     if world > 1:

@@ -79,17 +79,13 @@ def time_fn(fn, iters, flush):
     return ts[len(ts) // 2]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--shape", default="small_s0")
-    ap.add_argument("--dtype", default="bf16")
-    ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--ref", action="store_true")
-    ap.add_argument("--random-idx", action="store_true")
-    ap.add_argument("--once", action="store_true", help="run every op exactly once (for ncu captures)")
-    ap.add_argument("--generic", action="store_true", help="row-gather kernels only (no tile pack)")
-    args = ap.parse_args()
+def bench_ops(args, log=print):
+    """Times every op of the shape; returns the rows (dicts: op, ms, algo_MB, GBs, frac = fraction of peak on the INTERFACE bytes,
+    frac_data = the same on the data operands and results alone, i.e. without the int64 index the tile-union kernels never read)."""
     from autofocusformermod_b200 import _lib, ops
+    if os.path.dirname(os.path.abspath(__file__)) not in sys.path:
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    print = log
     S = SHAPES[args.shape]
     B, H, N, C, M, m = S["B"], S["H"], S["N"], S["C"], S["M"], S["m"]
     dt = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}[args.dtype]
@@ -120,23 +116,24 @@ def main():
     BHNC, BHNM, BNM8 = B * H * N * C * s, B * H * N * M * s, B * N * M * 8
     rows = []
 
-    def run(name, fn, nbytes):
+    def run(name, fn, nbytes, idx_bytes=0):
         ms = time_fn(fn, 0 if args.once else args.iters, flush)
         gbs = nbytes / ms / 1e6
-        rows.append(dict(op=name, ms=round(ms, 4), algo_MB=round(nbytes / 1e6, 1), GBs=round(gbs, 1), frac=round(gbs / peak, 3)))
+        rows.append(dict(op=name, ms=round(ms, 4), algo_MB=round(nbytes / 1e6, 1), GBs=round(gbs, 1), frac=round(gbs / peak, 3),
+                         frac_data=round((nbytes - idx_bytes) / ms / 1e6 / peak, 3)))
         print(json.dumps(rows[-1]), flush=True)
 
     ck = lambda rc: _lib.check(rc, "bench")
     run("qk_fwd", lambda: ck(L.clusten_qk_fwd(q.data_ptr(), k.data_ptr(), idx.data_ptr(), pk, out_attn.data_ptr(), B, H, N, N, C, M,
-                                              *s3(q), *s3(k), code, st())), 2 * BHNC + BNM8 + BHNM)
+                                              *s3(q), *s3(k), code, st())), 2 * BHNC + BNM8 + BHNM, BNM8)
     run("av_fwd", lambda: ck(L.clusten_av_fwd(attn.data_ptr(), v.data_ptr(), idx.data_ptr(), pk, feat.data_ptr(), B, H, N, N, C, M,
-                                              *s3(attn), *s3(v), *s3(feat), code, st())), BHNM + 2 * BHNC + BNM8)
+                                              *s3(attn), *s3(v), *s3(feat), code, st())), BHNM + 2 * BHNC + BNM8, BNM8)
     run("qk_bwd", lambda: ck(L.clusten_qk_bwd(d_attn.data_ptr(), q.data_ptr(), k.data_ptr(), idx.data_ptr(), off.data_ptr(),
                                               ent.data_ptr(), pk, d_q.data_ptr(), d_k.data_ptr(), B, H, N, N, C, M,
-                                              *s3(q), *s3(k), *s3(d_q), *s3(d_k), code, st())), BHNM + 4 * BHNC + BNM8)
+                                              *s3(q), *s3(k), *s3(d_q), *s3(d_k), code, st())), BHNM + 4 * BHNC + BNM8, BNM8)
     run("av_bwd", lambda: ck(L.clusten_av_bwd(d_feat.data_ptr(), attn.data_ptr(), v.data_ptr(), idx.data_ptr(), off.data_ptr(),
                                               ent.data_ptr(), pk, out_attn.data_ptr(), d_v.data_ptr(), B, H, N, N, C, M,
-                                              *s3(d_feat), *s3(attn), *s3(v), *s3(d_v), code, st())), 3 * BHNC + 2 * BHNM + BNM8)
+                                              *s3(d_feat), *s3(attn), *s3(v), *s3(d_v), code, st())), 3 * BHNC + 2 * BHNM + BNM8, BNM8)
     pb = L.clusten_pack_bytes(B, N, M, N)
     pbuf = torch.empty(pb, dtype=torch.uint8, device="cuda")
     run("pack_build", lambda: ck(L.clusten_pack_build(idx.data_ptr(), 0, B, N, M, N, pbuf.data_ptr(), pb, st())), BNM8)
@@ -164,24 +161,59 @@ def main():
         run("wf_plan_build", lambda: ck(L.clusten_wf_plan_build(idx_w.data_ptr(), B, Nq, M, N, pbuf2.data_ptr(), plb, st())), B * Nq * M * 8)
     wb, fb, ib, ob = B * Nq * M * IC * s, B * N * Cw * s, B * Nq * M * 8, B * Nq * IC * Cw * s
     run("wf_fwd", lambda: ck(L.clusten_wf_fwd(w.data_ptr(), f.data_ptr(), idx_w.data_ptr(), pl, out_w.data_ptr(), B, Nq, N, Cw, M, IC,
-                                              f.stride(0), f.stride(1), code, st())), wb + fb + ib + ob)
+                                              f.stride(0), f.stride(1), code, st())), wb + fb + ib + ob, ib)
     if plan is not None:
         run("wf_fwd (no plan: top-k token order)", lambda: ck(L.clusten_wf_fwd(w.data_ptr(), f.data_ptr(), idx_w.data_ptr(), 0, out_w.data_ptr(), B, Nq, N, Cw, M, IC,
-                                                                       f.stride(0), f.stride(1), code, st())), wb + fb + ib + ob)
+                                                                       f.stride(0), f.stride(1), code, st())), wb + fb + ib + ob, ib)
     run("wf_bwd", lambda: ck(L.clusten_wf_bwd(d_out.data_ptr(), w.data_ptr(), f.data_ptr(), idx_w.data_ptr(), offw.data_ptr(),
                                               entw.data_ptr(), pl, d_w.data_ptr(), d_f.data_ptr(), B, Nq, N, Cw, M, IC,
                                               f.stride(0), f.stride(1), d_f.stride(0), d_f.stride(1), code, st())),
-        ob + wb + fb + ib + wb + fb)
+        ob + wb + fb + ib + wb + fb, ib)
+    # weighted gather at the FPN upsample of the pixel decoder (point_utils.py:103-114): every token of the stage pulls K = 4
+    # nearest tokens of the next stage (Nq_wf of them), channel dim 256
+    from autofocusformermod_b200 import point_utils as pu
+    from _inputs import grid_positions, random_positions
+    hh, ww = S["grid"]
+    if N == hh * ww:
+        Cg, K = 256, 4
+        qpos = grid_positions(1, hh, ww).cuda()
+        dpos = random_positions(1, Nq, hh, ww, seed=1).cuda()
+        idx_g = pu.knn_keops(qpos, dpos, K).expand(B, -1, -1).contiguous()
+        wg = torch.rand(B, N, K, device="cuda", generator=gen).to(dt)
+        fg = torch.randn(B, Nq, Cg, device="cuda", generator=gen).to(dt)
+        og = torch.empty(B, N, Cg, device="cuda", dtype=dt)
+        run("wg_fwd", lambda: ck(L.clusten_wg_fwd(idx_g.data_ptr(), wg.data_ptr(), fg.data_ptr(), og.data_ptr(), B, N, Nq, Cg, K,
+                                                  fg.stride(0), fg.stride(1), code, st())),
+            B * N * K * s + B * Nq * Cg * s + B * N * K * 8 + B * N * Cg * s, B * N * K * 8)
     if args.ref and dt != torch.bfloat16:
         from oracle import ref_cuda
         qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
-        run("REF qk_fwd (incl. its K transpose)", lambda: ref_cuda.qk_forward(qc, kc, idx), 2 * BHNC + BNM8 + BHNM)
-        run("REF av_fwd", lambda: ref_cuda.av_forward(attn, vc, idx), BHNM + 2 * BHNC + BNM8)
-        run("REF qk_bwd", lambda: ref_cuda.qk_backward(d_attn, qc, kc, idx), BHNM + 4 * BHNC + BNM8)
-        run("REF av_bwd", lambda: ref_cuda.av_backward(d_feat.contiguous(), attn, vc, idx), 3 * BHNC + 2 * BHNM + BNM8)
+        run("REF qk_fwd (incl. its K transpose)", lambda: ref_cuda.qk_forward(qc, kc, idx), 2 * BHNC + BNM8 + BHNM, BNM8)
+        run("REF av_fwd", lambda: ref_cuda.av_forward(attn, vc, idx), BHNM + 2 * BHNC + BNM8, BNM8)
+        run("REF qk_bwd", lambda: ref_cuda.qk_backward(d_attn, qc, kc, idx), BHNM + 4 * BHNC + BNM8, BNM8)
+        run("REF av_bwd", lambda: ref_cuda.av_backward(d_feat.contiguous(), attn, vc, idx), 3 * BHNC + 2 * BHNM + BNM8, BNM8)
         run("REF wf_fwd", lambda: ref_cuda.wf_forward(w, f, idx_w), wb + fb + ib + ob)
         run("REF wf_bwd", lambda: ref_cuda.wf_backward(d_out, w, f, idx_w), ob + wb + fb + ib + wb + fb)
     print(json.dumps(dict(shape=args.shape, dtype=args.dtype, peak_gbs=peak, peak_source=psrc, idx="random" if args.random_idx else "reference pipeline (clustered)")))
+    return rows
+
+
+def default_args(**kw):
+    a = argparse.Namespace(shape="small_s0", dtype="bf16", iters=10, ref=False, random_idx=False, once=False, generic=False)
+    a.__dict__.update(kw)
+    return a
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="small_s0")
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--ref", action="store_true")
+    ap.add_argument("--random-idx", action="store_true")
+    ap.add_argument("--once", action="store_true", help="run every op exactly once (for ncu captures)")
+    ap.add_argument("--generic", action="store_true", help="row-gather kernels only (no tile pack)")
+    bench_ops(ap.parse_args())
 
 
 if __name__ == "__main__":

@@ -35,7 +35,7 @@ def test_parameter_names_match_reference():
 def test_forward_matches_reference_class_golden(name, preset, B, H, Wd):
     """The BASELINE presets at bench-scale token counts against outputs of the reference's own AFF class (oracle/make_golden.py):
     Mini 512^2 (configs[1]), Tiny-1/5 512^2 (ds 0.2: padded clusters, masks, 30 blocks), Base 256x512 (m = 24, M = 144).
-    Positions (clustering + every top-k selection) bit-exact; features to 1e-4 (fp32 through up to 30 blocks)."""
+    Positions (clustering + every top-k selection) bit-exact; features to 1e-5 (measured <= 3e-6 through up to 30 blocks)."""
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     cfg = ao.PRESETS[preset]
     m = _model(preset, ao.synthetic_state(cfg)).eval()
@@ -50,7 +50,7 @@ def test_forward_matches_reference_class_golden(name, preset, B, H, Wd):
         assert abs(float(out[f"res{i}"].double().sum()) - float(g[f"res{i}_sum"])) <= 1e-4 * float(g[f"res{i}_abs"])
         assert out[f"res{i}_spatial_shape"] == (H // 4, Wd // 4)
     print(name, {k: f"{v:.2e}" for k, v in errs.items()})
-    assert max(errs.values()) <= 1e-4, errs
+    assert max(errs.values()) <= 1e-5, errs
 
 
 @pytest.mark.parametrize("H,W", [(128, 192), (100, 134)])
@@ -96,9 +96,9 @@ def test_training_mode_caches_stage0_clustering():
     m = _model("test", ao.synthetic_state(ao.PRESETS["test"])).train()
     x = ao.synthetic_images(2, 128, 128).cuda()
     m(x)
-    cache = m.layers[0]._grid_cache
+    (entry,) = m.layers[0]._grid_cache.values()
     m(x)
-    assert m.layers[0]._grid_cache is cache
+    assert len(m.layers[0]._grid_cache) == 1 and next(iter(m.layers[0]._grid_cache.values())) is entry
 
 
 def test_fused_inference_path_matches_unfused_ops():
@@ -117,6 +117,33 @@ def test_fused_inference_path_matches_unfused_ops():
     for i in range(2, 6):
         assert torch.equal(fused[f"res{i}_pos"], plain[f"res{i}_pos"])
         assert rel_err(fused[f"res{i}"], plain[f"res{i}"]) <= 2e-5, f"res{i}"
+
+
+def test_graph_replay_survives_other_shapes():
+    """A CUDA graph holds raw addresses of the memoised on-grid structures (BasicLayer._grid_cache).  Forwards at other shapes
+    push the captured shape out of the cache; the graph pins what it captured, so a later replay still reads live memory."""
+    from autofocusformermod_b200 import aff as A
+    from autofocusformermod_b200.aff import build_aff
+    torch.manual_seed(0)
+    model = build_aff("test").cuda().eval()
+    g = torch.Generator().manual_seed(2)
+    xa = torch.randn(2, 3, 256, 256, generator=g).cuda()
+    graphed = model.graphed(xa)
+    with torch.no_grad():
+        ref = {k: v.clone() for k, v in model(xa).items() if torch.is_tensor(v)}
+        for i in range(A.GRID_CACHE_SHAPES + 1):                          # more shapes than the cache keeps
+            model(torch.randn(1 + i % 2, 3, 256 + 32 * (i + 1), 256, generator=g).cuda())
+    assert all(len(layer._grid_cache) <= A.GRID_CACHE_SHAPES for layer in model.layers)
+    assert (2, 64 * 64, 64, 64, 8, 6, xa.device) not in model.layers[0]._grid_cache          # the captured shape was evicted
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    junk = [torch.full((1 << 22,), float("nan"), device="cuda") for _ in range(8)]               # recycle whatever was freed
+    out = graphed(xa)
+    torch.cuda.synchronize()
+    for k, v in ref.items():
+        assert torch.equal(out[k], v), k
+    del junk
 
 
 def test_graphed_forward_equals_eager():

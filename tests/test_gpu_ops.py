@@ -447,7 +447,7 @@ def test_fused_attention_core(n, m, nbhd, kind, H, C, dtype):
     out, probs = ops.cluster_attention_fused(q.cuda().to(dtype), k.cuda().to(dtype), v.cuda().to(dtype), idx.cuda(), bias_tab.cuda(),
                                              bias_idx.cuda(), None if mask is None else mask.to(torch.uint8).cuda(),
                                              blank_k.cuda().to(dtype), blank_v.cuda().to(dtype), need_probs=True)
-    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
     assert rel_err(out.float(), ref_out) <= tol
     assert rel_err(probs, ref_p) <= tol
     if kind == "clustered":
