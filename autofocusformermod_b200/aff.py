@@ -584,6 +584,62 @@ def grid_pins(model):
     return [list(layer._grid_cache.values()) for layer in model.layers]
 
 
+@contextlib.contextmanager
+def _thread_local_capture_under_dist():
+    """Under torch.distributed the NCCL watchdog thread polls CUDA events while this thread captures; in the default (global) capture
+    mode its calls invalidate the capture.  torch.cuda.make_graphed_callables has no knob for the mode, so ``torch.cuda.graph`` is
+    swapped for a subclass that defaults to thread-local capture while it runs."""
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        yield
+        return
+    orig = torch.cuda.graph
+
+    class _ThreadLocalGraph(orig):
+        def __init__(self, *args, **kwargs):
+            kwargs.setdefault("capture_error_mode", "thread_local")
+            super().__init__(*args, **kwargs)
+
+    torch.cuda.graph = _ThreadLocalGraph
+    try:
+        yield
+    finally:
+        torch.cuda.graph = orig
+
+
+class FlatGradAllReduce:
+    """Gradient all-reduce for data-parallel training with CUDA graphs, one process per GPU (the only parallelism the reference has:
+    detectron2's DDP wrap behind train_net.py:423-430).  DistributedDataParallel hooks every parameter's AccumulateGrad node and
+    cannot ride a captured backward; here the backward graph replays as on one GPU, then every gradient is copied into ONE flat
+    fp32 buffer (a single multi-tensor kernel), the buffer is all-reduced with one NCCL call over NVLink / NVSwitch and averaged, and
+    ``param.grad`` is pointed at its slice (no copy back).  Call it between ``loss.backward()`` and ``optimizer.step()``.
+    Like DDP it averages gradients only; the stem's BatchNorm statistics stay per GPU (aff.py:529 uses plain BatchNorm2d)."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.world = torch.distributed.get_world_size(group)
+        dev = self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        self.views, o = [], 0
+        for p in self.params:
+            self.views.append(self.flat[o:o + p.numel()].view_as(p))
+            o += p.numel()
+        self.nbytes = self.flat.numel() * 4
+
+    def __call__(self):
+        have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+        if len(have) != len(self.params):
+            for v, p in zip(self.views, self.params):
+                if p.grad is None:
+                    v.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        torch.distributed.all_reduce(self.flat, group=self.group)
+        self.flat.mul_(1.0 / self.world)
+        for v, p in zip(self.views, self.params):
+            p.grad = v
+
+
 class _Features(nn.Module):
     """The backbone's feature tensors as a tuple (res2, res3, ...): what torch.cuda.make_graphed_callables can carry."""
 
@@ -605,8 +661,8 @@ def graphed_training_forward(model, example, autocast_dtype=None, num_warmup_ite
     if not model.training:
         raise RuntimeError("graphed_training_forward captures the training step: call model.train() first")
     wrapped = _Features(model)
-    with _quiet_capture(example.device), torch.autocast("cuda", dtype=autocast_dtype or torch.bfloat16,
-                                                        enabled=autocast_dtype is not None, cache_enabled=False):
+    with _quiet_capture(example.device), _thread_local_capture_under_dist(), torch.autocast(
+            "cuda", dtype=autocast_dtype or torch.bfloat16, enabled=autocast_dtype is not None, cache_enabled=False):
         f = torch.cuda.make_graphed_callables(wrapped, (example.detach().clone(),), num_warmup_iters=num_warmup_iters)
     f.grid_pins = grid_pins(model)       # the graphs hold raw addresses of the memoised stage structures: keep them alive
     return f

@@ -245,6 +245,7 @@ attn_fused_tile_kernel(const FArgsOf<PB> a, const PackView pk, int smem_per_warp
     }
     __syncwarp();
     // ---- phase 2: + bias + mask, softmax over M + 1 logits; two lanes per token row, e_j stay unnormalised in S ---------------
+    bool saw_mask = false;
     {
         const int row = lane >> 1, half = lane & 1;
         const int i = i0 + row;
@@ -257,19 +258,36 @@ attn_fused_tile_kernel(const FArgsOf<PB> a, const PackView pk, int smem_per_warp
             const uint8_t *mk = a.mask ? a.mask + ((int64_t)b * Nq + i) * M : nullptr;
             for (int j = j0; j < j1; j += 4) {                       // M % 8 == 0 -> Mh % 4 == 0, 16-byte aligned rows
                 float4 x = *reinterpret_cast<float4 *>(Sr + j);
+                float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
                 if constexpr (!PB) {                                 // (PB: the bias went in with the logits in phase 1)
                     const int4 bv = __ldg(reinterpret_cast<const int4 *>(bi + j));
-                    x.x += __ldg(a.bias_tab + bv.x * H + h);
-                    x.y += __ldg(a.bias_tab + bv.y * H + h);
-                    x.z += __ldg(a.bias_tab + bv.z * H + h);
-                    x.w += __ldg(a.bias_tab + bv.w * H + h);
+                    g0 = __ldg(a.bias_tab + bv.x * H + h); g1 = __ldg(a.bias_tab + bv.y * H + h);
+                    g2 = __ldg(a.bias_tab + bv.z * H + h); g3 = __ldg(a.bias_tab + bv.w * H + h);
+                    x.x += g0; x.y += g1; x.z += g2; x.w += g3;
                 }
                 if (mk) {
                     const uchar4 m4 = *reinterpret_cast<const uchar4 *>(mk + j);
-                    if (!m4.x) x.x += -100.f;
-                    if (!m4.y) x.y += -100.f;
-                    if (!m4.z) x.z += -100.f;
-                    if (!m4.w) x.w += -100.f;
+                    if (!(m4.x && m4.y && m4.z && m4.w)) {
+                        // a masked neighbour is a wildcard of the mask-aware pack (its column was scored against whatever row the octet
+                        // holds there); the reference scores it against row idx[b,i,j] and subtracts 100 (aff.py:137), which large logits
+                        // do not turn into nothing: exact logit here, exact value row before phase 3
+                        saw_mask = true;
+                        const int64_t *ir = a.idx + ((int64_t)b * Nq + i) * M + j;
+                        auto fix = [&](int64_t kidx, float gtab) {
+                            kidx = min(max(kidx, (int64_t)0), (int64_t)a.Nk - 1);
+                            const T *qr = reinterpret_cast<const T *>(a.q) + b * a.q_sb + h * a.q_sh + (int64_t)i * a.q_sn;
+                            const T *kr = reinterpret_cast<const T *>(a.k) + b * a.k_sb + h * a.k_sh + kidx * a.k_sn;
+                            float sdot = 0.f;
+                            for (int c = 0; c < C; ++c) sdot = fmaf(to_f(qr[c]), to_f(kr[c]), sdot);
+                            if constexpr (PB) gtab = pos_bias(pos_bias_load(a.pe_w, a.pe_b, h), __ldg(reinterpret_cast<const float2 *>(a.pos_q) + (int64_t)b * Nq + i),
+                                                              __ldg(reinterpret_cast<const float2 *>(a.pos_k) + (int64_t)b * a.Nk + kidx));
+                            return sdot + gtab - 100.f;
+                        };
+                        if (!m4.x) x.x = fix(ir[0], g0);
+                        if (!m4.y) x.y = fix(ir[1], g1);
+                        if (!m4.z) x.z = fix(ir[2], g2);
+                        if (!m4.w) x.w = fix(ir[3], g3);
+                    }
                 }
                 *reinterpret_cast<float4 *>(Sr + j) = x;
                 mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
@@ -301,6 +319,37 @@ attn_fused_tile_kernel(const FArgsOf<PB> a, const PackView pk, int smem_per_warp
     for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
     const T *vbase = V;
     const float *Sa = S + g * MP, *Sb = S + (g + 8) * MP;
+    if (__any_sync(FULL, saw_mask)) {
+        // masked entries: e_j leaves S (its octet column must not pull in the wildcard row) and enters the accumulators with the row the
+        // reference reads, v[idx[b,i,j]]; the lanes that own the token's row in the mma layout take it
+        const int cnt = min(TILE_TOK, Nq - i0) * M;
+        const uint8_t *mkt = a.mask + ((int64_t)b * Nq + i0) * M;
+        for (int x0 = 0; x0 < cnt; x0 += 32) {
+            unsigned bal = __ballot_sync(FULL, x0 + lane < cnt && !mkt[x0 + lane]);
+            while (bal) {
+                const int x = x0 + __ffs(bal) - 1;
+                bal &= bal - 1;
+                const int row = x / M, j = x - row * M;
+                if ((impm >> row) & 1u) continue;
+                const float e = S[row * MP + j];
+                __syncwarp();
+                if (lane == 0) S[row * MP + j] = 0.f;
+                const int64_t kidx = a.idx[((int64_t)b * Nq + i0 + row) * M + j];
+                const T *vr = reinterpret_cast<const T *>(a.v) + b * a.v_sb + h * a.v_sh + min(max(kidx, (int64_t)0), (int64_t)a.Nk - 1) * a.v_sn + 2 * t;
+                if (g == (row & 7)) {
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        if (8 * n + 2 * t < C) {
+                            const float v0 = e * to_f(vr[8 * n]), v1 = e * to_f(vr[8 * n + 1]);
+                            if (row < 8) { acc[n][0] += v0; acc[n][1] += v1; }
+                            else { acc[n][2] += v0; acc[n][3] += v1; }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
     if constexpr (!F32) {
         constexpr int ROWB = NT * 16 + 16, CPL = NT / 2;
         auto stage = [&](int p, int which) {

@@ -176,7 +176,7 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                       const PackView pk, const GroupView gv, const Launch L) {
     using G = Geo<T, C, PACKED>;
     extern __shared__ unsigned char dyn_raw[];
-    if (pk.flags[0]) return;                               // the pack routes this tensor to the generic kernels
+    const int generic_flag = pk.flags[0];                  // != 0: the pack routes this tensor to the generic kernels (checked below)
     constexpr bool F32 = sizeof(T) == 4;
     constexpr int KS = F32 ? C / 8 : C / 16;               // mma k-steps of the dot phase
     constexpr int NT = C / 8;                              // 8-channel n-tiles of the output
@@ -201,15 +201,22 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
     unsigned char *slot_s = wmem + (size_t)16 * MP * 4;                          // [8][SLOT_G_ROW]: slot16 of (row g | row g+8, union entry u)
     unsigned char *spos_s = slot_s + SLOT_G_TILE;                                // [U_MAX]: group position of union entry u
     const int nbar = cap / OCT_PER_BAR;
+    // (independent global reads first, so that their latencies overlap: group size, the first round's octet ids, tile context)
+    const int GU = gv.grp_u[bg];
+    const int *goct = gv.grp_oct + (int64_t)bg * GU_MAX;
+    int oct_first[4];                                      // warp 0: octets lane, lane+32, .. of the first load round (list is zero-padded)
+#pragma unroll
+    for (int x = 0; x < 4; ++x) oct_first[x] = (warp == 0 && lane + 32 * x < min(cap, GU_MAX)) ? __ldg(goct + lane + 32 * x) : 0;
+    const int U_ld = pk.tile_u[bt];
+    const uint4 imp_ld = __ldg(reinterpret_cast<const uint4 *>(pk.tok_imp + (int64_t)bt * TILE_TOK));
+    if (generic_flag) return;
     if (threadIdx.x == 0) {
         for (int k = 0; k < nbar; ++k) mbar_init(bars + 8 * k, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    const int GU = gv.grp_u[bg];
     const int rounds = (GU + cap - 1) / cap;
-    const int *goct = gv.grp_oct + (int64_t)bg * GU_MAX;
     // one load round: octets [r*cap, r*cap + n) of the group's list -> staging positions 0..n-1 (warp 0; every barrier gets exactly
     // one arrival per round, so its parity is the load counter's)
     auto issue_round = [&](int r, const CUtensorMap *map) {
@@ -223,14 +230,46 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
         for (int x = lane; x < n; x += 32)
             tma_box_4d(stage + (uint32_t)x * G::BOX, map, bars + 8 * (x / OCT_PER_BAR), 0, __ldg(goct + p0 + x) * 8, h, b);
     };
-    if (warp == 0) issue_round(0, &mapK);
+    if (warp == 0) {                                       // first round of K (or K|V) boxes, octet ids already in registers
+        const int n = min(GU, cap);
+        if (lane < nbar) {
+            const int cnt = min(max(n - lane * OCT_PER_BAR, 0), OCT_PER_BAR);
+            if (cnt > 0) mbar_expect_tx(bars + 8 * lane, (uint32_t)cnt * G::BOX);
+            else mbar_arrive(bars + 8 * lane);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+            if (lane + 32 * x < n) tma_box_4d(stage + (uint32_t)(lane + 32 * x) * G::BOX, &mapK, bars + 8 * ((lane + 32 * x) / OCT_PER_BAR), 0, oct_first[x] * 8, h, b);
+    }
 
     // ---- per-warp tile context -------------------------------------------------------------------------------------------------
-    const int U = active ? pk.tile_u[bt] : 0;
+    const int U = active ? U_ld : 0;
     const int ra = i0 + g, rb = ra + 8;
     uint32_t impm = 0;
+    // phase 2a's operands (bias indices -> bias values, mask bytes) of the first PF quads per lane: fetched now, used after phase 1
+    constexpr int PF = PB ? 0 : 6;
+    const int nquad = active ? min(TILE_TOK, Nq - i0) * (M >> 2) : 0;
+    float4 bias_pf[PF > 0 ? PF : 1];
+    uint32_t mask_pf[PF > 0 ? PF : 1];
+    if constexpr (PF > 0) {
+        const int4 *bi = reinterpret_cast<const int4 *>(a.bias_idx + ((int64_t)b * Nq + i0) * M);
+        const uint32_t *mk4 = a.mask ? reinterpret_cast<const uint32_t *>(a.mask + ((int64_t)b * Nq + i0) * M) : nullptr;
+        const float *tabh = t2::opaque(a.bias_tab + h);
+        int4 bv[PF];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int e = lane + 32 * k;
+            bv[k] = e < nquad ? __ldg(bi + e) : make_int4(0, 0, 0, 0);
+            mask_pf[k] = (mk4 && e < nquad) ? __ldg(mk4 + e) : 0x01010101u;
+        }
+#pragma unroll
+        for (int k = 0; k < PF; ++k)
+            bias_pf[k] = make_float4(__ldg(t2::at(tabh, bv[k].x * H)), __ldg(t2::at(tabh, bv[k].y * H)), __ldg(t2::at(tabh, bv[k].z * H)),
+                                     __ldg(t2::at(tabh, bv[k].w * H)));
+    }
     if (active) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(pk.tok_imp + (int64_t)bt * TILE_TOK));
+        const uint4 v = imp_ld;
         if (v.x | v.y | v.z | v.w) {
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -382,25 +421,28 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
         if constexpr (!PB) {
             const int4 *bi = reinterpret_cast<const int4 *>(a.bias_idx + ((int64_t)b * Nq + i0) * M);
             const float *tabh = t2::opaque(a.bias_tab + h);
-            for (int e = lane; e < rows * QM; e += 32) {
+            auto apply = [&](int e, float4 gq, uint32_t m4) {
                 const int row = (e * L.rcp_qm) >> 20, j = (e - row * QM) * 4;
-                const int4 bv = __ldg(bi + e);
-                const float g0 = __ldg(t2::at(tabh, bv.x * H)), g1 = __ldg(t2::at(tabh, bv.y * H));
-                const float g2 = __ldg(t2::at(tabh, bv.z * H)), g3 = __ldg(t2::at(tabh, bv.w * H));
                 float4 x = *reinterpret_cast<float4 *>(S + row * MP + j);
-                x.x += g0; x.y += g1; x.z += g2; x.w += g3;
-                if (mk) {
-                    const uchar4 m4 = __ldg(reinterpret_cast<const uchar4 *>(mk) + e);
-                    if (!(m4.x && m4.y && m4.z && m4.w)) {
-                        saw_mask = true;
-                        const int64_t *ir = a.idx + ((int64_t)b * Nq + i0 + row) * M + j;
-                        if (!m4.x) x.x = masked_logit(row, ir[0]) + g0;
-                        if (!m4.y) x.y = masked_logit(row, ir[1]) + g1;
-                        if (!m4.z) x.z = masked_logit(row, ir[2]) + g2;
-                        if (!m4.w) x.w = masked_logit(row, ir[3]) + g3;
-                    }
+                x.x += gq.x; x.y += gq.y; x.z += gq.z; x.w += gq.w;
+                if (m4 != 0x01010101u && ((m4 & 0xffu) == 0 || (m4 & 0xff00u) == 0 || (m4 & 0xff0000u) == 0 || (m4 >> 24) == 0)) {
+                    saw_mask = true;
+                    const int64_t *ir = a.idx + ((int64_t)b * Nq + i0 + row) * M + j;
+                    if (!(m4 & 0xffu)) x.x = masked_logit(row, ir[0]) + gq.x;
+                    if (!(m4 & 0xff00u)) x.y = masked_logit(row, ir[1]) + gq.y;
+                    if (!(m4 & 0xff0000u)) x.z = masked_logit(row, ir[2]) + gq.z;
+                    if (!(m4 >> 24)) x.w = masked_logit(row, ir[3]) + gq.w;
                 }
                 *reinterpret_cast<float4 *>(S + row * MP + j) = x;
+            };
+#pragma unroll
+            for (int k = 0; k < PF; ++k)
+                if (lane + 32 * k < nquad) apply(lane + 32 * k, bias_pf[k], mask_pf[k]);
+            for (int e = lane + 32 * PF; e < nquad; e += 32) {           // (M > 48: the quads beyond the prefetched ones)
+                const int4 bv = __ldg(bi + e);
+                const float4 gq = make_float4(__ldg(t2::at(tabh, bv.x * H)), __ldg(t2::at(tabh, bv.y * H)), __ldg(t2::at(tabh, bv.z * H)),
+                                              __ldg(t2::at(tabh, bv.w * H)));
+                apply(e, gq, mk ? __ldg(reinterpret_cast<const uint32_t *>(mk) + e) : 0x01010101u);
             }
         } else {
             const PosBiasW pw = pos_bias_load(a.pe_w, a.pe_b, h);

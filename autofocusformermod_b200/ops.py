@@ -225,7 +225,7 @@ def pack_flags(nbhd_idx, Nk, mask=None):
     pack = neighbourhood_pack(nbhd_idx, Nk, mask=mask)
     if pack is None:
         return (1, 0, 0, 0)
-    return tuple(int(x) for x in pack[:16].view(torch.int32).tolist())
+    return tuple(int(x) for x in pack[:28].view(torch.int32).tolist())
 
 
 def _s3(t):

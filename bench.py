@@ -270,9 +270,15 @@ def main():
     amp = wl["dtype"] == "bf16"
     opt = None
     net = model
+    sync_grads = None
     if train:
-        if world > 1:
+        if world > 1 and args.no_graph:
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
+        elif world > 1:
+            # CUDA-graph training under data parallelism: same initial weights on every rank (torch.manual_seed(0) above), the backward
+            # graph replays as on one GPU, then ONE flat NCCL all-reduce of the gradients (aff.FlatGradAllReduce)
+            from autofocusformermod_b200.aff import FlatGradAllReduce
+            sync_grads = FlatGradAllReduce(model.parameters())
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
 
     B = wl["batch"]
@@ -285,7 +291,7 @@ def main():
         graphed = model.graphed(x_dev, autocast_dtype=torch.bfloat16 if amp else None)
 
     graphed_train = None
-    if train and world == 1 and not args.no_graph:
+    if train and not args.no_graph:
         from autofocusformermod_b200.aff import graphed_training_forward
         graphed_train = graphed_training_forward(model, x_dev, autocast_dtype=torch.bfloat16 if amp else None)
 
@@ -296,6 +302,8 @@ def main():
                 loss = sum(out[f"res{i}"].float().mean() for i in range(2, 6))
             opt.zero_grad(set_to_none=True)
             loss.backward()
+            if sync_grads is not None:
+                sync_grads()
             opt.step()
             return {"loss": loss.detach()}
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
@@ -310,6 +318,8 @@ def main():
                 loss = sum(f.float().mean() for f in feats)
             opt.zero_grad(set_to_none=True)
             loss.backward()
+            if sync_grads is not None:
+                sync_grads()
             opt.step()
             return {"loss": loss.detach()}
         return eager_step(x)
@@ -471,7 +481,9 @@ def main():
                    "image": [wl["H"], wl["W"]], "parallelism": f"dp{world} (batch-sharded, no data-path collective"
                    + (", NCCL gradient all-reduce)" if train and world > 1 else ")"),
                    "execution": ("CUDA graph replay (AFF.graphed)" if graphed is not None else
-                                 "CUDA graphs for forward and backward (graphed_training_forward), eager AdamW" if graphed_train is not None
+                                 ("CUDA graphs for forward and backward (graphed_training_forward), eager AdamW"
+                                  + (f", one flat NCCL all-reduce of {sync_grads.nbytes / 2**20:.0f} MiB of fp32 gradients per step" if sync_grads is not None else ""))
+                                 if graphed_train is not None
                                  else "eager"),
                    "l2": f"no explicit flush: one step streams {peak_mem / 2**20:.0f} MiB of live activations (>> 126 MB L2)",
                    "memoised": ("the position-only structures of the on-grid stage 0 (clustering, kNN, neighbourhoods, tile pack) are constants "

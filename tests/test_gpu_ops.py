@@ -366,7 +366,7 @@ def test_tile_path_is_taken_for_clustered_idx_and_refused_for_random_idx():
     kernels (flag 0, union <= U_MAX, no impure slot); a random index tensor falls back to the generic kernels."""
     from autofocusformermod_b200 import ops
     c = inputs.qkv_case(B=2, H=2, N=4096, C=32, M=48, seed=0, structured=True)
-    generic, max_u, impure, over = ops.pack_flags(c["idx"].cuda(), 4096)
+    generic, max_u, impure, over = ops.pack_flags(c["idx"].cuda(), 4096)[:4]
     assert generic == 0 and impure == 0 and over == 0 and 6 <= max_u <= 48
     r = inputs.random_neighbourhood(2, 512, 512, 48, seed=1).cuda()
     assert ops.pack_flags(r, 512)[0] == 1
