@@ -53,6 +53,8 @@ SIGNATURES = {
     "clusten_wf_bwd": (_I, [_P] * 9 + [_I] * 6 + [_L] * 4 + [_I, _P]),
     "clusten_wg_fwd": (_I, [_P] * 4 + [_I] * 5 + [_L] * 2 + [_I, _P]),
     "clusten_wg_bwd": (_I, [_P] * 8 + [_I] * 5 + [_L] * 4 + [_I, _P]),
+    "clusten_msdetrpc_fwd": (_I, [_P] * 5 + [_I] * 6 + [_L] * 2 + [_I, _P]),
+    "clusten_msdetrpc_bwd": (_I, [_P] * 10 + [_I] * 6 + [_L] * 4 + [_I, _P]),
     "clusten_knn": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "clusten_sfc_workspace_bytes": (_Z, [_I, _I]),
     "clusten_sfc_cluster": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),

@@ -66,6 +66,13 @@ __device__ __forceinline__ float2 lds_f2(uint32_t s) {
     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(s));
     return v;
 }
+// x = hi + lo with hi = x truncated to tf32 (one LOP3) and lo = x - hi (exact, one FADD); the tensor cores read the upper 19 bits of
+// lo.  Two instructions instead of the seven `cvt.rna.tf32.f32` costs twice over (sm_100 emulates the rounding: FSETP, SEL, LOP3,
+// VIADD ...); hi + lo carries 21 mantissa bits, the dropped lo x lo products are below 2^-20.
+__device__ __forceinline__ void split3(uint32_t x, uint32_t &hi, uint32_t &lo) {
+    hi = x & 0xffffe000u;
+    lo = __float_as_uint(__uint_as_float(x) - __uint_as_float(hi));
+}
 __device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t b0h, uint32_t b1h,
                                      uint32_t b0l, uint32_t b1l) {
     t2::mma_tf32(d, al[0], al[1], al[2], al[3], b0h, b1h);
@@ -108,6 +115,12 @@ __device__ __forceinline__ void sts_f2_if(uint32_t s, float a, float b, int slot
 }
 __device__ __forceinline__ int s8(uint32_t w, int byte) { return (int)(int8_t)(w >> (8 * byte)); }
 
+template <typename T> __device__ __noinline__ float row_dot(const T *x, const T *y, int C) {      // (rare path: masked neighbours)
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(to_f(x[c]), to_f(y[c]), s);
+    return s;
+}
+
 // 16 x 8 logits of the warp's tokens against one staged K octet
 template <typename T, int C, bool PACKED>
 __device__ __forceinline__ void qk_octet(float (&acc)[4], const uint32_t (&qa)[sizeof(T) == 4 ? C / 8 : C / 16][4],
@@ -118,8 +131,8 @@ __device__ __forceinline__ void qk_octet(float (&acc)[4], const uint32_t (&qa)[s
 #pragma unroll
         for (int s = 0; s < C / 8; ++s) {
             uint32_t b0h, b0l, b1h, b1l;
-            t2::split_tf32(lds32(blk + k_off[2 * s]), b0h, b0l);
-            t2::split_tf32(lds32(blk + k_off[2 * s + 1]), b1h, b1l);
+            split3(lds32(blk + k_off[2 * s]), b0h, b0l);
+            split3(lds32(blk + k_off[2 * s + 1]), b1h, b1l);
             mma3(acc, qa[s], ql[s], b0h, b1h, b0l, b1l);
         }
     } else if constexpr (C == 32) {
@@ -157,15 +170,15 @@ template <int C>
 __device__ __forceinline__ void pv_octet32(float (&acc)[C / 8][4], uint32_t Sa_u, uint32_t Sb_u, uint32_t s16, uint32_t blk, const uint32_t *v_off) {
     const float2 p0 = lds_f2(Sa_u + s8(s16, 0) * 32), p1 = lds_f2(Sb_u + s8(s16, 1) * 32);
     uint32_t ah[4], al[4];
-    t2::split_tf32(__float_as_uint(p0.x), ah[0], al[0]);
-    t2::split_tf32(__float_as_uint(p1.x), ah[1], al[1]);
-    t2::split_tf32(__float_as_uint(p0.y), ah[2], al[2]);
-    t2::split_tf32(__float_as_uint(p1.y), ah[3], al[3]);
+    split3(__float_as_uint(p0.x), ah[0], al[0]);
+    split3(__float_as_uint(p1.x), ah[1], al[1]);
+    split3(__float_as_uint(p0.y), ah[2], al[2]);
+    split3(__float_as_uint(p1.y), ah[3], al[3]);
 #pragma unroll
     for (int n = 0; n < C / 8; ++n) {
         uint32_t b0h, b0l, b1h, b1l;
-        t2::split_tf32(lds32(blk + v_off[2 * n]), b0h, b0l);
-        t2::split_tf32(lds32(blk + v_off[2 * n + 1]), b1h, b1l);
+        split3(lds32(blk + v_off[2 * n]), b0h, b0l);
+        split3(lds32(blk + v_off[2 * n + 1]), b1h, b1l);
         mma3(acc[n], ah, al, b0h, b1h, b0l, b1l);
     }
 }
@@ -306,10 +319,10 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                 const float w0 = __ldg(bk + 8 * s + t), w1 = __ldg(bk + 8 * s + t + 4);
                 pa = fmaf(x0, w0, pa); pa = fmaf(x2, w1, pa);
                 pb = fmaf(x1, w0, pb); pb = fmaf(x3, w1, pb);
-                t2::split_tf32(__float_as_uint(x0), qa[s][0], ql[s][0]);
-                t2::split_tf32(__float_as_uint(x1), qa[s][1], ql[s][1]);
-                t2::split_tf32(__float_as_uint(x2), qa[s][2], ql[s][2]);
-                t2::split_tf32(__float_as_uint(x3), qa[s][3], ql[s][3]);
+                split3(__float_as_uint(x0), qa[s][0], ql[s][0]);
+                split3(__float_as_uint(x1), qa[s][1], ql[s][1]);
+                split3(__float_as_uint(x2), qa[s][2], ql[s][2]);
+                split3(__float_as_uint(x3), qa[s][3], ql[s][3]);
             } else {
                 qa[s][0] = t2::ldg4(t2::at(Q, oa + 16 * s + 2 * t));     qa[s][1] = t2::ldg4(t2::at(Q, ob + 16 * s + 2 * t));
                 qa[s][2] = t2::ldg4(t2::at(Q, oa + 16 * s + 8 + 2 * t)); qa[s][3] = t2::ldg4(t2::at(Q, ob + 16 * s + 8 + 2 * t));
@@ -411,9 +424,7 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
     auto masked_logit = [&](int row, int64_t kidx) {
         const T *qr = reinterpret_cast<const T *>(a.q) + b * a.q_sb + h * a.q_sh + (int64_t)(i0 + row) * a.q_sn;
         const T *kr = reinterpret_cast<const T *>(a.k) + b * a.k_sb + h * a.k_sh + min(max(kidx, (int64_t)0), (int64_t)a.Nk - 1) * a.k_sn;
-        float s = 0.f;
-        for (int c = 0; c < C; ++c) s = fmaf(to_f(qr[c]), to_f(kr[c]), s);
-        return s - 100.f;
+        return row_dot<T>(qr, kr, C) - 100.f;
     };
     if (active) {
         const int rows = min(TILE_TOK, Nq - i0), QM = M >> 2;

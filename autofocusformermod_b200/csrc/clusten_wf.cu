@@ -21,7 +21,7 @@ constexpr int WF_UNROLL = 2;
 template <typename T, int G, int IC>
 __global__ void __launch_bounds__(CTA_THREADS)
 wf_fwd_kernel(const T *__restrict__ Wt, const T *__restrict__ F, const int64_t *__restrict__ idx, T *__restrict__ out,
-              int B, int Nq, int nchunk, int M, int64_t f_sb, int64_t f_sn) {
+              int B, int Nq, int nchunk, int M, int64_t f_sb, int64_t f_sn, const T *__restrict__ outer = nullptr, int Kin = 1) {
     constexpr int VPT = Vec<T>::VPT;
     constexpr int RPI = 32 / G;
     extern __shared__ int smem_i[];
@@ -34,7 +34,9 @@ wf_fwd_kernel(const T *__restrict__ Wt, const T *__restrict__ F, const int64_t *
     const int64_t *irow = idx + tok * M;
     const T *wrow = Wt + tok * M * IC;
     for (int j = lane; j < M; j += 32) idx_s[j] = (int)irow[j];
-    for (int t = lane; t < M * IC; t += 32) w_s[t] = to_f(wrow[t]);
+    // MSDETRPC (IC = 1): the weight of gather t is the product attn[t / Kin] * nn_weight[t], formed here (msdetrpc_cuda_kernel.cu:40-47)
+    if (outer) { for (int t = lane; t < M; t += 32) w_s[t] = to_f(wrow[t]) * to_f(outer[tok * (M / Kin) + t / Kin]); }
+    else { for (int t = lane; t < M * IC; t += 32) w_s[t] = to_f(wrow[t]); }
     __syncwarp();
     const int grp = lane / G, lg = lane % G;
     const int C = nchunk * VPT;
@@ -82,7 +84,8 @@ wf_fwd_kernel(const T *__restrict__ Wt, const T *__restrict__ F, const int64_t *
 template <typename T, int G, int IC>
 __global__ void __launch_bounds__(CTA_THREADS)
 wf_dw_kernel(const T *__restrict__ dO, const T *__restrict__ F, const int64_t *__restrict__ idx, T *__restrict__ dW,
-             int B, int Nq, int nchunk, int M, int64_t f_sb, int64_t f_sn) {
+             int B, int Nq, int nchunk, int M, int64_t f_sb, int64_t f_sn, const T *__restrict__ outer = nullptr, int Kin = 1,
+             const T *__restrict__ Wt = nullptr, T *__restrict__ dOuter = nullptr) {
     constexpr int VPT = Vec<T>::VPT;
     constexpr int RPI = 32 / G;
     extern __shared__ int smem_i[];
@@ -135,14 +138,27 @@ wf_dw_kernel(const T *__restrict__ dO, const T *__restrict__ F, const int64_t *_
         __syncwarp();
     }
     T *wrow = dW + tok * M * IC;
-    for (int t = lane; t < M * IC; t += 32) wrow[t] = from_f<T>(dw_s[t]);
+    if (outer) {
+        // MSDETRPC: dw_s holds the gradient of the PRODUCT weights; d_nn_weight = it * attn, d_attn = sum_k it * nn_weight
+        // (msdetrpc_cuda_kernel.cu:160-177)
+        const int Mo = M / Kin;
+        for (int t = lane; t < M; t += 32) wrow[t] = from_f<T>(dw_s[t] * to_f(outer[tok * Mo + t / Kin]));
+        for (int mo = lane; mo < Mo; mo += 32) {
+            float s = 0.f;
+            for (int k = 0; k < Kin; ++k) s = fmaf(dw_s[mo * Kin + k], to_f(Wt[tok * M + mo * Kin + k]), s);
+            dOuter[tok * Mo + mo] = from_f<T>(s);
+        }
+    } else {
+        for (int t = lane; t < M * IC; t += 32) wrow[t] = from_f<T>(dw_s[t]);
+    }
 }
 
 template <typename T, int G, int IC>
 __global__ void __launch_bounds__(CTA_THREADS)
 wf_df_kernel(const T *__restrict__ dO, const T *__restrict__ Wt, const int32_t *__restrict__ offsets,
              const uint32_t *__restrict__ entries, T *__restrict__ dF,
-             int B, int Nq, int Nk, int nchunk, int M, int64_t df_sb, int64_t df_sn, const int *__restrict__ run_if) {
+             int B, int Nq, int Nk, int nchunk, int M, int64_t df_sb, int64_t df_sn, const int *__restrict__ run_if,
+             const T *__restrict__ outer = nullptr, int Kin = 1) {
     constexpr int VPT = Vec<T>::VPT;
     if (run_if && run_if[0] == 0) return;            // the octet kernels of clusten_wf2.cu own this call (wf2.cuh flags[0])
     constexpr int RPI = 32 / G;
@@ -173,7 +189,8 @@ wf_df_kernel(const T *__restrict__ dO, const T *__restrict__ Wt, const int32_t *
                 for (int ic = 0; ic < IC; ++ic) load16(dp + (int64_t)ic * C, d[ic]);
 #pragma unroll
                 for (int ic = 0; ic < IC; ++ic) {
-                    const float a = to_f(wp[ic]);
+                    float a = to_f(wp[ic]);
+                    if (outer) a *= to_f(outer[((int64_t)b * Nq + qi) * (M / Kin) + (pk & 255u) / Kin]);      // MSDETRPC product weight
 #pragma unroll
                     for (int v = 0; v < VPT; ++v) acc[v] = fmaf(a, d[ic][v], acc[v]);
                 }
@@ -355,6 +372,71 @@ extern "C" int clusten_wf_bwd(const void *d_out, const void *w, const void *f, c
     CLUSTEN_DISPATCH_DTYPE(dtype, return wf_bwd_impl<T>((const T *)d_out, (const T *)w, (const T *)f, nbhd_idx, csr_offsets,
                                                         csr_entries, plan, (T *)d_w, (T *)d_f, B, Nq, Nk, C, M, IC, f_sb, f_sn,
                                                         df_sb, df_sn, dtype, (cudaStream_t)stream));
+    return 0;
+}
+
+// ---- MSDETRPC: feat[b,i,c] = sum_m attn[b,i,m] * sum_k nn_weight[b,i,m,k] * val[b, nn_idx[b,i,m,k], c]   (msdetrpc_cuda_kernel.cu:18-55)
+// One pass: the weighted-gather kernels above with the product weight attn[m] * nn_weight[m,k] formed in shared memory / registers
+// (forward, d_val) and the two-term gradient taken from the product's gradient in the same kernel (d_nn_weight, d_attn).
+template <typename T>
+static int msd_fwd_impl(const int64_t *idx, const T *w, const T *attn, const T *val, T *out, int B, int N, int Nk, int C, int M, int K,
+                        int64_t v_sb, int64_t v_sn, cudaStream_t st) {
+    if ((int64_t)B * N == 0) return 0;
+    if (!wf_vec_ok<T>(C, 1, val, v_sb, v_sn, {out})) return set_error(CLUSTEN_EUNSUPPORTED, "MSDETRPC: C=%d / alignment outside the vector path", C);
+    const int nchunk = C / Vec<T>::VPT, MK = M * K;
+    const int grid = ceil_div((int64_t)B * N, WARPS_PER_CTA);
+    const size_t smem = (size_t)WARPS_PER_CTA * 2 * MK * sizeof(int);
+    CLUSTEN_DISPATCH_GROUP(pick_group(nchunk), (wf_fwd_kernel<T, G, 1><<<grid, CTA_THREADS, smem, st>>>(w, val, idx, out, B, N, nchunk, MK, v_sb, v_sn, attn, K)));
+    note_launches(1);
+    return check_launch("msdetrpc_fwd");
+}
+
+template <typename T>
+static int msd_bwd_impl(const T *d_out, const int64_t *idx, const T *w, const T *attn, const T *val, const int32_t *off, const uint32_t *ent,
+                        T *d_w, T *d_attn, T *d_val, int B, int N, int Nk, int C, int M, int K, int64_t v_sb, int64_t v_sn, int64_t dv_sb,
+                        int64_t dv_sn, cudaStream_t st) {
+    if (!wf_vec_ok<T>(C, 1, val, v_sb, v_sn, {d_out}) || !wf_vec_ok<T>(C, 1, d_val, dv_sb, dv_sn, {d_out}))
+        return set_error(CLUSTEN_EUNSUPPORTED, "MSDETRPC: C=%d / alignment outside the vector path", C);
+    const int nchunk = C / Vec<T>::VPT, MK = M * K;
+    if ((int64_t)B * N > 0) {
+        const int grid = ceil_div((int64_t)B * N, WARPS_PER_CTA);
+        const size_t smem = (size_t)WARPS_PER_CTA * 2 * MK * sizeof(int);
+        CLUSTEN_DISPATCH_GROUP(pick_group(nchunk), (wf_dw_kernel<T, G, 1><<<grid, CTA_THREADS, smem, st>>>(d_out, val, idx, d_w, B, N, nchunk, MK, v_sb, v_sn,
+                                                                                                   attn, K, w, d_attn)));
+        note_launches(1);
+        if (int e = check_launch("msdetrpc_dw")) return e;
+    }
+    if ((int64_t)B * Nk > 0) {
+        const int grid = ceil_div((int64_t)B * Nk, WARPS_PER_CTA);
+        CLUSTEN_DISPATCH_GROUP(pick_group(nchunk), (wf_df_kernel<T, G, 1><<<grid, CTA_THREADS, 0, st>>>(d_out, w, off, ent, d_val, B, N, Nk, nchunk, MK, dv_sb, dv_sn,
+                                                                                                nullptr, attn, K)));
+        note_launches(1);
+        if (int e = check_launch("msdetrpc_dval")) return e;
+    }
+    return 0;
+}
+
+extern "C" int clusten_msdetrpc_fwd(const int64_t *nn_idx, const void *nn_weight, const void *attn, const void *val, void *out,
+                                    int B, int N, int Nk, int C, int M, int K, int64_t v_sb, int64_t v_sn, int dtype, void *stream) {
+    if (int e = wf_check(B, N, Nk, C, M * (K > 0 ? K : 1), 1)) return e;
+    if (K <= 0 || M * K > 256) return set_error(CLUSTEN_EUNSUPPORTED, "MSDETRPC: M*K = %d outside 1..256", M * K);
+    if (!nn_idx || !nn_weight || !attn || !val || !out) return set_error(CLUSTEN_EINVAL, "null pointer");
+    CLUSTEN_DISPATCH_DTYPE(dtype, return msd_fwd_impl<T>(nn_idx, (const T *)nn_weight, (const T *)attn, (const T *)val, (T *)out, B, N, Nk, C, M, K,
+                                                         v_sb, v_sn, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int clusten_msdetrpc_bwd(const void *d_out, const int64_t *nn_idx, const void *nn_weight, const void *attn, const void *val,
+                                    const int32_t *csr_offsets, const uint32_t *csr_entries, void *d_weight, void *d_attn, void *d_val,
+                                    int B, int N, int Nk, int C, int M, int K, int64_t v_sb, int64_t v_sn, int64_t dv_sb, int64_t dv_sn,
+                                    int dtype, void *stream) {
+    if (int e = wf_check(B, N, Nk, C, M * (K > 0 ? K : 1), 1)) return e;
+    if (K <= 0 || M * K > 256) return set_error(CLUSTEN_EUNSUPPORTED, "MSDETRPC: M*K = %d outside 1..256", M * K);
+    if (!d_out || !nn_idx || !nn_weight || !attn || !val || !csr_offsets || !csr_entries || !d_weight || !d_attn || !d_val)
+        return set_error(CLUSTEN_EINVAL, "null pointer");
+    CLUSTEN_DISPATCH_DTYPE(dtype, return msd_bwd_impl<T>((const T *)d_out, nn_idx, (const T *)nn_weight, (const T *)attn, (const T *)val, csr_offsets,
+                                                         csr_entries, (T *)d_weight, (T *)d_attn, (T *)d_val, B, N, Nk, C, M, K, v_sb, v_sn,
+                                                         dv_sb, dv_sn, (cudaStream_t)stream));
     return 0;
 }
 

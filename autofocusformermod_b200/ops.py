@@ -1002,10 +1002,10 @@ class MSDETRPCFunction(Function):
 
         feat[b,i,c] = sum_m attn[b,i,m] * sum_k nn_weight[b,i,m,k] * val[b, nn_idx[b,i,m,k], c]
 
-    i.e. a weighted gather over the m*k interpolation points with the product weights attn[m] * nn_weight[m,k]: it runs
-    on the WEIGHTEDGATHER kernels (clusten_wg_fwd / clusten_wg_bwd, deterministic inverse-list backward instead of the
-    reference's atomics, msdetrpc_cuda_kernel.cu:113-131); the product and its two-term gradient are small elementwise
-    passes over [B,N,M,K].  ``.apply(nn_idx, nn_weight, attn, val)`` -> [B,N,C]; backward returns (None, d_weight, d_attn, d_val)."""
+    One kernel forward (clusten_msdetrpc_fwd: the weighted-gather kernel with the product weight attn[m] * nn_weight[m,k] formed in
+    shared memory), two backward (clusten_msdetrpc_bwd: d_nn_weight and d_attn from the product's gradient in one pass;
+    d_val by the deterministic inverse-list gather instead of the reference's atomics, msdetrpc_cuda_kernel.cu:113-131).
+    ``.apply(nn_idx, nn_weight, attn, val)`` -> [B,N,C]; backward returns (None, d_weight, d_attn, d_val)."""
 
     @staticmethod
     def forward(ctx, nn_idx, nn_weight, attn, val):
@@ -1016,14 +1016,16 @@ class MSDETRPCFunction(Function):
             raise RuntimeError(f"nn_idx must be int64 (got {nn_idx.dtype})")
         B, N, M, K = nn_idx.shape
         Nk, C = val.shape[1], val.shape[2]
-        nn_idx, nn_weight, attn, val = nn_idx.contiguous(), nn_weight.contiguous(), attn.contiguous(), _rows(val)
-        w = (attn.unsqueeze(3) * nn_weight).to(val.dtype).reshape(B, N, M * K)
-        out = torch.empty((B, N, C), dtype=val.dtype, device=dev)
+        dt = val.dtype
+        nn_idx, val = nn_idx.contiguous(), _rows(val)
+        ctx.in_dtypes = (nn_weight.dtype, attn.dtype)
+        nn_weight, attn = nn_weight.contiguous().to(dt), attn.contiguous().to(dt)
+        out = torch.empty((B, N, C), dtype=dt, device=dev)
         if out.numel():
             with torch.cuda.device(dev):
-                _call("clusten_wg_fwd", dev, nn_idx.data_ptr(), w.data_ptr(), val.data_ptr(), out.data_ptr(),
-                      B, N, Nk, C, M * K, val.stride(0), val.stride(1), _lib.dtype_code(val),
-                      nbytes=val.element_size() * (2 * B * N * M * K + B * Nk * C + B * N * C) + 8 * B * N * M * K)
+                _call("clusten_msdetrpc_fwd", dev, nn_idx.data_ptr(), nn_weight.data_ptr(), attn.data_ptr(), val.data_ptr(), out.data_ptr(),
+                      B, N, Nk, C, M, K, val.stride(0), val.stride(1), _lib.dtype_code(val),
+                      nbytes=val.element_size() * (B * N * M * K + B * N * M + B * Nk * C + B * N * C) + 8 * B * N * M * K)
         ctx.save_for_backward(nn_idx, nn_weight, attn, val)
         return out
 
@@ -1035,10 +1037,10 @@ class MSDETRPCFunction(Function):
         Nk, C = val.shape[1], val.shape[2]
         grad_feat = grad_feat.contiguous().to(val.dtype)
         d_val = torch.empty((B, Nk, C), dtype=val.dtype, device=dev)
+        d_weight, d_attn = torch.empty_like(nn_weight), torch.empty_like(attn)
+        wdt, adt = ctx.in_dtypes
         if B * N * M * K == 0:
-            return None, torch.zeros_like(nn_weight), torch.zeros_like(attn), d_val.zero_()
-        w = (attn.unsqueeze(3) * nn_weight).to(val.dtype).reshape(B, N, M * K)
-        d_w = torch.empty_like(w)
+            return None, d_weight.zero_().to(wdt), d_attn.zero_().to(adt), d_val.zero_()
         idx3 = nn_idx.view(B, N, M * K)
         cached = getattr(nn_idx, "_clusten_csr", None)           # built by an earlier backward on the same index tensor
         if cached is not None:
@@ -1049,11 +1051,8 @@ class MSDETRPCFunction(Function):
         except Exception:  # pragma: no cover
             pass
         with torch.cuda.device(dev):
-            _call("clusten_wg_bwd", dev, grad_feat.data_ptr(), idx3.data_ptr(), w.data_ptr(), val.data_ptr(), off.data_ptr(),
-                  ent.data_ptr(), d_w.data_ptr(), d_val.data_ptr(), B, N, Nk, C, M * K, val.stride(0), val.stride(1),
-                  d_val.stride(0), d_val.stride(1), _lib.dtype_code(val),
-                  nbytes=val.element_size() * (B * N * C + 2 * B * N * M * K + 2 * B * Nk * C) + 8 * B * N * M * K)
-        d_w = d_w.view(B, N, M, K)
-        d_weight = (d_w * attn.unsqueeze(3)).to(nn_weight.dtype)
-        d_attn = (d_w * nn_weight).sum(3).to(attn.dtype)
-        return None, d_weight, d_attn, d_val
+            _call("clusten_msdetrpc_bwd", dev, grad_feat.data_ptr(), nn_idx.data_ptr(), nn_weight.data_ptr(), attn.data_ptr(), val.data_ptr(),
+                  off.data_ptr(), ent.data_ptr(), d_weight.data_ptr(), d_attn.data_ptr(), d_val.data_ptr(), B, N, Nk, C, M, K,
+                  val.stride(0), val.stride(1), d_val.stride(0), d_val.stride(1), _lib.dtype_code(val),
+                  nbytes=val.element_size() * (B * N * C + 2 * B * N * M * K + 2 * B * N * M + 2 * B * Nk * C) + 8 * B * N * M * K)
+        return None, d_weight.to(wdt), d_attn.to(adt), d_val

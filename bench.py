@@ -443,9 +443,13 @@ def main():
                 "share_of_step": round(dom_ms / ms, 4), "timing": roof_timing,
                 "per_entry_ms_per_step": {n: round(v[0], 4) for n, v in sorted(per.items())}}
 
+    execution = ("CUDA graph replay (AFF.graphed)" if graphed is not None else
+                 ("CUDA graphs for forward and backward (graphed_training_forward), eager AdamW"
+                  + (f", one flat NCCL all-reduce of {sync_grads.nbytes / 2**20:.0f} MiB of fp32 gradients per step" if sync_grads is not None else ""))
+                 if graphed_train is not None else "eager")
     extras = {}
     if world == 1 and not args.no_extras and args.workload == DEFAULT_WORKLOAD:
-        del graphed, graphed_train, out
+        graphed = graphed_train = out = None              # release the graphs' memory pools before the op benchmarks
         torch.cuda.empty_cache()
         extras = contract_extras(dev, None)
 
@@ -480,11 +484,7 @@ def main():
         "config": {"workload": args.workload, "note": wl["note"], "batch_per_gpu": B, "global_batch": B * world,
                    "image": [wl["H"], wl["W"]], "parallelism": f"dp{world} (batch-sharded, no data-path collective"
                    + (", NCCL gradient all-reduce)" if train and world > 1 else ")"),
-                   "execution": ("CUDA graph replay (AFF.graphed)" if graphed is not None else
-                                 ("CUDA graphs for forward and backward (graphed_training_forward), eager AdamW"
-                                  + (f", one flat NCCL all-reduce of {sync_grads.nbytes / 2**20:.0f} MiB of fp32 gradients per step" if sync_grads is not None else ""))
-                                 if graphed_train is not None
-                                 else "eager"),
+                   "execution": execution,
                    "l2": f"no explicit flush: one step streams {peak_mem / 2**20:.0f} MiB of live activations (>> 126 MB L2)",
                    "memoised": ("the position-only structures of the on-grid stage 0 (clustering, kNN, neighbourhoods, tile pack) are constants "
                                 "of the input shape and are built once, outside the timed region (the reference memoises its stage-0 "

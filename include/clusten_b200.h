@@ -9,6 +9,7 @@
  *   clusten_av_fwd / clusten_av_bwd   <- clusten/src/clustenav_cuda.cpp:25-45
  *   clusten_wf_fwd / clusten_wf_bwd   <- clusten/src/clustenwf_cuda.cpp:25-45
  *   clusten_wg_fwd / clusten_wg_bwd   <- clusten/src/weighted_gather_cuda.cpp:25-45
+ *   clusten_msdetrpc_fwd / _bwd       <- clusten/src/msdetrpc_cuda.cpp:25-51
  *   clusten_csr_*                     <- replaces the fastAtomicAdd scatter of the reference backward kernels
  *                                        (clustenqk_cuda_kernel.cu:125, clustenav_cuda_kernel.cu:121,
  *                                         clustenwf_cuda_kernel.cu:129, weighted_gather_cuda_kernel.cu:115)
@@ -280,6 +281,18 @@ int clusten_wg_bwd(const void *d_out, const int64_t *nbhd_idx, const void *w, co
                    const int32_t *csr_offsets, const uint32_t *csr_entries, void *d_w, void *d_f,
                    int B, int Nq, int Nk, int C, int K, int64_t f_sb, int64_t f_sn,
                    int64_t df_sb, int64_t df_sn, int dtype, void *stream);
+
+/* ---- MSDETRPC (point-cloud deformable attention, pixel decoder): feat[b,i,c] = sum_m attn[b,i,m] * sum_k nn_weight[b,i,m,k] *
+ * val[b, nn_idx[b,i,m,k], c]   (clusten/src/msdetrpc_cuda.cpp:25-51, msdetrpc_cuda_kernel.cu:18-55); backward = d_nn_weight, d_attn
+ * (msdetrpc_cuda_kernel.cu:138-181) and d_val by the inverse neighbour list of nn_idx viewed as [B,N,M*K] (clusten_csr_build)
+ * instead of the reference's atomics (:113-131).  One pass each: the product weights are formed inside the kernels.
+ * nn_idx int64 [B,N,M,K], nn_weight [B,N,M,K], attn [B,N,M], val strided [B,Nk,C] (unit inner stride), out [B,N,C]; M*K <= 256. */
+int clusten_msdetrpc_fwd(const int64_t *nn_idx, const void *nn_weight, const void *attn, const void *val, void *out,
+                         int B, int N, int Nk, int C, int M, int K, int64_t v_sb, int64_t v_sn, int dtype, void *stream);
+int clusten_msdetrpc_bwd(const void *d_out, const int64_t *nn_idx, const void *nn_weight, const void *attn, const void *val,
+                         const int32_t *csr_offsets, const uint32_t *csr_entries, void *d_weight, void *d_attn, void *d_val,
+                         int B, int N, int Nk, int C, int M, int K, int64_t v_sb, int64_t v_sn, int64_t dv_sb, int64_t dv_sn,
+                         int dtype, void *stream);
 
 /* ---- kNN (2-D, fp32): the k nearest database points of each query, ascending distance, ties -> lowest index;
  * dist = sqrt_rn(fl(dx*dx) + fl(dy*dy)) without FMA contraction.  idx_out int64 [B,Nq,k]; dist_out fp32 [B,Nq,k] or NULL.

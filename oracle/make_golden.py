@@ -114,6 +114,53 @@ def make_aff(aff, name):
     print("aff", name, {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v) and not k.endswith("pos")})
 
 
+def msdeform_case():
+    """Inputs of the MSDeformAttnPc golden: three levels of tokens on a 24 x 32 stem grid (AFF reports the stem grid as the spatial
+    shape of every level), seeded weights with non-zero sampling offsets."""
+    g = torch.Generator().manual_seed(17)
+    b, c, heads, levels, points = 2, 32, 4, 3, 4
+    hw = (24, 32)
+    ns = [40, 150, 500]                                    # res5, res4, res3 token counts
+    poss = [inputs.random_positions(b, n, hw[0], hw[1], seed=20 + i) for i, n in enumerate(ns)]
+    querys = [torch.randn(b, n, c, generator=g) for n in ns]
+    values = [torch.randn(b, n, c, generator=g) for n in ns]
+    params = {"sampling_offsets.weight": torch.randn(heads * levels * points * 2, c, generator=g) * 0.3,
+              "attention_weights.weight": torch.randn(heads * levels * points, c, generator=g) * 0.5,
+              "attention_weights.bias": torch.randn(heads * levels * points, generator=g) * 0.5}
+    return dict(b=b, c=c, heads=heads, levels=levels, points=points, hw=hw, ns=ns, poss=poss, querys=querys, values=values, params=params)
+
+
+def make_msdeform():
+    """The reference's MSDeformAttnPc class (msdeformattn_pc.py:107-205) with its lookup tables built as forward_features does
+    (:486-502), forward and the gradients of a quadratic loss."""
+    cls, scale_pos = ref_loader.load_msdeformattn_pc()
+    pu, _ = ref_loader.load()
+    c = msdeform_case()
+    torch.manual_seed(3)
+    m = cls(c["c"], c["levels"], c["heads"], c["points"], 4.0, True)
+    sd = m.state_dict()
+    sd.update(c["params"])
+    m.load_state_dict(sd)
+    hw = c["hw"]
+    ys, xs = torch.meshgrid(torch.arange(hw[0]), torch.arange(hw[1]), indexing="ij")
+    grid_pos = torch.stack([xs, ys], dim=2).reshape(1, -1, 2).expand(c["b"], -1, -1).float()
+    ss = [hw] * (c["levels"] + 1)
+    with ref_loader.canonical_ties():
+        nb_idx = [pu.knn_keops(grid_pos, scale_pos(p, hw, hw, no_bias=True), 4) for p in c["poss"]]
+    qs = [q.clone().requires_grad_(True) for q in c["querys"]]
+    vs = [v.clone().requires_grad_(True) for v in c["values"]]
+    outs = m(qs, c["poss"], vs, ss, nb_idx)
+    sum(o.square().mean() for o in outs).backward()
+    save = {"state." + k: _np(v) for k, v in m.state_dict().items()}
+    for i in range(c["levels"]):
+        save[f"out{i}"], save[f"d_query{i}"], save[f"d_value{i}"] = _np(outs[i]), _np(qs[i].grad), _np(vs[i].grad)
+        save[f"nb_idx{i}"] = _np(nb_idx[i]).astype(np.int32)
+    for k, p in m.named_parameters():
+        save["grad." + k] = _np(p.grad)
+    np.savez_compressed(os.path.join(OUT, "msdeformattn_pc.npz"), **save)
+    print("msdeformattn_pc", [tuple(o.shape) for o in outs])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     pu, aff = ref_loader.load()
@@ -122,6 +169,8 @@ def main():
         make_sfc(pu)
         make_shepard(pu)
         make_wg()
+    if len(sys.argv) < 2 or "msdeformattn_pc" in sys.argv[1:]:
+        make_msdeform()
     for name in AFF_GOLDENS:
         if len(sys.argv) < 2 or name in sys.argv[1:]:
             make_aff(aff, name)

@@ -20,10 +20,21 @@ import types
 import torch
 
 REF_ROOT = "/root/reference/mask2former/modeling"
+# git-ignored copy of the few reference files the drop-in test executes, staged by oracle/stage_ref.py so that it travels to the
+# GPU box (never committed, never imported by the product package)
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "mask2former", "modeling")
 
 
 def available():
     return os.path.isfile(os.path.join(REF_ROOT, "backbone", "aff.py"))
+
+
+def dropin_root():
+    """Where the reference's backbone sources can be executed from: the reference tree, else the staged copy, else None."""
+    for root in (REF_ROOT, STAGED_ROOT):
+        if os.path.isfile(os.path.join(root, "backbone", "aff.py")):
+            return root
+    return None
 
 
 def _mod(name, **attrs):
@@ -99,6 +110,41 @@ def load():
     return pu, aff
 
 
+def load_dropin():
+    """The reference's OWN ``aff.py`` / ``point_utils.py`` with ``..clusten`` bound to THIS REPOSITORY'S CUDA ops and ``knn_keops`` to
+    its kNN -- the literal drop-in of clusten/__init__.py:6 and the call sites aff.py:114,154,361: returns (point_utils, aff).
+    The modules live under their own fake package, apart from the CPU-oracle binding of ``load()``."""
+    if "dropin" in _cache:
+        return _cache["dropin"]
+    root = dropin_root()
+    if root is None:
+        raise RuntimeError("no reference backbone sources (neither /root/reference nor baseline/_ref; run oracle/stage_ref.py)")
+    _install_stubs()
+    import autofocusformermod_b200 as P
+
+    pkg = _mod("_affdrop")
+    pkg.__path__ = []
+    pkg.clusten = _mod("_affdrop.clusten", CLUSTENQKFunction=P.CLUSTENQKFunction, CLUSTENAVFunction=P.CLUSTENAVFunction,
+                       CLUSTENWFFunction=P.CLUSTENWFFunction, WEIGHTEDGATHERFunction=P.WEIGHTEDGATHERFunction,
+                       MSDETRPCFunction=P.MSDETRPCFunction)
+    bb = _mod("_affdrop.backbone")
+    bb.__path__ = []
+
+    def _load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    pu = _load("_affdrop.backbone.point_utils", "backbone/point_utils.py")
+    aff = _load("_affdrop.backbone.aff", "backbone/aff.py")
+    pu.knn_keops = P.knn_keops                      # pykeops is not importable: the repo's kNN under the reference's name
+    aff.knn_keops = P.knn_keops
+    _cache["dropin"] = (pu, aff)
+    return pu, aff
+
+
 def load_point_conv():
     """The reference's own ``PointConv`` class (pixel_decoder/msdeformattn_pc.py:271-314), executed from the reference file
     without importing the rest of the module (which needs detectron2 / fvcore): the class source is cut out with ``ast``
@@ -113,6 +159,23 @@ def load_point_conv():
           "pre_table": aff.pre_table, "rel_pos_width": aff.rel_pos_width, "table_width": aff.table_width}
     exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
     return ns["PointConv"]
+
+
+def load_msdeformattn_pc():
+    """The reference's own ``MSDeformAttnPc`` class and ``scale_pos`` (pixel_decoder/msdeformattn_pc.py:28-53, 107-205), cut out with
+    ``ast`` and run against the reference ``point_utils`` (oracle kNN) and the oracle MSDETRPC restatement."""
+    import ast
+    import math
+    pu, _ = load()
+    from . import clusten_ops
+    path = os.path.join(REF_ROOT, "pixel_decoder", "msdeformattn_pc.py")
+    body = ast.parse(open(path).read()).body
+    nodes = [n for n in body if (isinstance(n, ast.ClassDef) and n.name == "MSDeformAttnPc") or (isinstance(n, ast.FunctionDef) and n.name == "scale_pos")]
+    ns = {"nn": torch.nn, "torch": torch, "F": torch.nn.functional, "math": math, "constant_": torch.nn.init.constant_,
+          "xavier_uniform_": torch.nn.init.xavier_uniform_, "upsample_feature_shepard": pu.upsample_feature_shepard,
+          "MSDETRPCFunction": clusten_ops.MSDETRPCFunction}
+    exec(compile(ast.Module(body=nodes, type_ignores=[]), path, "exec"), ns)
+    return ns["MSDeformAttnPc"], ns["scale_pos"]
 
 
 def load_point2img():

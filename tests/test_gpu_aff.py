@@ -278,3 +278,34 @@ def test_decoder_helpers_point2img_and_attn_mask():
     assert got.shape == want.shape and got.dtype == torch.bool
     near = (up.sigmoid() - 0.5).abs().unsqueeze(1).repeat(1, 4, 1, 1).flatten(0, 1) < 1e-5     # ignore logits on the threshold
     assert bool(((got == want) | near).all())
+
+
+def test_msdeformattn_pc_matches_reference_class():
+    """pixel_decoder.MSDeformAttnPc (index plumbing of msdeformattn_pc.py:143-205 + clusten_msdetrpc_fwd / _bwd) against the golden
+    made by the reference's own class (oracle/make_golden.py: make_msdeform): lookup tables bit-exact, per-level outputs, and the
+    gradients of queries, values and every parameter (incl. the learnable Shepard power, through d_nn_weight)."""
+    from autofocusformermod_b200.pixel_decoder import MSDeformAttnPc, grid_lookup_tables
+    from oracle.make_golden import msdeform_case
+    g = np.load(os.path.join(GOLDEN, "msdeformattn_pc.npz"))
+    c = msdeform_case()
+    m = MSDeformAttnPc(c["c"], c["levels"], c["heads"], c["points"], 4.0, True)
+    m.load_state_dict({k[len("state."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state.")})
+    m = m.cuda()
+    poss = [p.cuda() for p in c["poss"]]
+    ss = [c["hw"]] * (c["levels"] + 1)
+    nb_idx = grid_lookup_tables(poss, ss[:-1], c["hw"])
+    for i in range(c["levels"]):
+        assert torch.equal(nb_idx[i].cpu().int(), torch.from_numpy(g[f"nb_idx{i}"])), f"lookup table {i}"
+    qs = [q.cuda().requires_grad_(True) for q in c["querys"]]
+    vs = [v.cuda().requires_grad_(True) for v in c["values"]]
+    outs = m(qs, poss, vs, ss, nb_idx)
+    sum(o.square().mean() for o in outs).backward()
+    errs = {}
+    for i in range(c["levels"]):
+        errs[f"out{i}"] = rel_err(outs[i], torch.from_numpy(g[f"out{i}"]))
+        errs[f"d_query{i}"] = rel_err(qs[i].grad, torch.from_numpy(g[f"d_query{i}"]))
+        errs[f"d_value{i}"] = rel_err(vs[i].grad, torch.from_numpy(g[f"d_value{i}"]))
+    for k, p in m.named_parameters():
+        errs["grad." + k] = rel_err(p.grad, torch.from_numpy(g["grad." + k]))
+    print({k: f"{v:.1e}" for k, v in errs.items()})
+    assert max(errs.values()) <= 2e-5, errs

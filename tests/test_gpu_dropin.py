@@ -1,0 +1,73 @@
+"""The literal drop-in: the reference's OWN ``AFF`` class (mask2former/modeling/backbone/aff.py:568-686, executed unmodified from
+the staged copy under the git-ignored baseline/_ref/, oracle/stage_ref.py) running on the B200 with
+
+    from ..clusten import CLUSTENQKFunction, CLUSTENAVFunction, CLUSTENWFFunction     (aff.py:14 -> clusten/__init__.py:6)
+    from .point_utils import knn_keops                                                (pykeops is not installable here)
+
+bound to THIS repository's autograd Functions and kNN -- i.e. exactly what a maintainer gets by swapping the import.  Its call sites
+(aff.py:114, 154, 361; point_utils.py:51-59) hand our ops the reference's own non-contiguous views, dtypes and index tensors.
+The result must equal the repository's own AFF module (the fused fast path) on the same weights and images: positions bit-exact
+(with the canonical tie rule forced on the reference's torch.sort / topk), features to 1e-5; and the training
+backward through the reference class must give the same parameter gradients as ours."""
+import pytest
+import torch
+
+from oracle import aff_oracle as ao
+from oracle import ref_loader
+
+from conftest import rel_err
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(ref_loader.dropin_root() is None, reason="reference backbone sources not staged (oracle/stage_ref.py)")]
+
+
+def _reference_aff(preset):
+    _, aff = ref_loader.load_dropin()
+    cfg = ao.PRESETS[preset]
+    m = aff.AFF(embed_dim=cfg["embed_dim"], cluster_size=cfg["cluster_size"], nbhd_size=list(cfg["nbhd_size"]), alpha=cfg["alpha"],
+                ds_rate=cfg["ds_rate"], depths=cfg["depths"], num_heads=cfg["num_heads"], mlp_ratio=cfg["mlp_ratio"],
+                drop_path_rate=0.0, layer_scale=cfg["layer_scale"])
+    W = dict(ao.synthetic_state(cfg))
+    W["patch_embed.bn.num_batches_tracked"] = m.state_dict()["patch_embed.bn.num_batches_tracked"]
+    m.load_state_dict(W)
+    return m.cuda()
+
+
+def _ours(preset):
+    from autofocusformermod_b200.aff import build_aff
+    m = build_aff(preset, drop_path_rate=0.0)
+    m.load_state_dict(ao.synthetic_state(ao.PRESETS[preset]), strict=False)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("preset,B,H,W", [("test", 2, 256, 256), ("test", 2, 100, 134), ("mini", 1, 512, 512), ("base", 1, 256, 384)])
+def test_reference_aff_class_runs_on_our_ops(preset, B, H, W):
+    ref, ours = _reference_aff(preset).eval(), _ours(preset).eval()
+    x = ao.synthetic_images(B, H, W).cuda()
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        with ref_loader.canonical_ties():
+            r = ref(x)
+        o = ours(x)
+    errs = {}
+    for i in range(2, 6):
+        assert torch.equal(r[f"res{i}_pos"].float(), o[f"res{i}_pos"].float()), f"res{i}_pos"
+        errs[f"res{i}"] = rel_err(o[f"res{i}"], r[f"res{i}"])
+    print(preset, (B, H, W), {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) <= 1e-5, errs
+
+
+def test_reference_aff_class_trains_on_our_ops():
+    """Backward through the reference class -> our CLUSTENQK / AV / WF backward kernels; same parameter gradients as our module."""
+    ref, ours = _reference_aff("test").train(), _ours("test").train()
+    x = ao.synthetic_images(2, 128, 160, seed=3).cuda()
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        with ref_loader.canonical_ties():
+            r = ref(x)
+            sum(r[f"res{i}"].square().mean() for i in range(2, 6)).backward()
+        o = ours(x)
+        sum(o[f"res{i}"].square().mean() for i in range(2, 6)).backward()
+    for i in range(2, 6):
+        assert torch.equal(r[f"res{i}_pos"].float(), o[f"res{i}_pos"].float())
+        assert rel_err(o[f"res{i}"], r[f"res{i}"]) <= 1e-5
+    pr = dict(ref.named_parameters())
+    worst = max(rel_err(p.grad, pr[n].grad) for n, p in ours.named_parameters() if p.grad is not None and pr[n].grad is not None)
+    assert worst <= 1e-4, worst          # fp32, two different op decompositions (separate ops + torch glue vs ours)
