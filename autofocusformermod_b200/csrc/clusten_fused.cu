@@ -31,10 +31,9 @@ __device__ __forceinline__ void f_mma1688(float (&d)[4], const uint32_t (&a)[4],
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void f_split(float x, uint32_t &hi, uint32_t &lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float r = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+__device__ __forceinline__ void f_split(float x, uint32_t &hi, uint32_t &lo) {      // truncating split (see clusten_tile.cu: tf32_split)
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void f_mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
                                        uint32_t b0h, uint32_t b1h, uint32_t b0l, uint32_t b1l) {

@@ -184,7 +184,7 @@ __device__ __forceinline__ void pv_octet32(float (&acc)[C / 8][4], uint32_t Sa_u
 }
 
 template <typename T, int C, bool PACKED, bool PB>
-__global__ void __launch_bounds__(GW * 32)
+__global__ void __launch_bounds__(GW * 32, sizeof(T) == 4 ? 4 : 6)
 attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV, const FArgsOf<PB> a,
                       const PackView pk, const GroupView gv, const Launch L) {
     using G = Geo<T, C, PACKED>;
@@ -686,7 +686,7 @@ static int launch_cfg(const CUtensorMap &mk, const CUtensorMap &mv, const FusedA
     if (cap <= 0) {
         const int typical = a.M <= 64 ? 36 : 64;
         cap = 0;
-        for (int want = 4; want >= 1 && cap < typical; --want) {
+        for (int want = 6; want >= 1 && cap < typical; --want) {
             const int64_t room = (int64_t)(227 * 1024) / want - 1024 - (int64_t)fixed;
             cap = (int)std::min<int64_t>(room / G::BOX, 128);
         }

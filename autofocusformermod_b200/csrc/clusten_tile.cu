@@ -40,9 +40,11 @@ __device__ __forceinline__ uint32_t tf32_hi(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// x = hi + lo with hi = x truncated to tf32 (one LOP3) and lo = x - hi (exact; the tensor cores read its upper 19 bits): two
+// instructions where `cvt.rna.tf32.f32` costs seven twice over on sm_100 (the rounding is emulated).  hi + lo keeps 21 mantissa bits.
 __device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo) {
-    hi = tf32_hi(x);
-    lo = tf32_hi(x - __uint_as_float(hi));
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 // 3xTF32: d += a*b with fp32-level accuracy
 __device__ __forceinline__ void mma_3xtf32(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],

@@ -81,6 +81,40 @@ wf_fwd_kernel(const T *__restrict__ Wt, const T *__restrict__ F, const int64_t *
     }
 }
 
+// Weighted gather with a handful of neighbours (Shepard upsampling, point_utils.py:103-114: K = 4): one THREAD per 16-byte channel
+// chunk of an output row; the K rows of a token are all in flight at once, no shared memory, no shuffles; the threads of a token read
+// its K indices / weights as broadcast loads and its rows as contiguous segments.
+template <typename T, int KMAX>
+__global__ void __launch_bounds__(256)
+wg_small_kernel(const T *__restrict__ Wt, const T *__restrict__ F, const int64_t *__restrict__ idx, T *__restrict__ out,
+                int64_t tokens, int Nq, int nchunk, int K, int64_t f_sb, int64_t f_sn) {
+    constexpr int VPT = Vec<T>::VPT;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t tok = t / nchunk;
+    if (tok >= tokens) return;
+    const int ch = (int)(t - tok * nchunk);
+    const int b = (int)(tok / Nq);
+    const T *fb = F + b * f_sb + ch * VPT;
+    float v[KMAX][VPT], w[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+            w[k] = to_f(__ldg(Wt + tok * K + k));
+            load16(fb + __ldg(idx + tok * K + k) * f_sn, v[k]);
+        }
+    }
+    float acc[VPT];
+#pragma unroll
+    for (int x = 0; x < VPT; ++x) acc[x] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+        if (k < K) {
+#pragma unroll
+            for (int x = 0; x < VPT; ++x) acc[x] = fmaf(w[k], v[k][x], acc[x]);
+        }
+    store16(out + tok * (int64_t)nchunk * VPT + ch * VPT, acc);
+}
+
 template <typename T, int G, int IC>
 __global__ void __launch_bounds__(CTA_THREADS)
 wf_dw_kernel(const T *__restrict__ dO, const T *__restrict__ F, const int64_t *__restrict__ idx, T *__restrict__ dW,
@@ -279,6 +313,14 @@ static int wf_fwd_impl(const T *w, const T *f, const int64_t *idx, T *out, const
                        int64_t f_sb, int64_t f_sn, int dtype, cudaStream_t st) {
     if ((int64_t)B * Nq == 0) return 0;
     if (plan && wf3_fwd(w, f, idx, out, plan, B, Nq, Nk, C, M, IC_, f_sb, f_sn, dtype, st) > 0) return check_launch("wf3_fwd");
+    if (IC_ == 1 && M <= 8 && wf_vec_ok<T>(C, 1, f, f_sb, f_sn, {out})) {
+        const int nchunk = C / Vec<T>::VPT;
+        const int64_t threads = (int64_t)B * Nq * nchunk;
+        if (M <= 4) wg_small_kernel<T, 4><<<ceil_div(threads, 256), 256, 0, st>>>(w, f, idx, out, (int64_t)B * Nq, Nq, nchunk, M, f_sb, f_sn);
+        else wg_small_kernel<T, 8><<<ceil_div(threads, 256), 256, 0, st>>>(w, f, idx, out, (int64_t)B * Nq, Nq, nchunk, M, f_sb, f_sn);
+        note_launches(1);
+        return check_launch("wg_small");
+    }
     if (wf2_fwd(w, f, idx, out, plan, B, Nq, Nk, C, M, IC_, f_sb, f_sn, dtype, st)) return check_launch("wf2_fwd");
     if (wf_vec_ok<T>(C, IC_, f, f_sb, f_sn, {out})) {
         const int nchunk = C / Vec<T>::VPT;

@@ -141,14 +141,52 @@ rank_kernel(const uint8_t *__restrict__ present, int32_t *__restrict__ rank, int
 }
 
 __global__ void __launch_bounds__(256)
-rerank_kernel(const int32_t *__restrict__ pe, const int32_t *__restrict__ rank, int32_t *__restrict__ inv, int64_t total) {
+rerank_kernel(const int32_t *pe, const int32_t *__restrict__ rank, int32_t *inv, int64_t total) {      // (pe may alias inv)
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
         inv[e] = __ldg(rank + pe[e]);
+}
+
+// standalone ranking of table rows given as int64 indices (PointConv's pe_idx, msdeformattn_pc.py:305-306): mark + narrow to int32
+__global__ void __launch_bounds__(256)
+mark_rows_kernel(const int64_t *__restrict__ pe64, int64_t total, int32_t *__restrict__ pe32, uint8_t *__restrict__ present, int *__restrict__ range) {
+    int pmin = 0x7fffffff, pmax = -1;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)min(max(pe64[e], (int64_t)0), (int64_t)PE_ROWS - 1);
+        pe32[e] = v;
+        present[v] = 1;
+        pmin = min(pmin, v);
+        pmax = max(pmax, v);
+    }
+    pmin = __reduce_min_sync(FULL, pmin);
+    pmax = __reduce_max_sync(FULL, pmax);
+    if ((threadIdx.x & 31) == 0 && pmax >= 0) { atomicMin(range, pmin); atomicMax(range + 1, pmax); }
 }
 
 }  // namespace clusten
 
 using namespace clusten;
+
+extern "C" int clusten_table_rank(const int64_t *pe_idx, int64_t total, int32_t *inverse, int32_t *uniq, int uniq_cap, int32_t *count,
+                                  void *workspace, size_t workspace_bytes, void *stream) {
+    if (total < 0 || uniq_cap <= 0) return set_error(CLUSTEN_EINVAL, "bad sizes total=%lld cap=%d", (long long)total, uniq_cap);
+    if (!pe_idx || !inverse || !uniq || !count || !workspace) return set_error(CLUSTEN_EINVAL, "null pointer");
+    if (workspace_bytes < clusten_prepare_workspace_bytes()) return set_error(CLUSTEN_EWORKSPACE, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *present = reinterpret_cast<uint8_t *>(workspace);
+    const size_t pm = (size_t)((PE_ROWS + 255) & ~255);
+    int32_t *rank = reinterpret_cast<int32_t *>(present + pm);
+    int *range = reinterpret_cast<int *>(reinterpret_cast<char *>(workspace) + pm + (size_t)PE_ROWS * 4);
+    cudaMemsetAsync(present, 0, pm, st);
+    cudaMemsetAsync(range, 0x7f, 4, st);
+    cudaMemsetAsync(range + 1, 0, 4, st);
+    if (total == 0) { cudaMemsetAsync(count, 0, 4, st); return check_launch("table_rank memset"); }
+    const int grid = (int)std::min<int64_t>(148 * 16, (total + 255) / 256);
+    mark_rows_kernel<<<grid, 256, 0, st>>>(pe_idx, total, inverse, present, range);
+    rank_kernel<<<1, 1024, 0, st>>>(present, rank, uniq, count, uniq_cap, range);
+    rerank_kernel<<<grid, 256, 0, st>>>(inverse, rank, inverse, total);          // in place: every thread reads its element, then writes it
+    note_launches(3);
+    return check_launch("table_rank");
+}
 
 extern "C" size_t clusten_prepare_workspace_bytes(void) {
     // presence map (padded) + rank table

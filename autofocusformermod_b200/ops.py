@@ -1021,7 +1021,16 @@ class MSDETRPCFunction(Function):
         ctx.in_dtypes = (nn_weight.dtype, attn.dtype)
         nn_weight, attn = nn_weight.contiguous().to(dt), attn.contiguous().to(dt)
         out = torch.empty((B, N, C), dtype=dt, device=dev)
-        if out.numel():
+        ctx.vector = C % (16 // val.element_size()) == 0 and val.data_ptr() % 16 == 0 and (val.stride(0) * val.element_size()) % 16 == 0 \
+            and (val.stride(1) * val.element_size()) % 16 == 0
+        if out.numel() and not ctx.vector:
+            # channel counts off the 16-byte grid: the scalar weighted-gather kernels with the product weights formed by torch
+            w = (attn.unsqueeze(3) * nn_weight).reshape(B, N, M * K)
+            with torch.cuda.device(dev):
+                _call("clusten_wg_fwd", dev, nn_idx.data_ptr(), w.data_ptr(), val.data_ptr(), out.data_ptr(),
+                      B, N, Nk, C, M * K, val.stride(0), val.stride(1), _lib.dtype_code(val),
+                      nbytes=val.element_size() * (2 * B * N * M * K + B * Nk * C + B * N * C) + 8 * B * N * M * K)
+        elif out.numel():
             with torch.cuda.device(dev):
                 _call("clusten_msdetrpc_fwd", dev, nn_idx.data_ptr(), nn_weight.data_ptr(), attn.data_ptr(), val.data_ptr(), out.data_ptr(),
                       B, N, Nk, C, M, K, val.stride(0), val.stride(1), _lib.dtype_code(val),
@@ -1050,6 +1059,16 @@ class MSDETRPCFunction(Function):
             nn_idx._clusten_csr = idx3._clusten_csr
         except Exception:  # pragma: no cover
             pass
+        if not ctx.vector:
+            w = (attn.unsqueeze(3) * nn_weight).reshape(B, N, M * K)
+            d_w = torch.empty_like(w)
+            with torch.cuda.device(dev):
+                _call("clusten_wg_bwd", dev, grad_feat.data_ptr(), idx3.data_ptr(), w.data_ptr(), val.data_ptr(), off.data_ptr(),
+                      ent.data_ptr(), d_w.data_ptr(), d_val.data_ptr(), B, N, Nk, C, M * K, val.stride(0), val.stride(1),
+                      d_val.stride(0), d_val.stride(1), _lib.dtype_code(val),
+                      nbytes=val.element_size() * (B * N * C + 2 * B * N * M * K + 2 * B * Nk * C) + 8 * B * N * M * K)
+            d_w = d_w.view(B, N, M, K)
+            return None, (d_w * attn.unsqueeze(3)).to(wdt), (d_w * nn_weight).sum(3).to(adt), d_val
         with torch.cuda.device(dev):
             _call("clusten_msdetrpc_bwd", dev, grad_feat.data_ptr(), nn_idx.data_ptr(), nn_weight.data_ptr(), attn.data_ptr(), val.data_ptr(),
                   off.data_ptr(), ent.data_ptr(), d_weight.data_ptr(), d_attn.data_ptr(), d_val.data_ptr(), B, N, Nk, C, M, K,

@@ -18,7 +18,7 @@ from torch.nn import functional as F
 
 from .aff import REL_POS_WIDTH, TABLE_WIDTH, _TableLookup
 from .ops import CLUSTENWFFunction, MSDETRPCFunction
-from .point_utils import knn_keops, shepard_decay_weights, upsample_feature_shepard
+from .point_utils import knn_keops, shepard_decay_weights, table_rank, upsample_feature_shepard
 
 
 class PointConv(nn.Module):
@@ -38,7 +38,9 @@ class PointConv(nn.Module):
         rel_pos = pos.unsqueeze(2) - nn_pos                                                    # :297 (query minus neighbour)
         rel = (rel_pos.long() + REL_POS_WIDTH).clamp(0, TABLE_WIDTH - 1)                       # :305
         pe_idx = rel[..., 1] * TABLE_WIDTH + rel[..., 0]                                       # :306
-        weights = _TableLookup(pe_idx)(self.weight_net)                                        # :302-308 on the referenced rows
+        # :302-308 on the referenced table rows, ranked on the device (no sort, no host read: the decoder stays capturable)
+        uniq, inverse, count = table_rank(pe_idx)
+        weights = _TableLookup(uniq=uniq, inverse=inverse, count=count)(self.weight_net)
         feat = CLUSTENWFFunction.apply(weights, x, nn_idx).reshape(b, n, -1)                   # :309
         return self.linear(self.norm(feat))                                                    # :311-313
 

@@ -117,6 +117,27 @@ def stage_prepare(pos, nearest, member, cluster_mask, want_mask64=True, extent=N
     return member_idx, mask64, mask8, uniq[:U].long(), bias_idx
 
 
+def table_rank(pe_idx):
+    """``torch.unique(pe_idx, return_inverse=True)`` over relative-position table rows without the sort and without a host read
+    (clusten_table_rank): returns (uniq int64 [cap] -- the ascending distinct rows in its first ``count`` entries, the tail repeats
+    row 0 --, inverse int32 shaped like pe_idx, count int32 device scalar).  cap = min(1023^2, pe_idx.numel())."""
+    dev = _lib.require_cuda(pe_idx)
+    pe = pe_idx.contiguous()
+    if pe.dtype != torch.int64:
+        pe = pe.long()
+    total = pe.numel()
+    cap = max(1, min(PE_TABLE_WIDTH * PE_TABLE_WIDTH, total))
+    inverse = torch.empty(pe.shape, dtype=torch.int32, device=dev)
+    uniq = torch.zeros(cap, dtype=torch.int32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    ws_bytes = L.clusten_prepare_workspace_bytes()
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _call("clusten_table_rank", dev, pe.data_ptr(), total, inverse.data_ptr(), uniq.data_ptr(), cap, count.data_ptr(), ws.data_ptr(), ws_bytes)
+    return uniq.long(), inverse, count
+
+
 def topk_select(score, k, out=None):
     """Canonical ``score.topk(k, sorted=False)[1]`` (aff.py:320): first k of a stable descending sort, int64 [B,k]."""
     dev = _lib.require_cuda(score)

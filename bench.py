@@ -158,6 +158,8 @@ def contract_extras(dev, log):
       ref_cuda_kernels  the reference's OWN kernels (oracle/_ref, built unmodified from /root/reference for sm_100a; checker leg, like
                         cpu_baseline) on the same fp32 inputs -- the "kernel to beat"
       integer_path_us   clustering / kNN / stage preparation / merge selection / tile pack at N = 16 384 and 131 072
+      head_path_us      the pixel-decoder callers of the path (configs[1]'s head half): FPN Shepard upsample, PointConv, one
+                        MSDeformAttnPc layer at N0 = 16 384, conv dim 256, batch 16 (benchmarks/head_bench.py)
       north_star_model  AFF-Small backbone forward, 512x512, batch 16, fp32 (the model north_star's scaling target names)"""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
@@ -178,6 +180,9 @@ def contract_extras(dev, log):
                             "peak": op_bench.peak_gbs()[0], **ours},
            "ref_cuda_kernels": ({"kind": "reference (oracle/_ref, unmodified sources, sm_100a)", "dtype": "f32", **refk} if refk else None),
            "integer_path_us": int_bench.integer_path_us(iters=5)}
+    torch.cuda.empty_cache()
+    import head_bench
+    out["head_path_us"] = head_bench.head_path_us(batch=16, iters=3)     # PointConv / FPN upsample / MSDeformAttnPc at N0 = 16 384
     torch.cuda.empty_cache()
     # the north-star model on the same device: graph replay, inputs resident, CUDA events
     from autofocusformermod_b200.aff import build_aff

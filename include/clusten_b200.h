@@ -216,6 +216,11 @@ int clusten_stage_prepare(const int64_t *nearest /* [B,n,nnc] */, const int64_t 
                           int B, int n, int k, int m, int nnc,
                           int64_t *member_idx, int64_t *mask64, uint8_t *mask8, int32_t *pe_idx, int32_t *bias_idx,
                           int32_t *uniq, int uniq_cap, int32_t *count, void *workspace, size_t workspace_bytes, void *stream);
+/* The table-row restriction alone, for index tensors that arrive as int64 table rows (PointConv, msdeformattn_pc.py:305-306):
+ * uniq[0:count] = the ascending distinct rows of pe_idx (what torch.unique returns, without the sort), inverse[e] = rank of
+ * pe_idx[e]; uniq is filled up to uniq_cap rows, the count stays on the device (no host read).  Same workspace as above. */
+int clusten_table_rank(const int64_t *pe_idx, int64_t total, int32_t *inverse, int32_t *uniq, int uniq_cap, int32_t *count,
+                       void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- Linear(F -> H) over the rows of the relative-position feature table: out[r,h] = bias[h] + sum_j feat[r,j] * weight[h,j]
  * -- `self.pos_embed(pre_table)` of backbone/aff.py:101,129 on the rows a stage references.  fp32; F <= 8, H <= 32;

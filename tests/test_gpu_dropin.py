@@ -21,7 +21,20 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(ref_loader.dropin_root() is No
 
 
 def _reference_aff(preset):
-    _, aff = ref_loader.load_dropin()
+    pu, aff = ref_loader.load_dropin()
+    if not getattr(aff, "_sfc_on_cpu", False):
+        # The reference's clustering is plain torch code; run on the GPU its ``mean`` over a cluster's members sums in another order
+        # than on the CPU and cluster_mean_pos differs in the last bit for a few clusters (measured: 26 of 64 at Base stage 1, max
+        # 7.6e-6), which flips the 6-nearest-cluster list of tokens with near-tied distances (3 of 1536 there).  The pinned behaviour
+        # -- goldens, oracle, our kernel -- is the CPU arithmetic, so the reference's own function is evaluated on the CPU here.
+        ref_sfc = pu.space_filling_cluster
+
+        def sfc_cpu_arithmetic(pos, *args, **kwargs):
+            out = ref_sfc(pos.cpu(), *args, **kwargs)
+            return tuple(None if t is None else t.to(pos.device) for t in out)
+
+        aff.space_filling_cluster = sfc_cpu_arithmetic
+        aff._sfc_on_cpu = True
     cfg = ao.PRESETS[preset]
     m = aff.AFF(embed_dim=cfg["embed_dim"], cluster_size=cfg["cluster_size"], nbhd_size=list(cfg["nbhd_size"]), alpha=cfg["alpha"],
                 ds_rate=cfg["ds_rate"], depths=cfg["depths"], num_heads=cfg["num_heads"], mlp_ratio=cfg["mlp_ratio"],
@@ -69,5 +82,7 @@ def test_reference_aff_class_trains_on_our_ops():
         assert torch.equal(r[f"res{i}_pos"].float(), o[f"res{i}_pos"].float())
         assert rel_err(o[f"res{i}"], r[f"res{i}"]) <= 1e-5
     pr = dict(ref.named_parameters())
-    worst = max(rel_err(p.grad, pr[n].grad) for n, p in ours.named_parameters() if p.grad is not None and pr[n].grad is not None)
-    assert worst <= 1e-4, worst          # fp32, two different op decompositions (separate ops + torch glue vs ours)
+    errs = {n: rel_err(p.grad, pr[n].grad) for n, p in ours.named_parameters() if p.grad is not None and pr[n].grad is not None}
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    print(worst)
+    assert worst[0][1] <= 1e-4, worst    # fp32, two different op decompositions (separate ops + torch glue vs ours)
