@@ -35,3 +35,11 @@ def rel_err(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     den = b.abs().max().clamp_min(1e-30)
     return float((a - b).abs().max() / den)
+
+
+@pytest.fixture(params=["per-warp", "tma-staged"])
+def attn_fwd_kernel(request, monkeypatch):
+    """Runs a test once with each forward kernel behind clusten_attn_fwd / clusten_attn_pos_fwd: the per-warp kernel
+    (clusten_fused.cu, default) and the CTA-cooperative TMA-staged kernel (clusten_fused_tma.cu, CLUSTEN_TMA_ATTN=1)."""
+    monkeypatch.setenv("CLUSTEN_TMA_ATTN", "1" if request.param == "tma-staged" else "0")
+    return request.param

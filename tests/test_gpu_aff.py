@@ -32,7 +32,7 @@ def test_parameter_names_match_reference():
 
 @pytest.mark.parametrize("name,preset,B,H,Wd", [("aff_test_256", "test", 2, 256, 256), ("aff_mini_512", "mini", 2, 512, 512),
                                                  ("aff_tiny_1_5_512", "tiny_1_5", 2, 512, 512), ("aff_base_256x512", "base", 1, 256, 512)])
-def test_forward_matches_reference_class_golden(name, preset, B, H, Wd):
+def test_forward_matches_reference_class_golden(name, preset, B, H, Wd, attn_fwd_kernel):
     """The BASELINE presets at bench-scale token counts against outputs of the reference's own AFF class (oracle/make_golden.py):
     Mini 512^2 (configs[1]), Tiny-1/5 512^2 (ds 0.2: padded clusters, masks, 30 blocks), Base 256x512 (m = 24, M = 144).
     Positions (clustering + every top-k selection) bit-exact; features to 1e-5 (measured <= 3e-6 through up to 30 blocks)."""

@@ -82,7 +82,11 @@ def test_reference_aff_class_trains_on_our_ops():
         assert torch.equal(r[f"res{i}_pos"].float(), o[f"res{i}_pos"].float())
         assert rel_err(o[f"res{i}"], r[f"res{i}"]) <= 1e-5
     pr = dict(ref.named_parameters())
-    errs = {n: rel_err(p.grad, pr[n].grad) for n, p in ours.named_parameters() if p.grad is not None and pr[n].grad is not None}
+    gmax = max(float(p.grad.abs().max()) for p in pr.values() if p.grad is not None)
+    # (the bias of the first stem convolution feeds a BatchNorm in training mode: its true gradient is zero, both sides hold rounding
+    # noise ~1e-9 of the other gradients -- parameters whose gradient is below 1e-6 of the largest one are not compared)
+    errs = {n: rel_err(p.grad, pr[n].grad) for n, p in ours.named_parameters()
+            if p.grad is not None and pr[n].grad is not None and float(pr[n].grad.abs().max()) > 1e-6 * gmax}
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
     print(worst)
     assert worst[0][1] <= 1e-4, worst    # fp32, two different op decompositions (separate ops + torch glue vs ours)

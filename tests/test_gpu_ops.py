@@ -423,7 +423,7 @@ def _fused_reference(q, k, v, idx, bias_tab, bias_idx, mask, blank_k, blank_v):
 @pytest.mark.parametrize("H,C", [(2, 16), (3, 32), (16, 24)])
 @pytest.mark.parametrize("n,m,nbhd,kind", [(1024, 8, 48, "clustered"), (2003, 8, 48, "clustered"), (1540, 24, 144, "clustered"),
                                             (300, 8, 48, "random")])
-def test_fused_attention_core(n, m, nbhd, kind, H, C, dtype):
+def test_fused_attention_core(n, m, nbhd, kind, H, C, dtype, attn_fwd_kernel):
     """clusten_attn_fwd (QK + bias + mask + blank + softmax + AV fused) against the op-by-op oracle composition, on the
     tensor-core tile path (clustered idx, incl. padded last clusters -> cluster mask + impure tokens, and AFF-Base's
     M = 144) and on the generic kernel (random idx)."""

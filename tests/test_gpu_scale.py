@@ -71,7 +71,7 @@ def _inputs(name, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("name", list(SHAPES))
-def test_fused_attention_forward_at_bench_scale(name, dtype):
+def test_fused_attention_forward_at_bench_scale(name, dtype, attn_fwd_kernel):
     """clusten_attn_fwd through the inference entry (ops.cluster_attention_fused, what AFF.forward calls under no_grad)."""
     from autofocusformermod_b200 import ops
     pos, idx, mask8, bias_idx, q, kv, tab, bk, bv, _ = _inputs(name, dtype)
@@ -106,7 +106,7 @@ def test_fused_attention_training_at_bench_scale(name):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("name", list(SHAPES))
-def test_fused_attention_inkernel_bias_at_bench_scale(name, dtype):
+def test_fused_attention_inkernel_bias_at_bench_scale(name, dtype, attn_fwd_kernel):
     """clusten_attn_pos_fwd (bias from positions, posbias.cuh) against the table formulation evaluated in float64: the bias the
     reference gathers is pos_embed(pre_table)[pe_idx] (aff.py:17-31,129-132,481-485)."""
     from autofocusformermod_b200 import ops
