@@ -233,6 +233,57 @@ df_oct_kernel(const T *__restrict__ dO, const T *__restrict__ W, const WfPlanVie
     }
 }
 
+// fp32 form of the same scatter (the merge under AMP runs fp32 weights: the reference's CLUSTENWF casts feat up, clusten.py:80-81).
+// One warp per feature octet walks its sorted reference list; per entry (token i, slot s) the 8 x 4 weights w[i, 8s..8s+7, 0..3] are
+// ONE coalesced 128-byte load (lane = 4 r + ic, broadcast by shuffles) and the four d_out rows of the token are read once for all 8
+// feature rows -- the inverse-list kernel of clusten_wf.cu reads them once per (row, entry), 8x the L2 traffic.  Lane owns channels
+// c0 + lane + 32 k, k < KC; plain FFMA (exact fp32), entries in ascending order (deterministic).
+template <int KC>
+__global__ void __launch_bounds__(WPC * 32)
+df_oct32_kernel(const float *__restrict__ dO, const float *__restrict__ W, const WfPlanView pv, float *__restrict__ dF,
+                int B, int Nq, int Nk, int C, int M, int64_t df_sb, int64_t df_sn) {
+    if (pv.flags[0]) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t oid = (int64_t)blockIdx.x * WPC + warp;
+    if (oid >= (int64_t)B * pv.NO) return;
+    const int b = (int)(oid / pv.NO), o = (int)(oid - (int64_t)b * pv.NO);
+    const int lo = pv.oct_off[(int64_t)b * (pv.NO + 1) + o], hi = pv.oct_off[(int64_t)b * (pv.NO + 1) + o + 1];
+    const uint32_t *ent = pv.oct_ent + (int64_t)b * Nq * pv.S;
+    const float *dOb = dO + (int64_t)b * Nq * 4 * C;
+    const float *Wb = W + (int64_t)b * Nq * M * 4;
+    for (int c0 = 0; c0 < C; c0 += 32 * KC) {
+        float acc[8][KC];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int k = 0; k < KC; ++k) acc[r][k] = 0.f;
+        for (int e = lo; e < hi; ++e) {
+            const uint32_t v = __ldg(ent + e);
+            const int64_t i = v >> 5;
+            const float wl = __ldg(Wb + (i * M + 8 * (v & 31u)) * 4 + lane);           // w[i, 8s + lane/4, lane%4]
+            float d[4][KC];
+#pragma unroll
+            for (int ic = 0; ic < 4; ++ic)
+#pragma unroll
+                for (int k = 0; k < KC; ++k) d[ic][k] = __ldg(dOb + (i * 4 + ic) * C + c0 + lane + 32 * k);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int ic = 0; ic < 4; ++ic) {
+                    const float w = __shfl_sync(FULL, wl, 4 * r + ic);
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) acc[r][k] = fmaf(w, d[ic][k], acc[r][k]);
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (8 * o + r < Nk) {
+#pragma unroll
+                for (int k = 0; k < KC; ++k) dF[b * df_sb + (int64_t)(8 * o + r) * df_sn + c0 + lane + 32 * k] = acc[r][k];
+            }
+    }
+}
+
 // flagged rows (referenced by an impure slot): recomputed whole in fp32, one warp per row
 template <typename T>
 __global__ void __launch_bounds__(WPC * 32)
@@ -608,6 +659,21 @@ static int df_t(const T *d_out, const T *w, const int64_t *idx, T *d_f, const vo
     return 1;
 }
 
+static int df32_t(const float *d_out, const float *w, const int64_t *idx, float *d_f, const void *plan, int B, int Nq, int Nk, int C, int M,
+                  int IC, int64_t df_sb, int64_t df_sn, cudaStream_t st) {
+    if (!plan || IC != 4 || M % 8 || M > 256 || C % 32 || Nq >= (1 << 27)) return 0;
+    const WfPlanView pv = wf_plan_view(const_cast<void *>(plan), B, Nq, M, Nk);
+    const int blocks = C / 32;
+    const int grid = ceil_div((int64_t)B * pv.NO, WPC);
+    if (blocks % 4 == 0) df_oct32_kernel<4><<<grid, WPC * 32, 0, st>>>(d_out, w, pv, d_f, B, Nq, Nk, C, M, df_sb, df_sn);
+    else if (blocks % 3 == 0) df_oct32_kernel<3><<<grid, WPC * 32, 0, st>>>(d_out, w, pv, d_f, B, Nq, Nk, C, M, df_sb, df_sn);
+    else if (blocks % 2 == 0) df_oct32_kernel<2><<<grid, WPC * 32, 0, st>>>(d_out, w, pv, d_f, B, Nq, Nk, C, M, df_sb, df_sn);
+    else df_oct32_kernel<1><<<grid, WPC * 32, 0, st>>>(d_out, w, pv, d_f, B, Nq, Nk, C, M, df_sb, df_sn);
+    df_fix_kernel<float><<<dim3(4, B), WPC * 32, 0, st>>>(d_out, w, idx, pv, d_f, Nq, Nk, C, M, df_sb, df_sn);
+    note_launches(2);
+    return 1;
+}
+
 }  // namespace wf2
 
 int wf2_fwd(const void *w, const void *f, const int64_t *idx, void *out, const void *plan, int B, int Nq, int Nk, int C, int M,
@@ -640,6 +706,8 @@ int wf2_df(const void *d_out, const void *w, const int64_t *idx, void *d_f, cons
         return wf2::df_t<__nv_bfloat16>((const __nv_bfloat16 *)d_out, (const __nv_bfloat16 *)w, idx, (__nv_bfloat16 *)d_f, plan, B, Nq, Nk, C, M, IC, df_sb, df_sn, st);
     if (dtype == CLUSTEN_F16)
         return wf2::df_t<__half>((const __half *)d_out, (const __half *)w, idx, (__half *)d_f, plan, B, Nq, Nk, C, M, IC, df_sb, df_sn, st);
+    if (dtype == CLUSTEN_F32)
+        return wf2::df32_t((const float *)d_out, (const float *)w, idx, (float *)d_f, plan, B, Nq, Nk, C, M, IC, df_sb, df_sn, st);
     return 0;
 }
 

@@ -939,7 +939,9 @@ class CLUSTENWFFunction(Function):
         d_feat = torch.empty((B, Nk, C), dtype=weights.dtype, device=dev)
         if Nq * M == 0 or B == 0:
             return d_weights, d_feat.zero_(), None
-        plan = wf_plan(nbhd_idx, Nk) if weights.element_size() == 2 and IC == 4 and C % 16 == 0 else None
+        # the octet-form d_f kernels (16-bit tensor-core form, fp32 SIMT form) need the plan; fp32 is the AMP merge (clusten.py:80-81)
+        es = weights.element_size()
+        plan = wf_plan(nbhd_idx, Nk) if IC == 4 and ((es == 2 and C % 16 == 0) or (es == 4 and C % 32 == 0)) else None
         off, ent = inverse_neighbour_list(nbhd_idx, Nk, wf_plan_buf=plan)
         with torch.cuda.device(dev):
             _call("clusten_wf_bwd", dev, grad_feat_new.data_ptr(), weights.data_ptr(), feat.data_ptr(),

@@ -151,7 +151,7 @@ def bench_ops(args, log=print):
     out_w = torch.empty(B, Nq, IC, Cw, device="cuda", dtype=dt)
     d_out = torch.randn(B, Nq, IC, Cw, device="cuda", generator=gen).to(dt)
     d_w, d_f = torch.empty_like(w), torch.empty_like(f)
-    plan = ops.wf_plan(idx_w, N) if (s == 2 and not args.generic) else None
+    plan = ops.wf_plan(idx_w, N) if not args.generic else None          # (fp32: only the backward's octet-form d_f uses it)
     pl = 0 if plan is None else plan.data_ptr()
     offw, entw = ops.inverse_neighbour_list(idx_w, N, wf_plan_buf=plan)
     if plan is not None:

@@ -545,7 +545,6 @@ def test_fused_attention_core_backward(n, m, nbhd, kind, H, C, dtype):
 TC_LINEAR = os.environ.get("CLUSTEN_TC_LINEAR") == "1"
 
 
-@pytest.mark.skipif(not TC_LINEAR, reason="opt-in kernel (clusten_linear_f32): set CLUSTEN_TC_LINEAR=1")
 @pytest.mark.parametrize("R,K,N", [(1000, 32, 32), (4173, 128, 256), (300, 96, 288), (129, 768, 2304), (1, 32, 2), (16384, 64, 32)])
 def test_linear_f32_tensor_core(R, K, N):
     """clusten_linear_f32 (3xTF32 split on the tensor cores) against a float64 matmul: fp32-level accuracy, ragged R and N,
@@ -587,7 +586,6 @@ def _pos_bias_case(n, m, nbhd, kind, H, B=2, hw=64):
     return pos.float(), idx, mask, rel_pos_features(uniq), inverse.reshape(B, n, M).to(torch.int32), W, bvec
 
 
-@pytest.mark.skipif(not INKERNEL_BIAS, reason="opt-in round-2 kernels (clusten_attn_pos_*): set CLUSTEN_INKERNEL_BIAS=1")
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("H,C", [(2, 16), (3, 32)])
 @pytest.mark.parametrize("n,m,nbhd,kind", [(1024, 8, 48, "clustered"), (2003, 8, 48, "clustered"), (1540, 24, 144, "clustered"),
@@ -609,7 +607,6 @@ def test_inkernel_bias_forward_matches_table_variant(n, m, nbhd, kind, H, C, dty
     assert rel_err(out.float(), ref.float()) <= (2e-5 if dtype == torch.float32 else 1e-2)
 
 
-@pytest.mark.skipif(not INKERNEL_BIAS, reason="opt-in round-2 kernels (clusten_attn_pos_*): set CLUSTEN_INKERNEL_BIAS=1")
 @pytest.mark.parametrize("H,C", [(2, 32), (4, 16)])
 @pytest.mark.parametrize("n,m,nbhd,kind", [(1024, 8, 48, "clustered"), (2003, 8, 48, "clustered"), (1540, 24, 144, "clustered"),
                                             (300, 8, 48, "random")])
