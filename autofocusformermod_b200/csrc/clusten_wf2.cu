@@ -257,7 +257,8 @@ df_oct32_kernel(const float *__restrict__ dO, const float *__restrict__ W, const
         for (int r = 0; r < 8; ++r)
 #pragma unroll
             for (int k = 0; k < KC; ++k) acc[r][k] = 0.f;
-        for (int e = lo; e < hi; ++e) {
+#pragma unroll 2
+        for (int e = lo; e < hi; ++e) {                      // (two entries per trip: the second one's loads overlap the first one's FMAs)
             const uint32_t v = __ldg(ent + e);
             const int64_t i = v >> 5;
             const float wl = __ldg(Wb + (i * M + 8 * (v & 31u)) * 4 + lane);           // w[i, 8s + lane/4, lane%4]
