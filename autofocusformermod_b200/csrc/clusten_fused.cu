@@ -110,8 +110,10 @@ template <typename T, int CH> __device__ __forceinline__ float f_elem(const FFra
     }
 }
 
+// (3 CTAs of 8 warps per SM: without the bound the rare masked-neighbour path lifts the register count past 85 and costs the
+// common path a third of its resident warps; with it the spills, if any, sit in that rare path)
 template <typename T, int CH, int NT, bool PB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 attn_fused_tile_kernel(const FArgsOf<PB> a, const PackView pk, int smem_per_warp) {
     extern __shared__ __align__(16) unsigned char dyn[];
     if (pk.flags[0]) return;
@@ -267,31 +269,31 @@ attn_fused_tile_kernel(const FArgsOf<PB> a, const PackView pk, int smem_per_warp
                 if (mk) {
                     const uchar4 m4 = *reinterpret_cast<const uchar4 *>(mk + j);
                     if (!(m4.x && m4.y && m4.z && m4.w)) {
-                        // a masked neighbour is a wildcard of the mask-aware pack (its column was scored against whatever row the octet
-                        // holds there); the reference scores it against row idx[b,i,j] and subtracts 100 (aff.py:137), which large logits
-                        // do not turn into nothing: exact logit here, exact value row before phase 3
+                        // masked neighbours: the wildcard column's q.k term (and, PB, its bias) is dropped here; the exact logit
+                        // is added by masked_logit_pass below (fused.cuh)
                         saw_mask = true;
-                        const int64_t *ir = a.idx + ((int64_t)b * Nq + i) * M + j;
-                        auto fix = [&](int64_t kidx, float gtab) {
-                            kidx = min(max(kidx, (int64_t)0), (int64_t)a.Nk - 1);
-                            const T *qr = reinterpret_cast<const T *>(a.q) + b * a.q_sb + h * a.q_sh + (int64_t)i * a.q_sn;
-                            const T *kr = reinterpret_cast<const T *>(a.k) + b * a.k_sb + h * a.k_sh + kidx * a.k_sn;
-                            float sdot = 0.f;
-                            for (int c = 0; c < C; ++c) sdot = fmaf(to_f(qr[c]), to_f(kr[c]), sdot);
-                            if constexpr (PB) gtab = pos_bias(pos_bias_load(a.pe_w, a.pe_b, h), __ldg(reinterpret_cast<const float2 *>(a.pos_q) + (int64_t)b * Nq + i),
-                                                              __ldg(reinterpret_cast<const float2 *>(a.pos_k) + (int64_t)b * a.Nk + kidx));
-                            return sdot + gtab - 100.f;
-                        };
-                        if (!m4.x) x.x = fix(ir[0], g0);
-                        if (!m4.y) x.y = fix(ir[1], g1);
-                        if (!m4.z) x.z = fix(ir[2], g2);
-                        if (!m4.w) x.w = fix(ir[3], g3);
+                        if (!m4.x) x.x = g0;
+                        if (!m4.y) x.y = g1;
+                        if (!m4.z) x.z = g2;
+                        if (!m4.w) x.w = g3;
                     }
                 }
                 *reinterpret_cast<float4 *>(Sr + j) = x;
                 mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
             }
             if (half == 0) mx = fmaxf(mx, Sr[M]);
+        }
+        if (__any_sync(FULL, saw_mask)) {                            // (rare: tiles that touch the padded cluster)
+            __syncwarp();
+            masked_logit_pass<T, PB>(a, b, h, i0, min(TILE_TOK, Nq - i0), impm, S, MP, lane);
+            if (rvalid) {                                            // the row maxima again, now over the exact masked logits
+                mx = -INFINITY;
+                for (int j = j0; j < j1; j += 4) {
+                    const float4 x = *reinterpret_cast<float4 *>(Sr + j);
+                    mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+                }
+                if (half == 0) mx = fmaxf(mx, Sr[M]);
+            }
         }
         mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
         float sum = 0.f;
@@ -319,35 +321,21 @@ attn_fused_tile_kernel(const FArgsOf<PB> a, const PackView pk, int smem_per_warp
     const T *vbase = V;
     const float *Sa = S + g * MP, *Sb = S + (g + 8) * MP;
     if (__any_sync(FULL, saw_mask)) {
-        // masked entries: e_j leaves S (its octet column must not pull in the wildcard row) and enters the accumulators with the row the
-        // reference reads, v[idx[b,i,j]]; the lanes that own the token's row in the mma layout take it
-        const int cnt = min(TILE_TOK, Nq - i0) * M;
-        const uint8_t *mkt = a.mask + ((int64_t)b * Nq + i0) * M;
-        for (int x0 = 0; x0 < cnt; x0 += 32) {
-            unsigned bal = __ballot_sync(FULL, x0 + lane < cnt && !mkt[x0 + lane]);
-            while (bal) {
-                const int x = x0 + __ffs(bal) - 1;
-                bal &= bal - 1;
-                const int row = x / M, j = x - row * M;
-                if ((impm >> row) & 1u) continue;
-                const float e = S[row * MP + j];
-                __syncwarp();
-                if (lane == 0) S[row * MP + j] = 0.f;
-                const int64_t kidx = a.idx[((int64_t)b * Nq + i0 + row) * M + j];
-                const T *vr = reinterpret_cast<const T *>(a.v) + b * a.v_sb + h * a.v_sh + min(max(kidx, (int64_t)0), (int64_t)a.Nk - 1) * a.v_sn + 2 * t;
-                if (g == (row & 7)) {
+        // masked entries: e_j leaves S and enters the accumulators with the row the reference reads, v[idx[b,i,j]] (fused.cuh); the
+        // lanes that own the token's row in the mma layout take it
+        masked_value_pass<T, PB>(a, b, i0, min(TILE_TOK, Nq - i0), impm, S, MP, lane, [&](int row, int64_t kidx, float e) {
+            const T *vr = reinterpret_cast<const T *>(a.v) + b * a.v_sb + h * a.v_sh + kidx * a.v_sn + 2 * t;
+            if (g == (row & 7)) {
 #pragma unroll
-                    for (int n = 0; n < NT; ++n) {
-                        if (8 * n + 2 * t < C) {
-                            const float v0 = e * to_f(vr[8 * n]), v1 = e * to_f(vr[8 * n + 1]);
-                            if (row < 8) { acc[n][0] += v0; acc[n][1] += v1; }
-                            else { acc[n][2] += v0; acc[n][3] += v1; }
-                        }
+                for (int n = 0; n < NT; ++n) {
+                    if (8 * n + 2 * t < C) {
+                        const float v0 = e * to_f(vr[8 * n]), v1 = e * to_f(vr[8 * n + 1]);
+                        if (row < 8) { acc[n][0] += v0; acc[n][1] += v1; }
+                        else { acc[n][2] += v0; acc[n][3] += v1; }
                     }
                 }
             }
-        }
-        __syncwarp();
+        });
     }
     if constexpr (!F32) {
         constexpr int ROWB = NT * 16 + 16, CPL = NT / 2;

@@ -115,12 +115,6 @@ __device__ __forceinline__ void sts_f2_if(uint32_t s, float a, float b, int slot
 }
 __device__ __forceinline__ int s8(uint32_t w, int byte) { return (int)(int8_t)(w >> (8 * byte)); }
 
-template <typename T> __device__ __noinline__ float row_dot(const T *x, const T *y, int C) {      // (rare path: masked neighbours)
-    float s = 0.f;
-    for (int c = 0; c < C; ++c) s = fmaf(to_f(x[c]), to_f(y[c]), s);
-    return s;
-}
-
 // 16 x 8 logits of the warp's tokens against one staged K octet
 template <typename T, int C, bool PACKED>
 __device__ __forceinline__ void qk_octet(float (&acc)[4], const uint32_t (&qa)[sizeof(T) == 4 ? C / 8 : C / 16][4],
@@ -421,11 +415,6 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
     // row idx[b,i,j] (= 0 for the padded tail of the last cluster, point_utils.py:283), and with large logits exp(. - 100) is not
     // nothing: such entries (a few tokens per sample) get their exact logit here and their exact value row before phase 3.
     bool saw_mask = false;
-    auto masked_logit = [&](int row, int64_t kidx) {
-        const T *qr = reinterpret_cast<const T *>(a.q) + b * a.q_sb + h * a.q_sh + (int64_t)(i0 + row) * a.q_sn;
-        const T *kr = reinterpret_cast<const T *>(a.k) + b * a.k_sb + h * a.k_sh + min(max(kidx, (int64_t)0), (int64_t)a.Nk - 1) * a.k_sn;
-        return row_dot<T>(qr, kr, C) - 100.f;
-    };
     if (active) {
         const int rows = min(TILE_TOK, Nq - i0), QM = M >> 2;
         const uint8_t *mk = a.mask ? a.mask + ((int64_t)b * Nq + i0) * M : nullptr;
@@ -437,12 +426,11 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                 float4 x = *reinterpret_cast<float4 *>(S + row * MP + j);
                 x.x += gq.x; x.y += gq.y; x.z += gq.z; x.w += gq.w;
                 if (m4 != 0x01010101u && ((m4 & 0xffu) == 0 || (m4 & 0xff00u) == 0 || (m4 & 0xff0000u) == 0 || (m4 >> 24) == 0)) {
-                    saw_mask = true;
-                    const int64_t *ir = a.idx + ((int64_t)b * Nq + i0 + row) * M + j;
-                    if (!(m4 & 0xffu)) x.x = masked_logit(row, ir[0]) + gq.x;
-                    if (!(m4 & 0xff00u)) x.y = masked_logit(row, ir[1]) + gq.y;
-                    if (!(m4 & 0xff0000u)) x.z = masked_logit(row, ir[2]) + gq.z;
-                    if (!(m4 >> 24)) x.w = masked_logit(row, ir[3]) + gq.w;
+                    saw_mask = true;                                 // wildcard column: keep the bias only; masked_logit_pass adds the rest
+                    if (!(m4 & 0xffu)) x.x = gq.x;
+                    if (!(m4 & 0xff00u)) x.y = gq.y;
+                    if (!(m4 & 0xff0000u)) x.z = gq.z;
+                    if (!(m4 >> 24)) x.w = gq.w;
                 }
                 *reinterpret_cast<float4 *>(S + row * MP + j) = x;
             };
@@ -473,11 +461,11 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
                 if (mk) {
                     const uchar4 m4 = __ldg(reinterpret_cast<const uchar4 *>(mk) + e);
                     if (!(m4.x && m4.y && m4.z && m4.w)) {
-                        saw_mask = true;
-                        if (!m4.x) x.x = masked_logit(row, i01.x) + g0;
-                        if (!m4.y) x.y = masked_logit(row, i01.y) + g1;
-                        if (!m4.z) x.z = masked_logit(row, i23.x) + g2;
-                        if (!m4.w) x.w = masked_logit(row, i23.y) + g3;
+                        saw_mask = true;                             // (PB: masked_logit_pass adds the key row's bias too)
+                        if (!m4.x) x.x = 0.f;
+                        if (!m4.y) x.y = 0.f;
+                        if (!m4.z) x.z = 0.f;
+                        if (!m4.w) x.w = 0.f;
                     }
                 }
                 *reinterpret_cast<float4 *>(S + row * MP + j) = x;
@@ -485,6 +473,8 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
         }
     }
     __syncwarp();
+    const bool any_mask = __any_sync(FULL, saw_mask);
+    if (any_mask) masked_logit_pass<T, PB>(a, b, h, i0, min(TILE_TOK, Nq - i0), impm, S, MP, lane);
     // ---- phase 2b: softmax over M + 1 logits, two lanes per token row; e_j stay unnormalised in S ---------------------------------
     if (active) {
         constexpr float LOG2E = 1.4426950408889634f;
@@ -524,35 +514,19 @@ attn_fused_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_con
     float acc[NT][4];
 #pragma unroll
     for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-    if (__any_sync(FULL, saw_mask)) {
-        // masked entries: e_j leaves S (its octet column must not pull in the wildcard row) and enters the accumulators with the row
-        // the reference reads, v[idx[b,i,j]]; the lanes that own the token's row in the mma layout take it
-        const int cnt = min(TILE_TOK, Nq - i0) * M;
-        const uint8_t *mk = a.mask + ((int64_t)b * Nq + i0) * M;
-        const T *Vb = reinterpret_cast<const T *>(a.v) + b * a.v_sb + h * a.v_sh;
-        for (int x0 = 0; x0 < cnt; x0 += 32) {
-            unsigned bal = __ballot_sync(FULL, x0 + lane < cnt && !mk[x0 + lane]);
-            while (bal) {
-                const int x = x0 + __ffs(bal) - 1;
-                bal &= bal - 1;
-                const int row = x / M, j = x - row * M;
-                if ((impm >> row) & 1u) continue;
-                const float e = S[row * MP + j];
-                __syncwarp();
-                if (lane == 0) S[row * MP + j] = 0.f;
-                const int64_t kidx = a.idx[((int64_t)b * Nq + i0 + row) * M + j];
-                const T *vr = Vb + min(max(kidx, (int64_t)0), (int64_t)a.Nk - 1) * a.v_sn + 2 * t;
-                if (g == (row & 7)) {
+    if (any_mask) {
+        // masked entries: e_j leaves S and enters the accumulators with the row the reference reads, v[idx[b,i,j]] (fused.cuh)
+        masked_value_pass<T, PB>(a, b, i0, min(TILE_TOK, Nq - i0), impm, S, MP, lane, [&](int row, int64_t kidx, float e) {
+            const T *vr = reinterpret_cast<const T *>(a.v) + b * a.v_sb + h * a.v_sh + kidx * a.v_sn + 2 * t;
+            if (g == (row & 7)) {
 #pragma unroll
-                    for (int n = 0; n < NT; ++n) {
-                        const float v0 = e * to_f(vr[8 * n]), v1 = e * to_f(vr[8 * n + 1]);
-                        if (row < 8) { acc[n][0] += v0; acc[n][1] += v1; }
-                        else { acc[n][2] += v0; acc[n][3] += v1; }
-                    }
+                for (int n = 0; n < NT; ++n) {
+                    const float v0 = e * to_f(vr[8 * n]), v1 = e * to_f(vr[8 * n + 1]);
+                    if (row < 8) { acc[n][0] += v0; acc[n][1] += v1; }
+                    else { acc[n][2] += v0; acc[n][3] += v1; }
                 }
             }
-        }
-        __syncwarp();
+        });
     }
     if (rounds == 1) {
         int wmax = PACKED ? NBAR_MAX : -1;                 // (packed: every octet of the union was waited for in phase 1)
