@@ -20,6 +20,8 @@ Differences from the reference that a caller can observe, all deliberate:
     contiguous [B,H,N,C] result.
 There is no CPU path: non-CUDA operands raise RuntimeError, like CHECK_CUDA in clustenqk_cuda.cpp:21.
 """
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -809,6 +811,66 @@ def linear_f32(x, weight, bias=None):
     with torch.cuda.device(dev):
         _call("clusten_linear_f32", dev, x2.data_ptr(), w.data_ptr(), _lib.ptr(b), y.data_ptr(), x2.shape[0], K, N, x2.stride(0), N,
               nbytes=4 * (x2.shape[0] * (K + N) + N * K))
+    return y.view(*x.shape[:-1], N)
+
+
+# ---- fp32 Linear on tcgen05 (3xTF32) with the following element-wise line folded in ----------------------------------------------
+LINEAR_EPI = {"bias": 0, "gelu": 1, "residual": 2}
+_split_cache = {}                                      # id(weight) -> (weakref, version, data_ptr, hi, lo)
+LINEAR_TC_CHAIN = int(os.environ.get("CLUSTEN_TC_CHAIN", "0"))
+
+
+def tf32_split(weight):
+    """(hi, lo) of an fp32 weight for clusten_linear_tc_f32 (clusten_tf32_split), cached until the weight changes."""
+    import weakref
+    key = id(weight)
+    hit = _split_cache.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
+        return hit[3], hit[4]
+    dev = _lib.require_cuda(weight)
+    w = weight.detach().contiguous()
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    with torch.cuda.device(dev):
+        _call("clusten_tf32_split", dev, w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), nbytes=12 * w.numel())
+    if len(_split_cache) > 4096:
+        _split_cache.clear()
+    _split_cache[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), hi, lo)
+    return hi, lo
+
+
+def linear_tc_supported(x, weight, bias=None, res=None, gamma=None):
+    K = x.shape[-1]
+    ok = (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.dim() == 2 and weight.shape[1] == K
+          and K % 32 == 0 and weight.shape[0] % 4 == 0 and x.numel() > 0 and x.numel() // K < 2 ** 31 - 128)
+    for t in (bias, res, gamma):
+        ok = ok and (t is None or (t.dtype == torch.float32 and t.is_cuda))
+    return bool(ok)
+
+
+def linear_tc(x, weight, bias=None, epilogue="bias", res=None, gamma=None, alpha=1.0, alpha_cols=0, chain=None):
+    """fp32 ``F.linear`` on the tcgen05 tensor cores (clusten_linear_tc_f32; inference, no autograd) with one of
+    ``bias`` (y = x W^T + b, the first ``alpha_cols`` columns then times ``alpha``), ``gelu`` (y = GELU(x W^T + b)) or
+    ``residual`` (y = res + gamma * (x W^T + b)) as the epilogue.  The caller checks ``linear_tc_supported`` first."""
+    dev = _lib.require_cuda(x, weight, bias, res, gamma)
+    K, N = x.shape[-1], weight.shape[0]
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1 or x2.stride(0) % 4 or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    hi, lo = tf32_split(weight)
+    b = None if bias is None else bias.detach().contiguous()
+    g = None if gamma is None else gamma.detach().contiguous()
+    R = x2.shape[0]
+    r2, ldres = None, 0
+    if epilogue == "residual":
+        r2 = res.reshape(-1, N)
+        if r2.stride(1) != 1 or r2.stride(0) % 4 or r2.data_ptr() % 16:
+            r2 = r2.contiguous()
+        ldres = r2.stride(0)
+    y = torch.empty((R, N), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call("clusten_linear_tc_f32", dev, x2.data_ptr(), hi.data_ptr(), lo.data_ptr(), _lib.ptr(b), _lib.ptr(r2), _lib.ptr(g),
+              y.data_ptr(), R, K, N, x2.stride(0), N, ldres, LINEAR_EPI[epilogue], float(alpha), int(alpha_cols),
+              LINEAR_TC_CHAIN if chain is None else int(chain), nbytes=4 * (R * (K + N * (2 if r2 is not None else 1)) + 2 * N * K))
     return y.view(*x.shape[:-1], N)
 
 

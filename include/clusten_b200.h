@@ -240,6 +240,22 @@ int clusten_table_linear_bwd(const float *d_out, const float *feat, float *d_wei
 int clusten_linear_f32(const float *x, const float *weight, const float *bias, float *y, int64_t R, int K, int N,
                        int64_t ldx, int64_t ldy, void *stream);
 
+/* ---- fp32 Linear layer on the 5th-generation tensor cores (tcgen05.mma kind::tf32 with TMEM accumulators, TMA-fed, one persistent
+ * CTA per SM; 3xTF32 split, fp32-level accuracy): y = epilogue(x . weight^T + bias) -- the q / kv / proj / fc1 / fc2 layers of the
+ * block (backbone/aff.py:62-70,103-106,181-189) and the merge Linear (aff.py:282) in fp32 inference, with the element-wise line that
+ * follows each of them in the reference folded into the epilogue:
+ *   epi 0   y = acc + bias, columns < alpha_cols then multiplied by alpha     (`q = self.q(feat) * self.scale`, aff.py:107-108)
+ *   epi 1   y = GELU(acc + bias), exact erf form                               (`self.act(self.fc1(x))`, aff.py:45-46)
+ *   epi 2   y = res + gamma * (acc + bias), gamma [N] or NULL (= 1)            (`x = shortcut + gamma * x`, aff.py:230,236)
+ * clusten_tf32_split writes the two weight operands once per weight: hi = w rounded to TF32, lo = (w - hi) rounded to TF32.
+ * x [R,K] row stride ldx, w_hi / w_lo [N,K] contiguous, y [R,N] row stride ldy, res [R,N] row stride ldres; K % 32 == 0,
+ * N % 4 == 0, 16-byte aligned rows (else CLUSTEN_EUNSUPPORTED).  chain: K chunks of 32 summed inside one tensor-memory
+ * accumulator before it is added to the fp32 running sum in registers (<= 0: default). */
+int clusten_tf32_split(const float *w, float *hi, float *lo, int64_t n, void *stream);
+int clusten_linear_tc_f32(const float *x, const float *w_hi, const float *w_lo, const float *bias, const float *res,
+                          const float *gamma, float *y, int64_t R, int K, int N, int64_t ldx, int64_t ldy, int64_t ldres,
+                          int epi, float alpha, int alpha_cols, int chain, void *stream);
+
 /* ---- column sum: out[c] += sum_r x[r*ld + c] (fp32 accumulation INTO out; caller zeroes it).  The bias gradient of the
  * backbone's Linear layers (grad_bias = grad_output.sum(0)); x fp32 / fp16 / bf16, C and ld multiples of 16 bytes. */
 int clusten_col_sum(const void *x, float *out, int64_t R, int C, int64_t ld, int dtype, void *stream);
