@@ -25,7 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .ops import (CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction, cluster_attention_core, cluster_attention_fused,
-                  cluster_attention_core_pos, cluster_attention_fused_pos, layer_norm, linear, linear_f32, linear_f32_supported,
+                  cluster_attention_core_pos, cluster_attention_fused_pos, layer_norm, linear, linear_f32, linear_f32_supported, linear_tc, linear_tc_supported,
                   scale_residual, table_linear,
                   table_linear_supported, table_lookup)
 from .point_utils import knn_keops, merge_select, space_filling_cluster, stage_prepare
@@ -62,8 +62,16 @@ FUSED_RESIDUAL = _on("CLUSTEN_FUSED_RESIDUAL")
 NATIVE_WEIGHT_NET_NORM = _on("CLUSTEN_WEIGHT_NET_NORM")
 # opt-in: relative-position bias computed from positions inside the fused attention kernels (clusten_attn_pos_*)
 INKERNEL_BIAS = _opt_in("CLUSTEN_INKERNEL_BIAS")
-# opt-in: fp32 inference Linear layers on the tensor cores with the 3xTF32 split (clusten_linear_f32) instead of cuBLAS SIMT sgemm
+# opt-in: fp32 inference Linear layers through the round-1 mma.sync kernel (clusten_linear_f32); superseded by TCGEN05_LINEAR
 TC_LINEAR = _opt_in("CLUSTEN_TC_LINEAR")
+# fp32 inference Linear layers on tcgen05 (clusten_linear_tc_f32: TMA + TMEM, 3xTF32 split) with the element-wise line that follows
+# them in the block folded into the epilogue (q * scale, GELU, shortcut + gamma * x).  CLUSTEN_TCGEN05_LINEAR=0: cuBLAS.
+TCGEN05_LINEAR = os.environ.get("CLUSTEN_TCGEN05_LINEAR", "1") != "0"
+
+
+def _tcgen05_ok(x):
+    return (TCGEN05_LINEAR and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
+            and not torch.is_autocast_enabled())
 # opt-in: under autocast the merge's WF runs in the autocast dtype (tensor-core kernels) instead of fp32 like the reference under
 # AMP, whose CLUSTENWF casts feat up to the fp32 weights (clusten.py:80-81)
 MERGE_WF_AUTOCAST = _opt_in("CLUSTEN_MERGE_WF_AUTOCAST")
@@ -152,10 +160,26 @@ class Linear(nn.Linear):
     def forward(self, x):
         if FAST_LINEAR_BACKWARD and x.is_cuda and torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
             return linear(x, self.weight, self.bias)
+        if _tcgen05_ok(x) and linear_tc_supported(x, self.weight, self.bias):
+            return linear_tc(x, self.weight, self.bias)
         if (TC_LINEAR and not torch.is_grad_enabled() and not torch.is_autocast_enabled()
                 and linear_f32_supported(x, self.weight, self.bias)):
             return linear_f32(x, self.weight, self.bias)
         return F.linear(x, self.weight, self.bias)
+
+    def fused(self, x, epilogue, res=None, gamma=None, alpha=1.0, alpha_cols=0):
+        """The layer plus the element-wise line after it -- ``bias`` (the first ``alpha_cols`` outputs then times ``alpha``), ``gelu``
+        or ``residual`` (res + gamma * y) -- in one tcgen05 kernel when the operands allow, else the same arithmetic in torch."""
+        if _tcgen05_ok(x) and linear_tc_supported(x, self.weight, self.bias, res, gamma):
+            return linear_tc(x, self.weight, self.bias, epilogue, res=res, gamma=gamma, alpha=alpha, alpha_cols=alpha_cols)
+        y = self.forward(x)
+        if epilogue == "gelu":
+            return F.gelu(y)
+        if epilogue == "residual":
+            return res + (y if gamma is None else gamma * y)
+        if alpha_cols:
+            y[..., :alpha_cols] *= alpha
+        return y
 
 
 class TableLinear(nn.Linear):
@@ -202,7 +226,15 @@ class Mlp(nn.Module):
         self.fc2 = Linear(hidden_features or in_features, out_features or in_features)
         self.drop = nn.Dropout(drop)
 
-    def forward(self, x):
+    def forward(self, x, residual=None):
+        """``residual`` = (shortcut, gamma or None): return shortcut + gamma * mlp(x) (the caller has checked that nothing random
+        sits in between)."""
+        if residual is not None or (_tcgen05_ok(x) and isinstance(self.act, nn.GELU) and self.act.approximate == "none"
+                                    and (self.drop.p == 0.0 or not self.training)):
+            hidden = self.fc1.fused(x, "gelu") if isinstance(self.act, nn.GELU) and self.act.approximate == "none" else self.act(self.fc1(x))
+            if residual is not None:
+                return self.fc2.fused(hidden, "residual", res=residual[0], gamma=residual[1])
+            return self.fc2(hidden)
         return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
 
 
@@ -224,11 +256,19 @@ class ClusterAttention(nn.Module):
         self.proj = Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
 
-    def forward(self, feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup=None, fused_ctx=None):
+    def _project(self, out, residual):
+        if residual is not None:
+            return self.proj.fused(out, "residual", res=residual[0], gamma=residual[1])
+        return self.proj_drop(self.proj(out))
+
+    def forward(self, feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup=None, fused_ctx=None, residual=None):
         b, n, c = feat.shape
         h = self.num_heads
         c_ = c // h
-        q_tok = (self.q(feat) * self.scale).reshape(b, n, h, c_)                         # token-major b n h c_
+        if _tcgen05_ok(feat):
+            q_tok = self.q.fused(feat, "bias", alpha=self.scale, alpha_cols=c).reshape(b, n, h, c_)
+        else:
+            q_tok = (self.q(feat) * self.scale).reshape(b, n, h, c_)                     # token-major b n h c_
         kv_tok = self.kv(feat).view(b, n, h, 2, c_)
         fusable = (fused_ctx is not None and not global_attn and USE_FUSED_ATTENTION
                    and (self.attn_drop.p == 0.0 or not self.training))
@@ -241,7 +281,7 @@ class ClusterAttention(nn.Module):
             else:
                 out = cluster_attention_core(q_tok, kv_tok, self.pos_embed(pe_lookup.features, pe_lookup.count), self.blank_k,
                                              self.blank_v, member_idx, bias_idx, mask_u8, pe_lookup.count)
-            return self.proj_drop(self.proj(out))
+            return self._project(out, residual)
         q = q_tok.permute(0, 2, 1, 3)                                                    # b h n c_ (view)
         kv = kv_tok.permute(3, 0, 2, 1, 4)                                               # 2 b h n c_ (view)
         key, v = kv[0], kv[1]
@@ -254,7 +294,7 @@ class ClusterAttention(nn.Module):
             else:
                 out = cluster_attention_fused(q, key, v, member_idx, self.pos_embed(pe_lookup.features, pe_lookup.count), bias_idx,
                                               mask_u8, self.blank_k, self.blank_v)       # aff.py:114-155 in one kernel
-            return self.proj_drop(self.proj(out))
+            return self._project(out, residual)
         if global_attn:
             attn = q @ key.transpose(-1, -2)                                             # aff.py:121
             mask = None
@@ -276,7 +316,7 @@ class ClusterAttention(nn.Module):
         else:
             out = CLUSTENAVFunction.apply(attn, v, member_idx)                           # aff.py:154
         out = (out + blank_v).permute(0, 2, 1, 3).reshape(b, n, c)
-        return self.proj_drop(self.proj(out))
+        return self._project(out, residual)
 
 
 class ClusterTransformerBlock(nn.Module):
@@ -298,6 +338,12 @@ class ClusterTransformerBlock(nn.Module):
             self.gamma2 = nn.Parameter(layer_scale * torch.ones(dim), requires_grad=True)
 
     def forward(self, feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup=None, fused_ctx=None):
+        if (_tcgen05_ok(feat) and (not self.training or (isinstance(self.drop_path, nn.Identity) and self.attn.proj_drop.p == 0.0
+                                                          and self.mlp.drop.p == 0.0))):
+            # inference, fp32: both residual lines ride in the epilogue of the Linear before them
+            feat = self.attn(self.norm1(feat), member_idx, cluster_mask, pe_idx, global_attn, pe_lookup, fused_ctx,
+                             residual=(feat, self.gamma1 if self.layer_scale else None))
+            return self.mlp(self.norm2(feat), residual=(feat, self.gamma2 if self.layer_scale else None))
         a = self.attn(self.norm1(feat), member_idx, cluster_mask, pe_idx, global_attn, pe_lookup, fused_ctx)
         feat = self._residual(feat, a, self.gamma1 if self.layer_scale else None)                    # aff.py:230
         m = self.mlp(self.norm2(feat))

@@ -79,23 +79,48 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 // round to TF32 (nearest, ties away -- cvt.rna) on the bit pattern: the low 13 mantissa bits end up zero
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+                 "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+                   "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+                   "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+                   "r"(v[30]), "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }     // the four epilogue warps
+// byte offset of 16-byte chunk c of row r inside a [rows x 128 B] box written / read by the TMA unit with SWIZZLE_128B
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+constexpr int NA = 4;                                  // A-operand stages in tensor memory (64 columns each: xh | xl)
+constexpr int A_COL0 = 256;                            // tensor-memory columns 0..255: the two accumulators, 256..511: the A ring
+constexpr int SUB_BYTES = BM * 128;                    // one [128 rows x 32 columns] piece of the output tile, 16 KiB
+
 template <int BN> struct Cfg {
     static constexpr int B_BYTES = BN * BK * 4;
-    static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;              // xh | xl | wh | wl
+    static constexpr int STAGE = A_BYTES + 2 * B_BYTES;                  // x | wh | wl
     static constexpr int STAGES = BN >= 96 ? 3 : 4;
+    static constexpr int NSUB = BN / 32;                                 // output pieces per tile
+    static constexpr int CSETS = BN >= 128 ? 1 : 2;                      // tile-sized output staging sets
     static constexpr int ACC_COLS = BN == 96 ? 128 : BN;                 // column pitch of the two accumulators
-    static constexpr int TMEM_COLS = 2 * ACC_COLS;                       // a power of two >= 32
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE + 1024 /* alignment slack */ + 256 /* barriers */;
+    static constexpr int RING = STAGES * STAGE, CBUF = CSETS * NSUB * SUB_BYTES;
+    static constexpr int TAIL = 2048;                                    // barriers, TMEM slot, bias / gamma of the tile
+    static constexpr size_t SMEM = (size_t)RING + CBUF + TAIL + 1024 /* alignment slack */;
 };
 
 enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_RES = 2 };
 
 struct Args {
-    const float *bias, *res, *gamma;
-    float *y;
+    const float *bias, *gamma;
     int R, K, N;
-    int64_t ldy, ldres;
     int tiles_m, tiles_n, chain;
     float alpha;
     int alpha_cols;
@@ -104,31 +129,42 @@ struct Args {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWh,
-                 const __grid_constant__ CUtensorMap mapWl, const Args a) {
+                 const __grid_constant__ CUtensorMap mapWl, const __grid_constant__ CUtensorMap mapY,
+                 const __grid_constant__ CUtensorMap mapRes, const Args a) {
     using C = Cfg<BN>;
+    constexpr int S = C::STAGES;
     extern __shared__ uint8_t tc_smem_raw[];
     const uint32_t base = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
     uint8_t *gbase = tc_smem_raw + (base - smem_u32(tc_smem_raw));
-    const uint32_t bars = base + C::STAGES * C::STAGE;                   // 8-byte barriers
-    const uint32_t bar_full = bars, bar_conv = bars + 8 * C::STAGES, bar_empty = bars + 16 * C::STAGES;
-    const uint32_t bar_accf = bars + 24 * C::STAGES, bar_acce = bar_accf + 16;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gbase + C::STAGES * C::STAGE + 24 * C::STAGES + 32);
+    const uint32_t cbuf = base + C::RING, tail = cbuf + C::CBUF;
+    const uint32_t bar_xfull = tail, bar_xempty = tail + 8 * S, bar_wfull = tail + 16 * S, bar_wempty = tail + 24 * S;
+    const uint32_t bar_afull = tail + 32 * S, bar_aempty = bar_afull + 8 * NA, bar_accf = bar_aempty + 8 * NA, bar_acce = bar_accf + 16;
+    const uint32_t bar_cfull = bar_acce + 16;                            // CSETS * NSUB barriers
+    uint8_t *gtail = gbase + C::RING + C::CBUF;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gtail + 512);
+    float *s_bias = reinterpret_cast<float *>(gtail + 1024), *s_gamma = s_bias + 128;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_conv + 8 * s, 128);
-            mbar_init(bar_empty + 8 * s, 1);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bar_xfull + 8 * s, 1);
+            mbar_init(bar_xempty + 8 * s, 128);
+            mbar_init(bar_wfull + 8 * s, 1);
+            mbar_init(bar_wempty + 8 * s, 1);
+        }
+        for (int s = 0; s < NA; ++s) {
+            mbar_init(bar_afull + 8 * s, 128);
+            mbar_init(bar_aempty + 8 * s, 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_accf + 8 * b, 1);
             mbar_init(bar_acce + 8 * b, 128);
         }
+        for (int j = 0; j < C::CSETS * C::NSUB; ++j) mbar_init(bar_cfull + 8 * j, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -145,13 +181,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
                 const int m0 = (t / a.tiles_n) * BM, n0 = (t % a.tiles_n) * BN;
                 for (int kc = 0; kc < KC; ++kc, ++it) {
-                    const uint32_t s = it % C::STAGES, ph = (it / C::STAGES) & 1u;
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                    const uint32_t st = base + s * C::STAGE, full = bar_full + 8 * s;
-                    mbar_expect_tx(full, A_BYTES + 2 * C::B_BYTES);
-                    tma_box_2d(st, &mapX, full, kc * BK, m0);
-                    tma_box_2d(st + 2 * A_BYTES, &mapWh, full, kc * BK, n0);
-                    tma_box_2d(st + 2 * A_BYTES + C::B_BYTES, &mapWl, full, kc * BK, n0);
+                    const uint32_t s = it % S, ph = (it / S) & 1u;
+                    const uint32_t st = base + s * C::STAGE;
+                    mbar_wait(bar_xempty + 8 * s, ph ^ 1u);
+                    mbar_expect_tx(bar_xfull + 8 * s, A_BYTES);
+                    tma_box_2d(st, &mapX, bar_xfull + 8 * s, kc * BK, m0);
+                    mbar_wait(bar_wempty + 8 * s, ph ^ 1u);
+                    mbar_expect_tx(bar_wfull + 8 * s, 2 * C::B_BYTES);
+                    tma_box_2d(st + A_BYTES, &mapWh, bar_wfull + 8 * s, kc * BK, n0);
+                    tma_box_2d(st + A_BYTES + C::B_BYTES, &mapWl, bar_wfull + 8 * s, kc * BK, n0);
                 }
             }
         }
@@ -160,26 +198,26 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             uint32_t it = 0, ch = 0;
             for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
                 for (int kc = 0; kc < KC; ++kc, ++it) {
-                    const uint32_t s = it % C::STAGES, ph = (it / C::STAGES) & 1u;
+                    const uint32_t s = it % S, ph = (it / S) & 1u, sa = it % NA, pa = (it / NA) & 1u;
                     const uint32_t buf = ch & 1u;
                     const bool first = kc % chain == 0, last = (kc + 1) % chain == 0 || kc + 1 == KC;
-                    if (first) {
-                        mbar_wait(bar_acce + 8 * buf, ((ch >> 1) & 1u) ^ 1u);     // the epilogue has drained this accumulator
-                    }
-                    mbar_wait(bar_conv + 8 * s, ph);
+                    if (first) mbar_wait(bar_acce + 8 * buf, ((ch >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
+                    mbar_wait(bar_wfull + 8 * s, ph);
+                    mbar_wait(bar_afull + 8 * sa, pa);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = base + s * C::STAGE;
-                    const uint64_t xh = umma_desc(st), xl = umma_desc(st + A_BYTES);
-                    const uint64_t wh = umma_desc(st + 2 * A_BYTES), wl = umma_desc(st + 2 * A_BYTES + C::B_BYTES);
+                    const uint64_t wh = umma_desc(st + A_BYTES), wl = umma_desc(st + A_BYTES + C::B_BYTES);
+                    const uint32_t xh = tmem + A_COL0 + sa * 64, xl = xh + 32;
                     const uint32_t d = tmem + buf * C::ACC_COLS;
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k)                     // one K = 8 step is 32 bytes: +2 in the address field
-                        umma_tf32(d, xl + 2 * k, wh + 2 * k, C::IDESC, (first && k == 0) ? 0u : 1u);
+                    for (int k = 0; k < BK / 8; ++k)                     // one K = 8 step: 8 TMEM columns of A, 32 bytes (+2) of B
+                        umma_tf32_ts(d, xl + 8 * k, wh + 2 * k, C::IDESC, (first && k == 0) ? 0u : 1u);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) umma_tf32(d, xh + 2 * k, wl + 2 * k, C::IDESC, 1u);
+                    for (int k = 0; k < BK / 8; ++k) umma_tf32_ts(d, xh + 8 * k, wl + 2 * k, C::IDESC, 1u);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) umma_tf32(d, xh + 2 * k, wh + 2 * k, C::IDESC, 1u);
-                    umma_commit(bar_empty + 8 * s);                      // the ring slot is free once these MMAs have read it
+                    for (int k = 0; k < BK / 8; ++k) umma_tf32_ts(d, xh + 8 * k, wh + 2 * k, C::IDESC, 1u);
+                    umma_commit(bar_wempty + 8 * s);                     // both rings are free once these MMAs have read them
+                    umma_commit(bar_aempty + 8 * sa);
                     if (last) {
                         umma_commit(bar_accf + 8 * buf);
                         ++ch;
@@ -187,44 +225,70 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 }
             }
         }
-    } else if (warp < 6) {                                               // ---- split x -> (xh, xl) in place ----
-        const int c = threadIdx.x - 64;                                  // 0..127
+    } else if (warp < 6) {                                               // ---- split x -> (xh, xl), row per thread, into TMEM ----
+        const int q = warp & 3, row = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         uint32_t it = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
             for (int kc = 0; kc < KC; ++kc, ++it) {
-                const uint32_t s = it % C::STAGES, ph = (it / C::STAGES) & 1u;
-                mbar_wait(bar_full + 8 * s, ph);
-                float4 *xh = reinterpret_cast<float4 *>(gbase + s * C::STAGE), *xl = xh + A_BYTES / 16;
+                const uint32_t s = it % S, ph = (it / S) & 1u, sa = it % NA, pa = (it / NA) & 1u;
+                mbar_wait(bar_xfull + 8 * s, ph);
+                const uint8_t *xs = gbase + s * C::STAGE;
+                float4 x[8];
 #pragma unroll
-                for (int j = 0; j < A_BYTES / 16 / 128; ++j) {
-                    const float4 v = xh[c + 128 * j];
-                    float4 h, l;
-                    h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
-                    h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
-                    h.z = tf32_rn(v.z); l.z = tf32_rn(v.z - h.z);
-                    h.w = tf32_rn(v.w); l.w = tf32_rn(v.w - h.w);
-                    xh[c + 128 * j] = h;
-                    xl[c + 128 * j] = l;
+                for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4 *>(xs + swz(row, c));
+                uint32_t h[32], l[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float xv[4] = {x[c].x, x[c].y, x[c].z, x[c].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float hv = tf32_rn(xv[e]);
+                        h[4 * c + e] = __float_as_uint(hv);
+                        l[4 * c + e] = __float_as_uint(tf32_rn(xv[e] - hv));
+                    }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
-                mbar_arrive(bar_conv + 8 * s);
+                mbar_arrive(bar_xempty + 8 * s);                         // the landing slot has been read
+                mbar_wait(bar_aempty + 8 * sa, pa ^ 1u);                 // the MMAs of NA chunks ago are done with this A stage
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ta = tmem + lane_off + A_COL0 + sa * 64;
+                tmem_st32(ta, h);
+                tmem_st32(ta + 32, l);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(bar_afull + 8 * sa);
             }
         }
     } else {                                                             // ---- drain + epilogue ----
-        const int q = warp & 3, row = q * 32 + lane;                     // TMEM lane quadrant of this warp
-        uint32_t ch = 0;
+        const int q = warp & 3, row = q * 32 + lane, et = threadIdx.x - 192;          // et: 0..127
+        const bool elected = et == 0;
+        uint32_t ch = 0, nt = 0;                                         // chains, tiles of this CTA so far
         float acc[BN];
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-            const int m0 = (t / a.tiles_n) * BM, n0 = (t % a.tiles_n) * BN;
-            const int64_t r = (int64_t)m0 + row;
-            const float *__restrict__ rr = EPI == EPI_RES ? a.res + r * a.ldres + n0 : nullptr;
-            constexpr int G4 = BN >= 128 ? 2 : BN >= 96 ? 4 : 8;                               // float4 per thread and column group
-            constexpr bool PRE = EPI == EPI_RES && BN <= 64;             // the first 32 residual columns are fetched ahead of the MMAs
-            float4 pre[8];
-            if (PRE && r < a.R) {
+        if (EPI == EPI_RES && elected && (int)blockIdx.x < tiles) {      // residual pieces of the first tile
+            const int m0 = (blockIdx.x / a.tiles_n) * BM, n0 = (blockIdx.x % a.tiles_n) * BN;
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    pre[i] = n0 + 4 * i < a.N ? __ldg(reinterpret_cast<const float4 *>(rr + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < C::NSUB; ++j) {
+                mbar_expect_tx(bar_cfull + 8 * j, SUB_BYTES);
+                tma_box_2d(cbuf + j * SUB_BYTES, &mapRes, bar_cfull + 8 * j, n0 + 32 * j, m0);
+            }
+        }
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++nt) {
+            const int m0 = (t / a.tiles_n) * BM, n0 = (t % a.tiles_n) * BN;
+            const uint32_t set = C::CSETS == 2 ? (nt & 1u) : 0u;
+            if (EPI == EPI_RES && C::CSETS == 1 && nt > 0 && elected) {
+                // one staging set: the residual pieces of this tile go in as soon as the previous tile's stores have read it, and
+                // arrive while the MMAs of this tile run
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < C::NSUB; ++j) {
+                    mbar_expect_tx(bar_cfull + 8 * j, SUB_BYTES);
+                    tma_box_2d(cbuf + j * SUB_BYTES, &mapRes, bar_cfull + 8 * j, n0 + 32 * j, m0);
+                }
+            }
+            if (et < BN) {                                               // bias / gamma of this column block (the previous tile's
+                const bool in = n0 + et < a.N;                           // readers all passed the barrier before its stores)
+                s_bias[et] = a.bias && in ? __ldg(a.bias + n0 + et) : 0.f;
+                if (EPI == EPI_RES) s_gamma[et] = a.gamma && in ? __ldg(a.gamma + n0 + et) : 1.f;
             }
             for (int kc0 = 0; kc0 < KC; kc0 += chain, ++ch) {
                 const uint32_t buf = ch & 1u;
@@ -242,53 +306,68 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(bar_acce + 8 * buf);
             }
-            if (r < a.R) {
-                float *__restrict__ yr = a.y + r * a.ldy + n0;
+            // the staging set of this tile: the stores of its previous user must have read it (one set: the previous tile, two sets:
+            // the tile before that, whose stores were committed one group earlier)
+            if (elected) {
+                if (C::CSETS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            epi_bar();                                                   // bias in place; the staging set may be written
+            const uint32_t cset = cbuf + set * C::NSUB * SUB_BYTES;
 #pragma unroll
-                for (int g0 = 0; g0 < BN; g0 += 4 * G4) {                // a group of columns at a time: all loads first, then math + stores
-                    float4 rv[G4], bv[G4], gv[G4];
-                    if (EPI == EPI_RES && !(PRE && g0 == 0)) {
+            for (int j = 0; j < C::NSUB; ++j) {
+                if (EPI == EPI_RES) mbar_wait(bar_cfull + 8 * (set * C::NSUB + j), (C::CSETS == 2 ? (nt >> 1) : nt) & 1u);
+                uint8_t *piece = gbase + C::RING + (set * C::NSUB + j) * SUB_BYTES;
 #pragma unroll
-                        for (int i = 0; i < G4; ++i)
-                            rv[i] = n0 + g0 + 4 * i < a.N ? __ldg(reinterpret_cast<const float4 *>(rr + g0 + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = 0; c < 8; ++c) {
+                    float4 *cell = reinterpret_cast<float4 *>(piece + swz(row, c));
+                    const float4 bv = *reinterpret_cast<const float4 *>(s_bias + 32 * j + 4 * c);
+                    float o[4] = {acc[32 * j + 4 * c] + bv.x, acc[32 * j + 4 * c + 1] + bv.y, acc[32 * j + 4 * c + 2] + bv.z,
+                                  acc[32 * j + 4 * c + 3] + bv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (EPI == EPI_BIAS) {
+                            if (n0 + 32 * j + 4 * c + e < a.alpha_cols) o[e] *= a.alpha;
+                        } else if (EPI == EPI_GELU) {
+                            o[e] = 0.5f * o[e] * (1.f + erff(o[e] * 0.70710678118654752440f));
+                        }
                     }
-#pragma unroll
-                    for (int i = 0; i < G4; ++i) {
-                        const bool in = n0 + g0 + 4 * i < a.N;           // N % 4 == 0: the quad is inside or outside together
-                        bv[i] = a.bias && in ? __ldg(reinterpret_cast<const float4 *>(a.bias + n0 + g0 + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (EPI == EPI_RES)
-                            gv[i] = a.gamma && in ? __ldg(reinterpret_cast<const float4 *>(a.gamma + n0 + g0 + 4 * i)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (EPI == EPI_RES) {
+                        const float4 rv = *cell, gv = *reinterpret_cast<const float4 *>(s_gamma + 32 * j + 4 * c);
+                        o[0] = rv.x + gv.x * o[0]; o[1] = rv.y + gv.y * o[1]; o[2] = rv.z + gv.z * o[2]; o[3] = rv.w + gv.w * o[3];
                     }
+                    *cell = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic-proxy writes -> visible to the TMA unit
+            epi_bar();
+            if (elected) {
 #pragma unroll
-                    for (int i = 0; i < G4; ++i) {
-                        const int c0 = g0 + 4 * i;
-                        if (n0 + c0 < a.N) {
-                            float o[4] = {acc[c0] + bv[i].x, acc[c0 + 1] + bv[i].y, acc[c0 + 2] + bv[i].z, acc[c0 + 3] + bv[i].w};
+                for (int j = 0; j < C::NSUB; ++j)
+                    if (n0 + 32 * j < a.N) tma_store_2d(&mapY, cset + j * SUB_BYTES, n0 + 32 * j, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (EPI == EPI_RES && C::CSETS == 2) {                   // residual pieces of the next tile into the other set, whose
+                    const int tn = t + gridDim.x;                        // last stores (the previous tile's) must have read it
+                    if (tn < tiles) {
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        const int m1 = (tn / a.tiles_n) * BM, n1 = (tn % a.tiles_n) * BN;
+                        const uint32_t so = (set ^ 1u) * C::NSUB;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                if (EPI == EPI_BIAS) {
-                                    if (n0 + c0 + j < a.alpha_cols) o[j] *= a.alpha;
-                                } else if (EPI == EPI_GELU) {
-                                    o[j] = 0.5f * o[j] * (1.f + erff(o[j] * 0.70710678118654752440f));
-                                }
-                            }
-                            if (EPI == EPI_RES) {
-                                const float4 q = PRE && g0 == 0 ? pre[i] : rv[i];
-                                o[0] = q.x + gv[i].x * o[0]; o[1] = q.y + gv[i].y * o[1];
-                                o[2] = q.z + gv[i].z * o[2]; o[3] = q.w + gv[i].w * o[3];
-                            }
-                            *reinterpret_cast<float4 *>(yr + c0) = make_float4(o[0], o[1], o[2], o[3]);
+                        for (int j = 0; j < C::NSUB; ++j) {
+                            mbar_expect_tx(bar_cfull + 8 * (so + j), SUB_BYTES);
+                            tma_box_2d(cbuf + (so + j) * SUB_BYTES, &mapRes, bar_cfull + 8 * (so + j), n1 + 32 * j, m1);
                         }
                     }
                 }
             }
         }
+        if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA exits
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
     }
 }
 
@@ -337,7 +416,7 @@ static int sm_count() {
 }
 
 template <int BN, int EPI>
-static int launch(const CUtensorMap &mx, const CUtensorMap &mh, const CUtensorMap &ml, const Args &a, cudaStream_t st) {
+static int launch(const CUtensorMap *m, const Args &a, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(linear_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::SMEM) != cudaSuccess)
@@ -345,17 +424,17 @@ static int launch(const CUtensorMap &mx, const CUtensorMap &mh, const CUtensorMa
         attr_set = true;
     }
     const int tiles = a.tiles_m * a.tiles_n;
-    linear_tc_kernel<BN, EPI><<<std::min(tiles, sm_count()), THREADS, Cfg<BN>::SMEM, st>>>(mx, mh, ml, a);
+    linear_tc_kernel<BN, EPI><<<std::min(tiles, sm_count()), THREADS, Cfg<BN>::SMEM, st>>>(m[0], m[1], m[2], m[3], m[4], a);
     note_launches(1);
     return check_launch("linear_tc");
 }
 
 template <int BN>
-static int launch_epi(int epi, const CUtensorMap &mx, const CUtensorMap &mh, const CUtensorMap &ml, const Args &a, cudaStream_t st) {
+static int launch_epi(int epi, const CUtensorMap *m, const Args &a, cudaStream_t st) {
     switch (epi) {
-        case EPI_BIAS: return launch<BN, EPI_BIAS>(mx, mh, ml, a, st);
-        case EPI_GELU: return launch<BN, EPI_GELU>(mx, mh, ml, a, st);
-        case EPI_RES: return launch<BN, EPI_RES>(mx, mh, ml, a, st);
+        case EPI_BIAS: return launch<BN, EPI_BIAS>(m, a, st);
+        case EPI_GELU: return launch<BN, EPI_GELU>(m, a, st);
+        case EPI_RES: return launch<BN, EPI_RES>(m, a, st);
     }
     return set_error(CLUSTEN_EINVAL, "linear_tc: unknown epilogue %d", epi);
 }
@@ -394,20 +473,21 @@ extern "C" int clusten_linear_tc_f32(const float *x, const float *w_hi, const fl
         const int w = (N + cand - 1) / cand * cand - N;
         if (w < waste) { waste = w; BN = cand; }
     }
-    CUtensorMap mx, mh, ml;
-    if (!tc::map_2d(&mx, x, R, K, ldx, tc::BM) || !tc::map_2d(&mh, w_hi, N, K, K, BN) || !tc::map_2d(&ml, w_lo, N, K, K, BN))
+    CUtensorMap m[5];
+    if (!tc::map_2d(&m[0], x, R, K, ldx, tc::BM) || !tc::map_2d(&m[1], w_hi, N, K, K, BN) || !tc::map_2d(&m[2], w_lo, N, K, K, BN) ||
+        !tc::map_2d(&m[3], y, R, N, ldy, tc::BM) || !tc::map_2d(&m[4], epi == tc::EPI_RES ? res : y, R, N, epi == tc::EPI_RES ? ldres : ldy, tc::BM))
         return set_error(CLUSTEN_EUNSUPPORTED, "linear_tc: cuTensorMapEncodeTiled failed");
     tc::Args a;
-    a.bias = bias; a.res = res; a.gamma = gamma; a.y = y;
-    a.R = (int)R; a.K = K; a.N = N; a.ldy = ldy; a.ldres = ldres;
+    a.bias = bias; a.gamma = gamma;
+    a.R = (int)R; a.K = K; a.N = N;
     a.tiles_m = (int)((R + tc::BM - 1) / tc::BM); a.tiles_n = (N + BN - 1) / BN;
     a.chain = chain > 0 ? chain : 4;
     a.alpha = alpha; a.alpha_cols = epi == tc::EPI_BIAS ? alpha_cols : 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (BN) {
-        case 128: return tc::launch_epi<128>(epi, mx, mh, ml, a, st);
-        case 96: return tc::launch_epi<96>(epi, mx, mh, ml, a, st);
-        case 64: return tc::launch_epi<64>(epi, mx, mh, ml, a, st);
-        default: return tc::launch_epi<32>(epi, mx, mh, ml, a, st);
+        case 128: return tc::launch_epi<128>(epi, m, a, st);
+        case 96: return tc::launch_epi<96>(epi, m, a, st);
+        case 64: return tc::launch_epi<64>(epi, m, a, st);
+        default: return tc::launch_epi<32>(epi, m, a, st);
     }
 }
