@@ -256,6 +256,17 @@ class ClusterAttention(nn.Module):
         self.proj = Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
 
+    def _qkv_params(self):
+        """q and kv weights / biases stacked to [3 c, c] / [3 c] for the single inference GEMM; rebuilt when a parameter changes."""
+        ps = (self.q.weight, self.kv.weight, self.q.bias, self.kv.bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        hit = getattr(self, "_qkv_cache", None)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, torch.cat([self.q.weight, self.kv.weight], 0).contiguous(), torch.cat([self.q.bias, self.kv.bias], 0).contiguous())
+            self._qkv_cache = hit
+        return hit[1], hit[2]
+
     def _project(self, out, residual):
         if residual is not None:
             return self.proj.fused(out, "residual", res=residual[0], gamma=residual[1])
@@ -265,11 +276,15 @@ class ClusterAttention(nn.Module):
         b, n, c = feat.shape
         h = self.num_heads
         c_ = c // h
-        if _tcgen05_ok(feat):
-            q_tok = self.q.fused(feat, "bias", alpha=self.scale, alpha_cols=c).reshape(b, n, h, c_)
+        if _tcgen05_ok(feat) and linear_tc_supported(feat, self.q.weight, self.q.bias) and self.q.bias is not None and self.kv.bias is not None:
+            # one GEMM for q and kv (N = 3 c), q * scale in its epilogue; q_tok / kv_tok are column slices of its [b n, 3 c] result
+            w_qkv, b_qkv = self._qkv_params()
+            qkv = linear_tc(feat, w_qkv, b_qkv, "bias", alpha=self.scale, alpha_cols=c).view(b, n, 3 * c)
+            q_tok = qkv[:, :, :c].unflatten(2, (h, c_))
+            kv_tok = qkv[:, :, c:].unflatten(2, (h, 2, c_))
         else:
             q_tok = (self.q(feat) * self.scale).reshape(b, n, h, c_)                     # token-major b n h c_
-        kv_tok = self.kv(feat).view(b, n, h, 2, c_)
+            kv_tok = self.kv(feat).view(b, n, h, 2, c_)
         fusable = (fused_ctx is not None and not global_attn and USE_FUSED_ATTENTION
                    and (self.attn_drop.p == 0.0 or not self.training))
         if fusable and torch.is_grad_enabled() and q_tok.dtype in (torch.float16, torch.bfloat16):

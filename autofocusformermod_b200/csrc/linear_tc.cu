@@ -14,7 +14,7 @@
 //                       matter), fence.proxy.async, arrive
 //   warp 1 (one lane)   12 tcgen05.mma (M = 128, N = BN, K = 8) per chunk -- small terms first -- into one of two TMEM accumulators;
 //                       tcgen05.commit frees the ring slot and, at the end of a chain, hands the accumulator to the epilogue
-//   warps 6-9           drain: tcgen05.ld of their 32 TMEM lanes, add to the running fp32 sum in registers (the tensor core
+//   warps 6-13          drain: tcgen05.ld of their 32 TMEM lanes x half the columns, add to the running fp32 sum in registers (the tensor core
 //                       accumulates with truncation, so a chain is cut after `chain` chunks -- DESIGN.md section 7), then
 //                       bias / GELU / scaled residual and 16-byte stores of their row
 // The ring and the accumulator pair run across tile boundaries, so the next tile's loads, split and MMAs overlap the epilogue.
@@ -30,7 +30,8 @@ namespace clusten {
 namespace tc {
 
 constexpr int BM = 128, BK = 32;                       // rows per tile, K elements per chunk (= one 128-byte swizzle row)
-constexpr int THREADS = 320;
+constexpr int THREADS = 448;                         // 14 warps: producer, MMA issuer, 4 x split, 8 x epilogue
+constexpr int EPI_THREADS = 256;
 constexpr int A_BYTES = BM * BK * 4;                   // 16 KiB
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -95,7 +96,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }     // the four epilogue warps
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }     // the eight epilogue warps
 // byte offset of 16-byte chunk c of row r inside a [rows x 128 B] box written / read by the TMA unit with SWIZZLE_128B
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
@@ -158,7 +159,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_accf + 8 * b, 1);
-            mbar_init(bar_acce + 8 * b, 128);
+            mbar_init(bar_acce + 8 * b, EPI_THREADS);
         }
         for (int j = 0; j < C::CSETS * C::NSUB; ++j) mbar_init(bar_cfull + 8 * j, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -260,10 +261,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             }
         }
     } else {                                                             // ---- drain + epilogue ----
-        const int q = warp & 3, row = q * 32 + lane, et = threadIdx.x - 192;          // et: 0..127
+        // two warps per TMEM lane quadrant; each keeps half of the tile's columns (HC) of its 32 rows
+        const int q = warp & 3, row = q * 32 + lane, et = threadIdx.x - 192, hf = (warp - 6) >> 2;     // et: 0..255
+        constexpr int HC = BN / 2;
         const bool elected = et == 0;
         uint32_t ch = 0, nt = 0;                                         // chains, tiles of this CTA so far
-        float acc[BN];
+        float acc[HC];
         if (EPI == EPI_RES && elected && (int)blockIdx.x < tiles) {      // residual pieces of the first tile
             const int m0 = (blockIdx.x / a.tiles_n) * BM, n0 = (blockIdx.x % a.tiles_n) * BN;
 #pragma unroll
@@ -294,9 +297,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 const uint32_t buf = ch & 1u;
                 mbar_wait(bar_accf + 8 * buf, (ch >> 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * C::ACC_COLS;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * C::ACC_COLS + hf * HC;
 #pragma unroll
-                for (int c0 = 0; c0 < BN; c0 += 16) {
+                for (int c0 = 0; c0 < HC; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(taddr + c0, v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -315,29 +318,26 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             epi_bar();                                                   // bias in place; the staging set may be written
             const uint32_t cset = cbuf + set * C::NSUB * SUB_BYTES;
 #pragma unroll
-            for (int j = 0; j < C::NSUB; ++j) {
-                if (EPI == EPI_RES) mbar_wait(bar_cfull + 8 * (set * C::NSUB + j), (C::CSETS == 2 ? (nt >> 1) : nt) & 1u);
-                uint8_t *piece = gbase + C::RING + (set * C::NSUB + j) * SUB_BYTES;
+            for (int i = 0; i < HC / 4; ++i) {                           // 16-byte cells of this thread: columns hf * HC + 4 i ..
+                const int col = hf * HC + 4 * i, j = col >> 5, c = (col >> 2) & 7;
+                if (EPI == EPI_RES && (i == 0 || c == 0))
+                    mbar_wait(bar_cfull + 8 * (set * C::NSUB + j), (C::CSETS == 2 ? (nt >> 1) : nt) & 1u);
+                float4 *cell = reinterpret_cast<float4 *>(gbase + C::RING + (set * C::NSUB + j) * SUB_BYTES + swz(row, c));
+                const float4 bv = *reinterpret_cast<const float4 *>(s_bias + col);
+                float o[4] = {acc[4 * i] + bv.x, acc[4 * i + 1] + bv.y, acc[4 * i + 2] + bv.z, acc[4 * i + 3] + bv.w};
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float4 *cell = reinterpret_cast<float4 *>(piece + swz(row, c));
-                    const float4 bv = *reinterpret_cast<const float4 *>(s_bias + 32 * j + 4 * c);
-                    float o[4] = {acc[32 * j + 4 * c] + bv.x, acc[32 * j + 4 * c + 1] + bv.y, acc[32 * j + 4 * c + 2] + bv.z,
-                                  acc[32 * j + 4 * c + 3] + bv.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if (EPI == EPI_BIAS) {
-                            if (n0 + 32 * j + 4 * c + e < a.alpha_cols) o[e] *= a.alpha;
-                        } else if (EPI == EPI_GELU) {
-                            o[e] = 0.5f * o[e] * (1.f + erff(o[e] * 0.70710678118654752440f));
-                        }
+                for (int e = 0; e < 4; ++e) {
+                    if (EPI == EPI_BIAS) {
+                        if (n0 + col + e < a.alpha_cols) o[e] *= a.alpha;
+                    } else if (EPI == EPI_GELU) {
+                        o[e] = 0.5f * o[e] * (1.f + erff(o[e] * 0.70710678118654752440f));
                     }
-                    if (EPI == EPI_RES) {
-                        const float4 rv = *cell, gv = *reinterpret_cast<const float4 *>(s_gamma + 32 * j + 4 * c);
-                        o[0] = rv.x + gv.x * o[0]; o[1] = rv.y + gv.y * o[1]; o[2] = rv.z + gv.z * o[2]; o[3] = rv.w + gv.w * o[3];
-                    }
-                    *cell = make_float4(o[0], o[1], o[2], o[3]);
                 }
+                if (EPI == EPI_RES) {
+                    const float4 rv = *cell, gv = *reinterpret_cast<const float4 *>(s_gamma + col);
+                    o[0] = rv.x + gv.x * o[0]; o[1] = rv.y + gv.y * o[1]; o[2] = rv.z + gv.z * o[2]; o[3] = rv.w + gv.w * o[3];
+                }
+                *cell = make_float4(o[0], o[1], o[2], o[3]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic-proxy writes -> visible to the TMA unit
             epi_bar();

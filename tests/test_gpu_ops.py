@@ -568,6 +568,67 @@ def test_linear_f32_tensor_core(R, K, N):
     assert rel_err(ys.cpu().double(), wide[:, :K].cpu().double() @ w.double().t() + b.double()) <= 2e-6
 
 
+@pytest.mark.parametrize("R,K,N", [(1000, 32, 32), (4173, 128, 256), (300, 96, 288), (129, 768, 2304), (1, 32, 4), (16384, 64, 32),
+                                   (40000, 32, 96), (5000, 256, 100), (777, 1536, 384), (20000, 32, 36)])
+@pytest.mark.parametrize("epilogue", ["bias", "gelu", "residual"])
+def test_linear_tc_tcgen05(R, K, N, epilogue):
+    """clusten_linear_tc_f32 (tcgen05.mma kind::tf32 through TMA and tensor memory, 3xTF32 split) against a float64 product for the
+    three epilogues the block uses (aff.py:107-108 q * scale, aff.py:45-46 GELU(fc1), aff.py:230,236 shortcut + gamma * x): fp32-level
+    accuracy; ragged R (not a multiple of the 128-row tile), N that is not a multiple of the column tile, several tiles per CTA
+    (R = 40 000 -> 313 row tiles on 148 SMs), long K (48 chunks, 12 accumulator chains), strided input, no bias / no gamma."""
+    from autofocusformermod_b200 import ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(R + K + N)
+    x = torch.randn(R, K, generator=g)
+    w = torch.randn(N, K, generator=g) * K ** -0.5
+    b = torch.randn(N, generator=g)
+    res = torch.randn(R, N, generator=g)
+    gam = torch.rand(N, generator=g) + 0.5
+    ncol = (N // 2) // 4 * 4
+
+    def reference(xd, bias, gamma):
+        y = xd.double() @ w.double().t()
+        if bias is not None:
+            y = y + bias.double()
+        if epilogue == "gelu":
+            return F.gelu(y)
+        if epilogue == "residual":
+            return res.double() + (y if gamma is None else gamma.double() * y)
+        y[:, :ncol] *= 0.3
+        return y
+
+    xc, wc, bc, rc, gc = x.cuda(), w.cuda(), b.cuda(), res.cuda(), gam.cuda()
+    assert ops.linear_tc_supported(xc, wc, bc, rc, gc)
+    kw = dict(res=rc, gamma=gc, alpha=0.3, alpha_cols=ncol)
+    y = ops.linear_tc(xc, wc, bc, epilogue, **kw)
+    assert y.shape == (R, N) and y.dtype == torch.float32
+    assert rel_err(y.cpu().double(), reference(x, b, gam)) <= 2e-6
+    y1 = ops.linear_tc(xc, wc, bc, epilogue, chain=1, **kw)              # every K chunk summed in fp32 registers
+    assert rel_err(y1.cpu().double(), reference(x, b, gam)) <= 1e-6
+    y3 = ops.linear_tc(xc.view(1, R, K), wc, None, epilogue, res=rc.view(1, R, N), gamma=None, alpha=0.3, alpha_cols=ncol)
+    assert y3.shape == (1, R, N)                                         # leading dims, no bias, no gamma
+    assert rel_err(y3[0].cpu().double(), reference(x, None, None)) <= 2e-6
+    wide = torch.randn(R, K + 32, generator=g).cuda()                    # row stride K + 32: consumed in place
+    ys = ops.linear_tc(wide[:, :K], wc, bc, epilogue, **kw)
+    assert rel_err(ys.cpu().double(), reference(wide[:, :K].cpu(), b, gam)) <= 2e-6
+
+
+def test_linear_tc_weight_split_follows_the_weight():
+    """The (hi, lo) operands are cached per weight and rebuilt when the weight is updated in place."""
+    from autofocusformermod_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x, w = torch.randn(300, 64, generator=g).cuda(), torch.randn(32, 64, generator=g).cuda()
+    y0 = ops.linear_tc(x, w)
+    hi, lo = ops.tf32_split(w)
+    assert torch.equal((hi.view(torch.int32) & 0x1fff), torch.zeros_like(hi, dtype=torch.int32))       # TF32: 13 low bits clear
+    assert float((hi + lo - w).abs().max()) <= float(w.abs().max()) * 2.0 ** -21
+    assert ops.tf32_split(w)[0] is hi                                    # cached
+    w.mul_(2.0)
+    y1 = ops.linear_tc(x, w)
+    assert ops.tf32_split(w)[0] is not hi
+    assert rel_err(y1, 2.0 * y0) <= 1e-6
+
+
 INKERNEL_BIAS = os.environ.get("CLUSTEN_INKERNEL_BIAS") == "1"
 
 
