@@ -30,7 +30,7 @@ namespace clusten {
 namespace tc {
 
 constexpr int BM = 128, BK = 32;                       // rows per tile, K elements per chunk (= one 128-byte swizzle row)
-constexpr int THREADS = 448;                         // 14 warps: producer, MMA issuer, 4 x split, 8 x epilogue
+constexpr int THREADS = 480;                         // 15 warps: X producer, MMA issuer, 4 x split, 8 x epilogue, W producer
 constexpr int EPI_THREADS = 256;
 constexpr int A_BYTES = BM * BK * 4;                   // 16 KiB
 
@@ -54,6 +54,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
         if (spin > (1u << 24)) __trap();
+}
+// one lane of a converged warp (elect.sync): the warp runs the role's loop uniformly, so the operands of the instructions issued under
+// this predicate stay in uniform registers (a loop entered by `lane == 0` alone makes ptxas wrap every UTCHMMA / UTMALDG in a
+// per-lane waterfall, ~100 cycles each)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tma_box_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -96,7 +104,10 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }     // the eight epilogue warps
+__device__ __forceinline__ void epi_bar() {
+    __syncwarp();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+}     // the eight epilogue warps
 // byte offset of 16-byte chunk c of row r inside a [rows x 128 B] box written / read by the TMA unit with SWIZZLE_128B
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
@@ -106,15 +117,20 @@ constexpr int SUB_BYTES = BM * 128;                    // one [128 rows x 32 col
 
 template <int BN> struct Cfg {
     static constexpr int B_BYTES = BN * BK * 4;
-    static constexpr int STAGE = A_BYTES + 2 * B_BYTES;                  // x | wh | wl
-    static constexpr int STAGES = BN >= 96 ? 3 : 4;
+    static constexpr int WSTAGE = 2 * B_BYTES;                           // wh | wl
+    static constexpr int WS = BN >= 96 ? 3 : 4;                          // weight ring (L2-resident operand: short latency)
     static constexpr int NSUB = BN / 32;                                 // output pieces per tile
-    static constexpr int CSETS = BN >= 128 ? 1 : 2;                      // tile-sized output staging sets
+    static constexpr int CSETS = BN >= 96 ? 1 : 2;                       // tile-sized output staging sets
+    static constexpr int CBUF = CSETS * NSUB * SUB_BYTES;
+    static constexpr int TAIL = 2048;                                    // barriers, TMEM slot, bias / gamma of the tile
+    // the X ring takes what is left of 227 KiB, at most 8 stages: X comes from HBM and its latency is what the ring has to cover
+    static constexpr int XS_FIT = (232448 - 1024 - TAIL - CBUF - WS * WSTAGE) / A_BYTES;
+    static constexpr int XS = XS_FIT > 8 ? 8 : XS_FIT;
     static constexpr int ACC_COLS = BN == 96 ? 128 : BN;                 // column pitch of the two accumulators
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    static constexpr int RING = STAGES * STAGE, CBUF = CSETS * NSUB * SUB_BYTES;
-    static constexpr int TAIL = 2048;                                    // barriers, TMEM slot, bias / gamma of the tile
+    static constexpr int XRING = XS * A_BYTES, RING = XRING + WS * WSTAGE;
     static constexpr size_t SMEM = (size_t)RING + CBUF + TAIL + 1024 /* alignment slack */;
+    static_assert(XS >= 3, "X ring too shallow");
 };
 
 enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_RES = 2 };
@@ -133,13 +149,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                  const __grid_constant__ CUtensorMap mapWl, const __grid_constant__ CUtensorMap mapY,
                  const __grid_constant__ CUtensorMap mapRes, const Args a) {
     using C = Cfg<BN>;
-    constexpr int S = C::STAGES;
+    constexpr int XS = C::XS, WS = C::WS;
     extern __shared__ uint8_t tc_smem_raw[];
     const uint32_t base = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
     uint8_t *gbase = tc_smem_raw + (base - smem_u32(tc_smem_raw));
-    const uint32_t cbuf = base + C::RING, tail = cbuf + C::CBUF;
-    const uint32_t bar_xfull = tail, bar_xempty = tail + 8 * S, bar_wfull = tail + 16 * S, bar_wempty = tail + 24 * S;
-    const uint32_t bar_afull = tail + 32 * S, bar_aempty = bar_afull + 8 * NA, bar_accf = bar_aempty + 8 * NA, bar_acce = bar_accf + 16;
+    const uint32_t wring = base + C::XRING, cbuf = base + C::RING, tail = cbuf + C::CBUF;
+    const uint32_t bar_xfull = tail, bar_xempty = tail + 8 * XS, bar_wfull = tail + 16 * XS, bar_wempty = bar_wfull + 8 * WS;
+    const uint32_t bar_afull = bar_wempty + 8 * WS, bar_aempty = bar_afull + 8 * NA, bar_accf = bar_aempty + 8 * NA, bar_acce = bar_accf + 16;
     const uint32_t bar_cfull = bar_acce + 16;                            // CSETS * NSUB barriers
     uint8_t *gtail = gbase + C::RING + C::CBUF;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gtail + 512);
@@ -147,9 +163,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) {
+        for (int s = 0; s < XS; ++s) {
             mbar_init(bar_xfull + 8 * s, 1);
             mbar_init(bar_xempty + 8 * s, 128);
+        }
+        for (int s = 0; s < WS; ++s) {
             mbar_init(bar_wfull + 8 * s, 1);
             mbar_init(bar_wempty + 8 * s, 1);
         }
@@ -176,38 +194,50 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const int KC = a.K / BK, tiles = a.tiles_m * a.tiles_n;
     const int chain = a.chain;
 
-    if (warp == 0) {
-        if (lane == 0) {                                                 // ---- TMA producer ----
-            uint32_t it = 0;
-            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-                const int m0 = (t / a.tiles_n) * BM, n0 = (t % a.tiles_n) * BN;
-                for (int kc = 0; kc < KC; ++kc, ++it) {
-                    const uint32_t s = it % S, ph = (it / S) & 1u;
-                    const uint32_t st = base + s * C::STAGE;
-                    mbar_wait(bar_xempty + 8 * s, ph ^ 1u);
+    if (warp == 0) {                                                     // ---- TMA producer, X (from HBM: the deep ring) ----
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const int m0 = (t / a.tiles_n) * BM;
+            for (int kc = 0; kc < KC; ++kc, ++it) {
+                const uint32_t s = it % XS, ph = (it / XS) & 1u;
+                mbar_wait(bar_xempty + 8 * s, ph ^ 1u);
+                if (elect_one()) {
                     mbar_expect_tx(bar_xfull + 8 * s, A_BYTES);
-                    tma_box_2d(st, &mapX, bar_xfull + 8 * s, kc * BK, m0);
-                    mbar_wait(bar_wempty + 8 * s, ph ^ 1u);
-                    mbar_expect_tx(bar_wfull + 8 * s, 2 * C::B_BYTES);
-                    tma_box_2d(st + A_BYTES, &mapWh, bar_wfull + 8 * s, kc * BK, n0);
-                    tma_box_2d(st + A_BYTES + C::B_BYTES, &mapWl, bar_wfull + 8 * s, kc * BK, n0);
+                    tma_box_2d(base + s * A_BYTES, &mapX, bar_xfull + 8 * s, kc * BK, m0);
                 }
+                __syncwarp();
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {                                                 // ---- MMA issuer ----
-            uint32_t it = 0, ch = 0;
-            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-                for (int kc = 0; kc < KC; ++kc, ++it) {
-                    const uint32_t s = it % S, ph = (it / S) & 1u, sa = it % NA, pa = (it / NA) & 1u;
-                    const uint32_t buf = ch & 1u;
-                    const bool first = kc % chain == 0, last = (kc + 1) % chain == 0 || kc + 1 == KC;
-                    if (first) mbar_wait(bar_acce + 8 * buf, ((ch >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
-                    mbar_wait(bar_wfull + 8 * s, ph);
-                    mbar_wait(bar_afull + 8 * sa, pa);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t st = base + s * C::STAGE;
-                    const uint64_t wh = umma_desc(st + A_BYTES), wl = umma_desc(st + A_BYTES + C::B_BYTES);
+    } else if (warp == 14) {                                             // ---- TMA producer, pre-split weights (L2) ----
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const int n0 = (t % a.tiles_n) * BN;
+            for (int kc = 0; kc < KC; ++kc, ++it) {
+                const uint32_t s = it % WS, ph = (it / WS) & 1u;
+                const uint32_t st = wring + s * C::WSTAGE;
+                mbar_wait(bar_wempty + 8 * s, ph ^ 1u);
+                if (elect_one()) {
+                    mbar_expect_tx(bar_wfull + 8 * s, C::WSTAGE);
+                    tma_box_2d(st, &mapWh, bar_wfull + 8 * s, kc * BK, n0);
+                    tma_box_2d(st + C::B_BYTES, &mapWl, bar_wfull + 8 * s, kc * BK, n0);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {                                              // ---- MMA issuer ----
+        uint32_t it = 0, ch = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            for (int kc = 0; kc < KC; ++kc, ++it) {
+                const uint32_t s = it % WS, ph = (it / WS) & 1u, sa = it % NA, pa = (it / NA) & 1u;
+                const uint32_t buf = ch & 1u;
+                const bool first = kc % chain == 0, last = (kc + 1) % chain == 0 || kc + 1 == KC;
+                if (first) mbar_wait(bar_acce + 8 * buf, ((ch >> 1) & 1u) ^ 1u);          // the epilogue has drained this accumulator
+                mbar_wait(bar_wfull + 8 * s, ph);
+                mbar_wait(bar_afull + 8 * sa, pa);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t st = wring + s * C::WSTAGE;
+                    const uint64_t wh = umma_desc(st), wl = umma_desc(st + C::B_BYTES);
                     const uint32_t xh = tmem + A_COL0 + sa * 64, xl = xh + 32;
                     const uint32_t d = tmem + buf * C::ACC_COLS;
 #pragma unroll
@@ -219,11 +249,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     for (int k = 0; k < BK / 8; ++k) umma_tf32_ts(d, xh + 8 * k, wh + 2 * k, C::IDESC, 1u);
                     umma_commit(bar_wempty + 8 * s);                     // both rings are free once these MMAs have read them
                     umma_commit(bar_aempty + 8 * sa);
-                    if (last) {
-                        umma_commit(bar_accf + 8 * buf);
-                        ++ch;
-                    }
+                    if (last) umma_commit(bar_accf + 8 * buf);
                 }
+                __syncwarp();
+                if (last) ++ch;
             }
         }
     } else if (warp < 6) {                                               // ---- split x -> (xh, xl), row per thread, into TMEM ----
@@ -232,9 +261,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         uint32_t it = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
             for (int kc = 0; kc < KC; ++kc, ++it) {
-                const uint32_t s = it % S, ph = (it / S) & 1u, sa = it % NA, pa = (it / NA) & 1u;
+                const uint32_t s = it % XS, ph = (it / XS) & 1u, sa = it % NA, pa = (it / NA) & 1u;
                 mbar_wait(bar_xfull + 8 * s, ph);
-                const uint8_t *xs = gbase + s * C::STAGE;
+                const uint8_t *xs = gbase + s * A_BYTES;
                 float4 x[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4 *>(xs + swz(row, c));
@@ -249,8 +278,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                         l[4 * c + e] = __float_as_uint(tf32_rn(xv[e] - hv));
                     }
                 }
-                mbar_arrive(bar_xempty + 8 * s);                         // the landing slot has been read
+                // Generic-proxy reads, then async-proxy (TMA) writes to the same slot: the release needs a proxy fence.  Without it
+                // the arrive (scheduled right behind the ISSUE of the eight LDS) ran ahead of their completion and the next box
+                // landed under loads in flight -- one K chunk of a row wrong in ~0.1 % of the rows once the X ring was freed by
+                // this arrive alone.
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(bar_xempty + 8 * s);
                 mbar_wait(bar_aempty + 8 * sa, pa ^ 1u);                 // the MMAs of NA chunks ago are done with this A stage
+                __syncwarp();                                            // (.sync.aligned below: the lanes left the spin loops apart)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ta = tmem + lane_off + A_COL0 + sa * 64;
                 tmem_st32(ta, h);
@@ -260,7 +295,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 mbar_arrive(bar_afull + 8 * sa);
             }
         }
-    } else {                                                             // ---- drain + epilogue ----
+    } else if (warp < 14) {                                              // ---- drain + epilogue ----
         // two warps per TMEM lane quadrant; each keeps half of the tile's columns (HC) of its 32 rows
         const int q = warp & 3, row = q * 32 + lane, et = threadIdx.x - 192, hf = (warp - 6) >> 2;     // et: 0..255
         constexpr int HC = BN / 2;
@@ -296,6 +331,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             for (int kc0 = 0; kc0 < KC; kc0 += chain, ++ch) {
                 const uint32_t buf = ch & 1u;
                 mbar_wait(bar_accf + 8 * buf, (ch >> 1) & 1u);
+                __syncwarp();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * C::ACC_COLS + hf * HC;
 #pragma unroll

@@ -380,6 +380,8 @@ def main():
     k0 = ops.kernel_launches()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dom_flops = 0
+    f0 = ops.flops_issued(dominant)
     if not use_graph:
         ops.start_kernel_timer(dominant)
     ev0.record()
@@ -390,16 +392,19 @@ def main():
     ms = ev0.elapsed_time(ev1)
     if not use_graph:
         dom = ops.stop_kernel_timer()
+        dom_flops = ops.flops_issued(dominant) - f0
         launches = ops.kernel_launches() - k0
         roof_timing = "CUDA events around every launch of the entry point inside the timed region"
     else:
         # a graph replay cannot carry per-launch events: the dominant entry point is timed over the same number of EAGER
         # steps on the same inputs right after the timed region (same kernels, same arguments)
         k1 = ops.kernel_launches()
+        f0 = ops.flops_issued(dominant)
         ops.start_kernel_timer(dominant)
         for _ in range(args.steps):
             eager_step(x_dev)
         dom = ops.stop_kernel_timer()
+        dom_flops = ops.flops_issued(dominant) - f0
         # kernels of ours inside the replays of the timed region = what the same steps launch eagerly
         launches = graphed.launches_per_replay * args.steps if graphed is not None else ops.kernel_launches() - k1
         roof_timing = "CUDA events around every launch of the entry point over the same number of eager steps after the timed region (graph replays carry no per-launch events)"
@@ -470,6 +475,22 @@ def main():
                 "avg_launch_ms": round(dom_ms / max(len(dom), 1), 4),
                 "share_of_step": round(dom_ms / ms, 4), "timing": roof_timing,
                 "per_entry_ms_per_step": {n: round(v[0], 4) for n, v in sorted(per.items())}}
+
+    # every entry point of the untimed eager pre-pass against the HBM roofline (one step; the section 8(a) kernels stay visible when
+    # a Linear dominates the step)
+    roofline["by_entry"] = {n: {"ms": round(v[0], 4), "gbps": round(v[1] / v[0] / 1e6, 1), "frac": round(v[1] / v[0] / 1e6 / peak, 4)}
+                            for n, v in sorted(per.items()) if v[1] > 0 and v[0] > 0}
+    if dom_flops and dom_ms > 0:
+        # GEMM-shaped dominant kernel: also against the tensor-core ceiling.  fp32 products are three TF32 MMAs (3xTF32 split) and
+        # the TF32 dense rate is half the bf16 one, so the ceiling for ALGORITHMIC fp32 FLOPs is bf16 / 6.
+        bf16 = float(json.load(open(peaks_path)).get("bf16_tflops_sustained", 1404.1)) if os.path.exists(peaks_path) else 1404.1
+        tf = dom_flops / dom_ms / 1e9
+        roofline["tensor"] = {"achieved": round(tf, 1), "peak": round(bf16 / 6, 1), "unit": "TFLOP/s (algorithmic fp32, 2RKN)",
+                              "frac": round(tf / (bf16 / 6), 4),
+                              "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32) / 3 (3xTF32 split)"}
+        if roofline["tensor"]["frac"] > roofline["frac"]:
+            roofline["note"] = ("the launches of this entry point range from HBM-bound (K = 32) to tensor-bound (K >= 256); both "
+                                "ceilings are reported, the HBM one in the contract keys")
 
     execution = ("CUDA graph replay (AFF.graphed)" if graphed is not None else
                  ("CUDA graphs for forward and backward (graphed_training_forward), eager AdamW"
