@@ -25,7 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .ops import (CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction, cluster_attention_core, cluster_attention_fused,
-                  cluster_attention_core_pos, cluster_attention_fused_pos, layer_norm, linear, linear_f32, linear_f32_supported, linear_tc, linear_tc_supported,
+                  cluster_attention_core_pos, cluster_attention_fused_pos, layer_norm, layer_norm_stats, linear, linear_f32, linear_f32_supported, linear_tc, linear_tc_supported,
                   scale_residual, table_linear,
                   table_linear_supported, table_lookup)
 from .point_utils import knn_keops, merge_select, space_filling_cluster, stage_prepare
@@ -67,6 +67,11 @@ TC_LINEAR = _opt_in("CLUSTEN_TC_LINEAR")
 # fp32 inference Linear layers on tcgen05 (clusten_linear_tc_f32: TMA + TMEM, 3xTF32 split) with the element-wise line that follows
 # them in the block folded into the epilogue (q * scale, GELU, shortcut + gamma * x).  CLUSTEN_TCGEN05_LINEAR=0: cuBLAS.
 TCGEN05_LINEAR = os.environ.get("CLUSTEN_TCGEN05_LINEAR", "1") != "0"
+
+
+# the LayerNorm in front of those Linear layers (norm1 -> q / kv, norm2 -> fc1, merge norm -> merge linear) applied inside the GEMM
+# while it stages the rows: the norm kernel shrinks to its statistics pass.  CLUSTEN_LN_IN_GEMM=0: separate LayerNorm kernel.
+LN_IN_GEMM = os.environ.get("CLUSTEN_LN_IN_GEMM", "1") != "0"
 
 
 def _tcgen05_ok(x):
@@ -145,6 +150,16 @@ class LayerNorm(nn.LayerNorm):
         return layer_norm(x, self.weight, self.bias, self.eps, out_dtype)
 
 
+def _ln_operands(norm, x):
+    """(mean, rstd, weight, bias) for ``linear_tc(..., ln=...)`` when ``norm`` can ride inside the GEMM that consumes ``x``, else None."""
+    C = x.shape[-1]
+    if (LN_IN_GEMM and isinstance(norm, LayerNorm) and _tcgen05_ok(x) and len(norm.normalized_shape) == 1 and C <= 1024 and C % 32 == 0
+            and norm.weight is not None and norm.bias is not None and norm.weight.dtype == torch.float32):
+        mean, rstd = layer_norm_stats(x, norm.weight, norm.bias, norm.eps)
+        return mean, rstd, norm.weight, norm.bias
+    return None
+
+
 def _inner_norm(norm_layer, dim):
     """A norm whose output only feeds Linear layers."""
     n = norm_layer(dim)
@@ -167,11 +182,17 @@ class Linear(nn.Linear):
             return linear_f32(x, self.weight, self.bias)
         return F.linear(x, self.weight, self.bias)
 
-    def fused(self, x, epilogue, res=None, gamma=None, alpha=1.0, alpha_cols=0):
+    def fused(self, x, epilogue, res=None, gamma=None, alpha=1.0, alpha_cols=0, norm=None):
         """The layer plus the element-wise line after it -- ``bias`` (the first ``alpha_cols`` outputs then times ``alpha``), ``gelu``
-        or ``residual`` (res + gamma * y) -- in one tcgen05 kernel when the operands allow, else the same arithmetic in torch."""
+        or ``residual`` (res + gamma * y) -- and, with ``norm``, the LayerNorm in front of it, in one tcgen05 kernel when the operands
+        allow, else the same arithmetic in torch."""
         if _tcgen05_ok(x) and linear_tc_supported(x, self.weight, self.bias, res, gamma):
-            return linear_tc(x, self.weight, self.bias, epilogue, res=res, gamma=gamma, alpha=alpha, alpha_cols=alpha_cols)
+            ln = _ln_operands(norm, x) if norm is not None else None
+            if norm is not None and ln is None:
+                x = norm(x)
+            return linear_tc(x, self.weight, self.bias, epilogue, res=res, gamma=gamma, alpha=alpha, alpha_cols=alpha_cols, ln=ln)
+        if norm is not None:
+            x = norm(x)
         y = self.forward(x)
         if epilogue == "gelu":
             return F.gelu(y)
@@ -226,12 +247,15 @@ class Mlp(nn.Module):
         self.fc2 = Linear(hidden_features or in_features, out_features or in_features)
         self.drop = nn.Dropout(drop)
 
-    def forward(self, x, residual=None):
+    def forward(self, x, residual=None, norm=None):
         """``residual`` = (shortcut, gamma or None): return shortcut + gamma * mlp(x) (the caller has checked that nothing random
-        sits in between)."""
+        sits in between); ``norm``: the LayerNorm to apply to x first (it rides inside fc1 when it can)."""
+        if norm is not None and not (_tcgen05_ok(x) and isinstance(self.act, nn.GELU) and self.act.approximate == "none"):
+            x, norm = norm(x), None
         if residual is not None or (_tcgen05_ok(x) and isinstance(self.act, nn.GELU) and self.act.approximate == "none"
                                     and (self.drop.p == 0.0 or not self.training)):
-            hidden = self.fc1.fused(x, "gelu") if isinstance(self.act, nn.GELU) and self.act.approximate == "none" else self.act(self.fc1(x))
+            hidden = (self.fc1.fused(x, "gelu", norm=norm) if isinstance(self.act, nn.GELU) and self.act.approximate == "none"
+                      else self.act(self.fc1(x)))
             if residual is not None:
                 return self.fc2.fused(hidden, "residual", res=residual[0], gamma=residual[1])
             return self.fc2(hidden)
@@ -272,14 +296,20 @@ class ClusterAttention(nn.Module):
             return self.proj.fused(out, "residual", res=residual[0], gamma=residual[1])
         return self.proj_drop(self.proj(out))
 
-    def forward(self, feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup=None, fused_ctx=None, residual=None):
+    def forward(self, feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup=None, fused_ctx=None, residual=None, norm=None):
+        """``norm``: the LayerNorm still to be applied to ``feat`` (it rides inside the q / kv GEMM when it can)."""
         b, n, c = feat.shape
         h = self.num_heads
         c_ = c // h
-        if _tcgen05_ok(feat) and linear_tc_supported(feat, self.q.weight, self.q.bias) and self.q.bias is not None and self.kv.bias is not None:
+        one_gemm = (_tcgen05_ok(feat) and linear_tc_supported(feat, self.q.weight, self.q.bias) and self.q.bias is not None
+                    and self.kv.bias is not None)
+        ln = _ln_operands(norm, feat) if (norm is not None and one_gemm) else None
+        if norm is not None and ln is None:
+            feat = norm(feat)
+        if one_gemm:
             # one GEMM for q and kv (N = 3 c), q * scale in its epilogue; q_tok / kv_tok are column slices of its [b n, 3 c] result
             w_qkv, b_qkv = self._qkv_params()
-            qkv = linear_tc(feat, w_qkv, b_qkv, "bias", alpha=self.scale, alpha_cols=c).view(b, n, 3 * c)
+            qkv = linear_tc(feat, w_qkv, b_qkv, "bias", alpha=self.scale, alpha_cols=c, ln=ln).view(b, n, 3 * c)
             q_tok = qkv[:, :, :c].unflatten(2, (h, c_))
             kv_tok = qkv[:, :, c:].unflatten(2, (h, 2, c_))
         else:
@@ -356,9 +386,9 @@ class ClusterTransformerBlock(nn.Module):
         if (_tcgen05_ok(feat) and (not self.training or (isinstance(self.drop_path, nn.Identity) and self.attn.proj_drop.p == 0.0
                                                           and self.mlp.drop.p == 0.0))):
             # inference, fp32: both residual lines ride in the epilogue of the Linear before them
-            feat = self.attn(self.norm1(feat), member_idx, cluster_mask, pe_idx, global_attn, pe_lookup, fused_ctx,
-                             residual=(feat, self.gamma1 if self.layer_scale else None))
-            return self.mlp(self.norm2(feat), residual=(feat, self.gamma2 if self.layer_scale else None))
+            feat = self.attn(feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup, fused_ctx,
+                             residual=(feat, self.gamma1 if self.layer_scale else None), norm=self.norm1)
+            return self.mlp(feat, residual=(feat, self.gamma2 if self.layer_scale else None), norm=self.norm2)
         a = self.attn(self.norm1(feat), member_idx, cluster_mask, pe_idx, global_attn, pe_lookup, fused_ctx)
         feat = self._residual(feat, a, self.gamma1 if self.layer_scale else None)                    # aff.py:230
         m = self.mlp(self.norm2(feat))
@@ -429,7 +459,7 @@ class ClusterMerging(nn.Module):
         if MERGE_WF_AUTOCAST and torch.is_autocast_enabled() and weights.dtype == torch.float32:
             weights = weights.to(torch.get_autocast_dtype("cuda"))
         feat = CLUSTENWFFunction.apply(weights, feat, member_idx).reshape(b, n2, -1)                 # aff.py:361
-        return pos, self.linear(self.norm(feat))
+        return pos, self.linear.fused(feat, "bias", norm=self.norm)
 
 
 class BasicLayer(nn.Module):

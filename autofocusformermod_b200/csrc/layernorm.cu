@@ -78,7 +78,7 @@ ln_fwd_kernel(const TI *__restrict__ x, const float *__restrict__ gamma, const f
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
             const int c = lane + 32 * k;
-            if (c < C) {
+            if (c < C && y) {                           // y == NULL: statistics only (the consumer normalises on the fly)
                 const float g = KEEP ? gm[KEEP ? k : 0] : __ldg(gamma + c), be = KEEP ? bt[KEEP ? k : 0] : __ldg(beta + c);
                 ya[c] = from_f<TO>(fmaf((va[k] - ma) * ra, g, be));
                 if (two) yb[c] = from_f<TO>(fmaf((vb[k] - mb) * rb, g, be));
@@ -218,7 +218,7 @@ using namespace clusten;
 extern "C" int clusten_layer_norm_fwd(const void *x, const float *gamma, const float *beta, void *y, float *mean, float *rstd,
                                       int64_t R, int C, float eps, int x_dtype, int y_dtype, void *stream) {
     if (R < 0 || C <= 0 || C > 32 * LN_MAX_PER_LANE) return set_error(CLUSTEN_EUNSUPPORTED, "layer norm: C=%d outside 1..1024", C);
-    if (!x || !gamma || !beta || !y || (mean == nullptr) != (rstd == nullptr)) return set_error(CLUSTEN_EINVAL, "null pointer");
+    if (!x || !gamma || !beta || (!y && !mean) || (mean == nullptr) != (rstd == nullptr)) return set_error(CLUSTEN_EINVAL, "null pointer");
     if (R == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     LN_DISPATCH2(x_dtype, y_dtype, return ln_fwd_launch<TA, TB>((const TA *)x, gamma, beta, (TB *)y, mean, rstd, R, C, eps, st));

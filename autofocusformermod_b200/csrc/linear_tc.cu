@@ -137,6 +137,7 @@ enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_RES = 2 };
 
 struct Args {
     const float *bias, *gamma;
+    const float *ln_mean, *ln_rstd, *ln_gamma, *ln_beta;   // LayerNorm of the X rows applied while they are split (or NULL)
     int R, K, N;
     int tiles_m, tiles_n, chain;
     float alpha;
@@ -259,7 +260,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         const int q = warp & 3, row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         uint32_t it = 0;
+        const bool ln = a.ln_mean != nullptr;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const int64_t r = (int64_t)(t / a.tiles_n) * BM + row;
+            const float mu = ln && r < a.R ? __ldg(a.ln_mean + r) : 0.f, rs = ln && r < a.R ? __ldg(a.ln_rstd + r) : 0.f;
             for (int kc = 0; kc < KC; ++kc, ++it) {
                 const uint32_t s = it % XS, ph = (it / XS) & 1u, sa = it % NA, pa = (it / NA) & 1u;
                 mbar_wait(bar_xfull + 8 * s, ph);
@@ -267,6 +271,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 float4 x[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4 *>(xs + swz(row, c));
+                if (ln) {                                                // y = (x - mean) * rstd * gamma + beta, as ln_fwd_kernel rounds it
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 g = __ldg(reinterpret_cast<const float4 *>(a.ln_gamma + kc * BK + 4 * c));
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(a.ln_beta + kc * BK + 4 * c));
+                        x[c].x = fmaf((x[c].x - mu) * rs, g.x, b.x); x[c].y = fmaf((x[c].y - mu) * rs, g.y, b.y);
+                        x[c].z = fmaf((x[c].z - mu) * rs, g.z, b.z); x[c].w = fmaf((x[c].w - mu) * rs, g.w, b.w);
+                    }
+                }
                 uint32_t h[32], l[32];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -493,12 +506,17 @@ extern "C" int clusten_tf32_split(const float *w, float *hi, float *lo, int64_t 
 // Y [R,N] (row stride ldy); fp32.  epi 0: y = (acc + bias), columns < alpha_cols multiplied by alpha afterwards; epi 1: exact GELU of
 // (acc + bias); epi 2: y = res + gamma * (acc + bias) (res [R,N] row stride ldres, gamma [N] or NULL = 1).  chain = K chunks of 32
 // summed inside the tensor-core accumulator before it is added to the fp32 running sum (<= 0: the default, 4).
+// ln_mean / ln_rstd [R] + ln_gamma / ln_beta [K] (or all NULL): the rows of X are LayerNorm-ed while they are split, with the
+// statistics clusten_layer_norm_fwd(y = NULL) wrote -- the `self.norm1(x)` / `self.norm2(x)` / `self.norm(x)` in front of the layer.
 // Needs K % 32 == 0, N % 4 == 0, 16-byte aligned rows; anything else returns CLUSTEN_EUNSUPPORTED.
 extern "C" int clusten_linear_tc_f32(const float *x, const float *w_hi, const float *w_lo, const float *bias, const float *res,
                                      const float *gamma, float *y, int64_t R, int K, int N, int64_t ldx, int64_t ldy, int64_t ldres,
-                                     int epi, float alpha, int alpha_cols, int chain, void *stream) {
+                                     int epi, float alpha, int alpha_cols, int chain, const float *ln_mean, const float *ln_rstd,
+                                     const float *ln_gamma, const float *ln_beta, void *stream) {
     if (R < 0 || K <= 0 || N <= 0 || ldx < K || ldy < N || !x || !w_hi || !w_lo || !y || (epi == tc::EPI_RES && (!res || ldres < N)))
         return set_error(CLUSTEN_EINVAL, "linear_tc: bad arguments R=%lld K=%d N=%d", (long long)R, K, N);
+    if ((ln_mean != nullptr) != (ln_rstd != nullptr) || (ln_mean && (!ln_gamma || !ln_beta || !aligned16(ln_gamma) || !aligned16(ln_beta))))
+        return set_error(CLUSTEN_EINVAL, "linear_tc: LayerNorm needs mean, rstd [R] and 16-byte aligned gamma, beta [K]");
     if (R == 0) return 0;
     if (K % tc::BK || N % 4 || ldx % 4 || ldy % 4 || (epi == tc::EPI_RES && ldres % 4) || !aligned16(x) || !aligned16(w_hi) || !aligned16(w_lo) ||
         !aligned16(y) || (bias && !aligned16(bias)) || (res && !aligned16(res)) || (gamma && !aligned16(gamma)) || R > (1LL << 31) - tc::BM)
@@ -515,6 +533,7 @@ extern "C" int clusten_linear_tc_f32(const float *x, const float *w_hi, const fl
         return set_error(CLUSTEN_EUNSUPPORTED, "linear_tc: cuTensorMapEncodeTiled failed");
     tc::Args a;
     a.bias = bias; a.gamma = gamma;
+    a.ln_mean = ln_mean; a.ln_rstd = ln_rstd; a.ln_gamma = ln_gamma; a.ln_beta = ln_beta;
     a.R = (int)R; a.K = K; a.N = N;
     a.tiles_m = (int)((R + tc::BM - 1) / tc::BM); a.tiles_n = (N + BN - 1) / BN;
     a.chain = chain > 0 ? chain : 4;

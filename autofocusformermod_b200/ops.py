@@ -649,6 +649,23 @@ class LayerNormFunction(Function):
         return dx, dg.to(ctx.wdt[0]), db.to(ctx.wdt[1]), None, None
 
 
+def layer_norm_stats(x, weight, bias, eps=1e-5):
+    """(mean, rstd) fp32 [rows] of LayerNorm over the last dimension, exactly the statistics clusten_layer_norm_fwd normalises with
+    (same kernel, y = NULL): what ``linear_tc(..., ln=...)`` needs to apply the norm while it stages the rows.  No autograd."""
+    dev = _lib.require_cuda(x, weight, bias)
+    C = x.shape[-1]
+    xc = x.contiguous()
+    R = xc.numel() // C
+    mean = torch.empty(R, dtype=torch.float32, device=dev)
+    rstd = torch.empty(R, dtype=torch.float32, device=dev)
+    if R:
+        w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        with torch.cuda.device(dev):
+            _call("clusten_layer_norm_fwd", dev, xc.data_ptr(), w.data_ptr(), b.data_ptr(), 0, mean.data_ptr(), rstd.data_ptr(), R, C,
+                  float(eps), _lib.dtype_code(xc), _lib.DTYPES[torch.float32], nbytes=R * C * xc.element_size() + 8 * R)
+    return mean, rstd
+
+
 def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None):
     return LayerNormFunction.apply(x, weight, bias, eps, out_dtype or x.dtype)
 
@@ -857,10 +874,11 @@ def linear_tc_supported(x, weight, bias=None, res=None, gamma=None):
     return bool(ok)
 
 
-def linear_tc(x, weight, bias=None, epilogue="bias", res=None, gamma=None, alpha=1.0, alpha_cols=0, chain=None):
+def linear_tc(x, weight, bias=None, epilogue="bias", res=None, gamma=None, alpha=1.0, alpha_cols=0, chain=None, ln=None):
     """fp32 ``F.linear`` on the tcgen05 tensor cores (clusten_linear_tc_f32; inference, no autograd) with one of
     ``bias`` (y = x W^T + b, the first ``alpha_cols`` columns then times ``alpha``), ``gelu`` (y = GELU(x W^T + b)) or
-    ``residual`` (y = res + gamma * (x W^T + b)) as the epilogue.  The caller checks ``linear_tc_supported`` first."""
+    ``residual`` (y = res + gamma * (x W^T + b)) as the epilogue.  ``ln`` = (mean, rstd, ln_weight, ln_bias): the rows of x are
+    LayerNorm-ed on the fly with the statistics of ``layer_norm_stats``.  The caller checks ``linear_tc_supported`` first."""
     dev = _lib.require_cuda(x, weight, bias, res, gamma)
     K, N = x.shape[-1], weight.shape[0]
     x2 = x.reshape(-1, K)
@@ -877,10 +895,16 @@ def linear_tc(x, weight, bias=None, epilogue="bias", res=None, gamma=None, alpha
             r2 = r2.contiguous()
         ldres = r2.stride(0)
     y = torch.empty((R, N), dtype=torch.float32, device=dev)
+    lnp = [0, 0, 0, 0]
+    if ln is not None:
+        mean, rstd, lw, lb = ln
+        lw, lb = lw.detach().float().contiguous(), lb.detach().float().contiguous()
+        _check_shapes(mean.numel() == R and rstd.numel() == R and lw.numel() == K and lb.numel() == K, "linear_tc: LayerNorm operands")
+        lnp = [mean.data_ptr(), rstd.data_ptr(), lw.data_ptr(), lb.data_ptr()]
     with torch.cuda.device(dev):
         _call("clusten_linear_tc_f32", dev, x2.data_ptr(), hi.data_ptr(), lo.data_ptr(), _lib.ptr(b), _lib.ptr(r2), _lib.ptr(g),
               y.data_ptr(), R, K, N, x2.stride(0), N, ldres, LINEAR_EPI[epilogue], float(alpha), int(alpha_cols),
-              LINEAR_TC_CHAIN if chain is None else int(chain), nbytes=4 * (R * (K + N * (2 if r2 is not None else 1)) + 2 * N * K),
+              LINEAR_TC_CHAIN if chain is None else int(chain), *lnp, nbytes=4 * (R * (K + N * (2 if r2 is not None else 1)) + 2 * N * K),
               flops=2 * R * K * N)
     return y.view(*x.shape[:-1], N)
 

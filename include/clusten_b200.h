@@ -250,11 +250,14 @@ int clusten_linear_f32(const float *x, const float *weight, const float *bias, f
  * clusten_tf32_split writes the two weight operands once per weight: hi = w rounded to TF32, lo = (w - hi) rounded to TF32.
  * x [R,K] row stride ldx, w_hi / w_lo [N,K] contiguous, y [R,N] row stride ldy, res [R,N] row stride ldres; K % 32 == 0,
  * N % 4 == 0, 16-byte aligned rows (else CLUSTEN_EUNSUPPORTED).  chain: K chunks of 32 summed inside one tensor-memory
- * accumulator before it is added to the fp32 running sum in registers (<= 0: default). */
+ * accumulator before it is added to the fp32 running sum in registers (<= 0: default).  ln_mean / ln_rstd [R], ln_gamma / ln_beta [K]
+ * (all NULL: off): the `norm1` / `norm2` / `norm` LayerNorm in front of the layer (aff.py:196-199,258) applied to the rows of x while
+ * they are staged, from the statistics clusten_layer_norm_fwd writes when called with y = NULL. */
 int clusten_tf32_split(const float *w, float *hi, float *lo, int64_t n, void *stream);
 int clusten_linear_tc_f32(const float *x, const float *w_hi, const float *w_lo, const float *bias, const float *res,
                           const float *gamma, float *y, int64_t R, int K, int N, int64_t ldx, int64_t ldy, int64_t ldres,
-                          int epi, float alpha, int alpha_cols, int chain, void *stream);
+                          int epi, float alpha, int alpha_cols, int chain, const float *ln_mean, const float *ln_rstd,
+                          const float *ln_gamma, const float *ln_beta, void *stream);
 
 /* ---- column sum: out[c] += sum_r x[r*ld + c] (fp32 accumulation INTO out; caller zeroes it).  The bias gradient of the
  * backbone's Linear layers (grad_bias = grad_output.sum(0)); x fp32 / fp16 / bf16, C and ld multiples of 16 bytes. */

@@ -613,6 +613,32 @@ def test_linear_tc_tcgen05(R, K, N, epilogue):
     assert rel_err(ys.cpu().double(), reference(wide[:, :K].cpu(), b, gam)) <= 2e-6
 
 
+@pytest.mark.parametrize("R,K,N", [(1000, 32, 96), (4173, 128, 256), (300, 96, 288), (2049, 1024, 128)])
+@pytest.mark.parametrize("epilogue", ["bias", "gelu"])
+def test_linear_tc_layer_norm_in_gemm(R, K, N, epilogue):
+    """``linear_tc(..., ln=...)``: the LayerNorm in front of the layer (aff.py:196-199 norm1 / norm2, aff.py:258 merge norm) applied to
+    the rows while the GEMM stages them, from the statistics of the LayerNorm kernel itself (clusten_layer_norm_fwd with y = NULL).
+    Equal to LayerNorm-then-linear_tc BIT FOR BIT (same statistics, same rounding of the normalised value), and to float64 at 2e-6."""
+    from autofocusformermod_b200 import ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(R + K + N)
+    x = (torch.randn(R, K, generator=g) * 1.7 + 0.4).cuda()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    lw, lb = (torch.rand(K, generator=g) + 0.5).cuda(), torch.randn(K, generator=g).cuda()
+    mean, rstd = ops.layer_norm_stats(x, lw, lb, 1e-5)
+    xd = x.double()
+    m64, v64 = xd.mean(1), xd.var(1, unbiased=False)
+    assert rel_err(mean.double(), m64) <= 1e-6 and rel_err(rstd.double(), (v64 + 1e-5).rsqrt()) <= 1e-6
+    y = ops.linear_tc(x, w, b, epilogue, ln=(mean, rstd, lw, lb))
+    y_two = ops.linear_tc(ops.layer_norm(x, lw, lb, 1e-5), w, b, epilogue)
+    assert torch.equal(y, y_two)
+    ref = F.layer_norm(xd, (K,), lw.double(), lb.double(), 1e-5) @ w.double().t() + b.double()
+    if epilogue == "gelu":
+        ref = F.gelu(ref)
+    assert rel_err(y.double(), ref) <= 2e-6
+
+
 def test_linear_tc_weight_split_follows_the_weight():
     """The (hi, lo) operands are cached per weight and rebuilt when the weight is updated in place."""
     from autofocusformermod_b200 import ops

@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_ops.py -x -q -m gpu -k "linear_tc" > gpurun_out/pytest_lin.log 2>&1; echo "pytest lin rc=$?"; tail -4 gpurun_out/pytest_lin.log
+timeout 1200 python -m pytest tests/test_gpu_aff.py tests/test_gpu_dropin.py tests/test_gpu_scale.py -x -q -m gpu > gpurun_out/pytest_aff.log 2>&1; echo "pytest aff rc=$?"; tail -4 gpurun_out/pytest_aff.log
+timeout 600 python bench.py --no-extras > gpurun_out/bench_ln.json 2> gpurun_out/bench_ln.err; echo "bench rc=$?"; python - <<'PY'
+import json
+r=json.loads(open("gpurun_out/bench_ln.json").read().strip().splitlines()[-1])
+print(r["value"], r["ms_per_step"], "e2e", r["e2e"]["value"], r["roofline"]["kernel"], r["roofline"]["frac"], r["roofline"].get("tensor"))
+print(r["roofline"]["per_entry_ms_per_step"])
+PY
