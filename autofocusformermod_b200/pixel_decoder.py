@@ -16,7 +16,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
-from .aff import REL_POS_WIDTH, TABLE_WIDTH, _TableLookup
+from .aff import REL_POS_WIDTH, TABLE_WIDTH, LayerNorm, Linear, _TableLookup
 from .ops import CLUSTENWFFunction, MSDETRPCFunction
 from .point_utils import knn_keops, shepard_decay_weights, table_rank, upsample_feature_shepard
 
@@ -26,8 +26,10 @@ class PointConv(nn.Module):
         super().__init__()
         inner_ch = 4
         self.weight_net = nn.Sequential(nn.Linear(5, inner_ch, bias=True), nn.LayerNorm(inner_ch), nn.GELU())
-        self.norm = nn.LayerNorm(inner_ch * dim)
-        self.linear = nn.Linear(dim * inner_ch, out_dim, bias=bias)
+        # (aff.LayerNorm / aff.Linear: nn.LayerNorm / nn.Linear with the same parameters; in fp32 inference the pair runs as one
+        # tcgen05 GEMM with the norm applied while the rows are staged)
+        self.norm = LayerNorm(inner_ch * dim)
+        self.linear = Linear(dim * inner_ch, out_dim, bias=bias)
 
     def forward(self, inp):
         """inp = (x [b,n,c] point features, pos [b,n,2] point positions) -> [b,n,out_dim]"""
@@ -42,7 +44,7 @@ class PointConv(nn.Module):
         uniq, inverse, count = table_rank(pe_idx)
         weights = _TableLookup(uniq=uniq, inverse=inverse, count=count)(self.weight_net)
         feat = CLUSTENWFFunction.apply(weights, x, nn_idx).reshape(b, n, -1)                   # :309
-        return self.linear(self.norm(feat))                                                    # :311-313
+        return self.linear.fused(feat, "bias", norm=self.norm)                                  # :311-313
 
 
 def scale_pos(last_pos, last_ss, cur_ss, no_bias=False):
@@ -76,10 +78,10 @@ class MSDeformAttnPc(nn.Module):
     def __init__(self, d_model, n_levels, n_heads, n_points, shepard_power, shepard_power_learnable):
         super().__init__()
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
-        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
-        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
-        self.value_proj = nn.Linear(d_model, d_model)
-        self.output_proj = nn.Linear(d_model, d_model)
+        self.sampling_offsets = Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = Linear(d_model, d_model)
+        self.output_proj = Linear(d_model, d_model)
         self.shepard_power = nn.Parameter(shepard_power * torch.ones(1)) if shepard_power_learnable else shepard_power
         self._reset_parameters()
 
