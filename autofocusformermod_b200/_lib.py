@@ -36,7 +36,8 @@ SIGNATURES = {
     "clusten_col_sum": (_I, [_P, _P, _L, _I, _L, _I, _P]),
     "clusten_linear_f32": (_I, [_P] * 4 + [_L, _I, _I, _L, _L, _P]),
     "clusten_tf32_split": (_I, [_P, _P, _P, _L, _P]),
-    "clusten_linear_tc_f32": (_I, [_P] * 7 + [_L, _I, _I, _L, _L, _L, _I, _c.c_float, _I, _I] + [_P] * 5),
+    "clusten_f16_split": (_I, [_P, _P, _P, _L, _I, _P, _P, _P]),
+    "clusten_linear_tc_f32": (_I, [_P] * 7 + [_L, _I, _I, _L, _L, _L, _I, _c.c_float, _I, _I] + [_P] * 4 + [_I, _P, _P]),
     "clusten_table_linear_fwd": (_I, [_P] * 4 + [_I] * 3 + [_P, _P]),
     "clusten_table_linear_bwd": (_I, [_P] * 4 + [_I] * 3 + [_P, _P]),
     "clusten_scale_residual_fwd": (_I, [_P] * 5 + [_L, _L, _I, _I, _I, _I, _P]),

@@ -88,10 +88,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 // round to TF32 (nearest, ties away -- cvt.rna) on the bit pattern: the low 13 mantissa bits end up zero
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
-                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+// D[tmem] (+)= A[tmem] . B[smem]^T; H: fp16 operands (kind::f16, K = 16 per instruction), else TF32 (kind::tf32, K = 8)
+template <bool H>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (H)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                     ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                     ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major SWIZZLE_64B descriptor (rows of 64 bytes, 8-row groups 512 bytes apart): the fp16 weight boxes [BN x 32 halves]
+__device__ __forceinline__ uint64_t umma_desc64(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+                   "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
@@ -115,19 +131,24 @@ constexpr int NA = 4;                                  // A-operand stages in te
 constexpr int A_COL0 = 256;                            // tensor-memory columns 0..255: the two accumulators, 256..511: the A ring
 constexpr int SUB_BYTES = BM * 128;                    // one [128 rows x 32 columns] piece of the output tile, 16 KiB
 
-template <int BN> struct Cfg {
-    static constexpr int B_BYTES = BN * BK * 4;
+// H: the operands are split into fp16 hi / lo (11 + 11 significand bits, as the TF32 split) and multiplied with kind::f16 -- K = 16 per
+// instruction at the same 64 cycles, so half the MMAs, half the weight bytes and half the TMEM columns of the TF32 form.
+template <int BN, bool H> struct Cfg {
+    static constexpr int B_BYTES = BN * BK * (H ? 2 : 4);
     static constexpr int WSTAGE = 2 * B_BYTES;                           // wh | wl
-    static constexpr int WS = BN >= 96 ? 3 : 4;                          // weight ring (L2-resident operand: short latency)
+    static constexpr int WS = BN >= 96 && !H ? 3 : 4;                    // weight ring (L2-resident operand: short latency)
     static constexpr int NSUB = BN / 32;                                 // output pieces per tile
     static constexpr int CSETS = BN >= 96 ? 1 : 2;                       // tile-sized output staging sets
     static constexpr int CBUF = CSETS * NSUB * SUB_BYTES;
-    static constexpr int TAIL = 2048;                                    // barriers, TMEM slot, bias / gamma of the tile
+    static constexpr int TAIL = 2560;                                    // barriers, TMEM slot, bias / gamma / weight scale of the tile
     // the X ring takes what is left of 227 KiB, at most 8 stages: X comes from HBM and its latency is what the ring has to cover
     static constexpr int XS_FIT = (232448 - 1024 - TAIL - CBUF - WS * WSTAGE) / A_BYTES;
     static constexpr int XS = XS_FIT > 8 ? 8 : XS_FIT;
     static constexpr int ACC_COLS = BN == 96 ? 128 : BN;                 // column pitch of the two accumulators
-    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    static constexpr int A_COLS = H ? 32 : 64;                           // TMEM columns of one A stage: xh | xl
+    static constexpr int KSTEPS = H ? BK / 16 : BK / 8;                  // MMA K steps per chunk (8 TMEM columns / 32 B of B each)
+    static constexpr uint32_t IDESC = (1u << 4) | ((H ? 0u : 2u) << 7) | ((H ? 0u : 2u) << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                      ((uint32_t)(BM >> 4) << 24);
     static constexpr int XRING = XS * A_BYTES, RING = XRING + WS * WSTAGE;
     static constexpr size_t SMEM = (size_t)RING + CBUF + TAIL + 1024 /* alignment slack */;
     static_assert(XS >= 3, "X ring too shallow");
@@ -142,14 +163,15 @@ struct Args {
     int tiles_m, tiles_n, chain;
     float alpha;
     int alpha_cols;
+    const float *w_inv_scale;                              // fp16 split: 1 / (power-of-two scale of weight row n), [N]
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool H>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWh,
                  const __grid_constant__ CUtensorMap mapWl, const __grid_constant__ CUtensorMap mapY,
                  const __grid_constant__ CUtensorMap mapRes, const Args a) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, H>;
     constexpr int XS = C::XS, WS = C::WS;
     extern __shared__ uint8_t tc_smem_raw[];
     const uint32_t base = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
@@ -160,7 +182,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const uint32_t bar_cfull = bar_acce + 16;                            // CSETS * NSUB barriers
     uint8_t *gtail = gbase + C::RING + C::CBUF;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gtail + 512);
-    float *s_bias = reinterpret_cast<float *>(gtail + 1024), *s_gamma = s_bias + 128;
+    float *s_bias = reinterpret_cast<float *>(gtail + 1024), *s_gamma = s_bias + 128, *s_wsc = s_bias + 256;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -238,16 +260,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint32_t st = wring + s * C::WSTAGE;
-                    const uint64_t wh = umma_desc(st), wl = umma_desc(st + C::B_BYTES);
-                    const uint32_t xh = tmem + A_COL0 + sa * 64, xl = xh + 32;
+                    const uint64_t wh = H ? umma_desc64(st) : umma_desc(st), wl = H ? umma_desc64(st + C::B_BYTES) : umma_desc(st + C::B_BYTES);
+                    const uint32_t xh = tmem + A_COL0 + sa * C::A_COLS, xl = xh + C::A_COLS / 2;
                     const uint32_t d = tmem + buf * C::ACC_COLS;
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k)                     // one K = 8 step: 8 TMEM columns of A, 32 bytes (+2) of B
-                        umma_tf32_ts(d, xl + 8 * k, wh + 2 * k, C::IDESC, (first && k == 0) ? 0u : 1u);
+                    for (int k = 0; k < C::KSTEPS; ++k)                  // one K step: 8 TMEM columns of A, 32 bytes (+2) of B
+                        umma_ts<H>(d, xl + 8 * k, wh + 2 * k, C::IDESC, (first && k == 0) ? 0u : 1u);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) umma_tf32_ts(d, xh + 8 * k, wl + 2 * k, C::IDESC, 1u);
+                    for (int k = 0; k < C::KSTEPS; ++k) umma_ts<H>(d, xh + 8 * k, wl + 2 * k, C::IDESC, 1u);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) umma_tf32_ts(d, xh + 8 * k, wh + 2 * k, C::IDESC, 1u);
+                    for (int k = 0; k < C::KSTEPS; ++k) umma_ts<H>(d, xh + 8 * k, wh + 2 * k, C::IDESC, 1u);
                     umma_commit(bar_wempty + 8 * s);                     // both rings are free once these MMAs have read them
                     umma_commit(bar_aempty + 8 * sa);
                     if (last) umma_commit(bar_accf + 8 * buf);
@@ -280,15 +302,27 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                         x[c].z = fmaf((x[c].z - mu) * rs, g.z, b.z); x[c].w = fmaf((x[c].w - mu) * rs, g.w, b.w);
                     }
                 }
-                uint32_t h[32], l[32];
+                uint32_t h[H ? 16 : 32], l[H ? 16 : 32];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float xv[4] = {x[c].x, x[c].y, x[c].z, x[c].w};
+                    if (H) {                                             // fp16 hi / lo, two K elements per 32-bit TMEM column (even k low)
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float hv = tf32_rn(xv[e]);
-                        h[4 * c + e] = __float_as_uint(hv);
-                        l[4 * c + e] = __float_as_uint(tf32_rn(xv[e] - hv));
+                        for (int e = 0; e < 4; e += 2) {
+                            const float x0 = fminf(fmaxf(xv[e], -65504.f), 65504.f), x1 = fminf(fmaxf(xv[e + 1], -65504.f), 65504.f);
+                            const __half2 hh = __floats2half2_rn(x0, x1);
+                            const float2 hf = __half22float2(hh);
+                            const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                            h[2 * c + e / 2] = *reinterpret_cast<const uint32_t *>(&hh);
+                            l[2 * c + e / 2] = *reinterpret_cast<const uint32_t *>(&ll);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float hv = tf32_rn(xv[e]);
+                            h[4 * c + e] = __float_as_uint(hv);
+                            l[4 * c + e] = __float_as_uint(tf32_rn(xv[e] - hv));
+                        }
                     }
                 }
                 // Generic-proxy reads, then async-proxy (TMA) writes to the same slot: the release needs a proxy fence.  Without it
@@ -300,9 +334,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 mbar_wait(bar_aempty + 8 * sa, pa ^ 1u);                 // the MMAs of NA chunks ago are done with this A stage
                 __syncwarp();                                            // (.sync.aligned below: the lanes left the spin loops apart)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t ta = tmem + lane_off + A_COL0 + sa * 64;
-                tmem_st32(ta, h);
-                tmem_st32(ta + 32, l);
+                const uint32_t ta = tmem + lane_off + A_COL0 + sa * C::A_COLS;
+                if constexpr (H) {
+                    tmem_st16(ta, h);
+                    tmem_st16(ta + 16, l);
+                } else {
+                    tmem_st32(ta, h);
+                    tmem_st32(ta + 32, l);
+                }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(bar_afull + 8 * sa);
@@ -340,6 +379,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 const bool in = n0 + et < a.N;                           // readers all passed the barrier before its stores)
                 s_bias[et] = a.bias && in ? __ldg(a.bias + n0 + et) : 0.f;
                 if (EPI == EPI_RES) s_gamma[et] = a.gamma && in ? __ldg(a.gamma + n0 + et) : 1.f;
+                if (H) s_wsc[et] = in ? __ldg(a.w_inv_scale + n0 + et) : 1.f;     // powers of two: undo the row scaling of the fp16 weights
             }
             for (int kc0 = 0; kc0 < KC; kc0 += chain, ++ch) {
                 const uint32_t buf = ch & 1u;
@@ -373,7 +413,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     mbar_wait(bar_cfull + 8 * (set * C::NSUB + j), (C::CSETS == 2 ? (nt >> 1) : nt) & 1u);
                 float4 *cell = reinterpret_cast<float4 *>(gbase + C::RING + (set * C::NSUB + j) * SUB_BYTES + swz(row, c));
                 const float4 bv = *reinterpret_cast<const float4 *>(s_bias + col);
-                float o[4] = {acc[4 * i] + bv.x, acc[4 * i + 1] + bv.y, acc[4 * i + 2] + bv.z, acc[4 * i + 3] + bv.w};
+                float o[4];
+                if (H) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(s_wsc + col);
+                    o[0] = fmaf(acc[4 * i], wv.x, bv.x); o[1] = fmaf(acc[4 * i + 1], wv.y, bv.y);
+                    o[2] = fmaf(acc[4 * i + 2], wv.z, bv.z); o[3] = fmaf(acc[4 * i + 3], wv.w, bv.w);
+                } else {
+                    o[0] = acc[4 * i] + bv.x; o[1] = acc[4 * i + 1] + bv.y; o[2] = acc[4 * i + 2] + bv.z; o[3] = acc[4 * i + 3] + bv.w;
+                }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     if (EPI == EPI_BIAS) {
@@ -429,6 +476,23 @@ __global__ void tf32_split_kernel(const float *__restrict__ w, float *__restrict
     }
 }
 
+// hi = fp16(w * s_n), lo = fp16(w * s_n - hi) with s_n = the power of two that brings the largest |w| of OUTPUT ROW n to [512, 1024):
+// both halves stay in the normal fp16 range for every weight within 2^-13 of the row's largest (smaller ones lose bits that are below
+// fp32 resolution of that output's sum); inv_scale[n] = 1 / s_n is applied to column n in the epilogue
+__global__ void f16_split_kernel(const float *__restrict__ w, __half *__restrict__ hi, __half *__restrict__ lo, int64_t n, int K,
+                                 const float *__restrict__ amax, float *__restrict__ inv_scale) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int64_t row = i / K;
+        const float sc = exp2f(floorf(log2f(1024.f / fmaxf(amax[row], 1e-30f))));
+        if (i == row * K) inv_scale[row] = 1.f / sc;
+        const float x = w[i] * sc;
+        const __half h = __float2half_rn(x);
+        hi[i] = h;
+        lo[i] = __float2half_rn(x - __half2float(h));
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -444,14 +508,16 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// fp32 matrix [rows, K] with row stride ld (elements); box = [32 columns x box_rows], 128-byte swizzle, rows past the end read as 0
-static bool map_2d(CUtensorMap *m, const float *ptr, int64_t rows, int K, int64_t ld, int box_rows) {
+// matrix [rows, K] with row stride ld (elements), fp32 or fp16; box = [32 columns x box_rows] (one 128- or 64-byte swizzle row), rows
+// past the end read as 0
+static bool map_2d(CUtensorMap *m, const void *ptr, int64_t rows, int K, int64_t ld, int box_rows, bool half = false) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)ld * (half ? 2 : 4)};
     const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows}, estr[2] = {1u, 1u};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return enc(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(ptr), dims, strides, box,
+               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int sm_count() {
@@ -464,28 +530,38 @@ static int sm_count() {
     return n;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool H>
 static int launch(const CUtensorMap *m, const Args &a, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(linear_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::SMEM) != cudaSuccess)
-            return set_error(CLUSTEN_EUNSUPPORTED, "linear_tc: cannot reserve %zu bytes of shared memory", Cfg<BN>::SMEM);
+        if (cudaFuncSetAttribute(linear_tc_kernel<BN, EPI, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN, H>::SMEM) != cudaSuccess)
+            return set_error(CLUSTEN_EUNSUPPORTED, "linear_tc: cannot reserve %zu bytes of shared memory", Cfg<BN, H>::SMEM);
         attr_set = true;
     }
     const int tiles = a.tiles_m * a.tiles_n;
-    linear_tc_kernel<BN, EPI><<<std::min(tiles, sm_count()), THREADS, Cfg<BN>::SMEM, st>>>(m[0], m[1], m[2], m[3], m[4], a);
+    linear_tc_kernel<BN, EPI, H><<<std::min(tiles, sm_count()), THREADS, Cfg<BN, H>::SMEM, st>>>(m[0], m[1], m[2], m[3], m[4], a);
     note_launches(1);
     return check_launch("linear_tc");
 }
 
-template <int BN>
+template <int BN, bool H>
 static int launch_epi(int epi, const CUtensorMap *m, const Args &a, cudaStream_t st) {
     switch (epi) {
-        case EPI_BIAS: return launch<BN, EPI_BIAS>(m, a, st);
-        case EPI_GELU: return launch<BN, EPI_GELU>(m, a, st);
-        case EPI_RES: return launch<BN, EPI_RES>(m, a, st);
+        case EPI_BIAS: return launch<BN, EPI_BIAS, H>(m, a, st);
+        case EPI_GELU: return launch<BN, EPI_GELU, H>(m, a, st);
+        case EPI_RES: return launch<BN, EPI_RES, H>(m, a, st);
     }
     return set_error(CLUSTEN_EINVAL, "linear_tc: unknown epilogue %d", epi);
+}
+
+template <bool H>
+static int launch_bn(int BN, int epi, const CUtensorMap *m, const Args &a, cudaStream_t st) {
+    switch (BN) {
+        case 128: return launch_epi<128, H>(epi, m, a, st);
+        case 96: return launch_epi<96, H>(epi, m, a, st);
+        case 64: return launch_epi<64, H>(epi, m, a, st);
+        default: return launch_epi<32, H>(epi, m, a, st);
+    }
 }
 
 }  // namespace tc
@@ -508,11 +584,24 @@ extern "C" int clusten_tf32_split(const float *w, float *hi, float *lo, int64_t 
 // summed inside the tensor-core accumulator before it is added to the fp32 running sum (<= 0: the default, 4).
 // ln_mean / ln_rstd [R] + ln_gamma / ln_beta [K] (or all NULL): the rows of X are LayerNorm-ed while they are split, with the
 // statistics clusten_layer_norm_fwd(y = NULL) wrote -- the `self.norm1(x)` / `self.norm2(x)` / `self.norm(x)` in front of the layer.
+// w_fp16 = 1: w_hi / w_lo are the fp16 operands of clusten_f16_split and w_inv_scale [N] its per-row factors; X is split into fp16 hi / lo
+// as well (values beyond +-65504 saturate) and the products run as kind::f16 -- half the MMAs of the TF32 form at the same accuracy.
 // Needs K % 32 == 0, N % 4 == 0, 16-byte aligned rows; anything else returns CLUSTEN_EUNSUPPORTED.
-extern "C" int clusten_linear_tc_f32(const float *x, const float *w_hi, const float *w_lo, const float *bias, const float *res,
+// fp16 form of clusten_tf32_split for a weight [N, K]: hi / lo fp16 of w[n,:] * s_n, s_n the power of two that brings amax[n] (device,
+// max |w[n,:]|) to [512, 1024); writes 1 / s_n to inv_scale[n] (device, [N]) for the epilogue of clusten_linear_tc_f32(w_fp16 = 1).
+extern "C" int clusten_f16_split(const float *w, void *hi, void *lo, int64_t N, int K, const float *amax, float *inv_scale, void *stream) {
+    if (N < 0 || K <= 0 || !amax || !inv_scale || (N > 0 && (!w || !hi || !lo))) return set_error(CLUSTEN_EINVAL, "f16_split: bad arguments");
+    if (N == 0) return 0;
+    const int64_t n = N * K;
+    tc::f16_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, (__half *)hi, (__half *)lo, n, K, amax, inv_scale);
+    note_launches(1);
+    return check_launch("f16_split");
+}
+
+extern "C" int clusten_linear_tc_f32(const float *x, const void *w_hi, const void *w_lo, const float *bias, const float *res,
                                      const float *gamma, float *y, int64_t R, int K, int N, int64_t ldx, int64_t ldy, int64_t ldres,
                                      int epi, float alpha, int alpha_cols, int chain, const float *ln_mean, const float *ln_rstd,
-                                     const float *ln_gamma, const float *ln_beta, void *stream) {
+                                     const float *ln_gamma, const float *ln_beta, int w_fp16, const float *w_inv_scale, void *stream) {
     if (R < 0 || K <= 0 || N <= 0 || ldx < K || ldy < N || !x || !w_hi || !w_lo || !y || (epi == tc::EPI_RES && (!res || ldres < N)))
         return set_error(CLUSTEN_EINVAL, "linear_tc: bad arguments R=%lld K=%d N=%d", (long long)R, K, N);
     if ((ln_mean != nullptr) != (ln_rstd != nullptr) || (ln_mean && (!ln_gamma || !ln_beta || !aligned16(ln_gamma) || !aligned16(ln_beta))))
@@ -528,7 +617,8 @@ extern "C" int clusten_linear_tc_f32(const float *x, const float *w_hi, const fl
         if (w < waste) { waste = w; BN = cand; }
     }
     CUtensorMap m[5];
-    if (!tc::map_2d(&m[0], x, R, K, ldx, tc::BM) || !tc::map_2d(&m[1], w_hi, N, K, K, BN) || !tc::map_2d(&m[2], w_lo, N, K, K, BN) ||
+    const bool half = w_fp16 != 0;
+    if (!tc::map_2d(&m[0], x, R, K, ldx, tc::BM) || !tc::map_2d(&m[1], w_hi, N, K, K, BN, half) || !tc::map_2d(&m[2], w_lo, N, K, K, BN, half) ||
         !tc::map_2d(&m[3], y, R, N, ldy, tc::BM) || !tc::map_2d(&m[4], epi == tc::EPI_RES ? res : y, R, N, epi == tc::EPI_RES ? ldres : ldy, tc::BM))
         return set_error(CLUSTEN_EUNSUPPORTED, "linear_tc: cuTensorMapEncodeTiled failed");
     tc::Args a;
@@ -538,11 +628,8 @@ extern "C" int clusten_linear_tc_f32(const float *x, const float *w_hi, const fl
     a.tiles_m = (int)((R + tc::BM - 1) / tc::BM); a.tiles_n = (N + BN - 1) / BN;
     a.chain = chain > 0 ? chain : 4;
     a.alpha = alpha; a.alpha_cols = epi == tc::EPI_BIAS ? alpha_cols : 0;
+    if (half && !w_inv_scale) return set_error(CLUSTEN_EINVAL, "linear_tc: the fp16 split needs w_inv_scale [N]");
+    a.w_inv_scale = half ? w_inv_scale : nullptr;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (BN) {
-        case 128: return tc::launch_epi<128>(epi, m, a, st);
-        case 96: return tc::launch_epi<96>(epi, m, a, st);
-        case 64: return tc::launch_epi<64>(epi, m, a, st);
-        default: return tc::launch_epi<32>(epi, m, a, st);
-    }
+    return half ? tc::launch_bn<true>(BN, epi, m, a, st) : tc::launch_bn<false>(BN, epi, m, a, st);
 }

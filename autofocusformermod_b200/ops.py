@@ -865,6 +865,37 @@ def tf32_split(weight):
     return hi, lo
 
 
+# which split the tcgen05 Linear multiplies with: "f16" (fp16 hi / lo, kind::f16: half the MMAs) or "tf32" (TF32 hi / lo, kind::tf32)
+# Default ("auto"): fp16 where the input scale is known -- the LayerNorm-fused layers, whose rows are normalised -- and TF32 elsewhere
+# (fp16 has no exponent headroom for x: elements below 2^-14 keep an absolute error of 2^-25, values beyond 65504 saturate).
+LINEAR_TC_SPLIT = os.environ.get("CLUSTEN_TC_SPLIT", "auto")
+_split16_cache = {}
+
+
+def f16_split(weight):
+    """(hi, lo, inv_scale) of an fp32 weight [N, K] for clusten_linear_tc_f32(w_fp16 = 1) (clusten_f16_split): fp16 halves of
+    w[n] * s_n with s_n the power of two that brings max |w[n]| to [512, 1024), and 1 / s_n as a device vector [N].  No host read;
+    cached until the weight changes."""
+    import weakref
+    key = id(weight)
+    hit = _split16_cache.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
+        return hit[3], hit[4], hit[5]
+    dev = _lib.require_cuda(weight)
+    w = weight.detach().contiguous()
+    hi = torch.empty(w.shape, dtype=torch.float16, device=dev)
+    lo = torch.empty_like(hi)
+    amax = w.abs().amax(dim=1).float().contiguous()
+    inv = torch.empty(w.shape[0], dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call("clusten_f16_split", dev, w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.shape[0], w.shape[1], amax.data_ptr(), inv.data_ptr(),
+              nbytes=8 * w.numel())
+    if len(_split16_cache) > 4096:
+        _split16_cache.clear()
+    _split16_cache[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), hi, lo, inv)
+    return hi, lo, inv
+
+
 def linear_tc_supported(x, weight, bias=None, res=None, gamma=None):
     K = x.shape[-1]
     ok = (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.dim() == 2 and weight.shape[1] == K
@@ -874,7 +905,7 @@ def linear_tc_supported(x, weight, bias=None, res=None, gamma=None):
     return bool(ok)
 
 
-def linear_tc(x, weight, bias=None, epilogue="bias", res=None, gamma=None, alpha=1.0, alpha_cols=0, chain=None, ln=None):
+def linear_tc(x, weight, bias=None, epilogue="bias", res=None, gamma=None, alpha=1.0, alpha_cols=0, chain=None, ln=None, split=None):
     """fp32 ``F.linear`` on the tcgen05 tensor cores (clusten_linear_tc_f32; inference, no autograd) with one of
     ``bias`` (y = x W^T + b, the first ``alpha_cols`` columns then times ``alpha``), ``gelu`` (y = GELU(x W^T + b)) or
     ``residual`` (y = res + gamma * (x W^T + b)) as the epilogue.  ``ln`` = (mean, rstd, ln_weight, ln_bias): the rows of x are
@@ -884,7 +915,12 @@ def linear_tc(x, weight, bias=None, epilogue="bias", res=None, gamma=None, alpha
     x2 = x.reshape(-1, K)
     if x2.stride(1) != 1 or x2.stride(0) % 4 or x2.data_ptr() % 16:
         x2 = x2.contiguous()
-    hi, lo = tf32_split(weight)
+    mode = split or LINEAR_TC_SPLIT
+    half = mode == "f16" or (mode == "auto" and ln is not None)
+    if half:
+        hi, lo, inv = f16_split(weight)
+    else:
+        (hi, lo), inv = tf32_split(weight), None
     b = None if bias is None else bias.detach().contiguous()
     g = None if gamma is None else gamma.detach().contiguous()
     R = x2.shape[0]
@@ -904,7 +940,7 @@ def linear_tc(x, weight, bias=None, epilogue="bias", res=None, gamma=None, alpha
     with torch.cuda.device(dev):
         _call("clusten_linear_tc_f32", dev, x2.data_ptr(), hi.data_ptr(), lo.data_ptr(), _lib.ptr(b), _lib.ptr(r2), _lib.ptr(g),
               y.data_ptr(), R, K, N, x2.stride(0), N, ldres, LINEAR_EPI[epilogue], float(alpha), int(alpha_cols),
-              LINEAR_TC_CHAIN if chain is None else int(chain), *lnp, nbytes=4 * (R * (K + N * (2 if r2 is not None else 1)) + 2 * N * K),
+              LINEAR_TC_CHAIN if chain is None else int(chain), *lnp, int(half), _lib.ptr(inv), nbytes=4 * (R * (K + N * (2 if r2 is not None else 1)) + 2 * N * K),
               flops=2 * R * K * N)
     return y.view(*x.shape[:-1], N)
 

@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--chain", type=int, default=0)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--check-only", action="store_true")
+    ap.add_argument("--split", default=None, help="f16 | tf32 (default: the library default, CLUSTEN_TC_SPLIT)")
     ap.add_argument("--only", default="", help="comma-separated stage:layer picks, e.g. 0:proj,1:q+kv")
     a = ap.parse_args()
     from autofocusformermod_b200 import ops
@@ -80,7 +81,7 @@ def main():
                 return y
 
             def our_fn():
-                return ops.linear_tc(x, w, b, epi, res=res, gamma=gam, alpha=0.25, alpha_cols=C, chain=a.chain)
+                return ops.linear_tc(x, w, b, epi, res=res, gamma=gam, alpha=0.25, alpha_cols=C, chain=a.chain, split=a.split)
 
             sub = slice(0, min(R, 8192))
             y64 = x[sub].double() @ w.double().t() + b.double()

@@ -252,12 +252,18 @@ int clusten_linear_f32(const float *x, const float *weight, const float *bias, f
  * N % 4 == 0, 16-byte aligned rows (else CLUSTEN_EUNSUPPORTED).  chain: K chunks of 32 summed inside one tensor-memory
  * accumulator before it is added to the fp32 running sum in registers (<= 0: default).  ln_mean / ln_rstd [R], ln_gamma / ln_beta [K]
  * (all NULL: off): the `norm1` / `norm2` / `norm` LayerNorm in front of the layer (aff.py:196-199,258) applied to the rows of x while
- * they are staged, from the statistics clusten_layer_norm_fwd writes when called with y = NULL. */
+ * they are staged, from the statistics clusten_layer_norm_fwd writes when called with y = NULL.
+ * w_fp16 = 1: the fp16 form of the split -- clusten_f16_split writes hi / lo [N,K] fp16 of w[n,:] * s_n (s_n = the power of two that
+ * brings amax[n] = max |w[n,:]| to [512, 1024)) and 1 / s_n to inv_scale[n]; the kernel splits x into fp16 hi / lo too (11 + 11
+ * significand bits like the TF32 form) and multiplies with kind::f16: half the MMAs and weight bytes.  x is NOT rescaled: |x| beyond
+ * 65504 saturates and elements below 2^-14 keep an absolute error of 2^-25, so this form is meant for inputs of known scale -- the
+ * Python layer uses it for the LayerNorm-fused layers (normalised rows) and the TF32 form elsewhere. */
 int clusten_tf32_split(const float *w, float *hi, float *lo, int64_t n, void *stream);
-int clusten_linear_tc_f32(const float *x, const float *w_hi, const float *w_lo, const float *bias, const float *res,
+int clusten_f16_split(const float *w, void *hi, void *lo, int64_t N, int K, const float *amax, float *inv_scale, void *stream);
+int clusten_linear_tc_f32(const float *x, const void *w_hi, const void *w_lo, const float *bias, const float *res,
                           const float *gamma, float *y, int64_t R, int K, int N, int64_t ldx, int64_t ldy, int64_t ldres,
                           int epi, float alpha, int alpha_cols, int chain, const float *ln_mean, const float *ln_rstd,
-                          const float *ln_gamma, const float *ln_beta, void *stream);
+                          const float *ln_gamma, const float *ln_beta, int w_fp16, const float *w_inv_scale, void *stream);
 
 /* ---- column sum: out[c] += sum_r x[r*ld + c] (fp32 accumulation INTO out; caller zeroes it).  The bias gradient of the
  * backbone's Linear layers (grad_bias = grad_output.sum(0)); x fp32 / fp16 / bf16, C and ld multiples of 16 bytes. */

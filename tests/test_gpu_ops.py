@@ -571,7 +571,8 @@ def test_linear_f32_tensor_core(R, K, N):
 @pytest.mark.parametrize("R,K,N", [(1000, 32, 32), (4173, 128, 256), (300, 96, 288), (129, 768, 2304), (1, 32, 4), (16384, 64, 32),
                                    (40000, 32, 96), (5000, 256, 100), (777, 1536, 384), (20000, 32, 36)])
 @pytest.mark.parametrize("epilogue", ["bias", "gelu", "residual"])
-def test_linear_tc_tcgen05(R, K, N, epilogue):
+@pytest.mark.parametrize("split", ["tf32", "f16"])
+def test_linear_tc_tcgen05(R, K, N, epilogue, split):
     """clusten_linear_tc_f32 (tcgen05.mma kind::tf32 through TMA and tensor memory, 3xTF32 split) against a float64 product for the
     three epilogues the block uses (aff.py:107-108 q * scale, aff.py:45-46 GELU(fc1), aff.py:230,236 shortcut + gamma * x): fp32-level
     accuracy; ragged R (not a multiple of the 128-row tile), N that is not a multiple of the column tile, several tiles per CTA
@@ -599,13 +600,13 @@ def test_linear_tc_tcgen05(R, K, N, epilogue):
 
     xc, wc, bc, rc, gc = x.cuda(), w.cuda(), b.cuda(), res.cuda(), gam.cuda()
     assert ops.linear_tc_supported(xc, wc, bc, rc, gc)
-    kw = dict(res=rc, gamma=gc, alpha=0.3, alpha_cols=ncol)
+    kw = dict(res=rc, gamma=gc, alpha=0.3, alpha_cols=ncol, split=split)
     y = ops.linear_tc(xc, wc, bc, epilogue, **kw)
     assert y.shape == (R, N) and y.dtype == torch.float32
     assert rel_err(y.cpu().double(), reference(x, b, gam)) <= 2e-6
     y1 = ops.linear_tc(xc, wc, bc, epilogue, chain=1, **kw)              # every K chunk summed in fp32 registers
     assert rel_err(y1.cpu().double(), reference(x, b, gam)) <= 1e-6
-    y3 = ops.linear_tc(xc.view(1, R, K), wc, None, epilogue, res=rc.view(1, R, N), gamma=None, alpha=0.3, alpha_cols=ncol)
+    y3 = ops.linear_tc(xc.view(1, R, K), wc, None, epilogue, res=rc.view(1, R, N), gamma=None, alpha=0.3, alpha_cols=ncol, split=split)
     assert y3.shape == (1, R, N)                                         # leading dims, no bias, no gamma
     assert rel_err(y3[0].cpu().double(), reference(x, None, None)) <= 2e-6
     wide = torch.randn(R, K + 32, generator=g).cuda()                    # row stride K + 32: consumed in place
@@ -615,7 +616,8 @@ def test_linear_tc_tcgen05(R, K, N, epilogue):
 
 @pytest.mark.parametrize("R,K,N", [(1000, 32, 96), (4173, 128, 256), (300, 96, 288), (2049, 1024, 128)])
 @pytest.mark.parametrize("epilogue", ["bias", "gelu"])
-def test_linear_tc_layer_norm_in_gemm(R, K, N, epilogue):
+@pytest.mark.parametrize("split", ["tf32", "f16", None])
+def test_linear_tc_layer_norm_in_gemm(R, K, N, epilogue, split):
     """``linear_tc(..., ln=...)``: the LayerNorm in front of the layer (aff.py:196-199 norm1 / norm2, aff.py:258 merge norm) applied to
     the rows while the GEMM stages them, from the statistics of the LayerNorm kernel itself (clusten_layer_norm_fwd with y = NULL).
     Equal to LayerNorm-then-linear_tc BIT FOR BIT (same statistics, same rounding of the normalised value), and to float64 at 2e-6."""
@@ -630,13 +632,40 @@ def test_linear_tc_layer_norm_in_gemm(R, K, N, epilogue):
     xd = x.double()
     m64, v64 = xd.mean(1), xd.var(1, unbiased=False)
     assert rel_err(mean.double(), m64) <= 1e-6 and rel_err(rstd.double(), (v64 + 1e-5).rsqrt()) <= 1e-6
-    y = ops.linear_tc(x, w, b, epilogue, ln=(mean, rstd, lw, lb))
-    y_two = ops.linear_tc(ops.layer_norm(x, lw, lb, 1e-5), w, b, epilogue)
+    y = ops.linear_tc(x, w, b, epilogue, ln=(mean, rstd, lw, lb), split=split)     # None: the default, fp16 for normalised rows
+    y_two = ops.linear_tc(ops.layer_norm(x, lw, lb, 1e-5), w, b, epilogue, split=split or "f16")
     assert torch.equal(y, y_two)
     ref = F.layer_norm(xd, (K,), lw.double(), lb.double(), 1e-5) @ w.double().t() + b.double()
     if epilogue == "gelu":
         ref = F.gelu(ref)
     assert rel_err(y.double(), ref) <= 2e-6
+
+
+def test_linear_tc_f16_split_scales():
+    """The fp16 form of the split (kind::f16, half the MMAs): weight rows of very different magnitude each get their own power-of-two
+    scale, undone per output column in the epilogue; activations up to the fp16 range are exact to 22 bits, beyond it they saturate
+    instead of turning into inf / NaN."""
+    from autofocusformermod_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    R, K, N = 3000, 256, 160
+    x = (torch.randn(R, K, generator=g) * 40.0).cuda()
+    w = torch.randn(N, K, generator=g) * K ** -0.5
+    w = (w * torch.logspace(-7, 3, N).unsqueeze(1)).cuda()               # output rows from 1e-7 to 1e3
+    b = torch.zeros(N).cuda()
+    y = ops.linear_tc(x, w, b, split="f16")
+    ref = x.double() @ w.double().t()
+    col_err = (y.double() - ref).abs().amax(0) / ref.abs().amax(0)       # every output column on its own scale
+    assert float(col_err.max()) <= 2e-6, float(col_err.max())
+    hi, lo, inv = ops.f16_split(w)
+    assert hi.dtype == torch.float16 and inv.shape == (N,)
+    scaled = (hi.float() + lo.float()) * inv.unsqueeze(1)
+    assert float(((scaled - w).abs().amax(1) / w.abs().amax(1)).max()) <= 2.0 ** -21
+    big = x.clone()
+    big[0, 0] = 3.0e5                                                    # beyond fp16: saturates at 65504, finite result
+    yb = ops.linear_tc(big, w, b, split="f16")
+    assert bool(torch.isfinite(yb).all())
+    assert rel_err(yb[1:], y[1:]) == 0.0                                 # the other rows are untouched
+    assert rel_err(ops.linear_tc(big, w, b, split="tf32").double()[0], (big.double() @ w.double().t())[0]) <= 2e-6   # TF32 form: full range
 
 
 def test_linear_tc_weight_split_follows_the_weight():

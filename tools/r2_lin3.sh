@@ -8,5 +8,5 @@ for l in open(sys.argv[1]):
     else: print(r)
 PY
 }
-timeout 300 python benchmarks/linear_bench.py --model mini > gpurun_out/lin_mini.log 2>&1; echo "mini rc=$?"; show gpurun_out/lin_mini.log
-timeout 300 python benchmarks/linear_bench.py --model small > gpurun_out/lin_small.log 2>&1; echo "small rc=$?"; show gpurun_out/lin_small.log
+timeout 300 python benchmarks/linear_bench.py --model mini $LB_ARGS > gpurun_out/lin_mini.log 2>&1; echo "mini rc=$?"; show gpurun_out/lin_mini.log
+timeout 300 python benchmarks/linear_bench.py --model small $LB_ARGS > gpurun_out/lin_small.log 2>&1; echo "small rc=$?"; show gpurun_out/lin_small.log
