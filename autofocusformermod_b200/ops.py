@@ -82,21 +82,26 @@ def kernel_launches():
     return int(_lib.lib().clusten_kernel_launches())
 
 
-_flops = {}                                            # entry point -> algorithmic FLOPs issued so far (GEMM-shaped entry points only)
+_flops = {}                                            # entry point -> [executed, algorithmic] FLOPs so far (GEMM-shaped entry points only)
 
 
 def flops_issued(name):
-    """Algorithmic FLOPs (2 R K N per Linear call) issued through entry point ``name`` in this process."""
-    return _flops.get(name, 0)
+    """(executed, algorithmic) FLOPs issued through entry point ``name`` in this process.  Algorithmic = 2 R K N per Linear call;
+    executed = the tensor-core work behind it expressed at the bf16 / fp16 dense rate: three MMAs per product with the fp16 split
+    (3 x 2RKN), three TF32 MMAs at half that rate with the TF32 split (6 x 2RKN)."""
+    e = _flops.get(name, (0, 0))
+    return float(e[0]), float(e[1])
 
 
-def _call(name, dev, *args, nbytes=0, flops=0):
+def _call(name, dev, *args, nbytes=0, flops=None):
     """Invoke C-ABI entry point ``name`` on the current stream of ``dev``.  ``nbytes`` = ALGORITHMIC bytes of the call
     (each operand read once, each result written once, idx as the int64 delivered) for roofline reports."""
     global _launch_count
     _launch_count += 1
-    if flops:
-        _flops[name] = _flops.get(name, 0) + flops
+    if flops:                                          # (executed in bf16-rate equivalents, algorithmic)
+        e = _flops.setdefault(name, [0, 0])
+        e[0] += flops[0]
+        e[1] += flops[1]
     fn = getattr(_lib.lib(), name)
     _capture_status("before " + name)
     timed = _timer is not None and _timer["name"] in (name, "*")
@@ -941,7 +946,7 @@ def linear_tc(x, weight, bias=None, epilogue="bias", res=None, gamma=None, alpha
         _call("clusten_linear_tc_f32", dev, x2.data_ptr(), hi.data_ptr(), lo.data_ptr(), _lib.ptr(b), _lib.ptr(r2), _lib.ptr(g),
               y.data_ptr(), R, K, N, x2.stride(0), N, ldres, LINEAR_EPI[epilogue], float(alpha), int(alpha_cols),
               LINEAR_TC_CHAIN if chain is None else int(chain), *lnp, int(half), _lib.ptr(inv), nbytes=4 * (R * (K + N * (2 if r2 is not None else 1)) + 2 * N * K),
-              flops=2 * R * K * N)
+              flops=(2 * R * K * N * (3 if half else 6), 2 * R * K * N))
     return y.view(*x.shape[:-1], N)
 
 

@@ -380,7 +380,7 @@ def main():
     k0 = ops.kernel_launches()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dom_flops = 0
+    dom_flops = (0.0, 0.0)
     f0 = ops.flops_issued(dominant)
     if not use_graph:
         ops.start_kernel_timer(dominant)
@@ -392,7 +392,7 @@ def main():
     ms = ev0.elapsed_time(ev1)
     if not use_graph:
         dom = ops.stop_kernel_timer()
-        dom_flops = ops.flops_issued(dominant) - f0
+        dom_flops = tuple(a_ - b_ for a_, b_ in zip(ops.flops_issued(dominant), f0))
         launches = ops.kernel_launches() - k0
         roof_timing = "CUDA events around every launch of the entry point inside the timed region"
     else:
@@ -404,7 +404,7 @@ def main():
         for _ in range(args.steps):
             eager_step(x_dev)
         dom = ops.stop_kernel_timer()
-        dom_flops = ops.flops_issued(dominant) - f0
+        dom_flops = tuple(a_ - b_ for a_, b_ in zip(ops.flops_issued(dominant), f0))
         # kernels of ours inside the replays of the timed region = what the same steps launch eagerly
         launches = graphed.launches_per_replay * args.steps if graphed is not None else ops.kernel_launches() - k1
         roof_timing = "CUDA events around every launch of the entry point over the same number of eager steps after the timed region (graph replays carry no per-launch events)"
@@ -480,14 +480,15 @@ def main():
     # a Linear dominates the step)
     roofline["by_entry"] = {n: {"ms": round(v[0], 4), "gbps": round(v[1] / v[0] / 1e6, 1), "frac": round(v[1] / v[0] / 1e6 / peak, 4)}
                             for n, v in sorted(per.items()) if v[1] > 0 and v[0] > 0}
-    if dom_flops and dom_ms > 0:
-        # GEMM-shaped dominant kernel: also against the tensor-core ceiling.  fp32 products are three TF32 MMAs (3xTF32 split) and
-        # the TF32 dense rate is half the bf16 one, so the ceiling for ALGORITHMIC fp32 FLOPs is bf16 / 6.
+    if dom_flops[0] and dom_ms > 0:
+        # GEMM-shaped dominant kernel: also against the tensor-core ceiling.  An fp32 product is three MMAs (hi/lo split of both
+        # operands): fp16 halves run at the bf16 / fp16 dense rate, TF32 halves at half of it; `executed` counts them in bf16-rate
+        # equivalents, so its ceiling is the measured bf16 throughput.
         bf16 = float(json.load(open(peaks_path)).get("bf16_tflops_sustained", 1404.1)) if os.path.exists(peaks_path) else 1404.1
-        tf = dom_flops / dom_ms / 1e9
-        roofline["tensor"] = {"achieved": round(tf, 1), "peak": round(bf16 / 6, 1), "unit": "TFLOP/s (algorithmic fp32, 2RKN)",
-                              "frac": round(tf / (bf16 / 6), 4),
-                              "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32) / 3 (3xTF32 split)"}
+        ex, alg = dom_flops[0] / dom_ms / 1e9, dom_flops[1] / dom_ms / 1e9
+        roofline["tensor"] = {"achieved": round(ex, 1), "peak": bf16, "unit": "TFLOP/s executed on the tensor cores, bf16-rate equivalents",
+                              "frac": round(ex / bf16, 4), "algorithmic_fp32_tflops": round(alg, 1),
+                              "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"}
         if roofline["tensor"]["frac"] > roofline["frac"]:
             roofline["note"] = ("the launches of this entry point range from HBM-bound (K = 32) to tensor-bound (K >= 256); both "
                                 "ceilings are reported, the HBM one in the contract keys")
