@@ -72,6 +72,9 @@ TCGEN05_LINEAR = os.environ.get("CLUSTEN_TCGEN05_LINEAR", "1") != "0"
 # the LayerNorm in front of those Linear layers (norm1 -> q / kv, norm2 -> fc1, merge norm -> merge linear) applied inside the GEMM
 # while it stages the rows: the norm kernel shrinks to its statistics pass.  CLUSTEN_LN_IN_GEMM=0: separate LayerNorm kernel.
 LN_IN_GEMM = os.environ.get("CLUSTEN_LN_IN_GEMM", "1") != "0"
+# proj and fc2 take the fp16 form of the split when the parameters of the layer before them bound its output inside the fp16 range
+# (_ln_linear_bound).  CLUSTEN_FP16_AFTER_BOUND=0: they keep the TF32 form.
+AUTO_FP16_AFTER_BOUND = os.environ.get("CLUSTEN_FP16_AFTER_BOUND", "1") != "0"
 
 
 def _tcgen05_ok(x):
@@ -160,6 +163,40 @@ def _ln_operands(norm, x):
     return None
 
 
+_bound_cache = {}
+
+
+def _ln_linear_bound(linear, norm, extra=None):
+    """Upper bound of |linear(norm(x))| over ALL inputs x, from the parameters alone: a LayerNorm-ed row has ||(x - mean) rstd||_2 <=
+    sqrt(K), hence |y_n| <= ||w_n||_2 (sqrt(K) max|gamma| + ||beta||_2) + |b_n|; ``extra`` (a parameter) joins with its own max.  This
+    is what lets the layer AFTER it (proj after kv / attention, fc2 after fc1 / GELU) use the fp16 form of the tcgen05 split, whose
+    activations must stay inside the fp16 range.  One host read per parameter version; while a CUDA graph is being captured an
+    unknown bound stays unknown (None -> TF32 form)."""
+    if not isinstance(norm, nn.LayerNorm) or norm.weight is None or norm.bias is None:
+        return None
+    ps = [linear.weight, linear.bias, norm.weight, norm.bias, extra]
+    key = tuple((id(p), p.data_ptr(), p._version) for p in ps if p is not None)
+    hit = _bound_cache.get(key)
+    if hit is None:
+        if torch.cuda.is_available() and linear.weight.is_cuda and torch.cuda.is_current_stream_capturing():
+            return None
+        with torch.no_grad():
+            K = linear.weight.shape[1]
+            u = linear.weight.float().norm(dim=1).max() * (K ** 0.5 * norm.weight.float().abs().max() + norm.bias.float().norm())
+            if linear.bias is not None:
+                u = u + linear.bias.float().abs().max()
+            if extra is not None:
+                u = torch.maximum(u, extra.float().abs().max())
+            hit = float(u)
+        if len(_bound_cache) > 4096:
+            _bound_cache.clear()
+        _bound_cache[key] = hit
+    return hit
+
+
+FP16_RANGE_MARGIN = 6.0e4                              # below fp16's 65504
+
+
 def _inner_norm(norm_layer, dim):
     """A norm whose output only feeds Linear layers."""
     n = norm_layer(dim)
@@ -182,7 +219,7 @@ class Linear(nn.Linear):
             return linear_f32(x, self.weight, self.bias)
         return F.linear(x, self.weight, self.bias)
 
-    def fused(self, x, epilogue, res=None, gamma=None, alpha=1.0, alpha_cols=0, norm=None):
+    def fused(self, x, epilogue, res=None, gamma=None, alpha=1.0, alpha_cols=0, norm=None, split=None):
         """The layer plus the element-wise line after it -- ``bias`` (the first ``alpha_cols`` outputs then times ``alpha``), ``gelu``
         or ``residual`` (res + gamma * y) -- and, with ``norm``, the LayerNorm in front of it, in one tcgen05 kernel when the operands
         allow, else the same arithmetic in torch."""
@@ -190,7 +227,8 @@ class Linear(nn.Linear):
             ln = _ln_operands(norm, x) if norm is not None else None
             if norm is not None and ln is None:
                 x = norm(x)
-            return linear_tc(x, self.weight, self.bias, epilogue, res=res, gamma=gamma, alpha=alpha, alpha_cols=alpha_cols, ln=ln)
+            return linear_tc(x, self.weight, self.bias, epilogue, res=res, gamma=gamma, alpha=alpha, alpha_cols=alpha_cols, ln=ln,
+                             split=split)
         if norm is not None:
             x = norm(x)
         y = self.forward(x)
@@ -257,7 +295,10 @@ class Mlp(nn.Module):
             hidden = (self.fc1.fused(x, "gelu", norm=norm) if isinstance(self.act, nn.GELU) and self.act.approximate == "none"
                       else self.act(self.fc1(x)))
             if residual is not None:
-                return self.fc2.fused(hidden, "residual", res=residual[0], gamma=residual[1])
+                # |GELU(y)| <= max(|y|, 0.17): when the parameters bound fc1's output inside the fp16 range, fc2 can take the fp16 split
+                bound = _ln_linear_bound(self.fc1, norm) if (norm is not None and AUTO_FP16_AFTER_BOUND) else None
+                return self.fc2.fused(hidden, "residual", res=residual[0], gamma=residual[1],
+                                      split="f16" if bound is not None and bound < FP16_RANGE_MARGIN else None)
             return self.fc2(hidden)
         return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
 
@@ -291,9 +332,12 @@ class ClusterAttention(nn.Module):
             self._qkv_cache = hit
         return hit[1], hit[2]
 
-    def _project(self, out, residual):
+    def _project(self, out, residual, norm=None):
         if residual is not None:
-            return self.proj.fused(out, "residual", res=residual[0], gamma=residual[1])
+            # the attention output is a convex combination of v rows and blank_v: bounded by the kv layer's output bound
+            bound = _ln_linear_bound(self.kv, norm, self.blank_v) if (norm is not None and AUTO_FP16_AFTER_BOUND) else None
+            return self.proj.fused(out, "residual", res=residual[0], gamma=residual[1],
+                                   split="f16" if bound is not None and bound < FP16_RANGE_MARGIN else None)
         return self.proj_drop(self.proj(out))
 
     def forward(self, feat, member_idx, cluster_mask, pe_idx, global_attn, pe_lookup=None, fused_ctx=None, residual=None, norm=None):
@@ -301,6 +345,7 @@ class ClusterAttention(nn.Module):
         b, n, c = feat.shape
         h = self.num_heads
         c_ = c // h
+        norm_in = norm
         one_gemm = (_tcgen05_ok(feat) and linear_tc_supported(feat, self.q.weight, self.q.bias) and self.q.bias is not None
                     and self.kv.bias is not None)
         ln = _ln_operands(norm, feat) if (norm is not None and one_gemm) else None
@@ -326,7 +371,7 @@ class ClusterAttention(nn.Module):
             else:
                 out = cluster_attention_core(q_tok, kv_tok, self.pos_embed(pe_lookup.features, pe_lookup.count), self.blank_k,
                                              self.blank_v, member_idx, bias_idx, mask_u8, pe_lookup.count)
-            return self._project(out, residual)
+            return self._project(out, residual, norm_in)
         q = q_tok.permute(0, 2, 1, 3)                                                    # b h n c_ (view)
         kv = kv_tok.permute(3, 0, 2, 1, 4)                                               # 2 b h n c_ (view)
         key, v = kv[0], kv[1]
@@ -339,7 +384,7 @@ class ClusterAttention(nn.Module):
             else:
                 out = cluster_attention_fused(q, key, v, member_idx, self.pos_embed(pe_lookup.features, pe_lookup.count), bias_idx,
                                               mask_u8, self.blank_k, self.blank_v)       # aff.py:114-155 in one kernel
-            return self._project(out, residual)
+            return self._project(out, residual, norm_in)
         if global_attn:
             attn = q @ key.transpose(-1, -2)                                             # aff.py:121
             mask = None
@@ -361,7 +406,7 @@ class ClusterAttention(nn.Module):
         else:
             out = CLUSTENAVFunction.apply(attn, v, member_idx)                           # aff.py:154
         out = (out + blank_v).permute(0, 2, 1, 3).reshape(b, n, c)
-        return self._project(out, residual)
+        return self._project(out, residual, norm_in)
 
 
 class ClusterTransformerBlock(nn.Module):
