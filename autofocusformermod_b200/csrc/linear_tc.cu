@@ -218,25 +218,24 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const int chain = a.chain;
 
     if (warp == 0) {                                                     // ---- TMA producer, X (from HBM: the deep ring) ----
-        uint32_t it = 0;
+        uint32_t s = 0, ph = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
             const int m0 = (t / a.tiles_n) * BM;
-            for (int kc = 0; kc < KC; ++kc, ++it) {
-                const uint32_t s = it % XS, ph = (it / XS) & 1u;
+            for (int kc = 0; kc < KC; ++kc) {
                 mbar_wait(bar_xempty + 8 * s, ph ^ 1u);
                 if (elect_one()) {
                     mbar_expect_tx(bar_xfull + 8 * s, A_BYTES);
                     tma_box_2d(base + s * A_BYTES, &mapX, bar_xfull + 8 * s, kc * BK, m0);
                 }
                 __syncwarp();
+                if (++s == XS) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 14) {                                             // ---- TMA producer, pre-split weights (L2) ----
-        uint32_t it = 0;
+        uint32_t s = 0, ph = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
             const int n0 = (t % a.tiles_n) * BN;
-            for (int kc = 0; kc < KC; ++kc, ++it) {
-                const uint32_t s = it % WS, ph = (it / WS) & 1u;
+            for (int kc = 0; kc < KC; ++kc) {
                 const uint32_t st = wring + s * C::WSTAGE;
                 mbar_wait(bar_wempty + 8 * s, ph ^ 1u);
                 if (elect_one()) {
@@ -245,23 +244,29 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     tma_box_2d(st + C::B_BYTES, &mapWl, bar_wfull + 8 * s, kc * BK, n0);
                 }
                 __syncwarp();
+                if (++s == WS) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {                                              // ---- MMA issuer ----
-        uint32_t it = 0, ch = 0;
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-            for (int kc = 0; kc < KC; ++kc, ++it) {
-                const uint32_t s = it % WS, ph = (it / WS) & 1u, sa = it % NA, pa = (it / NA) & 1u;
-                const uint32_t buf = ch & 1u;
-                const bool first = kc % chain == 0, last = (kc + 1) % chain == 0 || kc + 1 == KC;
-                if (first) mbar_wait(bar_acce + 8 * buf, ((ch >> 1) & 1u) ^ 1u);          // the epilogue has drained this accumulator
+        // This warp's loop is the clock of the kernel: ncu showed it ~100 % busy at ~1100 cycles per chunk with the tensor pipe idle
+        // in between (ring slots by % and /, `kc % chain` by a runtime divisor, descriptors rebuilt from addresses, every chunk).
+        // Ring positions and parities are now carried, descriptors are a base plus a stride, the chain position is a counter.
+        const uint64_t wdesc0 = H ? umma_desc64(wring) : umma_desc(wring);
+        constexpr uint32_t WSTEP = C::WSTAGE >> 4, WLO = C::B_BYTES >> 4;            // descriptor address units (16 bytes)
+        const uint32_t xa0 = tmem + A_COL0;
+        uint32_t s = 0, ph = 0, sa = 0, pa = 0, buf = 0, pacc = 1;        // W slot / parity, A stage / parity, accumulator / its "drained" parity
+        const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            int cc = 0;                                                  // chunk inside the current accumulator chain
+            for (int kc = 0; kc < KC; ++kc) {
+                const bool first = cc == 0, last = cc == chain - 1 || kc == KC - 1;
+                if (first) mbar_wait(bar_acce + 8 * buf, pacc);          // the epilogue has drained this accumulator
                 mbar_wait(bar_wfull + 8 * s, ph);
                 mbar_wait(bar_afull + 8 * sa, pa);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
-                    const uint32_t st = wring + s * C::WSTAGE;
-                    const uint64_t wh = H ? umma_desc64(st) : umma_desc(st), wl = H ? umma_desc64(st + C::B_BYTES) : umma_desc(st + C::B_BYTES);
-                    const uint32_t xh = tmem + A_COL0 + sa * C::A_COLS, xl = xh + C::A_COLS / 2;
+                    const uint64_t wh = wdesc0 + s * WSTEP, wl = wh + WLO;
+                    const uint32_t xh = xa0 + sa * C::A_COLS, xl = xh + C::A_COLS / 2;
                     const uint32_t d = tmem + buf * C::ACC_COLS;
 #pragma unroll
                     for (int k = 0; k < C::KSTEPS; ++k)                  // one K step: 8 TMEM columns of A, 32 bytes (+2) of B
@@ -275,19 +280,25 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     if (last) umma_commit(bar_accf + 8 * buf);
                 }
                 __syncwarp();
-                if (last) ++ch;
+                if (++s == WS) { s = 0; ph ^= 1u; }
+                if (++sa == NA) { sa = 0; pa ^= 1u; }
+                ++cc;
+                if (last) {
+                    cc = 0;
+                    if (buf) pacc ^= 1u;                                 // both accumulators used once more: the parity to wait for flips
+                    buf ^= 1u;
+                }
             }
         }
     } else if (warp < 6) {                                               // ---- split x -> (xh, xl), row per thread, into TMEM ----
         const int q = warp & 3, row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        uint32_t it = 0;
+        uint32_t s = 0, ph = 0, sa = 0, pa = 0;
         const bool ln = a.ln_mean != nullptr;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
             const int64_t r = (int64_t)(t / a.tiles_n) * BM + row;
             const float mu = ln && r < a.R ? __ldg(a.ln_mean + r) : 0.f, rs = ln && r < a.R ? __ldg(a.ln_rstd + r) : 0.f;
-            for (int kc = 0; kc < KC; ++kc, ++it) {
-                const uint32_t s = it % XS, ph = (it / XS) & 1u, sa = it % NA, pa = (it / NA) & 1u;
+            for (int kc = 0; kc < KC; ++kc) {
                 mbar_wait(bar_xfull + 8 * s, ph);
                 const uint8_t *xs = gbase + s * A_BYTES;
                 float4 x[8];
@@ -345,6 +356,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(bar_afull + 8 * sa);
+                if (++s == XS) { s = 0; ph ^= 1u; }
+                if (++sa == NA) { sa = 0; pa ^= 1u; }
             }
         }
     } else if (warp < 14) {                                              // ---- drain + epilogue ----
