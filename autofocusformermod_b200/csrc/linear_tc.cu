@@ -536,6 +536,7 @@ static bool map_2d(CUtensorMap *m, const void *ptr, int64_t rows, int K, int64_t
 static int sm_count() {
     static int n = 0;
     if (!n) {
+        if (const char *e = getenv("CLUSTEN_TC_GRID")) { n = atoi(e); if (n > 0) return n; n = 0; }   // experiment: fewer persistent CTAs
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
