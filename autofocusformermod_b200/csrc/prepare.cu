@@ -53,7 +53,9 @@ prepare_kernel(const int64_t *__restrict__ nearest, const int64_t *__restrict__ 
             rx = fminf(fmaxf(rx, 0.f), (float)(PE_W - 1));
             ry = fminf(fmaxf(ry, 0.f), (float)(PE_W - 1));
             pv[x] = (int)__fadd_rn(__fmul_rn(ry, (float)PE_W), rx);       // (rel.y * 1023 + rel.x).long(), fp32 arithmetic
-            present[pv[x]] = 1;                          // benign race: every writer stores 1
+            // benign race: every writer stores 1.  Read first: the B*n*M entries reference only a few thousand distinct rows, and
+            // unconditional stores to those few bytes serialise in the L2 slices that own them (648 us at B*n*M = 12.6 M).
+            if (present[pv[x]] == 0) present[pv[x]] = 1;
             pmin = min(pmin, pv[x]);
             pmax = max(pmax, pv[x]);
         }
