@@ -73,9 +73,33 @@ def test_module_wrappers_keep_reference_parameter_names_and_cpu_semantics():
     assert {"weight_net.0.weight", "weight_net.1.weight", "weight_net.1.bias", "norm.weight", "linear.weight"} <= set(merge.state_dict())
 
 
+def test_layernorm_linear_bound_holds_for_any_input():
+    """aff._ln_linear_bound: what lets proj / fc2 use the fp16 form of the tcgen05 split.  The bound comes from
+    the parameters alone and must dominate |Linear(LayerNorm(x))| for every x -- including rows with huge, tiny and constant values."""
+    g = torch.Generator().manual_seed(3)
+    ln, lin = aff.LayerNorm(64), aff.Linear(64, 96)
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(64, generator=g) * 2.0)
+        ln.bias.copy_(torch.randn(64, generator=g))
+        lin.weight.copy_(torch.randn(96, 64, generator=g))
+        lin.bias.copy_(torch.randn(96, generator=g) * 3.0)
+    extra = torch.nn.Parameter(torch.tensor([0.5, -7.0]))
+    bound = aff._ln_linear_bound(lin, ln)
+    x = torch.cat([torch.randn(200, 64, generator=g) * s for s in (1e-6, 1.0, 1e6)] + [torch.full((1, 64), 3.0)])
+    x[5, 7] = 1e9                                                                     # one dominating element: the normalised row is ~ sqrt(K) e_7
+    y = lin(torch.nn.functional.layer_norm(x, (64,), ln.weight, ln.bias, ln.eps))
+    assert float(y.abs().max()) <= bound
+    assert aff._ln_linear_bound(lin, ln, extra) == max(bound, 7.0)
+    assert aff._ln_linear_bound(lin, torch.nn.Identity()) is None                     # no LayerNorm in front: no bound
+    with torch.no_grad():
+        lin.weight.mul_(2.0)                                                          # in-place update -> new version -> recomputed
+    assert aff._ln_linear_bound(lin, ln) > 1.5 * bound
+
+
 def test_kernel_dispatch_predicates_reject_what_the_kernels_do_not_take():
     x = torch.zeros(4, 48)
     w = torch.zeros(6, 48)
+    assert not ops.linear_tc_supported(x, w, None)                                    # not a CUDA tensor
     assert not ops.linear_f32_supported(x, w, None)                                   # not a CUDA tensor
     assert not ops.linear_f32_supported(x.to(torch.bfloat16), w, None)
     assert not ops.table_linear_supported(torch.zeros(4, 9), torch.zeros(3, 9), None)
