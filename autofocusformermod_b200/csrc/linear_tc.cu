@@ -1,23 +1,27 @@
-// fp32 Linear layer  Y[R,N] = epilogue( X[R,K] . W[N,K]^T + bias[N] )  on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
-// accumulators in tensor memory) with the 3xTF32 split that keeps fp32-level accuracy:
-//     x = xh + xl,  w = wh + wl   (xh, wh = the value rounded to TF32, xl, wl = the rounded remainder)
+// fp32 Linear layer  Y[R,N] = epilogue( [LayerNorm] X[R,K] . W[N,K]^T + bias[N] )  on the 5th-generation tensor cores (tcgen05.mma,
+// accumulators in tensor memory), fp32-level accuracy from a hi / lo split of both operands:
+//     x = xh + xl,  w = wh + wl   (xh, wh = the value rounded to an 11-bit significand, xl, wl = the rounded remainder)
 //     x.w ~ xl.wh + xh.wl + xh.wh                                   (the dropped xl.wl term is ~2^-22 of the product)
+// in two forms: TF32 halves (kind::tf32, K = 8 per MMA; any input range) or fp16 halves (kind::f16, K = 16 per MMA at the same 64
+// cycles: half the MMAs, half the weight bytes; weights scaled per output row by a power of two, activations must fit fp16).
 // These are the q / kv / proj / fc1 / fc2 layers of the block (backbone/aff.py:62-70,103-106,181-189) and the merge Linear
 // (aff.py:282) in fp32 inference, where cuBLAS answers the skinny shapes (K = 32..1536, N = 32..2304, R = 4 096..2 097 152) with
 // SIMT sgemm kernels plus a separate bias kernel: 64 % of the device time of the AFF-Mini forward
-// (profiles/r2_launches_default.md).
+// (profiles/r2_launches_default.md).  DESIGN.md section 5b has the history, the measurements and what bounds the kernel.
 //
-// One persistent CTA per SM, 10 warps, four roles (the canonical sm_100 pipeline; every hand-off is an mbarrier):
-//   warp 0 (one lane)   TMA producer: per 32-wide K chunk one box of X [128 rows x 128 B] and the matching boxes of the pre-split
-//                       weights Wh, Wl [BN rows x 128 B], SWIZZLE_128B, into a ring of STAGES buffers
-//   warps 2-5           split the X box in place: xh back over x, xl into the second A buffer (element-wise, so the swizzle does not
-//                       matter), fence.proxy.async, arrive
-//   warp 1 (one lane)   12 tcgen05.mma (M = 128, N = BN, K = 8) per chunk -- small terms first -- into one of two TMEM accumulators;
-//                       tcgen05.commit frees the ring slot and, at the end of a chain, hands the accumulator to the epilogue
-//   warps 6-13          drain: tcgen05.ld of their 32 TMEM lanes x half the columns, add to the running fp32 sum in registers (the tensor core
-//                       accumulates with truncation, so a chain is cut after `chain` chunks -- DESIGN.md section 7), then
-//                       bias / GELU / scaled residual and 16-byte stores of their row
-// The ring and the accumulator pair run across tile boundaries, so the next tile's loads, split and MMAs overlap the epilogue.
+// One persistent CTA per SM, 15 warps, five roles (the canonical sm_100 pipeline; every hand-off is an mbarrier):
+//   warp 0    X producer: per 32-wide K chunk one TMA box of X [128 rows x 128 B], SWIZZLE_128B, into a 4-8 stage ring (X comes from
+//             HBM: this ring covers its latency); the loop runs warp-uniform, an elect.sync lane issues
+//   warp 14   W producer: the matching boxes of the pre-split weights Wh, Wl [BN rows], into a 3-4 stage ring (L2-resident operand)
+//   warps 2-5 split: thread = row; 8 swizzled LDS.128, optional LayerNorm, hi / lo, tcgen05.st into a 4-stage A ring IN TENSOR MEMORY,
+//             fence.proxy.async before the X slot is released
+//   warp 1    issuer: 12 (TF32) or 6 (fp16) tcgen05.mma (M = 128, N = BN; A from TMEM, B by shared-memory descriptor) per chunk --
+//             small terms first -- into one of two TMEM accumulators; tcgen05.commit frees the W slot and the A stage and, at the end
+//             of a chain, hands the accumulator to the epilogue
+//   warps 6-13 drain + epilogue (two warps per TMEM lane quadrant, half the columns each): tcgen05.ld, fp32 running sum in registers
+//             (the tensor core accumulates with truncation, so a chain is cut after `chain` chunks), then weight-scale / bias /
+//             q-scale / GELU / residual into a swizzled staging tile (the residual tile is TMA-loaded into it ahead), TMA store
+// The rings and the accumulator pair run across tile boundaries, so the next tile's loads, split and MMAs overlap the epilogue.
 #include <cuda.h>
 
 #include <algorithm>
