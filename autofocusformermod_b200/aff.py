@@ -26,7 +26,7 @@ import torch.nn.functional as F
 
 from .ops import (CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction, cluster_attention_core, cluster_attention_fused,
                   cluster_attention_core_pos, cluster_attention_fused_pos, layer_norm, layer_norm_stats, linear, linear_f32, linear_f32_supported, linear_tc, linear_tc_supported,
-                  scale_residual, table_linear,
+                  gather_rows, scale_residual, stem_conv_bn_gelu, stem_conv_bn_gelu_supported, table_linear,
                   table_linear_supported, table_lookup)
 from .point_utils import knn_keops, merge_select, space_filling_cluster, stage_prepare
 
@@ -80,6 +80,20 @@ AUTO_FP16_AFTER_BOUND = os.environ.get("CLUSTEN_FP16_AFTER_BOUND", "1") != "0"
 def _tcgen05_ok(x):
     return (TCGEN05_LINEAR and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
             and not torch.is_autocast_enabled())
+# row reorders / selections (`x.gather(index=idx.expand(...), dim=1)`, aff.py:332,335,340,471) by clusten_gather_rows when no gradient
+# flows through them.  CLUSTEN_GATHER_ROWS=0: torch.gather
+NATIVE_GATHER_ROWS = _on("CLUSTEN_GATHER_ROWS")
+# fp32 inference stem: conv1 + BatchNorm + GELU in one pass (clusten_stem_conv_bn_gelu).  CLUSTEN_FUSED_STEM=0: cuDNN / ATen, four passes
+FUSED_STEM = _on("CLUSTEN_FUSED_STEM")
+
+
+def _gather(x, idx):
+    """``x.gather(1, idx.expand(-1, -1, x.shape[2]))`` for idx [b, k, 1]."""
+    if NATIVE_GATHER_ROWS and x.is_cuda:
+        return gather_rows(x, idx)
+    return x.gather(1, idx.expand(-1, -1, x.shape[2]))
+
+
 # opt-in: under autocast the merge's WF runs in the autocast dtype (tensor-core kernels) instead of fp32 like the reference under
 # AMP, whose CLUSTENWF casts feat up to the fp32 weights (clusten.py:80-81)
 MERGE_WF_AUTOCAST = _opt_in("CLUSTEN_MERGE_WF_AUTOCAST")
@@ -487,15 +501,15 @@ class ClusterMerging(nn.Module):
         M = member_idx.shape[-1]
         idx = self.select(pos, learned_prob, stride, reserve_num)
         n2 = idx.shape[1]
-        pos = pos.gather(index=idx.expand(-1, -1, d), dim=1)                                         # aff.py:332
-        member_idx = member_idx.gather(index=idx.expand(-1, -1, M), dim=1)                           # aff.py:335
+        pos = _gather(pos, idx)                                                                      # aff.py:332
+        member_idx = _gather(member_idx, idx)                                                        # aff.py:335
         if pe_lookup is None:
             pe_lookup = _TableLookup(pe_idx)
         weights = pe_lookup.select(idx)(self.weight_net)                                             # aff.py:346-349
         if cluster_mask is not None:
-            cluster_mask = cluster_mask.gather(index=idx.expand(-1, -1, M), dim=1)
+            cluster_mask = _gather(cluster_mask, idx)
         if learned_prob is not None:
-            lp = learned_prob.gather(index=member_idx.reshape(b, -1, 1), dim=1).reshape(b, n2, M, 1)  # aff.py:340
+            lp = _gather(learned_prob, member_idx.reshape(b, -1, 1)).reshape(b, n2, M, 1)            # aff.py:340
             if cluster_mask is not None:
                 lp = lp * cluster_mask.unsqueeze(3)
             weights = weights * lp
@@ -537,7 +551,7 @@ class BasicLayer(nn.Module):
     def _cluster(self, pos, feat, h, w, on_grid):
         b, n, c = feat.shape
         pos, mean_pos, member, cmask, reorder = space_filling_cluster(pos, self.cluster_size, h, w)
-        feat = feat.gather(1, reorder.expand(-1, -1, c))                                             # aff.py:471
+        feat = _gather(feat, reorder)                                                                # aff.py:471
         return pos, feat, mean_pos, member, cmask
 
     def _grid_structure(self, pos, b, n, h, w, m, nnc):
@@ -572,7 +586,7 @@ class BasicLayer(nn.Module):
             nnc = min(int(round(self.nbhd_size / float(m))), k)
             if on_grid and k != n and GRID_STRUCTURE_CACHE:
                 pos, reorder, prepared, pe_lookup = self._grid_structure(pos, b, n, h, w, m, nnc)
-                feat = feat.gather(1, reorder.expand(-1, -1, feat.shape[2]))                         # aff.py:471
+                feat = _gather(feat, reorder)                                                        # aff.py:471
                 member_idx, cluster_mask, mask_u8, uniq, bias_idx, count = prepared
             else:
                 pe_lookup = None
@@ -638,7 +652,11 @@ class PatchEmbed(nn.Module):
             # fp32 means fp32: cuDNN is otherwise free to pick TF32 tensor-core convolutions (torch's default), which it does from
             # ~512x512 inputs on -- 1e-3 off the fp32 reference in res2 and enough to flip top-k selections two stages later
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                x = self.proj2(self.act1(self.bn(self.proj1(x))))
+                if (FUSED_STEM and isinstance(self.act1, nn.GELU) and getattr(self.act1, "approximate", "none") == "none"
+                        and stem_conv_bn_gelu_supported(x, self.proj1, self.bn)):
+                    x = self.proj2(stem_conv_bn_gelu(x, self.proj1, self.bn))                        # conv1 + bn + act1 in one pass
+                else:
+                    x = self.proj2(self.act1(self.bn(self.proj1(x))))
         else:
             x = self.proj2(self.act1(self.bn(self.proj1(x))))
         b, c, h, w = x.shape

@@ -11,6 +11,9 @@
 // before (torch.unique over the B*n*M int64 indices) is a 25 M-key radix sort per stage.  Here the prepare kernel marks the
 // referenced table rows in a 1023^2-byte presence map, a single-CTA-per-chunk scan ranks them (ascending row id = the order
 // torch.unique returns), and a second pass rewrites pe -> rank.  Three launches, no sort, one host read (the row count U).
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace clusten {
@@ -79,6 +82,109 @@ prepare_kernel(const int64_t *__restrict__ nearest, const int64_t *__restrict__ 
     pmin = __reduce_min_sync(FULL, pmin);
     pmax = __reduce_max_sync(FULL, pmax);
     if ((threadIdx.x & 31) == 0 && pmax >= 0) { atomicMin(range, pmin); atomicMax(range + 1, pmax); }
+}
+
+// The same pass with the presence marks kept ON CHIP.  The B*n*M entries of a stage reference a few hundred to a few thousand
+// distinct table rows, and marking them in the global byte map -- even read-first -- leaves thousands of same-address stores per
+// row (the zeros every thread of the first wave reads come from its own L1): stage-prepare was 215 us at B*n*M = 12.6 M where
+// the data movement is ~30 us, and 0.2 ms of the 4.9 ms AFF-Mini forward.  Here one CTA per SM keeps a BITMAP of all 1023^2
+// rows in shared memory (128 KiB), marks with shared-memory atomics, and touches the global map once per CTA and row at the
+// end (reading through L2 first).  The min / max of the referenced rows takes one pair of global atomics per CTA instead of
+// one per warp.  Two thread-items are in flight per iteration: the pass is a chain of four dependent loads.
+constexpr int PE_WORDS = (PE_ROWS + 31) / 32;            // 32 705 words
+constexpr int PBM_THREADS = 1024;
+constexpr size_t PBM_SMEM = (size_t)PE_WORDS * 4;
+
+__global__ void __launch_bounds__(PBM_THREADS, 1)
+prepare_bm_kernel(const int64_t *__restrict__ nearest, const int64_t *__restrict__ member, const int64_t *__restrict__ cmask,
+                  const float *__restrict__ pos, int B, int n, int k, int m, int nnc,
+                  int64_t *__restrict__ member_idx, int64_t *__restrict__ mask64, uint8_t *__restrict__ mask8,
+                  int32_t *__restrict__ pe, uint8_t *__restrict__ present, int *__restrict__ range) {
+    extern __shared__ uint32_t pbm[];
+    __shared__ int s_min, s_max;
+    for (int w = threadIdx.x; w < PE_WORDS; w += PBM_THREADS) pbm[w] = 0u;
+    if (threadIdx.x == 0) { s_min = 0x7fffffff; s_max = -1; }
+    __syncthreads();
+    const int M = nnc * m;
+    const int gpc = m >> 2;                              // groups of 4 members per cluster (m % 4 == 0 on this path)
+    const int64_t total = (int64_t)B * n * nnc * gpc;
+    const int64_t stride = (int64_t)gridDim.x * PBM_THREADS;
+    int pmin = 0x7fffffff, pmax = -1;
+    for (int64_t t0 = (int64_t)blockIdx.x * PBM_THREADS + threadIdx.x; t0 < total; t0 += 2 * stride) {
+        bool ok[2];
+        int64_t src[2], e[2], brow[2];
+        float qx[2], qy[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t t = t0 + u * stride;
+            ok[u] = t < total;
+            const int64_t tt = ok[u] ? t : t0;
+            const int gq = (int)(tt % gpc);
+            const int64_t tc = tt / gpc;                 // (b * n + i) * nnc + c
+            const int c = (int)(tc % nnc);
+            const int64_t bi = tc / nnc;                 // b * n + i
+            const int b = (int)(bi / n);
+            const int64_t cl = __ldg(nearest + tc);
+            src[u] = ((int64_t)b * k + cl) * m + gq * 4;
+            e[u] = bi * M + c * m + gq * 4;
+            brow[u] = (int64_t)b * n;
+            const float2 pi = __ldg(reinterpret_cast<const float2 *>(pos + bi * 2));
+            qx[u] = __fsub_rn(pi.x, PE_HALF);
+            qy[u] = __fsub_rn(pi.y, PE_HALF);
+        }
+        longlong4 mi[2], mk[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            mi[u] = *reinterpret_cast<const longlong4 *>(member + src[u]);
+            mk[u] = cmask ? *reinterpret_cast<const longlong4 *>(cmask + src[u]) : make_longlong4(1, 1, 1, 1);
+        }
+        float2 pn[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            pn[u][0] = __ldg(reinterpret_cast<const float2 *>(pos + (brow[u] + mi[u].x) * 2));
+            pn[u][1] = __ldg(reinterpret_cast<const float2 *>(pos + (brow[u] + mi[u].y) * 2));
+            pn[u][2] = __ldg(reinterpret_cast<const float2 *>(pos + (brow[u] + mi[u].z) * 2));
+            pn[u][3] = __ldg(reinterpret_cast<const float2 *>(pos + (brow[u] + mi[u].w) * 2));
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!ok[u]) continue;
+            int pv[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                float rx = __fsub_rn(pn[u][x].x, qx[u]), ry = __fsub_rn(pn[u][x].y, qy[u]);
+                rx = fminf(fmaxf(rx, 0.f), (float)(PE_W - 1));
+                ry = fminf(fmaxf(ry, 0.f), (float)(PE_W - 1));
+                pv[x] = (int)__fadd_rn(__fmul_rn(ry, (float)PE_W), rx);       // (rel.y * 1023 + rel.x).long(), fp32 arithmetic
+                const uint32_t bit = 1u << (pv[x] & 31);
+                uint32_t *wd = pbm + (pv[x] >> 5);
+                if (!(*reinterpret_cast<volatile uint32_t *>(wd) & bit)) atomicOr(wd, bit);
+                pmin = min(pmin, pv[x]);
+                pmax = max(pmax, pv[x]);
+            }
+            *reinterpret_cast<longlong4 *>(member_idx + e[u]) = mi[u];
+            *reinterpret_cast<int4 *>(pe + e[u]) = make_int4(pv[0], pv[1], pv[2], pv[3]);
+            if (cmask) {
+                if (mask64) *reinterpret_cast<longlong4 *>(mask64 + e[u]) = mk[u];
+                if (mask8) *reinterpret_cast<uchar4 *>(mask8 + e[u]) = make_uchar4(mk[u].x != 0, mk[u].y != 0, mk[u].z != 0, mk[u].w != 0);
+            }
+        }
+    }
+    pmin = __reduce_min_sync(FULL, pmin);
+    pmax = __reduce_max_sync(FULL, pmax);
+    if ((threadIdx.x & 31) == 0 && pmax >= 0) { atomicMin(&s_min, pmin); atomicMax(&s_max, pmax); }
+    __syncthreads();
+    if (s_max < 0) return;
+    // this CTA's marks -> the global byte map the ranking scan reads (benign race: every writer stores 1)
+    for (int w = (s_min >> 5) + threadIdx.x; w <= (s_max >> 5); w += PBM_THREADS) {
+        uint32_t v = pbm[w];
+        while (v) {
+            const int p = w * 32 + __ffs(v) - 1;
+            v &= v - 1;
+            if (__ldcg(present + p) == 0) present[p] = 1;
+        }
+    }
+    if (threadIdx.x == 0) { atomicMin(range, s_min); atomicMax(range + 1, s_max); }
 }
 
 // rank of every present table row (exclusive prefix count), U = number of present rows, uniq[rank] = row id.
@@ -155,13 +261,27 @@ mark_rows_kernel(const int64_t *__restrict__ pe64, int64_t total, int32_t *__res
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int v = (int)min(max(pe64[e], (int64_t)0), (int64_t)PE_ROWS - 1);
         pe32[e] = v;
-        present[v] = 1;
+        if (__ldcg(present + v) == 0) present[v] = 1;         // read first (through L2): see prepare_kernel
         pmin = min(pmin, v);
         pmax = max(pmax, v);
     }
     pmin = __reduce_min_sync(FULL, pmin);
     pmax = __reduce_max_sync(FULL, pmax);
     if ((threadIdx.x & 31) == 0 && pmax >= 0) { atomicMin(range, pmin); atomicMax(range + 1, pmax); }
+}
+
+static bool prepare_bitmap_enabled() {
+    const char *e = getenv("CLUSTEN_PREPARE_BITMAP");                  // A/B switch, read per call: 0 = the global byte-map marks
+    return !(e && e[0] == '0');
+}
+static int sm_count_prepare() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
 }
 
 }  // namespace clusten
@@ -218,7 +338,23 @@ extern "C" int clusten_stage_prepare(const int64_t *nearest, const int64_t *memb
     const int64_t pthreads = (m & 3) == 0 ? total / 4 : total;
     const int pgrid = (int)std::min<int64_t>(148 * 16, (pthreads + 255) / 256);
     const int grid = (int)std::min<int64_t>(148 * 16, (total + 255) / 256);
-    prepare_kernel<<<pgrid, 256, 0, st>>>(nearest, member, cluster_mask, pos, B, n, k, m, nnc, member_idx, mask64, mask8, pe_idx, present, range);
+    // (longlong4 accesses: 32-byte aligned rows -- member / mask / member_idx come from the allocator, m % 4 == 0 keeps the groups aligned)
+    const bool vec_ok = (m & 3) == 0 && ((reinterpret_cast<uintptr_t>(member) | reinterpret_cast<uintptr_t>(member_idx) |
+                                           reinterpret_cast<uintptr_t>(cluster_mask) | reinterpret_cast<uintptr_t>(mask64)) & 31u) == 0 &&
+                        (reinterpret_cast<uintptr_t>(pe_idx) & 15u) == 0 && (reinterpret_cast<uintptr_t>(mask8) & 3u) == 0;
+    if (vec_ok && prepare_bitmap_enabled()) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(prepare_bm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PBM_SMEM) != cudaSuccess)
+                return set_error(CLUSTEN_EUNSUPPORTED, "stage_prepare: cannot reserve %zu bytes of shared memory", PBM_SMEM);
+            attr_set = true;
+        }
+        const int bgrid = (int)std::min<int64_t>(sm_count_prepare(), (pthreads + 2 * PBM_THREADS - 1) / (2 * PBM_THREADS));
+        prepare_bm_kernel<<<bgrid, PBM_THREADS, PBM_SMEM, st>>>(nearest, member, cluster_mask, pos, B, n, k, m, nnc, member_idx, mask64, mask8,
+                                                               pe_idx, present, range);
+    } else {
+        prepare_kernel<<<pgrid, 256, 0, st>>>(nearest, member, cluster_mask, pos, B, n, k, m, nnc, member_idx, mask64, mask8, pe_idx, present, range);
+    }
     rank_kernel<<<1, 1024, 0, st>>>(present, rank, uniq, count, uniq_cap, range);
     rerank_kernel<<<grid, 256, 0, st>>>(pe_idx, rank, bias_idx, total);
     note_launches(3);

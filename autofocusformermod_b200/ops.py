@@ -1215,3 +1215,60 @@ class MSDETRPCFunction(Function):
                   val.stride(0), val.stride(1), d_val.stride(0), d_val.stride(1), _lib.dtype_code(val),
                   nbytes=val.element_size() * (B * N * C + 2 * B * N * M * K + 2 * B * N * M + 2 * B * Nk * C) + 8 * B * N * M * K)
         return None, d_weight.to(wdt), d_attn.to(adt), d_val
+
+
+# ---- row gather ------------------------------------------------------------------------------------------------------------
+def gather_rows(src, idx):
+    """``src.gather(1, idx.expand(-1, -1, src.shape[2]))`` for src [B, n, c] and idx int64 [B, k, 1] (the row reorders and
+    selections of backbone/aff.py:332,335,340,471) through clusten_gather_rows: one index load per ROW and 16-byte copies instead
+    of ATen's element-wise gather over the expanded index.  Any dtype (rows are opaque bytes).  No autograd: a source that needs a
+    gradient, or a layout the kernel does not take, goes through ``torch.gather`` (same values)."""
+    c = src.shape[2] if src.dim() == 3 else 0
+    fast = (src.dim() == 3 and idx.dim() == 3 and idx.shape[2] == 1 and idx.shape[0] == src.shape[0] and src.is_cuda and idx.is_cuda
+            and idx.dtype == torch.int64 and c > 0 and src.shape[1] > 0
+            and not (torch.is_grad_enabled() and src.requires_grad)
+            and src.shape[0] <= 0x7fffffff and src.shape[1] <= 0x7fffffff and idx.shape[1] <= 0x7fffffff
+            and c * src.element_size() <= 0x7fffffff)
+    if not fast:
+        return src.gather(1, idx.expand(-1, -1, c) if src.dim() == 3 else idx)
+    dev = _lib.require_cuda(src, idx)
+    src, idx = src.contiguous(), idx.contiguous()
+    B, n, k = src.shape[0], src.shape[1], idx.shape[1]
+    out = torch.empty((B, k, c), dtype=src.dtype, device=dev)
+    if B * k:
+        rb = c * src.element_size()
+        with torch.cuda.device(dev):
+            _call("clusten_gather_rows", dev, src.data_ptr(), idx.data_ptr(), out.data_ptr(), B, n, k, rb, 0, nbytes=2 * B * k * rb + 8 * B * k)
+    return out
+
+
+# ---- stem: conv 3x3 / 2 + BatchNorm (eval) + GELU in one pass ------------------------------------------------------------------
+STEM_OC = (16, 24, 32, 48, 64)
+
+
+def stem_conv_bn_gelu_supported(x, conv, bn):
+    return bool(x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3 and conv.in_channels == 3
+                and conv.out_channels in STEM_OC and conv.kernel_size == (3, 3) and conv.stride == (2, 2) and conv.padding == (1, 1)
+                and conv.dilation == (1, 1) and conv.groups == 1 and conv.padding_mode == "zeros" and conv.weight.dtype == torch.float32
+                and not bn.training and bn.track_running_stats and bn.running_mean is not None and x.shape[0] <= 65535
+                and not torch.is_autocast_enabled()
+                and not (torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad or (bn.weight is not None and bn.weight.requires_grad))))
+
+
+def stem_conv_bn_gelu(x, conv, bn):
+    """``gelu(bn(conv(x)))`` for the first stem convolution (PatchEmbed.forward, backbone/aff.py:549) in fp32 inference:
+    clusten_stem_conv_bn_gelu, one pass over the [B, OC, H/2, W/2] map instead of cuDNN conv + ATen bias add + cuDNN BatchNorm + ATen
+    GELU.  Caller checks ``stem_conv_bn_gelu_supported`` first.  No autograd."""
+    dev = _lib.require_cuda(x, conv.weight, conv.bias, bn.running_mean, bn.running_var, bn.weight, bn.bias)
+    x = x.contiguous()
+    B, IC, H, W = x.shape
+    OC = conv.out_channels
+    y = torch.empty((B, OC, (H + 1) // 2, (W + 1) // 2), dtype=torch.float32, device=dev)
+    if y.numel():
+        w = conv.weight.detach().contiguous()
+        f = lambda t: None if t is None else t.detach().float().contiguous()  # noqa: E731
+        cb, m, v, g, b = f(conv.bias), f(bn.running_mean), f(bn.running_var), f(bn.weight), f(bn.bias)
+        with torch.cuda.device(dev):
+            _call("clusten_stem_conv_bn_gelu", dev, x.data_ptr(), w.data_ptr(), _lib.ptr(cb), m.data_ptr(), v.data_ptr(), _lib.ptr(g),
+                  _lib.ptr(b), float(bn.eps), y.data_ptr(), B, IC, H, W, OC, nbytes=4 * (x.numel() + y.numel()))
+    return y

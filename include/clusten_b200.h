@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CLUSTEN_ABI_VERSION 5
+#define CLUSTEN_ABI_VERSION 6
 
 enum { CLUSTEN_F32 = 0, CLUSTEN_F16 = 1, CLUSTEN_BF16 = 2 };
 
@@ -348,6 +348,23 @@ size_t clusten_topk_workspace_bytes(int B, int n);
 int clusten_topk_select(const float *score, int B, int n, int k, int64_t *idx_out, int64_t out_stride,
                         void *workspace, size_t workspace_bytes, void *stream);
 int clusten_mask_select(const float *mask, int B, int n, int count, int64_t *idx_out, int64_t out_stride, void *stream);
+
+/* ---- row gather: out[b,i,:] = src[b, idx[b,i], :] for i < n_out -- the `x.gather(index=idx.expand(-1,-1,c), dim=1)` row
+ * reorders / selections of backbone/aff.py:332,335,340,471 (features into cluster order, kept tokens' positions, member rows and
+ * masks after a merge).  Rows are opaque: row_bytes bytes each (fp32 features, int64 member rows, uint8 masks alike), copied as
+ * 16 / 8 / 4 / 1-byte pieces by alignment.  src [B,n_src,row_bytes], idx int64 [B,n_out], out [B,n_out,row_bytes], all contiguous.
+ * An index outside [0, n_src) copies nothing and sets *bad (device int, or NULL) to 1. */
+int clusten_gather_rows(const void *src, const int64_t *idx, void *out, int B, int n_src, int n_out, int row_bytes,
+                        int *bad, void *stream);
+
+/* ---- first half of the stem, fp32 inference: y = GELU(BatchNorm_eval(Conv2d(3 -> OC, 3x3, stride 2, padding 1)(x))) --
+ * `self.act1(self.bn(self.proj1(x)))` of PatchEmbed.forward (backbone/aff.py:527-529,549) in one pass instead of four.
+ * x [B,IC,H,W], weight [OC,IC,3,3], bias [OC] or NULL, bn_mean / bn_var [OC] (running statistics), bn_weight / bn_bias [OC] or
+ * NULL, y [B,OC,(H+1)/2,(W+1)/2]; NCHW, contiguous, fp32.  IC = 3 and OC in {16, 24, 32, 48, 64}; anything else returns
+ * CLUSTEN_EUNSUPPORTED (the caller keeps the four-pass formulation). */
+int clusten_stem_conv_bn_gelu(const float *x, const float *weight, const float *bias, const float *bn_mean, const float *bn_var,
+                              const float *bn_weight, const float *bn_bias, float eps, float *y, int B, int IC, int H, int W,
+                              int OC, void *stream);
 
 #ifdef __cplusplus
 }

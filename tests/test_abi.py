@@ -44,7 +44,7 @@ def test_ctypes_table_mirrors_header(lib):
 
 
 def test_abi_version(lib):
-    assert lib.clusten_abi_version() == 5
+    assert lib.clusten_abi_version() == 6
 
 
 def test_argument_errors_without_gpu(lib):

@@ -873,12 +873,15 @@ def test_scale_residual_falls_back_for_shapes_the_kernel_does_not_take():
     assert torch.equal(ops.scale_residual(res2, x2), res2 + x2)
 
 
-@pytest.mark.parametrize("n,m,nbhd,hw", [(4096, 8, 48, 64), (2003, 8, 48, 64), (1540, 24, 144, 64), (655, 8, 48, 128)])
-def test_stage_prepare_matches_torch_formulation(n, m, nbhd, hw):
-    """clusten_stage_prepare against the op-by-op torch formulation of aff.py:475-485 + torch.unique (bit-exact integers)."""
+@pytest.mark.parametrize("bitmap", ["1", "0"])
+@pytest.mark.parametrize("n,m,nbhd,hw,B", [(4096, 8, 48, 64, 2), (2003, 8, 48, 64, 2), (1540, 24, 144, 64, 2), (655, 8, 48, 128, 2),
+                                          (40000, 8, 48, 256, 4), (30001, 8, 48, 512, 3), (1540, 6, 36, 64, 2)])
+def test_stage_prepare_matches_torch_formulation(n, m, nbhd, hw, B, bitmap, monkeypatch):
+    """clusten_stage_prepare against the op-by-op torch formulation of aff.py:475-485 + torch.unique (bit-exact integers); both
+    marking schemes (shared-memory bitmap per CTA = default, global byte map), incl. sizes where every CTA loops and m % 4 != 0."""
     import math
     from autofocusformermod_b200 import point_utils as pu
-    B = 2
+    monkeypatch.setenv("CLUSTEN_PREPARE_BITMAP", bitmap)
     g = torch.Generator().manual_seed(n)
     pos = torch.stack([torch.randperm(hw * hw, generator=g)[:n] for _ in range(B)])
     pos = torch.stack([pos % hw, pos // hw], dim=-1).float().cuda()
@@ -906,3 +909,67 @@ def test_stage_prepare_matches_torch_formulation(n, m, nbhd, hw):
     U = int(r2[5].item())
     assert U == ref_uniq.numel() and r2[3].numel() == min((2 * hw - 1) ** 2, B * n * nnc * m) >= U
     assert torch.equal(r2[3][:U], ref_uniq) and bool((r2[3][U:] == 0).all()) and torch.equal(r2[4], bias_idx)
+
+
+@pytest.mark.parametrize("dtype,c", [(torch.float32, 32), (torch.float32, 96), (torch.float32, 2), (torch.float32, 1), (torch.int64, 48),
+                                     (torch.int64, 1), (torch.uint8, 48), (torch.uint8, 3), (torch.bfloat16, 5), (torch.float16, 384)])
+@pytest.mark.parametrize("B,n,k", [(2, 1000, 1000), (3, 4099, 517), (1, 7, 20)])
+def test_gather_rows_equals_torch_gather(dtype, c, B, n, k):
+    """clusten_gather_rows against ``src.gather(1, idx.expand(-1, -1, c))`` (aff.py:332,335,340,471): bit-identical for every
+    row width / alignment class (16-, 8-, 4-, 1-byte pieces), permutations, subsets and repeated rows."""
+    from autofocusformermod_b200 import ops
+    g = torch.Generator().manual_seed(1000 * c + n)
+    if dtype.is_floating_point:
+        src = torch.randn(B, n, c, generator=g).to(dtype).cuda()
+    else:
+        src = torch.randint(0, 200, (B, n, c), generator=g).to(dtype).cuda()
+    if k == n:
+        idx = torch.stack([torch.randperm(n, generator=g) for _ in range(B)]).unsqueeze(2).cuda()
+    else:
+        idx = torch.randint(0, n, (B, k, 1), generator=g).cuda()
+    before = ops.launch_count()
+    out = ops.gather_rows(src, idx)
+    assert ops.launch_count() == before + 1, "the native row gather did not run"
+    assert out.dtype == src.dtype and torch.equal(out, src.gather(1, idx.expand(-1, -1, c)))
+    # a view whose rows are not contiguous is copied first; a source that needs a gradient keeps autograd (torch.gather)
+    wide = torch.cat([src, src], dim=2)[:, :, :c]
+    assert torch.equal(ops.gather_rows(wide, idx), out)
+    if dtype == torch.float32:
+        leaf = src.clone().requires_grad_(True)
+        o2 = ops.gather_rows(leaf, idx)
+        assert o2.requires_grad and torch.equal(o2.detach(), out)
+        with torch.no_grad():
+            assert not ops.gather_rows(leaf, idx).requires_grad
+
+
+@pytest.mark.parametrize("oc", [16, 24, 32, 48, 64])
+@pytest.mark.parametrize("B,H,W", [(2, 64, 96), (1, 37, 50), (3, 128, 128)])
+def test_stem_conv_bn_gelu_matches_torch(oc, B, H, W):
+    """clusten_stem_conv_bn_gelu against ``act1(bn(proj1(x)))`` of PatchEmbed.forward (aff.py:527-529,549) evaluated in float64:
+    <= 1e-5 (north-star tolerance; the fp32 cuDNN / ATen chain itself is ~1e-6 from float64), odd sizes included."""
+    from torch import nn
+    from autofocusformermod_b200 import ops
+    torch.manual_seed(oc + H)
+    conv = nn.Conv2d(3, oc, 3, stride=2, padding=1).cuda()
+    bn = nn.BatchNorm2d(oc).cuda()
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.5)
+        bn.running_var.uniform_(0.3, 2.0)
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.3)
+    bn.eval()
+    x = torch.randn(B, 3, H, W, device="cuda") * 1.7
+    with torch.no_grad():
+        assert ops.stem_conv_bn_gelu_supported(x, conv, bn)
+        before = ops.launch_count()
+        y = ops.stem_conv_bn_gelu(x, conv, bn)
+        assert ops.launch_count() == before + 1
+        c64, b64 = conv.double(), bn.double()
+        ref = torch.nn.functional.gelu(b64(c64(x.double())))
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    assert rel_err(y, ref) <= 1e-5
+    assert float((y.double() - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+    # not supported -> the caller keeps the four-pass formulation
+    bn.train()
+    assert not ops.stem_conv_bn_gelu_supported(x, conv.float(), bn.float())
+    assert not ops.stem_conv_bn_gelu_supported(x.half(), conv, bn.eval())
