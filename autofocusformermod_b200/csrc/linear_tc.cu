@@ -89,6 +89,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
                    "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr) : "memory");
 }
+// {lo half = fp16(a), hi half = fp16(b)}, round to nearest even, values beyond the fp16 range -> +-65504
+__device__ __forceinline__ uint32_t f16x2_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
 // round to TF32 (nearest, ties away -- cvt.rna) on the bit pattern: the low 13 mantissa bits end up zero
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
@@ -131,7 +137,7 @@ __device__ __forceinline__ void epi_bar() {
 // byte offset of 16-byte chunk c of row r inside a [rows x 128 B] box written / read by the TMA unit with SWIZZLE_128B
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
-constexpr int NA = 4;                                  // A-operand stages in tensor memory (64 columns each: xh | xl)
+constexpr int NA_MAX = 8;                              // A-operand stages in tensor memory: 4 x 64 columns (TF32) or 8 x 32 columns (fp16)
 constexpr int A_COL0 = 256;                            // tensor-memory columns 0..255: the two accumulators, 256..511: the A ring
 constexpr int SUB_BYTES = BM * 128;                    // one [128 rows x 32 columns] piece of the output tile, 16 KiB
 
@@ -150,6 +156,7 @@ template <int BN, bool H> struct Cfg {
     static constexpr int XS = XS_FIT > 8 ? 8 : XS_FIT;
     static constexpr int ACC_COLS = BN == 96 ? 128 : BN;                 // column pitch of the two accumulators
     static constexpr int A_COLS = H ? 32 : 64;                           // TMEM columns of one A stage: xh | xl
+    static constexpr int NA = 256 / A_COLS;                              // A stages: tensor-memory columns 256..511
     static constexpr int KSTEPS = H ? BK / 16 : BK / 8;                  // MMA K steps per chunk (8 TMEM columns / 32 B of B each)
     static constexpr uint32_t IDESC = (1u << 4) | ((H ? 0u : 2u) << 7) | ((H ? 0u : 2u) << 10) | ((uint32_t)(BN >> 3) << 17) |
                                       ((uint32_t)(BM >> 4) << 24);
@@ -160,6 +167,17 @@ template <int BN, bool H> struct Cfg {
 
 enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_RES = 2 };
 
+// -DCLUSTEN_TC_PROFILE: cycle counters of the issuer warp and of the first epilogue warp, per CTA (tools/lin_profile.py reads them
+// through clusten_linear_tc_profile).  Not compiled into the shipped library.
+#ifdef CLUSTEN_TC_PROFILE
+__device__ long long tc_prof[148 * 16];
+#define TC_CLK(v) const long long v = clock64()
+#define TC_ADD(slot, a_, b_) prof[slot] += (b_) - (a_)
+#else
+#define TC_CLK(v)
+#define TC_ADD(slot, a_, b_)
+#endif
+
 struct Args {
     const float *bias, *gamma;
     const float *ln_mean, *ln_rstd, *ln_gamma, *ln_beta;   // LayerNorm of the X rows applied while they are split (or NULL)
@@ -168,6 +186,8 @@ struct Args {
     float alpha;
     int alpha_cols;
     const float *w_inv_scale;                              // fp16 split: 1 / (power-of-two scale of weight row n), [N]
+    int resident;                                          // 1: a CTA owns ROW tiles and walks their column tiles with the split rows kept in tensor memory
+    int dbg;                                               // experiment switches (CLUSTEN_TC_DBG; wrong results): 1 = no X loads, 2 = no W loads, 4 = no split, 8 = no epilogue
 };
 
 template <int BN, int EPI, bool H>
@@ -176,13 +196,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                  const __grid_constant__ CUtensorMap mapWl, const __grid_constant__ CUtensorMap mapY,
                  const __grid_constant__ CUtensorMap mapRes, const Args a) {
     using C = Cfg<BN, H>;
-    constexpr int XS = C::XS, WS = C::WS;
+    constexpr int XS = C::XS, WS = C::WS, NA = C::NA;
     extern __shared__ uint8_t tc_smem_raw[];
     const uint32_t base = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
     uint8_t *gbase = tc_smem_raw + (base - smem_u32(tc_smem_raw));
     const uint32_t wring = base + C::XRING, cbuf = base + C::RING, tail = cbuf + C::CBUF;
     const uint32_t bar_xfull = tail, bar_xempty = tail + 8 * XS, bar_wfull = tail + 16 * XS, bar_wempty = bar_wfull + 8 * WS;
-    const uint32_t bar_afull = bar_wempty + 8 * WS, bar_aempty = bar_afull + 8 * NA, bar_accf = bar_aempty + 8 * NA, bar_acce = bar_accf + 16;
+    const uint32_t bar_afull = bar_wempty + 8 * WS, bar_aempty = bar_afull + 8 * NA_MAX, bar_accf = bar_aempty + 8 * NA_MAX, bar_acce = bar_accf + 16;
     const uint32_t bar_cfull = bar_acce + 16;                            // CSETS * NSUB barriers
     uint8_t *gtail = gbase + C::RING + C::CBUF;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gtail + 512);
@@ -220,16 +240,25 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 
     const int KC = a.K / BK, tiles = a.tiles_m * a.tiles_n;
     const int chain = a.chain;
+    // Tile walk of this CTA.  Default: tiles t = blockIdx.x, + gridDim.x, ... with the column tile running fastest across CTAs; every
+    // tile loads and splits its X rows.  Resident (K <= NA chunks, more than one column tile): the CTA owns ROW tiles o = blockIdx.x,
+    // + gridDim.x, ... and walks their column tiles i = 0 .. tiles_n - 1 itself; the rows are loaded and split ONCE, stay in their
+    // tensor-memory stages for all column tiles, and only the weights stream (what an SM ingests per chunk halves, section 5b).
+    const bool res = a.resident != 0;
+    const int outer_n = res ? a.tiles_m : tiles, inner_n = res ? a.tiles_n : 1;
 
     if (warp == 0) {                                                     // ---- TMA producer, X (from HBM: the deep ring) ----
         uint32_t s = 0, ph = 0;
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-            const int m0 = (t / a.tiles_n) * BM;
+        for (int o = blockIdx.x; o < outer_n; o += gridDim.x) {
+            const int m0 = (res ? o : o / a.tiles_n) * BM;
             for (int kc = 0; kc < KC; ++kc) {
                 mbar_wait(bar_xempty + 8 * s, ph ^ 1u);
                 if (elect_one()) {
-                    mbar_expect_tx(bar_xfull + 8 * s, A_BYTES);
-                    tma_box_2d(base + s * A_BYTES, &mapX, bar_xfull + 8 * s, kc * BK, m0);
+                    if (a.dbg & 1) mbar_arrive(bar_xfull + 8 * s);
+                    else {
+                        mbar_expect_tx(bar_xfull + 8 * s, A_BYTES);
+                        tma_box_2d(base + s * A_BYTES, &mapX, bar_xfull + 8 * s, kc * BK, m0);
+                    }
                 }
                 __syncwarp();
                 if (++s == XS) { s = 0; ph ^= 1u; }
@@ -237,15 +266,19 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         }
     } else if (warp == 14) {                                             // ---- TMA producer, pre-split weights (L2) ----
         uint32_t s = 0, ph = 0;
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-            const int n0 = (t % a.tiles_n) * BN;
+        for (int o = blockIdx.x; o < outer_n; o += gridDim.x)
+        for (int i = 0; i < inner_n; ++i) {
+            const int n0 = (res ? i : o % a.tiles_n) * BN;
             for (int kc = 0; kc < KC; ++kc) {
                 const uint32_t st = wring + s * C::WSTAGE;
                 mbar_wait(bar_wempty + 8 * s, ph ^ 1u);
                 if (elect_one()) {
-                    mbar_expect_tx(bar_wfull + 8 * s, C::WSTAGE);
-                    tma_box_2d(st, &mapWh, bar_wfull + 8 * s, kc * BK, n0);
-                    tma_box_2d(st + C::B_BYTES, &mapWl, bar_wfull + 8 * s, kc * BK, n0);
+                    if (a.dbg & 2) mbar_arrive(bar_wfull + 8 * s);
+                    else {
+                        mbar_expect_tx(bar_wfull + 8 * s, C::WSTAGE);
+                        tma_box_2d(st, &mapWh, bar_wfull + 8 * s, kc * BK, n0);
+                        tma_box_2d(st + C::B_BYTES, &mapWl, bar_wfull + 8 * s, kc * BK, n0);
+                    }
                 }
                 __syncwarp();
                 if (++s == WS) { s = 0; ph ^= 1u; }
@@ -259,14 +292,26 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         constexpr uint32_t WSTEP = C::WSTAGE >> 4, WLO = C::B_BYTES >> 4;            // descriptor address units (16 bytes)
         const uint32_t xa0 = tmem + A_COL0;
         uint32_t s = 0, ph = 0, sa = 0, pa = 0, buf = 0, pacc = 1;        // W slot / parity, A stage / parity, accumulator / its "drained" parity
-        const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-        for (int t = 0; t < my_tiles; ++t) {
+#ifdef CLUSTEN_TC_PROFILE
+        long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const long long prof_t0 = clock64();
+#endif
+        for (int o = blockIdx.x; o < outer_n; o += gridDim.x) {
+            const uint32_t sa0 = sa, pa0 = pa;                           // resident: every column tile revisits the A stages of its row tile
+        for (int i = 0; i < inner_n; ++i) {
+            sa = sa0; pa = pa0;
+            const bool free_a = i == inner_n - 1;                        // ... and the last one hands them back to the split warps
             int cc = 0;                                                  // chunk inside the current accumulator chain
             for (int kc = 0; kc < KC; ++kc) {
                 const bool first = cc == 0, last = cc == chain - 1 || kc == KC - 1;
+                TC_CLK(c0);
                 if (first) mbar_wait(bar_acce + 8 * buf, pacc);          // the epilogue has drained this accumulator
+                TC_CLK(c1);
                 mbar_wait(bar_wfull + 8 * s, ph);
+                TC_CLK(c2);
                 mbar_wait(bar_afull + 8 * sa, pa);
+                TC_CLK(c3);
+                TC_ADD(0, c0, c1); TC_ADD(1, c1, c2); TC_ADD(2, c2, c3);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint64_t wh = wdesc0 + s * WSTEP, wl = wh + WLO;
@@ -280,10 +325,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < C::KSTEPS; ++k) umma_ts<H>(d, xh + 8 * k, wh + 2 * k, C::IDESC, 1u);
                     umma_commit(bar_wempty + 8 * s);                     // both rings are free once these MMAs have read them
-                    umma_commit(bar_aempty + 8 * sa);
+                    if (free_a) umma_commit(bar_aempty + 8 * sa);
                     if (last) umma_commit(bar_accf + 8 * buf);
                 }
                 __syncwarp();
+                TC_CLK(c4);
+                TC_ADD(3, c3, c4);
+#ifdef CLUSTEN_TC_PROFILE
+                prof[4] += 1;
+#endif
                 if (++s == WS) { s = 0; ph ^= 1u; }
                 if (++sa == NA) { sa = 0; pa ^= 1u; }
                 ++cc;
@@ -294,21 +344,41 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 }
             }
         }
+        }
+#ifdef CLUSTEN_TC_PROFILE
+        if (lane == 0 && blockIdx.x < 148) {
+            for (int x = 0; x < 5; ++x) tc_prof[blockIdx.x * 16 + x] = prof[x];
+            tc_prof[blockIdx.x * 16 + 5] = clock64() - prof_t0;
+        }
+#endif
     } else if (warp < 6) {                                               // ---- split x -> (xh, xl), row per thread, into TMEM ----
         const int q = warp & 3, row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         uint32_t s = 0, ph = 0, sa = 0, pa = 0;
-        const bool ln = a.ln_mean != nullptr;
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-            const int64_t r = (int64_t)(t / a.tiles_n) * BM + row;
+        const bool ln = a.ln_mean != nullptr, ln_affine = a.ln_gamma != nullptr;
+        for (int o = blockIdx.x; o < outer_n; o += gridDim.x) {
+            const int64_t r = (int64_t)(res ? o : o / a.tiles_n) * BM + row;
             const float mu = ln && r < a.R ? __ldg(a.ln_mean + r) : 0.f, rs = ln && r < a.R ? __ldg(a.ln_rstd + r) : 0.f;
             for (int kc = 0; kc < KC; ++kc) {
                 mbar_wait(bar_xfull + 8 * s, ph);
+                if (a.dbg & 4) {                                         // experiment: no LDS / split / tcgen05.st, hand-offs only
+                    mbar_arrive(bar_xempty + 8 * s);
+                    mbar_wait(bar_aempty + 8 * sa, pa ^ 1u);
+                    mbar_arrive(bar_afull + 8 * sa);
+                    if (++s == XS) { s = 0; ph ^= 1u; }
+                    if (++sa == NA) { sa = 0; pa ^= 1u; }
+                    continue;
+                }
                 const uint8_t *xs = gbase + s * A_BYTES;
                 float4 x[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4 *>(xs + swz(row, c));
-                if (ln) {                                                // y = (x - mean) * rstd * gamma + beta, as ln_fwd_kernel rounds it
+                if (ln && !ln_affine) {                                  // gamma / beta folded into the weights and the bias by the caller
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        x[c].x = (x[c].x - mu) * rs; x[c].y = (x[c].y - mu) * rs; x[c].z = (x[c].z - mu) * rs; x[c].w = (x[c].w - mu) * rs;
+                    }
+                } else if (ln) {                                         // y = (x - mean) * rstd * gamma + beta, as ln_fwd_kernel rounds it
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         const float4 g = __ldg(reinterpret_cast<const float4 *>(a.ln_gamma + kc * BK + 4 * c));
@@ -324,12 +394,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     if (H) {                                             // fp16 hi / lo, two K elements per 32-bit TMEM column (even k low)
 #pragma unroll
                         for (int e = 0; e < 4; e += 2) {
-                            const float x0 = fminf(fmaxf(xv[e], -65504.f), 65504.f), x1 = fminf(fmaxf(xv[e + 1], -65504.f), 65504.f);
-                            const __half2 hh = __floats2half2_rn(x0, x1);
-                            const float2 hf = __half22float2(hh);
-                            const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-                            h[2 * c + e / 2] = *reinterpret_cast<const uint32_t *>(&hh);
-                            l[2 * c + e / 2] = *reinterpret_cast<const uint32_t *>(&ll);
+                            // saturating conversions (F2FP.SATFINITE, one instruction per pair): |x| beyond the fp16 range gives
+                            // hi = +-65504 and a lo that saturates as well -- a finite result instead of inf.  (The explicit clamp
+                            // this replaces was 64 of the ~180 instructions of a chunk, and these warps are what the MMAs wait for.)
+                            const uint32_t hh = f16x2_sat(xv[e], xv[e + 1]);
+                            const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&hh));
+                            h[2 * c + e / 2] = hh;
+                            l[2 * c + e / 2] = f16x2_sat(xv[e] - hf.x, xv[e + 1] - hf.y);
                         }
                     } else {
 #pragma unroll
@@ -371,16 +442,21 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         const bool elected = et == 0;
         uint32_t ch = 0, nt = 0;                                         // chains, tiles of this CTA so far
         float acc[HC];
-        if (EPI == EPI_RES && elected && (int)blockIdx.x < tiles) {      // residual pieces of the first tile
-            const int m0 = (blockIdx.x / a.tiles_n) * BM, n0 = (blockIdx.x % a.tiles_n) * BN;
+#ifdef CLUSTEN_TC_PROFILE
+        long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const long long prof_t0 = clock64();
+#endif
+        if (EPI == EPI_RES && elected && (int)blockIdx.x < outer_n) {    // residual pieces of the first tile
+            const int m0 = (res ? blockIdx.x : blockIdx.x / a.tiles_n) * BM, n0 = (res ? 0 : blockIdx.x % a.tiles_n) * BN;
 #pragma unroll
             for (int j = 0; j < C::NSUB; ++j) {
                 mbar_expect_tx(bar_cfull + 8 * j, SUB_BYTES);
                 tma_box_2d(cbuf + j * SUB_BYTES, &mapRes, bar_cfull + 8 * j, n0 + 32 * j, m0);
             }
         }
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++nt) {
-            const int m0 = (t / a.tiles_n) * BM, n0 = (t % a.tiles_n) * BN;
+        for (int o = blockIdx.x; o < outer_n; o += gridDim.x)
+        for (int ci = 0; ci < inner_n; ++ci, ++nt) {
+            const int m0 = (res ? o : o / a.tiles_n) * BM, n0 = (res ? ci : o % a.tiles_n) * BN;
             const uint32_t set = C::CSETS == 2 ? (nt & 1u) : 0u;
             if (EPI == EPI_RES && C::CSETS == 1 && nt > 0 && elected) {
                 // one staging set: the residual pieces of this tile go in as soon as the previous tile's stores have read it, and
@@ -400,7 +476,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             }
             for (int kc0 = 0; kc0 < KC; kc0 += chain, ++ch) {
                 const uint32_t buf = ch & 1u;
+                TC_CLK(e0);
                 mbar_wait(bar_accf + 8 * buf, (ch >> 1) & 1u);
+                TC_CLK(e1);
+                TC_ADD(0, e0, e1);
                 __syncwarp();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * C::ACC_COLS + hf * HC;
@@ -414,14 +493,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(bar_acce + 8 * buf);
+                TC_CLK(e2);
+                TC_ADD(1, e1, e2);
             }
+            TC_CLK(e3);
             // the staging set of this tile: the stores of its previous user must have read it (one set: the previous tile, two sets:
             // the tile before that, whose stores were committed one group earlier)
+            if (EPI != EPI_RES && (a.dbg & 8)) continue;                 // experiment: drains only, no epilogue arithmetic / stores
             if (elected) {
                 if (C::CSETS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             }
             epi_bar();                                                   // bias in place; the staging set may be written
+            TC_CLK(e4);
+            TC_ADD(2, e3, e4);
             const uint32_t cset = cbuf + set * C::NSUB * SUB_BYTES;
 #pragma unroll
             for (int i = 0; i < HC / 4; ++i) {                           // 16-byte cells of this thread: columns hf * HC + 4 i ..
@@ -453,17 +538,23 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 *cell = make_float4(o[0], o[1], o[2], o[3]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic-proxy writes -> visible to the TMA unit
+            TC_CLK(e5);
+            TC_ADD(3, e4, e5);
             epi_bar();
+            TC_CLK(e6);
+            TC_ADD(4, e5, e6);
             if (elected) {
 #pragma unroll
                 for (int j = 0; j < C::NSUB; ++j)
                     if (n0 + 32 * j < a.N) tma_store_2d(&mapY, cset + j * SUB_BYTES, n0 + 32 * j, m0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 if (EPI == EPI_RES && C::CSETS == 2) {                   // residual pieces of the next tile into the other set, whose
-                    const int tn = t + gridDim.x;                        // last stores (the previous tile's) must have read it
-                    if (tn < tiles) {
+                    // last stores (the previous tile's) must have read it
+                    const bool same_row = ci + 1 < inner_n;              // the next tile of this CTA's walk
+                    const int on = same_row ? o : o + (int)gridDim.x, in_ = same_row ? ci + 1 : 0;
+                    if (on < outer_n) {
                         asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        const int m1 = (tn / a.tiles_n) * BM, n1 = (tn % a.tiles_n) * BN;
+                        const int m1 = (res ? on : on / a.tiles_n) * BM, n1 = (res ? in_ : on % a.tiles_n) * BN;
                         const uint32_t so = (set ^ 1u) * C::NSUB;
 #pragma unroll
                         for (int j = 0; j < C::NSUB; ++j) {
@@ -475,6 +566,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             }
         }
         if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA exits
+#ifdef CLUSTEN_TC_PROFILE
+        if (elected && blockIdx.x < 148) {
+            for (int x = 0; x < 5; ++x) tc_prof[blockIdx.x * 16 + 8 + x] = prof[x];
+            tc_prof[blockIdx.x * 16 + 13] = clock64() - prof_t0;
+        }
+#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -557,7 +654,7 @@ static int launch(const CUtensorMap *m, const Args &a, cudaStream_t st) {
         attr_set = true;
     }
     const int tiles = a.tiles_m * a.tiles_n;
-    linear_tc_kernel<BN, EPI, H><<<std::min(tiles, sm_count()), THREADS, Cfg<BN, H>::SMEM, st>>>(m[0], m[1], m[2], m[3], m[4], a);
+    linear_tc_kernel<BN, EPI, H><<<std::min(a.resident ? a.tiles_m : tiles, sm_count()), THREADS, Cfg<BN, H>::SMEM, st>>>(m[0], m[1], m[2], m[3], m[4], a);
     note_launches(1);
     return check_launch("linear_tc");
 }
@@ -602,6 +699,9 @@ extern "C" int clusten_tf32_split(const float *w, float *hi, float *lo, int64_t 
 // summed inside the tensor-core accumulator before it is added to the fp32 running sum (<= 0: the default, 4).
 // ln_mean / ln_rstd [R] + ln_gamma / ln_beta [K] (or all NULL): the rows of X are LayerNorm-ed while they are split, with the
 // statistics clusten_layer_norm_fwd(y = NULL) wrote -- the `self.norm1(x)` / `self.norm2(x)` / `self.norm(x)` in front of the layer.
+// ln_gamma = ln_beta = NULL with statistics given: the rows are only normalised, (x - mean) * rstd -- for callers that folded the
+// affine part into the layer (W' = W * gamma per input column, bias' = bias + W beta), which takes ~90 instructions and 16 loads per
+// chunk off the split warps, the role the MMAs wait for.
 // w_fp16 = 1: w_hi / w_lo are the fp16 operands of clusten_f16_split and w_inv_scale [N] its per-row factors; X is split into fp16 hi / lo
 // as well (values beyond +-65504 saturate) and the products run as kind::f16 -- half the MMAs of the TF32 form at the same accuracy.
 // Needs K % 32 == 0, N % 4 == 0, 16-byte aligned rows; anything else returns CLUSTEN_EUNSUPPORTED.
@@ -622,8 +722,9 @@ extern "C" int clusten_linear_tc_f32(const float *x, const void *w_hi, const voi
                                      const float *ln_gamma, const float *ln_beta, int w_fp16, const float *w_inv_scale, void *stream) {
     if (R < 0 || K <= 0 || N <= 0 || ldx < K || ldy < N || !x || !w_hi || !w_lo || !y || (epi == tc::EPI_RES && (!res || ldres < N)))
         return set_error(CLUSTEN_EINVAL, "linear_tc: bad arguments R=%lld K=%d N=%d", (long long)R, K, N);
-    if ((ln_mean != nullptr) != (ln_rstd != nullptr) || (ln_mean && (!ln_gamma || !ln_beta || !aligned16(ln_gamma) || !aligned16(ln_beta))))
-        return set_error(CLUSTEN_EINVAL, "linear_tc: LayerNorm needs mean, rstd [R] and 16-byte aligned gamma, beta [K]");
+    if ((ln_mean != nullptr) != (ln_rstd != nullptr) || (ln_gamma != nullptr) != (ln_beta != nullptr) || (ln_gamma && !ln_mean) ||
+        (ln_gamma && (!aligned16(ln_gamma) || !aligned16(ln_beta))))
+        return set_error(CLUSTEN_EINVAL, "linear_tc: LayerNorm needs mean, rstd [R] and, unless they are folded into the weights, 16-byte aligned gamma, beta [K]");
     if (R == 0) return 0;
     if (K % tc::BK || N % 4 || ldx % 4 || ldy % 4 || (epi == tc::EPI_RES && ldres % 4) || !aligned16(x) || !aligned16(w_hi) || !aligned16(w_lo) ||
         !aligned16(y) || (bias && !aligned16(bias)) || (res && !aligned16(res)) || (gamma && !aligned16(gamma)) || R > (1LL << 31) - tc::BM)
@@ -648,6 +749,24 @@ extern "C" int clusten_linear_tc_f32(const float *x, const void *w_hi, const voi
     a.alpha = alpha; a.alpha_cols = epi == tc::EPI_BIAS ? alpha_cols : 0;
     if (half && !w_inv_scale) return set_error(CLUSTEN_EINVAL, "linear_tc: the fp16 split needs w_inv_scale [N]");
     a.w_inv_scale = half ? w_inv_scale : nullptr;
+    // resident rows: K fits the A stages of tensor memory (8 chunks fp16, 4 chunks TF32), there is more than one column tile to walk,
+    // and the row tiles alone fill most of the SMs (else spreading row x column tiles over all SMs wins).  CLUSTEN_TC_RESIDENT=0: off
+    {
+        const char *e = getenv("CLUSTEN_TC_RESIDENT");
+        const int kc = K / tc::BK, na = half ? 8 : 4;
+        a.resident = !(e && e[0] == '0') && kc <= na && a.tiles_n >= 2 && a.tiles_m * 4 >= tc::sm_count() * 3;
+        const char *d = getenv("CLUSTEN_TC_DBG");
+        a.dbg = d ? atoi(d) : 0;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     return half ? tc::launch_bn<true>(BN, epi, m, a, st) : tc::launch_bn<false>(BN, epi, m, a, st);
 }
+
+#ifdef CLUSTEN_TC_PROFILE
+// per CTA (148 x 16 counters): issuer [0] wait drained accumulator, [1] wait W, [2] wait A, [3] issue MMAs + commits, [4] chunks, [5] role
+// cycles; first epilogue thread [8] wait accumulator, [9] drain, [10] wait staging + barrier, [11] arithmetic + STS, [12] barrier, [13] role cycles
+extern "C" int clusten_linear_tc_profile(long long *host_out) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(host_out, tc::tc_prof, sizeof(long long) * 148 * 16) == cudaSuccess ? 0 : -1;
+}
+#endif

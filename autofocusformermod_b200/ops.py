@@ -901,6 +901,35 @@ def f16_split(weight):
     return hi, lo, inv
 
 
+# LayerNorm in front of the layer: gamma / beta folded into the layer (W' = W * gamma per input column, b' = b + W beta; computed once per
+# parameter version in float64) so that the GEMM's split warps only normalise, (x - mean) * rstd.  CLUSTEN_LN_FOLD=0: the affine part
+# is applied while the rows are split (bit-identical to LayerNorm-then-Linear; ~90 more instructions per K chunk in the critical role).
+LN_FOLD = os.environ.get("CLUSTEN_LN_FOLD", "1") != "0"
+_lnfold_cache = {}                                     # id(weight) -> (weakrefs, versions, W', b')
+
+
+def ln_folded_layer(weight, bias, ln_weight, ln_bias):
+    """(W', b') with ``F.linear(F.layer_norm(x, w=ln_weight, b=ln_bias), weight, bias) == F.linear(normalise(x), W', b')``; cached until
+    one of the four parameters changes (version counters / storage)."""
+    import weakref
+    ts = (weight, bias, ln_weight, ln_bias)
+    sig = tuple((None if t is None else (t._version, t.data_ptr())) for t in ts)
+    hit = _lnfold_cache.get(id(weight))
+    if hit is not None and hit[1] == sig and all((r is None and t is None) or (r is not None and r() is t) for r, t in zip(hit[0], ts)):
+        return hit[2], hit[3]
+    with torch.no_grad():
+        w64 = weight.detach().double()
+        wf = (w64 * ln_weight.detach().double().unsqueeze(0)).float().contiguous()
+        bf = w64 @ ln_bias.detach().double()
+        if bias is not None:
+            bf = bf + bias.detach().double()
+        bf = bf.float().contiguous()
+    if len(_lnfold_cache) > 4096:
+        _lnfold_cache.clear()
+    _lnfold_cache[id(weight)] = (tuple(None if t is None else weakref.ref(t) for t in ts), sig, wf, bf)
+    return wf, bf
+
+
 def linear_tc_supported(x, weight, bias=None, res=None, gamma=None):
     K = x.shape[-1]
     ok = (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.dim() == 2 and weight.shape[1] == K
@@ -910,13 +939,19 @@ def linear_tc_supported(x, weight, bias=None, res=None, gamma=None):
     return bool(ok)
 
 
-def linear_tc(x, weight, bias=None, epilogue="bias", res=None, gamma=None, alpha=1.0, alpha_cols=0, chain=None, ln=None, split=None):
+def linear_tc(x, weight, bias=None, epilogue="bias", res=None, gamma=None, alpha=1.0, alpha_cols=0, chain=None, ln=None, split=None,
+              ln_fold=None):
     """fp32 ``F.linear`` on the tcgen05 tensor cores (clusten_linear_tc_f32; inference, no autograd) with one of
     ``bias`` (y = x W^T + b, the first ``alpha_cols`` columns then times ``alpha``), ``gelu`` (y = GELU(x W^T + b)) or
     ``residual`` (y = res + gamma * (x W^T + b)) as the epilogue.  ``ln`` = (mean, rstd, ln_weight, ln_bias): the rows of x are
-    LayerNorm-ed on the fly with the statistics of ``layer_norm_stats``.  The caller checks ``linear_tc_supported`` first."""
+    LayerNorm-ed on the fly with the statistics of ``layer_norm_stats``; ``ln_fold`` (default: LN_FOLD) folds its gamma / beta into the
+    weights and the bias (``ln_folded_layer``) so that the kernel only normalises.  The caller checks ``linear_tc_supported`` first."""
     dev = _lib.require_cuda(x, weight, bias, res, gamma)
     K, N = x.shape[-1], weight.shape[0]
+    fold = ln is not None and (LN_FOLD if ln_fold is None else bool(ln_fold))
+    if fold:
+        _check_shapes(ln[2].numel() == K and ln[3].numel() == K, "linear_tc: LayerNorm operands")
+        weight, bias = ln_folded_layer(weight, bias, ln[2], ln[3])
     x2 = x.reshape(-1, K)
     if x2.stride(1) != 1 or x2.stride(0) % 4 or x2.data_ptr() % 16:
         x2 = x2.contiguous()
@@ -941,7 +976,7 @@ def linear_tc(x, weight, bias=None, epilogue="bias", res=None, gamma=None, alpha
         mean, rstd, lw, lb = ln
         lw, lb = lw.detach().float().contiguous(), lb.detach().float().contiguous()
         _check_shapes(mean.numel() == R and rstd.numel() == R and lw.numel() == K and lb.numel() == K, "linear_tc: LayerNorm operands")
-        lnp = [mean.data_ptr(), rstd.data_ptr(), lw.data_ptr(), lb.data_ptr()]
+        lnp = [mean.data_ptr(), rstd.data_ptr(), 0, 0] if fold else [mean.data_ptr(), rstd.data_ptr(), lw.data_ptr(), lb.data_ptr()]
     with torch.cuda.device(dev):
         _call("clusten_linear_tc_f32", dev, x2.data_ptr(), hi.data_ptr(), lo.data_ptr(), _lib.ptr(b), _lib.ptr(r2), _lib.ptr(g),
               y.data_ptr(), R, K, N, x2.stride(0), N, ldres, LINEAR_EPI[epilogue], float(alpha), int(alpha_cols),

@@ -569,7 +569,8 @@ def test_linear_f32_tensor_core(R, K, N):
 
 
 @pytest.mark.parametrize("R,K,N", [(1000, 32, 32), (4173, 128, 256), (300, 96, 288), (129, 768, 2304), (1, 32, 4), (16384, 64, 32),
-                                   (40000, 32, 96), (5000, 256, 100), (777, 1536, 384), (20000, 32, 36)])
+                                   (40000, 32, 96), (5000, 256, 100), (777, 1536, 384), (20000, 32, 36),
+                                   (16384, 256, 768), (20000, 128, 384), (40000, 96, 288), (16500, 256, 200)])
 @pytest.mark.parametrize("epilogue", ["bias", "gelu", "residual"])
 @pytest.mark.parametrize("split", ["tf32", "f16"])
 def test_linear_tc_tcgen05(R, K, N, epilogue, split):
@@ -632,13 +633,57 @@ def test_linear_tc_layer_norm_in_gemm(R, K, N, epilogue, split):
     xd = x.double()
     m64, v64 = xd.mean(1), xd.var(1, unbiased=False)
     assert rel_err(mean.double(), m64) <= 1e-6 and rel_err(rstd.double(), (v64 + 1e-5).rsqrt()) <= 1e-6
-    y = ops.linear_tc(x, w, b, epilogue, ln=(mean, rstd, lw, lb), split=split)     # None: the default, fp16 for normalised rows
+    y = ops.linear_tc(x, w, b, epilogue, ln=(mean, rstd, lw, lb), split=split, ln_fold=False)     # split None: the default, fp16 for normalised rows
     y_two = ops.linear_tc(ops.layer_norm(x, lw, lb, 1e-5), w, b, epilogue, split=split or "f16")
     assert torch.equal(y, y_two)
     ref = F.layer_norm(xd, (K,), lw.double(), lb.double(), 1e-5) @ w.double().t() + b.double()
     if epilogue == "gelu":
         ref = F.gelu(ref)
     assert rel_err(y.double(), ref) <= 2e-6
+    # default: gamma / beta folded into the layer (W * gamma, b + W beta), the kernel only normalises -- same result to fp32 rounding
+    y_f = ops.linear_tc(x, w, b, epilogue, ln=(mean, rstd, lw, lb), split=split)
+    assert rel_err(y_f.double(), ref) <= 2e-6 and rel_err(y_f, y) <= 2e-6
+    wf, bf = ops.ln_folded_layer(w, b, lw, lb)
+    assert ops.ln_folded_layer(w, b, lw, lb)[0] is wf                   # cached ...
+    lw.mul_(1.5)
+    wf2, _ = ops.ln_folded_layer(w, b, lw, lb)                           # ... until a parameter changes
+    assert wf2 is not wf and rel_err(wf2, 1.5 * wf) <= 1e-6
+    y_n = ops.linear_tc(x, w, None, epilogue, ln=(mean, rstd, lw, lb), split=split)      # no bias: b' = W beta alone
+    ref_n = F.layer_norm(xd, (K,), lw.double(), lb.double(), 1e-5) @ w.double().t()
+    assert rel_err(y_n.double(), F.gelu(ref_n) if epilogue == "gelu" else ref_n) <= 2e-6
+
+
+@pytest.mark.parametrize("R,K,N", [(16384, 256, 768), (20000, 128, 384), (40000, 96, 288), (19000, 64, 160), (16500, 256, 200)])
+@pytest.mark.parametrize("epilogue", ["bias", "gelu", "residual"])
+@pytest.mark.parametrize("split", ["tf32", "f16"])
+def test_linear_tc_resident_rows_equal_streamed(R, K, N, epilogue, split, monkeypatch):
+    """The resident tile walk (a CTA owns row tiles, splits their rows once into tensor memory and walks the column tiles; taken when
+    K fits the A stages -- 8 chunks fp16, 4 chunks TF32 -- and the row tiles fill the SMs) performs the same MMAs in the same order
+    as the streamed walk: BIT-identical results, incl. more row tiles than SMs, K chunk counts that wrap the stage ring mid-tile
+    (K = 96), ragged R and ragged N, and the LayerNorm-on-load form."""
+    from autofocusformermod_b200 import ops
+    g = torch.Generator().manual_seed(R + K + N)
+    x = (torch.randn(R, K, generator=g) * 1.3).cuda()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    res = torch.randn(R, N, generator=g).cuda()
+    gam = (torch.rand(N, generator=g) + 0.5).cuda()
+    lw, lb = (torch.rand(K, generator=g) + 0.5).cuda(), torch.randn(K, generator=g).cuda()
+    kw = dict(res=res, gamma=gam, alpha=0.3, alpha_cols=(N // 2) // 4 * 4, split=split)
+    stats = ops.layer_norm_stats(x, lw, lb, 1e-5)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("CLUSTEN_TC_RESIDENT", mode)
+        out[mode] = (ops.linear_tc(x, w, b, epilogue, **kw), ops.linear_tc(x, w, b, epilogue, ln=stats + (lw, lb), **kw))
+    assert torch.equal(out["1"][0], out["0"][0]) and torch.equal(out["1"][1], out["0"][1])
+    ref = x.double() @ w.double().t() + b.double()
+    if epilogue == "gelu":
+        ref = torch.nn.functional.gelu(ref)
+    elif epilogue == "residual":
+        ref = res.double() + gam.double() * ref
+    else:
+        ref[:, :kw["alpha_cols"]] *= 0.3
+    assert rel_err(out["1"][0].double(), ref) <= 2e-6
 
 
 def test_linear_tc_f16_split_scales():
