@@ -66,7 +66,8 @@ SIGNATURES = {
     "clusten_topk_select": (_I, [_P, _I, _I, _I, _P, _L, _P, _Z, _P]),
     "clusten_mask_select": (_I, [_P, _I, _I, _I, _P, _L, _P]),
     "clusten_gather_rows": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
-    "clusten_stem_conv_bn_gelu": (_I, [_P] * 7 + [_c.c_float, _P] + [_I] * 5 + [_P]),
+    "clusten_stem_conv_bn_gelu": (_I, [_P] * 7 + [_c.c_float, _P] + [_I] * 6 + [_P]),
+    "clusten_stem_im2col": (_I, [_P, _P] + [_I] * 5 + [_P]),
 }
 
 _lib = None

@@ -26,7 +26,7 @@ import torch.nn.functional as F
 
 from .ops import (CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction, cluster_attention_core, cluster_attention_fused,
                   cluster_attention_core_pos, cluster_attention_fused_pos, layer_norm, layer_norm_stats, linear, linear_f32, linear_f32_supported, linear_tc, linear_tc_supported,
-                  gather_rows, scale_residual, stem_conv_bn_gelu, stem_conv_bn_gelu_supported, table_linear,
+                  gather_rows, scale_residual, stem_conv_bn_gelu, stem_conv_bn_gelu_supported, stem_gemm_supported, stem_tokens, table_linear,
                   table_linear_supported, table_lookup)
 from .point_utils import knn_keops, merge_select, space_filling_cluster, stage_prepare
 
@@ -85,6 +85,8 @@ def _tcgen05_ok(x):
 NATIVE_GATHER_ROWS = _on("CLUSTEN_GATHER_ROWS")
 # fp32 inference stem: conv1 + BatchNorm + GELU in one pass (clusten_stem_conv_bn_gelu).  CLUSTEN_FUSED_STEM=0: cuDNN / ATen, four passes
 FUSED_STEM = _on("CLUSTEN_FUSED_STEM")
+# ... and its second convolution as an im2col + tcgen05 GEMM whose output rows are the tokens (ops.stem_tokens).  CLUSTEN_STEM_GEMM=0: cuDNN
+STEM_GEMM = _on("CLUSTEN_STEM_GEMM")
 
 
 def _gather(x, idx):
@@ -648,6 +650,11 @@ class PatchEmbed(nn.Module):
         if CHANNELS_LAST_STEM and torch.is_autocast_enabled():
             x = x.contiguous(memory_format=torch.channels_last)
             x = self.proj2(self.act1(self.bn(self.proj1(x))))
+        elif (x.dtype == torch.float32 and x.is_cuda and not torch.is_autocast_enabled() and FUSED_STEM and STEM_GEMM and TCGEN05_LINEAR
+              and not torch.is_grad_enabled() and isinstance(self.act1, nn.GELU) and getattr(self.act1, "approximate", "none") == "none"
+              and stem_gemm_supported(x, self.proj1, self.bn, self.proj2)):
+            tokens, h, w = stem_tokens(x, self.proj1, self.bn, self.proj2)                           # already [b, h * w, c]
+            return self._finish(tokens, h, w)
         elif x.dtype == torch.float32 and x.is_cuda and not torch.is_autocast_enabled():
             # fp32 means fp32: cuDNN is otherwise free to pick TF32 tensor-core convolutions (torch's default), which it does from
             # ~512x512 inputs on -- 1e-3 off the fp32 reference in res2 and enough to flip top-k selections two stages later
@@ -660,7 +667,11 @@ class PatchEmbed(nn.Module):
         else:
             x = self.proj2(self.act1(self.bn(self.proj1(x))))
         b, c, h, w = x.shape
-        x = x.flatten(2).transpose(1, 2)
+        return self._finish(x.flatten(2).transpose(1, 2), h, w)
+
+    def _finish(self, x, h, w):
+        """tokens [b, h * w, c] -> (pos, tokens, h, w): patch norm + the integer grid positions (aff.py:553-563)."""
+        b = x.shape[0]
         if self.norm is not None:
             x = self.norm(x)
         ys, xs = torch.meshgrid(torch.arange(h, device=x.device), torch.arange(w, device=x.device), indexing="ij")

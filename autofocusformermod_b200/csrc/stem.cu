@@ -15,7 +15,9 @@ namespace clusten {
 
 constexpr int STEM_TX = 64, STEM_TY = 4;                 // output pixels of a CTA: 64 along x, 4 rows
 
-template <int OC, int IC>
+// NHWC: y is written pixel-major [B, OH, OW, OC] (each thread stores its OC values as 16-byte pieces) -- the layout the im2col pass
+// below gathers from; else NCHW, what cuDNN's second convolution takes.
+template <int OC, int IC, bool NHWC>
 __global__ void __launch_bounds__(STEM_TX * STEM_TY)
 stem_conv_bn_gelu_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
                          const float *__restrict__ bn_mean, const float *__restrict__ bn_var, const float *__restrict__ bn_w,
@@ -65,22 +67,55 @@ stem_conv_bn_gelu_kernel(const float *__restrict__ x, const float *__restrict__ 
             acc[4 * c4 + 3] = fmaf(in[t], wv.w, acc[4 * c4 + 3]);
         }
     }
-    float *yb = y + ((int64_t)b * OC * OH + oy) * OW + ox;
 #pragma unroll
     for (int c = 0; c < OC; ++c) {
         float v = acc[c] + s_bias[c];
         v = fmaf((v - s_mean[c]) * s_inv[c], s_g[c], s_b[c]);
-        v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-        yb[(int64_t)c * OH * OW] = v;
+        acc[c] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    }
+    if constexpr (NHWC) {
+        float4 *yp = reinterpret_cast<float4 *>(y + (((int64_t)b * OH + oy) * OW + ox) * OC);
+#pragma unroll
+        for (int c4 = 0; c4 < OC / 4; ++c4) yp[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+    } else {
+        float *yb = y + ((int64_t)b * OC * OH + oy) * OW + ox;
+#pragma unroll
+        for (int c = 0; c < OC; ++c) yb[(int64_t)c * OH * OW] = acc[c];
+    }
+}
+
+// im2col of a 3x3 / stride 2 / padding 1 convolution over a pixel-major map: A[(b, py, px), (ky * 3 + kx) * C + c] =
+// mid[b, 2 py - 1 + ky, 2 px - 1 + kx, c] (0 outside the map), columns 9 C .. Kp - 1 zero (K padded to the GEMM's chunk).  One thread per
+// 16-byte piece of an A row: writes are contiguous, reads are C-float runs.  The second stem convolution (proj2, aff.py:530,549) then is
+// ONE GEMM [B OH OW, Kp] x [E, Kp]^T on the tcgen05 Linear kernel, whose output rows are the tokens -- cuDNN answers that convolution
+// with a SIMT sgemm (0.80 ms of the 13.6 ms AFF-Small forward) plus a bias pass plus the NCHW -> token-major copy.
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float4 *__restrict__ mid, float4 *__restrict__ A, int B, int H, int W, int C4, int OH, int OW, int Kp4) {
+    const int64_t total = (int64_t)B * OH * OW * Kp4;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = x / Kp4;
+        const int p = (int)(x - row * Kp4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < 9 * C4) {
+            const int tap = p / C4, c4 = p - tap * C4;
+            const int ky = tap / 3, kx = tap - 3 * ky;
+            const int px = (int)(row % OW);
+            const int64_t t = row / OW;
+            const int py = (int)(t % OH), b = (int)(t / OH);
+            const int iy = 2 * py - 1 + ky, ix = 2 * px - 1 + kx;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(mid + (((int64_t)b * H + iy) * W + ix) * C4 + c4);
+        }
+        A[x] = v;
     }
 }
 
 template <int OC>
 static int stem_launch(const float *x, const float *w, const float *bias, const float *m, const float *v, const float *g, const float *b,
-                       float eps, float *y, int B, int H, int W, cudaStream_t st) {
+                       float eps, float *y, int B, int H, int W, bool nhwc, cudaStream_t st) {
     const int OH = (H + 1) / 2, OW = (W + 1) / 2;
     const dim3 grid((OW + STEM_TX - 1) / STEM_TX, (OH + STEM_TY - 1) / STEM_TY, B), block(STEM_TX, STEM_TY);
-    stem_conv_bn_gelu_kernel<OC, 3><<<grid, block, 0, st>>>(x, w, bias, m, v, g, b, eps, y, H, W, OH, OW);
+    if (nhwc) stem_conv_bn_gelu_kernel<OC, 3, true><<<grid, block, 0, st>>>(x, w, bias, m, v, g, b, eps, y, H, W, OH, OW);
+    else stem_conv_bn_gelu_kernel<OC, 3, false><<<grid, block, 0, st>>>(x, w, bias, m, v, g, b, eps, y, H, W, OH, OW);
     note_launches(1);
     return check_launch("stem_conv_bn_gelu");
 }
@@ -91,18 +126,33 @@ using namespace clusten;
 
 extern "C" int clusten_stem_conv_bn_gelu(const float *x, const float *weight, const float *bias, const float *bn_mean, const float *bn_var,
                                          const float *bn_weight, const float *bn_bias, float eps, float *y, int B, int IC, int H, int W,
-                                         int OC, void *stream) {
+                                         int OC, int channels_last, void *stream) {
     if (B < 0 || H <= 0 || W <= 0 || IC <= 0 || OC <= 0) return set_error(CLUSTEN_EINVAL, "stem: bad sizes B=%d IC=%d H=%d W=%d OC=%d", B, IC, H, W, OC);
     if (!x || !weight || !bn_mean || !bn_var || !y) return set_error(CLUSTEN_EINVAL, "null pointer");
     if (IC != 3 || B > 65535) return set_error(CLUSTEN_EUNSUPPORTED, "stem: IC=%d (3 supported), B=%d (<= 65535)", IC, B);
     if (B == 0) return 0;
+    if (channels_last && !aligned16(y)) return set_error(CLUSTEN_EUNSUPPORTED, "stem: the pixel-major output must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    const bool nhwc = channels_last != 0;
     switch (OC) {
-        case 16: return stem_launch<16>(x, weight, bias, bn_mean, bn_var, bn_weight, bn_bias, eps, y, B, H, W, st);
-        case 24: return stem_launch<24>(x, weight, bias, bn_mean, bn_var, bn_weight, bn_bias, eps, y, B, H, W, st);
-        case 32: return stem_launch<32>(x, weight, bias, bn_mean, bn_var, bn_weight, bn_bias, eps, y, B, H, W, st);
-        case 48: return stem_launch<48>(x, weight, bias, bn_mean, bn_var, bn_weight, bn_bias, eps, y, B, H, W, st);
-        case 64: return stem_launch<64>(x, weight, bias, bn_mean, bn_var, bn_weight, bn_bias, eps, y, B, H, W, st);
+        case 16: return stem_launch<16>(x, weight, bias, bn_mean, bn_var, bn_weight, bn_bias, eps, y, B, H, W, nhwc, st);
+        case 24: return stem_launch<24>(x, weight, bias, bn_mean, bn_var, bn_weight, bn_bias, eps, y, B, H, W, nhwc, st);
+        case 32: return stem_launch<32>(x, weight, bias, bn_mean, bn_var, bn_weight, bn_bias, eps, y, B, H, W, nhwc, st);
+        case 48: return stem_launch<48>(x, weight, bias, bn_mean, bn_var, bn_weight, bn_bias, eps, y, B, H, W, nhwc, st);
+        case 64: return stem_launch<64>(x, weight, bias, bn_mean, bn_var, bn_weight, bn_bias, eps, y, B, H, W, nhwc, st);
     }
     return set_error(CLUSTEN_EUNSUPPORTED, "stem: OC=%d (16, 24, 32, 48, 64 supported)", OC);
+}
+
+extern "C" int clusten_stem_im2col(const float *mid, float *A, int B, int H, int W, int C, int Kp, void *stream) {
+    if (B < 0 || H <= 0 || W <= 0 || C <= 0 || Kp < 9 * C) return set_error(CLUSTEN_EINVAL, "im2col: bad sizes B=%d H=%d W=%d C=%d Kp=%d", B, H, W, C, Kp);
+    if (!mid || !A) return set_error(CLUSTEN_EINVAL, "null pointer");
+    if (C % 4 || Kp % 4 || !aligned16(mid) || !aligned16(A)) return set_error(CLUSTEN_EUNSUPPORTED, "im2col: C and Kp must be multiples of 4, 16-byte aligned buffers");
+    if (B == 0) return 0;
+    const int OH = (H + 1) / 2, OW = (W + 1) / 2;
+    const int64_t total = (int64_t)B * OH * OW * (Kp / 4);
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 64);
+    stem_im2col_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(mid), reinterpret_cast<float4 *>(A), B, H, W, C / 4, OH, OW, Kp / 4);
+    note_launches(1);
+    return check_launch("stem_im2col");
 }

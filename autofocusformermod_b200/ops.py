@@ -1290,20 +1290,79 @@ def stem_conv_bn_gelu_supported(x, conv, bn):
                 and not (torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad or (bn.weight is not None and bn.weight.requires_grad))))
 
 
-def stem_conv_bn_gelu(x, conv, bn):
+def stem_conv_bn_gelu(x, conv, bn, channels_last=False):
     """``gelu(bn(conv(x)))`` for the first stem convolution (PatchEmbed.forward, backbone/aff.py:549) in fp32 inference:
     clusten_stem_conv_bn_gelu, one pass over the [B, OC, H/2, W/2] map instead of cuDNN conv + ATen bias add + cuDNN BatchNorm + ATen
-    GELU.  Caller checks ``stem_conv_bn_gelu_supported`` first.  No autograd."""
+    GELU.  ``channels_last``: the result is pixel-major [B, H/2, W/2, OC] (what ``stem_im2col`` reads).  Caller checks
+    ``stem_conv_bn_gelu_supported`` first.  No autograd."""
     dev = _lib.require_cuda(x, conv.weight, conv.bias, bn.running_mean, bn.running_var, bn.weight, bn.bias)
     x = x.contiguous()
     B, IC, H, W = x.shape
     OC = conv.out_channels
-    y = torch.empty((B, OC, (H + 1) // 2, (W + 1) // 2), dtype=torch.float32, device=dev)
+    OH, OW = (H + 1) // 2, (W + 1) // 2
+    y = torch.empty((B, OH, OW, OC) if channels_last else (B, OC, OH, OW), dtype=torch.float32, device=dev)
     if y.numel():
         w = conv.weight.detach().contiguous()
         f = lambda t: None if t is None else t.detach().float().contiguous()  # noqa: E731
         cb, m, v, g, b = f(conv.bias), f(bn.running_mean), f(bn.running_var), f(bn.weight), f(bn.bias)
         with torch.cuda.device(dev):
             _call("clusten_stem_conv_bn_gelu", dev, x.data_ptr(), w.data_ptr(), _lib.ptr(cb), m.data_ptr(), v.data_ptr(), _lib.ptr(g),
-                  _lib.ptr(b), float(bn.eps), y.data_ptr(), B, IC, H, W, OC, nbytes=4 * (x.numel() + y.numel()))
+                  _lib.ptr(b), float(bn.eps), y.data_ptr(), B, IC, H, W, OC, int(bool(channels_last)), nbytes=4 * (x.numel() + y.numel()))
     return y
+
+
+def stem_im2col(mid, Kp):
+    """Rows of a 3x3 / stride 2 / padding 1 convolution over the pixel-major map ``mid`` [B, H, W, C] (clusten_stem_im2col):
+    A [B * OH * OW, Kp] with A[(b, py, px), (ky * 3 + kx) * C + c] = mid[b, 2 py - 1 + ky, 2 px - 1 + kx, c], zero outside the map and in
+    the padding columns 9 C .. Kp - 1."""
+    dev = _lib.require_cuda(mid)
+    B, H, W, C = mid.shape
+    OH, OW = (H + 1) // 2, (W + 1) // 2
+    A = torch.empty((B * OH * OW, Kp), dtype=torch.float32, device=dev)
+    if A.numel():
+        with torch.cuda.device(dev):
+            _call("clusten_stem_im2col", dev, mid.data_ptr(), A.data_ptr(), B, H, W, C, Kp, nbytes=4 * (mid.numel() + A.numel()))
+    return A
+
+
+_stem_w_cache = {}
+
+
+def stem_proj2_weight(conv):
+    """The second stem convolution's weight [E, C, 3, 3] as the GEMM operand of ``stem_im2col`` rows: [E, Kp] with column
+    (ky * 3 + kx) * C + c, zero-padded to the 32-wide K chunk of the tcgen05 Linear; cached until the weight changes."""
+    import weakref
+    w = conv.weight
+    hit = _stem_w_cache.get(id(w))
+    if hit is not None and hit[0]() is w and hit[1] == w._version and hit[2] == w.data_ptr():
+        return hit[3]
+    E, C = w.shape[0], w.shape[1]
+    Kp = (9 * C + 31) // 32 * 32
+    w2 = torch.zeros((E, Kp), dtype=torch.float32, device=w.device)
+    w2[:, :9 * C] = w.detach().permute(0, 2, 3, 1).reshape(E, 9 * C)
+    if len(_stem_w_cache) > 256:
+        _stem_w_cache.clear()
+    _stem_w_cache[id(w)] = (weakref.ref(w), w._version, w.data_ptr(), w2)
+    return w2
+
+
+def stem_gemm_supported(x, conv1, bn, conv2):
+    """The whole fp32 inference stem on our kernels: conv1 + BatchNorm + GELU (pixel-major), im2col, conv2 as a tcgen05 GEMM."""
+    return bool(stem_conv_bn_gelu_supported(x, conv1, bn) and conv2.in_channels == conv1.out_channels and conv2.kernel_size == (3, 3)
+                and conv2.stride == (2, 2) and conv2.padding == (1, 1) and conv2.dilation == (1, 1) and conv2.groups == 1
+                and conv2.padding_mode == "zeros" and conv2.weight.dtype == torch.float32 and conv2.out_channels % 4 == 0
+                and not (torch.is_grad_enabled() and conv2.weight.requires_grad))
+
+
+def stem_tokens(x, conv1, bn, conv2):
+    """``proj2(act1(bn(proj1(x)))).flatten(2).transpose(1, 2)`` (PatchEmbed.forward, backbone/aff.py:549-553) -> (tokens [B, h * w, E],
+    h, w): conv1 + BatchNorm + GELU in one pass (pixel-major), the rows of the second convolution gathered once (``stem_im2col``),
+    and that convolution as ONE GEMM on the tcgen05 Linear kernel (TF32 form of the split: its input is not range-bounded) whose
+    output rows are the tokens -- no bias pass, no NCHW -> token-major copy.  Caller checks ``stem_gemm_supported``."""
+    mid = stem_conv_bn_gelu(x, conv1, bn, channels_last=True)
+    B, H2, W2, _ = mid.shape
+    w2 = stem_proj2_weight(conv2)
+    A = stem_im2col(mid, w2.shape[1])
+    h, w = (H2 + 1) // 2, (W2 + 1) // 2
+    y = linear_tc(A, w2, conv2.bias, "bias", split="tf32")
+    return y.view(B, h * w, conv2.out_channels), h, w

@@ -357,14 +357,20 @@ int clusten_mask_select(const float *mask, int B, int n, int count, int64_t *idx
 int clusten_gather_rows(const void *src, const int64_t *idx, void *out, int B, int n_src, int n_out, int row_bytes,
                         int *bad, void *stream);
 
-/* ---- first half of the stem, fp32 inference: y = GELU(BatchNorm_eval(Conv2d(3 -> OC, 3x3, stride 2, padding 1)(x))) --
- * `self.act1(self.bn(self.proj1(x)))` of PatchEmbed.forward (backbone/aff.py:527-529,549) in one pass instead of four.
- * x [B,IC,H,W], weight [OC,IC,3,3], bias [OC] or NULL, bn_mean / bn_var [OC] (running statistics), bn_weight / bn_bias [OC] or
- * NULL, y [B,OC,(H+1)/2,(W+1)/2]; NCHW, contiguous, fp32.  IC = 3 and OC in {16, 24, 32, 48, 64}; anything else returns
- * CLUSTEN_EUNSUPPORTED (the caller keeps the four-pass formulation). */
+/* ---- the stem, fp32 inference (PatchEmbed.forward, backbone/aff.py:527-530,549):
+ * clusten_stem_conv_bn_gelu: y = GELU(BatchNorm_eval(Conv2d(3 -> OC, 3x3, stride 2, padding 1)(x))) -- `self.act1(self.bn(self.proj1(x)))`
+ *   in one pass instead of four.  x [B,IC,H,W] NCHW, weight [OC,IC,3,3], bias [OC] or NULL, bn_mean / bn_var [OC] (running
+ *   statistics), bn_weight / bn_bias [OC] or NULL; y [B,OC,(H+1)/2,(W+1)/2] NCHW, or pixel-major [B,(H+1)/2,(W+1)/2,OC] with
+ *   channels_last = 1; contiguous fp32.  IC = 3 and OC in {16, 24, 32, 48, 64}; anything else returns CLUSTEN_EUNSUPPORTED (the
+ *   caller keeps the four-pass formulation).
+ * clusten_stem_im2col: the rows of the second convolution (3x3, stride 2, padding 1) over a pixel-major map mid [B,H,W,C]:
+ *   A[(b,py,px), (ky*3+kx)*C + c] = mid[b, 2py-1+ky, 2px-1+kx, c] (0 outside), columns 9C .. Kp-1 zero; A [B*OH*OW, Kp] with
+ *   OH = (H+1)/2, OW = (W+1)/2.  `self.proj2` then is clusten_linear_tc_f32 over A with the weight as [E, (ky,kx,c)] padded to Kp,
+ *   and its output rows are the tokens [B, OH*OW, E] of `x.flatten(2).transpose(1, 2)`.  C % 4 == 0, Kp % 4 == 0, Kp >= 9C. */
 int clusten_stem_conv_bn_gelu(const float *x, const float *weight, const float *bias, const float *bn_mean, const float *bn_var,
                               const float *bn_weight, const float *bn_bias, float eps, float *y, int B, int IC, int H, int W,
-                              int OC, void *stream);
+                              int OC, int channels_last, void *stream);
+int clusten_stem_im2col(const float *mid, float *A, int B, int H, int W, int C, int Kp, void *stream);
 
 #ifdef __cplusplus
 }

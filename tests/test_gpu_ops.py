@@ -1018,3 +1018,38 @@ def test_stem_conv_bn_gelu_matches_torch(oc, B, H, W):
     bn.train()
     assert not ops.stem_conv_bn_gelu_supported(x, conv.float(), bn.float())
     assert not ops.stem_conv_bn_gelu_supported(x.half(), conv, bn.eval())
+
+
+@pytest.mark.parametrize("E", [32, 64, 96, 128])
+@pytest.mark.parametrize("B,H,W", [(2, 64, 96), (1, 50, 37), (2, 128, 128)])
+def test_stem_as_gemm_matches_torch(E, B, H, W, monkeypatch):
+    """PatchEmbed.forward (aff.py:537-565) with conv1 + BatchNorm + GELU in one pass, the second convolution as im2col + tcgen05 GEMM
+    (ops.stem_tokens) and the patch norm, against the same module on cuDNN / ATen evaluated in float64: tokens <= 1e-5, positions equal;
+    the im2col rows against F.unfold (bit-exact); odd sizes (padded to a multiple of 4 first) included."""
+    import torch.nn.functional as F
+    from autofocusformermod_b200 import aff, ops
+    torch.manual_seed(E + H)
+    pe = aff.PatchEmbed(in_chans=3, embed_dim=E, norm_layer=aff.LayerNorm).cuda().eval()
+    with torch.no_grad():
+        pe.bn.running_mean.normal_(0, 0.5)
+        pe.bn.running_var.uniform_(0.3, 2.0)
+        pe.bn.weight.uniform_(0.5, 1.5)
+        pe.bn.bias.normal_(0, 0.3)
+        x = torch.randn(B, 3, H, W, device="cuda") * 1.3
+        before = ops.launch_count()
+        pos, tok, h, w = pe(x)
+        assert ops.launch_count() >= before + 3, "the stem did not take the native path"
+        monkeypatch.setattr(aff, "STEM_GEMM", False)
+        monkeypatch.setattr(aff, "FUSED_STEM", False)
+        pos_t, tok_t, h_t, w_t = pe(x)                                   # cuDNN / ATen, fp32
+        pe64 = aff.PatchEmbed(in_chans=3, embed_dim=E, norm_layer=torch.nn.LayerNorm).cuda().double().eval()
+        pe64.load_state_dict({k: v.double() for k, v in pe.state_dict().items()})
+        _, tok64, _, _ = pe64(x.double())
+    assert (h, w) == (h_t, w_t) and torch.equal(pos, pos_t) and tok.shape == tok_t.shape == tok64.shape
+    assert rel_err(tok, tok64) <= 1e-5 and rel_err(tok_t, tok64) <= 1e-5
+    # the im2col rows alone
+    mid = torch.randn(B, 24, 30, 16, device="cuda")                      # pixel-major [B, H, W, C]
+    A = ops.stem_im2col(mid, 160)
+    ref = F.unfold(mid.permute(0, 3, 1, 2), kernel_size=3, stride=2, padding=1)          # [B, C * 9, L], row index c * 9 + tap
+    ref = ref.view(B, 16, 9, -1).permute(0, 3, 2, 1).reshape(-1, 144)                  # [(b, py, px), tap * C + c]
+    assert torch.equal(A[:, :144], ref) and bool((A[:, 144:] == 0).all())
