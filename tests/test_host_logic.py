@@ -105,3 +105,48 @@ def test_kernel_dispatch_predicates_reject_what_the_kernels_do_not_take():
     assert not ops.table_linear_supported(torch.zeros(4, 9), torch.zeros(3, 9), None)
     res = torch.zeros(2, 5, 30)
     assert not ops.scale_residual_supported(res, res, None, torch.ones(2))
+
+
+def test_layer_norm_fold_is_the_same_layer():
+    """ops.ln_folded_layer: LayerNorm(gamma, beta) followed by Linear(W, b) equals plain normalisation followed by Linear(W * gamma,
+    b + W beta) -- the identity behind CLUSTEN_LN_FOLD (the tcgen05 Linear's split warps then only compute (x - mean) * rstd).
+    Evaluated in float64 on host tensors; the folded operands are cached until a parameter changes."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(1)
+    K, N = 96, 40
+    x = torch.randn(50, K, generator=g, dtype=torch.float64) * 2.0 + 0.7
+    w = torch.randn(N, K, generator=g) * K ** -0.5
+    b = torch.randn(N, generator=g)
+    lw, lb = torch.rand(K, generator=g) + 0.5, torch.randn(K, generator=g)
+    want = F.linear(F.layer_norm(x, (K,), lw.double(), lb.double(), 1e-5), w.double(), b.double())
+    wf, bf = ops.ln_folded_layer(w, b, lw, lb)
+    norm = (x - x.mean(1, keepdim=True)) * (x.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+    got = F.linear(norm, wf.double(), bf.double())
+    assert wf.dtype == torch.float32 and bf.dtype == torch.float32
+    assert float((got - want).abs().max() / want.abs().max()) <= 5e-7                # fp32 rounding of W' and b' only
+    assert ops.ln_folded_layer(w, b, lw, lb)[0] is wf                                # cached
+    lb.add_(1.0)
+    wf2, bf2 = ops.ln_folded_layer(w, b, lw, lb)                                     # beta changed: b' follows, W' is rebuilt equal
+    assert wf2 is not wf and torch.equal(wf2, wf) and not torch.equal(bf2, bf)
+    wn, bn_ = ops.ln_folded_layer(w, None, lw, lb)                                   # a layer without bias still gets b' = W beta
+    assert float((bn_.double() - w.double() @ lb.double()).abs().max()) <= 1e-6
+
+
+def test_stem_gemm_operands_are_the_second_convolution():
+    """ops.stem_proj2_weight: the [E, C, 3, 3] convolution weight as [E, (ky, kx, c)] zero-padded to a multiple of 32 columns.  With
+    the im2col rows A[(b, py, px), (ky * 3 + kx) * C + c] = mid[b, 2 py - 1 + ky, 2 px - 1 + kx, c] (what clusten_stem_im2col writes;
+    built here with F.unfold) the GEMM A W'^T + bias IS conv2d(stride 2, padding 1) in token-major order (aff.py:549-552)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(2)
+    B, C, E, H, W = 2, 16, 32, 10, 14
+    conv = nn.Conv2d(C, E, 3, stride=2, padding=1).double()
+    mid = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    want = conv(mid).flatten(2).transpose(1, 2)                                      # [B, h * w, E]
+    conv32 = nn.Conv2d(C, E, 3, stride=2, padding=1)
+    conv32.load_state_dict({k: v.float() for k, v in conv.state_dict().items()})
+    w2 = ops.stem_proj2_weight(conv32)
+    assert w2.shape == (E, 160) and bool((w2[:, 144:] == 0).all()) and ops.stem_proj2_weight(conv32) is w2
+    cols = F.unfold(mid, kernel_size=3, stride=2, padding=1)                         # [B, C * 9, L], row c * 9 + tap
+    A = cols.view(B, C, 9, -1).permute(0, 3, 2, 1).reshape(B, -1, 9 * C)             # [B, L, tap * C + c]
+    got = A @ w2[:, :144].double().t() + conv32.bias.double()
+    assert got.shape == want.shape and float((got - want).abs().max()) <= 1e-6
