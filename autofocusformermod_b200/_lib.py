@@ -65,6 +65,7 @@ SIGNATURES = {
     "clusten_topk_workspace_bytes": (_Z, [_I, _I]),
     "clusten_topk_select": (_I, [_P, _I, _I, _I, _P, _L, _P, _Z, _P]),
     "clusten_mask_select": (_I, [_P, _I, _I, _I, _P, _L, _P]),
+    "clusten_merge_scores": (_I, [_P, _P, _I, _P, _c.c_float, _I, _I, _P, _P, _I, _I, _P]),
     "clusten_gather_rows": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "clusten_stem_conv_bn_gelu": (_I, [_P] * 7 + [_c.c_float, _P] + [_I] * 6 + [_P]),
     "clusten_stem_im2col": (_I, [_P, _P] + [_I] * 5 + [_P]),

@@ -28,7 +28,7 @@ from .ops import (CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction, clust
                   cluster_attention_core_pos, cluster_attention_fused_pos, layer_norm, layer_norm_stats, linear, linear_f32, linear_f32_supported, linear_tc, linear_tc_supported,
                   gather_rows, scale_residual, stem_conv_bn_gelu, stem_conv_bn_gelu_supported, stem_gemm_supported, stem_tokens, table_linear,
                   table_linear_supported, table_lookup)
-from .point_utils import knn_keops, merge_select, space_filling_cluster, stage_prepare
+from .point_utils import knn_keops, merge_scores, merge_select, space_filling_cluster, stage_prepare
 
 # aff.py:17-19: the relative-position table covers inputs up to 2048 px (stem grid 512)
 REL_POS_WIDTH = 2048 // 4 - 1
@@ -83,6 +83,9 @@ def _tcgen05_ok(x):
 # row reorders / selections (`x.gather(index=idx.expand(...), dim=1)`, aff.py:332,335,340,471) by clusten_gather_rows when no gradient
 # flows through them.  CLUSTEN_GATHER_ROWS=0: torch.gather
 NATIVE_GATHER_ROWS = _on("CLUSTEN_GATHER_ROWS")
+# the scores of the adaptive downsampling (grid / learned / reserve terms, aff.py:292-315) in one kernel (clusten_merge_scores) instead of
+# ~22 element-wise launches per merge.  CLUSTEN_MERGE_SCORES=0: the op-by-op torch formulation (same bits)
+NATIVE_MERGE_SCORES = _on("CLUSTEN_MERGE_SCORES")
 # fp32 inference stem: conv1 + BatchNorm + GELU in one pass (clusten_stem_conv_bn_gelu).  CLUSTEN_FUSED_STEM=0: cuDNN / ATen, four passes
 FUSED_STEM = _on("CLUSTEN_FUSED_STEM")
 # ... and its second convolution as an im2col + tcgen05 GEMM whose output rows are the tokens (ops.stem_tokens).  CLUSTEN_STEM_GEMM=0: cuDNN
@@ -481,6 +484,14 @@ class ClusterMerging(nn.Module):
         """Indices [b, keep, 1] of the tokens that survive (aff.py:292-329)."""
         b, n, _ = pos.shape
         keep_num = int(n * self.ds_rate)
+        if NATIVE_MERGE_SCORES and pos.is_cuda and pos.dtype == torch.float32 and pos.shape[2] == 2:
+            min_dist = None
+            if stride != 2:
+                _, min_dist = knn_keops(pos, pos, 2, return_dist=True)                               # aff.py:299
+            final_prob, reserve_mask = merge_scores(pos, min_dist, learned_prob, stride, self.alpha, self.reserve_on)
+            if self.reserve_on:
+                return merge_select(final_prob, reserve_mask, keep_num, reserve_num)
+            return merge_select(final_prob, final_prob, keep_num, 0)
         pos_long = pos.long()
         if stride == 2:
             grid_prob = ((pos_long % stride) == 0).all(-1).float()                                   # aff.py:297

@@ -64,6 +64,40 @@ mask_select_kernel(const float *__restrict__ mask, int n, int count, int64_t *__
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+
+// Scores of the adaptive downsampling, ClusterMerging.forward (aff.py:292-315), in ONE pass over the tokens:
+//   grid_prob    = all(pos.long() % s == 0),  s = stride (stride == 2) or the token's own 2 ** (ceil(log2(d_nearest)) + 1)   :297-302
+//   final_prob   = grid_prob + learned_prob * alpha                                                                  :307-310
+//   reserve_mask = all(pos.long() % (2 stride) == 0);  final_prob += reserve_mask * (-100)                            :313-315
+// The reference spends ~22 element-wise / reduction launches of 1-3 us per merge on it (55 of the ~300 launches of an AFF-Mini
+// forward).  Every fp32 operation is rounded separately, in the reference's order (no FMA contraction): the scores feed a top-k.
+__global__ void __launch_bounds__(256)
+merge_scores_kernel(const float2 *__restrict__ pos, const float *__restrict__ min_dist, int dist_stride, const float *__restrict__ lp,
+                    float alpha, int stride, int reserve_on, float *__restrict__ final_prob, float *__restrict__ reserve_mask, int64_t total) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const float2 p = pos[e];
+    const long long px = (long long)p.x, py = (long long)p.y;           // .long(): towards zero
+    long long s = stride;
+    if (min_dist) {
+        const float k = __fadd_rn(ceilf(log2f(min_dist[e * dist_stride + 1])), 1.f);
+        const float a = k < -149.f ? 0.f : k > 127.f ? INFINITY : ldexpf(1.f, (int)k);       // 2 ** k, exact
+        s = (long long)a;
+    }
+    // (positions are non-negative, so the remainder of ATen -- sign of the divisor -- is the C one; s = 0 cannot occur for distinct
+    // integer positions, whose nearest distance is >= 1: it is scored as "not on the grid" instead of dividing by zero)
+    const float grid = (s != 0 && px % s == 0 && py % s == 0) ? 1.f : 0.f;
+    float f = grid;
+    if (lp) f = __fadd_rn(f, __fmul_rn(lp[e], alpha));
+    if (reserve_on) {
+        const long long s2 = 2LL * stride;
+        const float r = (px % s2 == 0 && py % s2 == 0) ? 1.f : 0.f;
+        f = __fadd_rn(f, __fmul_rn(r, -100.f));
+        reserve_mask[e] = r;
+    }
+    final_prob[e] = f;
+}
+
 }  // namespace clusten
 
 using namespace clusten;
@@ -104,4 +138,17 @@ extern "C" int clusten_mask_select(const float *mask, int B, int n, int count, i
     mask_select_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(mask, n, count, idx_out, out_stride);
     note_launches(1);
     return check_launch("mask_select");
+}
+
+extern "C" int clusten_merge_scores(const float *pos, const float *min_dist, int dist_stride, const float *learned_prob, float alpha,
+                                    int stride, int reserve_on, float *final_prob, float *reserve_mask, int B, int n, void *stream) {
+    if (B < 0 || n < 0 || stride <= 0 || (min_dist && dist_stride < 2)) return set_error(CLUSTEN_EINVAL, "merge_scores: bad sizes B=%d n=%d stride=%d", B, n, stride);
+    if (!pos || !final_prob || (reserve_on && !reserve_mask)) return set_error(CLUSTEN_EINVAL, "null pointer");
+    if (reinterpret_cast<uintptr_t>(pos) & 7u) return set_error(CLUSTEN_EUNSUPPORTED, "positions must be 8-byte aligned");
+    const int64_t total = (int64_t)B * n;
+    if (total == 0) return 0;
+    merge_scores_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2 *>(pos), min_dist, dist_stride, learned_prob, alpha, stride, reserve_on, final_prob, reserve_mask, total);
+    note_launches(1);
+    return check_launch("merge_scores");
 }

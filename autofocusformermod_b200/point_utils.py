@@ -165,6 +165,24 @@ def mask_select(mask, count, out=None):
     return out
 
 
+def merge_scores(pos, min_dist, learned_prob, stride, alpha, reserve_on=True):
+    """(final_prob [B,n], reserve_mask [B,n] or None) of ClusterMerging.forward (aff.py:292-315) in one kernel (clusten_merge_scores)
+    instead of ~22 element-wise launches: pos fp32 [B,n,2], min_dist fp32 [B,n,>=2] (the kNN-2 distances of aff.py:299) or None for
+    stride 2, learned_prob [B,n,1] / [B,n] or None.  Bit-identical to the op-by-op formulation (each fp32 operation rounded alone)."""
+    dev = _lib.require_cuda(pos, min_dist, learned_prob)
+    B, n = pos.shape[0], pos.shape[1]
+    p = _f32c(pos)
+    md = None if min_dist is None else _f32c(min_dist)
+    lp = None if learned_prob is None else _f32c(learned_prob.detach().reshape(B, n))
+    final_prob = torch.empty((B, n), dtype=torch.float32, device=dev)
+    reserve = torch.empty((B, n), dtype=torch.float32, device=dev) if reserve_on else None
+    if B * n:
+        with torch.cuda.device(dev):
+            _call("clusten_merge_scores", dev, p.data_ptr(), _lib.ptr(md), 0 if md is None else md.shape[-1], _lib.ptr(lp), float(alpha),
+                  int(stride), int(bool(reserve_on)), final_prob.data_ptr(), _lib.ptr(reserve), B, n)
+    return final_prob, reserve
+
+
 def merge_select(final_prob, reserve_mask, keep_num, reserve_num):
     """idx [B, keep_num, 1] = cat(canonical top-(keep-reserve) of final_prob, reserve tokens ascending) (aff.py:320-324)."""
     B = final_prob.shape[0]

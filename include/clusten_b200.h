@@ -348,6 +348,12 @@ size_t clusten_topk_workspace_bytes(int B, int n);
 int clusten_topk_select(const float *score, int B, int n, int k, int64_t *idx_out, int64_t out_stride,
                         void *workspace, size_t workspace_bytes, void *stream);
 int clusten_mask_select(const float *mask, int B, int n, int count, int64_t *idx_out, int64_t out_stride, void *stream);
+/* merge_scores: the scores those two select from (aff.py:292-315) in one pass: grid_prob = all(pos.long() % s == 0) with s = stride, or
+ * per token 2 ** (ceil(log2(min_dist[.., 1])) + 1) when min_dist (fp32 [B,n,dist_stride], the kNN-2 distances of aff.py:299) is given;
+ * final_prob = grid_prob + learned_prob * alpha (learned_prob fp32 [B,n] or NULL) [+ reserve_mask * (-100)];
+ * reserve_mask = all(pos.long() % (2 stride) == 0) (written when reserve_on).  fp32, every operation rounded separately. */
+int clusten_merge_scores(const float *pos /* [B,n,2] */, const float *min_dist, int dist_stride, const float *learned_prob, float alpha,
+                         int stride, int reserve_on, float *final_prob, float *reserve_mask, int B, int n, void *stream);
 
 /* ---- row gather: out[b,i,:] = src[b, idx[b,i], :] for i < n_out -- the `x.gather(index=idx.expand(-1,-1,c), dim=1)` row
  * reorders / selections of backbone/aff.py:332,335,340,471 (features into cluster order, kept tokens' positions, member rows and

@@ -164,3 +164,36 @@ def test_inverse_neighbour_list_is_exact():
         order = torch.sort(flat, stable=True)[1]
         assert torch.equal(off[b], torch.searchsorted(flat[order], torch.arange(Nk + 1)))
         assert torch.equal(ent[b], ((order // M) << 8) | (order % M))
+
+
+@pytest.mark.parametrize("stride", [2, 4, 8])
+@pytest.mark.parametrize("with_lp,reserve_on", [(True, True), (False, True), (True, False)])
+@pytest.mark.parametrize("B,n,hw", [(2, 4096, 128), (3, 1000, 64), (1, 37, 16)])
+def test_merge_scores_bit_exact(stride, with_lp, reserve_on, B, n, hw):
+    """clusten_merge_scores against the op-by-op formulation of ClusterMerging.forward (aff.py:292-315) on the same device: final_prob
+    and reserve_mask bit for bit (they feed a top-k), for the fixed stride of the first merge and the per-token adaptive stride
+    2 ** (ceil(log2(d_nearest)) + 1) of the later ones, with / without learned probabilities and reserve tokens."""
+    from autofocusformermod_b200 import point_utils as pu
+    g = torch.Generator().manual_seed(100 * stride + n)
+    cells = torch.stack([torch.randperm(hw * hw, generator=g)[:n] for _ in range(B)])
+    pos = torch.stack([cells % hw, cells // hw], dim=-1).float().cuda()           # distinct integer positions
+    lp = torch.rand(B, n, 1, generator=g).cuda() if with_lp else None
+    alpha = 4.0
+    pos_long = pos.long()
+    min_dist = None
+    if stride == 2:
+        grid = ((pos_long % stride) == 0).all(-1).float()
+    else:
+        _, min_dist = pu.knn_keops(pos, pos, 2, return_dist=True)
+        ada = 2 ** (min_dist[:, :, 1].log2().ceil() + 1)
+        grid = ((pos_long % ada.unsqueeze(2).long()) == 0).all(-1).float()
+    want = grid
+    if lp is not None:
+        want = want + lp.view(B, n).float() * alpha
+    want_r = None
+    if reserve_on:
+        want_r = ((pos_long % (stride * 2)) == 0).all(dim=-1).float()
+        want = want + want_r * (-100)
+    got, got_r = pu.merge_scores(pos, min_dist, lp, stride, alpha, reserve_on)
+    assert torch.equal(got, want)
+    assert (got_r is None and want_r is None) or torch.equal(got_r, want_r)
