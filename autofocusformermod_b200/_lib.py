@@ -49,6 +49,7 @@ SIGNATURES = {
     "clusten_prepare_workspace_bytes": (_Z, []),
     "clusten_stage_prepare": (_I, [_P] * 4 + [_I] * 5 + [_P] * 6 + [_I, _P, _P, _Z, _P]),
     "clusten_table_rank": (_I, [_P, _L, _P, _P, _I, _P, _P, _Z, _P]),
+    "clusten_rel_pos_features": (_I, [_P, _P, _L, _P]),
     "clusten_table_gather": (_I, [_P, _P, _I, _P, _L, _I, _I, _I, _P]),
     "clusten_table_grad": (_I, [_P, _P, _I, _P, _L, _I, _P, _I, _L, _L, _L, _L, _I, _P]),
     "clusten_wf_plan_bytes": (_Z, [_I] * 4),

@@ -26,7 +26,7 @@ import torch.nn.functional as F
 
 from .ops import (CLUSTENAVFunction, CLUSTENQKFunction, CLUSTENWFFunction, cluster_attention_core, cluster_attention_fused,
                   cluster_attention_core_pos, cluster_attention_fused_pos, layer_norm, layer_norm_stats, linear, linear_f32, linear_f32_supported, linear_tc, linear_tc_supported,
-                  gather_rows, scale_residual, stem_conv_bn_gelu, stem_conv_bn_gelu_supported, stem_gemm_supported, stem_tokens, table_linear,
+                  gather_rows, rel_pos_feature_rows, scale_residual, stem_conv_bn_gelu, stem_conv_bn_gelu_supported, stem_gemm_supported, stem_tokens, table_linear,
                   table_linear_supported, table_lookup)
 from .point_utils import knn_keops, merge_scores, merge_select, space_filling_cluster, stage_prepare
 
@@ -104,9 +104,15 @@ def _gather(x, idx):
 MERGE_WF_AUTOCAST = _opt_in("CLUSTEN_MERGE_WF_AUTOCAST")
 
 
+# rows of pre_table by clusten_rel_pos_features.  CLUSTEN_REL_POS_FEATURES=0: the torch formulation below (same bits)
+NATIVE_REL_POS_FEATURES = _on("CLUSTEN_REL_POS_FEATURES")
+
+
 def rel_pos_features(pe_idx):
     """Rows of the reference's ``pre_table`` (aff.py:21-31) for the given table indices, computed on the fly:
     (dx, dy, dist, dy/dist, dx/dist) with the 0/0 centre zeroed.  pe_idx int64 [...] -> fp32 [..., 5]."""
+    if NATIVE_REL_POS_FEATURES and pe_idx.is_cuda and pe_idx.dtype == torch.int64:
+        return rel_pos_feature_rows(pe_idx)               # one kernel, the same IEEE operations (12 launches per stage otherwise)
     ys = (pe_idx // TABLE_WIDTH - REL_POS_WIDTH).to(torch.float32)
     xs = (pe_idx % TABLE_WIDTH - REL_POS_WIDTH).to(torch.float32)
     dis = (ys ** 2 + xs ** 2) ** 0.5
@@ -144,7 +150,7 @@ class _TableLookup:
         """Keep only the given token rows (dim 1) of the lookup: used by ClusterMerging after top-k."""
         out = _TableLookup.__new__(_TableLookup)
         inv = self.inverse.view(self.shape)
-        inv = inv.gather(1, rows.expand(-1, -1, self.shape[2]))
+        inv = _gather(inv, rows)
         out.shape, out.features, out.inverse, out.count = inv.shape, self.features, inv.reshape(-1), self.count
         return out
 

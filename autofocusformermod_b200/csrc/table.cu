@@ -250,6 +250,26 @@ static int launch_table_grad(const T *dout, const I *inv, float *dtab, int64_t n
     return check_launch("table_grad");
 }
 
+// Rows of the reference's pre_table (aff.py:21-31) for the given table indices: (dx, dy, dist, dy / dist, dx / dist) with the 0 / 0 centre
+// zeroed, dx = idx % 1023 - 511, dy = idx / 1023 - 511.  The torch formulation (floor-divide, remainder, two casts, two squares, add,
+// sqrt, two divisions, stack, isfinite, zeros_like, where) is ~12 launches per stage for a few thousand rows; every fp32 operation
+// here is the same IEEE operation, rounded separately.
+__global__ void __launch_bounds__(256)
+rel_pos_features_kernel(const int64_t *__restrict__ rows, float *__restrict__ out, int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int64_t r = rows[e];
+    int64_t qy = r / 1023, rx = r - qy * 1023;
+    if (rx < 0) { rx += 1023; --qy; }                                  // floor-divide / remainder of ATen (indices are >= 0 on this path)
+    const float ys = (float)(qy - 511), xs = (float)(rx - 511);
+    const float dis = __fsqrt_rn(__fadd_rn(__fmul_rn(ys, ys), __fmul_rn(xs, xs)));
+    float a = __fdiv_rn(ys, dis), b = __fdiv_rn(xs, dis);
+    if (!isfinite(a)) a = 0.f;
+    if (!isfinite(b)) b = 0.f;
+    float *o = out + e * 5;
+    o[0] = xs; o[1] = ys; o[2] = dis; o[3] = a; o[4] = b;
+}
+
 }  // namespace clusten
 
 using namespace clusten;
@@ -280,4 +300,12 @@ extern "C" int clusten_table_grad(const void *d_out, const void *inv, int inv_is
         return launch_table_grad<T, int32_t>((const T *)d_out, (const int32_t *)inv, d_tab, n, U, U_dev, CH, n_per, d_sb, d_se, d_sc, st);
     });
     return 0;
+}
+
+extern "C" int clusten_rel_pos_features(const int64_t *rows, float *out, int64_t n, void *stream) {
+    if (n < 0 || (n > 0 && (!rows || !out))) return set_error(CLUSTEN_EINVAL, "rel_pos_features: bad arguments");
+    if (n == 0) return 0;
+    rel_pos_features_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, out, n);
+    note_launches(1);
+    return check_launch("rel_pos_features");
 }

@@ -1366,3 +1366,16 @@ def stem_tokens(x, conv1, bn, conv2):
     h, w = (H2 + 1) // 2, (W2 + 1) // 2
     y = linear_tc(A, w2, conv2.bias, "bias", split="tf32")
     return y.view(B, h * w, conv2.out_channels), h, w
+
+
+# ---- rows of the relative-position feature table -------------------------------------------------------------------------------
+def rel_pos_feature_rows(rows):
+    """(dx, dy, dist, dy / dist, dx / dist) of the table rows ``rows`` (int64, any shape) -> fp32 [..., 5]: the reference's
+    ``pre_table`` (backbone/aff.py:21-31) restricted to those rows, one kernel (clusten_rel_pos_features)."""
+    dev = _lib.require_cuda(rows)
+    r = rows.contiguous()
+    out = torch.empty((*r.shape, 5), dtype=torch.float32, device=dev)
+    if r.numel():
+        with torch.cuda.device(dev):
+            _call("clusten_rel_pos_features", dev, r.data_ptr(), out.data_ptr(), r.numel(), nbytes=28 * r.numel())
+    return out

@@ -190,6 +190,9 @@ int clusten_scatter_rows(const void *w, const void *x, const int32_t *csr_offset
  *   Replaces ATen index / index_put_(accumulate) on this path; the gradient uses fp32 atomics (summation order is not fixed). */
 int clusten_table_gather(const void *tab, const void *inv, int inv_is_i64, void *out, int64_t n, int U, int CH,
                          int dtype, void *stream);
+/* Rows of the reference's pre_table (aff.py:21-31) for table indices rows[0:n] (int64, row = (dy + 511) * 1023 + dx + 511):
+ * out[e,:] = (dx, dy, dist, dy / dist, dx / dist), the 0 / 0 centre zeroed; fp32 [n,5].  Same IEEE operations as the torch formulation. */
+int clusten_rel_pos_features(const int64_t *rows, float *out, int64_t n, void *stream);
 /* U_dev (device int32 scalar or NULL): number of table rows actually referenced when U is only an upper bound (the count
  * clusten_stage_prepare leaves on the device) -- lets the caller skip the device->host read of U. */
 int clusten_table_grad(const void *d_out, const void *inv, int inv_is_i64, float *d_tab, int64_t n, int U, const int32_t *U_dev,

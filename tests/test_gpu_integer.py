@@ -197,3 +197,21 @@ def test_merge_scores_bit_exact(stride, with_lp, reserve_on, B, n, hw):
     got, got_r = pu.merge_scores(pos, min_dist, lp, stride, alpha, reserve_on)
     assert torch.equal(got, want)
     assert (got_r is None and want_r is None) or torch.equal(got_r, want_r)
+
+
+def test_rel_pos_feature_rows_bit_exact(monkeypatch):
+    """clusten_rel_pos_features against the torch formulation of the reference's pre_table rows (aff.py:21-31: dx, dy, dist, dy / dist,
+    dx / dist with the centre zeroed), bit for bit -- incl. the centre row (0 / 0), the corner rows and a whole band of the table."""
+    from autofocusformermod_b200 import aff, ops
+    g = torch.Generator().manual_seed(7)
+    centre = 511 * 1023 + 511
+    rows = torch.cat([torch.tensor([0, centre, 1023 * 1023 - 1, 1022, centre + 1, centre - 1023]),
+                      torch.randint(0, 1023 * 1023, (5000,), generator=g), torch.arange(centre - 3000, centre + 3000)]).cuda()
+    before = ops.launch_count()
+    got = aff.rel_pos_features(rows)
+    assert ops.launch_count() == before + 1
+    monkeypatch.setattr(aff, "NATIVE_REL_POS_FEATURES", False)
+    want = aff.rel_pos_features(rows)
+    assert got.shape == want.shape == (rows.numel(), 5) and got.dtype == torch.float32
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+    assert torch.equal(aff.rel_pos_features(rows.view(2, -1)[:, :100].contiguous()), want.view(2, -1, 5)[:, :100])      # leading dims
