@@ -150,3 +150,27 @@ def test_stem_gemm_operands_are_the_second_convolution():
     A = cols.view(B, C, 9, -1).permute(0, 3, 2, 1).reshape(B, -1, 9 * C)             # [B, L, tap * C + c]
     got = A @ w2[:, :144].double().t() + conv32.bias.double()
     assert got.shape == want.shape and float((got - want).abs().max()) <= 1e-6
+
+
+def test_new_fast_paths_keep_torch_semantics_outside_their_operand_set():
+    """The row gather, the stem kernels and the merge-score / table-feature kernels only take CUDA operands without a gradient;
+    everything else goes through the torch formulation with the same values (evaluated on host tensors here)."""
+    g = torch.Generator().manual_seed(3)
+    src = torch.randn(2, 9, 5, generator=g)
+    idx = torch.randint(0, 9, (2, 4, 1), generator=g)
+    assert torch.equal(ops.gather_rows(src, idx), src.gather(1, idx.expand(-1, -1, 5)))          # host tensors: torch.gather
+    assert torch.equal(aff._gather(src, idx), src.gather(1, idx.expand(-1, -1, 5)))
+    leaf = src.clone().requires_grad_(True)
+    out = ops.gather_rows(leaf, idx)                                                             # a gradient flows: autograd's gather
+    out.sum().backward()
+    assert leaf.grad is not None and float(leaf.grad.sum()) == 2 * 4 * 5
+    conv1, bn, conv2 = nn.Conv2d(3, 16, 3, stride=2, padding=1), nn.BatchNorm2d(16).eval(), nn.Conv2d(16, 32, 3, stride=2, padding=1)
+    x = torch.randn(1, 3, 16, 16, generator=g)
+    with torch.no_grad():
+        assert not ops.stem_conv_bn_gelu_supported(x, conv1, bn)                                 # host tensor
+        assert not ops.stem_gemm_supported(x, conv1, bn, conv2)
+    rows = torch.tensor([0, 511 * 1023 + 511, 1023 * 1023 - 1, 511 * 1023 + 512])
+    f = aff.rel_pos_features(rows)                                                               # host tensor: the torch formulation
+    assert f.shape == (4, 5) and torch.equal(f[1], torch.zeros(5))                               # the 0 / 0 centre is zeroed
+    assert torch.equal(f[3], torch.tensor([1.0, 0.0, 1.0, 0.0, 1.0]))                            # dx = 1, dy = 0
+    assert torch.equal(f[0, :2], torch.tensor([-511.0, -511.0])) and torch.equal(f[2, :2], torch.tensor([511.0, 511.0]))
